@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the differentiable ball rollout (BASELINE.json metric: ball-steps/s, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A "step" is one pass of the hot path over one batch: forward rollout + L1 loss + backward
+rollout of the whole workload (default: BASELINE configs[1] = C2, 4,096 balls x 201 segments x
+500 simulation steps).  Prints ONE JSON line (rank 0).  See DESIGN.md §7 for every field.
+
+  value     ball-steps/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the public API (doper_b200.sim.ball_sim.vmapped_grad_and_value)
+            with HOST numpy inputs: pinned H2D + 3 launches + pinned D2H inside the timed region
+  roofline  dominant kernel (rollout_fwd_kernel): algorithmic FP32 flops / its event-timed duration
+            against the non-FMA FP32 issue rate measured in this run (doper_fp32_probe)
+  cpu_baseline / --impl reference   the oracle's C restatement of the reference (OpenMP, all host
+            cores) — the reference itself is JAX, which is not installable in this image
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "ball_steps_per_sec_fwd_bwd"
+UNIT = "ball-steps/s"
+
+
+def workload_label(name, B, S, n_steps, per_env):
+    scene = f"{S} segments per env ({B} private maps)" if per_env else f"one shared {S}-segment map"
+    return f"{name}: {B} balls x {n_steps} steps, {scene}, rollout fwd + L1 loss + bwd"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's C restatement on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(w, steps, warmup, min_seconds=0.0):
+    from oracle import ball_sim_np as onp
+    from oracle.cref import CRef
+
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        cr, flavour = CRef("native"), "native(-O3 -march=native)"
+    except Exception:  # no compiler on the box: the prebuilt portable build travels with the repo
+        cr, flavour = CRef("portable"), "portable(-O2)"
+    c = onp.make_constants(w["constants"])
+    n = w["n_steps"]
+    dt = np.float32(w["sim_time"] / n)
+    B = w["x0"].shape[0]
+
+    def one():
+        return cr.value_and_grad(n, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+
+    for _ in range(warmup):
+        one()
+    times = []
+    t_all = time.perf_counter()
+    k = 0
+    while k < steps or (time.perf_counter() - t_all) < min_seconds:
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+        k += 1
+    ms = 1e3 * float(np.mean(times))
+    return {"ms_per_step": ms, "value": B * n / (ms * 1e-3), "cores": cores, "steps": k,
+            "flavour": flavour, "balls": B}
+
+
+def bounded_sample(w, max_ball_steps_x_segs=4096 * 500 * 201):
+    """Cap the CPU work of one step at about one C2 (~0.4 s on 8 cores): first balls only."""
+    B, n, S = w["x0"].shape[0], w["n_steps"], w["segments"].shape[-3]
+    cap = max(64, int(max_ball_steps_x_segs // (n * S)))
+    if B <= cap:
+        return w, f"the full workload ({B} balls x {n} steps)"
+    s = dict(w)
+    s["x0"], s["v0"] = w["x0"][:cap], w["v0"][:cap]
+    if w["per_env"]:
+        s["segments"] = w["segments"][:cap]
+    return s, f"first {cap} of {B} balls x all {n} steps (per-ball work is independent)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML, polls during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.mask, self.stop_flag, self.max_mhz, self.err = index, [], 0, False, None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(
+                    nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                time.sleep(0.002)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def summary(self):
+        reasons = [n for b, n in self.REASONS.items() if self.mask & b and n != "gpu_idle"]
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples),
+                **({"error": self.err} if self.err else {})}
+
+
+def physical_gpu_index(local_index):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except Exception:
+            return local_index
+    return local_index
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours(args):
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from doper_b200 import synthetic as syn
+    from doper_b200._abi import check, lib
+    from doper_b200._device import ptr
+    from doper_b200.sim import ball_sim
+    from doper_b200.sim.jax_geometry import JaxScene
+
+    # ---- inputs: global arrays generated with the global seed, sliced by rank (weak scaling) ----
+    name = args.workload
+    per_gpu = args.balls or syn.WORKLOADS[name][0]
+    if name == "c5" and not args.balls:
+        per_gpu = syn.WORKLOADS[name][0] // 8
+    if name == "c3" and not args.balls:
+        per_gpu = syn.WORKLOADS[name][0] // max(world, 1) if args.strong else syn.WORKLOADS[name][0]
+    total = per_gpu * world
+    w = syn.make_workload(name, n_balls=total, lo=rank * per_gpu, hi=(rank + 1) * per_gpu)
+    B, n_steps = per_gpu, (args.sim_steps or w["n_steps"])
+    w["n_steps"], w["sim_time"] = n_steps, n_steps / 1000.0
+    S = int(w["segments"].shape[-3])
+    opts = ball_sim.RolloutOptions(ckpt_every=args.ckpt_every, lanes_per_ball=args.lanes,
+                                   force_exact_sweep=args.exact)
+    scene = JaxScene(w["segments"])
+    desc = ball_sim._make_desc(B, scene, w["sim_time"], n_steps, w["attractor"], w["constants"], opts)
+    _, sws = scene.prepared(device)
+    x0 = torch.tensor(w["x0"], device=device)
+    v0 = torch.tensor(w["v0"], device=device)
+    bufs = ball_sim._Buffers.get(device, desc)
+    o = bufs.out
+    loss_sum, xT, vT = o[0:1], o[4:4 + 2 * B], o[4 + 2 * B:4 + 4 * B]
+    gv, gx, lpb = o[4 + 4 * B:4 + 6 * B], o[4 + 6 * B:4 + 8 * B], o[4 + 8 * B:4 + 9 * B]
+    tgt = ball_sim._target2(w["target"])
+    st = torch.cuda.current_stream().cuda_stream
+    dref = ctypes.byref(desc)
+    # the one exchange step of a data-parallel trainer: controller grads (6,602 fp32,
+    # reference controllers.py:12-18) + the scalar loss, summed over ranks
+    ar_buf = torch.zeros(6602 + 1, dtype=torch.float32, device=device)
+
+    def fwd():
+        check(lib.doper_rollout_fwd(st, dref, ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT), 0, 0, 0,
+                                    ptr(bufs.ws)), "fwd")
+
+    def loss_bwd():
+        check(lib.doper_l1_loss(st, B, ptr(xT), tgt, ptr(lpb), ptr(loss_sum), ptr(bufs.scratch)), "loss")
+        check(lib.doper_rollout_bwd(st, dref, ptr(sws), ptr(bufs.ws), ptr(bufs.scratch), 0, ptr(gx), ptr(gv)),
+              "bwd")
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        fwd(); loss_bwd()
+    barrier()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    time.sleep(0.01)
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    pending = None
+    barrier()
+    t_wall = time.perf_counter()
+    for k in range(K):
+        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (untimed: outside the event pairs)
+        ev[k][0].record()
+        fwd()
+        ev[k][1].record()
+        loss_bwd()
+        if world > 1:
+            if pending is not None:
+                pending.wait()
+            ar_buf[6602:].copy_(loss_sum)
+            pending = dist.all_reduce(ar_buf, async_op=True)
+            pending.wait()  # the optimiser step needs the reduced gradient: it is on the step's critical path
+        ev[k][2].record()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    fwd_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    tot = torch.tensor([step_ms.sum()], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tot.item()) / K
+    value = world * B * n_steps / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API with host inputs (H2D + launches + D2H inside the timed region) ----
+    xh, vh = w["x0"], w["v0"]
+    api_args = (w["sim_time"], n_steps, scene, xh, vh, w["target"], w["attractor"], w["constants"], opts)
+    for _ in range(3):
+        ball_sim.vmapped_grad_and_value(*api_args)
+    barrier()
+    e2e_steps = max(5, min(K, 50))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        (l_e2e, (xT_e2e, _)), gv_e2e = ball_sim.vmapped_grad_and_value(*api_args)
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * n_steps / (float(e2e_ms.item()) * 1e-3)
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------
+    roof = None
+    cpu = None
+    if rank == 0:
+        probe_out = torch.empty(148 * 8 * 256, dtype=torch.float32, device=device)
+        rates = {}
+        for use_fma in (0, 1):
+            iters = 8192
+            for _ in range(2):
+                check(lib.doper_fp32_probe(st, 148 * 8, 256, iters, use_fma, ptr(probe_out)), "probe")
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            check(lib.doper_fp32_probe(st, 148 * 8, 256, iters, use_fma, ptr(probe_out)), "probe")
+            b.record()
+            torch.cuda.synchronize()
+            rates[use_fma] = 148 * 8 * 256 * iters * 16 / (a.elapsed_time(b) * 1e-3)
+        fwd_flops = B * n_steps * (24.0 * S + 34.0)  # algorithmic flops of the fwd kernel
+        achieved = fwd_flops / (float(fwd_ms.mean()) * 1e-3) / 1e12
+        peak = rates[0] / 1e12
+        ws_bytes = (-(-n_steps // (desc.ckpt_every or 32)) * 16 + n_steps * 4) * B  # ckpt + hit log written
+        traffic = None
+        tp = ROOT / "profiles" / "roofline_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(name)
+            except Exception:
+                traffic = None
+        peaks = {}
+        mp = ROOT / "MEASURED_PEAKS.json"
+        if mp.exists():
+            peaks = json.loads(mp.read_text())
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roof = {
+            "kernel": "rollout_fwd_kernel", "bound": "fp32", "achieved": round(achieved, 3),
+            "peak": round(peak, 3), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+            "peak_source": "non-FMA FADD/FMUL lane-op rate measured in this run (doper_fp32_probe); "
+                           "a bit-exact sweep cannot contract the reference's mul+add pairs",
+            "frac_of_fma_peak": round(fwd_flops / (float(fwd_ms.mean()) * 1e-3) / (2 * rates[1]), 4),
+            "fma_peak_tflops": round(2 * rates[1] / 1e12, 3),
+            "kernel_ms": round(float(fwd_ms.mean()), 4),
+            "kernel_share_of_step": round(float(fwd_ms.sum() / step_ms.sum()), 4),
+            "algorithmic_flops_per_launch": fwd_flops,
+            "traffic": traffic,
+            "hbm": {"achieved": round(ws_bytes / (float(fwd_ms.mean()) * 1e-3) / 1e9, 2), "peak": hbm_peak,
+                    "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "algorithmic_bytes_per_launch": ws_bytes},
+        }
+        if world == 1 and not args.no_cpu:
+            sample, what = bounded_sample(w)
+            r = cpu_reference_run(sample, steps=3, warmup=1, min_seconds=10.0)
+            cpu = {"value": round(r["value"], 1), "unit": UNIT, "cores": r["cores"], "kind": "port",
+                   "sample": f"{what}, {r['steps']} repetitions, oracle/ball_sim_ref.c {r['flavour']} + OpenMP "
+                             f"(restated reference; the reference's JAX is not installable here)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_label(name, B, S, n_steps, bool(w["per_env"])) +
+                       (f" per GPU ({world} GPUs, balls sharded, allreduce of 6,603 fp32 per step)" if world > 1 else ""),
+                       "l2": "256 MiB buffer rewritten between timed iterations (flush), outside the event pairs",
+                       "lanes_per_ball": int(desc.lanes_per_ball) or "auto", "ckpt_every": desc.ckpt_every or 32,
+                       "sweep": "exact" if args.exact else "filtered+exact"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 4 * B * 4,
+                    "d2h_bytes_per_step": (4 + 6 * B) * 4, "ms_per_step": round(float(e2e_ms.item()), 5),
+                    "api": "doper_b200.sim.ball_sim.vmapped_grad_and_value(host numpy arrays)"},
+            "gpu_launches": 3 * K,
+            "wall_ms_timed_region": round(wall_ms, 3),
+            "roofline": roof,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from doper_b200 import synthetic as syn
+
+    name = args.workload
+    per_gpu = args.balls or syn.WORKLOADS[name][0]
+    w = syn.make_workload(name, n_balls=per_gpu)
+    if args.sim_steps:
+        w["n_steps"], w["sim_time"] = args.sim_steps, args.sim_steps / 1000.0
+    sample, what = bounded_sample(w)
+    S = int(w["segments"].shape[-3])
+    r = cpu_reference_run(sample, steps=args.steps, warmup=max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(r["value"], 1), "unit": UNIT,
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(1, min(args.warmup, 3)),
+        "ms_per_step": round(r["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_label(name, per_gpu, S, w["n_steps"], bool(w["per_env"]))},
+        "cpu_baseline": {"value": round(r["value"], 1), "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": f"each step = {what}; oracle/ball_sim_ref.c {r['flavour']} + OpenMP on all host "
+                                   f"cores (restated reference: the reference is JAX/XLA:CPU, not installable here)"},
+        "e2e": {"value": round(r["value"], 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["c1", "c2", "c3", "c4", "c5"], default="c2")
+    ap.add_argument("--balls", type=int, default=0, help="balls per GPU (default: the workload's)")
+    ap.add_argument("--sim-steps", type=int, default=0, help="rollout length (default: the workload's)")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--ckpt-every", type=int, default=0)
+    ap.add_argument("--exact", action="store_true", help="force the exact (unfiltered) sweep")
+    ap.add_argument("--strong", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

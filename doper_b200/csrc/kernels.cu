@@ -1,0 +1,709 @@
+// doper_b200 CUDA kernels (sm_100a) and their C-ABI launchers (include/doper_b200.h).
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//          -prec-div=true -prec-sqrt=true -ftz=false  (see doper_b200/build.py)
+//
+// Kernels
+//   scene_prepare_kernel   raw segments -> staging layout (one block per scene)
+//   rollout_fwd_kernel<G>  whole rollout per launch: state in registers, scene staged into shared
+//                          memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier), G lanes per
+//                          ball on the sweep, warp-shuffle lexicographic min, K-step checkpoints +
+//                          per-step hit log for the backward
+//   rollout_bwd_kernel     reverse pass over checkpoints: replay a K-block from the hit log (no
+//                          sweep: argmin has no gradient), stash states in shared memory, apply the
+//                          hand-derived step adjoint
+//   l1_loss_kernel         per-ball L1 loss, its seed cotangent and a deterministic total
+//   closest_segment_kernel / points_inside_kernel   the scene-sampler queries
+//   fp32_probe_kernel      register-only FP32 issue-rate probe for the roofline denominator
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/doper_b200.h"
+#include "physics.cuh"
+#include "sweep.cuh"
+
+namespace doper {
+
+// ------------------------------------------------------------------------------------------
+// scene workspace layout
+// ------------------------------------------------------------------------------------------
+struct SceneHeader {  // 16 B per scene
+    float scale;      // max |coordinate|
+    int weird;        // degenerate / non-finite segment present -> exact sweep only
+    int S;
+    int S_pad;
+};
+
+struct SceneLayout {
+    size_t hdr_off, q_off, rl_off, total;
+    int S_pad;
+};
+
+__host__ __device__ inline SceneLayout scene_layout(int64_t n_scenes, int S) {
+    SceneLayout L;
+    L.S_pad = (S + 31) / 32 * 32;
+    L.hdr_off = 0;
+    size_t hdr = (size_t)n_scenes * sizeof(SceneHeader);
+    L.q_off = (hdr + 255) / 256 * 256;
+    L.rl_off = L.q_off + (size_t)n_scenes * L.S_pad * sizeof(float4);
+    L.total = L.rl_off + (size_t)n_scenes * L.S_pad * sizeof(float);
+    L.total = (L.total + 255) / 256 * 256;
+    return L;
+}
+
+constexpr float kSentinel = 1.0e18f;  // far-away padding segment: never a candidate
+
+__global__ void __launch_bounds__(128) scene_prepare_kernel(int64_t n_scenes, int S,
+                                                            const float4* __restrict__ segs,
+                                                            unsigned char* __restrict__ ws) {
+    const SceneLayout L = scene_layout(n_scenes, S);
+    const int64_t sc = blockIdx.x;
+    const float4* in = segs + sc * (int64_t)S;
+    float4* q = reinterpret_cast<float4*>(ws + L.q_off) + sc * (int64_t)L.S_pad;
+    float* rl = reinterpret_cast<float*>(ws + L.rl_off) + sc * (int64_t)L.S_pad;
+    float mx = 0.0f;
+    int weird = 0;
+    for (int i = threadIdx.x; i < L.S_pad; i += blockDim.x) {
+        if (i < S) {
+            float4 s = in[i];
+            float svx = s.z - s.x, svy = s.w - s.y;  // jax_geometry.py:132
+            float len2 = svx * svx + svy * svy;      // :133
+            q[i] = make_float4(s.x, s.y, svx, svy);
+            rl[i] = 1.0f / len2;
+            float m = fmaxf(fmaxf(fabsf(s.x), fabsf(s.y)), fmaxf(fabsf(s.z), fabsf(s.w)));
+            mx = fmaxf(mx, m);
+            // the filtered sweep's error analysis needs a normal, finite, non-degenerate segment
+            bool ok = (len2 >= 1.0e-30f) && (len2 <= 1.0e30f) && (m <= 1.0e15f);
+            weird |= !ok;  // also true for NaN coordinates (comparisons false)
+        } else {
+            q[i] = make_float4(kSentinel, kSentinel, 0.0f, 0.0f);
+            rl[i] = 0.0f;
+        }
+    }
+    __shared__ float s_mx[128];
+    __shared__ int s_w[128];
+    s_mx[threadIdx.x] = mx;
+    s_w[threadIdx.x] = weird;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)blockDim.x; ++i) { mx = fmaxf(mx, s_mx[i]); weird |= s_w[i]; }
+        SceneHeader h;
+        h.scale = mx; h.weird = weird; h.S = S; h.S_pad = L.S_pad;
+        reinterpret_cast<SceneHeader*>(ws + L.hdr_off)[sc] = h;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA (1-D bulk copy) + mbarrier primitives
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+constexpr uint32_t kTmaChunk = 32768;  // bytes per bulk copy (multiple of 16)
+
+// One elected thread stages `n_local` consecutive prepared scenes into shared memory.
+__device__ __forceinline__ void stage_scenes(float4* sq, float* srl, const unsigned char* ws,
+                                             const SceneLayout& L, int64_t first_scene, int n_local,
+                                             uint64_t* bar) {
+    const unsigned char* gq = ws + L.q_off + (size_t)first_scene * L.S_pad * sizeof(float4);
+    const unsigned char* gr = ws + L.rl_off + (size_t)first_scene * L.S_pad * sizeof(float);
+    const uint32_t qb = (uint32_t)n_local * L.S_pad * sizeof(float4);
+    const uint32_t rb = (uint32_t)n_local * L.S_pad * sizeof(float);
+    mbar_expect_tx(bar, qb + rb);
+    for (uint32_t o = 0; o < qb; o += kTmaChunk)
+        tma_load_1d(reinterpret_cast<unsigned char*>(sq) + o, gq + o, min(kTmaChunk, qb - o), bar);
+    for (uint32_t o = 0; o < rb; o += kTmaChunk)
+        tma_load_1d(reinterpret_cast<unsigned char*>(srl) + o, gr + o, min(kTmaChunk, rb - o), bar);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward rollout
+// ------------------------------------------------------------------------------------------
+constexpr int kFwdThreads = 128;
+
+struct FwdParams {
+    int64_t B;
+    int S, per_env, n_steps, K, force_exact;
+    Consts c;
+    const unsigned char* scene_ws;
+    const float2* x0;
+    const float2* v0;
+    float2* xT;
+    float2* vT;
+    float2* traj_x;
+    float2* traj_v;
+    float2* traj_a;
+    float4* ckpt;     // [n_ckpt][B]
+    int32_t* hitlog;  // [n_steps][B]
+};
+
+template <int G>
+__global__ void __launch_bounds__(kFwdThreads) rollout_fwd_kernel(const FwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int BPB = kFwdThreads / G;  // balls per block
+    const int tid = threadIdx.x, lane = tid % G, slot = tid / G;
+    const int64_t n_scenes = p.per_env ? p.B : 1;
+    const SceneLayout L = scene_layout(n_scenes, p.S);
+    const int n_local = p.per_env ? BPB : 1;
+
+    float4* sq = reinterpret_cast<float4*>(smem);
+    float* srl = reinterpret_cast<float*>(smem + (size_t)n_local * L.S_pad * sizeof(float4));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_local * L.S_pad * 20);
+
+    const int64_t first_ball = (int64_t)blockIdx.x * BPB;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        int64_t first_scene = p.per_env ? first_ball : 0;
+        int n = p.per_env ? (int)min((int64_t)BPB, p.B - first_ball) : 1;
+        stage_scenes(sq, srl, p.scene_ws, L, first_scene, n, bar);
+    }
+
+    int64_t ball = first_ball + slot;
+    const bool active = ball < p.B;
+    if (!active) ball = p.B - 1;  // duplicate the last ball: keeps every lane in the shuffles
+    const int local_scene = p.per_env ? (int)(ball - first_ball) : 0;
+    const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off)[p.per_env ? ball : 0];
+
+    SceneView sc;
+    sc.q = sq + (size_t)local_scene * L.S_pad;
+    sc.rl = srl + (size_t)local_scene * L.S_pad;
+    sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
+
+    float2 xx = p.x0[ball], vv = p.v0[ball];
+    float x = xx.x, y = xx.y, vx = vv.x, vy = vv.y;
+    const Consts c = p.c;
+    const bool writer = active && lane == 0;
+
+    mbar_wait(bar, 0);
+
+    int prev_idx = 0;
+    for (int t = 0; t < p.n_steps; ++t) {
+        if (writer && p.ckpt && (t % p.K) == 0)
+            p.ckpt[(size_t)(t / p.K) * p.B + ball] = make_float4(x, y, vx, vy);
+        State s1;
+        free_step(x, y, vx, vy, c, s1);
+        int idx; float dist;
+        sweep_any<G>(sc, s1.x, s1.y, lane, prev_idx, idx, dist);
+        prev_idx = idx;
+        const bool hit = dist <= c.r;  // NaN -> false (ball_sim.py:164)
+        if (hit) {
+            State s2;
+            resolve(x, y, vx, vy, s1, sc.q[idx], c, s2);
+            s1 = s2;
+        }
+        x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
+        if (writer) {
+            const size_t o = (size_t)t * p.B + ball;
+            if (p.hitlog) p.hitlog[o] = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31));
+            if (p.traj_x) p.traj_x[o] = make_float2(x, y);
+            if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
+            if (p.traj_a) p.traj_a[o] = make_float2(s1.ax, s1.ay);
+        }
+    }
+    if (writer) {
+        p.xT[ball] = make_float2(x, y);
+        p.vT[ball] = make_float2(vx, vy);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward rollout
+// ------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 128;
+
+struct BwdParams {
+    int64_t B;
+    int S, per_env, n_steps, K;
+    Consts c;
+    const unsigned char* scene_ws;
+    const float4* ckpt;
+    const int32_t* hitlog;
+    const float2* xT_bar;
+    const float2* vT_bar;  // nullable
+    float2* x0_bar;        // nullable
+    float2* v0_bar;
+};
+
+__global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* stash = reinterpret_cast<float4*>(smem);  // [K][kBwdThreads]
+    const int tid = threadIdx.x;
+    const int64_t ball = (int64_t)blockIdx.x * kBwdThreads + tid;
+    if (ball >= p.B) return;
+    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
+    const float4* q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) +
+                      (p.per_env ? (size_t)ball * L.S_pad : 0);
+    const Consts c = p.c;
+    float2 g = p.xT_bar[ball];
+    float gx = g.x, gy = g.y, gvx = 0.0f, gvy = 0.0f;
+    if (p.vT_bar) { float2 h = p.vT_bar[ball]; gvx = h.x; gvy = h.y; }
+
+    const int n_ckpt = (p.n_steps + p.K - 1) / p.K;
+    for (int ck = n_ckpt - 1; ck >= 0; --ck) {
+        const int t0 = ck * p.K, t1 = min(p.n_steps, t0 + p.K);
+        float4 s = p.ckpt[(size_t)ck * p.B + ball];
+        // replay the block from its checkpoint with the logged (idx, hit): bit-identical states
+        for (int t = t0; t < t1; ++t) {
+            stash[(size_t)(t - t0) * kBwdThreads + tid] = s;
+            if (t + 1 < t1) {
+                const int32_t h = p.hitlog[(size_t)t * p.B + ball];
+                State s1;
+                free_step(s.x, s.y, s.z, s.w, c, s1);
+                if (h < 0) {
+                    State s2;
+                    resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c, s2);
+                    s1 = s2;
+                }
+                s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
+            }
+        }
+        for (int t = t1 - 1; t >= t0; --t) {
+            const float4 st = stash[(size_t)(t - t0) * kBwdThreads + tid];
+            const int32_t h = p.hitlog[(size_t)t * p.B + ball];
+            const float4 seg = __ldg(q + (h & 0x7fffffff));
+            step_vjp(st.x, st.y, st.z, st.w, h < 0, seg, c, gx, gy, gvx, gvy);
+        }
+    }
+    p.v0_bar[ball] = make_float2(gvx, gvy);
+    if (p.x0_bar) p.x0_bar[ball] = make_float2(gx, gy);
+}
+
+// ------------------------------------------------------------------------------------------
+// loss
+// ------------------------------------------------------------------------------------------
+constexpr int kLossThreads = 256;
+
+// block 0: deterministic total (fixed strided partials + fixed tree); blocks >= 1: per-ball outputs
+__global__ void __launch_bounds__(kLossThreads) l1_loss_kernel(int64_t B, const float2* __restrict__ xT,
+                                                              float tx, float ty,
+                                                              float* __restrict__ loss_pb,
+                                                              float* __restrict__ loss_sum,
+                                                              float2* __restrict__ xT_bar) {
+    if (blockIdx.x == 0) {
+        __shared__ float part[kLossThreads];
+        float acc = 0.0f;
+        for (int64_t b = threadIdx.x; b < B; b += kLossThreads) {
+            float2 p = xT[b];
+            acc += fabsf(p.x - tx) + fabsf(p.y - ty);  // ball_sim.py:286
+        }
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        for (int s = kLossThreads / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) *loss_sum = part[0];  // ball_sim.py:324
+        return;
+    }
+    const int64_t b = (int64_t)(blockIdx.x - 1) * kLossThreads + threadIdx.x;
+    if (b >= B) return;
+    float2 p = xT[b];
+    float ex = p.x - tx, ey = p.y - ty;
+    if (loss_pb) loss_pb[b] = fabsf(ex) + fabsf(ey);
+    if (xT_bar) xT_bar[b] = make_float2(sgnf(ex), sgnf(ey));  // d|e|/de, 0 at e == 0 (and NaN -> 0)
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry queries
+// ------------------------------------------------------------------------------------------
+constexpr int kQueryThreads = 128;
+
+template <int G>
+__global__ void __launch_bounds__(kQueryThreads) closest_segment_kernel(
+    int64_t N, int S, const float2* __restrict__ pts, const float4* __restrict__ raw,
+    const unsigned char* __restrict__ scene_ws, int32_t* __restrict__ idx_out,
+    float* __restrict__ dist_out, float4* __restrict__ seg_out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SceneLayout L = scene_layout(1, S);
+    float4* sq = reinterpret_cast<float4*>(smem);
+    float* srl = reinterpret_cast<float*>(smem + (size_t)L.S_pad * sizeof(float4));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)L.S_pad * 20);
+    const int tid = threadIdx.x, lane = tid % G;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) stage_scenes(sq, srl, scene_ws, L, 0, 1, bar);
+    const SceneHeader hdr = *reinterpret_cast<const SceneHeader*>(scene_ws + L.hdr_off);
+    SceneView sc;
+    sc.q = sq; sc.rl = srl; sc.S = S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird;
+    int64_t i = (int64_t)blockIdx.x * (kQueryThreads / G) + tid / G;
+    const bool active = i < N;
+    if (!active) i = N - 1;
+    const float2 p = pts[i];
+    mbar_wait(bar, 0);
+    int idx; float dist;
+    sweep_any<G>(sc, p.x, p.y, lane, 0, idx, dist);
+    if (active && lane == 0) {
+        idx_out[i] = idx;
+        dist_out[i] = dist;
+        if (seg_out) seg_out[i] = raw[idx];
+    }
+}
+
+constexpr int kInsideTile = 3 * 1024;  // segments per shared-memory tile (multiple of 3)
+
+// jax_geometry.py:12-24,41-53,97-116. The unit normal is point-independent: computed once per
+// block per segment with the reference's arithmetic, then reused for every point.
+__global__ void __launch_bounds__(kQueryThreads) points_inside_kernel(int64_t N, int S,
+                                                                     const float2* __restrict__ pts,
+                                                                     const float4* __restrict__ raw,
+                                                                     uint8_t* __restrict__ flag) {
+    __shared__ float4 tile[kInsideTile];  // (s0x, s0y, nhx, nhy)
+    const int64_t i = (int64_t)blockIdx.x * kQueryThreads + threadIdx.x;
+    float px = 0.f, py = 0.f;
+    if (i < N) { float2 p = pts[i]; px = p.x; py = p.y; }
+    bool any = false;
+    for (int base = 0; base < S; base += kInsideTile) {
+        const int n = min(kInsideTile, S - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += kQueryThreads) {
+            float4 s = raw[base + j];
+            float svx = s.z - s.x, svy = s.w - s.y;      // :21
+            float nx = svy, ny = -svx;                   // :22
+            float nrm = sqrtf(nx * nx + ny * ny);        // :23
+            tile[j] = make_float4(s.x, s.y, nx / nrm, ny / nrm);
+        }
+        __syncthreads();
+        for (int t = 0; t + 2 < n; t += 3) {
+            bool all = true;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                float4 q = tile[t + e];
+                float pvx = px - q.x, pvy = py - q.y;    // :52
+                float d = pvx * q.z + pvy * q.w;         // :53
+                all = all && (d < 0.0f);                 // sign(d) < 0 ; NaN -> false
+            }
+            any = any || all;
+        }
+    }
+    if (i < N) flag[i] = any ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 issue-rate probe
+// ------------------------------------------------------------------------------------------
+__global__ void fp32_probe_kernel(int iters, int use_fma, float* out) {
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = 1.0f + 1e-3f * (float)(threadIdx.x + k);
+    const float m = 0.9999999f, cc = 1.0e-4f;
+    if (use_fma) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = __fmaf_rn(a[k], m, cc);
+        }
+    } else {
+        for (int it = 0; it < iters; it += 2) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = __fmul_rn(a[k], m);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = __fadd_rn(a[k], cc);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace doper
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace doper;
+
+namespace {
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+inline int launch_status() { return cudaPeekAtLastError() == cudaSuccess ? DOPER_OK : DOPER_ERR_LAUNCH; }
+
+int max_optin_smem() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+    return v;
+}
+
+Consts make_consts(const doper_rollout_desc* d) {
+    Consts c;
+    c.r = d->consts[0]; c.m = d->consts[1]; c.f = d->consts[2]; c.e = d->consts[3]; c.ks = d->consts[4];
+    c.ax = d->attractor[0]; c.ay = d->attractor[1];
+    c.dt = d->dt;
+    return c;
+}
+
+int resolve_K(const doper_rollout_desc* d) { return d->ckpt_every > 0 ? d->ckpt_every : 32; }
+
+int validate_desc(const doper_rollout_desc* d) {
+    if (!d) return DOPER_ERR_NULL_PTR;
+    if (d->B <= 0 || d->S <= 0 || d->n_steps < 0 || d->ckpt_every < 0) return DOPER_ERR_BAD_SHAPE;
+    if (d->ckpt_every > 1024) return DOPER_ERR_BAD_SHAPE;
+    const int g = d->lanes_per_ball;
+    if (!(g == 0 || g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32)) return DOPER_ERR_BAD_SHAPE;
+    return DOPER_OK;
+}
+
+// lanes per ball: enough threads to fill 148 SMs x 256 threads; per-env scenes are staged per
+// ball, so spreading one ball over 8 lanes keeps the shared-memory footprint per thread sane.
+int auto_lanes(const doper_rollout_desc* d) {
+    if (d->lanes_per_ball) return d->lanes_per_ball;
+    if (d->per_env) return 8;
+    int g = 1;
+    while (g < 32 && d->B * g < 148 * 256) g *= 2;
+    return g;
+}
+
+size_t fwd_smem_bytes(const doper_rollout_desc* d, int G) {
+    const SceneLayout L = scene_layout(1, d->S);
+    const size_t n_local = d->per_env ? (size_t)(kFwdThreads / G) : 1;
+    return n_local * L.S_pad * 20 + 16;
+}
+
+template <int G>
+int launch_fwd(cudaStream_t st, const FwdParams& p, size_t smem) {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(rollout_fwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+        return DOPER_ERR_SMEM_LIMIT;
+    const int bpb = kFwdThreads / G;
+    const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
+    rollout_fwd_kernel<G><<<grid, kFwdThreads, smem, st>>>(p);
+    return launch_status();
+}
+
+template <int G>
+int launch_closest(cudaStream_t st, int64_t N, int S, const float* pts, const float* segs, const void* ws,
+                   int32_t* idx, float* dist, float* seg_out, size_t smem) {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(closest_segment_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return DOPER_ERR_SMEM_LIMIT;
+    const int ppb = kQueryThreads / G;
+    const unsigned grid = (unsigned)((N + ppb - 1) / ppb);
+    closest_segment_kernel<G><<<grid, kQueryThreads, smem, st>>>(
+        N, S, reinterpret_cast<const float2*>(pts), reinterpret_cast<const float4*>(segs),
+        reinterpret_cast<const unsigned char*>(ws), idx, dist, reinterpret_cast<float4*>(seg_out));
+    return launch_status();
+}
+
+}  // namespace
+
+extern "C" {
+
+int doper_abi_version(void) { return DOPER_ABI_VERSION; }
+
+const char* doper_error_string(int code) {
+    switch (code) {
+        case DOPER_OK: return "ok";
+        case DOPER_ERR_BAD_SHAPE: return "bad shape or size argument";
+        case DOPER_ERR_NULL_PTR: return "required pointer is NULL";
+        case DOPER_ERR_MISALIGNED: return "pointer is not aligned as documented";
+        case DOPER_ERR_SMEM_LIMIT: return "scene does not fit the shared-memory plan of the kernel";
+        case DOPER_ERR_LAUNCH: return "CUDA kernel launch failed";
+        case DOPER_ERR_WORKSPACE: return "workspace too small";
+        case DOPER_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown doper_b200 error";
+    }
+}
+
+size_t doper_scene_workspace_bytes(int64_t n_scenes, int32_t S) {
+    if (n_scenes <= 0 || S <= 0) return 0;
+    return scene_layout(n_scenes, S).total;
+}
+
+int doper_scene_prepare(doper_stream_t stream, int64_t n_scenes, int32_t S, const float* segments,
+                        void* scene_ws) {
+    if (n_scenes <= 0 || S <= 0 || n_scenes > 0x7fffffff) return DOPER_ERR_BAD_SHAPE;
+    if (!segments || !scene_ws) return DOPER_ERR_NULL_PTR;
+    if (!aligned(segments, 16) || !aligned(scene_ws, 256)) return DOPER_ERR_MISALIGNED;
+    scene_prepare_kernel<<<(unsigned)n_scenes, 128, 0, (cudaStream_t)stream>>>(
+        n_scenes, S, reinterpret_cast<const float4*>(segments), reinterpret_cast<unsigned char*>(scene_ws));
+    return launch_status();
+}
+
+int doper_closest_segment(doper_stream_t stream, int64_t N, int32_t S, const float* points,
+                          const float* segments, const void* scene_ws, int32_t* idx, float* dist,
+                          float* seg_out) {
+    if (N < 0 || S <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (N == 0) return DOPER_OK;
+    if (!points || !segments || !scene_ws || !idx || !dist) return DOPER_ERR_NULL_PTR;
+    if (!aligned(points, 8) || !aligned(segments, 16) || !aligned(scene_ws, 256) ||
+        (seg_out && !aligned(seg_out, 16)))
+        return DOPER_ERR_MISALIGNED;
+    const SceneLayout L = scene_layout(1, S);
+    const size_t smem = (size_t)L.S_pad * 20 + 16;
+    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    int G = 1;
+    while (G < 32 && N * G < 148 * 256) G *= 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (G) {
+        case 1: return launch_closest<1>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
+        case 2: return launch_closest<2>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
+        case 4: return launch_closest<4>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
+        case 8: return launch_closest<8>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
+        case 16: return launch_closest<16>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
+        default: return launch_closest<32>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
+    }
+}
+
+int doper_points_inside(doper_stream_t stream, int64_t N, int32_t S, const float* points,
+                        const float* segments, uint8_t* flag) {
+    if (N < 0 || S <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (S % 3 != 0) return DOPER_ERR_UNSUPPORTED;  // jax_geometry.py:113 reshapes to (.., polygons, 3)
+    if (N == 0) return DOPER_OK;
+    if (!points || !segments || !flag) return DOPER_ERR_NULL_PTR;
+    if (!aligned(points, 8) || !aligned(segments, 16)) return DOPER_ERR_MISALIGNED;
+    const unsigned grid = (unsigned)((N + kQueryThreads - 1) / kQueryThreads);
+    points_inside_kernel<<<grid, kQueryThreads, 0, (cudaStream_t)stream>>>(
+        N, S, reinterpret_cast<const float2*>(points), reinterpret_cast<const float4*>(segments), flag);
+    return launch_status();
+}
+
+size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d) {
+    if (validate_desc(d) != DOPER_OK) return 0;
+    const int K = resolve_K(d);
+    const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
+    size_t bytes = n_ckpt * (size_t)d->B * sizeof(float4);
+    bytes = (bytes + 255) / 256 * 256;
+    bytes += (size_t)d->n_steps * (size_t)d->B * sizeof(int32_t);
+    return (bytes + 255) / 256 * 256 + 256;
+}
+
+int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                      const float* x0, const float* v0, float* xT, float* vT, float* traj_x,
+                      float* traj_v, float* traj_a, void* ws) {
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    if (!scene_ws || !x0 || !v0 || !xT || !vT) return DOPER_ERR_NULL_PTR;
+    if (!aligned(scene_ws, 256) || !aligned(x0, 8) || !aligned(v0, 8) || !aligned(xT, 8) || !aligned(vT, 8) ||
+        (ws && !aligned(ws, 256)) || (traj_x && !aligned(traj_x, 8)) || (traj_v && !aligned(traj_v, 8)) ||
+        (traj_a && !aligned(traj_a, 8)))
+        return DOPER_ERR_MISALIGNED;
+    const int G = auto_lanes(d);
+    const size_t smem = fwd_smem_bytes(d, G);
+    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    const int K = resolve_K(d);
+    FwdParams p;
+    p.B = d->B; p.S = d->S; p.per_env = d->per_env ? 1 : 0; p.n_steps = d->n_steps; p.K = K;
+    p.force_exact = d->flags & 1;
+    p.c = make_consts(d);
+    p.scene_ws = reinterpret_cast<const unsigned char*>(scene_ws);
+    p.x0 = reinterpret_cast<const float2*>(x0); p.v0 = reinterpret_cast<const float2*>(v0);
+    p.xT = reinterpret_cast<float2*>(xT); p.vT = reinterpret_cast<float2*>(vT);
+    p.traj_x = reinterpret_cast<float2*>(traj_x); p.traj_v = reinterpret_cast<float2*>(traj_v);
+    p.traj_a = reinterpret_cast<float2*>(traj_a);
+    p.ckpt = nullptr; p.hitlog = nullptr;
+    if (ws) {
+        const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
+        size_t off = (n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
+        p.ckpt = reinterpret_cast<float4*>(ws);
+        p.hitlog = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(ws) + off);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (G) {
+        case 1: return launch_fwd<1>(st, p, smem);
+        case 2: return launch_fwd<2>(st, p, smem);
+        case 4: return launch_fwd<4>(st, p, smem);
+        case 8: return launch_fwd<8>(st, p, smem);
+        case 16: return launch_fwd<16>(st, p, smem);
+        default: return launch_fwd<32>(st, p, smem);
+    }
+}
+
+int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                      const void* ws, const float* xT_bar, const float* vT_bar, float* x0_bar,
+                      float* v0_bar) {
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    if (!scene_ws || !ws || !xT_bar || !v0_bar) return DOPER_ERR_NULL_PTR;
+    if (!aligned(scene_ws, 256) || !aligned(ws, 256) || !aligned(xT_bar, 8) || !aligned(v0_bar, 8) ||
+        (vT_bar && !aligned(vT_bar, 8)) || (x0_bar && !aligned(x0_bar, 8)))
+        return DOPER_ERR_MISALIGNED;
+    const int K = resolve_K(d);
+    const size_t smem = (size_t)K * kBwdThreads * sizeof(float4);
+    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(rollout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+        return DOPER_ERR_SMEM_LIMIT;
+    BwdParams p;
+    p.B = d->B; p.S = d->S; p.per_env = d->per_env ? 1 : 0; p.n_steps = d->n_steps; p.K = K;
+    p.c = make_consts(d);
+    p.scene_ws = reinterpret_cast<const unsigned char*>(scene_ws);
+    const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
+    size_t off = (n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
+    p.ckpt = reinterpret_cast<const float4*>(ws);
+    p.hitlog = reinterpret_cast<const int32_t*>(reinterpret_cast<const unsigned char*>(ws) + off);
+    p.xT_bar = reinterpret_cast<const float2*>(xT_bar);
+    p.vT_bar = reinterpret_cast<const float2*>(vT_bar);
+    p.x0_bar = reinterpret_cast<float2*>(x0_bar);
+    p.v0_bar = reinterpret_cast<float2*>(v0_bar);
+    const unsigned grid = (unsigned)((d->B + kBwdThreads - 1) / kBwdThreads);
+    rollout_bwd_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(p);
+    return launch_status();
+}
+
+int doper_l1_loss(doper_stream_t stream, int64_t B, const float* xT, const float target[2],
+                  float* loss_per_ball, float* loss_sum, float* xT_bar) {
+    if (B <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (!xT || !target || !loss_sum) return DOPER_ERR_NULL_PTR;
+    if (!aligned(xT, 8) || (xT_bar && !aligned(xT_bar, 8))) return DOPER_ERR_MISALIGNED;
+    const unsigned grid = 1 + (unsigned)((B + kLossThreads - 1) / kLossThreads);
+    l1_loss_kernel<<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(
+        B, reinterpret_cast<const float2*>(xT), target[0], target[1], loss_per_ball, loss_sum,
+        reinterpret_cast<float2*>(xT_bar));
+    return launch_status();
+}
+
+int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                         const float* x0, const float* v0, const float target[2], void* ws,
+                         float* scratch, float* loss_sum, float* loss_per_ball, float* xT,
+                         float* vT, float* v0_bar, float* x0_bar) {
+    if (!ws || !scratch || !target) return DOPER_ERR_NULL_PTR;
+    int rc = doper_rollout_fwd(stream, d, scene_ws, x0, v0, xT, vT, nullptr, nullptr, nullptr, ws);
+    if (rc) return rc;
+    rc = doper_l1_loss(stream, d->B, xT, target, loss_per_ball, loss_sum, scratch);
+    if (rc) return rc;
+    return doper_rollout_bwd(stream, d, scene_ws, ws, scratch, nullptr, x0_bar, v0_bar);
+}
+
+int doper_fp32_probe(doper_stream_t stream, int32_t blocks, int32_t threads, int32_t iters,
+                     int32_t use_fma, float* out) {
+    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (!out) return DOPER_ERR_NULL_PTR;
+    fp32_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, use_fma, out);
+    return launch_status();
+}
+
+}  // extern "C"

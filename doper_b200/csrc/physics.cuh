@@ -1,0 +1,207 @@
+// O(1) per-step physics of the rollout and its adjoint, in the reference's exact fp32
+// operation order.
+//
+// This translation unit is compiled with -fmad=false, IEEE division / sqrt (-prec-div=true
+// -prec-sqrt=true, no -use_fast_math, denormals kept), so every `a*b + c` below is two
+// roundings exactly as written; the only single-rounding fused multiply-adds are the explicit
+// __fmaf_rn calls: get_new_state's coordinate update (reference ball_sim.py:76), which the
+// reference's recorded output pins as contracted, and the sweep's candidate
+// filter (sweep.cuh), which never decides a result.
+//
+// Reference: doper/sim/ball_sim.py:15-132,171-209 ; doper/sim/jax_geometry.py:119-138.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace doper {
+
+struct Consts {
+    float r, m, f, e, ks;  // radius, mass, friction coeff, wall elasticity, attractor strength
+    float ax, ay;          // attractor
+    float dt;
+};
+
+struct State {
+    float x, y, vx, vy, ax, ay;
+};
+
+// jnp.clip = min(max(x, lo), hi) with NaN propagation (CUDA fminf/fmaxf would drop the NaN)
+__device__ __forceinline__ float clip_nan(float x, float lo, float hi) {
+    float c = fminf(fmaxf(x, lo), hi);
+    return (x != x) ? x : c;
+}
+
+// ball_sim.py:43-45 : ((((-clip(v,-1,1)) * m) * 9.8) * f) / r
+__device__ __forceinline__ float fric(float v, const Consts& c) {
+    return ((((-clip_nan(v, -1.0f, 1.0f)) * c.m) * 9.8f) * c.f) / c.r;
+}
+
+// get_new_state coordinate update, ball_sim.py:76 (single rounding, see header comment)
+__device__ __forceinline__ float pos_update(float v, float dt, float x) { return __fmaf_rn(v, dt, x); }
+
+// jax_geometry.py:132-136 on a pre-digested segment q = (s0x, s0y, svx, svy).
+// sv = s1 - s0 is ball-independent, so reading it is bit-identical to recomputing it.
+__device__ __forceinline__ void proj(float px, float py, const float4& q, float& cx, float& cy,
+                                     float& t) {
+    float L = q.z * q.z + q.w * q.w;
+    float pvx = px - q.x, pvy = py - q.y;
+    t = clip_nan((pvx * q.z + pvy * q.w) / L, 0.0f, 1.0f);
+    cx = q.x + t * q.z;
+    cy = q.y + t * q.w;
+}
+
+// squared distance exactly as the reference computes it before the sqrt (jax_geometry.py:151-152)
+__device__ __forceinline__ float seg_dist2(float px, float py, const float4& q) {
+    float cx, cy, t;
+    proj(px, py, q, cx, cy, t);
+    float dx = px - cx, dy = py - cy;
+    return dx * dx + dy * dy;
+}
+
+// ball_sim.py:192-202 : forces + semi-implicit Euler -> candidate state (x1, v1, a)
+__device__ __forceinline__ void free_step(float x, float y, float vx, float vy, const Consts& c,
+                                          State& o) {
+    float px = -(2.0f * (x - c.ax)), py = -(2.0f * (y - c.ay));
+    float fx = fric(vx, c), fy = fric(vy, c);
+    float ax = (c.ks * px + fx) / c.m, ay = (c.ks * py + fy) / c.m;
+    float v1x = vx + ax * c.dt, v1y = vy + ay * c.dt;
+    o.x = pos_update(v1x, c.dt, x);
+    o.y = pos_update(v1y, c.dt, y);
+    o.vx = v1x; o.vy = v1y; o.ax = ax; o.ay = ay;
+}
+
+// ball_sim.py:97-132 : time-of-impact sub-step, reflection, remaining sub-step
+__device__ __forceinline__ void resolve(float x, float y, float vx, float vy, const State& s1,
+                                        const float4& seg, const Consts& c, State& o) {
+    float c1x, c1y, t1;
+    proj(s1.x, s1.y, seg, c1x, c1y, t1);
+    float ox = c1x - x, oy = c1y - y;  // OLD coordinate (ball_sim.py:100)
+    float od = sqrtf(ox * ox + oy * oy);
+    float nx = ox / od, ny = oy / od;
+    float toi = fabsf(od - c.r) / fabsf(nx * s1.vx + ny * s1.vy);
+    toi = clip_nan(toi, 0.0f, c.dt);
+    float vsx = vx + s1.ax * toi, vsy = vy + s1.ay * toi;
+    float xsx = pos_update(vsx, toi, x), xsy = pos_update(vsy, toi, y);
+    float c2x, c2y, t2;
+    proj(xsx, xsy, seg, c2x, c2y, t2);
+    float o2x = c2x - xsx, o2y = c2y - xsy;
+    float o2d = sqrtf(o2x * o2x + o2y * o2y);
+    float n2x = o2x / o2d, n2y = o2y / o2d;
+    float k = n2x * vsx + n2y * vsy;
+    float vnx = n2x * k, vny = n2y * k;
+    float vpx = vsx - vnx, vpy = vsy - vny;
+    float vax = vpx - c.e * vnx, vay = vpy - c.e * vny;
+    float pbx = -(2.0f * (xsx - c.ax)), pby = -(2.0f * (xsy - c.ay));  // no attractor_strength (:124)
+    float fbx = fric(vax, c), fby = fric(vay, c);
+    float abx = (pbx + fbx) / c.m, aby = (pby + fby) / c.m;
+    float tau = c.dt - toi;
+    float vbx = vax + abx * tau, vby = vay + aby * tau;
+    o.x = pos_update(vbx, tau, xsx);
+    o.y = pos_update(vby, tau, xsy);
+    o.vx = vbx; o.vy = vby; o.ax = abx; o.ay = aby;
+}
+
+// ---------------------------------------------------------------------------------------
+// adjoint.  Operation order mirrors oracle/ball_sim_ref.c:step_vjp so
+// that, on a bit-identical forward history, the gradients are bit-identical too.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float dfric(float v, const Consts& c) {
+    return (v > -1.0f && v < 1.0f) ? -((((c.m) * 9.8f) * c.f) / c.r) : 0.0f;
+}
+
+__device__ __forceinline__ float sgnf(float a) { return a > 0.0f ? 1.0f : (a < 0.0f ? -1.0f : 0.0f); }
+
+// J^T w of proj(): [0 < t < 1] sv sv^T / L
+__device__ __forceinline__ void proj_vjp(const float4& q, float t, float wx, float wy, float& gx,
+                                         float& gy) {
+    if (t > 0.0f && t < 1.0f) {
+        float L = q.z * q.z + q.w * q.w;
+        float s = (wx * q.z + wy * q.w) / L;
+        gx = s * q.z; gy = s * q.w;
+    } else {
+        gx = 0.0f; gy = 0.0f;
+    }
+}
+
+// In/out g = (gx, gy, gvx, gvy): cotangent of the step output -> cotangent of the step input.
+__device__ __forceinline__ void step_vjp(float x, float y, float vx, float vy, bool hit,
+                                         const float4& seg, const Consts& c, float& gx, float& gy,
+                                         float& gvx, float& gvy) {
+    State s1;
+    free_step(x, y, vx, vy, c, s1);
+    float bx = 0.f, by = 0.f, bvx = 0.f, bvy = 0.f, bax = 0.f, bay = 0.f;
+    float b1x, b1y, b1vx, b1vy;
+    if (hit) {
+        float c1x, c1y, t1;
+        proj(s1.x, s1.y, seg, c1x, c1y, t1);
+        float ox = c1x - x, oy = c1y - y;
+        float od = sqrtf(ox * ox + oy * oy);
+        float nx = ox / od, ny = oy / od;
+        float s = nx * s1.vx + ny * s1.vy;
+        float num = fabsf(od - c.r), den = fabsf(s);
+        float toi_raw = num / den;
+        float toi = clip_nan(toi_raw, 0.0f, c.dt);
+        float vsx = vx + s1.ax * toi, vsy = vy + s1.ay * toi;
+        float xsx = pos_update(vsx, toi, x), xsy = pos_update(vsy, toi, y);
+        float c2x, c2y, t2;
+        proj(xsx, xsy, seg, c2x, c2y, t2);
+        float o2x = c2x - xsx, o2y = c2y - xsy;
+        float o2d = sqrtf(o2x * o2x + o2y * o2y);
+        float n2x = o2x / o2d, n2y = o2y / o2d;
+        float k = n2x * vsx + n2y * vsy;
+        float vnx = n2x * k, vny = n2y * k;
+        float vax = (vsx - vnx) - c.e * vnx, vay = (vsy - vny) - c.e * vny;
+        float pbx = -(2.0f * (xsx - c.ax)), pby = -(2.0f * (xsy - c.ay));
+        float abx = (pbx + fric(vax, c)) / c.m, aby = (pby + fric(vay, c)) / c.m;
+        float tau = c.dt - toi;
+        float vbx = vax + abx * tau, vby = vay + aby * tau;
+        // reverse
+        float gvbx = gvx + gx * tau, gvby = gvy + gy * tau;
+        float gxsx = gx, gxsy = gy;
+        float gtau = (gx * vbx + gy * vby) + (gvbx * abx + gvby * aby);
+        float gvax = gvbx, gvay = gvby;
+        float gabx = gvbx * tau, gaby = gvby * tau;
+        gxsx += -2.0f * (gabx / c.m); gxsy += -2.0f * (gaby / c.m);
+        gvax += (gabx / c.m) * dfric(vax, c); gvay += (gaby / c.m) * dfric(vay, c);
+        float gtoi = -gtau;
+        float gvsx = gvax, gvsy = gvay;
+        float gvnx = -(1.0f + c.e) * gvax, gvny = -(1.0f + c.e) * gvay;
+        float gk = gvnx * n2x + gvny * n2y;
+        float gn2x = gvnx * k + gk * vsx, gn2y = gvny * k + gk * vsy;
+        gvsx += gk * n2x; gvsy += gk * n2y;
+        float nd = n2x * gn2x + n2y * gn2y;
+        float go2x = (gn2x - n2x * nd) / o2d, go2y = (gn2y - n2y * nd) / o2d;
+        float jx, jy;
+        proj_vjp(seg, t2, go2x, go2y, jx, jy);
+        gxsx += jx - go2x; gxsy += jy - go2y;
+        bx += gxsx; by += gxsy;
+        gvsx += gxsx * toi; gvsy += gxsy * toi;
+        gtoi += gxsx * vsx + gxsy * vsy;
+        bvx += gvsx; bvy += gvsy;
+        bax += gvsx * toi; bay += gvsy * toi;
+        gtoi += gvsx * s1.ax + gvsy * s1.ay;
+        float graw = (toi_raw > 0.0f && toi_raw < c.dt) ? gtoi : 0.0f;
+        float gnum = graw / den;
+        float gden = -(graw * toi_raw) / den;
+        float god = gnum * sgnf(od - c.r);
+        float gs = gden * sgnf(s);
+        float gnx = gs * s1.vx, gny = gs * s1.vy;
+        b1vx = gs * nx; b1vy = gs * ny;
+        float nd1 = nx * gnx + ny * gny;
+        float gox = (gnx - nx * nd1) / od + god * nx, goy = (gny - ny * nd1) / od + god * ny;
+        bx -= gox; by -= goy;
+        proj_vjp(seg, t1, gox, goy, b1x, b1y);
+    } else {
+        b1x = gx; b1y = gy; b1vx = gvx; b1vy = gvy;
+    }
+    float tvx = b1vx + b1x * c.dt, tvy = b1vy + b1y * c.dt;
+    bx += b1x; by += b1y;
+    bvx += tvx; bvy += tvy;
+    bax += tvx * c.dt; bay += tvy * c.dt;
+    float amx = bax / c.m, amy = bay / c.m;
+    bx += -2.0f * (c.ks * amx); by += -2.0f * (c.ks * amy);
+    bvx += amx * dfric(vx, c); bvy += amy * dfric(vy, c);
+    gx = bx; gy = by; gvx = bvx; gvy = bvy;
+}
+
+}  // namespace doper

@@ -1,0 +1,337 @@
+"""Drop-in mirror of the reference ``doper/sim/ball_sim.py`` rollout API.
+
+Same names, positional signatures and return nesting as the reference: ``run_sim``
+(ball_sim.py:212-253,327), ``compute_loss`` (:256-286,329), ``vmapped_loss`` (:332),
+``reduce_loss`` (:289-324) and ``vmapped_grad_and_value`` (:334-338), so that
+``doper/trainers/ball_trainer.py:10`` only has to change the package it imports from.
+
+All compute happens in the sm_100a kernels behind the C ABI (include/doper_b200.h); there is
+no CPU path.  Host inputs (numpy / lists / CPU tensors) take the end-to-end path: one pinned
+H2D copy in, the three launches, one pinned D2H copy out, results as numpy.  torch CUDA inputs
+stay on the device (zero-copy in, torch CUDA tensors out).  ``rollout`` is the same thing as a
+``torch.autograd.Function`` for callers that keep the controller's graph on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import namedtuple
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .._abi import RolloutDesc, check, lib
+from .._device import PINNED, as_f32_device, is_device_tensor, ptr, require_cuda, stream_ptr
+from .jax_geometry import JaxScene, _as_scene
+
+__all__ = [
+    "BallState", "run_sim", "compute_loss", "vmapped_loss", "reduce_loss", "vmapped_grad_and_value",
+    "rollout", "RolloutOptions", "set_default_options",
+]
+
+BallState = namedtuple("BallState", ["coordinate", "velocity", "acceleration"])  # ball_sim.py:12
+
+_CONST_KEYS = ("radius", "mass", "rolling_friction_coefficient", "walls_elasticity", "attractor_strength")
+
+
+class RolloutOptions:
+    """Tuning knobs that do not change results."""
+
+    def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False):
+        self.ckpt_every = int(ckpt_every)
+        self.lanes_per_ball = int(lanes_per_ball)
+        self.force_exact_sweep = bool(force_exact_sweep)
+
+
+_DEFAULT_OPTIONS = RolloutOptions()
+
+
+def set_default_options(opts: RolloutOptions) -> None:
+    global _DEFAULT_OPTIONS
+    _DEFAULT_OPTIONS = opts
+
+
+def _consts_array(constants: dict) -> np.ndarray:
+    """The five f32 runtime scalars the path reads (ball_sim.py:104,119,127-129,195-200)."""
+    c = dict(constants)
+    if "mass" not in c and "density" in c:  # ball_trainer.py:22-23, host double
+        c["mass"] = (4 * np.pi * (float(c["radius"]) ** 3) / 3) * float(c["density"])
+    return np.array([np.float32(float(c[k])) for k in _CONST_KEYS], dtype=np.float32)
+
+
+def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, constants,
+               opts: RolloutOptions) -> RolloutDesc:
+    n_steps = int(n_steps)
+    if n_steps <= 0:
+        raise ValueError("n_steps must be positive")
+    d = RolloutDesc()
+    d.B = int(B)
+    d.S = scene.n_segments
+    d.per_env = 1 if scene.per_env else 0
+    d.n_steps = n_steps
+    d.ckpt_every = opts.ckpt_every
+    d.dt = np.float32(sim_time / n_steps)  # ball_sim.py:237: host double, rounded once
+    k = _consts_array(constants)
+    for i in range(5):
+        d.consts[i] = k[i]
+    a = np.asarray(attractor.detach().cpu() if isinstance(attractor, torch.Tensor) else attractor,
+                   dtype=np.float32).reshape(2)
+    d.attractor[0], d.attractor[1] = a[0], a[1]
+    d.lanes_per_ball = opts.lanes_per_ball
+    d.flags = 1 if opts.force_exact_sweep else 0
+    if scene.per_env and scene.n_scenes != d.B:
+        raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
+    return d
+
+
+def _target2(target) -> "ctypes.Array":
+    t = np.asarray(target.detach().cpu() if isinstance(target, torch.Tensor) else target,
+                   dtype=np.float32).reshape(2)
+    return (ctypes.c_float * 2)(t[0], t[1])
+
+
+class _Buffers:
+    """Per-(device, shape) reusable device buffers: backward workspace, scratch, packed outputs."""
+
+    _cache: Dict[tuple, "_Buffers"] = {}
+
+    def __init__(self, device, desc: RolloutDesc):
+        B = desc.B
+        self.ws = torch.empty(lib.doper_rollout_workspace_bytes(ctypes.byref(desc)), dtype=torch.uint8,
+                              device=device)
+        self.scratch = torch.empty(2 * B, dtype=torch.float32, device=device)
+        # packed [loss_sum (4 floats, 16-B slot) | xT 2B | vT 2B | v0_bar 2B | x0_bar 2B | loss_pb B]
+        self.out = torch.empty(4 + 9 * B, dtype=torch.float32, device=device)
+        self.inp = torch.empty(4 * B, dtype=torch.float32, device=device)  # [x0 2B | v0 2B]
+
+    @classmethod
+    def get(cls, device, desc: RolloutDesc) -> "_Buffers":
+        key = (device.index, desc.B, desc.S, desc.per_env, desc.n_steps, desc.ckpt_every)
+        b = cls._cache.get(key)
+        if b is None:
+            if len(cls._cache) > 8:
+                cls._cache.clear()
+            b = cls(device, desc)
+            cls._cache[key] = b
+        return b
+
+
+def _stage_inputs(x0, v0, device, bufs: Optional[_Buffers]) -> Tuple[torch.Tensor, torch.Tensor, bool]:
+    """-> (x0 [B,2], v0 [B,2] device f32, host_path)."""
+    if is_device_tensor(x0) and is_device_tensor(v0):
+        return as_f32_device(x0, device).reshape(-1, 2), as_f32_device(v0, device).reshape(-1, 2), False
+    if is_device_tensor(x0) or is_device_tensor(v0):  # mixed: move the host one over
+        return as_f32_device(x0, device).reshape(-1, 2), as_f32_device(v0, device).reshape(-1, 2), True
+    xh = np.asarray(x0.detach() if isinstance(x0, torch.Tensor) else x0, dtype=np.float32).reshape(-1, 2)
+    vh = np.asarray(v0.detach() if isinstance(v0, torch.Tensor) else v0, dtype=np.float32).reshape(-1, 2)
+    B = xh.shape[0]
+    if vh.shape[0] != B:
+        raise ValueError("coordinate_init and velocity_init batch sizes differ")
+    pin = PINNED.get("in", 4 * B)
+    pv = pin.numpy()
+    pv[: 2 * B] = xh.reshape(-1)
+    pv[2 * B:] = vh.reshape(-1)
+    dst = bufs.inp if bufs is not None else torch.empty(4 * B, dtype=torch.float32, device=device)
+    dst.copy_(pin, non_blocking=True)  # ONE pinned H2D copy
+    return dst[: 2 * B].view(B, 2), dst[2 * B:].view(B, 2), True
+
+
+def _batch_of(x0) -> int:
+    shp = tuple(x0.shape) if hasattr(x0, "shape") else np.asarray(x0).shape
+    return 1 if len(shp) == 1 else int(shp[0])
+
+
+# ------------------------------------------------------------------------------------------
+# public API (reference names)
+# ------------------------------------------------------------------------------------------
+def run_sim(sim_time, n_steps, scene, coordinate_init, velocity_init, attractor, constants,
+            options: RolloutOptions = None):
+    """``run_sim`` (ball_sim.py:212-253,327).
+
+    Unbatched ``[2]`` inputs return ``(x_T [2], v_T [2], BallState of [n_steps,2])`` like the
+    reference; batched ``[B,2]`` inputs return ``[B,2]`` and ``[n_steps,B,2]``.
+    """
+    opts = options or _DEFAULT_OPTIONS
+    device = require_cuda()
+    scene = _as_scene(scene)
+    unbatched = len(np.shape(coordinate_init) if not hasattr(coordinate_init, "shape")
+                    else coordinate_init.shape) == 1
+    B = _batch_of(coordinate_init)
+    desc = _make_desc(B, scene, sim_time, n_steps, attractor, constants, opts)
+    _, sws = scene.prepared(device)
+    x0, v0, host = _stage_inputs(coordinate_init, velocity_init, device, None)
+    n = desc.n_steps
+    out = torch.empty((2, B, 2), dtype=torch.float32, device=device)
+    traj = torch.empty((3, n, B, 2), dtype=torch.float32, device=device)
+    check(lib.doper_rollout_fwd(stream_ptr(), ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), ptr(out[0]),
+                                ptr(out[1]), ptr(traj[0]), ptr(traj[1]), ptr(traj[2]), 0),
+          "doper_rollout_fwd")
+    xT, vT = out[0], out[1]
+    if unbatched:
+        xT, vT, traj = xT[0], vT[0], traj[:, :, 0]
+    if host:
+        xT, vT, traj = xT.cpu().numpy(), vT.cpu().numpy(), traj.cpu().numpy()
+    return xT, vT, BallState(coordinate=traj[0], velocity=traj[1], acceleration=traj[2])
+
+
+def _value_and_grad_raw(sim_time, n_steps, scene, coordinate_init, velocity_init, target_coordinate,
+                        attractor, constants, opts, want_grad: bool):
+    device = require_cuda()
+    scene = _as_scene(scene)
+    B = _batch_of(coordinate_init)
+    desc = _make_desc(B, scene, sim_time, n_steps, attractor, constants, opts)
+    _, sws = scene.prepared(device)
+    bufs = _Buffers.get(device, desc)
+    x0, v0, host = _stage_inputs(coordinate_init, velocity_init, device, bufs)
+    o = bufs.out
+    loss_sum, xT, vT = o[0:1], o[4:4 + 2 * B], o[4 + 2 * B:4 + 4 * B]
+    gv, gx, lpb = o[4 + 4 * B:4 + 6 * B], o[4 + 6 * B:4 + 8 * B], o[4 + 8 * B:4 + 9 * B]
+    tgt = _target2(target_coordinate)
+    st = stream_ptr()
+    if want_grad:
+        check(lib.doper_value_and_grad(st, ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), tgt, ptr(bufs.ws),
+                                       ptr(bufs.scratch), ptr(loss_sum), ptr(lpb), ptr(xT), ptr(vT), ptr(gv),
+                                       ptr(gx)), "doper_value_and_grad")
+    else:
+        check(lib.doper_rollout_fwd(st, ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT), 0, 0,
+                                    0, 0), "doper_rollout_fwd")
+        check(lib.doper_l1_loss(st, B, ptr(xT), tgt, ptr(lpb), ptr(loss_sum), 0), "doper_l1_loss")
+    if host:
+        pin = PINNED.get("out", 4 + 9 * B)
+        if want_grad:
+            pin[: 4 + 6 * B].copy_(o[: 4 + 6 * B], non_blocking=True)  # ONE pinned D2H copy
+        else:
+            pin[: 4 + 4 * B].copy_(o[: 4 + 4 * B], non_blocking=True)
+            pin[4 + 8 * B: 4 + 9 * B].copy_(lpb, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = pin.numpy()
+        res = {
+            "loss": np.float32(h[0]),
+            "x_T": h[4:4 + 2 * B].reshape(B, 2).copy(),
+            "v_T": h[4 + 2 * B:4 + 4 * B].reshape(B, 2).copy(),
+            "grad_v0": h[4 + 4 * B:4 + 6 * B].reshape(B, 2).copy() if want_grad else None,
+            "loss_per_ball": None if want_grad else h[4 + 8 * B:4 + 9 * B].copy(),
+        }
+        return res, host
+    res = {
+        "loss": loss_sum[0].clone(), "x_T": xT.view(B, 2).clone(), "v_T": vT.view(B, 2).clone(),
+        "grad_v0": gv.view(B, 2).clone() if want_grad else None,
+        "grad_x0": gx.view(B, 2).clone() if want_grad else None,
+        "loss_per_ball": lpb.clone(),
+    }
+    return res, host
+
+
+def vmapped_grad_and_value(sim_time, n_steps, scene, coordinate_init, velocity_init, target_coordinate,
+                           attractor, constants, options: RolloutOptions = None):
+    """``vmapped_grad_and_value`` (ball_sim.py:334-338).
+
+    Returns ``((loss, (x_T [B,2], v_T [B,2])), dloss/dvelocity_init [B,2])``.
+    """
+    r, _ = _value_and_grad_raw(sim_time, n_steps, scene, coordinate_init, velocity_init,
+                               target_coordinate, attractor, constants, options or _DEFAULT_OPTIONS, True)
+    return (r["loss"], (r["x_T"], r["v_T"])), r["grad_v0"]
+
+
+def vmapped_loss(sim_time, n_steps, scene, coordinate_init, velocity_init, target_coordinate, attractor,
+                 constants, options: RolloutOptions = None):
+    """``vmapped_loss`` (ball_sim.py:332): ``(loss [B], x_T [B,2], v_T [B,2])``."""
+    r, host = _value_and_grad_raw(sim_time, n_steps, scene, coordinate_init, velocity_init,
+                                  target_coordinate, attractor, constants, options or _DEFAULT_OPTIONS, False)
+    return r["loss_per_ball"], r["x_T"], r["v_T"]
+
+
+def reduce_loss(sim_time, n_steps, scene, coordinate_init, velocity_init, target_coordinate, attractor,
+                constants, options: RolloutOptions = None):
+    """``reduce_loss`` (ball_sim.py:289-324): ``(sum of losses, (x_T, v_T))``."""
+    r, _ = _value_and_grad_raw(sim_time, n_steps, scene, coordinate_init, velocity_init,
+                               target_coordinate, attractor, constants, options or _DEFAULT_OPTIONS, False)
+    return r["loss"], (r["x_T"], r["v_T"])
+
+
+def compute_loss(sim_time, n_steps, scene, coordinate_init, velocity_init, target_coordinate, attractor,
+                 constants, options: RolloutOptions = None):
+    """``compute_loss`` (ball_sim.py:256-286,329), unbatched: ``(loss, x_T [2], v_T [2])``."""
+    r, _ = _value_and_grad_raw(sim_time, n_steps, scene, coordinate_init, velocity_init,
+                               target_coordinate, attractor, constants, options or _DEFAULT_OPTIONS, False)
+    return r["loss_per_ball"][0], r["x_T"][0], r["v_T"][0]
+
+
+# ------------------------------------------------------------------------------------------
+# torch autograd binding (custom_vjp-style pair: fwd saves checkpoints + hit log)
+# ------------------------------------------------------------------------------------------
+class _RolloutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, v0, scene, desc):
+        device = x0.device
+        _, sws = scene.prepared(device)
+        x0c = as_f32_device(x0, device).reshape(-1, 2)
+        v0c = as_f32_device(v0, device).reshape(-1, 2)
+        B = desc.B
+        ws = torch.empty(lib.doper_rollout_workspace_bytes(ctypes.byref(desc)), dtype=torch.uint8, device=device)
+        out = torch.empty((2, B, 2), dtype=torch.float32, device=device)
+        check(lib.doper_rollout_fwd(stream_ptr(), ctypes.byref(desc), ptr(sws), ptr(x0c), ptr(v0c), ptr(out[0]),
+                                    ptr(out[1]), 0, 0, 0, ptr(ws)), "doper_rollout_fwd")
+        ctx.scene, ctx.desc, ctx.ws = scene, desc, ws
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_xT, g_vT):
+        desc, device = ctx.desc, ctx.ws.device
+        _, sws = ctx.scene.prepared(device)
+        B = desc.B
+        gx = torch.zeros((B, 2), dtype=torch.float32, device=device) if g_xT is None else \
+            g_xT.to(torch.float32).contiguous()
+        gv = None if g_vT is None else g_vT.to(torch.float32).contiguous()
+        bar = torch.empty((2, B, 2), dtype=torch.float32, device=device)
+        check(lib.doper_rollout_bwd(stream_ptr(), ctypes.byref(desc), ptr(sws), ptr(ctx.ws), ptr(gx), ptr(gv),
+                                    ptr(bar[0]), ptr(bar[1])), "doper_rollout_bwd")
+        return bar[0], bar[1], None, None
+
+
+def rollout(sim_time, n_steps, scene, coordinate_init: torch.Tensor, velocity_init: torch.Tensor, attractor,
+            constants, options: RolloutOptions = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Differentiable ``(x_T, v_T) = rollout(x0, v0)`` on CUDA tensors (grads w.r.t. both)."""
+    scene = _as_scene(scene)
+    if not (is_device_tensor(coordinate_init) and is_device_tensor(velocity_init)):
+        raise ValueError("rollout() takes CUDA tensors; use vmapped_grad_and_value for host arrays")
+    desc = _make_desc(coordinate_init.reshape(-1, 2).shape[0], scene, sim_time, n_steps, attractor, constants,
+                      options or _DEFAULT_OPTIONS)
+    return _RolloutFn.apply(coordinate_init, velocity_init, scene, desc)
+
+
+def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, attractor, constants,
+                    options: RolloutOptions = None, want_trajectory: bool = False) -> dict:
+    """Forward rollout that also returns the discrete history the backward replays.
+
+    -> dict(x_T, v_T [B,2]; idx int32 [n,B]; hit bool [n,B]; checkpoints [n_ckpt,B,4];
+    trajectory BallState or None), all numpy.  Used by the parity tests (segment indices and
+    hit flags must match the reference bit-exactly) and by debugging tools.
+    """
+    opts = options or _DEFAULT_OPTIONS
+    device = require_cuda()
+    scene = _as_scene(scene)
+    B = _batch_of(coordinate_init)
+    desc = _make_desc(B, scene, sim_time, n_steps, attractor, constants, opts)
+    _, sws = scene.prepared(device)
+    x0 = as_f32_device(coordinate_init, device).reshape(-1, 2)
+    v0 = as_f32_device(velocity_init, device).reshape(-1, 2)
+    n = desc.n_steps
+    K = desc.ckpt_every if desc.ckpt_every > 0 else 32
+    n_ckpt = (n + K - 1) // K
+    ws = torch.zeros(lib.doper_rollout_workspace_bytes(ctypes.byref(desc)), dtype=torch.uint8, device=device)
+    out = torch.empty((2, B, 2), dtype=torch.float32, device=device)
+    traj = torch.empty((3, n, B, 2), dtype=torch.float32, device=device) if want_trajectory else None
+    tp = [ptr(traj[i]) for i in range(3)] if want_trajectory else [0, 0, 0]
+    check(lib.doper_rollout_fwd(stream_ptr(), ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), ptr(out[0]),
+                                ptr(out[1]), tp[0], tp[1], tp[2], ptr(ws)), "doper_rollout_fwd")
+    ck_bytes = n_ckpt * B * 16
+    off = (ck_bytes + 255) // 256 * 256
+    ckpt = ws[:ck_bytes].view(torch.float32).view(n_ckpt, B, 4).cpu().numpy()
+    hl = ws[off:off + n * B * 4].view(torch.int32).view(n, B).cpu().numpy()
+    t = None
+    if want_trajectory:
+        th = traj.cpu().numpy()
+        t = BallState(th[0], th[1], th[2])
+    return {"x_T": out[0].cpu().numpy(), "v_T": out[1].cpu().numpy(), "idx": hl & 0x7FFFFFFF, "hit": hl < 0,
+            "hitlog": hl, "checkpoints": ckpt, "trajectory": t}

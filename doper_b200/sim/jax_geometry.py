@@ -1,0 +1,167 @@
+"""Drop-in mirror of the reference ``doper/sim/jax_geometry.py`` for the hot-path functions.
+
+Same names, positional signatures and return nesting as the reference
+(``jax_geometry.py:8-9`` containers, ``:97-116`` inner check, ``:159-177`` closest segment,
+``:281-305`` scene construction), computed by the sm_100a kernels behind the C ABI.
+Inputs may be numpy arrays / lists (host: results come back as numpy) or torch CUDA tensors
+(device: results stay on the device, zero-copy).  The module keeps the reference's file name
+so that ``from doper.sim.jax_geometry import ...`` call sites only change the package name.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+from typing import List, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _abi
+from .._abi import check, lib
+from .._device import as_f32_device, is_device_tensor, ptr, require_cuda, stream_ptr
+
+__all__ = [
+    "Polygon", "JaxScene", "create_polygon", "create_scene", "create_env_scenes",
+    "find_closest_segment_to_point", "find_closest_segment_to_points_batch",
+    "if_points_inside_any_polygon",
+]
+
+Polygon = namedtuple("Polygon", ["segments"])  # jax_geometry.py:8
+
+
+class JaxScene:
+    """``JaxScene(segments, polygons)`` (jax_geometry.py:9) plus the prepared device scene.
+
+    ``segments`` is ``[S,2,2]`` (shared scene, the reference's only form) or ``[E,S,2,2]``
+    (one scene per environment — an extension, the reference broadcasts the scene,
+    ball_sim.py:332).  The staging layout the kernels read (``doper_scene_prepare``) is built
+    lazily, once per device, and cached on the object.
+    """
+
+    __slots__ = ("segments", "polygons", "_dev")
+
+    def __init__(self, segments, polygons=None):
+        self.segments = segments
+        self.polygons = polygons if polygons is not None else []
+        self._dev = {}
+
+    # namedtuple-style access used by reference code: scene.segments / scene.polygons / unpacking
+    def __iter__(self):
+        yield self.segments
+        yield self.polygons
+
+    def __len__(self):
+        return 2
+
+    def __getitem__(self, i):
+        return (self.segments, self.polygons)[i]
+
+    @property
+    def per_env(self) -> bool:
+        return len(self.segments.shape) == 4
+
+    @property
+    def n_segments(self) -> int:
+        return int(self.segments.shape[-3])
+
+    @property
+    def n_scenes(self) -> int:
+        return int(self.segments.shape[0]) if self.per_env else 1
+
+    def prepared(self, device: torch.device = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(raw segments f32 on device ``[..., S, 4]``, prepared workspace bytes)."""
+        device = device or require_cuda()
+        key = (device.type, device.index)
+        hit = self._dev.get(key)
+        if hit is not None:
+            return hit
+        raw = as_f32_device(self.segments, device)
+        if raw.shape[-2:] != (2, 2) or raw.dim() not in (3, 4):
+            raise ValueError(f"segments must be [S,2,2] or [E,S,2,2], got {tuple(raw.shape)}")
+        S = int(raw.shape[-3])
+        n = int(raw.shape[0]) if raw.dim() == 4 else 1
+        raw = raw.reshape(*raw.shape[:-2], 4).contiguous()
+        nbytes = lib.doper_scene_workspace_bytes(n, S)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        check(lib.doper_scene_prepare(stream_ptr(), n, S, ptr(raw), ptr(ws)), "doper_scene_prepare")
+        self._dev[key] = (raw, ws)
+        return raw, ws
+
+
+def create_polygon(segments) -> Polygon:
+    """jax_geometry.py:281-299."""
+    if isinstance(segments, (np.ndarray, torch.Tensor)):
+        return Polygon(segments=segments)
+    return Polygon(segments=np.asarray(segments, dtype=np.float32))
+
+
+def create_scene(polygons: List[Polygon]) -> JaxScene:
+    """jax_geometry.py:302-305: concatenate the polygons' segments, polygon-major."""
+    segs = [p.segments for p in polygons]
+    if any(isinstance(s, torch.Tensor) for s in segs):
+        cat = torch.cat([torch.as_tensor(s, dtype=torch.float32) for s in segs], dim=0)
+    else:
+        cat = np.concatenate([np.asarray(s, dtype=np.float32) for s in segs], axis=0)
+    return JaxScene(segments=cat, polygons=polygons)
+
+
+def create_env_scenes(segments) -> JaxScene:
+    """Extension: per-environment scenes ``[E,S,2,2]`` (3 segments per CCW triangle each)."""
+    return JaxScene(segments=segments, polygons=None)
+
+
+def _as_scene(segments_or_scene) -> JaxScene:
+    if isinstance(segments_or_scene, JaxScene):
+        return segments_or_scene
+    return JaxScene(segments=segments_or_scene, polygons=None)
+
+
+def _closest(points, segments):
+    device = require_cuda()
+    on_device = is_device_tensor(points)
+    scene = _as_scene(segments)
+    if scene.per_env:
+        raise ValueError("find_closest_segment_*: per-environment scenes are not supported here")
+    raw, ws = scene.prepared(device)
+    pts = as_f32_device(points, device).reshape(-1, 2)
+    N, S = int(pts.shape[0]), scene.n_segments
+    idx = torch.empty(N, dtype=torch.int32, device=device)
+    dist = torch.empty(N, dtype=torch.float32, device=device)
+    seg = torch.empty((N, 2, 2), dtype=torch.float32, device=device)
+    check(lib.doper_closest_segment(stream_ptr(), N, S, ptr(pts), ptr(raw), ptr(ws), ptr(idx), ptr(dist),
+                                    ptr(seg)), "doper_closest_segment")
+    if on_device:
+        return seg, dist, idx
+    return seg.cpu().numpy(), dist.cpu().numpy(), idx.cpu().numpy()
+
+
+def find_closest_segment_to_points_batch(points, segments_batch):
+    """jax_geometry.py:177: ``[N,2] x [S,2,2] -> (closest segments [N,2,2], distances [N])``."""
+    seg, dist, _ = _closest(points, segments_batch)
+    return seg, dist
+
+
+def find_closest_segment_to_point(point, segments_batch):
+    """jax_geometry.py:159-174: ``[2] x [S,2,2] -> (closest segment [2,2], distance scalar)``."""
+    seg, dist, _ = _closest(point, segments_batch)
+    return seg[0], dist[0]
+
+
+def closest_segment_index(points, segments_batch):
+    """Extension: also return ``argmin`` itself (int32 ``[N]``), which the reference discards."""
+    return _closest(points, segments_batch)
+
+
+def if_points_inside_any_polygon(points, scene: JaxScene):
+    """jax_geometry.py:97-116: bool ``[N]``; a 1-D point is treated as a batch of one (:108-109)."""
+    device = require_cuda()
+    on_device = is_device_tensor(points)
+    scene = _as_scene(scene)
+    if scene.per_env:
+        raise ValueError("if_points_inside_any_polygon: per-environment scenes are not supported here")
+    raw, _ = scene.prepared(device)
+    pts = as_f32_device(points, device).reshape(-1, 2)
+    N, S = int(pts.shape[0]), scene.n_segments
+    flag = torch.empty(N, dtype=torch.uint8, device=device)
+    check(lib.doper_points_inside(stream_ptr(), N, S, ptr(pts), ptr(raw), ptr(flag)), "doper_points_inside")
+    out = flag.to(torch.bool)
+    return out if on_device else out.cpu().numpy()

@@ -1,0 +1,142 @@
+/*
+ * doper_b200 — C ABI of the B200-native differentiable ball-rollout path.
+ *
+ * This is the drop-in boundary for the one hot path of VGGVRobotics/doper: the
+ * doper/sim step + rollout and its reverse-mode backward.  Every entry point is
+ * `extern "C"`, takes plain device pointers, sizes and a CUDA stream, returns an
+ * int status (0 = ok), never aborts, never synchronises, allocates nothing and
+ * keeps no global mutable state: the caller owns every buffer including the
+ * workspaces whose sizes the *_bytes() queries return.  All launches go to the
+ * caller's stream; the library is re-entrant (one host thread per GPU is safe).
+ *
+ * Reference interfaces replaced (file:line in the reference tree):
+ *   doper_scene_prepare        create_scene                     doper/sim/jax_geometry.py:302-305
+ *   doper_closest_segment      find_closest_segment_to_point(s_batch)
+ *                                                               doper/sim/jax_geometry.py:159-177
+ *   doper_points_inside        if_points_inside_any_polygon     doper/sim/jax_geometry.py:97-116
+ *   doper_rollout_fwd          run_sim / _run_sim (lax.scan of sim_step)
+ *                                                               doper/sim/ball_sim.py:171-253,327
+ *   doper_l1_loss              _compute_loss / reduce_loss      doper/sim/ball_sim.py:256-324
+ *   doper_rollout_bwd          the VJP of the scan that jax.value_and_grad builds
+ *                                                               doper/sim/ball_sim.py:334-338
+ *   doper_value_and_grad       vmapped_grad_and_value           doper/sim/ball_sim.py:334-338
+ *
+ * Data layout (all float = IEEE binary32, row-major, device memory):
+ *   segments  [S][2][2] = (x0,y0,x1,y1) per segment, polygon-major, 3 per triangle;
+ *             per-environment scenes are [E][S][2][2].
+ *   points / x0 / v0 / xT / vT / cotangents   [B][2]
+ *   trajectory (optional)  traj_x, traj_v, traj_a  [n_steps][B][2]
+ *   hit log   [n_steps][B] int32 : closest segment index | (hit << 31)
+ *   checkpoints [ceil(n_steps/ckpt_every)][B][4] = (x,y,vx,vy) at the START of step k*ckpt_every
+ *   consts    host float[5] = {radius, mass, rolling_friction_coefficient,
+ *             walls_elasticity, attractor_strength}  (reference constants dict,
+ *             doper/sim/ball_sim.py:104,119,127-129,195-200); g = 9.8f is the literal
+ *             default of compute_rolling_friction_force (ball_sim.py:29).
+ *   attractor / target  host float[2].
+ */
+#ifndef DOPER_B200_H
+#define DOPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* doper_stream_t; /* cudaStream_t */
+
+enum {
+    DOPER_OK = 0,
+    DOPER_ERR_BAD_SHAPE = 1,   /* negative / zero / inconsistent sizes */
+    DOPER_ERR_NULL_PTR = 2,    /* a required pointer is NULL */
+    DOPER_ERR_MISALIGNED = 3,  /* pointer not aligned as documented */
+    DOPER_ERR_SMEM_LIMIT = 4,  /* scene does not fit the kernel's shared-memory plan */
+    DOPER_ERR_LAUNCH = 5,      /* cudaPeekAtLastError() != success after launch */
+    DOPER_ERR_WORKSPACE = 6,   /* workspace too small */
+    DOPER_ERR_UNSUPPORTED = 7  /* e.g. S >= 2^31, triangle count mismatch */
+};
+
+#define DOPER_ABI_VERSION 1
+
+int doper_abi_version(void);
+const char* doper_error_string(int code);
+
+/* ---- scene ---------------------------------------------------------------------------- */
+
+/* Bytes of the prepared-scene workspace for n_scenes scenes of S segments each (256-B aligned
+ * device buffer owned by the caller). */
+size_t doper_scene_workspace_bytes(int64_t n_scenes, int32_t S);
+
+/* Pre-digest raw segments into the kernels' staging layout: per segment (s0x,s0y,svx,svy) and
+ * 1/|sv|^2, padded to a multiple of 32 with far-away sentinels, plus a per-scene header (max
+ * |coordinate|, degenerate-segment flag).  Bit-identical to computing sv/L per pair as the
+ * reference does (jax_geometry.py:132-133): both are ball-independent.  n_scenes = 1 for a
+ * shared scene (reference semantics, ball_sim.py:332) or E for per-environment scenes. */
+int doper_scene_prepare(doper_stream_t stream, int64_t n_scenes, int32_t S, const float* segments,
+                        void* scene_ws);
+
+/* ---- geometry queries ----------------------------------------------------------------- */
+
+/* idx[i] = first index attaining min_j dist(points[i], segment j); dist[i] that distance
+ * (NaN distances count as minimal, like argmin). seg_out (nullable) [N][2][2] = segments[idx]. */
+int doper_closest_segment(doper_stream_t stream, int64_t N, int32_t S, const float* points,
+                          const float* segments, const void* scene_ws, int32_t* idx, float* dist,
+                          float* seg_out);
+
+/* flag[i] = 1 iff points[i] is strictly inside any of the S/3 counter-clockwise triangles. */
+int doper_points_inside(doper_stream_t stream, int64_t N, int32_t S, const float* points,
+                        const float* segments, uint8_t* flag);
+
+/* ---- rollout -------------------------------------------------------------------------- */
+
+typedef struct {
+    int64_t B;           /* balls (= environments when per_env) */
+    int32_t S;           /* segments per scene */
+    int32_t per_env;     /* 0: one shared scene; 1: scene b belongs to ball b */
+    int32_t n_steps;     /* rollout length */
+    int32_t ckpt_every;  /* K: checkpoint period in steps (>= 1); 0 = library default */
+    float dt;            /* f32(sim_time / n_steps), rounded on the host (ball_sim.py:237) */
+    float consts[5];     /* radius, mass, friction, elasticity, attractor_strength */
+    float attractor[2];
+    int32_t lanes_per_ball; /* 0 = auto; else 1,2,4,8,16,32 lanes cooperating on one ball's sweep */
+    int32_t flags;          /* bit 0: force the exact (unfiltered) sweep */
+} doper_rollout_desc;
+
+/* Bytes of the backward workspace (checkpoints + hit log) for this rollout. */
+size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d);
+
+/* Forward rollout.  traj_* and ws may be NULL (no trajectory / no backward wanted). */
+int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                      const float* x0, const float* v0, float* xT, float* vT, float* traj_x,
+                      float* traj_v, float* traj_a, void* ws);
+
+/* Backward: cotangents (xT_bar, vT_bar) -> (x0_bar, v0_bar).  vT_bar / x0_bar may be NULL. */
+int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                      const void* ws, const float* xT_bar, const float* vT_bar, float* x0_bar,
+                      float* v0_bar);
+
+/* loss_per_ball[b] = |xT[b].x - t.x| + |xT[b].y - t.y|; *loss_sum = sum_b (deterministic order);
+ * xT_bar[b] = sign(xT[b] - t) (the seed of the backward).  loss_per_ball / xT_bar nullable. */
+int doper_l1_loss(doper_stream_t stream, int64_t B, const float* xT, const float target[2],
+                  float* loss_per_ball, float* loss_sum, float* xT_bar);
+
+/* vmapped_grad_and_value in one call: fwd -> loss -> bwd on `stream`.
+ * scratch: device float[2*B] (holds xT_bar).  x0_bar nullable. */
+int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                         const float* x0, const float* v0, const float target[2], void* ws,
+                         float* scratch, float* loss_sum, float* loss_per_ball, float* xT,
+                         float* vT, float* v0_bar, float* x0_bar);
+
+/* ---- measurement helper --------------------------------------------------------------- */
+
+/* Register-only dependent FADD/FMUL chains (no FMA): every thread executes `iters` x 16
+ * independent-chain ops; out[thread] keeps the result alive.  Used by bench.py to measure the
+ * non-FMA FP32 lane-op rate that bounds a bit-exact sweep. */
+int doper_fp32_probe(doper_stream_t stream, int32_t blocks, int32_t threads, int32_t iters,
+                     int32_t use_fma, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOPER_B200_H */

@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar (BASELINE.json north_star): collision segment indices, hit flags and inside/outside flags
+bit-exact; positions / velocities bit-exact (stronger than the rtol 1e-5 per step asked for);
+loss within rtol 1e-5; end-of-rollout gradients bit-exact against the oracle's C adjoint (same
+operation order) and within 1e-4 (relative to the per-ball gradient norm) of torch autograd.
+"""
+import numpy as np
+import pytest
+import torch
+
+from doper_b200 import synthetic as syn
+from oracle import ball_sim_np as onp
+from oracle import ball_sim_torch as ot
+from tests.helpers import assert_bitexact, grad_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sim():
+    from doper_b200.sim import ball_sim, jax_geometry
+    return ball_sim, jax_geometry
+
+
+def _opts(ball_sim, **kw):
+    return ball_sim.RolloutOptions(**kw)
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("exact", [False, True])
+def test_rollout_forward_bitexact_all_lane_counts(sim, cref, lanes, exact):
+    ball_sim, _ = sim
+    w = syn.make_workload("c2", n_balls=333)  # ragged: not a multiple of any block size
+    n = 300
+    c = onp.make_constants(w["constants"])
+    ref = cref.rollout_fwd(n, np.float32((n / 1000) / n), c, w["attractor"], w["segments"], w["x0"], w["v0"],
+                           want_traj=True)
+    assert ref["hit"].sum() > 30
+    got = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], w["constants"],
+                                   _opts(ball_sim, lanes_per_ball=lanes, force_exact_sweep=exact, ckpt_every=16),
+                                   want_trajectory=True)
+    assert np.array_equal(got["idx"], ref["idx"]), "closest-segment indices"
+    assert np.array_equal(got["hit"], ref["hit"]), "hit flags"
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    assert_bitexact(got["v_T"], ref["v_T"], "v_T")
+    assert_bitexact(got["trajectory"].coordinate, ref["traj_x"], "trajectory x")
+    assert_bitexact(got["trajectory"].velocity, ref["traj_v"], "trajectory v")
+    assert_bitexact(got["trajectory"].acceleration, ref["traj_a"], "trajectory a")
+    # checkpoints are the states at the start of steps 0, K, 2K, ...
+    assert_bitexact(got["checkpoints"][0, :, :2], w["x0"], "ckpt 0")
+    assert_bitexact(got["checkpoints"][1, :, :2], ref["traj_x"][15], "ckpt 1")
+
+
+@pytest.mark.parametrize("n_balls,n_steps,K", [(1, 300, 0), (16, 300, 32), (257, 500, 7), (1024, 130, 64)])
+def test_value_and_grad_vs_oracle(sim, cref, n_balls, n_steps, K):
+    ball_sim, _ = sim
+    w = syn.make_workload("c2", n_balls=n_balls)
+    c = onp.make_constants(w["constants"])
+    ref = cref.value_and_grad(n_steps, np.float32((n_steps / 1000) / n_steps), c, w["attractor"], w["target"],
+                              w["segments"], w["x0"], w["v0"])
+    (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(
+        n_steps / 1000, n_steps, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], w["constants"],
+        _opts(ball_sim, ckpt_every=K))
+    assert isinstance(gv, np.ndarray) and gv.shape == (n_balls, 2)  # host in -> host out
+    assert_bitexact(xT, ref["x_T"], "x_T")
+    assert_bitexact(vT, ref["v_T"], "v_T")
+    ref_loss = ref["loss_per_ball"].sum(dtype=np.float64)
+    assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert_bitexact(gv, ref["grad_v0"], "dL/dv0 vs C adjoint")
+
+
+def test_gradient_vs_torch_autograd(sim):
+    """Independent gradient truth: torch autograd of the select-form graph (fp32)."""
+    ball_sim, _ = sim
+    w = syn.make_workload("c2", n_balls=512)
+    n = 500
+    c = onp.make_constants(w["constants"])
+    (res, aux) = ot.value_and_grad(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], c,
+                                   grad_wrt_x0=True)
+    (loss_ref, (xT_ref, vT_ref)), gv_ref = res
+    x0 = torch.tensor(w["x0"], device="cuda", requires_grad=True)
+    v0 = torch.tensor(w["v0"], device="cuda", requires_grad=True)
+    scene = ball_sim.JaxScene(w["segments"])
+    xT, vT = ball_sim.rollout(n / 1000, n, scene, x0, v0, w["attractor"], w["constants"])
+    loss = (xT - torch.tensor(w["target"], device="cuda")).abs().sum()
+    loss.backward()
+    assert_bitexact(xT.detach().cpu().numpy(), xT_ref, "x_T")
+    finite = np.isfinite(gv_ref).all(axis=1)
+    assert finite.mean() > 0.99
+    e = grad_rel_err(v0.grad.cpu().numpy()[finite], gv_ref[finite])
+    assert e.max() < 1e-4, e.max()
+    ex = grad_rel_err(x0.grad.cpu().numpy()[finite], aux["grad_x0"][finite])
+    assert ex.max() < 1e-4, ex.max()
+    assert abs(loss.item() - loss_ref) <= 1e-5 * abs(loss_ref)
+
+
+def test_device_inputs_stay_on_device(sim, cref):
+    ball_sim, _ = sim
+    w = syn.make_workload("c1")
+    c = onp.make_constants(w["constants"])
+    x0 = torch.tensor(w["x0"], device="cuda")
+    v0 = torch.tensor(w["v0"], device="cuda")
+    (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(0.3, 300, w["segments"], x0, v0, w["target"],
+                                                          w["attractor"], w["constants"])
+    assert gv.is_cuda and xT.is_cuda and loss.is_cuda
+    ref = cref.value_and_grad(300, np.float32(0.3 / 300), c, w["attractor"], w["target"], w["segments"], w["x0"],
+                              w["v0"])
+    assert_bitexact(gv.cpu().numpy(), ref["grad_v0"])
+
+
+def test_run_sim_unbatched_like_reference(sim, cref):
+    """ball_trainer.py:33-46 calls run_sim with a single ball and reads trajectory.coordinate."""
+    ball_sim, _ = sim
+    w = syn.make_workload("c1")
+    c = onp.make_constants(w["constants"])
+    xT, vT, traj = ball_sim.run_sim(0.3, 300, w["segments"], w["x0"][3], w["v0"][3], w["attractor"], w["constants"])
+    assert xT.shape == (2,) and traj.coordinate.shape == (300, 2)
+    ref = cref.rollout_fwd(300, np.float32(0.3 / 300), c, w["attractor"], w["segments"], w["x0"][3:4], w["v0"][3:4],
+                           want_traj=True)
+    assert_bitexact(xT, ref["x_T"][0])
+    assert_bitexact(traj.coordinate, ref["traj_x"][:, 0])
+    assert_bitexact(traj.acceleration, ref["traj_a"][:, 0])
+    l, x2, v2 = ball_sim.compute_loss(0.3, 300, w["segments"], w["x0"][3], w["v0"][3], w["target"], w["attractor"],
+                                      w["constants"])
+    assert_bitexact(x2, xT)
+    assert abs(l - np.abs(xT - w["target"]).sum()) < 1e-5
+
+
+def test_per_env_scenes(sim, cref):
+    ball_sim, geo = sim
+    E, n = 300, 250
+    segs = syn.make_env_maps(11, E, 67)
+    x0, v0 = syn.make_init_states(12, E, segs)
+    c = onp.make_constants(syn.reference_constants())
+    A, T = np.array(syn.REFERENCE_ATTRACTOR, np.float32), np.array(syn.REFERENCE_TARGET, np.float32)
+    ref = cref.value_and_grad(n, np.float32((n / 1000) / n), c, A, T, segs, x0, v0)
+    assert ref["hit"].sum() > 20
+    scene = geo.create_env_scenes(segs)
+    for lanes in (0, 4, 32):
+        h = ball_sim.rollout_history(n / 1000, n, scene, x0, v0, A, syn.reference_constants(),
+                                     _opts(ball_sim, lanes_per_ball=lanes))
+        assert np.array_equal(h["idx"], ref["idx"]) and np.array_equal(h["hit"], ref["hit"])
+        assert_bitexact(h["x_T"], ref["x_T"])
+    (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, scene, x0, v0, T, A, syn.reference_constants())
+    assert_bitexact(gv, ref["grad_v0"])
+
+
+def test_closest_segment_and_inner_check(sim, cref):
+    _, geo = sim
+    segs = syn.make_map(5, 67)
+    rng = np.random.default_rng(2)
+    for N in (1, 37, 5000, 70000):  # exercises every lanes-per-point choice
+        pts = rng.uniform([-13, -1], [13, 21], size=(N, 2)).astype(np.float32)
+        pts[: N // 3] = segs[rng.integers(0, len(segs), N // 3), 0] + np.float32(0.25)  # exact ties
+        i_ref, d_ref = cref.closest_segment(pts, segs)
+        seg, dist, idx = geo.closest_segment_index(pts, segs)
+        assert np.array_equal(idx, i_ref)
+        assert_bitexact(dist, d_ref)
+        assert_bitexact(seg, segs[i_ref])
+        scene = geo.create_scene([geo.create_polygon(segs[i:i + 3]) for i in range(0, len(segs), 3)])
+        inside = geo.if_points_inside_any_polygon(pts, scene)
+        assert np.array_equal(inside, cref.points_inside(pts, segs))
+    s1, d1 = geo.find_closest_segment_to_point(pts[0], segs)
+    assert s1.shape == (2, 2) and d1 == d_ref[0]
+    assert geo.if_points_inside_any_polygon(pts[0], scene).shape == (1,)
+
+
+def test_degenerate_segment_nan_semantics(sim, cref):
+    """A zero-length segment gives 0/0 = NaN, which argmin treats as minimal."""
+    ball_sim, geo = sim
+    segs = syn.make_map(5, 10)
+    segs[4] = segs[4][0]  # collapse segment 4
+    pts = np.random.default_rng(0).uniform(-5, 5, (100, 2)).astype(np.float32)
+    i_ref, d_ref = cref.closest_segment(pts, segs)
+    assert (i_ref == 4).all() and np.isnan(d_ref).all()
+    _, dist, idx = geo.closest_segment_index(pts, segs)
+    assert np.array_equal(idx, i_ref) and np.isnan(dist).all()
+
+
+def test_dense_scene_10k_segments(sim, cref):
+    """C4-shaped scene (10,002 segments, 200 KB staged in shared memory), few balls."""
+    ball_sim, _ = sim
+    w = syn.make_workload("c4", n_balls=96)
+    n = 60
+    c = onp.make_constants(w["constants"])
+    ref = cref.value_and_grad(n, np.float32((n / 1000) / n), c, w["attractor"], w["target"], w["segments"], w["x0"],
+                              w["v0"])
+    h = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], w["constants"])
+    assert np.array_equal(h["idx"], ref["idx"]) and np.array_equal(h["hit"], ref["hit"])
+    assert_bitexact(h["x_T"], ref["x_T"])
+
+
+def test_full_size_c2_properties(sim, cref):
+    """BASELINE configs[1] at full size: parity on a slice + size-independent properties."""
+    ball_sim, _ = sim
+    w = syn.make_workload("c2")
+    n = w["n_steps"]
+    args = (w["sim_time"], n, w["segments"])
+    (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(*args, w["x0"], w["v0"], w["target"], w["attractor"],
+                                                          w["constants"])
+    assert np.isfinite(gv).all() and np.isfinite(xT).all()
+    # (1) batch independence: any slice run alone gives the same bits (balls do not interact)
+    sl = slice(1000, 1100)
+    (l2, (xT2, _)), gv2 = ball_sim.vmapped_grad_and_value(*args, w["x0"][sl], w["v0"][sl], w["target"],
+                                                         w["attractor"], w["constants"])
+    assert_bitexact(xT2, xT[sl])
+    assert_bitexact(gv2, gv[sl])
+    # (2) the slice matches the oracle bit-exactly
+    c = onp.make_constants(w["constants"])
+    ref = cref.value_and_grad(n, np.float32(w["sim_time"] / n), c, w["attractor"], w["target"], w["segments"],
+                              w["x0"][sl], w["v0"][sl])
+    assert_bitexact(xT2, ref["x_T"])
+    assert_bitexact(gv2, ref["grad_v0"])
+    # (3) loss is the sum of per-ball L1 distances
+    assert abs(float(loss) - np.abs(xT - w["target"]).sum(dtype=np.float64)) <= 1e-5 * float(loss)
+    # (4) determinism
+    (_, (xT3, _)), gv3 = ball_sim.vmapped_grad_and_value(*args, w["x0"], w["v0"], w["target"], w["attractor"],
+                                                        w["constants"])
+    assert_bitexact(xT3, xT)
+    assert_bitexact(gv3, gv)
