@@ -174,7 +174,7 @@ def ours(args):
     w["n_steps"], w["sim_time"] = n_steps, n_steps / 1000.0
     S = int(w["segments"].shape[-3])
     opts = ball_sim.RolloutOptions(ckpt_every=args.ckpt_every, lanes_per_ball=args.lanes,
-                                   force_exact_sweep=args.exact)
+                                   force_exact_sweep=args.exact, sequential_backward=args.seq_bwd)
     scene = JaxScene(w["segments"])
     desc = ball_sim._make_desc(B, scene, w["sim_time"], n_steps, w["attractor"], w["constants"], opts)
     _, sws = scene.prepared(device)
@@ -279,7 +279,8 @@ def ours(args):
         fwd_flops = B * n_steps * (24.0 * S + 34.0)  # algorithmic flops of the fwd kernel
         achieved = fwd_flops / (float(fwd_ms.mean()) * 1e-3) / 1e12
         peak = rates[0] / 1e12
-        ws_bytes = (-(-n_steps // (desc.ckpt_every or 32)) * 16 + n_steps * 4) * B  # ckpt + hit log written
+        K_ck = int(lib.doper_rollout_ckpt_every(dref))
+        ws_bytes = (-(-n_steps // K_ck) * 16 + n_steps * 4) * B  # ckpt + hit log written
         traffic = None
         tp = ROOT / "profiles" / "roofline_traffic.json"
         if tp.exists():
@@ -322,7 +323,7 @@ def ours(args):
             "config": {"workload": workload_label(name, B, S, n_steps, bool(w["per_env"])) +
                        (f" per GPU ({world} GPUs, balls sharded, allreduce of 6,603 fp32 per step)" if world > 1 else ""),
                        "l2": "256 MiB buffer rewritten between timed iterations (flush), outside the event pairs",
-                       "lanes_per_ball": int(desc.lanes_per_ball) or "auto", "ckpt_every": desc.ckpt_every or 32,
+                       "lanes_per_ball": int(desc.lanes_per_ball) or "auto", "ckpt_every": int(lib.doper_rollout_ckpt_every(dref)),
                        "sweep": "exact" if args.exact else "filtered+exact"},
             "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 4 * B * 4,
@@ -379,6 +380,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--ckpt-every", type=int, default=0)
     ap.add_argument("--exact", action="store_true", help="force the exact (unfiltered) sweep")
+    ap.add_argument("--seq-bwd", action="store_true", help="force the sequential (oracle-order) backward")
     ap.add_argument("--strong", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -298,6 +298,83 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
     if (p.x0_bar) p.x0_bar[ball] = make_float2(gx, gy);
 }
 
+// Chunk-parallel backward for small batches (few balls cannot fill 148 SMs with one thread per
+// ball): thread (ball, chunk) replays its K-step chunk from the chunk's checkpoint, stashes the
+// states, and pulls the four basis cotangents e_0..e_3 back through the chunk, which yields the
+// chunk's transposed Jacobian M_c = J_t0^T ... J_t1-1^T (4x4; the step adjoint is linear in the
+// cotangent, and the recomputed step internals are shared by the four pulls).  One thread per
+// ball then folds g <- M_c g from the last chunk to the first.  Same mathematics as the
+// sequential kernel, different rounding order (tolerance-checked, not bit-exact).
+struct ChunkGeom { int C_pad; int balls_per_block; };
+
+__global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const BwdParams p, const int C_pad) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* stash = reinterpret_cast<float4*>(smem);                                   // [K][threads]
+    float* mats = reinterpret_cast<float*>(smem + (size_t)p.K * kBwdThreads * sizeof(float4));  // [threads][16]
+    const int tid = threadIdx.x;
+    const int bpb = kBwdThreads / C_pad;
+    const int chunk = tid % C_pad, slot = tid / C_pad;
+    const int64_t ball = (int64_t)blockIdx.x * bpb + slot;
+    const int n_ckpt = (p.n_steps + p.K - 1) / p.K;
+    const bool active = ball < p.B && chunk < n_ckpt;
+    const Consts c = p.c;
+    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
+    if (active) {
+        const float4* q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) +
+                          (p.per_env ? (size_t)ball * L.S_pad : 0);
+        const int t0 = chunk * p.K, t1 = min(p.n_steps, t0 + p.K);
+        float4 s = p.ckpt[(size_t)chunk * p.B + ball];
+        for (int t = t0; t < t1; ++t) {
+            stash[(size_t)(t - t0) * kBwdThreads + tid] = s;
+            if (t + 1 < t1) {
+                const int32_t h = p.hitlog[(size_t)t * p.B + ball];
+                State s1;
+                free_step(s.x, s.y, s.z, s.w, c, s1);
+                if (h < 0) {
+                    State s2;
+                    resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c, s2);
+                    s1 = s2;
+                }
+                s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
+            }
+        }
+        float g[4][4];  // g[k] = pull-back of e_k
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0f : 0.0f;
+        for (int t = t1 - 1; t >= t0; --t) {
+            const float4 st = stash[(size_t)(t - t0) * kBwdThreads + tid];
+            const int32_t h = p.hitlog[(size_t)t * p.B + ball];
+            const float4 seg = __ldg(q + (h & 0x7fffffff));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                step_vjp(st.x, st.y, st.z, st.w, h < 0, seg, c, g[k][0], g[k][1], g[k][2], g[k][3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) mats[(size_t)tid * 16 + k * 4 + r] = g[k][r];
+    }
+    __syncthreads();
+    if (ball < p.B && chunk == 0) {
+        float2 gg = p.xT_bar[ball];
+        float v[4] = {gg.x, gg.y, 0.0f, 0.0f};
+        if (p.vT_bar) { float2 h = p.vT_bar[ball]; v[2] = h.x; v[3] = h.y; }
+        for (int cc = n_ckpt - 1; cc >= 0; --cc) {
+            const float* M = mats + (size_t)(tid + cc) * 16;
+            float o[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                o[r] = (v[0] * M[r] + v[1] * M[4 + r]) + (v[2] * M[8 + r] + v[3] * M[12 + r]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = o[r];
+        }
+        p.v0_bar[ball] = make_float2(v[2], v[3]);
+        if (p.x0_bar) p.x0_bar[ball] = make_float2(v[0], v[1]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // loss
 // ------------------------------------------------------------------------------------------
@@ -463,7 +540,29 @@ Consts make_consts(const doper_rollout_desc* d) {
     return c;
 }
 
-int resolve_K(const doper_rollout_desc* d) { return d->ckpt_every > 0 ? d->ckpt_every : 32; }
+// Backward plan. Small batches use the chunk-parallel kernel (<= 32 chunks per ball, one thread
+// each); large batches have enough balls for one thread per ball and use the sequential kernel
+// (bit-identical to the oracle's adjoint). flags bit 1 forces the sequential kernel.
+constexpr int64_t kChunkedMaxBalls = 32768;
+constexpr int kChunkedMaxK = 96;  // stash of K x 128 float4 + matrices must fit in shared memory
+
+bool chunked_eligible(const doper_rollout_desc* d) {
+    return !(d->flags & 2) && d->B <= kChunkedMaxBalls && d->n_steps >= 64;
+}
+
+int resolve_K(const doper_rollout_desc* d) {
+    if (d->ckpt_every > 0) return d->ckpt_every;
+    if (chunked_eligible(d)) {
+        const int K = (d->n_steps + 31) / 32;
+        if (K <= kChunkedMaxK) return K < 4 ? 4 : K;
+    }
+    return 32;
+}
+
+bool use_chunked(const doper_rollout_desc* d, int K) {
+    const int n_ckpt = (d->n_steps + K - 1) / K;
+    return chunked_eligible(d) && n_ckpt <= 32 && n_ckpt >= 2 && K <= kChunkedMaxK;
+}
 
 int validate_desc(const doper_rollout_desc* d) {
     if (!d) return DOPER_ERR_NULL_PTR;
@@ -590,6 +689,11 @@ int doper_points_inside(doper_stream_t stream, int64_t N, int32_t S, const float
     return launch_status();
 }
 
+int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d) {
+    if (validate_desc(d) != DOPER_OK) return 0;
+    return resolve_K(d);
+}
+
 size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d) {
     if (validate_desc(d) != DOPER_OK) return 0;
     const int K = resolve_K(d);
@@ -651,12 +755,6 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         (vT_bar && !aligned(vT_bar, 8)) || (x0_bar && !aligned(x0_bar, 8)))
         return DOPER_ERR_MISALIGNED;
     const int K = resolve_K(d);
-    const size_t smem = (size_t)K * kBwdThreads * sizeof(float4);
-    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(rollout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
-        return DOPER_ERR_SMEM_LIMIT;
     BwdParams p;
     p.B = d->B; p.S = d->S; p.per_env = d->per_env ? 1 : 0; p.n_steps = d->n_steps; p.K = K;
     p.c = make_consts(d);
@@ -669,6 +767,27 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     p.vT_bar = reinterpret_cast<const float2*>(vT_bar);
     p.x0_bar = reinterpret_cast<float2*>(x0_bar);
     p.v0_bar = reinterpret_cast<float2*>(v0_bar);
+    if (d->n_steps == 0) return DOPER_ERR_BAD_SHAPE;
+    if (use_chunked(d, K)) {
+        int C_pad = 2;
+        while (C_pad < (int)n_ckpt) C_pad *= 2;
+        const size_t smem = (size_t)K * kBwdThreads * sizeof(float4) + (size_t)kBwdThreads * 16 * sizeof(float);
+        if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(rollout_bwd_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return DOPER_ERR_SMEM_LIMIT;
+        const int bpb = kBwdThreads / C_pad;
+        const unsigned grid = (unsigned)((d->B + bpb - 1) / bpb);
+        rollout_bwd_chunked_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(p, C_pad);
+        return launch_status();
+    }
+    const size_t smem = (size_t)K * kBwdThreads * sizeof(float4);
+    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(rollout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+        return DOPER_ERR_SMEM_LIMIT;
     const unsigned grid = (unsigned)((d->B + kBwdThreads - 1) / kBwdThreads);
     rollout_bwd_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(p);
     return launch_status();

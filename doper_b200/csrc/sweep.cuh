@@ -76,14 +76,104 @@ __device__ __forceinline__ unsigned long long lane_exact(const SceneView& sc, fl
     return kNoKey;
 }
 
-// Group-cooperative sweep. Every lane of the warp must call this (full-mask shuffles); lanes of
-// one group pass the same point. `prev_idx` is a hint (last step's winner), never trusted.
+// ---------------------------------------------------------------------------------------
+// filtered sweep
+// ---------------------------------------------------------------------------------------
+// Estimate of the squared distance: same formula, FMA-contracted, reciprocal instead of the
+// division, saturate instead of clip. 9 FP32 instructions.
+__device__ __forceinline__ float approx_d2(float px, float py, const float4& q, float rl) {
+    float pvx = px - q.x, pvy = py - q.y;
+    float dot = __fmaf_rn(pvx, q.z, pvy * q.w);
+    float t = __saturatef(dot * rl);
+    float ex = __fmaf_rn(-t, q.z, pvx), ey = __fmaf_rn(-t, q.w, pvy);
+    return __fmaf_rn(ex, ex, ey * ey);
+}
+
+// Error model: for a non-degenerate scene and a finite point with
+// M = max(|coordinate|) over scene and point, both |sqrt(estimate) - D| and |d_ref - D| are
+// bounded by 49 u M and 38 u M (u = 2^-24, D the real-arithmetic distance), so
+// |sqrt(a_i) - d_ref_i| <= delta = 128 u M (measured worst case: 7.3 u M, tools/filter_margin_check.py).
+// The winner i* of the reference argmin therefore satisfies, for ANY j,
+//   a_i* <= (sqrt(a_j) + 2 delta)^2 <= a_j (1 + eps) + 4 delta^2 (1 + 1/eps)      (AM-GM)
+// and every segment passing that test against the running minimum estimate is kept as a
+// candidate; candidates get the reference arithmetic and the lexicographic (distance, index) min.
+constexpr float kFilterOneEps = 1.0f + 0.0078125f;            // eps = 2^-7
+constexpr float kFilterKappaPerM2 = 4.0f * 129.0f * 1.02f *   // 4 (1 + 1/eps), 2 % slack for the
+                                    (7.62939453125e-6f * 7.62939453125e-6f);  // roundings; (128 u)^2
+constexpr int kMaxCand = 8;
+
+template <int G>
+__device__ __forceinline__ unsigned long long lane_filtered(const SceneView& sc, float px, float py,
+                                                            int lane, int prev_idx, float kappa) {
+    // hint: last step's winner bounds the minimum estimate from above (any index is valid)
+    float m = approx_d2(px, py, sc.q[prev_idx], sc.rl[prev_idx]);
+    float thr = __fmaf_rn(m, kFilterOneEps, kappa);
+    int cand[kMaxCand];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxCand; ++k) cand[k] = 0;
+
+    auto keep = [&](int i, float a) {
+        if (a <= thr) {
+#pragma unroll
+            for (int k = kMaxCand - 1; k > 0; --k) cand[k] = cand[k - 1];
+            cand[0] = i;
+            ++cnt;
+            if (a < m) { m = a; thr = __fmaf_rn(m, kFilterOneEps, kappa); }
+        }
+    };
+    int i = lane;
+    // four independent estimates per trip, ONE (rarely taken) branch for the four of them
+    for (; i + 3 * G < sc.S_pad; i += 4 * G) {
+        const float a0 = approx_d2(px, py, sc.q[i], sc.rl[i]);
+        const float a1 = approx_d2(px, py, sc.q[i + G], sc.rl[i + G]);
+        const float a2 = approx_d2(px, py, sc.q[i + 2 * G], sc.rl[i + 2 * G]);
+        const float a3 = approx_d2(px, py, sc.q[i + 3 * G], sc.rl[i + 3 * G]);
+        if (fminf(fminf(a0, a1), fminf(a2, a3)) <= thr) {
+            keep(i, a0); keep(i + G, a1); keep(i + 2 * G, a2); keep(i + 3 * G, a3);
+        }
+    }
+    for (; i < sc.S_pad; i += G) keep(i, approx_d2(px, py, sc.q[i], sc.rl[i]));
+
+    if (cnt > kMaxCand) return lane_exact<G>(sc, px, py, lane);  // list overflowed: rare
+    unsigned long long key = kNoKey;
+#pragma unroll
+    for (int k = 0; k < kMaxCand; ++k) {
+        if (k < cnt) {
+            const int j = cand[k];
+            const float d = sqrtf(seg_dist2(px, py, sc.q[j]));
+            const unsigned long long kk = make_key(d, j);
+            key = kk < key ? kk : key;
+        }
+    }
+    return key;
+}
+
+// min over the G lanes of a group: two REDUX (distance bits, then index among the minima).
+template <int G>
+__device__ __forceinline__ unsigned long long group_min_redux(unsigned long long key) {
+    if (G == 1) return key;
+    const unsigned lane_id = threadIdx.x & 31u;
+    const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane_id & ~(unsigned)(G - 1)));
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned hmin = __reduce_min_sync(mask, hi);
+    const unsigned lmin = __reduce_min_sync(mask, hi == hmin ? lo : 0xffffffffu);
+    return ((unsigned long long)hmin << 32) | lmin;
+}
+
+// Group-cooperative sweep. Every lane of the warp must call this (warp-wide sync primitives);
+// lanes of one group pass the same point. `prev_idx` (in [0,S)) is a hint, never trusted.
 template <int G>
 __device__ __forceinline__ void sweep_any(const SceneView& sc, float px, float py, int lane,
                                           int prev_idx, int& idx, float& dist) {
-    (void)prev_idx;
-    unsigned long long key = lane_exact<G>(sc, px, py, lane);
-    key = group_min<G>(key);
+    const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)));
+    unsigned long long key;
+    if (!sc.weird && M <= 1.0e15f) {  // false for NaN / inf points
+        key = lane_filtered<G>(sc, px, py, lane, prev_idx, kFilterKappaPerM2 * M * M);
+    } else {
+        key = lane_exact<G>(sc, px, py, lane);
+    }
+    key = group_min_redux<G>(key);
     unpack_key(key, idx, dist);
 }
 

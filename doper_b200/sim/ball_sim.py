@@ -37,10 +37,12 @@ _CONST_KEYS = ("radius", "mass", "rolling_friction_coefficient", "walls_elastici
 class RolloutOptions:
     """Tuning knobs that do not change results."""
 
-    def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False):
+    def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False,
+                 sequential_backward: bool = False):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
-        self.force_exact_sweep = bool(force_exact_sweep)
+        self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
+        self.sequential_backward = bool(sequential_backward)  # oracle-order adjoint (bit-exact)
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -78,7 +80,7 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
                    dtype=np.float32).reshape(2)
     d.attractor[0], d.attractor[1] = a[0], a[1]
     d.lanes_per_ball = opts.lanes_per_ball
-    d.flags = 1 if opts.force_exact_sweep else 0
+    d.flags = (1 if opts.force_exact_sweep else 0) | (2 if opts.sequential_backward else 0)
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d
@@ -106,7 +108,7 @@ class _Buffers:
 
     @classmethod
     def get(cls, device, desc: RolloutDesc) -> "_Buffers":
-        key = (device.index, desc.B, desc.S, desc.per_env, desc.n_steps, desc.ckpt_every)
+        key = (device.index, desc.B, desc.S, desc.per_env, desc.n_steps, desc.ckpt_every, desc.flags)
         b = cls._cache.get(key)
         if b is None:
             if len(cls._cache) > 8:
@@ -317,7 +319,7 @@ def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, at
     x0 = as_f32_device(coordinate_init, device).reshape(-1, 2)
     v0 = as_f32_device(velocity_init, device).reshape(-1, 2)
     n = desc.n_steps
-    K = desc.ckpt_every if desc.ckpt_every > 0 else 32
+    K = int(lib.doper_rollout_ckpt_every(ctypes.byref(desc)))
     n_ckpt = (n + K - 1) // K
     ws = torch.zeros(lib.doper_rollout_workspace_bytes(ctypes.byref(desc)), dtype=torch.uint8, device=device)
     out = torch.empty((2, B, 2), dtype=torch.float32, device=device)

@@ -100,8 +100,13 @@ typedef struct {
     float consts[5];     /* radius, mass, friction, elasticity, attractor_strength */
     float attractor[2];
     int32_t lanes_per_ball; /* 0 = auto; else 1,2,4,8,16,32 lanes cooperating on one ball's sweep */
-    int32_t flags;          /* bit 0: force the exact (unfiltered) sweep */
+    int32_t flags;          /* bit 0: force the exact (unfiltered) sweep;
+                               bit 1: force the sequential (oracle-order, bit-exact) backward */
 } doper_rollout_desc;
+
+/* The checkpoint period the library will use for this rollout (ckpt_every if > 0, else chosen
+ * from B and n_steps: small batches get <= 32 chunks per ball for the chunk-parallel backward). */
+int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d);
 
 /* Bytes of the backward workspace (checkpoints + hit log) for this rollout. */
 size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d);
