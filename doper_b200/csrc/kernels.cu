@@ -206,28 +206,141 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_kernel(const FwdParam
 
     mbar_wait(bar, 0);
 
-    int prev_idx = 0;
+    int prev_idx = -1;  // no hint at the first step
+    int32_t* hl = p.hitlog ? p.hitlog + ball : nullptr;
+    float4* ck = p.ckpt ? p.ckpt + ball : nullptr;
+    float2* tx = p.traj_x ? p.traj_x + ball : nullptr;
+    float2* tv = p.traj_v ? p.traj_v + ball : nullptr;
+    float2* ta = p.traj_a ? p.traj_a + ball : nullptr;
+    int until_ckpt = 0;
     for (int t = 0; t < p.n_steps; ++t) {
-        if (writer && p.ckpt && (t % p.K) == 0)
-            p.ckpt[(size_t)(t / p.K) * p.B + ball] = make_float4(x, y, vx, vy);
+        if (until_ckpt == 0) {
+            until_ckpt = p.K;
+            if (writer && ck) { *ck = make_float4(x, y, vx, vy); ck += p.B; }
+        }
+        --until_ckpt;
         State s1;
         free_step(x, y, vx, vy, c, s1);
         int idx; float dist;
         sweep_any<G>(sc, s1.x, s1.y, lane, prev_idx, idx, dist);
         prev_idx = idx;
         const bool hit = dist <= c.r;  // NaN -> false (ball_sim.py:164)
-        if (hit) {
-            State s2;
-            resolve(x, y, vx, vy, s1, sc.q[idx], c, s2);
-            s1 = s2;
-        }
+        if (hit) s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c);
         x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
         if (writer) {
-            const size_t o = (size_t)t * p.B + ball;
-            if (p.hitlog) p.hitlog[o] = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31));
-            if (p.traj_x) p.traj_x[o] = make_float2(x, y);
-            if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
-            if (p.traj_a) p.traj_a[o] = make_float2(s1.ax, s1.ay);
+            if (hl) { *hl = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31)); hl += p.B; }
+            if (tx) { *tx = make_float2(x, y); tx += p.B; }
+            if (tv) { *tv = make_float2(vx, vy); tv += p.B; }
+            if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += p.B; }
+        }
+    }
+    if (writer) {
+        p.xT[ball] = make_float2(x, y);
+        p.vT[ball] = make_float2(vx, vy);
+    }
+}
+
+// Small scenes (S_pad <= 256): every lane keeps ITS OWN segments (indices lane, lane+G, ...) in
+// registers for the whole rollout, so the estimate loop is straight-line code with no loads at
+// all (NV = S_pad / G visits, fully unrolled, candidates recorded in one 32-bit mask). The few
+// reference-arithmetic evaluations (hint, candidates, collision) read the prepared scene through
+// the read-only L1 path. Same results as rollout_fwd_kernel, by the same argument.
+// Register budget per G so that a 4,096-ball batch is co-resident in ONE wave (a second wave of a
+// whole-rollout kernel doubles the time): blocks/SM = 2, 4, 7 for G = 8, 16, 32.
+template <int G, int NV>
+__global__ void __launch_bounds__(kFwdThreads, (G == 8 ? 2 : (G == 16 ? 4 : 7)))
+rollout_fwd_reg_kernel(const FwdParams p) {
+    constexpr int BPB = kFwdThreads / G;
+    const int tid = threadIdx.x, lane = tid % G, slot = tid / G;
+    int64_t ball = (int64_t)blockIdx.x * BPB + slot;
+    const bool active = ball < p.B;
+    if (!active) ball = p.B - 1;  // duplicate the last ball: keeps every lane in the warp-wide REDUX
+    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
+    const int64_t scene_id = p.per_env ? ball : 0;
+    const float4* __restrict__ gq = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) + scene_id * L.S_pad;
+    const float* __restrict__ grl = reinterpret_cast<const float*>(p.scene_ws + L.rl_off) + scene_id * L.S_pad;
+    const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off)[scene_id];
+    SceneView sc;
+    sc.q = gq; sc.rl = grl; sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale;
+    sc.weird = hdr.weird | p.force_exact;
+
+    float4 q[NV];
+    float rl[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        q[j] = __ldg(gq + lane + j * G);
+        rl[j] = __ldg(grl + lane + j * G);
+    }
+
+    const float2 xx = p.x0[ball], vv = p.v0[ball];
+    float x = xx.x, y = xx.y, vx = vv.x, vy = vv.y;
+    const Consts c = p.c;
+    const bool writer = active && lane == 0;
+    int32_t* hl = p.hitlog ? p.hitlog + ball : nullptr;
+    float4* ck = p.ckpt ? p.ckpt + ball : nullptr;
+    float2* tx = p.traj_x ? p.traj_x + ball : nullptr;
+    float2* tv = p.traj_v ? p.traj_v + ball : nullptr;
+    float2* ta = p.traj_a ? p.traj_a + ball : nullptr;
+    int prev_idx = 0, until_ckpt = 0;
+    const int64_t stride = p.B;
+    if (!sc.weird) {  // hint for the first step: smallest estimate at the initial position (any index is valid)
+        float best = __int_as_float(0x7f800000);
+        int bj = 0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float a = approx_d2(x, y, q[j], rl[j]);
+            if (a < best) { best = a; bj = j; }
+        }
+        const unsigned long long k =
+            group_min_redux<G>(((unsigned long long)__float_as_uint(best) << 32) | (unsigned)(lane + bj * G));
+        const int h = (int)(unsigned)(k & 0xffffffffull);
+        prev_idx = (h >= 0 && h < p.S) ? h : 0;
+    }
+
+    for (int t = 0; t < p.n_steps; ++t) {
+        if (until_ckpt == 0) {
+            until_ckpt = p.K;
+            if (writer && ck) { *ck = make_float4(x, y, vx, vy); ck += stride; }
+        }
+        --until_ckpt;
+        State s1;
+        free_step(x, y, vx, vy, c, s1);
+        const float px = s1.x, py = s1.y;
+        const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)));
+        unsigned long long key;
+        if (!sc.weird && M <= 1.0e15f) {
+            const float kappa = kFilterKappaPerM2 * M * M;
+            const float thr = __fmaf_rn(approx_d2(px, py, __ldg(gq + prev_idx), __ldg(grl + prev_idx)),
+                                        kFilterOneEps, kappa);
+            unsigned mask = 0u;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const float a = approx_d2(px, py, q[j], rl[j]);
+                mask |= (a <= thr) ? (1u << j) : 0u;
+            }
+            key = kNoKey;
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const int cidx = lane + j * G;
+                const unsigned long long kk = make_key(cand_dist(px, py, __ldg(gq + cidx)), cidx);
+                key = kk < key ? kk : key;
+            }
+        } else {
+            key = lane_exact<G>(sc, px, py, lane);
+        }
+        key = group_min_redux<G>(key);
+        int idx; float dist;
+        unpack_key(key, idx, dist);
+        prev_idx = idx;
+        const bool hit = dist <= c.r;  // NaN -> false (ball_sim.py:164)
+        if (hit) s1 = resolve(x, y, vx, vy, s1, __ldg(gq + idx), c);
+        x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
+        if (writer) {
+            if (hl) { *hl = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31)); hl += stride; }
+            if (tx) { *tx = make_float2(x, y); tx += stride; }
+            if (tv) { *tv = make_float2(vx, vy); tv += stride; }
+            if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += stride; }
         }
     }
     if (writer) {
@@ -279,11 +392,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
                 const int32_t h = p.hitlog[(size_t)t * p.B + ball];
                 State s1;
                 free_step(s.x, s.y, s.z, s.w, c, s1);
-                if (h < 0) {
-                    State s2;
-                    resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c, s2);
-                    s1 = s2;
-                }
+                if (h < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c);
                 s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
             }
         }
@@ -330,11 +439,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const 
                 const int32_t h = p.hitlog[(size_t)t * p.B + ball];
                 State s1;
                 free_step(s.x, s.y, s.z, s.w, c, s1);
-                if (h < 0) {
-                    State s2;
-                    resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c, s2);
-                    s1 = s2;
-                }
+                if (h < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c);
                 s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
             }
         }
@@ -438,7 +543,7 @@ __global__ void __launch_bounds__(kQueryThreads) closest_segment_kernel(
     const float2 p = pts[i];
     mbar_wait(bar, 0);
     int idx; float dist;
-    sweep_any<G>(sc, p.x, p.y, lane, 0, idx, dist);
+    sweep_any<G>(sc, p.x, p.y, lane, -1, idx, dist);
     if (active && lane == 0) {
         idx_out[i] = idx;
         dist_out[i] = dist;
@@ -537,6 +642,13 @@ Consts make_consts(const doper_rollout_desc* d) {
     c.r = d->consts[0]; c.m = d->consts[1]; c.f = d->consts[2]; c.e = d->consts[3]; c.ks = d->consts[4];
     c.ax = d->attractor[0]; c.ay = d->attractor[1];
     c.dt = d->dt;
+    // div_invariant(): fast path only for well-scaled divisors (then y = RN(1/b) is normal and the
+    // residuals stay normal for |a| in [1e-18, 1e18]); otherwise an empty range = always a / b
+    const bool ok = c.r >= 1e-6f && c.r <= 1e6f && c.m >= 1e-6f && c.m <= 1e6f;
+    c.rcp_r = 1.0f / c.r;
+    c.rcp_m = 1.0f / c.m;
+    c.div_lo = ok ? 1e-18f : 1.0f;
+    c.div_hi = ok ? 1e18f : 0.0f;
     return c;
 }
 
@@ -587,6 +699,29 @@ size_t fwd_smem_bytes(const doper_rollout_desc* d, int G) {
     const SceneLayout L = scene_layout(1, d->S);
     const size_t n_local = d->per_env ? (size_t)(kFwdThreads / G) : 1;
     return n_local * L.S_pad * 20 + 16;
+}
+
+template <int G, int NV>
+int launch_fwd_reg(cudaStream_t st, const FwdParams& p) {
+    const int bpb = kFwdThreads / G;
+    const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
+    rollout_fwd_reg_kernel<G, NV><<<grid, kFwdThreads, 0, st>>>(p);
+    return launch_status();
+}
+
+// register-resident scene: S_pad in {32,...,256}, G in {8,16,32}, NV = S_pad / G
+template <int G>
+int dispatch_fwd_reg(cudaStream_t st, const FwdParams& p, int S_pad) {
+    switch (S_pad / 32) {
+        case 1: return launch_fwd_reg<G, 32 / G>(st, p);
+        case 2: return launch_fwd_reg<G, 64 / G>(st, p);
+        case 3: return launch_fwd_reg<G, 96 / G>(st, p);
+        case 4: return launch_fwd_reg<G, 128 / G>(st, p);
+        case 5: return launch_fwd_reg<G, 160 / G>(st, p);
+        case 6: return launch_fwd_reg<G, 192 / G>(st, p);
+        case 7: return launch_fwd_reg<G, 224 / G>(st, p);
+        default: return launch_fwd_reg<G, 256 / G>(st, p);
+    }
 }
 
 template <int G>
@@ -735,6 +870,14 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         p.hitlog = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(ws) + off);
     }
     cudaStream_t st = (cudaStream_t)stream;
+    const int S_pad = scene_layout(1, d->S).S_pad;
+    if (S_pad <= 256 && G >= 8 && !(d->flags & 4)) {  // flags bit 2: force the shared-memory kernel
+        switch (G) {
+            case 8: return dispatch_fwd_reg<8>(st, p, S_pad);
+            case 16: return dispatch_fwd_reg<16>(st, p, S_pad);
+            default: return dispatch_fwd_reg<32>(st, p, S_pad);
+        }
+    }
     switch (G) {
         case 1: return launch_fwd<1>(st, p, smem);
         case 2: return launch_fwd<2>(st, p, smem);

@@ -56,7 +56,7 @@ __device__ __forceinline__ void unpack_key(unsigned long long key, int& idx, flo
 // index keeps a tie) and d2 < best_d2 needs the sqrt'd compare to keep the earlier index when the
 // two sqrt's round to the same value.
 template <int G>
-__device__ __forceinline__ unsigned long long lane_exact(const SceneView& sc, float px, float py,
+__device__ __noinline__ unsigned long long lane_exact(const SceneView& sc, float px, float py,
                                                          int lane) {
     float best_d2 = __int_as_float(0x7f800000), best_d = best_d2;
     int best_i = 0x7fffffff, nan_i = 0x7fffffff;
@@ -100,75 +100,108 @@ __device__ __forceinline__ float approx_d2(float px, float py, const float4& q, 
 constexpr float kFilterOneEps = 1.0f + 0.0078125f;            // eps = 2^-7
 constexpr float kFilterKappaPerM2 = 4.0f * 129.0f * 1.02f *   // 4 (1 + 1/eps), 2 % slack for the
                                     (7.62939453125e-6f * 7.62939453125e-6f);  // roundings; (128 u)^2
-constexpr int kMaxCand = 8;
 
+// Reference distance of ONE candidate. The division is skipped exactly when the clip decides
+// alone: dot <= 0 -> t = 0 and dot >= L -> t = 1 (L > 0 finite on this path; RN is monotone).
+__device__ __forceinline__ float cand_dist(float px, float py, const float4& q) {
+    const float L = q.z * q.z + q.w * q.w;
+    const float pvx = px - q.x, pvy = py - q.y;
+    const float dot = pvx * q.z + pvy * q.w;
+    float t = 0.0f;
+    if (dot > 0.0f) t = (dot >= L) ? 1.0f : dot / L;
+    const float cx = q.x + t * q.z, cy = q.y + t * q.w;
+    const float dx = px - cx, dy = py - cy;
+    return sqrtf(dx * dx + dy * dy);
+}
+
+// One lane's share of the filtered sweep: branch-free estimate loop that records candidates as
+// bits (bit j = j-th segment this lane visited since `base`), then the reference arithmetic for
+// the set bits.  The threshold is fixed for the whole sweep: thr = U(estimate of last step's
+// winner); the ball moves < radius per step, so that winner is almost always still within a
+// hair of the minimum and the candidate set is the true winner plus its exact ties.
 template <int G>
 __device__ __forceinline__ unsigned long long lane_filtered(const SceneView& sc, float px, float py,
                                                             int lane, int prev_idx, float kappa) {
-    // hint: last step's winner bounds the minimum estimate from above (any index is valid)
-    float m = approx_d2(px, py, sc.q[prev_idx], sc.rl[prev_idx]);
-    float thr = __fmaf_rn(m, kFilterOneEps, kappa);
-    int cand[kMaxCand];
-    int cnt = 0;
-#pragma unroll
-    for (int k = 0; k < kMaxCand; ++k) cand[k] = 0;
-
-    auto keep = [&](int i, float a) {
-        if (a <= thr) {
-#pragma unroll
-            for (int k = kMaxCand - 1; k > 0; --k) cand[k] = cand[k - 1];
-            cand[0] = i;
-            ++cnt;
-            if (a < m) { m = a; thr = __fmaf_rn(m, kFilterOneEps, kappa); }
+    const float thr = __fmaf_rn(approx_d2(px, py, sc.q[prev_idx], sc.rl[prev_idx]), kFilterOneEps, kappa);
+    unsigned long long key = kNoKey;
+    unsigned mask = 0u, bit = 1u;
+    int base = lane, i = lane;
+    auto flush = [&]() {
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const int c = base + j * G;
+            const unsigned long long kk = make_key(cand_dist(px, py, sc.q[c]), c);
+            key = kk < key ? kk : key;
         }
     };
-    int i = lane;
-    // four independent estimates per trip, ONE (rarely taken) branch for the four of them
     for (; i + 3 * G < sc.S_pad; i += 4 * G) {
         const float a0 = approx_d2(px, py, sc.q[i], sc.rl[i]);
         const float a1 = approx_d2(px, py, sc.q[i + G], sc.rl[i + G]);
         const float a2 = approx_d2(px, py, sc.q[i + 2 * G], sc.rl[i + 2 * G]);
         const float a3 = approx_d2(px, py, sc.q[i + 3 * G], sc.rl[i + 3 * G]);
-        if (fminf(fminf(a0, a1), fminf(a2, a3)) <= thr) {
-            keep(i, a0); keep(i + G, a1); keep(i + 2 * G, a2); keep(i + 3 * G, a3);
+        mask |= (a0 <= thr ? bit : 0u) | (a1 <= thr ? bit << 1 : 0u) | (a2 <= thr ? bit << 2 : 0u) |
+                (a3 <= thr ? bit << 3 : 0u);
+        bit <<= 4;
+        if (bit == 0u) {  // 32 visits recorded: evaluate them, start a new window
+            flush();
+            base = i + 4 * G;
+            bit = 1u;
         }
     }
-    for (; i < sc.S_pad; i += G) keep(i, approx_d2(px, py, sc.q[i], sc.rl[i]));
-
-    if (cnt > kMaxCand) return lane_exact<G>(sc, px, py, lane);  // list overflowed: rare
-    unsigned long long key = kNoKey;
-#pragma unroll
-    for (int k = 0; k < kMaxCand; ++k) {
-        if (k < cnt) {
-            const int j = cand[k];
-            const float d = sqrtf(seg_dist2(px, py, sc.q[j]));
-            const unsigned long long kk = make_key(d, j);
-            key = kk < key ? kk : key;
-        }
+    for (; i < sc.S_pad; i += G) {  // at most 3 visits: the window cannot overflow here
+        const float a = approx_d2(px, py, sc.q[i], sc.rl[i]);
+        mask |= (a <= thr) ? bit : 0u;
+        bit <<= 1;
     }
+    flush();
     return key;
 }
 
-// min over the G lanes of a group: two REDUX (distance bits, then index among the minima).
+// min over the G lanes of a group.  A full warp uses two REDUX (distance bits, then index among
+// the minima); sub-warp groups use a shuffle butterfly (REDUX with per-group masks is serialised
+// over the distinct masks of the warp: measured 4x slower at G = 8).
 template <int G>
 __device__ __forceinline__ unsigned long long group_min_redux(unsigned long long key) {
     if (G == 1) return key;
-    const unsigned lane_id = threadIdx.x & 31u;
-    const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane_id & ~(unsigned)(G - 1)));
-    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-    const unsigned hmin = __reduce_min_sync(mask, hi);
-    const unsigned lmin = __reduce_min_sync(mask, hi == hmin ? lo : 0xffffffffu);
-    return ((unsigned long long)hmin << 32) | lmin;
+    if (G == 32) {
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned hmin = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned lmin = __reduce_min_sync(0xffffffffu, hi == hmin ? lo : 0xffffffffu);
+        return ((unsigned long long)hmin << 32) | lmin;
+    }
+    return group_min<G>(key);
+}
+
+// No temporal hint (first step, one-shot queries): a branch-free pre-pass finds the segment with
+// the smallest estimate; it only seeds the threshold, so any index would be correct.
+template <int G>
+__device__ __forceinline__ int hint_by_estimate(const SceneView& sc, float px, float py, int lane) {
+    float best = __int_as_float(0x7f800000);
+    int bi = 0;
+    for (int i = lane; i < sc.S_pad; i += G) {
+        const float a = approx_d2(px, py, sc.q[i], sc.rl[i]);
+        if (a < best) { best = a; bi = i; }
+    }
+    const unsigned long long k = group_min_redux<G>(((unsigned long long)__float_as_uint(best) << 32) | (unsigned)bi);
+    const int h = (int)(unsigned)(k & 0xffffffffull);
+    return h < sc.S ? h : 0;
 }
 
 // Group-cooperative sweep. Every lane of the warp must call this (warp-wide sync primitives);
-// lanes of one group pass the same point. `prev_idx` (in [0,S)) is a hint, never trusted.
+// lanes of one group pass the same point. `prev_idx` in [0,S) is a hint (never trusted); < 0 =
+// no hint available.
 template <int G>
 __device__ __forceinline__ void sweep_any(const SceneView& sc, float px, float py, int lane,
                                           int prev_idx, int& idx, float& dist) {
     const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)));
+    const bool fast = !sc.weird && M <= 1.0e15f;  // false for NaN / inf points
+    if (prev_idx < 0) {                           // uniform across the warp (step counter / query)
+        const int h = hint_by_estimate<G>(sc, fast ? px : 0.0f, fast ? py : 0.0f, lane);
+        prev_idx = h;
+    }
     unsigned long long key;
-    if (!sc.weird && M <= 1.0e15f) {  // false for NaN / inf points
+    if (fast) {
         key = lane_filtered<G>(sc, px, py, lane, prev_idx, kFilterKappaPerM2 * M * M);
     } else {
         key = lane_exact<G>(sc, px, py, lane);

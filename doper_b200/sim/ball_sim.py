@@ -38,11 +38,12 @@ class RolloutOptions:
     """Tuning knobs that do not change results."""
 
     def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False,
-                 sequential_backward: bool = False):
+                 sequential_backward: bool = False, smem_forward: bool = False):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
         self.sequential_backward = bool(sequential_backward)  # oracle-order adjoint (bit-exact)
+        self.smem_forward = bool(smem_forward)  # TMA/shared-memory forward even for small scenes
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -80,7 +81,8 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
                    dtype=np.float32).reshape(2)
     d.attractor[0], d.attractor[1] = a[0], a[1]
     d.lanes_per_ball = opts.lanes_per_ball
-    d.flags = (1 if opts.force_exact_sweep else 0) | (2 if opts.sequential_backward else 0)
+    d.flags = ((1 if opts.force_exact_sweep else 0) | (2 if opts.sequential_backward else 0) |
+               (4 if opts.smem_forward else 0))
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d

@@ -101,7 +101,9 @@ typedef struct {
     float attractor[2];
     int32_t lanes_per_ball; /* 0 = auto; else 1,2,4,8,16,32 lanes cooperating on one ball's sweep */
     int32_t flags;          /* bit 0: force the exact (unfiltered) sweep;
-                               bit 1: force the sequential (oracle-order, bit-exact) backward */
+                               bit 1: force the sequential (oracle-order, bit-exact) backward;
+                               bit 2: force the shared-memory forward kernel (small scenes default
+                                      to the register-resident one) */
 } doper_rollout_desc;
 
 /* The checkpoint period the library will use for this rollout (ckpt_every if > 0, else chosen

@@ -28,8 +28,8 @@ def _opts(ball_sim, **kw):
 
 
 @pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
-@pytest.mark.parametrize("exact", [False, True])
-def test_rollout_forward_bitexact_all_lane_counts(sim, cref, lanes, exact):
+@pytest.mark.parametrize("exact,smem", [(False, False), (True, False), (False, True)])
+def test_rollout_forward_bitexact_all_lane_counts(sim, cref, lanes, exact, smem):
     ball_sim, _ = sim
     w = syn.make_workload("c2", n_balls=333)  # ragged: not a multiple of any block size
     n = 300
@@ -38,7 +38,8 @@ def test_rollout_forward_bitexact_all_lane_counts(sim, cref, lanes, exact):
                            want_traj=True)
     assert ref["hit"].sum() > 30
     got = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], w["constants"],
-                                   _opts(ball_sim, lanes_per_ball=lanes, force_exact_sweep=exact, ckpt_every=16),
+                                   _opts(ball_sim, lanes_per_ball=lanes, force_exact_sweep=exact, ckpt_every=16,
+                                         smem_forward=smem),
                                    want_trajectory=True)
     assert np.array_equal(got["idx"], ref["idx"]), "closest-segment indices"
     assert np.array_equal(got["hit"], ref["hit"]), "hit flags"

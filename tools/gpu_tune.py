@@ -42,9 +42,9 @@ def main():
     tgt = ball_sim._target2(w["target"])
     out = {"workload": name, "B": B, "n_steps": n, "S": int(w["segments"].shape[-3])}
     lanes_list = [1, 2, 4, 8, 16, 32] if not w["per_env"] else [2, 4, 8, 16, 32]
-    for exact in (False, True):
+    for exact, smem in ((False, False), (False, True), (True, True)):
         for lanes in lanes_list:
-            opts = ball_sim.RolloutOptions(lanes_per_ball=lanes, force_exact_sweep=exact)
+            opts = ball_sim.RolloutOptions(lanes_per_ball=lanes, force_exact_sweep=exact, smem_forward=smem)
             desc = ball_sim._make_desc(B, scene, w["sim_time"], n, w["attractor"], w["constants"], opts)
             bufs = ball_sim._Buffers.get(dev, desc)
             xT = torch.empty((B, 2), device=dev); vT = torch.empty((B, 2), device=dev)
@@ -53,8 +53,8 @@ def main():
                                                                   ptr(xT), ptr(vT), 0, 0, 0, ptr(bufs.ws)), "fwd"))
             except Exception as e:
                 ms = repr(e)
-            out[f"fwd_ms_lanes{lanes}{'_exact' if exact else ''}"] = ms
-            print(f"fwd lanes={lanes:2d} exact={exact}: {ms}", flush=True)
+            out[f"fwd_ms_lanes{lanes}{'_exact' if exact else ''}{'_smem' if smem else ''}"] = ms
+            print(f"fwd lanes={lanes:2d} exact={exact} smem={smem}: {ms}", flush=True)
     # backward variants
     res = {}
     for seq in (True, False):
