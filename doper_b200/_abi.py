@@ -16,7 +16,8 @@ ABI_VERSION = 1
 
 EXPORTS = (
     "doper_abi_version", "doper_error_string", "doper_scene_workspace_bytes", "doper_scene_prepare",
-    "doper_closest_segment", "doper_points_inside", "doper_rollout_ckpt_every", "doper_rollout_workspace_bytes",
+    "doper_closest_segment", "doper_points_inside", "doper_rollout_ckpt_every", "doper_rollout_log_ball_major",
+    "doper_rollout_workspace_bytes",
     "doper_rollout_fwd", "doper_rollout_bwd", "doper_l1_loss", "doper_value_and_grad",
     "doper_fp32_probe",
 )
@@ -69,6 +70,8 @@ def _load() -> ctypes.CDLL:
     lib.doper_points_inside.argtypes = [vp, c_int64, c_int32, fp, fp, vp]
     lib.doper_rollout_ckpt_every.restype = c_int32
     lib.doper_rollout_ckpt_every.argtypes = [POINTER(RolloutDesc)]
+    lib.doper_rollout_log_ball_major.restype = c_int32
+    lib.doper_rollout_log_ball_major.argtypes = [POINTER(RolloutDesc)]
     lib.doper_rollout_workspace_bytes.restype = c_size_t
     lib.doper_rollout_workspace_bytes.argtypes = [POINTER(RolloutDesc)]
     lib.doper_rollout_fwd.argtypes = [vp, POINTER(RolloutDesc), vp, fp, fp, fp, fp, fp, fp, fp, vp]
@@ -79,7 +82,8 @@ def _load() -> ctypes.CDLL:
     lib.doper_fp32_probe.argtypes = [vp, c_int32, c_int32, c_int32, c_int32, fp]
     for name in EXPORTS:
         if name not in ("doper_error_string", "doper_scene_workspace_bytes",
-                        "doper_rollout_workspace_bytes", "doper_abi_version", "doper_rollout_ckpt_every"):
+                        "doper_rollout_workspace_bytes", "doper_abi_version", "doper_rollout_ckpt_every",
+                        "doper_rollout_log_ball_major"):
             getattr(lib, name).restype = ctypes.c_int
     if lib.doper_abi_version() != ABI_VERSION:
         raise ImportError(f"doper_b200: ABI version mismatch: library {lib.doper_abi_version()}, "

@@ -163,7 +163,8 @@ struct FwdParams {
     float2* traj_v;
     float2* traj_a;
     float4* ckpt;     // [n_ckpt][B]
-    int32_t* hitlog;  // [n_steps][B]
+    int32_t* hitlog;  // element (t, ball) at t * hl_st + ball * hl_sb
+    int64_t hl_st, hl_sb;
 };
 
 template <int G>
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_kernel(const FwdParam
     mbar_wait(bar, 0);
 
     int prev_idx = -1;  // no hint at the first step
-    int32_t* hl = p.hitlog ? p.hitlog + ball : nullptr;
+    int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
     float4* ck = p.ckpt ? p.ckpt + ball : nullptr;
     float2* tx = p.traj_x ? p.traj_x + ball : nullptr;
     float2* tv = p.traj_v ? p.traj_v + ball : nullptr;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_kernel(const FwdParam
         if (hit) s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c);
         x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
         if (writer) {
-            if (hl) { *hl = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31)); hl += p.B; }
+            if (hl) { *hl = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31)); hl += p.hl_st; }
             if (tx) { *tx = make_float2(x, y); tx += p.B; }
             if (tv) { *tv = make_float2(vx, vy); tv += p.B; }
             if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += p.B; }
@@ -276,7 +277,7 @@ rollout_fwd_reg_kernel(const FwdParams p) {
     float x = xx.x, y = xx.y, vx = vv.x, vy = vv.y;
     const Consts c = p.c;
     const bool writer = active && lane == 0;
-    int32_t* hl = p.hitlog ? p.hitlog + ball : nullptr;
+    int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
     float4* ck = p.ckpt ? p.ckpt + ball : nullptr;
     float2* tx = p.traj_x ? p.traj_x + ball : nullptr;
     float2* tv = p.traj_v ? p.traj_v + ball : nullptr;
@@ -337,13 +338,149 @@ rollout_fwd_reg_kernel(const FwdParams p) {
         if (hit) s1 = resolve(x, y, vx, vy, s1, __ldg(gq + idx), c);
         x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
         if (writer) {
-            if (hl) { *hl = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31)); hl += stride; }
+            if (hl) { *hl = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31)); hl += p.hl_st; }
             if (tx) { *tx = make_float2(x, y); tx += stride; }
             if (tv) { *tv = make_float2(vx, vy); tv += stride; }
             if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += stride; }
         }
     }
     if (writer) {
+        p.xT[ball] = make_float2(x, y);
+        p.vT[ball] = make_float2(vx, vy);
+    }
+}
+
+// Time-parallel forward for small and medium batches: ONE WARP PER BALL, LANE = TIME STEP.
+// Collisions are rare (~1 per 1,000 ball-steps), so the warp first integrates 32 steps of free
+// flight (phase 1: O(1) work per step, every lane redundantly, lane k keeps step k), then all 32
+// lanes run the closest-segment sweep of their own step at once (phase 2: the scene is read from
+// shared memory as warp-wide broadcasts, no cross-lane reduction, no redundant sweep work).  A
+// ballot finds the first step that hit; steps before it are committed exactly as a sequential
+// rollout would have produced them (free flight until a hit is the reference's own branch), the
+// hit step is resolved, and the next chunk starts right after it.  A ball that keeps colliding
+// (resting against a wall) switches to the lane-split sequential sweep for a while.
+// Results are bit-identical to the sequential kernels: same arithmetic per step, only scheduled
+// speculatively.
+constexpr int kTpEarlyHit = 6;     // a hit this early in a chunk ...
+constexpr int kTpSeqSteps = 64;    // ... sends the ball to sequential mode for this many steps
+
+__global__ void __launch_bounds__(1024) rollout_fwd_tp_kernel(const FwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wpb = blockDim.x >> 5;  // balls per block
+    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
+    const int n_local = p.per_env ? wpb : 1;
+    float4* sq = reinterpret_cast<float4*>(smem);
+    float* srl = reinterpret_cast<float*>(smem + (size_t)n_local * L.S_pad * sizeof(float4));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_local * L.S_pad * 20);
+    const int64_t first_ball = (int64_t)blockIdx.x * wpb;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const int n = p.per_env ? (int)min((int64_t)wpb, p.B - first_ball) : 1;
+        stage_scenes(sq, srl, p.scene_ws, L, p.per_env ? first_ball : 0, n, bar);
+    }
+    const int64_t ball = first_ball + warp;
+    const bool active = ball < p.B;  // warp-uniform
+    SceneView sc;
+    float x = 0.f, y = 0.f, vx = 0.f, vy = 0.f;
+    if (active) {
+        const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off)[p.per_env ? ball : 0];
+        const int ls = p.per_env ? warp : 0;
+        sc.q = sq + (size_t)ls * L.S_pad; sc.rl = srl + (size_t)ls * L.S_pad;
+        sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
+        const float2 xx = p.x0[ball], vv = p.v0[ball];
+        x = xx.x; y = xx.y; vx = vv.x; vy = vv.y;
+    }
+    mbar_wait(bar, 0);
+    if (!active) return;  // whole warp leaves; no block-wide sync below
+
+    const Consts c = p.c;
+    int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
+    int t = 0, prev_idx = -1, seq_left = 0;
+    const int n = p.n_steps, K = p.K;
+
+    while (t < n) {
+        if (seq_left > 0) {
+            // ---- sequential mode: lanes split the segments of ONE step ----
+            if (p.ckpt && (t % K) == 0 && lane == 0) p.ckpt[(size_t)(t / K) * p.B + ball] = make_float4(x, y, vx, vy);
+            State s1;
+            free_step(x, y, vx, vy, c, s1);
+            int idx; float dist;
+            sweep_any<32>(sc, s1.x, s1.y, lane, prev_idx, idx, dist);
+            prev_idx = idx;
+            const bool hit = dist <= c.r;
+            if (hit) { s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c); seq_left = kTpSeqSteps; }
+            x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
+            if (lane == 0) {
+                const size_t o = (size_t)t * p.B + ball;
+                if (hl) hl[(size_t)t * p.hl_st] = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31));
+                if (p.traj_x) p.traj_x[o] = make_float2(x, y);
+                if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
+                if (p.traj_a) p.traj_a[o] = make_float2(s1.ax, s1.ay);
+            }
+            ++t; --seq_left;
+            continue;
+        }
+        // ---- speculative chunk: phase 1, free flight; lane k keeps step t+k ----
+        const int T = min(32, n - t);
+        float sx = x, sy = y, svx = vx, svy = vy;  // state at the START of my step
+        State my; my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
+        {
+            float cx = x, cy = y, cvx = vx, cvy = vy;
+            const int last = min(lane, T - 1);  // lane k integrates steps 0..k, then holds
+            for (int k = 0; k < T; ++k) {
+                if (k <= last) {
+                    sx = cx; sy = cy; svx = cvx; svy = cvy;
+                    free_step(cx, cy, cvx, cvy, c, my);
+                    cx = my.x; cy = my.y; cvx = my.vx; cvy = my.vy;
+                }
+            }
+        }
+        // ---- phase 2: every lane sweeps the whole scene for its own step ----
+        int idx; float dist;
+        if (prev_idx < 0) prev_idx = hint_by_estimate<32>(sc, x, y, lane);  // first chunk only
+        {
+            const float M = fmaxf(sc.scale, fmaxf(fabsf(my.x), fabsf(my.y)));
+            unsigned long long key;
+            if (!sc.weird && M <= 1.0e15f) key = lane_filtered<1>(sc, my.x, my.y, 0, prev_idx, kFilterKappaPerM2 * M * M);
+            else key = lane_exact<1>(sc, my.x, my.y, 0);
+            unpack_key(key, idx, dist);
+        }
+        const bool hit = (lane < T) && (dist <= c.r);  // NaN -> false (ball_sim.py:164)
+        const unsigned hits = __ballot_sync(0xffffffffu, hit);
+        const int first = hits ? (__ffs(hits) - 1) : T;  // first step of the chunk that collided
+        const int n_commit = min(first + 1, T);          // steps t .. t+n_commit-1 are final
+        State out = my;
+        if (first < T) {  // resolve the collision of step t+first (all lanes, redundantly)
+            const float bx = __shfl_sync(0xffffffffu, sx, first), by = __shfl_sync(0xffffffffu, sy, first);
+            const float bvx = __shfl_sync(0xffffffffu, svx, first), bvy = __shfl_sync(0xffffffffu, svy, first);
+            State b1;
+            b1.x = __shfl_sync(0xffffffffu, my.x, first); b1.y = __shfl_sync(0xffffffffu, my.y, first);
+            b1.vx = __shfl_sync(0xffffffffu, my.vx, first); b1.vy = __shfl_sync(0xffffffffu, my.vy, first);
+            b1.ax = __shfl_sync(0xffffffffu, my.ax, first); b1.ay = __shfl_sync(0xffffffffu, my.ay, first);
+            const int hidx = __shfl_sync(0xffffffffu, idx, first);
+            const State r = resolve(bx, by, bvx, bvy, b1, sc.q[hidx], c);
+            if (lane == first) out = r;
+            x = r.x; y = r.y; vx = r.vx; vy = r.vy;
+            if (first < kTpEarlyHit) seq_left = kTpSeqSteps;
+        } else {  // no collision: the state after the last step of the chunk
+            x = __shfl_sync(0xffffffffu, my.x, T - 1); y = __shfl_sync(0xffffffffu, my.y, T - 1);
+            vx = __shfl_sync(0xffffffffu, my.vx, T - 1); vy = __shfl_sync(0xffffffffu, my.vy, T - 1);
+        }
+        prev_idx = __shfl_sync(0xffffffffu, idx, n_commit - 1);
+        if (lane < n_commit) {
+            const int ts = t + lane;
+            if (hl) hl[(size_t)ts * p.hl_st] = (int32_t)((uint32_t)idx | ((uint32_t)(lane == first) << 31));
+            if (p.ckpt && (ts % K) == 0) p.ckpt[(size_t)(ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
+            const size_t o = (size_t)ts * p.B + ball;
+            if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
+            if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
+            if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+        }
+        t += n_commit;
+    }
+    if (lane == 0) {
         p.xT[ball] = make_float2(x, y);
         p.vT[ball] = make_float2(vx, vy);
     }
@@ -360,7 +497,8 @@ struct BwdParams {
     Consts c;
     const unsigned char* scene_ws;
     const float4* ckpt;
-    const int32_t* hitlog;
+    const int32_t* hitlog;  // element (t, ball) at t * hl_st + ball * hl_sb
+    int64_t hl_st, hl_sb;
     const float2* xT_bar;
     const float2* vT_bar;  // nullable
     float2* x0_bar;        // nullable
@@ -389,7 +527,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
         for (int t = t0; t < t1; ++t) {
             stash[(size_t)(t - t0) * kBwdThreads + tid] = s;
             if (t + 1 < t1) {
-                const int32_t h = p.hitlog[(size_t)t * p.B + ball];
+                const int32_t h = p.hitlog[(size_t)t * p.hl_st + (size_t)ball * p.hl_sb];
                 State s1;
                 free_step(s.x, s.y, s.z, s.w, c, s1);
                 if (h < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c);
@@ -398,7 +536,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
         }
         for (int t = t1 - 1; t >= t0; --t) {
             const float4 st = stash[(size_t)(t - t0) * kBwdThreads + tid];
-            const int32_t h = p.hitlog[(size_t)t * p.B + ball];
+            const int32_t h = p.hitlog[(size_t)t * p.hl_st + (size_t)ball * p.hl_sb];
             const float4 seg = __ldg(q + (h & 0x7fffffff));
             step_vjp(st.x, st.y, st.z, st.w, h < 0, seg, c, gx, gy, gvx, gvy);
         }
@@ -436,7 +574,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const 
         for (int t = t0; t < t1; ++t) {
             stash[(size_t)(t - t0) * kBwdThreads + tid] = s;
             if (t + 1 < t1) {
-                const int32_t h = p.hitlog[(size_t)t * p.B + ball];
+                const int32_t h = p.hitlog[(size_t)t * p.hl_st + (size_t)ball * p.hl_sb];
                 State s1;
                 free_step(s.x, s.y, s.z, s.w, c, s1);
                 if (h < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c);
@@ -450,7 +588,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const 
             for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0f : 0.0f;
         for (int t = t1 - 1; t >= t0; --t) {
             const float4 st = stash[(size_t)(t - t0) * kBwdThreads + tid];
-            const int32_t h = p.hitlog[(size_t)t * p.B + ball];
+            const int32_t h = p.hitlog[(size_t)t * p.hl_st + (size_t)ball * p.hl_sb];
             const float4 seg = __ldg(q + (h & 0x7fffffff));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -671,6 +809,23 @@ int resolve_K(const doper_rollout_desc* d) {
     return 32;
 }
 
+// Forward plan: time-parallel kernel (one warp per ball) unless the caller pinned a lane count,
+// disabled it (flags bit 3) or the batch is large enough for one thread per ball.
+constexpr int64_t kTpMaxBalls = 65536;
+
+bool use_tp(const doper_rollout_desc* d) {
+    return d->lanes_per_ball == 0 && !(d->flags & 8) && d->B <= kTpMaxBalls;
+}
+
+int tp_warps_per_block(const doper_rollout_desc* d) {
+    if (d->per_env) return 4;
+    const size_t scene = (size_t)scene_layout(1, d->S).S_pad * 20;
+    if (scene <= 24 * 1024) return 4;
+    if (scene <= 56 * 1024) return 8;
+    if (scene <= 110 * 1024) return 16;
+    return 32;
+}
+
 bool use_chunked(const doper_rollout_desc* d, int K) {
     const int n_ckpt = (d->n_steps + K - 1) / K;
     return chunked_eligible(d) && n_ckpt <= 32 && n_ckpt >= 2 && K <= kChunkedMaxK;
@@ -829,6 +984,11 @@ int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d) {
     return resolve_K(d);
 }
 
+int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
+    if (validate_desc(d) != DOPER_OK) return 0;
+    return use_tp(d) ? 1 : 0;
+}
+
 size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d) {
     if (validate_desc(d) != DOPER_OK) return 0;
     const int K = resolve_K(d);
@@ -850,10 +1010,15 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         (traj_a && !aligned(traj_a, 8)))
         return DOPER_ERR_MISALIGNED;
     const int G = auto_lanes(d);
-    const size_t smem = fwd_smem_bytes(d, G);
+    const bool tp = use_tp(d);
+    const int tp_wpb = tp_warps_per_block(d);
+    const size_t smem = tp ? (size_t)(d->per_env ? tp_wpb : 1) * scene_layout(1, d->S).S_pad * 20 + 16
+                           : fwd_smem_bytes(d, G);
     if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
     const int K = resolve_K(d);
     FwdParams p;
+    p.hl_st = tp ? 1 : d->B;            // hit log is ball-major for the time-parallel kernel
+    p.hl_sb = tp ? d->n_steps : 1;
     p.B = d->B; p.S = d->S; p.per_env = d->per_env ? 1 : 0; p.n_steps = d->n_steps; p.K = K;
     p.force_exact = d->flags & 1;
     p.c = make_consts(d);
@@ -870,6 +1035,15 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         p.hitlog = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(ws) + off);
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (tp) {
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(rollout_fwd_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+                cudaSuccess)
+            return DOPER_ERR_SMEM_LIMIT;
+        const unsigned grid = (unsigned)((d->B + tp_wpb - 1) / tp_wpb);
+        rollout_fwd_tp_kernel<<<grid, tp_wpb * 32, smem, st>>>(p);
+        return launch_status();
+    }
     const int S_pad = scene_layout(1, d->S).S_pad;
     if (S_pad <= 256 && G >= 8 && !(d->flags & 4)) {  // flags bit 2: force the shared-memory kernel
         switch (G) {
@@ -906,6 +1080,8 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     size_t off = (n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
     p.ckpt = reinterpret_cast<const float4*>(ws);
     p.hitlog = reinterpret_cast<const int32_t*>(reinterpret_cast<const unsigned char*>(ws) + off);
+    p.hl_st = use_tp(d) ? 1 : d->B;
+    p.hl_sb = use_tp(d) ? d->n_steps : 1;
     p.xT_bar = reinterpret_cast<const float2*>(xT_bar);
     p.vT_bar = reinterpret_cast<const float2*>(vT_bar);
     p.x0_bar = reinterpret_cast<float2*>(x0_bar);

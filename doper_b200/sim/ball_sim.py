@@ -38,12 +38,13 @@ class RolloutOptions:
     """Tuning knobs that do not change results."""
 
     def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False,
-                 sequential_backward: bool = False, smem_forward: bool = False):
+                 sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
         self.sequential_backward = bool(sequential_backward)  # oracle-order adjoint (bit-exact)
         self.smem_forward = bool(smem_forward)  # TMA/shared-memory forward even for small scenes
+        self.time_parallel = bool(time_parallel)  # allow the warp-per-ball speculative forward
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -82,7 +83,7 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
     d.attractor[0], d.attractor[1] = a[0], a[1]
     d.lanes_per_ball = opts.lanes_per_ball
     d.flags = ((1 if opts.force_exact_sweep else 0) | (2 if opts.sequential_backward else 0) |
-               (4 if opts.smem_forward else 0))
+               (4 if opts.smem_forward else 0) | (0 if opts.time_parallel else 8))
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d
@@ -332,7 +333,11 @@ def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, at
     ck_bytes = n_ckpt * B * 16
     off = (ck_bytes + 255) // 256 * 256
     ckpt = ws[:ck_bytes].view(torch.float32).view(n_ckpt, B, 4).cpu().numpy()
-    hl = ws[off:off + n * B * 4].view(torch.int32).view(n, B).cpu().numpy()
+    hl = ws[off:off + n * B * 4].view(torch.int32)
+    if lib.doper_rollout_log_ball_major(ctypes.byref(desc)):
+        hl = hl.view(B, n).t().contiguous().cpu().numpy()
+    else:
+        hl = hl.view(n, B).cpu().numpy()
     t = None
     if want_trajectory:
         th = traj.cpu().numpy()

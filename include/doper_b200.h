@@ -26,7 +26,8 @@
  *             per-environment scenes are [E][S][2][2].
  *   points / x0 / v0 / xT / vT / cotangents   [B][2]
  *   trajectory (optional)  traj_x, traj_v, traj_a  [n_steps][B][2]
- *   hit log   [n_steps][B] int32 : closest segment index | (hit << 31)
+ *   hit log   int32 : closest segment index | (hit << 31), [n_steps][B] or [B][n_steps]
+ *             (see doper_rollout_log_ball_major)
  *   checkpoints [ceil(n_steps/ckpt_every)][B][4] = (x,y,vx,vy) at the START of step k*ckpt_every
  *   consts    host float[5] = {radius, mass, rolling_friction_coefficient,
  *             walls_elasticity, attractor_strength}  (reference constants dict,
@@ -102,13 +103,19 @@ typedef struct {
     int32_t lanes_per_ball; /* 0 = auto; else 1,2,4,8,16,32 lanes cooperating on one ball's sweep */
     int32_t flags;          /* bit 0: force the exact (unfiltered) sweep;
                                bit 1: force the sequential (oracle-order, bit-exact) backward;
-                               bit 2: force the shared-memory forward kernel (small scenes default
-                                      to the register-resident one) */
+                               bit 2: force the shared-memory lane-split forward kernel over the
+                                      register-resident one (only with lanes_per_ball != 0);
+                               bit 3: disable the time-parallel (warp per ball) forward kernel */
 } doper_rollout_desc;
 
 /* The checkpoint period the library will use for this rollout (ckpt_every if > 0, else chosen
  * from B and n_steps: small batches get <= 32 chunks per ball for the chunk-parallel backward). */
 int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d);
+
+/* Layout of the hit log inside the workspace: 0 = [n_steps][B] (step-major), 1 = [B][n_steps]
+ * (ball-major, written by the time-parallel forward kernel). Only tools that decode the
+ * workspace need this; doper_rollout_bwd derives it from the same descriptor. */
+int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d);
 
 /* Bytes of the backward workspace (checkpoints + hit log) for this rollout. */
 size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d);

@@ -33,26 +33,42 @@
 #define POS_UPDATE(v, dt, x) ((x) + (v) * (dt))
 #endif
 
-typedef struct {
-    float r, m, f, e, ks, g;
-} consts_t;
+#define R float
+#define N(name) name##_f
+#define SQRT sqrtf
+#define FABS fabsf
+#define LIT(x) x##f
+#include "ball_sim_step.inc"
+#undef R
+#undef N
+#undef SQRT
+#undef FABS
+#undef LIT
+#undef POS_UPDATE
 
-static inline float clipf(float x, float lo, float hi) {
-    if (x != x) return x; /* NaN propagates like jnp.clip */
-    x = x < lo ? lo : x;
-    return x > hi ? hi : x;
-}
+#define R double
+#define N(name) name##_d
+#define SQRT sqrt
+#define FABS fabs
+#define LIT(x) x
+#define POS_UPDATE(v, dt, x) ((x) + (v) * (dt))
+#include "ball_sim_step.inc"
+#undef R
+#undef N
+#undef SQRT
+#undef FABS
+#undef LIT
+#undef POS_UPDATE
 
-/* jax_geometry.py:132-136 */
-static inline void proj(float px, float py, const float *s, float *cx, float *cy, float *tt) {
-    float svx = s[2] - s[0], svy = s[3] - s[1];
-    float L = svx * svx + svy * svy;
-    float pvx = px - s[0], pvy = py - s[1];
-    float t = clipf((pvx * svx + pvy * svy) / L, 0.0f, 1.0f);
-    *cx = s[0] + t * svx;
-    *cy = s[1] + t * svy;
-    *tt = t;
-}
+/* the fp32 instantiation under its historical names */
+typedef consts_t_f consts_t;
+typedef state_t_f state_t;
+#define clipf clipf_f
+#define proj proj_f
+#define fric fric_f
+#define free_step free_step_f
+#define resolve resolve_f
+#define step_vjp step_vjp_f
 
 /* jax_geometry.py:151-152 */
 static inline float seg_dist(float px, float py, const float *s) {
@@ -76,55 +92,6 @@ static inline int closest(float px, float py, const float *segs, int S, float *d
     }
     *dist = bd;
     return best;
-}
-
-/* ball_sim.py:43-45 */
-static inline float fric(float v, const consts_t *c) {
-    return ((((-clipf(v, -1.0f, 1.0f)) * c->m) * c->g) * c->f) / c->r;
-}
-
-typedef struct { float x, y, vx, vy, ax, ay; } state_t;
-
-/* ball_sim.py:192-202: forces + Euler. Returns candidate state (x1,v1,a). */
-static inline void free_step(float x, float y, float vx, float vy, const float *A,
-                             const consts_t *c, float dt, state_t *o) {
-    float px = -(2.0f * (x - A[0])), py = -(2.0f * (y - A[1]));
-    float fx = fric(vx, c), fy = fric(vy, c);
-    float ax = (c->ks * px + fx) / c->m, ay = (c->ks * py + fy) / c->m;
-    float v1x = vx + ax * dt, v1y = vy + ay * dt;
-    o->x = POS_UPDATE(v1x, dt, x); o->y = POS_UPDATE(v1y, dt, y);
-    o->vx = v1x; o->vy = v1y; o->ax = ax; o->ay = ay;
-}
-
-/* ball_sim.py:97-132 */
-static inline void resolve(float x, float y, float vx, float vy, const state_t *s1,
-                           const float *seg, const float *A, const consts_t *c, float dt,
-                           state_t *o) {
-    float c1x, c1y, t1;
-    proj(s1->x, s1->y, seg, &c1x, &c1y, &t1);
-    float ox = c1x - x, oy = c1y - y;
-    float od = sqrtf(ox * ox + oy * oy);
-    float nx = ox / od, ny = oy / od;
-    float toi = fabsf(od - c->r) / fabsf(nx * s1->vx + ny * s1->vy);
-    toi = clipf(toi, 0.0f, dt);
-    float vsx = vx + s1->ax * toi, vsy = vy + s1->ay * toi;
-    float xsx = POS_UPDATE(vsx, toi, x), xsy = POS_UPDATE(vsy, toi, y);
-    float c2x, c2y, t2;
-    proj(xsx, xsy, seg, &c2x, &c2y, &t2);
-    float o2x = c2x - xsx, o2y = c2y - xsy;
-    float o2d = sqrtf(o2x * o2x + o2y * o2y);
-    float n2x = o2x / o2d, n2y = o2y / o2d;
-    float k = n2x * vsx + n2y * vsy;
-    float vnx = n2x * k, vny = n2y * k;
-    float vpx = vsx - vnx, vpy = vsy - vny;
-    float vax = vpx - c->e * vnx, vay = vpy - c->e * vny;
-    float pbx = -(2.0f * (xsx - A[0])), pby = -(2.0f * (xsy - A[1]));
-    float fbx = fric(vax, c), fby = fric(vay, c);
-    float abx = (pbx + fbx) / c->m, aby = (pby + fby) / c->m;
-    float tau = dt - toi;
-    float vbx = vax + abx * tau, vby = vay + aby * tau;
-    o->x = POS_UPDATE(vbx, tau, xsx); o->y = POS_UPDATE(vby, tau, xsy);
-    o->vx = vbx; o->vy = vby; o->ax = abx; o->ay = aby;
 }
 
 /* ball_sim.py:171-209 */
@@ -207,113 +174,6 @@ void oracle_rollout_fwd(int64_t B, int S, int64_t seg_stride, int n_steps, float
     }
 }
 
-/* d fric / d v  (ball_sim.py:43-45; clip passes gradient strictly inside) */
-static inline float dfric(float v, const consts_t *c) {
-    return (v > -1.0f && v < 1.0f) ? -((((c->m) * c->g) * c->f) / c->r) : 0.0f;
-}
-
-/* J^T w for proj(): [0<t<1] * sv sv^T / L  (symmetric) */
-static inline void proj_vjp(const float *s, float t, float wx, float wy, float *gx, float *gy) {
-    if (t > 0.0f && t < 1.0f) {
-        float svx = s[2] - s[0], svy = s[3] - s[1];
-        float L = svx * svx + svy * svy;
-        float q = (wx * svx + wy * svy) / L;
-        *gx = q * svx; *gy = q * svy;
-    } else {
-        *gx = 0.0f; *gy = 0.0f;
-    }
-}
-
-/* Adjoint of one sim_step given the state at step start and the logged (idx,hit).
- * In/out: (gx,gy,gvx,gvy) = cotangent of the step OUTPUT (x',v') -> cotangent of INPUT (x,v).
- * SURVEY.md Appendix B. The branch (not select) form: no 0*inf leakage. */
-static inline void step_vjp(float x, float y, float vx, float vy, int32_t h, const float *segs,
-                            const float *A, const consts_t *c, float dt, float *gx, float *gy,
-                            float *gvx, float *gvy) {
-    state_t s1;
-    free_step(x, y, vx, vy, A, c, dt, &s1);
-    float bx = 0.f, by = 0.f, bvx = 0.f, bvy = 0.f; /* cotangent of step input */
-    float bax = 0.f, bay = 0.f;                     /* cotangent of a */
-    float b1x, b1y, b1vx, b1vy;                     /* cotangent of (x1, v1) */
-    if (h < 0) {
-        const float *seg = segs + 4 * (size_t)(h & 0x7fffffff);
-        /* recompute resolve() intermediates */
-        float c1x, c1y, t1;
-        proj(s1.x, s1.y, seg, &c1x, &c1y, &t1);
-        float ox = c1x - x, oy = c1y - y;
-        float od = sqrtf(ox * ox + oy * oy);
-        float nx = ox / od, ny = oy / od;
-        float s = nx * s1.vx + ny * s1.vy;
-        float num = fabsf(od - c->r), den = fabsf(s);
-        float toi_raw = num / den;
-        float toi = clipf(toi_raw, 0.0f, dt);
-        float vsx = vx + s1.ax * toi, vsy = vy + s1.ay * toi;
-        float xsx = POS_UPDATE(vsx, toi, x), xsy = POS_UPDATE(vsy, toi, y);
-        float c2x, c2y, t2;
-        proj(xsx, xsy, seg, &c2x, &c2y, &t2);
-        float o2x = c2x - xsx, o2y = c2y - xsy;
-        float o2d = sqrtf(o2x * o2x + o2y * o2y);
-        float n2x = o2x / o2d, n2y = o2y / o2d;
-        float k = n2x * vsx + n2y * vsy;
-        float vnx = n2x * k, vny = n2y * k;
-        float vax = (vsx - vnx) - c->e * vnx, vay = (vsy - vny) - c->e * vny;
-        float pbx = -(2.0f * (xsx - A[0])), pby = -(2.0f * (xsy - A[1]));
-        float abx = (pbx + fric(vax, c)) / c->m, aby = (pby + fric(vay, c)) / c->m;
-        float tau = dt - toi;
-        float vbx = vax + abx * tau, vby = vay + aby * tau;
-        /* reverse */
-        float gvbx = *gvx + *gx * tau, gvby = *gvy + *gy * tau; /* xb = xs + vb*tau */
-        float gxsx = *gx, gxsy = *gy;
-        float gtau = (*gx * vbx + *gy * vby) + (gvbx * abx + gvby * aby);
-        float gvax = gvbx, gvay = gvby;
-        float gabx = gvbx * tau, gaby = gvby * tau;
-        gxsx += -2.0f * (gabx / c->m); gxsy += -2.0f * (gaby / c->m);
-        gvax += (gabx / c->m) * dfric(vax, c); gvay += (gaby / c->m) * dfric(vay, c);
-        float gtoi = -gtau;
-        /* va = vs - (1+e) * n2 * (n2.vs) */
-        float gvsx = gvax, gvsy = gvay;
-        float gvnx = -(1.0f + c->e) * gvax, gvny = -(1.0f + c->e) * gvay;
-        float gk = gvnx * n2x + gvny * n2y;
-        float gn2x = gvnx * k + gk * vsx, gn2y = gvny * k + gk * vsy;
-        gvsx += gk * n2x; gvsy += gk * n2y;
-        float nd = n2x * gn2x + n2y * gn2y;
-        float go2x = (gn2x - n2x * nd) / o2d, go2y = (gn2y - n2y * nd) / o2d;
-        float jx, jy;
-        proj_vjp(seg, t2, go2x, go2y, &jx, &jy);
-        gxsx += jx - go2x; gxsy += jy - go2y;
-        /* xs = x + vs*toi ; vs = v + a*toi */
-        bx += gxsx; by += gxsy;
-        gvsx += gxsx * toi; gvsy += gxsy * toi;
-        gtoi += gxsx * vsx + gxsy * vsy;
-        bvx += gvsx; bvy += gvsy;
-        bax += gvsx * toi; bay += gvsy * toi;
-        gtoi += gvsx * s1.ax + gvsy * s1.ay;
-        /* toi = clip(num/den, 0, dt) */
-        float graw = (toi_raw > 0.0f && toi_raw < dt) ? gtoi : 0.0f;
-        float gnum = graw / den;
-        float gden = -(graw * toi_raw) / den;
-        float god = gnum * ((od - c->r) > 0.0f ? 1.0f : ((od - c->r) < 0.0f ? -1.0f : 0.0f));
-        float gs = gden * (s > 0.0f ? 1.0f : (s < 0.0f ? -1.0f : 0.0f));
-        float gnx = gs * s1.vx, gny = gs * s1.vy;
-        b1vx = gs * nx; b1vy = gs * ny;
-        float nd1 = nx * gnx + ny * gny;
-        float gox = (gnx - nx * nd1) / od + god * nx, goy = (gny - ny * nd1) / od + god * ny;
-        bx -= gox; by -= goy;
-        proj_vjp(seg, t1, gox, goy, &b1x, &b1y);
-    } else {
-        b1x = *gx; b1y = *gy; b1vx = *gvx; b1vy = *gvy;
-    }
-    /* common tail: x1 = x + v1*dt ; v1 = v + a*dt ; a = (ks*pot + fric(v))/m */
-    float tvx = b1vx + b1x * dt, tvy = b1vy + b1y * dt;
-    bx += b1x; by += b1y;
-    bvx += tvx; bvy += tvy;
-    bax += tvx * dt; bay += tvy * dt;
-    float amx = bax / c->m, amy = bay / c->m;
-    bx += -2.0f * (c->ks * amx); by += -2.0f * (c->ks * amy);
-    bvx += amx * dfric(vx, c); bvy += amy * dfric(vy, c);
-    *gx = bx; *gy = by; *gvx = bvx; *gvy = bvy;
-}
-
 /* value_and_grad of sum_b |x_T - target|_1 w.r.t. v0 (and x0).  Stores the whole per-step
  * (x,v) history per ball (what XLA's transposed scan keeps), then walks it backwards.
  * Outputs: loss_per_ball [B], xT, vT [B][2], gv0, gx0 [B][2]; hitlog optional [n][B]. */
@@ -350,5 +210,44 @@ void oracle_value_and_grad(int64_t B, int S, int64_t seg_stride, int n_steps, fl
         }
         free(hist);
         free(hl);
+    }
+}
+
+/* Gradient "truth": fp32 forward rollout (bit-identical to oracle_value_and_grad's), then the
+ * binary64 adjoint of the real-arithmetic step evaluated at each fp32 step-start state with the
+ * logged (idx, hit).  Any fp32 ordering of the backward (the reference's XLA transpose, torch
+ * autograd, the sequential or the chunk-parallel CUDA kernels) is this plus rounding noise. */
+void oracle_grad_truth64(int64_t B, int S, int64_t seg_stride, int n_steps, float dt,
+                         const float *consts, const float *attractor, const float *target,
+                         const float *segs, const float *x0, const float *v0, double *gv0,
+                         double *gx0) {
+    consts_t c = mk(consts);
+    consts_t_d cd = {c.r, c.m, c.f, c.e, c.ks, c.g};
+    const double Ad[2] = {attractor[0], attractor[1]};
+#pragma omp parallel
+    {
+        float *hist = (float *)malloc(sizeof(float) * 4 * (size_t)(n_steps > 0 ? n_steps : 1));
+        int32_t *hl = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_steps > 0 ? n_steps : 1));
+        double *sd = (double *)malloc(sizeof(double) * 4 * (size_t)S);
+#pragma omp for schedule(static)
+        for (int64_t b = 0; b < B; ++b) {
+            const float *sg = segs + seg_stride * b;
+            for (int i = 0; i < 4 * S; ++i) sd[i] = sg[i];
+            state_t st = {x0[2 * b], x0[2 * b + 1], v0[2 * b], v0[2 * b + 1], 0.0f, 0.0f};
+            for (int t = 0; t < n_steps; ++t) {
+                hist[4 * t] = st.x; hist[4 * t + 1] = st.y;
+                hist[4 * t + 2] = st.vx; hist[4 * t + 3] = st.vy;
+                hl[t] = sim_step(&st, sg, S, attractor, &c, dt);
+            }
+            float ex = st.x - target[0], ey = st.y - target[1];
+            double gx = ex > 0.f ? 1. : (ex < 0.f ? -1. : 0.), gy = ey > 0.f ? 1. : (ey < 0.f ? -1. : 0.);
+            double gvx = 0., gvy = 0.;
+            for (int t = n_steps - 1; t >= 0; --t)
+                step_vjp_d(hist[4 * t], hist[4 * t + 1], hist[4 * t + 2], hist[4 * t + 3], hl[t], sd, Ad,
+                           &cd, (double)dt, &gx, &gy, &gvx, &gvy);
+            gv0[2 * b] = gvx; gv0[2 * b + 1] = gvy;
+            if (gx0) { gx0[2 * b] = gx; gx0[2 * b + 1] = gy; }
+        }
+        free(hist); free(hl); free(sd);
     }
 }

@@ -19,6 +19,7 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 _SRC = _HERE / "ball_sim_ref.c"
+_INC = _HERE / "ball_sim_step.inc"
 _OUT = _HERE / "_build"
 
 _FLAGS = {
@@ -30,7 +31,7 @@ _FLAGS = {
 def build(flavour: str = "portable", force: bool = False) -> Path:
     _OUT.mkdir(exist_ok=True)
     so = _OUT / f"liboracle_{flavour}.so"
-    if so.exists() and not force and so.stat().st_mtime >= _SRC.stat().st_mtime:
+    if so.exists() and not force and so.stat().st_mtime >= max(_SRC.stat().st_mtime, _INC.stat().st_mtime):
         return so
     cmd = ["gcc", "-std=c11", "-shared", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math",
            *_FLAGS[flavour], str(_SRC), "-o", str(so), "-lm"]
@@ -59,8 +60,11 @@ class CRef:
                                          ctypes.c_float, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i]
         L.oracle_value_and_grad.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
                                             ctypes.c_float, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i]
+        _d = ctypes.POINTER(ctypes.c_double)
+        L.oracle_grad_truth64.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
+                                          ctypes.c_float, _f, _f, _f, _f, _f, _f, _d, _d]
         for fn in (L.oracle_closest_segment, L.oracle_points_inside, L.oracle_rollout_fwd,
-                   L.oracle_value_and_grad):
+                   L.oracle_value_and_grad, L.oracle_grad_truth64):
             fn.restype = None
 
     @staticmethod
@@ -133,3 +137,18 @@ class CRef:
                                        _fp(gx), hl.ctypes.data_as(_i))
         return {"loss_per_ball": loss, "x_T": xT, "v_T": vT, "grad_v0": gv, "grad_x0": gx,
                 "idx": hl & 0x7FFFFFFF, "hit": hl < 0, "hitlog": hl}
+
+    def grad_truth64(self, n_steps, dt, consts, attractor, target, segments, x0, v0):
+        """float64 adjoint on the fp32 forward history -> (dL/dv0, dL/dx0) as float64 [B,2]."""
+        s, S, stride = self._scene(segments)
+        x0 = self._c(x0).reshape(-1, 2)
+        v0 = self._c(v0).reshape(-1, 2)
+        B = x0.shape[0]
+        gv, gx = np.empty((B, 2), np.float64), np.empty((B, 2), np.float64)
+        k = self.consts_array(consts)
+        A = self._c(attractor).reshape(2)
+        tg = self._c(target).reshape(2)
+        dp = ctypes.POINTER(ctypes.c_double)
+        self.lib.oracle_grad_truth64(B, S, stride, n_steps, np.float32(dt), _fp(k), _fp(A), _fp(tg), _fp(s),
+                                     _fp(x0), _fp(v0), gv.ctypes.data_as(dp), gx.ctypes.data_as(dp))
+        return gv, gx

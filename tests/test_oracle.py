@@ -101,6 +101,21 @@ def test_torch_forward_bitexact_and_c_adjoint_matches_autograd(small, cref):
     assert abs(g["loss_per_ball"].sum(dtype=np.float64) - loss) < 1e-4 * abs(loss)
 
 
+def test_fp32_adjoints_vs_float64_truth(small, cref):
+    """Calibrates the gradient tolerance: the reference-order fp32 adjoint (C) and torch autograd
+    are both within rounding noise of the float64 adjoint evaluated on the same fp32 trajectory —
+    median ~1e-7, but a few 1e-4 on the worst ball (bounces amplify rounding)."""
+    w, n = small, 300
+    dt = np.float32((n / 1000) / n)
+    truth, _ = cref.grad_truth64(n, dt, w["c"], w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+    seq = cref.value_and_grad(n, dt, w["c"], w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])["grad_v0"]
+    (res, _) = ot.value_and_grad(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], w["c"])
+    e_seq, e_torch = grad_rel_err(seq, truth), grad_rel_err(res[1], truth)
+    assert np.median(e_seq) < 1e-6 and np.median(e_torch) < 1e-6
+    assert e_seq.max() < 2e-3 and e_torch.max() < 2e-3
+    assert np.quantile(e_seq, 0.95) < 1e-4 and np.quantile(e_torch, 0.95) < 1e-4
+
+
 def test_per_env_scenes(cref):
     E, n = 24, 200
     segs = syn.make_env_maps(7, E, 20, domain=(-4, 4, 0, 6))

@@ -31,7 +31,7 @@ def time_ms(fn, reps=20, warm=3):
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "c2"
-    balls = int(sys.argv[2]) if len(sys.argv) > 2 else None
+    balls = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else None
     w = syn.make_workload(name, n_balls=balls)
     B, n = w["x0"].shape[0], w["n_steps"]
     dev = torch.device("cuda", 0)
@@ -41,8 +41,10 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     tgt = ball_sim._target2(w["target"])
     out = {"workload": name, "B": B, "n_steps": n, "S": int(w["segments"].shape[-3])}
-    lanes_list = [1, 2, 4, 8, 16, 32] if not w["per_env"] else [2, 4, 8, 16, 32]
-    for exact, smem in ((False, False), (False, True), (True, True)):
+    lanes_list = [0, 1, 2, 4, 8, 16, 32] if not w["per_env"] else [0, 2, 4, 8, 16, 32]
+    if len(sys.argv) > 3:
+        lanes_list = [int(v) for v in sys.argv[3].split(',')]
+    for exact, smem in ((False, False), (False, True)):
         for lanes in lanes_list:
             opts = ball_sim.RolloutOptions(lanes_per_ball=lanes, force_exact_sweep=exact, smem_forward=smem)
             desc = ball_sim._make_desc(B, scene, w["sim_time"], n, w["attractor"], w["constants"], opts)
