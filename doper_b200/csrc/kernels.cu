@@ -813,8 +813,17 @@ int resolve_K(const doper_rollout_desc* d) {
 // disabled it (flags bit 3) or the batch is large enough for one thread per ball.
 constexpr int64_t kTpMaxBalls = 65536;
 
+// Measured on B200 (tools/gpu_tune.py, profiles/): a shared small scene with a few thousand balls
+// (BASELINE configs[1]) runs fastest on the register-resident lane-split kernel with 8 lanes per
+// ball (0.63 ms vs 0.74 ms time-parallel); per-environment scenes, dense scenes and every other
+// batch size up to 65,536 run fastest time-parallel; beyond that one thread per ball wins.
+bool plan_reg8(const doper_rollout_desc* d) {
+    return d->lanes_per_ball == 0 && !d->per_env && !(d->flags & 4) && scene_layout(1, d->S).S_pad <= 256 &&
+           d->B >= 1536 && d->B <= 6144;
+}
+
 bool use_tp(const doper_rollout_desc* d) {
-    return d->lanes_per_ball == 0 && !(d->flags & 8) && d->B <= kTpMaxBalls;
+    return d->lanes_per_ball == 0 && !(d->flags & 8) && d->B <= kTpMaxBalls && !plan_reg8(d);
 }
 
 int tp_warps_per_block(const doper_rollout_desc* d) {
@@ -840,10 +849,13 @@ int validate_desc(const doper_rollout_desc* d) {
     return DOPER_OK;
 }
 
+bool plan_reg8(const doper_rollout_desc* d);
+
 // lanes per ball: enough threads to fill 148 SMs x 256 threads; per-env scenes are staged per
 // ball, so spreading one ball over 8 lanes keeps the shared-memory footprint per thread sane.
 int auto_lanes(const doper_rollout_desc* d) {
     if (d->lanes_per_ball) return d->lanes_per_ball;
+    if (plan_reg8(d)) return 8;
     if (d->per_env) return 8;
     int g = 1;
     while (g < 32 && d->B * g < 148 * 256) g *= 2;
