@@ -174,7 +174,8 @@ def ours(args):
     w["n_steps"], w["sim_time"] = n_steps, n_steps / 1000.0
     S = int(w["segments"].shape[-3])
     opts = ball_sim.RolloutOptions(ckpt_every=args.ckpt_every, lanes_per_ball=args.lanes,
-                                   force_exact_sweep=args.exact, sequential_backward=args.seq_bwd)
+                                   force_exact_sweep=args.exact, sequential_backward=args.seq_bwd,
+                                   smem_forward=args.no_reg)
     scene = JaxScene(w["segments"])
     desc = ball_sim._make_desc(B, scene, w["sim_time"], n_steps, w["attractor"], w["constants"], opts)
     _, sws = scene.prepared(device)
@@ -381,6 +382,7 @@ def main():
     ap.add_argument("--ckpt-every", type=int, default=0)
     ap.add_argument("--exact", action="store_true", help="force the exact (unfiltered) sweep")
     ap.add_argument("--seq-bwd", action="store_true", help="force the sequential (oracle-order) backward")
+    ap.add_argument("--no-reg", action="store_true", help="do not use the register-resident forward kernel")
     ap.add_argument("--strong", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

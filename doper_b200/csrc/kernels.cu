@@ -554,10 +554,10 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
 // sequential kernel, different rounding order (tolerance-checked, not bit-exact).
 struct ChunkGeom { int C_pad; int balls_per_block; };
 
-__global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const BwdParams p, const int C_pad) {
+__global__ void __launch_bounds__(kBwdThreads, 7) rollout_bwd_chunked_kernel(const BwdParams p, const int C_pad) {
     extern __shared__ __align__(128) unsigned char smem[];
-    float4* stash = reinterpret_cast<float4*>(smem);                                   // [K][threads]
-    float* mats = reinterpret_cast<float*>(smem + (size_t)p.K * kBwdThreads * sizeof(float4));  // [threads][16]
+    float4* stash = reinterpret_cast<float4*>(smem);  // [K][threads]
+    float* mats = reinterpret_cast<float*>(smem);     // [threads][16], aliases the stash once it is dead
     const int tid = threadIdx.x;
     const int bpb = kBwdThreads / C_pad;
     const int chunk = tid % C_pad, slot = tid / C_pad;
@@ -566,38 +566,41 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const 
     const bool active = ball < p.B && chunk < n_ckpt;
     const Consts c = p.c;
     const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
+    float g[4][4];  // g[k] = pull-back of e_k through this thread's chunk
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0f : 0.0f;
     if (active) {
         const float4* q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) +
                           (p.per_env ? (size_t)ball * L.S_pad : 0);
+        const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
         const int t0 = chunk * p.K, t1 = min(p.n_steps, t0 + p.K);
         float4 s = p.ckpt[(size_t)chunk * p.B + ball];
         for (int t = t0; t < t1; ++t) {
             stash[(size_t)(t - t0) * kBwdThreads + tid] = s;
             if (t + 1 < t1) {
-                const int32_t h = p.hitlog[(size_t)t * p.hl_st + (size_t)ball * p.hl_sb];
+                const int32_t h = hl[(size_t)t * p.hl_st];
                 State s1;
                 free_step(s.x, s.y, s.z, s.w, c, s1);
                 if (h < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c);
                 s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
             }
         }
-        float g[4][4];  // g[k] = pull-back of e_k
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0f : 0.0f;
         for (int t = t1 - 1; t >= t0; --t) {
             const float4 st = stash[(size_t)(t - t0) * kBwdThreads + tid];
-            const int32_t h = p.hitlog[(size_t)t * p.hl_st + (size_t)ball * p.hl_sb];
+            const int32_t h = hl[(size_t)t * p.hl_st];
             const float4 seg = __ldg(q + (h & 0x7fffffff));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 step_vjp(st.x, st.y, st.z, st.w, h < 0, seg, c, g[k][0], g[k][1], g[k][2], g[k][3]);
         }
+    }
+    __syncthreads();  // every stash column has been consumed: the region becomes `mats`
+    if (active) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) mats[(size_t)tid * 16 + k * 4 + r] = g[k][r];
+            *reinterpret_cast<float4*>(mats + (size_t)tid * 16 + k * 4) = make_float4(g[k][0], g[k][1], g[k][2], g[k][3]);
     }
     __syncthreads();
     if (ball < p.B && chunk == 0) {
@@ -806,7 +809,7 @@ int resolve_K(const doper_rollout_desc* d) {
         const int K = (d->n_steps + 31) / 32;
         if (K <= kChunkedMaxK) return K < 4 ? 4 : K;
     }
-    return 32;
+    return 16;  // sequential backward: 32 KB of stash per 128-thread block -> 7 blocks per SM
 }
 
 // Forward plan: time-parallel kernel (one warp per ball) unless the caller pinned a lane count,
@@ -1102,7 +1105,7 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     if (use_chunked(d, K)) {
         int C_pad = 2;
         while (C_pad < (int)n_ckpt) C_pad *= 2;
-        const size_t smem = (size_t)K * kBwdThreads * sizeof(float4) + (size_t)kBwdThreads * 16 * sizeof(float);
+        const size_t smem = (size_t)(K < 4 ? 4 : K) * kBwdThreads * sizeof(float4);  // stash, later reused for the 4x4s
         if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
         if (smem > 48 * 1024 &&
             cudaFuncSetAttribute(rollout_bwd_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

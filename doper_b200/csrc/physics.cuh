@@ -145,15 +145,24 @@ __device__ __forceinline__ void proj_vjp(const float4& q, float t, float wx, flo
     }
 }
 
-// In/out g = (gx, gy, gvx, gvy): cotangent of the step output -> cotangent of the step input.
-__device__ __forceinline__ void step_vjp(float x, float y, float vx, float vy, bool hit,
-                                         const float4& seg, const Consts& c, float& gx, float& gy,
-                                         float& gvx, float& gvy) {
+// Adjoint of one step, split so that the rare collision part lives out of line (it is ~300
+// instructions; inlining it into every backward loop blew the instruction cache):
+//   step_vjp_tail  free-flight part, common to both branches (x1 = x + v1 dt, v1 = v + a dt, a = ...)
+//   step_vjp_hit   collision part: consumes the output cotangent, returns the cotangents of
+//                  (x1, v1) in `b1` and the direct contributions to (x, v, a) in `b`/`ba`.
+// Operation order is exactly oracle/ball_sim_step.inc:step_vjp.
+struct HitAdj {
+    float bx, by, bvx, bvy, bax, bay;  // direct cotangent contributions to the step input and to a
+    float b1x, b1y, b1vx, b1vy;        // cotangent of the free-flight candidate (x1, v1)
+};
+
+__device__ __noinline__ HitAdj step_vjp_hit(float x, float y, float vx, float vy, float4 seg, const Consts& c,
+                                            float gx, float gy, float gvx, float gvy) {
     State s1;
     free_step(x, y, vx, vy, c, s1);
     float bx = 0.f, by = 0.f, bvx = 0.f, bvy = 0.f, bax = 0.f, bay = 0.f;
     float b1x, b1y, b1vx, b1vy;
-    if (hit) {
+    {
         float c1x, c1y, t1;
         proj(s1.x, s1.y, seg, c1x, c1y, t1);
         float ox = c1x - x, oy = c1y - y;
@@ -213,6 +222,23 @@ __device__ __forceinline__ void step_vjp(float x, float y, float vx, float vy, b
         float gox = (gnx - nx * nd1) / od + god * nx, goy = (gny - ny * nd1) / od + god * ny;
         bx -= gox; by -= goy;
         proj_vjp(seg, t1, gox, goy, b1x, b1y);
+    }
+    HitAdj r;
+    r.bx = bx; r.by = by; r.bvx = bvx; r.bvy = bvy; r.bax = bax; r.bay = bay;
+    r.b1x = b1x; r.b1y = b1y; r.b1vx = b1vx; r.b1vy = b1vy;
+    return r;
+}
+
+// In/out g = (gx, gy, gvx, gvy): cotangent of the step output -> cotangent of the step input.
+__device__ __forceinline__ void step_vjp(float x, float y, float vx, float vy, bool hit,
+                                         const float4& seg, const Consts& c, float& gx, float& gy,
+                                         float& gvx, float& gvy) {
+    float bx = 0.f, by = 0.f, bvx = 0.f, bvy = 0.f, bax = 0.f, bay = 0.f;
+    float b1x, b1y, b1vx, b1vy;
+    if (hit) {
+        const HitAdj r = step_vjp_hit(x, y, vx, vy, seg, c, gx, gy, gvx, gvy);
+        bx = r.bx; by = r.by; bvx = r.bvx; bvy = r.bvy; bax = r.bax; bay = r.bay;
+        b1x = r.b1x; b1y = r.b1y; b1vx = r.b1vx; b1vy = r.b1vy;
     } else {
         b1x = gx; b1y = gy; b1vx = gvx; b1vy = gvy;
     }
