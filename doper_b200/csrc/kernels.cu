@@ -246,12 +246,19 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_kernel(const FwdParam
 // all (NV = S_pad / G visits, fully unrolled, candidates recorded in one 32-bit mask). The few
 // reference-arithmetic evaluations (hint, candidates, collision) read the prepared scene through
 // the read-only L1 path. Same results as rollout_fwd_kernel, by the same argument.
+#ifndef DOPER_REG_THREADS
+#define DOPER_REG_THREADS 128
+#endif
+// Block size of the register-resident kernel. (32-thread blocks spread a 4,096-ball batch more
+// evenly over the 148 SMs but measured the same 0.636 ms: each warp is latency-bound on its own.)
+constexpr int kRegThreads = DOPER_REG_THREADS;
+
 // Register budget per G so that a 4,096-ball batch is co-resident in ONE wave (a second wave of a
 // whole-rollout kernel doubles the time): blocks/SM = 2, 4, 7 for G = 8, 16, 32.
 template <int G, int NV>
-__global__ void __launch_bounds__(kFwdThreads, (G == 8 ? 2 : (G == 16 ? 4 : 7)))
+__global__ void __launch_bounds__(kRegThreads, (G == 8 ? 2 : (G == 16 ? 4 : 7)) * (128 / kRegThreads))
 rollout_fwd_reg_kernel(const FwdParams p) {
-    constexpr int BPB = kFwdThreads / G;
+    constexpr int BPB = kRegThreads / G;
     const int tid = threadIdx.x, lane = tid % G, slot = tid / G;
     int64_t ball = (int64_t)blockIdx.x * BPB + slot;
     const bool active = ball < p.B;
@@ -576,19 +583,23 @@ __global__ void __launch_bounds__(kBwdThreads, 7) rollout_bwd_chunked_kernel(con
                           (p.per_env ? (size_t)ball * L.S_pad : 0);
         const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
         const int t0 = chunk * p.K, t1 = min(p.n_steps, t0 + p.K);
+        // replay the chunk; only every other state is stashed (the whole batch's states would not
+        // fit the SMs' shared memory in one wave otherwise): odd steps are re-derived on the way back
         float4 s = p.ckpt[(size_t)chunk * p.B + ball];
+        auto advance = [&](const float4& a, int32_t h) {
+            State s1;
+            free_step(a.x, a.y, a.z, a.w, c, s1);
+            if (h < 0) s1 = resolve(a.x, a.y, a.z, a.w, s1, __ldg(q + (h & 0x7fffffff)), c);
+            return make_float4(s1.x, s1.y, s1.vx, s1.vy);
+        };
         for (int t = t0; t < t1; ++t) {
-            stash[(size_t)(t - t0) * kBwdThreads + tid] = s;
-            if (t + 1 < t1) {
-                const int32_t h = hl[(size_t)t * p.hl_st];
-                State s1;
-                free_step(s.x, s.y, s.z, s.w, c, s1);
-                if (h < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c);
-                s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
-            }
+            if (((t - t0) & 1) == 0) stash[(size_t)((t - t0) >> 1) * kBwdThreads + tid] = s;
+            if (t + 1 < t1) s = advance(s, hl[(size_t)t * p.hl_st]);
         }
         for (int t = t1 - 1; t >= t0; --t) {
-            const float4 st = stash[(size_t)(t - t0) * kBwdThreads + tid];
+            const int j = t - t0;
+            float4 st = stash[(size_t)(j >> 1) * kBwdThreads + tid];
+            if (j & 1) st = advance(st, hl[(size_t)(t - 1) * p.hl_st]);
             const int32_t h = hl[(size_t)t * p.hl_st];
             const float4 seg = __ldg(q + (h & 0x7fffffff));
 #pragma unroll
@@ -873,9 +884,9 @@ size_t fwd_smem_bytes(const doper_rollout_desc* d, int G) {
 
 template <int G, int NV>
 int launch_fwd_reg(cudaStream_t st, const FwdParams& p) {
-    const int bpb = kFwdThreads / G;
+    const int bpb = kRegThreads / G;
     const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
-    rollout_fwd_reg_kernel<G, NV><<<grid, kFwdThreads, 0, st>>>(p);
+    rollout_fwd_reg_kernel<G, NV><<<grid, kRegThreads, 0, st>>>(p);
     return launch_status();
 }
 
@@ -1105,7 +1116,8 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     if (use_chunked(d, K)) {
         int C_pad = 2;
         while (C_pad < (int)n_ckpt) C_pad *= 2;
-        const size_t smem = (size_t)(K < 4 ? 4 : K) * kBwdThreads * sizeof(float4);  // stash, later reused for the 4x4s
+        // stash of every other state; the region is reused for the 4x4 chunk matrices (16 floats/thread)
+        const size_t smem = (size_t)((K + 1) / 2 < 4 ? 4 : (K + 1) / 2) * kBwdThreads * sizeof(float4);
         if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
         if (smem > 48 * 1024 &&
             cudaFuncSetAttribute(rollout_bwd_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
