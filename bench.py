@@ -169,7 +169,9 @@ def ours(args):
     if name == "c3" and not args.balls:
         per_gpu = syn.WORKLOADS[name][0] // max(world, 1) if args.strong else syn.WORKLOADS[name][0]
     total = per_gpu * world
-    w = syn.make_workload(name, n_balls=total, lo=rank * per_gpu, hi=(rank + 1) * per_gpu)
+    from doper_b200.distributed import ball_shard
+    lo, hi = ball_shard(total, rank, world)  # contiguous slice of the globally seeded batch
+    w = syn.make_workload(name, n_balls=total, lo=lo, hi=hi)
     B, n_steps = per_gpu, (args.sim_steps or w["n_steps"])
     w["n_steps"], w["sim_time"] = n_steps, n_steps / 1000.0
     S = int(w["segments"].shape[-3])
@@ -286,7 +288,7 @@ def ours(args):
         tp = ROOT / "profiles" / "roofline_traffic.json"
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text()).get(name)
+                traffic = json.loads(tp.read_text()).get(name) if (not args.balls and not args.sim_steps) else None
             except Exception:
                 traffic = None
         peaks = {}
