@@ -92,7 +92,7 @@ __device__ __forceinline__ void free_step(float x, float y, float vx, float vy, 
 // ball_sim.py:97-132 : time-of-impact sub-step, reflection, remaining sub-step
 // (out of line: rare, and keeps the hot step loop small; everything by value = in registers)
 __device__ __noinline__ State resolve(float x, float y, float vx, float vy, State s1, float4 seg,
-                                      const Consts& c) {
+                                      const Consts c) {
     State o;
     float c1x, c1y, t1;
     proj(s1.x, s1.y, seg, c1x, c1y, t1);
@@ -156,7 +156,7 @@ struct HitAdj {
     float b1x, b1y, b1vx, b1vy;        // cotangent of the free-flight candidate (x1, v1)
 };
 
-__device__ __noinline__ HitAdj step_vjp_hit(float x, float y, float vx, float vy, float4 seg, const Consts& c,
+__device__ __noinline__ HitAdj step_vjp_hit(float x, float y, float vx, float vy, float4 seg, const Consts c,
                                             float gx, float gy, float gvx, float gvy) {
     State s1;
     free_step(x, y, vx, vy, c, s1);
