@@ -89,6 +89,35 @@ __device__ __forceinline__ void free_step(float x, float y, float vx, float vy, 
     o.vx = v1x; o.vy = v1y; o.ax = ax; o.ay = ay;
 }
 
+// Straight-line variant for software-pipelined loops: the Markstein path of div_invariant for all
+// four divisions with no branch in between; returns false when any numerator was outside the range
+// in which that path is exact (then the caller must redo the step with free_step()).  Same values
+// as free_step() whenever it returns true.
+__device__ __forceinline__ float div_markstein(float a, float b, float y) {
+    float q = __fmul_rn(a, y);
+    q = __fmaf_rn(__fmaf_rn(-b, q, a), y, q);
+    q = __fmaf_rn(__fmaf_rn(-b, q, a), y, q);
+    return q;
+}
+
+__device__ __forceinline__ bool div_in_range(float a, const Consts& c) {
+    return fabsf(a) >= c.div_lo && fabsf(a) <= c.div_hi;
+}
+
+__device__ __forceinline__ bool free_step_fast(float x, float y, float vx, float vy, const Consts& c, State& o) {
+    const float px = -(2.0f * (x - c.ax)), py = -(2.0f * (y - c.ay));
+    const float nfx = (((-clip_nan(vx, -1.0f, 1.0f)) * c.m) * 9.8f) * c.f;
+    const float nfy = (((-clip_nan(vy, -1.0f, 1.0f)) * c.m) * 9.8f) * c.f;
+    const float fx = div_markstein(nfx, c.r, c.rcp_r), fy = div_markstein(nfy, c.r, c.rcp_r);
+    const float nax = c.ks * px + fx, nay = c.ks * py + fy;
+    const float ax = div_markstein(nax, c.m, c.rcp_m), ay = div_markstein(nay, c.m, c.rcp_m);
+    const float v1x = vx + ax * c.dt, v1y = vy + ay * c.dt;
+    o.x = pos_update(v1x, c.dt, x);
+    o.y = pos_update(v1y, c.dt, y);
+    o.vx = v1x; o.vy = v1y; o.ax = ax; o.ay = ay;
+    return div_in_range(nfx, c) && div_in_range(nfy, c) && div_in_range(nax, c) && div_in_range(nay, c);
+}
+
 // ball_sim.py:97-132 : time-of-impact sub-step, reflection, remaining sub-step
 // (out of line: rare, and keeps the hot step loop small; everything by value = in registers)
 __device__ __noinline__ State resolve(float x, float y, float vx, float vy, State s1, float4 seg,

@@ -158,6 +158,68 @@ __device__ __forceinline__ unsigned long long lane_filtered(const SceneView& sc,
     return key;
 }
 
+// out-of-line copy for the multi-point sweep (P call sites; candidates are ~1.5 per sweep)
+__device__ __noinline__ float cand_dist_ol(float px, float py, float4 q) { return cand_dist(px, py, q); }
+
+// P points per lane against ONE scene (the multi-ball time-parallel kernel: lane = time step,
+// P balls per warp).  Every segment is loaded once (warp-wide broadcast from shared memory) and
+// estimated for all P points: (2 + 11 P) / P issue slots per pair instead of 13, and P independent
+// dependency chains per lane.  Candidates are recorded per point in 32-segment windows and get the
+// reference arithmetic exactly as in lane_filtered.  sc.rl must be 16-byte aligned.
+// The inner loop is deliberately NOT unrolled beyond 4 segments: a fully unrolled window is ~1,500
+// instructions of straight-line code, and with one or two warps per scheduler the kernel then
+// stalls on instruction fetch (ncu: 45 % of the sweep's samples were stall_no_inst).
+template <int P>
+__device__ __forceinline__ void sweep_points(const SceneView& sc, const float (&px)[P], const float (&py)[P],
+                                             const int (&prev)[P], const float (&kappa)[P],
+                                             unsigned long long (&key)[P]) {
+    float thr[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        thr[p] = __fmaf_rn(approx_d2(px[p], py[p], sc.q[prev[p]], sc.rl[prev[p]]), kFilterOneEps, kappa[p]);
+        key[p] = kNoKey;
+    }
+    const float4* rl4 = reinterpret_cast<const float4*>(sc.rl);
+    for (int base = 0; base < sc.S_pad; base += 32) {
+        unsigned mask[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) mask[p] = 0u;
+        unsigned bit = 1u;
+#pragma unroll 1
+        for (int j = base; j < base + 32; j += 4) {
+            const float4 r = rl4[j >> 2];
+            const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 q = sc.q[j + u];
+                const unsigned bu = bit << u;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const float a = approx_d2(px[p], py[p], q, rr[u]);
+                    mask[p] |= (a <= thr[p]) ? bu : 0u;
+                }
+            }
+            bit <<= 4;
+        }
+        unsigned any = 0u;
+#pragma unroll
+        for (int p = 0; p < P; ++p) any |= mask[p];
+        if (any) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                unsigned m = mask[p];
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const int c = base + j;
+                    const unsigned long long kk = make_key(cand_dist_ol(px[p], py[p], sc.q[c]), c);
+                    key[p] = kk < key[p] ? kk : key[p];
+                }
+            }
+        }
+    }
+}
+
 // min over the G lanes of a group.  A full warp uses two REDUX (distance bits, then index among
 // the minima); sub-warp groups use a shuffle butterfly (REDUX with per-group masks is serialised
 // over the distinct masks of the warp: measured 4x slower at G = 8).
@@ -186,6 +248,138 @@ __device__ __forceinline__ int hint_by_estimate(const SceneView& sc, float px, f
     const unsigned long long k = group_min_redux<G>(((unsigned long long)__float_as_uint(best) << 32) | (unsigned)bi);
     const int h = (int)(unsigned)(k & 0xffffffffull);
     return h < sc.S ? h : 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// broad phase: per-ball candidate lists
+// ---------------------------------------------------------------------------------------
+// A list is built around a centre c with a radius rho and stays valid for every query point p
+// with |p - c| <= rho.  With e_j = sqrt(estimate_j(c)), D_j the real-arithmetic distance (which is
+// 1-Lipschitz in the point), |e_j - D_j| <= 49 u M and |d_ref_j - D_j| <= 38 u M (error model of the
+// filter above), the reference argmin i* at p (and every exact tie) satisfies, for ANY segment j0,
+//     e_i* <= D_i*(c) + 49uM <= D_i*(p) + rho + 49uM <= D_j0(p) + rho + (49 + 76)uM
+//          <= D_j0(c) + 2 rho + 125uM <= e_j0 + 2 rho + 174 u M.
+// The list keeps every j with e_j <= e_j0 + 2 rho + 256 u M (j0 = last step's winner; any j0 is
+// valid, a near one keeps the list short), evaluated on squares with upward slack.  Per step the
+// filtered sweep then runs over the list only: it contains the argmin and all its ties with their
+// original indices, so the result is bit-identical to the full sweep.  M bounds the scene and every
+// point of the list's lifetime.  A lane whose share overflows its capacity sweeps all its
+// segments until the next refresh (always correct).
+constexpr float kCullDeltaPerM = 256.0f * 5.9604644775390625e-08f;  // 256 u, u = 2^-24
+constexpr float kCullUp = 1.0f + 9.5367431640625e-07f;              // 1 + 2^-20: covers the roundings of T
+constexpr float kCullRhoCheck = 0.98f;                              // the guard compares against (0.98 rho)^2
+
+constexpr float kCullSafePerM = 128.0f * 5.9604644775390625e-08f;   // 128 u >= 49 u + 38 u: see cull_far()
+
+struct CullState {
+    float cx, cy;  // centre of the list
+    float rho2;    // (kCullRhoCheck rho)^2; the list is used only while |p - c|^2 <= rho2
+    int cnt;       // entries of this lane's share; > LCAP = overflow (sweep everything)
+    float far2;    // estimates above this prove "no collision this step" (see cull_refresh)
+};
+
+__device__ __forceinline__ float cull_far2(float radius, float M);
+
+// list entry k of this lane lives at list[k * stride]
+template <int G, int LCAP>
+__device__ __forceinline__ void cull_refresh(const SceneView& sc, float px, float py, float rho, float radius,
+                                             int lane, int j0, unsigned short* list, int stride, CullState& cs) {
+    const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)) + rho);
+    const float e = sqrtf(approx_d2(px, py, sc.q[j0], sc.rl[j0])) * kCullUp;
+    const float w = __fmaf_rn(kCullDeltaPerM, M, rho + rho);
+    const float T = ((e + w) * (e + w)) * kCullUp;
+    int cnt = 0;
+    for (int i = lane; i < sc.S_pad; i += G) {
+        const float a = approx_d2(px, py, sc.q[i], sc.rl[i]);
+        if (a <= T) {
+            if (cnt < LCAP) list[cnt * stride] = (unsigned short)i;
+            ++cnt;
+        }
+    }
+    cs.cnt = cnt; cs.cx = px; cs.cy = py;
+    cs.rho2 = (kCullRhoCheck * rho) * (kCullRhoCheck * rho);
+    cs.far2 = cull_far2(radius, M);  // M covers every point of the list's lifetime
+}
+
+// No-collision proof from estimates alone: if every list entry has estimate^2 > far2 with
+//   far2 >= (radius + 128 u M)^2, then est_j > r + 87uM, so D_j > r + 38uM and d_ref_j > r for the
+// argmin (which is in the list), hence min_j d_ref_j > r: the step cannot collide, and neither the
+// exact distance nor the winning index is needed (the index is only consumed at collisions).
+__device__ __forceinline__ float cull_far2(float radius, float M) {
+    const float s = __fmaf_rn(kCullSafePerM, M, radius) * kCullUp;
+    return (s * s) * kCullUp;
+}
+
+// min of a non-negative float over the G lanes of a group (every lane of the warp calls)
+template <int G>
+__device__ __forceinline__ float group_min_f(float v) {
+    if (G == 1) return v;
+    if (G == 32) return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));  // v >= +0: bit order = value order
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+// smallest estimate over this lane's share of the list (all its segments when the share overflowed)
+template <int G, int LCAP>
+__device__ __forceinline__ float lane_list_min(const SceneView& sc, float px, float py, int lane,
+                                               const unsigned short* list, int stride, const CullState& cs) {
+    float amin = __int_as_float(0x7f800000);
+    if (cs.cnt > LCAP) {
+        for (int i = lane; i < sc.S_pad; i += G) amin = fminf(amin, approx_d2(px, py, sc.q[i], sc.rl[i]));
+    } else {
+        for (int k = 0; k < cs.cnt; ++k) {
+            const int i = list[k * stride];
+            amin = fminf(amin, approx_d2(px, py, sc.q[i], sc.rl[i]));
+        }
+    }
+    return amin;
+}
+
+// this lane's share of the exact evaluation: candidates are the list entries whose estimate passes
+// thr (thr derived from the estimate of ANY segment is valid; the caller passes the group minimum)
+template <int G, int LCAP>
+__device__ __noinline__ unsigned long long lane_culled(const SceneView& sc, float px, float py, int lane,
+                                                       float thr, const unsigned short* list, int stride,
+                                                       int cnt) {
+    unsigned long long key = kNoKey;
+    if (cnt > LCAP) {
+        for (int i = lane; i < sc.S_pad; i += G) {
+            const float4 q = sc.q[i];
+            if (approx_d2(px, py, q, sc.rl[i]) <= thr) {
+                const unsigned long long kk = make_key(cand_dist(px, py, q), i);
+                key = kk < key ? kk : key;
+            }
+        }
+        return key;
+    }
+    for (int k = 0; k < cnt; ++k) {
+        const int i = list[k * stride];
+        const float4 q = sc.q[i];
+        if (approx_d2(px, py, q, sc.rl[i]) <= thr) {
+            const unsigned long long kk = make_key(cand_dist(px, py, q), i);
+            key = kk < key ? kk : key;
+        }
+    }
+    return key;
+}
+
+// group argmin of the estimate over the current list (seed j0 of the next refresh)
+template <int G, int LCAP>
+__device__ __forceinline__ int list_argmin(const SceneView& sc, float px, float py, int lane,
+                                           const unsigned short* list, int stride, const CullState& cs, int fallback) {
+    float amin = __int_as_float(0x7f800000);
+    int imin = fallback;
+    if (cs.cnt <= LCAP) {
+        for (int k = 0; k < cs.cnt; ++k) {
+            const int i = list[k * stride];
+            const float a = approx_d2(px, py, sc.q[i], sc.rl[i]);
+            if (a < amin) { amin = a; imin = i; }
+        }
+    }
+    const unsigned long long k = group_min_redux<G>(((unsigned long long)__float_as_uint(amin) << 32) | (unsigned)imin);
+    const int h = (int)(unsigned)(k & 0xffffffffull);
+    return (h >= 0 && h < sc.S) ? h : fallback;
 }
 
 // Group-cooperative sweep. Every lane of the warp must call this (warp-wide sync primitives);

@@ -38,13 +38,23 @@ class RolloutOptions:
     """Tuning knobs that do not change results."""
 
     def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False,
-                 sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True):
+                 sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True,
+                 balls_per_warp: int = 0, single_ball_time_parallel: bool = False, warps_per_block: int = 0,
+                 broad_phase: bool = None, exact_index_log: bool = False):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
         self.sequential_backward = bool(sequential_backward)  # oracle-order adjoint (bit-exact)
         self.smem_forward = bool(smem_forward)  # TMA/shared-memory forward even for small scenes
         self.time_parallel = bool(time_parallel)  # allow the warp-per-ball speculative forward
+        self.balls_per_warp = int(balls_per_warp)  # multi-ball time-parallel kernel: 0 = auto, else 1, 2, 4, 8
+        self.single_ball_time_parallel = bool(single_ball_time_parallel)  # keep the one-ball-per-warp kernel
+        self.warps_per_block = int(warps_per_block)  # multi-ball time-parallel kernel: 0 = auto
+        # candidate-list (broad phase) forward: None = library default, True / False = force on / off
+        self.broad_phase = broad_phase
+        # hit log: exact closest-segment index at EVERY step (default for the broad-phase kernel: at
+        # collisions only, which is all the backward and the reference's outputs depend on)
+        self.exact_index_log = bool(exact_index_log)
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -83,7 +93,11 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
     d.attractor[0], d.attractor[1] = a[0], a[1]
     d.lanes_per_ball = opts.lanes_per_ball
     d.flags = ((1 if opts.force_exact_sweep else 0) | (2 if opts.sequential_backward else 0) |
-               (4 if opts.smem_forward else 0) | (0 if opts.time_parallel else 8))
+               (4 if opts.smem_forward else 0) | (0 if opts.time_parallel else 8) |
+               ((opts.balls_per_warp & 0xF) << 4) | (256 if opts.single_ball_time_parallel else 0) |
+               ((opts.warps_per_block & 0x3F) << 9) |
+               ((1 << 16) if opts.broad_phase else 0) | ((1 << 15) if opts.broad_phase is False else 0) |
+               ((1 << 17) if opts.exact_index_log else 0))
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d

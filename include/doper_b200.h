@@ -105,7 +105,18 @@ typedef struct {
                                bit 1: force the sequential (oracle-order, bit-exact) backward;
                                bit 2: force the shared-memory lane-split forward kernel over the
                                       register-resident one (only with lanes_per_ball != 0);
-                               bit 3: disable the time-parallel (warp per ball) forward kernel */
+                               bit 3: disable the time-parallel (warp per ball) forward kernel;
+                               bits 4-7: balls per warp of the multi-ball time-parallel kernel
+                                      (1, 2, 4 or 8; 0 = chosen from B);
+                               bit 8: keep the single-ball time-parallel kernel;
+                               bits 9-14: warps per block of the multi-ball kernel (0 = default);
+                               bit 15 / bit 16: forbid / force the broad-phase (candidate list)
+                                      forward kernel;
+                               bit 17: hit log holds the exact closest index at EVERY step (the
+                                      broad-phase kernel otherwise logs it at collisions only and 0
+                                      elsewhere: the index is consumed at collisions only).
+                               None of these changes x_T, v_T, trajectories, hit flags, collision
+                               indices or gradients. */
 } doper_rollout_desc;
 
 /* The checkpoint period the library will use for this rollout (ckpt_every if > 0, else chosen

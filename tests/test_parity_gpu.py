@@ -53,6 +53,93 @@ def test_rollout_forward_bitexact_all_lane_counts(sim, cref, lanes, exact, smem)
     assert_bitexact(got["checkpoints"][1, :, :2], ref["traj_x"][15], "ckpt 1")
 
 
+@pytest.mark.parametrize("bpw,legacy", [(1, False), (2, False), (4, False), (8, False), (0, True)])
+@pytest.mark.parametrize("regime", ["reference", "bouncy", "exact", "per_env"])
+def test_time_parallel_kernels_bitexact(sim, cref, bpw, legacy, regime):
+    """Multi-ball time-parallel kernel (P = 1, 2, 4, 8 balls per warp) and the single-ball one:
+    indices, hit flags, states, trajectories and checkpoints bit-exact in every regime."""
+    ball_sim, geo = sim
+    n, B = 330, 203  # ragged in balls (not a multiple of 4 warps x P) and in steps (330 = 10 * 32 + 10)
+    consts = syn.reference_constants()
+    if regime == "per_env":
+        segs = syn.make_env_maps(21, B, 67)
+        x0, v0 = syn.make_init_states(22, B, segs)
+        scene = geo.create_env_scenes(segs)
+    else:
+        w = syn.make_workload("c2", n_balls=B)
+        segs, x0, v0 = w["segments"], w["x0"], w["v0"]
+        scene = segs
+    if regime == "bouncy":
+        consts["attractor_strength"] = 2000.0
+    A = np.array(syn.REFERENCE_ATTRACTOR, np.float32)
+    c = onp.make_constants(consts)
+    ref = cref.rollout_fwd(n, np.float32((n / 1000) / n), c, A, segs, x0, v0, want_traj=True)
+    assert ref["hit"].sum() > (1500 if regime == "bouncy" else 15)
+    got = ball_sim.rollout_history(n / 1000, n, scene, x0, v0, A, consts,
+                                   _opts(ball_sim, balls_per_warp=bpw, single_ball_time_parallel=legacy,
+                                         smem_forward=True, force_exact_sweep=(regime == "exact"), ckpt_every=11),
+                                   want_trajectory=True)
+    assert np.array_equal(got["idx"], ref["idx"]), "closest-segment indices"
+    assert np.array_equal(got["hit"], ref["hit"]), "hit flags"
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    assert_bitexact(got["v_T"], ref["v_T"], "v_T")
+    assert_bitexact(got["trajectory"].coordinate, ref["traj_x"], "trajectory x")
+    assert_bitexact(got["trajectory"].velocity, ref["traj_v"], "trajectory v")
+    assert_bitexact(got["trajectory"].acceleration, ref["traj_a"], "trajectory a")
+    assert_bitexact(got["checkpoints"][0, :, :2], x0, "ckpt 0")
+    for k in (1, 7, 29):
+        assert_bitexact(got["checkpoints"][k, :, :2], ref["traj_x"][11 * k - 1], f"ckpt {k} x")
+        assert_bitexact(got["checkpoints"][k, :, 2:], ref["traj_v"][11 * k - 1], f"ckpt {k} v")
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("regime", ["reference", "bouncy", "fast_balls", "per_env", "dense", "every_index"])
+def test_broad_phase_kernel_bitexact(sim, cref, lanes, regime):
+    """Candidate-list (broad phase) forward: the list provably contains the argmin and its ties, so
+    indices, hit flags, states and trajectories must equal the full sweep's / the oracle's bits."""
+    ball_sim, geo = sim
+    n, B = 330, 203
+    consts = syn.reference_constants()
+    rng = np.random.default_rng(5)
+    if regime == "per_env" and lanes < 4:
+        pytest.skip("per-environment scenes are staged per ball: 128 / lanes scenes must fit shared memory")
+    if regime == "per_env":
+        segs = syn.make_env_maps(21, B, 67)
+        x0, v0 = syn.make_init_states(22, B, segs)
+        scene = geo.create_env_scenes(segs)
+    elif regime == "dense":
+        w = syn.make_workload("c4", n_balls=64)
+        segs, x0, v0, n = w["segments"], w["x0"], w["v0"], 90
+        scene = segs
+    else:
+        w = syn.make_workload("c2", n_balls=B)
+        segs, x0, v0 = w["segments"], w["x0"], w["v0"]
+        scene = segs
+    if regime == "bouncy":
+        consts["attractor_strength"] = 2000.0
+    if regime == "fast_balls":  # 60-100 m/s: a step moves up to a ball radius; lists go stale every few steps
+        v0 = (v0 / np.maximum(np.linalg.norm(v0, axis=1, keepdims=True), 1e-6) *
+              rng.uniform(60, 100, (len(v0), 1))).astype(np.float32)
+    A = np.array(syn.REFERENCE_ATTRACTOR, np.float32)
+    c = onp.make_constants(consts)
+    ref = cref.rollout_fwd(n, np.float32((n / 1000) / n), c, A, segs, x0, v0, want_traj=True)
+    assert ref["hit"].sum() > (1500 if regime == "bouncy" else 5)
+    got = ball_sim.rollout_history(n / 1000, n, scene, x0, v0, A, consts,
+                                   _opts(ball_sim, lanes_per_ball=lanes, broad_phase=True, ckpt_every=11,
+                                         exact_index_log=(regime == "every_index")),
+                                   want_trajectory=True)
+    assert np.array_equal(got["hit"], ref["hit"]), "hit flags"
+    assert np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]]), "collision segment indices"
+    if regime == "every_index":
+        assert np.array_equal(got["idx"], ref["idx"]), "closest-segment index at every step"
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    assert_bitexact(got["v_T"], ref["v_T"], "v_T")
+    assert_bitexact(got["trajectory"].coordinate, ref["traj_x"], "trajectory x")
+    assert_bitexact(got["trajectory"].velocity, ref["traj_v"], "trajectory v")
+    assert_bitexact(got["trajectory"].acceleration, ref["traj_a"], "trajectory a")
+    assert_bitexact(got["checkpoints"][3, :, :2], ref["traj_x"][32], "ckpt 3 x")
+
+
 @pytest.mark.parametrize("n_balls,n_steps,K", [(1, 300, 0), (16, 300, 32), (257, 500, 7), (1024, 130, 64)])
 def test_value_and_grad_sequential_backward_bitexact(sim, cref, n_balls, n_steps, K):
     """The sequential backward replays the oracle adjoint's operation order: bit-exact gradients."""
