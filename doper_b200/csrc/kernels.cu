@@ -385,6 +385,234 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_cull_kernel(const Fwd
     }
 }
 
+// Time-parallel broad-phase forward: G lanes per ball, LANE = TIME STEP, one candidate list per
+// ball.  Per round a group (1) refreshes its list when the ball has drifted half a radius from the
+// list's centre, (2) integrates up to G steps of free flight (lane k keeps step k), (3) every lane
+// tests ITS step against the list: the estimate alone proves "no collision" for almost every step
+// (cull_far2); the few near-wall steps get the exact distance, (4) a ballot finds the first
+// collided (or out-of-list) step: the steps before it commit, the collision is resolved, the next
+// round starts after it.  The per-step critical path is the free-flight chain (~100 cycles)
+// instead of chain + sweep + reduction.  A ball that keeps colliding shrinks its speculation
+// length to one step.  Results are bit-identical to every other forward kernel.
+constexpr int kTpcListCap = 64;
+constexpr int kContactSteps = 16;  // sequential steps per round of a ball in contact mode
+
+template <int G>
+__global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int BPB = kFwdThreads / G;  // balls per block
+    constexpr unsigned kLow = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    const int tid = threadIdx.x, lane = tid % G, slot = tid / G, gbase = (tid & 31) - lane;
+    const int64_t n_scenes = p.per_env ? p.B : 1;
+    const SceneLayout L = scene_layout(n_scenes, p.S);
+    const int n_local = p.per_env ? BPB : 1;
+
+    float4* sq = reinterpret_cast<float4*>(smem);
+    float* srl = reinterpret_cast<float*>(smem + (size_t)n_local * L.S_pad * sizeof(float4));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_local * L.S_pad * 20);
+    unsigned short* lists = reinterpret_cast<unsigned short*>(smem + (size_t)n_local * L.S_pad * 20 + 16);
+
+    const int64_t first_ball = (int64_t)blockIdx.x * BPB;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        int64_t first_scene = p.per_env ? first_ball : 0;
+        int ns = p.per_env ? (int)min((int64_t)BPB, p.B - first_ball) : 1;
+        stage_scenes(sq, srl, p.scene_ws, L, first_scene, ns, bar);
+    }
+
+    int64_t ball = first_ball + slot;
+    const bool active = ball < p.B;
+    if (!active) ball = p.B - 1;  // absent ball: reads the last ball's inputs, never advances, writes nothing
+    const int local_scene = p.per_env ? (int)(ball - first_ball) : 0;
+    const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off)[p.per_env ? ball : 0];
+
+    SceneView sc;
+    sc.q = sq + (size_t)local_scene * L.S_pad;
+    sc.rl = srl + (size_t)local_scene * L.S_pad;
+    sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
+
+    const float2 xx = p.x0[ball], vv = p.v0[ball];
+    float x = xx.x, y = xx.y, vx = vv.x, vy = vv.y;  // state at step t (uniform within the group)
+    const Consts c = p.c;
+    const int n = p.n_steps, K = p.K;
+    const bool exact_idx = p.exact_idx != 0;
+    mbar_wait(bar, 0);
+
+    int t = active ? 0 : n;
+    int T = G;       // speculation length of the next round
+    int trouble = 0; // 1: refresh before the next round no matter what; 2: sweep every segment exactly next round
+    int j0 = 0;
+    if (__all_sync(0xffffffffu, !sc.weird)) j0 = hint_by_estimate<G>(sc, x, y, lane);
+    GroupList gl;
+    gl.e = lists + (size_t)slot * kTpcListCap; gl.cap = kTpcListCap; gl.cnt = 0;
+    gl.cx = 0.f; gl.cy = 0.f; gl.rho2 = -1.0f; gl.far2 = 0.f;
+    const float rho_min = sc.scale * 0.001953125f, rho_max = sc.scale * 0.125f;
+    int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
+
+    while (__any_sync(0xffffffffu, t < n)) {
+        // ---- (0) contact mode --------------------------------------------------------------------------
+        // A ball that collided at the first step of its last round (resting / sliding contact) gains
+        // nothing from speculation: it runs up to kContactSteps plain sequential steps here, every lane
+        // of the group redundantly (identical inputs -> identical values, so the group's state stays
+        // uniform without any exchange; no warp-wide primitive inside), then sits this round out.
+        bool sat_out = false;
+        if (t < n && T == 1 && trouble == 0 && gl.rho2 >= 0.0f && !sc.weird) {
+            int miss = 0;
+            for (int it = 0; it < kContactSteps && t < n; ++it) {
+                State s1;
+                free_step(x, y, vx, vy, c, s1);
+                const float px = s1.x, py = s1.y;
+                const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)));
+                const float ddx = px - gl.cx, ddy = py - gl.cy;
+                if (!(M <= 1.0e15f)) break;                                              // normal path: exact sweep
+                if (!(ddx * ddx + ddy * ddy <= gl.rho2)) { trouble = 1; break; }          // normal path: refresh
+                const float amin = glist_min(sc, px, py, gl);
+                int idx = 0;
+                bool hit = false;
+                if (exact_idx || !(amin > gl.far2)) {
+                    unsigned long long key = glist_exact(sc, px, py, __fmaf_rn(amin, kFilterOneEps, kFilterKappaPerM2 * M * M),
+                                                         gl.e, gl.cap, gl.cnt);
+                    if (key == kNoKey) key = lane_exact<1>(sc, px, py, 0);
+                    float dist;
+                    unpack_key(key, idx, dist);
+                    hit = dist <= c.r;
+                }
+                if (active && lane == 0) {
+                    if (p.ckpt && (t % K) == 0) p.ckpt[(size_t)(t / K) * p.B + ball] = make_float4(x, y, vx, vy);
+                }
+                if (hit) s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c);
+                x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
+                if (active && lane == 0) {
+                    if (hl) hl[(int64_t)t * p.hl_st] = (int32_t)((uint32_t)((hit || exact_idx) ? idx : 0) | ((uint32_t)hit << 31));
+                    const size_t o = (size_t)t * p.B + ball;
+                    if (p.traj_x) p.traj_x[o] = make_float2(x, y);
+                    if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
+                    if (p.traj_a) p.traj_a[o] = make_float2(s1.ax, s1.ay);
+                }
+                ++t;
+                sat_out = true;
+                if (hit) miss = 0;
+                else if (++miss >= 2) { T = 2; break; }  // left the wall: speculate again
+            }
+        }
+        const bool alive = t < n && !sat_out;
+        // ---- (1) list refresh at the current position -------------------------------------------------
+        {
+            const float M0 = fmaxf(sc.scale, fmaxf(fabsf(x), fabsf(y)));
+            const bool fast0 = !sc.weird && M0 <= 1.0e15f;
+            const float ddx = x - gl.cx, ddy = y - gl.cy;
+            const bool want = alive && fast0 && (trouble == 1 || !(ddx * ddx + ddy * ddy <= 0.25f * gl.rho2));
+            if (__any_sync(0xffffffffu, want)) {
+                if (want) j0 = glist_argmin(sc, x, y, gl, j0);
+                const float dstep = sqrtf(vx * vx + vy * vy) * c.dt;
+                const float rho = fminf(fmaxf(1.25f * (float)(kCullPeriod + 2 * G) * dstep, rho_min), rho_max);
+                glist_refresh<G>(sc, want ? x : 0.f, want ? y : 0.f, rho, c.r, lane, gbase, j0, want, gl);
+            }
+        }
+        // ---- (2) free flight: lane k keeps step t + k ---------------------------------------------------
+        const int Tq = alive ? min(T, n - t) : 0;
+        const int Tmax = __reduce_max_sync(0xffffffffu, Tq);
+        float sx = x, sy = y, svx = vx, svy = vy;  // state at the START of my step
+        State my; my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
+        bool ok = true;
+        {
+            float cx = x, cy = y, cvx = vx, cvy = vy;
+            const int last = min(lane, Tq - 1);
+            for (int k = 0; k < Tmax; ++k) {
+                if (k <= last) {
+                    sx = cx; sy = cy; svx = cvx; svy = cvy;
+                    ok = free_step_fast(cx, cy, cvx, cvy, c, my) && ok;
+                    cx = my.x; cy = my.y; cvx = my.vx; cvy = my.vy;
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, !ok)) {  // a numerator left the range of the fast division: redo exactly
+            float cx = x, cy = y, cvx = vx, cvy = vy;
+            const int last = min(lane, Tq - 1);
+            for (int k = 0; k < Tmax; ++k) {
+                if (k <= last) {
+                    sx = cx; sy = cy; svx = cvx; svy = cvy;
+                    free_step(cx, cy, cvx, cvy, c, my);
+                    cx = my.x; cy = my.y; cvx = my.vx; cvy = my.vy;
+                }
+            }
+        }
+        // ---- (3) my step against the list -------------------------------------------------------------------
+        const bool valid = lane < Tq;
+        const float px = valid ? my.x : x, py = valid ? my.y : y;
+        const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)));
+        const bool fast = !sc.weird && M <= 1.0e15f && trouble != 2;  // false for NaN / inf points
+        const float ddx = px - gl.cx, ddy = py - gl.cy;
+        const bool stale = fast && !(ddx * ddx + ddy * ddy <= gl.rho2);
+        const float amin = (fast && !stale) ? glist_min(sc, px, py, gl) : 0.0f;
+        const bool near = !fast || exact_idx || !(amin > gl.far2);
+        int idx = 0;
+        float dist = __int_as_float(0x7f800000);
+        if (valid && near && !stale) {  // exact distance and index for my own step (no warp primitives inside)
+            unsigned long long key = kNoKey;
+            if (fast) key = glist_exact(sc, px, py, __fmaf_rn(amin, kFilterOneEps, kFilterKappaPerM2 * M * M), gl.e, gl.cap, gl.cnt);
+            if (key == kNoKey) key = lane_exact<1>(sc, px, py, 0);  // not fast; or (cannot happen) an empty candidate set
+            unpack_key(key, idx, dist);
+        }
+        const bool hit = valid && !stale && (dist <= c.r);  // NaN -> false (ball_sim.py:164)
+        // ---- (4) first event of the group, commit ---------------------------------------------------------
+        const unsigned evb = (__ballot_sync(0xffffffffu, valid && (stale || hit)) >> gbase) & kLow;
+        const int f = evb ? (__ffs(evb) - 1) : Tq;       // lanes < f: free flight, final
+        const int hit_f = __shfl_sync(0xffffffffu, (int)hit, f < Tq ? f : 0, G);  // every lane executes the shuffle
+        const bool ev_hit = (f < Tq) && hit_f != 0;
+        State out = my;
+        float nx = __shfl_sync(0xffffffffu, my.x, f > 0 ? f - 1 : 0, G), ny = __shfl_sync(0xffffffffu, my.y, f > 0 ? f - 1 : 0, G);
+        float nvx = __shfl_sync(0xffffffffu, my.vx, f > 0 ? f - 1 : 0, G), nvy = __shfl_sync(0xffffffffu, my.vy, f > 0 ? f - 1 : 0, G);
+        if (f == 0) { nx = x; ny = y; nvx = vx; nvy = vy; }
+        if (__any_sync(0xffffffffu, ev_hit)) {  // resolve the collision of step t + f (all lanes of the group, redundantly)
+            const int src = ev_hit ? f : 0;
+            const float bx = __shfl_sync(0xffffffffu, sx, src, G), by = __shfl_sync(0xffffffffu, sy, src, G);
+            const float bvx = __shfl_sync(0xffffffffu, svx, src, G), bvy = __shfl_sync(0xffffffffu, svy, src, G);
+            State b1;
+            b1.x = __shfl_sync(0xffffffffu, my.x, src, G); b1.y = __shfl_sync(0xffffffffu, my.y, src, G);
+            b1.vx = __shfl_sync(0xffffffffu, my.vx, src, G); b1.vy = __shfl_sync(0xffffffffu, my.vy, src, G);
+            b1.ax = __shfl_sync(0xffffffffu, my.ax, src, G); b1.ay = __shfl_sync(0xffffffffu, my.ay, src, G);
+            const int hidx = __shfl_sync(0xffffffffu, idx, src, G);
+            if (ev_hit) {
+                const State r = resolve(bx, by, bvx, bvy, b1, sc.q[hidx], c);
+                if (lane == f) out = r;
+                nx = r.x; ny = r.y; nvx = r.vx; nvy = r.vy;
+            }
+        }
+        const int n_commit = f + (ev_hit ? 1 : 0);
+        if (active && lane < n_commit) {
+            const int ts = t + lane;
+            const bool h = ev_hit && lane == f;
+            if (hl) hl[(int64_t)ts * p.hl_st] = (int32_t)((uint32_t)((h || exact_idx) ? idx : 0) | ((uint32_t)h << 31));
+            if (p.ckpt && (ts % K) == 0) p.ckpt[(size_t)(ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
+            const size_t o = (size_t)ts * p.B + ball;
+            if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
+            if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
+            if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+        }
+        x = nx; y = ny; vx = nvx; vy = nvy;
+        t += n_commit;
+        // ---- (5) speculation length / trouble handling for the next round ---------------------------
+        if (sat_out) {
+            // contact mode this round: T / trouble were set there
+        } else if (f < Tq && !ev_hit) {      // the list did not cover step t + f
+            trouble = (f == 0) ? min(trouble + 1, 2) : 1;
+        } else {
+            trouble = 0;
+            if (ev_hit && f == 0) {          // colliding step after step: stop speculating, and rebuild the
+                if (T != 1) trouble = 1;     // list for the (now slow) ball: contact steps scan it serially
+                T = 1;
+            }
+            else T = min(2 * T, G);
+        }
+    }
+    if (active && lane == 0) {
+        p.xT[ball] = make_float2(x, y);
+        p.vT[ball] = make_float2(vx, vy);
+    }
+}
+
 // Small scenes (S_pad <= 256): every lane keeps ITS OWN segments (indices lane, lane+G, ...) in
 // registers for the whole rollout, so the estimate loop is straight-line code with no loads at
 // all (NV = S_pad / G visits, fully unrolled, candidates recorded in one 32-bit mask). The few
@@ -1231,8 +1459,36 @@ constexpr int64_t kTpMaxBalls = 65536;
 // (BASELINE configs[1]) runs fastest on the register-resident lane-split kernel with 8 lanes per
 // ball (0.63 ms vs 0.74 ms time-parallel); per-environment scenes, dense scenes and every other
 // batch size up to 65,536 run fastest time-parallel; beyond that one thread per ball wins.
-// Broad-phase (candidate list) lane-split kernel: flags bit 16 selects it, bit 15 forbids it.
-bool use_cull(const doper_rollout_desc* d) { return (d->flags & (1 << 16)) && !(d->flags & (1 << 15)); }
+// Broad-phase (candidate list) kernels are the default plan.  They are not used when the caller
+// forbids them (flags bit 15), forces the exact sweep (bit 0) or pins one of the full-sweep kernels
+// (lanes_per_ball != 0 or any of the kernel-selection bits 2-14) without forcing them (bit 16).
+// Measured on B200 (tools/tune_tp2.py, profiles/r1_plan_sweep.md): shared scene up to 8,192 balls ->
+// time-parallel variant with 16 lanes (steps) per ball; 8,192-32,767 balls -> lane-split, 4 lanes;
+// more -> one thread per ball; dense scenes (>= 2,048 segments) at least 2 lanes (the refresh scan
+// is split over them); per-environment scenes -> lane-split, 8 lanes (16 scenes staged per block).
+constexpr int kLegacyPlanBits = 4 | 8 | 0xF0 | 256 | 0x7E00;
+
+bool use_cull(const doper_rollout_desc* d) {
+    if ((d->flags & (1 << 15)) || (d->flags & 1)) return false;
+    if (d->flags & (1 << 16)) return true;
+    return d->lanes_per_ball == 0 && !(d->flags & kLegacyPlanBits);
+}
+
+bool use_tpc(const doper_rollout_desc* d) {
+    if (!use_cull(d)) return false;
+    if (d->lanes_per_ball != 0) return (d->flags & (1 << 18)) != 0 && d->lanes_per_ball >= 2;
+    if (d->flags & (1 << 18)) return true;
+    return !d->per_env && d->B <= 8192;
+}
+
+int cull_lanes(const doper_rollout_desc* d) {
+    if (d->lanes_per_ball != 0) return d->lanes_per_ball;
+    if (d->per_env) return 8;
+    if (use_tpc(d)) return 16;
+    int g = d->B < 32768 ? 4 : 1;
+    if (scene_layout(1, d->S).S_pad >= 2048 && g < 2) g = 2;
+    return g;
+}
 
 bool plan_reg8(const doper_rollout_desc* d) {
     return d->lanes_per_ball == 0 && !d->per_env && !(d->flags & 4) && scene_layout(1, d->S).S_pad <= 256 &&
@@ -1290,6 +1546,9 @@ int dispatch_fwd_tp2(cudaStream_t st, const FwdParams& p, int P, int wpb) {
     }
 }
 
+// lane = time step kernels write [B][n_steps] so that a group's stores are contiguous
+bool log_ball_major(const doper_rollout_desc* d) { return use_tp(d) || use_tpc(d); }
+
 int tp_warps_per_block(const doper_rollout_desc* d) {
     if (d->per_env) return 4;
     const size_t scene = (size_t)scene_layout(1, d->S).S_pad * 20;
@@ -1318,6 +1577,7 @@ bool plan_reg8(const doper_rollout_desc* d);
 // lanes per ball: enough threads to fill 148 SMs x 256 threads; per-env scenes are staged per
 // ball, so spreading one ball over 8 lanes keeps the shared-memory footprint per thread sane.
 int auto_lanes(const doper_rollout_desc* d) {
+    if (use_cull(d)) return cull_lanes(d);
     if (d->lanes_per_ball) return d->lanes_per_ball;
     if (plan_reg8(d)) return 8;
     if (d->per_env) return 8;
@@ -1378,6 +1638,20 @@ int launch_fwd_cull(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
     const int bpb = kFwdThreads / G;
     const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
     rollout_fwd_cull_kernel<G><<<grid, kFwdThreads, smem, st>>>(p);
+    return launch_status();
+}
+
+template <int G>
+int launch_fwd_tpc(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
+    const size_t smem = scene_smem + (size_t)(kFwdThreads / G) * kTpcListCap * sizeof(unsigned short);
+    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(rollout_fwd_tpc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+        return DOPER_ERR_SMEM_LIMIT;
+    const int bpb = kFwdThreads / G;
+    const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
+    rollout_fwd_tpc_kernel<G><<<grid, kFwdThreads, smem, st>>>(p);
     return launch_status();
 }
 
@@ -1476,7 +1750,7 @@ int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d) {
 
 int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
     if (validate_desc(d) != DOPER_OK) return 0;
-    return use_tp(d) ? 1 : 0;
+    return log_ball_major(d) ? 1 : 0;
 }
 
 size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d) {
@@ -1507,8 +1781,8 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
     const int K = resolve_K(d);
     FwdParams p;
-    p.hl_st = tp ? 1 : d->B;            // hit log is ball-major for the time-parallel kernel
-    p.hl_sb = tp ? d->n_steps : 1;
+    p.hl_st = log_ball_major(d) ? 1 : d->B;  // hit log is ball-major for the time-parallel kernels
+    p.hl_sb = log_ball_major(d) ? d->n_steps : 1;
     p.B = d->B; p.S = d->S; p.per_env = d->per_env ? 1 : 0; p.n_steps = d->n_steps; p.K = K;
     p.force_exact = d->flags & 1;
     p.exact_idx = (d->flags >> 17) & 1;
@@ -1538,6 +1812,16 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         const unsigned grid = (unsigned)((d->B + tp_wpb - 1) / tp_wpb);
         rollout_fwd_tp_kernel<<<grid, tp_wpb * 32, smem, st>>>(p);
         return launch_status();
+    }
+    if (use_tpc(d)) {
+        switch (G) {
+            case 1: return DOPER_ERR_UNSUPPORTED;
+            case 2: return launch_fwd_tpc<2>(st, p, smem);
+            case 4: return launch_fwd_tpc<4>(st, p, smem);
+            case 8: return launch_fwd_tpc<8>(st, p, smem);
+            case 16: return launch_fwd_tpc<16>(st, p, smem);
+            default: return launch_fwd_tpc<32>(st, p, smem);
+        }
     }
     if (use_cull(d)) {
         switch (G) {
@@ -1585,8 +1869,8 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     size_t off = (n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
     p.ckpt = reinterpret_cast<const float4*>(ws);
     p.hitlog = reinterpret_cast<const int32_t*>(reinterpret_cast<const unsigned char*>(ws) + off);
-    p.hl_st = use_tp(d) ? 1 : d->B;
-    p.hl_sb = use_tp(d) ? d->n_steps : 1;
+    p.hl_st = log_ball_major(d) ? 1 : d->B;
+    p.hl_sb = log_ball_major(d) ? d->n_steps : 1;
     p.xT_bar = reinterpret_cast<const float2*>(xT_bar);
     p.vT_bar = reinterpret_cast<const float2*>(vT_bar);
     p.x0_bar = reinterpret_cast<float2*>(x0_bar);

@@ -382,6 +382,93 @@ __device__ __forceinline__ int list_argmin(const SceneView& sc, float px, float 
     return (h >= 0 && h < sc.S) ? h : fallback;
 }
 
+// ---------------------------------------------------------------------------------------
+// per-BALL candidate list (time-parallel broad-phase kernel: the G lanes of a group hold G
+// consecutive time steps of one ball and all read the same list)
+// ---------------------------------------------------------------------------------------
+struct GroupList {
+    unsigned short* e;  // [cap] entries in shared memory, ascending segment index
+    int cap;
+    int cnt;            // > cap = overflow: sweep every segment
+    float cx, cy, rho2, far2;  // as CullState
+};
+
+// Every lane of the warp calls (warp-wide ballots); `doit` is uniform within a group.  Segment
+// i0 + lane of each stride-G slice is tested by lane `lane`; passing indices are appended in
+// ascending order (ballot + popc prefix inside the group).
+template <int G>
+__device__ __forceinline__ void glist_refresh(const SceneView& sc, float px, float py, float rho, float radius,
+                                              int lane, int gbase, int j0, bool doit, GroupList& gl) {
+    const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)) + rho);
+    const float e = sqrtf(approx_d2(px, py, sc.q[j0], sc.rl[j0])) * kCullUp;
+    const float w = __fmaf_rn(kCullDeltaPerM, M, rho + rho);
+    const float T = ((e + w) * (e + w)) * kCullUp;
+    const unsigned low = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    int cnt = 0;
+    for (int i0 = 0; i0 < sc.S_pad; i0 += G) {
+        const int i = i0 + lane;
+        const bool pass = doit && approx_d2(px, py, sc.q[i], sc.rl[i]) <= T;
+        const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> gbase) & low;
+        const int pos = cnt + __popc(gb & ((1u << lane) - 1u));
+        if (pass && pos < gl.cap) gl.e[pos] = (unsigned short)i;
+        cnt += __popc(gb);
+    }
+    __syncwarp();
+    if (doit) {
+        gl.cnt = cnt; gl.cx = px; gl.cy = py;
+        gl.rho2 = (kCullRhoCheck * rho) * (kCullRhoCheck * rho);
+        gl.far2 = cull_far2(radius, M);
+    }
+}
+
+// smallest estimate over the WHOLE list for this lane's own point
+__device__ __forceinline__ float glist_min(const SceneView& sc, float px, float py, const GroupList& gl) {
+    float amin = __int_as_float(0x7f800000);
+    if (gl.cnt > gl.cap) {
+        for (int i = 0; i < sc.S_pad; ++i) amin = fminf(amin, approx_d2(px, py, sc.q[i], sc.rl[i]));
+    } else {
+        int k = 0;
+        for (; k + 1 < gl.cnt; k += 2) {
+            const int i0 = gl.e[k], i1 = gl.e[k + 1];
+            const float a0 = approx_d2(px, py, sc.q[i0], sc.rl[i0]);
+            const float a1 = approx_d2(px, py, sc.q[i1], sc.rl[i1]);
+            amin = fminf(amin, fminf(a0, a1));
+        }
+        if (k < gl.cnt) { const int i = gl.e[k]; amin = fminf(amin, approx_d2(px, py, sc.q[i], sc.rl[i])); }
+    }
+    return amin;
+}
+
+// exact (distance, index) of the closest segment for this lane's own point, over the whole list
+__device__ __noinline__ unsigned long long glist_exact(const SceneView& sc, float px, float py, float thr,
+                                                       const unsigned short* e, int cap, int cnt) {
+    unsigned long long key = kNoKey;
+    const int n = cnt > cap ? sc.S_pad : cnt;
+    for (int k = 0; k < n; ++k) {
+        const int i = cnt > cap ? k : (int)e[k];
+        const float4 q = sc.q[i];
+        if (approx_d2(px, py, q, sc.rl[i]) <= thr) {
+            const unsigned long long kk = make_key(cand_dist(px, py, q), i);
+            key = kk < key ? kk : key;
+        }
+    }
+    return key;
+}
+
+// list entry with the smallest estimate at (px, py): seed of the next refresh (any index is valid)
+__device__ __forceinline__ int glist_argmin(const SceneView& sc, float px, float py, const GroupList& gl, int fallback) {
+    float amin = __int_as_float(0x7f800000);
+    int imin = fallback;
+    if (gl.cnt <= gl.cap) {
+        for (int k = 0; k < gl.cnt; ++k) {
+            const int i = gl.e[k];
+            const float a = approx_d2(px, py, sc.q[i], sc.rl[i]);
+            if (a < amin) { amin = a; imin = i; }
+        }
+    }
+    return (imin >= 0 && imin < sc.S) ? imin : fallback;
+}
+
 // Group-cooperative sweep. Every lane of the warp must call this (warp-wide sync primitives);
 // lanes of one group pass the same point. `prev_idx` in [0,S) is a hint (never trusted); < 0 =
 // no hint available.

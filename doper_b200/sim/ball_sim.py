@@ -40,7 +40,8 @@ class RolloutOptions:
     def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False,
                  sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True,
                  balls_per_warp: int = 0, single_ball_time_parallel: bool = False, warps_per_block: int = 0,
-                 broad_phase: bool = None, exact_index_log: bool = False):
+                 broad_phase: bool = None, exact_index_log: bool = False,
+                 broad_phase_time_parallel: bool = False):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
@@ -55,6 +56,7 @@ class RolloutOptions:
         # hit log: exact closest-segment index at EVERY step (default for the broad-phase kernel: at
         # collisions only, which is all the backward and the reference's outputs depend on)
         self.exact_index_log = bool(exact_index_log)
+        self.broad_phase_time_parallel = bool(broad_phase_time_parallel)  # lane = time step variant
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -97,7 +99,8 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
                ((opts.balls_per_warp & 0xF) << 4) | (256 if opts.single_ball_time_parallel else 0) |
                ((opts.warps_per_block & 0x3F) << 9) |
                ((1 << 16) if opts.broad_phase else 0) | ((1 << 15) if opts.broad_phase is False else 0) |
-               ((1 << 17) if opts.exact_index_log else 0))
+               ((1 << 17) if opts.exact_index_log else 0) |
+               ((1 << 18) if opts.broad_phase_time_parallel else 0))
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d

@@ -39,7 +39,7 @@ def test_rollout_forward_bitexact_all_lane_counts(sim, cref, lanes, exact, smem)
     assert ref["hit"].sum() > 30
     got = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], w["constants"],
                                    _opts(ball_sim, lanes_per_ball=lanes, force_exact_sweep=exact, ckpt_every=16,
-                                         smem_forward=smem),
+                                         smem_forward=smem, exact_index_log=True),
                                    want_trajectory=True)
     assert np.array_equal(got["idx"], ref["idx"]), "closest-segment indices"
     assert np.array_equal(got["hit"], ref["hit"]), "hit flags"
@@ -92,9 +92,10 @@ def test_time_parallel_kernels_bitexact(sim, cref, bpw, legacy, regime):
         assert_bitexact(got["checkpoints"][k, :, 2:], ref["traj_v"][11 * k - 1], f"ckpt {k} v")
 
 
+@pytest.mark.parametrize("tp", [False, True])
 @pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
 @pytest.mark.parametrize("regime", ["reference", "bouncy", "fast_balls", "per_env", "dense", "every_index"])
-def test_broad_phase_kernel_bitexact(sim, cref, lanes, regime):
+def test_broad_phase_kernel_bitexact(sim, cref, lanes, regime, tp):
     """Candidate-list (broad phase) forward: the list provably contains the argmin and its ties, so
     indices, hit flags, states and trajectories must equal the full sweep's / the oracle's bits."""
     ball_sim, geo = sim
@@ -103,6 +104,8 @@ def test_broad_phase_kernel_bitexact(sim, cref, lanes, regime):
     rng = np.random.default_rng(5)
     if regime == "per_env" and lanes < 4:
         pytest.skip("per-environment scenes are staged per ball: 128 / lanes scenes must fit shared memory")
+    if tp and lanes == 1:
+        pytest.skip("lane = time step needs at least two lanes per ball")
     if regime == "per_env":
         segs = syn.make_env_maps(21, B, 67)
         x0, v0 = syn.make_init_states(22, B, segs)
@@ -126,7 +129,7 @@ def test_broad_phase_kernel_bitexact(sim, cref, lanes, regime):
     assert ref["hit"].sum() > (1500 if regime == "bouncy" else 5)
     got = ball_sim.rollout_history(n / 1000, n, scene, x0, v0, A, consts,
                                    _opts(ball_sim, lanes_per_ball=lanes, broad_phase=True, ckpt_every=11,
-                                         exact_index_log=(regime == "every_index")),
+                                         exact_index_log=(regime == "every_index"), broad_phase_time_parallel=tp),
                                    want_trajectory=True)
     assert np.array_equal(got["hit"], ref["hit"]), "hit flags"
     assert np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]]), "collision segment indices"
@@ -213,7 +216,7 @@ def test_bouncy_regime_many_collisions(sim, cref, lanes):
                            want_traj=True)
     assert ref["hit"].sum() > 3000 and ref["hit"].sum(0).max() > 100
     got = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], consts,
-                                   _opts(ball_sim, lanes_per_ball=lanes), want_trajectory=True)
+                                   _opts(ball_sim, lanes_per_ball=lanes, exact_index_log=True), want_trajectory=True)
     assert np.array_equal(got["idx"], ref["idx"]) and np.array_equal(got["hit"], ref["hit"])
     assert_bitexact(got["x_T"], ref["x_T"], "x_T")
     assert_bitexact(got["trajectory"].velocity, ref["traj_v"], "trajectory v")
@@ -298,7 +301,7 @@ def test_per_env_scenes(sim, cref):
     scene = geo.create_env_scenes(segs)
     for lanes in (0, 4, 32):
         h = ball_sim.rollout_history(n / 1000, n, scene, x0, v0, A, syn.reference_constants(),
-                                     _opts(ball_sim, lanes_per_ball=lanes))
+                                     _opts(ball_sim, lanes_per_ball=lanes, exact_index_log=True))
         assert np.array_equal(h["idx"], ref["idx"]) and np.array_equal(h["hit"], ref["hit"])
         assert_bitexact(h["x_T"], ref["x_T"])
     (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, scene, x0, v0, T, A, syn.reference_constants(),
@@ -348,8 +351,11 @@ def test_dense_scene_10k_segments(sim, cref):
     c = onp.make_constants(w["constants"])
     ref = cref.value_and_grad(n, np.float32((n / 1000) / n), c, w["attractor"], w["target"], w["segments"], w["x0"],
                               w["v0"])
-    h = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], w["constants"])
+    h = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], w["constants"],
+                                 _opts(ball_sim, exact_index_log=True))
     assert np.array_equal(h["idx"], ref["idx"]) and np.array_equal(h["hit"], ref["hit"])
+    h = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], w["constants"])
+    assert np.array_equal(h["hit"], ref["hit"]) and np.array_equal(h["idx"][ref["hit"]], ref["idx"][ref["hit"]])
     assert_bitexact(h["x_T"], ref["x_T"])
 
 

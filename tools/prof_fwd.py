@@ -18,7 +18,9 @@ from doper_b200.sim.jax_geometry import JaxScene  # noqa: E402
 name, var = sys.argv[1], sys.argv[2]
 balls = int(sys.argv[3]) if len(sys.argv) > 3 and int(sys.argv[3]) > 0 else None
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
-w = syn.make_workload(name, n_balls=balls)
+lo = int(sys.argv[5]) if len(sys.argv) > 6 else 0
+hi = int(sys.argv[6]) if len(sys.argv) > 6 else None
+w = syn.make_workload(name, n_balls=balls, lo=lo, hi=hi)
 B, n = w["x0"].shape[0], w["n_steps"]
 dev = torch.device("cuda", 0)
 scene = JaxScene(w["segments"])
@@ -27,6 +29,8 @@ x0, v0 = torch.tensor(w["x0"], device=dev), torch.tensor(w["v0"], device=dev)
 st = torch.cuda.current_stream().cuda_stream
 if var == "default":
     kw = {}
+elif var.startswith("tpc"):
+    kw = dict(lanes_per_ball=int(var[3:]), broad_phase=True, broad_phase_time_parallel=True)
 elif var.startswith("cull"):
     kw = dict(lanes_per_ball=int(var[4:]), broad_phase=True)
 elif var == "tp1":

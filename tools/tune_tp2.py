@@ -45,11 +45,12 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     tgt = ball_sim._target2(w["target"])
     out = {"workload": name, "B": B, "n_steps": n, "S": int(w["segments"].shape[-3]), "fwd_ms": {}}
-    variants = [("default", {})]
+    variants = [("default", {}), ("nocull", dict(broad_phase=False))]
     variants += [(f"tp2_P{P}_w{W}", dict(balls_per_warp=P, warps_per_block=W, smem_forward=True))
                  for P in (1, 2, 4, 8) for W in (4, 2)]
     variants += [("tp1", dict(single_ball_time_parallel=True, smem_forward=True))]
     variants += [(f"cull_G{g}", dict(lanes_per_ball=g, broad_phase=True)) for g in (1, 2, 4, 8, 16, 32)]
+    variants += [(f"tpc_G{g}", dict(lanes_per_ball=g, broad_phase=True, broad_phase_time_parallel=True)) for g in (2, 4, 8, 16, 32)]
     only = [a[5:] for a in sys.argv if a.startswith("only=")]
     if only:
         variants = [v for v in variants if any(v[0].startswith(o) for o in only[0].split(","))]
