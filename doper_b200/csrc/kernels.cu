@@ -164,6 +164,7 @@ struct FwdParams {
     float2* traj_v;
     float2* traj_a;
     float4* ckpt;     // [n_ckpt][B]
+    float4* hitstate; // [n_steps][B], written at collided steps only: the state at the START of the step
     int32_t* hitlog;  // element (t, ball) at t * hl_st + ball * hl_sb
     int64_t hl_st, hl_sb;
 };
@@ -223,14 +224,16 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_kernel(const FwdParam
         --until_ckpt;
         State s1;
         free_step(x, y, vx, vy, c, s1);
+        const uint32_t clipb = clip_bits(vx, vy);
         int idx; float dist;
         sweep_any<G>(sc, s1.x, s1.y, lane, prev_idx, idx, dist);
         prev_idx = idx;
         const bool hit = dist <= c.r;  // NaN -> false (ball_sim.py:164)
+        if (hit && writer && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
         if (hit) s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c);
         x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
         if (writer) {
-            if (hl) { *hl = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31)); hl += p.hl_st; }
+            if (hl) { *hl = pack_log(idx, hit, clipb); hl += p.hl_st; }
             if (tx) { *tx = make_float2(x, y); tx += p.B; }
             if (tv) { *tv = make_float2(vx, vy); tv += p.B; }
             if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += p.B; }
@@ -364,14 +367,16 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_cull_kernel(const Fwd
                 hit = dist <= c.r;  // NaN -> false (ball_sim.py:164)
             }
         }
+        const uint32_t clipb = clip_bits(vx, vy);
         if (hit) {
+            if (writer && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
             s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c);
             x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
         } else {
             x = px; y = py; vx = s1.vx; vy = s1.vy;
         }
         if (writer) {
-            if (hl) { *hl = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31)); hl += p.hl_st; }
+            if (hl) { *hl = pack_log(idx, hit, clipb); hl += p.hl_st; }
             if (tx) { *tx = make_float2(x, y); tx += p.B; }
             if (tv) { *tv = make_float2(vx, vy); tv += p.B; }
             if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += p.B; }
@@ -481,10 +486,12 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
                 if (active && lane == 0) {
                     if (p.ckpt && (t % K) == 0) p.ckpt[(size_t)(t / K) * p.B + ball] = make_float4(x, y, vx, vy);
                 }
+                const uint32_t clipb = clip_bits(vx, vy);
+                if (hit && active && lane == 0 && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
                 if (hit) s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c);
                 x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
                 if (active && lane == 0) {
-                    if (hl) hl[(int64_t)t * p.hl_st] = (int32_t)((uint32_t)((hit || exact_idx) ? idx : 0) | ((uint32_t)hit << 31));
+                    if (hl) hl[(int64_t)t * p.hl_st] = pack_log((hit || exact_idx) ? idx : 0, hit, clipb);
                     const size_t o = (size_t)t * p.B + ball;
                     if (p.traj_x) p.traj_x[o] = make_float2(x, y);
                     if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
@@ -584,7 +591,8 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
         if (active && lane < n_commit) {
             const int ts = t + lane;
             const bool h = ev_hit && lane == f;
-            if (hl) hl[(int64_t)ts * p.hl_st] = (int32_t)((uint32_t)((h || exact_idx) ? idx : 0) | ((uint32_t)h << 31));
+            if (hl) hl[(int64_t)ts * p.hl_st] = pack_log((h || exact_idx) ? idx : 0, h, clip_bits(svx, svy));
+            if (h && p.hitstate) p.hitstate[(size_t)ts * p.B + ball] = make_float4(sx, sy, svx, svy);
             if (p.ckpt && (ts % K) == 0) p.ckpt[(size_t)(ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
             const size_t o = (size_t)ts * p.B + ball;
             if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
@@ -685,6 +693,7 @@ rollout_fwd_reg_kernel(const FwdParams p) {
         --until_ckpt;
         State s1;
         free_step(x, y, vx, vy, c, s1);
+        const uint32_t clipb = clip_bits(vx, vy);
         const float px = s1.x, py = s1.y;
         const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)));
         unsigned long long key;
@@ -714,10 +723,11 @@ rollout_fwd_reg_kernel(const FwdParams p) {
         unpack_key(key, idx, dist);
         prev_idx = idx;
         const bool hit = dist <= c.r;  // NaN -> false (ball_sim.py:164)
+        if (hit && writer && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
         if (hit) s1 = resolve(x, y, vx, vy, s1, __ldg(gq + idx), c);
         x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
         if (writer) {
-            if (hl) { *hl = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31)); hl += p.hl_st; }
+            if (hl) { *hl = pack_log(idx, hit, clipb); hl += p.hl_st; }
             if (tx) { *tx = make_float2(x, y); tx += stride; }
             if (tv) { *tv = make_float2(vx, vy); tv += stride; }
             if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += stride; }
@@ -785,15 +795,17 @@ __global__ void __launch_bounds__(1024) rollout_fwd_tp_kernel(const FwdParams p)
             if (p.ckpt && (t % K) == 0 && lane == 0) p.ckpt[(size_t)(t / K) * p.B + ball] = make_float4(x, y, vx, vy);
             State s1;
             free_step(x, y, vx, vy, c, s1);
+            const uint32_t clipb = clip_bits(vx, vy);
             int idx; float dist;
             sweep_any<32>(sc, s1.x, s1.y, lane, prev_idx, idx, dist);
             prev_idx = idx;
             const bool hit = dist <= c.r;
+            if (hit && lane == 0 && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
             if (hit) { s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c); seq_left = kTpSeqSteps; }
             x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
             if (lane == 0) {
                 const size_t o = (size_t)t * p.B + ball;
-                if (hl) hl[(size_t)t * p.hl_st] = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31));
+                if (hl) hl[(size_t)t * p.hl_st] = pack_log(idx, hit, clipb);
                 if (p.traj_x) p.traj_x[o] = make_float2(x, y);
                 if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
                 if (p.traj_a) p.traj_a[o] = make_float2(s1.ax, s1.ay);
@@ -850,7 +862,8 @@ __global__ void __launch_bounds__(1024) rollout_fwd_tp_kernel(const FwdParams p)
         prev_idx = __shfl_sync(0xffffffffu, idx, n_commit - 1);
         if (lane < n_commit) {
             const int ts = t + lane;
-            if (hl) hl[(size_t)ts * p.hl_st] = (int32_t)((uint32_t)idx | ((uint32_t)(lane == first) << 31));
+            if (hl) hl[(size_t)ts * p.hl_st] = pack_log(idx, lane == first, clip_bits(svx, svy));
+            if (lane == first && p.hitstate) p.hitstate[(size_t)ts * p.B + ball] = make_float4(sx, sy, svx, svy);
             if (p.ckpt && (ts % K) == 0) p.ckpt[(size_t)(ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
             const size_t o = (size_t)ts * p.B + ball;
             if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
@@ -962,15 +975,17 @@ __global__ void __launch_bounds__(kTp2Threads) rollout_fwd_tp2_kernel(const FwdP
                     if (p.ckpt && (tq % K) == 0 && lane == 0) p.ckpt[(size_t)(tq / K) * p.B + ball] = make_float4(x, y, vx, vy);
                     State s1;
                     free_step(x, y, vx, vy, c, s1);
+                    const uint32_t clipb = clip_bits(vx, vy);
                     int idx; float dist;
                     sweep_any<32>(s, s1.x, s1.y, lane, pv, idx, dist);
                     pv = idx;
                     const bool hit = dist <= c.r;
+                    if (hit && lane == 0 && p.hitstate) p.hitstate[(size_t)tq * p.B + ball] = make_float4(x, y, vx, vy);
                     if (hit) { s1 = resolve(x, y, vx, vy, s1, s.q[idx], c); sl = kTpSeqSteps; }
                     x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
                     if (lane == 0) {
                         const size_t o = (size_t)tq * p.B + ball;
-                        if (p.hitlog) p.hitlog[ball * p.hl_sb + (int64_t)tq * p.hl_st] = (int32_t)((uint32_t)idx | ((uint32_t)hit << 31));
+                        if (p.hitlog) p.hitlog[ball * p.hl_sb + (int64_t)tq * p.hl_st] = pack_log(idx, hit, clipb);
                         if (p.traj_x) p.traj_x[o] = make_float2(x, y);
                         if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
                         if (p.traj_a) p.traj_a[o] = make_float2(s1.ax, s1.ay);
@@ -1102,7 +1117,8 @@ __global__ void __launch_bounds__(kTp2Threads) rollout_fwd_tp2_kernel(const FwdP
             const int t0 = wb.t[q];
             if (lane < n_commit) {
                 const int ts = t0 + lane;
-                if (p.hitlog) p.hitlog[ball * p.hl_sb + (int64_t)ts * p.hl_st] = (int32_t)((uint32_t)idx | ((uint32_t)(lane == first) << 31));
+                if (p.hitlog) p.hitlog[ball * p.hl_sb + (int64_t)ts * p.hl_st] = pack_log(idx, lane == first, clip_bits(pre.z, pre.w));
+                if (lane == first && p.hitstate) p.hitstate[(size_t)ts * p.B + ball] = pre;
                 if (p.ckpt && (ts % K) == 0) p.ckpt[(size_t)(ts / K) * p.B + ball] = pre;
                 const size_t o = (size_t)ts * p.B + ball;
                 if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
@@ -1132,6 +1148,7 @@ struct BwdParams {
     Consts c;
     const unsigned char* scene_ws;
     const float4* ckpt;
+    const float4* hitstate;  // nullable: [n_steps][B] states at the start of collided steps
     const int32_t* hitlog;  // element (t, ball) at t * hl_st + ball * hl_sb
     int64_t hl_st, hl_sb;
     const float2* xT_bar;
@@ -1140,9 +1157,15 @@ struct BwdParams {
     float2* v0_bar;
 };
 
+// Sequential backward, one thread per ball, bit-exact against the oracle's adjoint.  A step that
+// did not collide is pulled back from its log word alone (step_vjp_free: no state, no replay);
+// only a K-block that contains a collision is replayed from its checkpoint (with the logged
+// indices), up to its last collision, into the shared-memory stash.
+constexpr int kBwdPrefetch = 16;  // log words fetched ahead per thread (independent loads in flight)
+
 __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    float4* stash = reinterpret_cast<float4*>(smem);  // [K][kBwdThreads]
+    float4* stash = reinterpret_cast<float4*>(smem);  // [K][kBwdThreads], replay fallback only
     const int tid = threadIdx.x;
     const int64_t ball = (int64_t)blockIdx.x * kBwdThreads + tid;
     if (ball >= p.B) return;
@@ -1150,30 +1173,60 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
     const float4* q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) +
                       (p.per_env ? (size_t)ball * L.S_pad : 0);
     const Consts c = p.c;
+    const float dk = dfric_value(c);
     float2 g = p.xT_bar[ball];
     float gx = g.x, gy = g.y, gvx = 0.0f, gvy = 0.0f;
     if (p.vT_bar) { float2 h = p.vT_bar[ball]; gvx = h.x; gvy = h.y; }
+    const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
 
     const int n_ckpt = (p.n_steps + p.K - 1) / p.K;
     for (int ck = n_ckpt - 1; ck >= 0; --ck) {
         const int t0 = ck * p.K, t1 = min(p.n_steps, t0 + p.K);
-        float4 s = p.ckpt[(size_t)ck * p.B + ball];
-        // replay the block from its checkpoint with the logged (idx, hit): bit-identical states
-        for (int t = t0; t < t1; ++t) {
-            stash[(size_t)(t - t0) * kBwdThreads + tid] = s;
-            if (t + 1 < t1) {
-                const int32_t h = p.hitlog[(size_t)t * p.hl_st + (size_t)ball * p.hl_sb];
-                State s1;
-                free_step(s.x, s.y, s.z, s.w, c, s1);
-                if (h < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (h & 0x7fffffff)), c);
-                s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
+        int have = -1;  // states of steps t0 .. t0 + have are in the stash
+        for (int tb = t1; tb > t0;) {
+            // the log words of steps [ta, tb): kBwdPrefetch independent loads, then a latency-free loop
+            const int ta = max(t0, tb - kBwdPrefetch);
+            // condensed into three bit masks (bit j = step ta + j), so the processing loop stays compact
+            unsigned m_hit = 0u, m_cx = 0u, m_cy = 0u;
+#pragma unroll
+            for (int j = 0; j < kBwdPrefetch; ++j) {
+                const uint32_t w = (ta + j < tb) ? (uint32_t)hl[(size_t)(ta + j) * p.hl_st] : 0u;
+                m_hit |= (w >> 31) << j;
+                m_cx |= ((w >> 29) & 1u) << j;
+                m_cy |= ((w >> 30) & 1u) << j;
             }
-        }
-        for (int t = t1 - 1; t >= t0; --t) {
-            const float4 st = stash[(size_t)(t - t0) * kBwdThreads + tid];
-            const int32_t h = p.hitlog[(size_t)t * p.hl_st + (size_t)ball * p.hl_sb];
-            const float4 seg = __ldg(q + (h & 0x7fffffff));
-            step_vjp(st.x, st.y, st.z, st.w, h < 0, seg, c, gx, gy, gvx, gvy);
+            for (int t = tb - 1; t >= ta; --t) {
+                const int j = t - ta;
+                if (!((m_hit >> j) & 1u)) {
+                    step_vjp_free_1d(((m_cx >> j) & 1u) != 0u, dk, c, gx, gvx);
+                    step_vjp_free_1d(((m_cy >> j) & 1u) != 0u, dk, c, gy, gvy);
+                    continue;
+                }
+                const int32_t h = hl[(size_t)t * p.hl_st];  // collided step: the index is needed (rare reload)
+                float4 st;
+                if (p.hitstate) {
+                    st = p.hitstate[(size_t)t * p.B + ball];  // the forward kept the state of every collided step
+                } else {
+                    if (have < 0) {  // first (= latest) collision of the block: replay t0 .. t, bit-identical states
+                        float4 s = p.ckpt[(size_t)ck * p.B + ball];
+                        for (int u = t0; u <= t; ++u) {
+                            stash[(size_t)(u - t0) * kBwdThreads + tid] = s;
+                            if (u < t) {
+                                const int32_t hu = hl[(size_t)u * p.hl_st];
+                                State s1;
+                                free_step(s.x, s.y, s.z, s.w, c, s1);
+                                if (hu < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (hu & kLogIdx)), c);
+                                s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
+                            }
+                        }
+                        have = t - t0;
+                    }
+                    st = stash[(size_t)(t - t0) * kBwdThreads + tid];
+                }
+                const float4 seg = __ldg(q + (h & kLogIdx));
+                step_vjp(st.x, st.y, st.z, st.w, true, seg, c, gx, gy, gvx, gvy);
+            }
+            tb = ta;
         }
     }
     p.v0_bar[ball] = make_float2(gvx, gvy);
@@ -1181,18 +1234,16 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
 }
 
 // Chunk-parallel backward for small batches (few balls cannot fill 148 SMs with one thread per
-// ball): thread (ball, chunk) replays its K-step chunk from the chunk's checkpoint, stashes the
-// states, and pulls the four basis cotangents e_0..e_3 back through the chunk, which yields the
-// chunk's transposed Jacobian M_c = J_t0^T ... J_t1-1^T (4x4; the step adjoint is linear in the
-// cotangent, and the recomputed step internals are shared by the four pulls).  One thread per
-// ball then folds g <- M_c g from the last chunk to the first.  Same mathematics as the
-// sequential kernel, different rounding order (tolerance-checked, not bit-exact).
-struct ChunkGeom { int C_pad; int balls_per_block; };
-
-__global__ void __launch_bounds__(kBwdThreads, 7) rollout_bwd_chunked_kernel(const BwdParams p, const int C_pad) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    float4* stash = reinterpret_cast<float4*>(smem);  // [K][threads]
-    float* mats = reinterpret_cast<float*>(smem);     // [threads][16], aliases the stash once it is dead
+// ball): thread (ball, chunk) pulls the four basis cotangents e_0..e_3 back through its K-step
+// chunk, which yields the chunk's transposed Jacobian M_c = J_t0^T ... J_t1-1^T (4x4; the step
+// adjoint is linear in the cotangent).  Free-flight steps come from the log word alone; a chunk
+// with a collision is replayed from its checkpoint first.  One thread per ball then folds
+// g <- M_c g from the last chunk to the first.  Same mathematics as the sequential kernel,
+// different rounding order (tolerance-checked, not bit-exact).
+// No block-wide synchronisation: a ball's C_pad <= 32 chunks sit in one warp, the fold runs on warp
+// shuffles.  Until a chunk meets a collision its Jacobian is block diagonal (x and y decouple in
+// free flight), so only the four non-zero (position, velocity) pairs are pulled back.
+__global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const BwdParams p, const int C_pad) {
     const int tid = threadIdx.x;
     const int bpb = kBwdThreads / C_pad;
     const int chunk = tid % C_pad, slot = tid / C_pad;
@@ -1200,6 +1251,7 @@ __global__ void __launch_bounds__(kBwdThreads, 7) rollout_bwd_chunked_kernel(con
     const int n_ckpt = (p.n_steps + p.K - 1) / p.K;
     const bool active = ball < p.B && chunk < n_ckpt;
     const Consts c = p.c;
+    const float dk = dfric_value(c);
     const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
     float g[4][4];  // g[k] = pull-back of e_k through this thread's chunk
 #pragma unroll
@@ -1211,50 +1263,82 @@ __global__ void __launch_bounds__(kBwdThreads, 7) rollout_bwd_chunked_kernel(con
                           (p.per_env ? (size_t)ball * L.S_pad : 0);
         const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
         const int t0 = chunk * p.K, t1 = min(p.n_steps, t0 + p.K);
-        // replay the chunk; only every other state is stashed (the whole batch's states would not
-        // fit the SMs' shared memory in one wave otherwise): odd steps are re-derived on the way back
-        float4 s = p.ckpt[(size_t)chunk * p.B + ball];
-        auto advance = [&](const float4& a, int32_t h) {
-            State s1;
-            free_step(a.x, a.y, a.z, a.w, c, s1);
-            if (h < 0) s1 = resolve(a.x, a.y, a.z, a.w, s1, __ldg(q + (h & 0x7fffffff)), c);
-            return make_float4(s1.x, s1.y, s1.vx, s1.vy);
-        };
-        for (int t = t0; t < t1; ++t) {
-            if (((t - t0) & 1) == 0) stash[(size_t)((t - t0) >> 1) * kBwdThreads + tid] = s;
-            if (t + 1 < t1) s = advance(s, hl[(size_t)t * p.hl_st]);
-        }
-        for (int t = t1 - 1; t >= t0; --t) {
-            const int j = t - t0;
-            float4 st = stash[(size_t)(j >> 1) * kBwdThreads + tid];
-            if (j & 1) st = advance(st, hl[(size_t)(t - 1) * p.hl_st]);
-            const int32_t h = hl[(size_t)t * p.hl_st];
-            const float4 seg = __ldg(q + (h & 0x7fffffff));
+        bool coupled = false;  // a collision has mixed x and y
+        for (int tb = t1; tb > t0;) {
+            const int ta = max(t0, tb - kBwdPrefetch);
+            unsigned m_hit = 0u, m_cx = 0u, m_cy = 0u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                step_vjp(st.x, st.y, st.z, st.w, h < 0, seg, c, g[k][0], g[k][1], g[k][2], g[k][3]);
+            for (int j = 0; j < kBwdPrefetch; ++j) {
+                const uint32_t w = (ta + j < tb) ? (uint32_t)hl[(size_t)(ta + j) * p.hl_st] : 0u;
+                m_hit |= (w >> 31) << j;
+                m_cx |= ((w >> 29) & 1u) << j;
+                m_cy |= ((w >> 30) & 1u) << j;
+            }
+            if (m_hit == 0u && !coupled) {  // free flight, decoupled: 4 (position, velocity) pairs per step
+                for (int j = tb - ta - 1; j >= 0; --j) {
+                    const bool cx = ((m_cx >> j) & 1u) != 0u, cy = ((m_cy >> j) & 1u) != 0u;
+                    step_vjp_free_1d(cx, dk, c, g[0][0], g[0][2]);
+                    step_vjp_free_1d(cx, dk, c, g[2][0], g[2][2]);
+                    step_vjp_free_1d(cy, dk, c, g[1][1], g[1][3]);
+                    step_vjp_free_1d(cy, dk, c, g[3][1], g[3][3]);
+                }
+            } else {
+                for (int t = tb - 1; t >= ta; --t) {
+                    const int32_t h = hl[(size_t)t * p.hl_st];
+                    if (h >= 0) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) step_vjp_free((uint32_t)h, dk, c, g[k][0], g[k][1], g[k][2], g[k][3]);
+                        continue;
+                    }
+                    float4 st;
+                    if (p.hitstate) {
+                        st = p.hitstate[(size_t)t * p.B + ball];
+                    } else {  // no hit-state array: replay t0 .. t from the chunk's checkpoint (<= K steps)
+                        st = p.ckpt[(size_t)chunk * p.B + ball];
+                        for (int u = t0; u < t; ++u) {
+                            const int32_t hu = hl[(size_t)u * p.hl_st];
+                            State s1;
+                            free_step(st.x, st.y, st.z, st.w, c, s1);
+                            if (hu < 0) s1 = resolve(st.x, st.y, st.z, st.w, s1, __ldg(q + (hu & kLogIdx)), c);
+                            st = make_float4(s1.x, s1.y, s1.vx, s1.vy);
+                        }
+                    }
+                    const float4 seg = __ldg(q + (h & kLogIdx));
+                    {   // through a copy: the out-of-line call takes its array by reference (local memory), and
+                        // g itself must stay in registers for the straight-line free-flight path
+                        float tmp[4][4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int r2 = 0; r2 < 4; ++r2) tmp[k][r2] = g[k][r2];
+                        step_vjp_hit_n<4>(st.x, st.y, st.z, st.w, seg, c, tmp);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int r2 = 0; r2 < 4; ++r2) g[k][r2] = tmp[k][r2];
+                    }
+                    coupled = true;
+                }
+            }
+            tb = ta;
         }
     }
-    __syncthreads();  // every stash column has been consumed: the region becomes `mats`
-    if (active) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<float4*>(mats + (size_t)tid * 16 + k * 4) = make_float4(g[k][0], g[k][1], g[k][2], g[k][3]);
+    // fold g <- M_c g from the last chunk to the first; lane `chunk` of the ball's C_pad lanes holds M_c
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ball < p.B) {
+        const float2 gg = p.xT_bar[ball];
+        v[0] = gg.x; v[1] = gg.y;
+        if (p.vT_bar) { const float2 h = p.vT_bar[ball]; v[2] = h.x; v[3] = h.y; }
     }
-    __syncthreads();
+    for (int cc = n_ckpt - 1; cc >= 0; --cc) {
+        float o[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            o[r] = (v[0] * g[0][r] + v[1] * g[1][r]) + (v[2] * g[2][r] + v[3] * g[3][r]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = __shfl_sync(0xffffffffu, o[r], cc, C_pad);  // chunk cc's product
+    }
     if (ball < p.B && chunk == 0) {
-        float2 gg = p.xT_bar[ball];
-        float v[4] = {gg.x, gg.y, 0.0f, 0.0f};
-        if (p.vT_bar) { float2 h = p.vT_bar[ball]; v[2] = h.x; v[3] = h.y; }
-        for (int cc = n_ckpt - 1; cc >= 0; --cc) {
-            const float* M = mats + (size_t)(tid + cc) * 16;
-            float o[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                o[r] = (v[0] * M[r] + v[1] * M[4 + r]) + (v[2] * M[8 + r] + v[3] * M[12 + r]);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) v[r] = o[r];
-        }
         p.v0_bar[ball] = make_float2(v[2], v[3]);
         if (p.x0_bar) p.x0_bar[ball] = make_float2(v[0], v[1]);
     }
@@ -1449,6 +1533,29 @@ int resolve_K(const doper_rollout_desc* d) {
         if (K <= kChunkedMaxK) return K < 4 ? 4 : K;
     }
     return 16;  // sequential backward: 32 KB of stash per 128-thread block -> 7 blocks per SM
+}
+
+// Backward workspace: [checkpoints n_ckpt x B x 16 B | hit log n x B x 4 B | hit states n x B x 16 B].
+// The hit-state array is written and read at collided steps only (no bandwidth; it spares the
+// backward every replay); flags bit 19 drops it (memory: 16 B per ball-step) and the backward
+// replays blocks with a collision from their checkpoint instead.
+struct WsLayout { size_t log_off, state_off, total; };
+
+WsLayout ws_layout(const doper_rollout_desc* d) {
+    const int K = resolve_K(d);
+    const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
+    WsLayout w;
+    w.log_off = (n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
+    size_t end = w.log_off + (size_t)d->n_steps * (size_t)d->B * sizeof(int32_t);
+    end = (end + 255) / 256 * 256;
+    w.state_off = 0;
+    if (!(d->flags & (1 << 19))) {
+        w.state_off = end;
+        end += (size_t)d->n_steps * (size_t)d->B * sizeof(float4);
+        end = (end + 255) / 256 * 256;
+    }
+    w.total = end + 256;
+    return w;
 }
 
 // Forward plan: time-parallel kernel (one warp per ball) unless the caller pinned a lane count,
@@ -1755,12 +1862,8 @@ int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
 
 size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d) {
     if (validate_desc(d) != DOPER_OK) return 0;
-    const int K = resolve_K(d);
-    const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
-    size_t bytes = n_ckpt * (size_t)d->B * sizeof(float4);
-    bytes = (bytes + 255) / 256 * 256;
-    bytes += (size_t)d->n_steps * (size_t)d->B * sizeof(int32_t);
-    return (bytes + 255) / 256 * 256 + 256;
+    const WsLayout w = ws_layout(d);
+    return w.total;
 }
 
 int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
@@ -1792,12 +1895,13 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     p.xT = reinterpret_cast<float2*>(xT); p.vT = reinterpret_cast<float2*>(vT);
     p.traj_x = reinterpret_cast<float2*>(traj_x); p.traj_v = reinterpret_cast<float2*>(traj_v);
     p.traj_a = reinterpret_cast<float2*>(traj_a);
-    p.ckpt = nullptr; p.hitlog = nullptr;
+    p.ckpt = nullptr; p.hitlog = nullptr; p.hitstate = nullptr;
     if (ws) {
-        const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
-        size_t off = (n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
-        p.ckpt = reinterpret_cast<float4*>(ws);
-        p.hitlog = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(ws) + off);
+        const WsLayout w = ws_layout(d);
+        unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+        p.ckpt = reinterpret_cast<float4*>(base);
+        p.hitlog = reinterpret_cast<int32_t*>(base + w.log_off);
+        if (w.state_off) p.hitstate = reinterpret_cast<float4*>(base + w.state_off);
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (tp && use_tp2(d)) {
@@ -1866,9 +1970,11 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     p.c = make_consts(d);
     p.scene_ws = reinterpret_cast<const unsigned char*>(scene_ws);
     const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
-    size_t off = (n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
-    p.ckpt = reinterpret_cast<const float4*>(ws);
-    p.hitlog = reinterpret_cast<const int32_t*>(reinterpret_cast<const unsigned char*>(ws) + off);
+    const WsLayout w = ws_layout(d);
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(ws);
+    p.ckpt = reinterpret_cast<const float4*>(base);
+    p.hitlog = reinterpret_cast<const int32_t*>(base + w.log_off);
+    p.hitstate = w.state_off ? reinterpret_cast<const float4*>(base + w.state_off) : nullptr;
     p.hl_st = log_ball_major(d) ? 1 : d->B;
     p.hl_sb = log_ball_major(d) ? d->n_steps : 1;
     p.xT_bar = reinterpret_cast<const float2*>(xT_bar);
@@ -1879,19 +1985,12 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     if (use_chunked(d, K)) {
         int C_pad = 2;
         while (C_pad < (int)n_ckpt) C_pad *= 2;
-        // stash of every other state; the region is reused for the 4x4 chunk matrices (16 floats/thread)
-        const size_t smem = (size_t)((K + 1) / 2 < 4 ? 4 : (K + 1) / 2) * kBwdThreads * sizeof(float4);
-        if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(rollout_bwd_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess)
-            return DOPER_ERR_SMEM_LIMIT;
         const int bpb = kBwdThreads / C_pad;
         const unsigned grid = (unsigned)((d->B + bpb - 1) / bpb);
-        rollout_bwd_chunked_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(p, C_pad);
+        rollout_bwd_chunked_kernel<<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p, C_pad);
         return launch_status();
     }
-    const size_t smem = (size_t)K * kBwdThreads * sizeof(float4);
+    const size_t smem = p.hitstate ? 0 : (size_t)K * kBwdThreads * sizeof(float4);
     if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(rollout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=

@@ -77,6 +77,22 @@ __device__ __forceinline__ float seg_dist2(float px, float py, const float4& q) 
     return dx * dx + dy * dy;
 }
 
+// Hit-log word (one per ball-step, written by every forward kernel, read by the backward kernels):
+//   bit 31     the step collided
+//   bit 30/29  |vy| < 1 / |vx| < 1 for the velocity at the START of the step: the only thing the
+//              adjoint of a free-flight step depends on (the friction clip's derivative,
+//              ball_sim.py:43), so the backward needs no state for the steps that did not collide
+//   bits 0-28  closest-segment index (consumed at collisions only)
+constexpr uint32_t kLogHit = 0x80000000u, kLogClipY = 0x40000000u, kLogClipX = 0x20000000u, kLogIdx = 0x1fffffffu;
+
+__device__ __forceinline__ uint32_t clip_bits(float vx, float vy) {
+    return ((vx > -1.0f && vx < 1.0f) ? kLogClipX : 0u) | ((vy > -1.0f && vy < 1.0f) ? kLogClipY : 0u);
+}
+
+__device__ __forceinline__ int32_t pack_log(int idx, bool hit, uint32_t clipb) {
+    return (int32_t)(((uint32_t)idx & kLogIdx) | (hit ? kLogHit : 0u) | clipb);
+}
+
 // ball_sim.py:192-202 : forces + semi-implicit Euler -> candidate state (x1, v1, a)
 __device__ __forceinline__ void free_step(float x, float y, float vx, float vy, const Consts& c,
                                           State& o) {
@@ -185,77 +201,151 @@ struct HitAdj {
     float b1x, b1y, b1vx, b1vy;        // cotangent of the free-flight candidate (x1, v1)
 };
 
-__device__ __noinline__ HitAdj step_vjp_hit(float x, float y, float vx, float vy, float4 seg, const Consts c,
-                                            float gx, float gy, float gvx, float gvy) {
+// Forward internals of a collided step that its adjoint needs (recomputed from the step's start
+// state with the logged segment; identical arithmetic to resolve()).
+struct HitFwd {
+    float s1vx, s1vy, s1ax, s1ay;   // free-flight candidate (v1, a)
+    float t1, t2;                   // clipped projection parameters (candidate point / sub-step point)
+    float nx, ny, od, s, den, toi_raw, toi;
+    float vsx, vsy, o2d, n2x, n2y, k, vax, vay, abx, aby, tau, vbx, vby;
+};
+
+__device__ __forceinline__ HitFwd hit_forward(float x, float y, float vx, float vy, const float4& seg, const Consts& c) {
+    HitFwd f;
     State s1;
     free_step(x, y, vx, vy, c, s1);
+    f.s1vx = s1.vx; f.s1vy = s1.vy; f.s1ax = s1.ax; f.s1ay = s1.ay;
+    float c1x, c1y;
+    proj(s1.x, s1.y, seg, c1x, c1y, f.t1);
+    float ox = c1x - x, oy = c1y - y;
+    f.od = sqrtf(ox * ox + oy * oy);
+    f.nx = ox / f.od; f.ny = oy / f.od;
+    f.s = f.nx * s1.vx + f.ny * s1.vy;
+    float num = fabsf(f.od - c.r);
+    f.den = fabsf(f.s);
+    f.toi_raw = num / f.den;
+    f.toi = clip_nan(f.toi_raw, 0.0f, c.dt);
+    f.vsx = vx + s1.ax * f.toi; f.vsy = vy + s1.ay * f.toi;
+    float xsx = pos_update(f.vsx, f.toi, x), xsy = pos_update(f.vsy, f.toi, y);
+    float c2x, c2y;
+    proj(xsx, xsy, seg, c2x, c2y, f.t2);
+    float o2x = c2x - xsx, o2y = c2y - xsy;
+    f.o2d = sqrtf(o2x * o2x + o2y * o2y);
+    f.n2x = o2x / f.o2d; f.n2y = o2y / f.o2d;
+    f.k = f.n2x * f.vsx + f.n2y * f.vsy;
+    float vnx = f.n2x * f.k, vny = f.n2y * f.k;
+    f.vax = (f.vsx - vnx) - c.e * vnx; f.vay = (f.vsy - vny) - c.e * vny;
+    float pbx = -(2.0f * (xsx - c.ax)), pby = -(2.0f * (xsy - c.ay));
+    f.abx = div_invariant(pbx + fric(f.vax, c), c.m, c.rcp_m, c);
+    f.aby = div_invariant(pby + fric(f.vay, c), c.m, c.rcp_m, c);
+    f.tau = c.dt - f.toi;
+    f.vbx = f.vax + f.abx * f.tau; f.vby = f.vay + f.aby * f.tau;
+    return f;
+}
+
+// reverse pass of the collision part for ONE output cotangent (gx, gy, gvx, gvy)
+__device__ __forceinline__ HitAdj hit_reverse(const HitFwd& f, const float4& seg, const Consts& c,
+                                              float gx, float gy, float gvx, float gvy) {
     float bx = 0.f, by = 0.f, bvx = 0.f, bvy = 0.f, bax = 0.f, bay = 0.f;
     float b1x, b1y, b1vx, b1vy;
-    {
-        float c1x, c1y, t1;
-        proj(s1.x, s1.y, seg, c1x, c1y, t1);
-        float ox = c1x - x, oy = c1y - y;
-        float od = sqrtf(ox * ox + oy * oy);
-        float nx = ox / od, ny = oy / od;
-        float s = nx * s1.vx + ny * s1.vy;
-        float num = fabsf(od - c.r), den = fabsf(s);
-        float toi_raw = num / den;
-        float toi = clip_nan(toi_raw, 0.0f, c.dt);
-        float vsx = vx + s1.ax * toi, vsy = vy + s1.ay * toi;
-        float xsx = pos_update(vsx, toi, x), xsy = pos_update(vsy, toi, y);
-        float c2x, c2y, t2;
-        proj(xsx, xsy, seg, c2x, c2y, t2);
-        float o2x = c2x - xsx, o2y = c2y - xsy;
-        float o2d = sqrtf(o2x * o2x + o2y * o2y);
-        float n2x = o2x / o2d, n2y = o2y / o2d;
-        float k = n2x * vsx + n2y * vsy;
-        float vnx = n2x * k, vny = n2y * k;
-        float vax = (vsx - vnx) - c.e * vnx, vay = (vsy - vny) - c.e * vny;
-        float pbx = -(2.0f * (xsx - c.ax)), pby = -(2.0f * (xsy - c.ay));
-        float abx = div_invariant(pbx + fric(vax, c), c.m, c.rcp_m, c), aby = div_invariant(pby + fric(vay, c), c.m, c.rcp_m, c);
-        float tau = c.dt - toi;
-        float vbx = vax + abx * tau, vby = vay + aby * tau;
-        // reverse
-        float gvbx = gvx + gx * tau, gvby = gvy + gy * tau;
-        float gxsx = gx, gxsy = gy;
-        float gtau = (gx * vbx + gy * vby) + (gvbx * abx + gvby * aby);
-        float gvax = gvbx, gvay = gvby;
-        float gabx = gvbx * tau, gaby = gvby * tau;
-        gxsx += -2.0f * (gabx / c.m); gxsy += -2.0f * (gaby / c.m);
-        gvax += (gabx / c.m) * dfric(vax, c); gvay += (gaby / c.m) * dfric(vay, c);
-        float gtoi = -gtau;
-        float gvsx = gvax, gvsy = gvay;
-        float gvnx = -(1.0f + c.e) * gvax, gvny = -(1.0f + c.e) * gvay;
-        float gk = gvnx * n2x + gvny * n2y;
-        float gn2x = gvnx * k + gk * vsx, gn2y = gvny * k + gk * vsy;
-        gvsx += gk * n2x; gvsy += gk * n2y;
-        float nd = n2x * gn2x + n2y * gn2y;
-        float go2x = (gn2x - n2x * nd) / o2d, go2y = (gn2y - n2y * nd) / o2d;
-        float jx, jy;
-        proj_vjp(seg, t2, go2x, go2y, jx, jy);
-        gxsx += jx - go2x; gxsy += jy - go2y;
-        bx += gxsx; by += gxsy;
-        gvsx += gxsx * toi; gvsy += gxsy * toi;
-        gtoi += gxsx * vsx + gxsy * vsy;
-        bvx += gvsx; bvy += gvsy;
-        bax += gvsx * toi; bay += gvsy * toi;
-        gtoi += gvsx * s1.ax + gvsy * s1.ay;
-        float graw = (toi_raw > 0.0f && toi_raw < c.dt) ? gtoi : 0.0f;
-        float gnum = graw / den;
-        float gden = -(graw * toi_raw) / den;
-        float god = gnum * sgnf(od - c.r);
-        float gs = gden * sgnf(s);
-        float gnx = gs * s1.vx, gny = gs * s1.vy;
-        b1vx = gs * nx; b1vy = gs * ny;
-        float nd1 = nx * gnx + ny * gny;
-        float gox = (gnx - nx * nd1) / od + god * nx, goy = (gny - ny * nd1) / od + god * ny;
-        bx -= gox; by -= goy;
-        proj_vjp(seg, t1, gox, goy, b1x, b1y);
-    }
+    float gvbx = gvx + gx * f.tau, gvby = gvy + gy * f.tau;
+    float gxsx = gx, gxsy = gy;
+    float gtau = (gx * f.vbx + gy * f.vby) + (gvbx * f.abx + gvby * f.aby);
+    float gvax = gvbx, gvay = gvby;
+    float gabx = gvbx * f.tau, gaby = gvby * f.tau;
+    gxsx += -2.0f * (gabx / c.m); gxsy += -2.0f * (gaby / c.m);
+    gvax += (gabx / c.m) * dfric(f.vax, c); gvay += (gaby / c.m) * dfric(f.vay, c);
+    float gtoi = -gtau;
+    float gvsx = gvax, gvsy = gvay;
+    float gvnx = -(1.0f + c.e) * gvax, gvny = -(1.0f + c.e) * gvay;
+    float gk = gvnx * f.n2x + gvny * f.n2y;
+    float gn2x = gvnx * f.k + gk * f.vsx, gn2y = gvny * f.k + gk * f.vsy;
+    gvsx += gk * f.n2x; gvsy += gk * f.n2y;
+    float nd = f.n2x * gn2x + f.n2y * gn2y;
+    float go2x = (gn2x - f.n2x * nd) / f.o2d, go2y = (gn2y - f.n2y * nd) / f.o2d;
+    float jx, jy;
+    proj_vjp(seg, f.t2, go2x, go2y, jx, jy);
+    gxsx += jx - go2x; gxsy += jy - go2y;
+    bx += gxsx; by += gxsy;
+    gvsx += gxsx * f.toi; gvsy += gxsy * f.toi;
+    gtoi += gxsx * f.vsx + gxsy * f.vsy;
+    bvx += gvsx; bvy += gvsy;
+    bax += gvsx * f.toi; bay += gvsy * f.toi;
+    gtoi += gvsx * f.s1ax + gvsy * f.s1ay;
+    float graw = (f.toi_raw > 0.0f && f.toi_raw < c.dt) ? gtoi : 0.0f;
+    float gnum = graw / f.den;
+    float gden = -(graw * f.toi_raw) / f.den;
+    float god = gnum * sgnf(f.od - c.r);
+    float gs = gden * sgnf(f.s);
+    float gnx = gs * f.s1vx, gny = gs * f.s1vy;
+    b1vx = gs * f.nx; b1vy = gs * f.ny;
+    float nd1 = f.nx * gnx + f.ny * gny;
+    float gox = (gnx - f.nx * nd1) / f.od + god * f.nx, goy = (gny - f.ny * nd1) / f.od + god * f.ny;
+    bx -= gox; by -= goy;
+    proj_vjp(seg, f.t1, gox, goy, b1x, b1y);
     HitAdj r;
     r.bx = bx; r.by = by; r.bvx = bvx; r.bvy = bvy; r.bax = bax; r.bay = bay;
     r.b1x = b1x; r.b1y = b1y; r.b1vx = b1vx; r.b1vy = b1vy;
     return r;
+}
+
+__device__ __noinline__ HitAdj step_vjp_hit(float x, float y, float vx, float vy, float4 seg, const Consts c,
+                                            float gx, float gy, float gvx, float gvy) {
+    const HitFwd f = hit_forward(x, y, vx, vy, seg, c);
+    return hit_reverse(f, seg, c, gx, gy, gvx, gvy);
+}
+
+// free-flight part of the step adjoint, common to both branches (x1 = x + v1 dt, v1 = v + a dt, a = ...):
+// consumes the collision part's result (or the plain output cotangent) -> cotangent of the step input
+__device__ __forceinline__ void step_vjp_tail(const HitAdj& r, float vx, float vy, const Consts& c, float& gx,
+                                              float& gy, float& gvx, float& gvy) {
+    float bx = r.bx, by = r.by, bvx = r.bvx, bvy = r.bvy, bax = r.bax, bay = r.bay;
+    float tvx = r.b1vx + r.b1x * c.dt, tvy = r.b1vy + r.b1y * c.dt;
+    bx += r.b1x; by += r.b1y;
+    bvx += tvx; bvy += tvy;
+    bax += tvx * c.dt; bay += tvy * c.dt;
+    float amx = bax / c.m, amy = bay / c.m;
+    bx += -2.0f * (c.ks * amx); by += -2.0f * (c.ks * amy);
+    bvx += amx * dfric(vx, c); bvy += amy * dfric(vy, c);
+    gx = bx; gy = by; gvx = bvx; gvy = bvy;
+}
+
+// N output cotangents through ONE collided step: the forward internals once, N independent reverse
+// passes (instruction-level parallelism for the chunk-parallel backward's four basis vectors)
+template <int N>
+__device__ __noinline__ void step_vjp_hit_n(float x, float y, float vx, float vy, float4 seg, const Consts c,
+                                            float (&g)[N][4]) {
+    const HitFwd f = hit_forward(x, y, vx, vy, seg, c);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const HitAdj r = hit_reverse(f, seg, c, g[k][0], g[k][1], g[k][2], g[k][3]);
+        step_vjp_tail(r, vx, vy, c, g[k][0], g[k][1], g[k][2], g[k][3]);
+    }
+}
+
+// Adjoint of a step that did NOT collide, from its log word alone: the same operations, in the same
+// order, as step_vjp(hit = false) below (bit-identical results), with dfric() read from the logged
+// clip bits instead of the recomputed velocity.  dk = dfric's non-zero value, hoisted by the caller:
+//   dk = -((((c.m) * 9.8f) * c.f) / c.r)
+__device__ __forceinline__ float dfric_value(const Consts& c) { return -((((c.m) * 9.8f) * c.f) / c.r); }
+
+// one coordinate of the free-flight adjoint: (gp, gv) = cotangent of (position, velocity)
+__device__ __forceinline__ void step_vjp_free_1d(bool clip_active, float dk, const Consts& c, float& gp, float& gv) {
+    float bp = 0.f, bv = 0.f, ba = 0.f;
+    const float tv = gv + gp * c.dt;
+    bp += gp;
+    bv += tv;
+    ba += tv * c.dt;
+    const float am = div_invariant(ba, c.m, c.rcp_m, c);  // == ba / c.m (correctly rounded either way)
+    bp += -2.0f * (c.ks * am);
+    bv += am * (clip_active ? dk : 0.0f);
+    gp = bp; gv = bv;
+}
+
+__device__ __forceinline__ void step_vjp_free(uint32_t w, float dk, const Consts& c, float& gx, float& gy,
+                                              float& gvx, float& gvy) {
+    step_vjp_free_1d((w & kLogClipX) != 0u, dk, c, gx, gvx);
+    step_vjp_free_1d((w & kLogClipY) != 0u, dk, c, gy, gvy);
 }
 
 // In/out g = (gx, gy, gvx, gvy): cotangent of the step output -> cotangent of the step input.

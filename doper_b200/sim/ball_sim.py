@@ -41,7 +41,7 @@ class RolloutOptions:
                  sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True,
                  balls_per_warp: int = 0, single_ball_time_parallel: bool = False, warps_per_block: int = 0,
                  broad_phase: bool = None, exact_index_log: bool = False,
-                 broad_phase_time_parallel: bool = False):
+                 broad_phase_time_parallel: bool = False, hit_state_array: bool = True):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
@@ -57,6 +57,9 @@ class RolloutOptions:
         # collisions only, which is all the backward and the reference's outputs depend on)
         self.exact_index_log = bool(exact_index_log)
         self.broad_phase_time_parallel = bool(broad_phase_time_parallel)  # lane = time step variant
+        # keep the state of every collided step for the backward (16 B per ball-step of workspace, touched
+        # at collisions only); False: the backward replays from the K-step checkpoints instead
+        self.hit_state_array = bool(hit_state_array)
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -100,7 +103,8 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
                ((opts.warps_per_block & 0x3F) << 9) |
                ((1 << 16) if opts.broad_phase else 0) | ((1 << 15) if opts.broad_phase is False else 0) |
                ((1 << 17) if opts.exact_index_log else 0) |
-               ((1 << 18) if opts.broad_phase_time_parallel else 0))
+               ((1 << 18) if opts.broad_phase_time_parallel else 0) |
+               (0 if opts.hit_state_array else (1 << 19)))
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d
@@ -326,7 +330,7 @@ def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, at
                     options: RolloutOptions = None, want_trajectory: bool = False) -> dict:
     """Forward rollout that also returns the discrete history the backward replays.
 
-    -> dict(x_T, v_T [B,2]; idx int32 [n,B]; hit bool [n,B]; checkpoints [n_ckpt,B,4];
+    -> dict(x_T, v_T [B,2]; idx int32 [n,B] (bits 0-28 of the log word); hit bool [n,B]; checkpoints [n_ckpt,B,4];
     trajectory BallState or None), all numpy.  Used by the parity tests (segment indices and
     hit flags must match the reference bit-exactly) and by debugging tools.
     """
@@ -359,5 +363,5 @@ def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, at
     if want_trajectory:
         th = traj.cpu().numpy()
         t = BallState(th[0], th[1], th[2])
-    return {"x_T": out[0].cpu().numpy(), "v_T": out[1].cpu().numpy(), "idx": hl & 0x7FFFFFFF, "hit": hl < 0,
+    return {"x_T": out[0].cpu().numpy(), "v_T": out[1].cpu().numpy(), "idx": hl & 0x1FFFFFFF, "hit": hl < 0,
             "hitlog": hl, "checkpoints": ckpt, "trajectory": t}

@@ -143,8 +143,9 @@ def test_broad_phase_kernel_bitexact(sim, cref, lanes, regime, tp):
     assert_bitexact(got["checkpoints"][3, :, :2], ref["traj_x"][32], "ckpt 3 x")
 
 
+@pytest.mark.parametrize("hit_states", [True, False])  # False: the backward replays from the checkpoints
 @pytest.mark.parametrize("n_balls,n_steps,K", [(1, 300, 0), (16, 300, 32), (257, 500, 7), (1024, 130, 64)])
-def test_value_and_grad_sequential_backward_bitexact(sim, cref, n_balls, n_steps, K):
+def test_value_and_grad_sequential_backward_bitexact(sim, cref, n_balls, n_steps, K, hit_states):
     """The sequential backward replays the oracle adjoint's operation order: bit-exact gradients."""
     ball_sim, _ = sim
     w = syn.make_workload("c2", n_balls=n_balls)
@@ -153,7 +154,7 @@ def test_value_and_grad_sequential_backward_bitexact(sim, cref, n_balls, n_steps
                               w["segments"], w["x0"], w["v0"])
     (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(
         n_steps / 1000, n_steps, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], w["constants"],
-        _opts(ball_sim, ckpt_every=K, sequential_backward=True))
+        _opts(ball_sim, ckpt_every=K, sequential_backward=True, hit_state_array=hit_states))
     assert isinstance(gv, np.ndarray) and gv.shape == (n_balls, 2)  # host in -> host out
     assert_bitexact(xT, ref["x_T"], "x_T")
     assert_bitexact(vT, ref["v_T"], "v_T")
@@ -185,9 +186,10 @@ def check_grad_against_truth(gv, cref, w, n_steps, c):
     return e_got.max(), e_seq.max()
 
 
+@pytest.mark.parametrize("hit_states", [True, False])
 @pytest.mark.parametrize("n_balls,n_steps,K", [(1, 300, 0), (16, 300, 0), (257, 500, 0), (1024, 130, 0),
                                                (333, 500, 25), (2048, 1000, 0), (1024, 2000, 0)])
-def test_value_and_grad_default_backward(sim, cref, n_balls, n_steps, K):
+def test_value_and_grad_default_backward(sim, cref, n_balls, n_steps, K, hit_states):
     """Default plan (chunk-parallel backward for small batches): forward bit-exact, gradient as
     accurate as the reference-order fp32 adjoint (same mathematics, different summation order)."""
     ball_sim, _ = sim
@@ -197,7 +199,7 @@ def test_value_and_grad_default_backward(sim, cref, n_balls, n_steps, K):
                               w["segments"], w["x0"], w["v0"])
     (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(
         n_steps / 1000, n_steps, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], w["constants"],
-        _opts(ball_sim, ckpt_every=K))
+        _opts(ball_sim, ckpt_every=K, hit_state_array=hit_states))
     assert_bitexact(xT, ref["x_T"], "x_T")
     assert_bitexact(vT, ref["v_T"], "v_T")
     check_grad_against_truth(gv, cref, w, n_steps, c)
@@ -225,7 +227,8 @@ def test_bouncy_regime_many_collisions(sim, cref, lanes):
     step = -(-n // K) if K else n
     (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"],
                                                           w["attractor"], consts,
-                                                          _opts(ball_sim, lanes_per_ball=lanes, sequential_backward=True))
+                                                          _opts(ball_sim, lanes_per_ball=lanes, sequential_backward=True,
+                                                                hit_state_array=(lanes != 8)))
     refg = cref.value_and_grad(n, np.float32((n / 1000) / n), c, w["attractor"], w["target"], w["segments"],
                                w["x0"], w["v0"])
     assert_bitexact(gv, refg["grad_v0"], "gradient (sequential backward)")
