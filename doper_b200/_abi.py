@@ -17,7 +17,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "doper_abi_version", "doper_error_string", "doper_scene_workspace_bytes", "doper_scene_prepare",
     "doper_closest_segment", "doper_points_inside", "doper_rollout_ckpt_every", "doper_rollout_log_ball_major",
-    "doper_rollout_workspace_bytes",
+    "doper_rollout_workspace_bytes", "doper_rollout_plan_name",
     "doper_rollout_fwd", "doper_rollout_bwd", "doper_l1_loss", "doper_value_and_grad",
     "doper_fp32_probe",
 )
@@ -72,6 +72,8 @@ def _load() -> ctypes.CDLL:
     lib.doper_rollout_ckpt_every.argtypes = [POINTER(RolloutDesc)]
     lib.doper_rollout_log_ball_major.restype = c_int32
     lib.doper_rollout_log_ball_major.argtypes = [POINTER(RolloutDesc)]
+    lib.doper_rollout_plan_name.restype = c_char_p
+    lib.doper_rollout_plan_name.argtypes = [POINTER(RolloutDesc), c_int32]
     lib.doper_rollout_workspace_bytes.restype = c_size_t
     lib.doper_rollout_workspace_bytes.argtypes = [POINTER(RolloutDesc)]
     lib.doper_rollout_fwd.argtypes = [vp, POINTER(RolloutDesc), vp, fp, fp, fp, fp, fp, fp, fp, vp]
@@ -83,7 +85,7 @@ def _load() -> ctypes.CDLL:
     for name in EXPORTS:
         if name not in ("doper_error_string", "doper_scene_workspace_bytes",
                         "doper_rollout_workspace_bytes", "doper_abi_version", "doper_rollout_ckpt_every",
-                        "doper_rollout_log_ball_major"):
+                        "doper_rollout_log_ball_major", "doper_rollout_plan_name"):
             getattr(lib, name).restype = ctypes.c_int
     if lib.doper_abi_version() != ABI_VERSION:
         raise ImportError(f"doper_b200: ABI version mismatch: library {lib.doper_abi_version()}, "

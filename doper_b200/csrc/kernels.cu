@@ -1860,6 +1860,25 @@ int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
     return log_ball_major(d) ? 1 : 0;
 }
 
+const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward) {
+    if (validate_desc(d) != DOPER_OK) return "invalid";
+    if (backward) return use_chunked(d, resolve_K(d)) ? "rollout_bwd_chunked_kernel" : "rollout_bwd_kernel";
+    const int G = auto_lanes(d);
+    static const char* const tpc[] = {"rollout_fwd_tpc_kernel<2>", "rollout_fwd_tpc_kernel<4>", "rollout_fwd_tpc_kernel<8>",
+                                      "rollout_fwd_tpc_kernel<16>", "rollout_fwd_tpc_kernel<32>"};
+    static const char* const cull[] = {"rollout_fwd_cull_kernel<1>", "rollout_fwd_cull_kernel<2>", "rollout_fwd_cull_kernel<4>",
+                                       "rollout_fwd_cull_kernel<8>", "rollout_fwd_cull_kernel<16>", "rollout_fwd_cull_kernel<32>"};
+    static const char* const split[] = {"rollout_fwd_kernel<1>", "rollout_fwd_kernel<2>", "rollout_fwd_kernel<4>",
+                                        "rollout_fwd_kernel<8>", "rollout_fwd_kernel<16>", "rollout_fwd_kernel<32>"};
+    int lg = 0;
+    while ((1 << lg) < G) ++lg;
+    if (use_tpc(d)) return tpc[lg > 0 ? lg - 1 : 0];
+    if (use_cull(d)) return cull[lg];
+    if (use_tp(d)) return use_tp2(d) ? "rollout_fwd_tp2_kernel" : "rollout_fwd_tp_kernel";
+    if (scene_layout(1, d->S).S_pad <= 256 && G >= 8 && !(d->flags & 4)) return "rollout_fwd_reg_kernel";
+    return split[lg];
+}
+
 size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d) {
     if (validate_desc(d) != DOPER_OK) return 0;
     const WsLayout w = ws_layout(d);

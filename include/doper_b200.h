@@ -26,8 +26,12 @@
  *             per-environment scenes are [E][S][2][2].
  *   points / x0 / v0 / xT / vT / cotangents   [B][2]
  *   trajectory (optional)  traj_x, traj_v, traj_a  [n_steps][B][2]
- *   hit log   int32 : closest segment index | (hit << 31), [n_steps][B] or [B][n_steps]
- *             (see doper_rollout_log_ball_major)
+ *   hit log   int32 : bit 31 = the step collided; bits 30 / 29 = |v_y| < 1 / |v_x| < 1 at the start
+ *             of the step (the friction clip's derivative: all the adjoint of a free-flight step
+ *             needs); bits 0-28 = closest segment index (valid at collisions; at every step with
+ *             flags bit 17).  [n_steps][B] or [B][n_steps] (see doper_rollout_log_ball_major)
+ *   hit states [n_steps][B][4] = (x,y,vx,vy) at the START of each collided step; other entries are
+ *             never written nor read
  *   checkpoints [ceil(n_steps/ckpt_every)][B][4] = (x,y,vx,vy) at the START of step k*ckpt_every
  *   consts    host float[5] = {radius, mass, rolling_friction_coefficient,
  *             walls_elasticity, attractor_strength}  (reference constants dict,
@@ -112,6 +116,8 @@ typedef struct {
                                bits 9-14: warps per block of the multi-ball kernel (0 = default);
                                bit 15 / bit 16: forbid / force the broad-phase (candidate list)
                                       forward kernel;
+                               bit 19: no hit-state array in the workspace (saves 16 B per ball-step;
+                                      the backward then replays collided K-blocks from checkpoints);
                                bit 17: hit log holds the exact closest index at EVERY step (the
                                       broad-phase kernel otherwise logs it at collisions only and 0
                                       elsewhere: the index is consumed at collisions only).
@@ -128,7 +134,11 @@ int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d);
  * workspace need this; doper_rollout_bwd derives it from the same descriptor. */
 int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d);
 
-/* Bytes of the backward workspace (checkpoints + hit log) for this rollout. */
+/* Name of the kernel the library will launch for this rollout (backward = 0: forward, 1: backward);
+ * a static string, for benchmark / profile reports. */
+const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward);
+
+/* Bytes of the backward workspace (checkpoints + hit log + hit states) for this rollout. */
 size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d);
 
 /* Forward rollout.  traj_* and ws may be NULL (no trajectory / no backward wanted). */
