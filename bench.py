@@ -153,9 +153,20 @@ def ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=device)
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 when the first
+        # communicator is created, so fd 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from doper_b200 import synthetic as syn
     from doper_b200._abi import check, lib
@@ -172,8 +183,19 @@ def ours(args):
         per_gpu = syn.WORKLOADS[name][0] // max(world, 1) if args.strong else syn.WORKLOADS[name][0]
     total = per_gpu * world
     from doper_b200.distributed import ball_shard
-    lo, hi = ball_shard(total, rank, world)  # contiguous slice of the globally seeded batch
-    w = syn.make_workload(name, n_balls=total, lo=lo, hi=hi)
+    # Shards.  The named single-GPU workloads (c1, c2, c4) are defined by their seeds for ONE GPU; under
+    # weak scaling every rank runs that same seeded batch (identical work per GPU, which is what the
+    # scaling figure is about: launch + all-reduce overheads).  --distinct-shards slices a globally
+    # seeded batch of world x per_gpu balls instead: the synchronous step then waits for the rank that
+    # drew the ball with the longest collision chain (DESIGN.md "stragglers"), a property of the inputs.
+    # c3 / c5 are DEFINED as global batches and are always sliced.
+    replicated = world > 1 and name in ("c1", "c2", "c4") and not args.distinct_shards
+    if replicated:
+        lo, hi = 0, per_gpu
+        w = syn.make_workload(name, n_balls=per_gpu)
+    else:
+        lo, hi = ball_shard(total, rank, world)  # contiguous slice of the globally seeded batch
+        w = syn.make_workload(name, n_balls=total, lo=lo, hi=hi)
     B, n_steps = per_gpu, (args.sim_steps or w["n_steps"])
     w["n_steps"], w["sim_time"] = n_steps, n_steps / 1000.0
     S = int(w["segments"].shape[-3])
@@ -344,8 +366,11 @@ def ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_label(name, B, S, n_steps, bool(w["per_env"])) +
-                       (f" per GPU ({world} GPUs, a globally seeded batch of {total} balls sliced by rank, "
-                        f"allreduce of 6,603 fp32 per step)" if world > 1 else ""),
+                       ((f" per GPU ({world} GPUs, every rank runs the workload's own seeded batch, "
+                         if replicated else
+                         f" per GPU ({world} GPUs, a globally seeded batch of {total} balls sliced by rank, ") +
+                        "allreduce of 6,603 fp32 per step)" if world > 1 else ""),
+                       "shards": ("n/a" if world == 1 else ("replicated seeded batch" if replicated else "sliced global batch")),
                        "ms_per_step_fastest_rank": round(ms_per_step_fastest_rank, 5),
                        "l2": "256 MiB buffer rewritten between timed iterations (flush), outside the event pairs",
                        "lanes_per_ball": int(desc.lanes_per_ball) or "auto", "ckpt_every": int(lib.doper_rollout_ckpt_every(dref)),
@@ -411,6 +436,8 @@ def main():
     ap.add_argument("--full-sweep", action="store_true",
                     help="forbid the broad-phase kernels: every (ball, segment) pair is evaluated every step")
     ap.add_argument("--strong", action="store_true")
+    ap.add_argument("--distinct-shards", action="store_true",
+                    help="N > 1: slice one globally seeded batch instead of running the workload's batch on every rank")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

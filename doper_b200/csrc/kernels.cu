@@ -464,31 +464,48 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
         bool sat_out = false;
         if (t < n && T == 1 && trouble == 0 && gl.rho2 >= 0.0f && !sc.weird) {
             int miss = 0;
+            int cj = -1;  // segment of the last collision: almost always the next one too (sliding contact)
             for (int it = 0; it < kContactSteps && t < n; ++it) {
                 State s1;
-                free_step(x, y, vx, vy, c, s1);
+                if (!free_step_fast(x, y, vx, vy, c, s1)) free_step(x, y, vx, vy, c, s1);
                 const float px = s1.x, py = s1.y;
                 const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)));
                 const float ddx = px - gl.cx, ddy = py - gl.cy;
                 if (!(M <= 1.0e15f)) break;                                              // normal path: exact sweep
                 if (!(ddx * ddx + ddy * ddy <= gl.rho2)) { trouble = 1; break; }          // normal path: refresh
-                const float amin = glist_min(sc, px, py, gl);
                 int idx = 0;
-                bool hit = false;
-                if (exact_idx || !(amin > gl.far2)) {
-                    unsigned long long key = glist_exact(sc, px, py, __fmaf_rn(amin, kFilterOneEps, kFilterKappaPerM2 * M * M),
-                                                         gl.e, gl.cap, gl.cnt);
-                    if (key == kNoKey) key = lane_exact<1>(sc, px, py, 0);
-                    float dist;
-                    unpack_key(key, idx, dist);
-                    hit = dist <= c.r;
+                bool hit = false, decided = false;
+                if (cj >= 0 && gl.cnt <= gl.cap) {
+                    // fast decision: the exact distance to segment cj, and a proof that no other list entry
+                    // can tie or beat it (estimate^2 > (d + 128 u M)^2 => reference distance > d)
+                    const float dj = cand_dist(px, py, sc.q[cj]);
+                    const float lim0 = __fmaf_rn(kCullSafePerM, M, dj) * kCullUp;
+                    const float lim = (lim0 * lim0) * kCullUp;
+                    bool sole = dj == dj;
+                    for (int k = 0; k < gl.cnt; ++k) {
+                        const int i = gl.e[k];
+                        const float a = approx_d2(px, py, sc.q[i], sc.rl[i]);
+                        sole = sole && (i == cj || a > lim);
+                    }
+                    if (sole) { idx = cj; hit = dj <= c.r; decided = true; }
                 }
-                if (active && lane == 0) {
-                    if (p.ckpt && (t % K) == 0) p.ckpt[(size_t)(t / K) * p.B + ball] = make_float4(x, y, vx, vy);
+                if (!decided) {
+                    const float amin = glist_min(sc, px, py, gl);
+                    if (exact_idx || !(amin > gl.far2)) {
+                        unsigned long long key = glist_exact(sc, px, py, __fmaf_rn(amin, kFilterOneEps, kFilterKappaPerM2 * M * M),
+                                                             gl.e, gl.cap, gl.cnt);
+                        if (key == kNoKey) key = lane_exact<1>(sc, px, py, 0);
+                        float dist;
+                        unpack_key(key, idx, dist);
+                        hit = dist <= c.r;
+                    }
                 }
                 const uint32_t clipb = clip_bits(vx, vy);
-                if (hit && active && lane == 0 && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
-                if (hit) s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c);
+                if (active && lane == 0) {
+                    if (p.ckpt && (t % K) == 0) p.ckpt[(size_t)(t / K) * p.B + ball] = make_float4(x, y, vx, vy);
+                    if (hit && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
+                }
+                if (hit) { s1 = resolve_inline(x, y, vx, vy, s1, sc.q[idx], c); cj = idx; }
                 x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
                 if (active && lane == 0) {
                     if (hl) hl[(int64_t)t * p.hl_st] = pack_log((hit || exact_idx) ? idx : 0, hit, clipb);

@@ -136,8 +136,17 @@ __device__ __forceinline__ bool free_step_fast(float x, float y, float vx, float
 
 // ball_sim.py:97-132 : time-of-impact sub-step, reflection, remaining sub-step
 // (out of line: rare, and keeps the hot step loop small; everything by value = in registers)
+__device__ __forceinline__ State resolve_inline(float x, float y, float vx, float vy, const State& s1, const float4& seg,
+                                                const Consts& c);
+
 __device__ __noinline__ State resolve(float x, float y, float vx, float vy, State s1, float4 seg,
                                       const Consts c) {
+    return resolve_inline(x, y, vx, vy, s1, seg, c);
+}
+
+// the same, inlined at the call site (contact loop of the time-parallel kernel: one collision per step)
+__device__ __forceinline__ State resolve_inline(float x, float y, float vx, float vy, const State& s1, const float4& seg,
+                                                const Consts& c) {
     State o;
     float c1x, c1y, t1;
     proj(s1.x, s1.y, seg, c1x, c1y, t1);
