@@ -20,6 +20,7 @@ EXPORTS = (
     "doper_rollout_workspace_bytes", "doper_rollout_plan_name",
     "doper_rollout_fwd", "doper_rollout_bwd", "doper_l1_loss", "doper_value_and_grad",
     "doper_fp32_probe",
+    "doper_ray_segment_points", "doper_range_sensor", "doper_agent_observations",
 )
 
 
@@ -82,6 +83,10 @@ def _load() -> ctypes.CDLL:
     lib.doper_value_and_grad.argtypes = [vp, POINTER(RolloutDesc), vp, fp, fp, POINTER(c_float), vp, fp,
                                          fp, fp, fp, fp, fp, fp]
     lib.doper_fp32_probe.argtypes = [vp, c_int32, c_int32, c_int32, c_int32, fp]
+    lib.doper_ray_segment_points.argtypes = [vp, c_int64, c_int32, fp, fp, fp, fp]
+    lib.doper_range_sensor.argtypes = [vp, c_int64, c_int32, c_int32, fp, fp, vp, c_float, fp, fp, vp]
+    lib.doper_agent_observations.argtypes = [vp, c_int64, c_int32, c_int32, fp, fp, fp, vp, c_float,
+                                             POINTER(ctypes.c_double), fp]
     for name in EXPORTS:
         if name not in ("doper_error_string", "doper_scene_workspace_bytes",
                         "doper_rollout_workspace_bytes", "doper_abi_version", "doper_rollout_ckpt_every",

@@ -1500,6 +1500,8 @@ __global__ void fp32_probe_kernel(int iters, int use_fma, float* out) {
 
 }  // namespace doper
 
+#include "sensor.cuh"
+
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
@@ -1796,6 +1798,26 @@ int launch_closest(cudaStream_t st, int64_t N, int S, const float* pts, const fl
 
 }  // namespace
 
+namespace {
+template <bool OBS>
+int launch_range_sensor(cudaStream_t st, int64_t N, int R, int S, const float* pos, const float* vel,
+                        const float* ray_dirs, const void* scene_ws, float distance_range, double tx, double ty,
+                        float* ranges, float* points, int32_t* idx, float* obs) {
+    const size_t smem = (size_t)scene_layout(1, S).S_pad * 20 + 16;
+    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(range_sensor_kernel<OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+        return DOPER_ERR_SMEM_LIMIT;
+    const int64_t n = N * (int64_t)R;
+    range_sensor_kernel<OBS><<<(unsigned)((n + kSensorThreads - 1) / kSensorThreads), kSensorThreads, smem, st>>>(
+        N, R, S, reinterpret_cast<const float2*>(pos), reinterpret_cast<const float2*>(vel),
+        reinterpret_cast<const float2*>(ray_dirs), reinterpret_cast<const unsigned char*>(scene_ws), distance_range,
+        tx, ty, ranges, reinterpret_cast<float2*>(points), idx, obs);
+    return launch_status();
+}
+}  // namespace
+
 extern "C" {
 
 int doper_abi_version(void) { return DOPER_ABI_VERSION; }
@@ -1865,6 +1887,47 @@ int doper_points_inside(doper_stream_t stream, int64_t N, int32_t S, const float
     points_inside_kernel<<<grid, kQueryThreads, 0, (cudaStream_t)stream>>>(
         N, S, reinterpret_cast<const float2*>(points), reinterpret_cast<const float4*>(segments), flag);
     return launch_status();
+}
+
+int doper_ray_segment_points(doper_stream_t stream, int64_t R, int32_t S, const float* origins,
+                             const float* directions, const float* segments, float* points) {
+    if (R < 0 || S <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (R == 0) return DOPER_OK;
+    if (!origins || !directions || !segments || !points) return DOPER_ERR_NULL_PTR;
+    if (!aligned(origins, 8) || !aligned(directions, 8) || !aligned(segments, 16) || !aligned(points, 8))
+        return DOPER_ERR_MISALIGNED;
+    const int64_t n = R * (int64_t)S;
+    if (n > (int64_t)0x7fffffff * 256) return DOPER_ERR_UNSUPPORTED;
+    ray_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        R, S, reinterpret_cast<const float2*>(origins), reinterpret_cast<const float2*>(directions),
+        reinterpret_cast<const float4*>(segments), reinterpret_cast<float2*>(points));
+    return launch_status();
+}
+
+int doper_range_sensor(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
+                       const float* ray_directions, const void* scene_ws, float distance_range, float* ranges,
+                       float* points, int32_t* idx) {
+    if (N < 0 || R <= 0 || S <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (N == 0) return DOPER_OK;
+    if (!positions || !ray_directions || !scene_ws || !ranges) return DOPER_ERR_NULL_PTR;
+    if (!aligned(positions, 8) || !aligned(ray_directions, 8) || !aligned(scene_ws, 256) ||
+        (points && !aligned(points, 8)))
+        return DOPER_ERR_MISALIGNED;
+    return launch_range_sensor<false>((cudaStream_t)stream, N, R, S, positions, nullptr, ray_directions, scene_ws,
+                                      distance_range, 0.0, 0.0, ranges, points, idx, nullptr);
+}
+
+int doper_agent_observations(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
+                             const float* velocities, const float* ray_directions, const void* scene_ws,
+                             float distance_range, const double target[2], float* observations) {
+    if (N < 0 || R <= 0 || S <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (N == 0) return DOPER_OK;
+    if (!positions || !velocities || !ray_directions || !scene_ws || !target || !observations)
+        return DOPER_ERR_NULL_PTR;
+    if (!aligned(positions, 8) || !aligned(velocities, 8) || !aligned(ray_directions, 8) || !aligned(scene_ws, 256))
+        return DOPER_ERR_MISALIGNED;
+    return launch_range_sensor<true>((cudaStream_t)stream, N, R, S, positions, velocities, ray_directions, scene_ws,
+                                     distance_range, target[0], target[1], nullptr, nullptr, nullptr, observations);
 }
 
 int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d) {

@@ -23,6 +23,7 @@ __all__ = [
     "Polygon", "JaxScene", "create_polygon", "create_scene", "create_env_scenes",
     "find_closest_segment_to_point", "find_closest_segment_to_points_batch",
     "if_points_inside_any_polygon",
+    "line_ray_intersection_point", "batch_line_ray_intersection_point", "range_sensor",
 ]
 
 Polygon = namedtuple("Polygon", ["segments"])  # jax_geometry.py:8
@@ -165,3 +166,60 @@ def if_points_inside_any_polygon(points, scene: JaxScene):
     check(lib.doper_points_inside(stream_ptr(), N, S, ptr(pts), ptr(raw), ptr(flag)), "doper_points_inside")
     out = flag.to(torch.bool)
     return out if on_device else out.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------
+# ray casting (reference jax_geometry.py:180-261)
+# ------------------------------------------------------------------------------------------
+def batch_line_ray_intersection_point(ray_origins, ray_directions, segments):
+    """jax_geometry.py:237-261: ``[R,2] x [R,2] x [S,2,2] -> [R,S,2]`` intersection points,
+    ``inf`` where ray and segment do not meet (directions need not be normalised)."""
+    device = require_cuda()
+    on_device = is_device_tensor(ray_origins) and is_device_tensor(ray_directions)
+    scene = _as_scene(segments)
+    if scene.per_env:
+        raise ValueError("batch_line_ray_intersection_point: per-environment scenes are not supported here")
+    raw, _ = scene.prepared(device)
+    o = as_f32_device(ray_origins, device).reshape(-1, 2)
+    d = as_f32_device(ray_directions, device).reshape(-1, 2)
+    if o.shape[0] != d.shape[0]:
+        raise ValueError("ray_origins and ray_directions must have the same length")
+    R, S = int(o.shape[0]), scene.n_segments
+    out = torch.empty((R, S, 2), dtype=torch.float32, device=device)
+    check(lib.doper_ray_segment_points(stream_ptr(), R, S, ptr(o), ptr(d), ptr(raw), ptr(out)),
+          "doper_ray_segment_points")
+    return out if on_device else out.cpu().numpy()
+
+
+def line_ray_intersection_point(ray_origin, ray_direction, segment):
+    """jax_geometry.py:180-218: one ray against one ``[2,2]`` segment -> ``[2]`` point (or inf, inf)."""
+    seg = segment.reshape(1, 2, 2) if hasattr(segment, "reshape") else np.asarray(segment, np.float32).reshape(1, 2, 2)
+    o = ray_origin.reshape(1, 2) if hasattr(ray_origin, "reshape") else np.asarray(ray_origin, np.float32).reshape(1, 2)
+    d = ray_direction.reshape(1, 2) if hasattr(ray_direction, "reshape") else \
+        np.asarray(ray_direction, np.float32).reshape(1, 2)
+    return batch_line_ray_intersection_point(o, d, seg)[0, 0]
+
+
+def range_sensor(positions, ray_directions, scene, distance_range: float, want_points: bool = False):
+    """All sensors at once (extension of observations.py:29-79, which handles one position per
+    call): ``positions [N,2]``, ``ray_directions [R,2]`` shared by every position ->
+    ``ranges [N,R]`` (and ``points [N,R,2]``, ``closest index [N,R]`` when asked)."""
+    device = require_cuda()
+    on_device = is_device_tensor(positions)
+    scene = _as_scene(scene)
+    if scene.per_env:
+        raise ValueError("range_sensor: per-environment scenes are not supported here")
+    _, ws = scene.prepared(device)
+    pos = as_f32_device(positions, device).reshape(-1, 2)
+    dirs = as_f32_device(ray_directions, device).reshape(-1, 2)
+    N, R, S = int(pos.shape[0]), int(dirs.shape[0]), scene.n_segments
+    ranges = torch.empty((N, R), dtype=torch.float32, device=device)
+    points = torch.empty((N, R, 2), dtype=torch.float32, device=device) if want_points else None
+    idx = torch.empty((N, R), dtype=torch.int32, device=device) if want_points else None
+    check(lib.doper_range_sensor(stream_ptr(), N, R, S, ptr(pos), ptr(dirs), ptr(ws), float(distance_range),
+                                 ptr(ranges), ptr(points), ptr(idx)), "doper_range_sensor")
+    if not want_points:
+        return ranges if on_device else ranges.cpu().numpy()
+    if on_device:
+        return ranges, points, idx
+    return ranges.cpu().numpy(), points.cpu().numpy(), idx.cpu().numpy()

@@ -20,6 +20,11 @@
  *   doper_rollout_bwd          the VJP of the scan that jax.value_and_grad builds
  *                                                               doper/sim/ball_sim.py:334-338
  *   doper_value_and_grad       vmapped_grad_and_value           doper/sim/ball_sim.py:334-338
+ *   doper_ray_segment_points   batch_line_ray_intersection_point doper/sim/jax_geometry.py:237-261
+ *   doper_range_sensor         (Undirected/Simple)RangeSensor.get_observation
+ *                                                               doper/agents/observations.py:29-110
+ *   doper_agent_observations   RangeSensingAgent.get_observations
+ *                                                               doper/agents/range_sensor_agent.py:17-41
  *
  * Data layout (all float = IEEE binary32, row-major, device memory):
  *   segments  [S][2][2] = (x0,y0,x1,y1) per segment, polygon-major, 3 per triangle;
@@ -92,6 +97,31 @@ int doper_closest_segment(doper_stream_t stream, int64_t N, int32_t S, const flo
 /* flag[i] = 1 iff points[i] is strictly inside any of the S/3 counter-clockwise triangles. */
 int doper_points_inside(doper_stream_t stream, int64_t N, int32_t S, const float* points,
                         const float* segments, uint8_t* flag);
+
+/* ---- range sensor (observation path) ------------------------------- */
+
+/* batch_line_ray_intersection_point (doper/sim/jax_geometry.py:237-261):
+ * points[r][s] = intersection of ray r (origin, direction; the direction need not be normalised)
+ * with segment s, or (inf, inf) when they do not meet.  origins / directions [R][2], points [R][S][2]. */
+int doper_ray_segment_points(doper_stream_t stream, int64_t R, int32_t S, const float* origins,
+                             const float* directions, const float* segments, float* points);
+
+/* SimpleRangeSensor / UndirectedRangeSensor.get_observation (doper/agents/observations.py:29-110) for N
+ * sensor positions at once, all with the same R ray directions: ranges[i][r] = distance from
+ * positions[i] to the closest intersection along ray r, clamped to distance_range; points (nullable)
+ * [N][R][2] that intersection (inf beyond distance_range); idx (nullable) [N][R] its segment
+ * (first index on ties, 0 when nothing is hit). */
+int doper_range_sensor(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
+                       const float* ray_directions, const void* scene_ws, float distance_range, float* ranges,
+                       float* points, int32_t* idx);
+
+/* RangeSensingAgent.get_observations (doper/agents/range_sensor_agent.py:17-41), fused:
+ * observations[i] = [ |x_i - target|, (x_i - target) / |x_i - target| (2), x_i (2), v_i (2),
+ * ranges[i][0..R) / distance_range ], float32 [N][7 + R]; the first three entries are evaluated in
+ * float64 like the reference's numpy code (its target is a float64 array) and cast once. */
+int doper_agent_observations(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
+                             const float* velocities, const float* ray_directions, const void* scene_ws,
+                             float distance_range, const double target[2], float* observations);
 
 /* ---- rollout -------------------------------------------------------------------------- */
 
