@@ -895,265 +895,6 @@ __global__ void __launch_bounds__(1024) rollout_fwd_tp_kernel(const FwdParams p)
     }
 }
 
-// Multi-ball time-parallel forward: ONE WARP OWNS P BALLS.  Same speculation as above, but
-//   phase 1 (free flight, 32 steps) runs with lane = ball (lane % P; the 32/P replicas compute the
-//     same values), so its ~65 instructions per step are paid once per P balls instead of once per
-//     ball; the per-step states go through a small per-warp shared-memory buffer,
-//   phase 2 (lane = time step) sweeps the scene for all P balls at once (sweep_points<P>: each
-//     segment is loaded once for P points, P independent dependency chains per lane),
-//   commit / collision resolve per ball as in the single-ball kernel; a ball that keeps colliding
-//     runs lane-split sequential steps for a while.
-// Per-environment scenes (PER_ENV): the warp's P scenes sit in shared memory and are swept one
-// after the other (nothing to share between them).  Results are bit-identical to every other
-// forward kernel: same arithmetic per step, only scheduled differently.
-template <int P>
-struct Tp2Warp {       // per-warp shared-memory block of the multi-ball time-parallel kernel
-    float4 st[P][33];  // [q][0] = state at the start of the chunk, [q][k+1] = (x1, v1) after free step k
-    float2 ac[P][32];  // acceleration of free step k
-    int t[P];          // next step of ball q (n_steps = finished / no such ball)
-    int prev[P];       // last committed closest segment (hint for the filter threshold)
-    int seq_left[P];   // > 0: ball q runs lane-split sequential steps
-    int T[P];          // speculative steps of ball q in this round
-    float scale[P];    // scene header of ball q's scene
-    int weird[P];
-};
-
-constexpr int kTp2Threads = 128;
-
-template <int P, bool PER_ENV>
-__global__ void __launch_bounds__(kTp2Threads) rollout_fwd_tp2_kernel(const FwdParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wpb = blockDim.x >> 5;
-    const SceneLayout L = scene_layout(PER_ENV ? p.B : 1, p.S);
-    const int n_local = PER_ENV ? wpb * P : 1;
-    float4* sq = reinterpret_cast<float4*>(smem);
-    float* srl = reinterpret_cast<float*>(smem + (size_t)n_local * L.S_pad * sizeof(float4));
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_local * L.S_pad * 20);
-    Tp2Warp<P>& wb = reinterpret_cast<Tp2Warp<P>*>(smem + (size_t)n_local * L.S_pad * 20 + 16)[warp];
-    const int64_t first_ball = (int64_t)blockIdx.x * wpb * P;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (tid == 0) {
-        const int ns = PER_ENV ? (int)min((int64_t)(wpb * P), p.B - first_ball) : 1;
-        stage_scenes(sq, srl, p.scene_ws, L, PER_ENV ? first_ball : 0, ns, bar);
-    }
-    const int n = p.n_steps, K = p.K;
-    const Consts c = p.c;
-    const int64_t ball0 = first_ball + (int64_t)warp * P;
-    if (lane < P) {
-        const int64_t ball = ball0 + lane;
-        const bool active = ball < p.B;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) { const float2 xx = p.x0[ball], vv = p.v0[ball]; s = make_float4(xx.x, xx.y, vv.x, vv.y); }
-        const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off)[PER_ENV ? (active ? ball : p.B - 1) : 0];
-        wb.st[lane][0] = s;
-        wb.t[lane] = active ? 0 : n;
-        wb.prev[lane] = 0;
-        wb.seq_left[lane] = 0;
-        wb.scale[lane] = hdr.scale;
-        wb.weird[lane] = hdr.weird | p.force_exact;
-    }
-    mbar_wait(bar, 0);
-    __syncwarp();
-    if (ball0 >= p.B) return;  // whole warp leaves; no block-wide sync below
-    // scene of ball q (an absent ball reads the warp's first scene: staged, finite)
-    auto scene_of = [&](int q) {
-        SceneView v;
-        const int ls = PER_ENV ? ((ball0 + q < p.B) ? warp * P + q : warp * P) : 0;
-        v.q = sq + (size_t)ls * L.S_pad; v.rl = srl + (size_t)ls * L.S_pad;
-        v.S = p.S; v.S_pad = L.S_pad; v.scale = wb.scale[q]; v.weird = wb.weird[q];
-        return v;
-    };
-#pragma unroll 1
-    for (int q = 0; q < P; ++q) {  // hint for the first chunk (only seeds the threshold)
-        const SceneView s = scene_of(q);
-        const float4 s0 = wb.st[q][0];
-        if (wb.t[q] < n && !s.weird) {
-            const int h = hint_by_estimate<32>(s, s0.x, s0.y, lane);
-            if (lane == 0) wb.prev[q] = h;
-        }
-    }
-    __syncwarp();
-
-    while (true) {
-        // ---- balls in sequential mode: lanes split the segments of ONE step, up to 32 steps ----
-        int Tmax = 0, alive = 0;
-#pragma unroll 1
-        for (int q = 0; q < P; ++q) {
-            int tq = wb.t[q], sl = wb.seq_left[q];
-            if (sl > 0 && tq < n) {
-                const SceneView s = scene_of(q);
-                const int64_t ball = ball0 + q;
-                const float4 s0 = wb.st[q][0];
-                float x = s0.x, y = s0.y, vx = s0.z, vy = s0.w;
-                int pv = wb.prev[q];
-                for (int it = 0; it < 32 && sl > 0 && tq < n; ++it) {
-                    if (p.ckpt && (tq % K) == 0 && lane == 0) p.ckpt[(size_t)(tq / K) * p.B + ball] = make_float4(x, y, vx, vy);
-                    State s1;
-                    free_step(x, y, vx, vy, c, s1);
-                    const uint32_t clipb = clip_bits(vx, vy);
-                    int idx; float dist;
-                    sweep_any<32>(s, s1.x, s1.y, lane, pv, idx, dist);
-                    pv = idx;
-                    const bool hit = dist <= c.r;
-                    if (hit && lane == 0 && p.hitstate) p.hitstate[(size_t)tq * p.B + ball] = make_float4(x, y, vx, vy);
-                    if (hit) { s1 = resolve(x, y, vx, vy, s1, s.q[idx], c); sl = kTpSeqSteps; }
-                    x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
-                    if (lane == 0) {
-                        const size_t o = (size_t)tq * p.B + ball;
-                        if (p.hitlog) p.hitlog[ball * p.hl_sb + (int64_t)tq * p.hl_st] = pack_log(idx, hit, clipb);
-                        if (p.traj_x) p.traj_x[o] = make_float2(x, y);
-                        if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
-                        if (p.traj_a) p.traj_a[o] = make_float2(s1.ax, s1.ay);
-                    }
-                    ++tq; --sl;
-                }
-                __syncwarp();
-                if (lane == 0) { wb.st[q][0] = make_float4(x, y, vx, vy); wb.t[q] = tq; wb.seq_left[q] = sl; wb.prev[q] = pv; }
-            }
-            const int Tq = (sl == 0 && tq < n) ? min(32, n - tq) : 0;
-            if (lane == 0) wb.T[q] = Tq;
-            Tmax = max(Tmax, Tq);
-            alive |= tq < n;
-        }
-        if (!alive) break;
-        __syncwarp();
-        if (Tmax == 0) continue;
-        {   // phase 1: lane % P = ball; free flight, states handed over through shared memory
-            const int pb = lane & (P - 1);
-            const int Tm = wb.T[pb];
-            const float4 s0 = wb.st[pb][0];
-            float cx = s0.x, cy = s0.y, cvx = s0.z, cvy = s0.w;
-            for (int k = 0; k < Tmax; ++k) {
-                if (k < Tm) {
-                    State o;
-                    free_step(cx, cy, cvx, cvy, c, o);
-                    cx = o.x; cy = o.y; cvx = o.vx; cvy = o.vy;
-                    if (lane < P) {
-                        wb.st[pb][k + 1] = make_float4(o.x, o.y, o.vx, o.vy);
-                        wb.ac[pb][k] = make_float2(o.ax, o.ay);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // phase 2: lane = step; P points per lane
-        float px[P], py[P], kap[P];
-        int prev[P];
-        unsigned long long key[P];
-        bool fast = true;
-#pragma unroll
-        for (int q = 0; q < P; ++q) {
-            const float4 s1 = wb.st[q][lane < wb.T[q] ? lane + 1 : 0];  // idle lanes sweep the (finite) start point
-            px[q] = s1.x; py[q] = s1.y;
-            prev[q] = wb.prev[q];
-            const float M = fmaxf(wb.scale[q], fmaxf(fabsf(px[q]), fabsf(py[q])));
-            kap[q] = kFilterKappaPerM2 * M * M;
-            fast = fast && !wb.weird[q] && M <= 1.0e15f;
-        }
-        if (__all_sync(0xffffffffu, fast)) {
-            if (PER_ENV) {
-#pragma unroll
-                for (int q = 0; q < P; ++q) key[q] = kNoKey;
-#pragma unroll 1
-                for (int q = 0; q < P; ++q) {
-                    if (wb.T[q] > 0) {
-                        float ax[1], ay[1], ak[1];
-                        int ap[1];
-                        unsigned long long k1[1];
-#pragma unroll
-                        for (int r = 0; r < P; ++r)
-                            if (r == q) { ax[0] = px[r]; ay[0] = py[r]; ak[0] = kap[r]; ap[0] = prev[r]; }
-                        sweep_points<1>(scene_of(q), ax, ay, ap, ak, k1);
-#pragma unroll
-                        for (int r = 0; r < P; ++r)
-                            if (r == q) key[r] = k1[0];
-                    }
-                }
-            } else {
-                sweep_points<P>(scene_of(0), px, py, prev, kap, key);
-            }
-        } else {  // degenerate scene or non-finite point somewhere: reference arithmetic for every pair
-#pragma unroll 1
-            for (int q = 0; q < P; ++q) {
-                const SceneView s = scene_of(q);
-                float x1 = 0.f, y1 = 0.f, k1 = 0.f;
-                int p1 = 0;
-#pragma unroll
-                for (int r = 0; r < P; ++r)
-                    if (r == q) { x1 = px[r]; y1 = py[r]; k1 = kap[r]; p1 = prev[r]; }
-                const float M = fmaxf(s.scale, fmaxf(fabsf(x1), fabsf(y1)));
-                unsigned long long kq;
-                if (!s.weird && M <= 1.0e15f) kq = lane_filtered<1>(s, x1, y1, 0, p1, k1);
-                else kq = lane_exact<1>(s, x1, y1, 0);
-#pragma unroll
-                for (int r = 0; r < P; ++r)
-                    if (r == q) key[r] = kq;
-            }
-        }
-        // commit per ball
-#pragma unroll 1
-        for (int q = 0; q < P; ++q) {
-            const int Tq = wb.T[q];
-            if (Tq == 0) continue;
-            const int64_t ball = ball0 + q;
-            unsigned long long kq = kNoKey;
-#pragma unroll
-            for (int r = 0; r < P; ++r)
-                if (r == q) kq = key[r];
-            int idx; float dist;
-            unpack_key(kq, idx, dist);
-            const bool hit = (lane < Tq) && (dist <= c.r);  // NaN -> false (ball_sim.py:164)
-            const unsigned hits = __ballot_sync(0xffffffffu, hit);
-            const int first = hits ? (__ffs(hits) - 1) : Tq;  // first step of the chunk that collided
-            const int n_commit = min(first + 1, Tq);          // steps t .. t+n_commit-1 are final
-            const int kk = min(lane, Tq - 1);
-            const float4 pre = wb.st[q][kk];       // state at the start of my step
-            const float4 post = wb.st[q][kk + 1];  // free-flight state after my step
-            const float2 acc = wb.ac[q][kk];
-            State out;
-            out.x = post.x; out.y = post.y; out.vx = post.z; out.vy = post.w; out.ax = acc.x; out.ay = acc.y;
-            float4 next;
-            int seq = 0;
-            if (first < Tq) {  // resolve the collision of step t+first (all lanes, redundantly)
-                const float4 b0 = wb.st[q][first], b1f = wb.st[q][first + 1];
-                const float2 ba = wb.ac[q][first];
-                State b1;
-                b1.x = b1f.x; b1.y = b1f.y; b1.vx = b1f.z; b1.vy = b1f.w; b1.ax = ba.x; b1.ay = ba.y;
-                const int hidx = __shfl_sync(0xffffffffu, idx, first);
-                const float4* sqq = sq + (PER_ENV ? (size_t)(warp * P + q) * L.S_pad : 0);
-                const State r = resolve(b0.x, b0.y, b0.z, b0.w, b1, sqq[hidx], c);
-                if (lane == first) out = r;
-                next = make_float4(r.x, r.y, r.vx, r.vy);
-                if (first < kTpEarlyHit) seq = kTpSeqSteps;
-            } else {
-                next = wb.st[q][Tq];
-            }
-            const int np = __shfl_sync(0xffffffffu, idx, n_commit - 1);
-            const int t0 = wb.t[q];
-            if (lane < n_commit) {
-                const int ts = t0 + lane;
-                if (p.hitlog) p.hitlog[ball * p.hl_sb + (int64_t)ts * p.hl_st] = pack_log(idx, lane == first, clip_bits(pre.z, pre.w));
-                if (lane == first && p.hitstate) p.hitstate[(size_t)ts * p.B + ball] = pre;
-                if (p.ckpt && (ts % K) == 0) p.ckpt[(size_t)(ts / K) * p.B + ball] = pre;
-                const size_t o = (size_t)ts * p.B + ball;
-                if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
-                if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
-                if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
-            }
-            __syncwarp();
-            if (lane == 0) { wb.st[q][0] = next; wb.t[q] = t0 + n_commit; wb.prev[q] = np; wb.seq_left[q] = seq; }
-        }
-        __syncwarp();
-    }
-    if (lane < P && ball0 + lane < p.B) {
-        const float4 s = wb.st[lane][0];
-        p.xT[ball0 + lane] = make_float2(s.x, s.y);
-        p.vT[ball0 + lane] = make_float2(s.z, s.w);
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // backward rollout
 // ------------------------------------------------------------------------------------------
@@ -1587,12 +1328,12 @@ constexpr int64_t kTpMaxBalls = 65536;
 // batch size up to 65,536 run fastest time-parallel; beyond that one thread per ball wins.
 // Broad-phase (candidate list) kernels are the default plan.  They are not used when the caller
 // forbids them (flags bit 15), forces the exact sweep (bit 0) or pins one of the full-sweep kernels
-// (lanes_per_ball != 0 or any of the kernel-selection bits 2-14) without forcing them (bit 16).
-// Measured on B200 (tools/tune_tp2.py, profiles/r1_plan_sweep.md): shared scene up to 8,192 balls ->
+// (lanes_per_ball != 0 or the kernel-selection bits 2-3) without forcing them (bit 16).
+// Measured on B200 (tools/tune_fwd.py, profiles/r1_plan_sweep.md): shared scene up to 8,192 balls ->
 // time-parallel variant with 16 lanes (steps) per ball; 8,192-32,767 balls -> lane-split, 4 lanes;
 // more -> one thread per ball; dense scenes (>= 2,048 segments) at least 2 lanes (the refresh scan
 // is split over them); per-environment scenes -> lane-split, 8 lanes (16 scenes staged per block).
-constexpr int kLegacyPlanBits = 4 | 8 | 0xF0 | 256 | 0x7E00;
+constexpr int kLegacyPlanBits = 4 | 8;
 
 bool use_cull(const doper_rollout_desc* d) {
     if ((d->flags & (1 << 15)) || (d->flags & 1)) return false;
@@ -1623,53 +1364,6 @@ bool plan_reg8(const doper_rollout_desc* d) {
 
 bool use_tp(const doper_rollout_desc* d) {
     return d->lanes_per_ball == 0 && !(d->flags & 8) && d->B <= kTpMaxBalls && !plan_reg8(d) && !use_cull(d);
-}
-
-// Multi-ball time-parallel kernel (rollout_fwd_tp2_kernel): scenes up to 56 KB staged (>= 3 blocks
-// of 4 warps per SM); flags bit 8 keeps the single-ball kernel.  Balls per warp: flags bits 4-7
-// (1, 2, 4, 8) or chosen so that the batch still gives every SM sub-partition about two warps.
-bool use_tp2(const doper_rollout_desc* d) {
-    return use_tp(d) && !(d->flags & 256) && (size_t)scene_layout(1, d->S).S_pad * 20 <= 56 * 1024;
-}
-
-int tp2_balls_per_warp(const doper_rollout_desc* d) {
-    const int ov = (d->flags >> 4) & 0xf;
-    if (ov == 1 || ov == 2 || ov == 4 || ov == 8) return ov;
-    if (d->per_env) return d->B >= 8192 ? 4 : 1;
-    int P = 8;
-    while (P > 1 && d->B / P < 2 * 148 * 4) P /= 2;
-    return P;
-}
-
-int tp2_warps_per_block(const doper_rollout_desc* d) {
-    const int ov = (d->flags >> 9) & 0x3f;
-    if (ov >= 1 && ov <= kTp2Threads / 32) return ov;
-    return kTp2Threads / 32;
-}
-
-template <int P, bool PER_ENV>
-int launch_fwd_tp2(cudaStream_t st, const FwdParams& p, int wpb) {
-    const size_t scene = (size_t)scene_layout(1, p.S).S_pad * 20;
-    const size_t smem = (PER_ENV ? (size_t)wpb * P : 1) * scene + 16 + (size_t)wpb * sizeof(Tp2Warp<P>);
-    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(rollout_fwd_tp2_kernel<P, PER_ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem) != cudaSuccess)
-        return DOPER_ERR_SMEM_LIMIT;
-    const int64_t bpb = (int64_t)wpb * P;
-    const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
-    rollout_fwd_tp2_kernel<P, PER_ENV><<<grid, wpb * 32, smem, st>>>(p);
-    return launch_status();
-}
-
-template <bool PER_ENV>
-int dispatch_fwd_tp2(cudaStream_t st, const FwdParams& p, int P, int wpb) {
-    switch (P) {
-        case 1: return launch_fwd_tp2<1, PER_ENV>(st, p, wpb);
-        case 2: return launch_fwd_tp2<2, PER_ENV>(st, p, wpb);
-        case 4: return launch_fwd_tp2<4, PER_ENV>(st, p, wpb);
-        default: return launch_fwd_tp2<8, PER_ENV>(st, p, wpb);
-    }
 }
 
 // lane = time step kernels write [B][n_steps] so that a group's stores are contiguous
@@ -1954,7 +1648,7 @@ const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backwar
     while ((1 << lg) < G) ++lg;
     if (use_tpc(d)) return tpc[lg > 0 ? lg - 1 : 0];
     if (use_cull(d)) return cull[lg];
-    if (use_tp(d)) return use_tp2(d) ? "rollout_fwd_tp2_kernel" : "rollout_fwd_tp_kernel";
+    if (use_tp(d)) return "rollout_fwd_tp_kernel";
     if (scene_layout(1, d->S).S_pad <= 256 && G >= 8 && !(d->flags & 4)) return "rollout_fwd_reg_kernel";
     return split[lg];
 }
@@ -2003,10 +1697,6 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         if (w.state_off) p.hitstate = reinterpret_cast<float4*>(base + w.state_off);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (tp && use_tp2(d)) {
-        const int P = tp2_balls_per_warp(d), wpb = tp2_warps_per_block(d);
-        return d->per_env ? dispatch_fwd_tp2<true>(st, p, P, wpb) : dispatch_fwd_tp2<false>(st, p, P, wpb);
-    }
     if (tp) {
         if (smem > 48 * 1024 &&
             cudaFuncSetAttribute(rollout_fwd_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=

@@ -158,68 +158,6 @@ __device__ __forceinline__ unsigned long long lane_filtered(const SceneView& sc,
     return key;
 }
 
-// out-of-line copy for the multi-point sweep (P call sites; candidates are ~1.5 per sweep)
-__device__ __noinline__ float cand_dist_ol(float px, float py, float4 q) { return cand_dist(px, py, q); }
-
-// P points per lane against ONE scene (the multi-ball time-parallel kernel: lane = time step,
-// P balls per warp).  Every segment is loaded once (warp-wide broadcast from shared memory) and
-// estimated for all P points: (2 + 11 P) / P issue slots per pair instead of 13, and P independent
-// dependency chains per lane.  Candidates are recorded per point in 32-segment windows and get the
-// reference arithmetic exactly as in lane_filtered.  sc.rl must be 16-byte aligned.
-// The inner loop is deliberately NOT unrolled beyond 4 segments: a fully unrolled window is ~1,500
-// instructions of straight-line code, and with one or two warps per scheduler the kernel then
-// stalls on instruction fetch (ncu: 45 % of the sweep's samples were stall_no_inst).
-template <int P>
-__device__ __forceinline__ void sweep_points(const SceneView& sc, const float (&px)[P], const float (&py)[P],
-                                             const int (&prev)[P], const float (&kappa)[P],
-                                             unsigned long long (&key)[P]) {
-    float thr[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        thr[p] = __fmaf_rn(approx_d2(px[p], py[p], sc.q[prev[p]], sc.rl[prev[p]]), kFilterOneEps, kappa[p]);
-        key[p] = kNoKey;
-    }
-    const float4* rl4 = reinterpret_cast<const float4*>(sc.rl);
-    for (int base = 0; base < sc.S_pad; base += 32) {
-        unsigned mask[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) mask[p] = 0u;
-        unsigned bit = 1u;
-#pragma unroll 1
-        for (int j = base; j < base + 32; j += 4) {
-            const float4 r = rl4[j >> 2];
-            const float rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 q = sc.q[j + u];
-                const unsigned bu = bit << u;
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const float a = approx_d2(px[p], py[p], q, rr[u]);
-                    mask[p] |= (a <= thr[p]) ? bu : 0u;
-                }
-            }
-            bit <<= 4;
-        }
-        unsigned any = 0u;
-#pragma unroll
-        for (int p = 0; p < P; ++p) any |= mask[p];
-        if (any) {
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                unsigned m = mask[p];
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1u;
-                    const int c = base + j;
-                    const unsigned long long kk = make_key(cand_dist_ol(px[p], py[p], sc.q[c]), c);
-                    key[p] = kk < key[p] ? kk : key[p];
-                }
-            }
-        }
-    }
-}
-
 // min over the G lanes of a group.  A full warp uses two REDUX (distance bits, then index among
 // the minima); sub-warp groups use a shuffle butterfly (REDUX with per-group masks is serialised
 // over the distinct masks of the warp: measured 4x slower at G = 8).

@@ -39,7 +39,6 @@ class RolloutOptions:
 
     def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False,
                  sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True,
-                 balls_per_warp: int = 0, single_ball_time_parallel: bool = False, warps_per_block: int = 0,
                  broad_phase: bool = None, exact_index_log: bool = False,
                  broad_phase_time_parallel: bool = False, hit_state_array: bool = True):
         self.ckpt_every = int(ckpt_every)
@@ -48,9 +47,6 @@ class RolloutOptions:
         self.sequential_backward = bool(sequential_backward)  # oracle-order adjoint (bit-exact)
         self.smem_forward = bool(smem_forward)  # TMA/shared-memory forward even for small scenes
         self.time_parallel = bool(time_parallel)  # allow the warp-per-ball speculative forward
-        self.balls_per_warp = int(balls_per_warp)  # multi-ball time-parallel kernel: 0 = auto, else 1, 2, 4, 8
-        self.single_ball_time_parallel = bool(single_ball_time_parallel)  # keep the one-ball-per-warp kernel
-        self.warps_per_block = int(warps_per_block)  # multi-ball time-parallel kernel: 0 = auto
         # candidate-list (broad phase) forward: None = library default, True / False = force on / off
         self.broad_phase = broad_phase
         # hit log: exact closest-segment index at EVERY step (default for the broad-phase kernel: at
@@ -99,8 +95,6 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
     d.lanes_per_ball = opts.lanes_per_ball
     d.flags = ((1 if opts.force_exact_sweep else 0) | (2 if opts.sequential_backward else 0) |
                (4 if opts.smem_forward else 0) | (0 if opts.time_parallel else 8) |
-               ((opts.balls_per_warp & 0xF) << 4) | (256 if opts.single_ball_time_parallel else 0) |
-               ((opts.warps_per_block & 0x3F) << 9) |
                ((1 << 16) if opts.broad_phase else 0) | ((1 << 15) if opts.broad_phase is False else 0) |
                ((1 << 17) if opts.exact_index_log else 0) |
                ((1 << 18) if opts.broad_phase_time_parallel else 0) |

@@ -139,13 +139,10 @@ typedef struct {
                                bit 1: force the sequential (oracle-order, bit-exact) backward;
                                bit 2: force the shared-memory lane-split forward kernel over the
                                       register-resident one (only with lanes_per_ball != 0);
-                               bit 3: disable the time-parallel (warp per ball) forward kernel;
-                               bits 4-7: balls per warp of the multi-ball time-parallel kernel
-                                      (1, 2, 4 or 8; 0 = chosen from B);
-                               bit 8: keep the single-ball time-parallel kernel;
-                               bits 9-14: warps per block of the multi-ball kernel (0 = default);
+                               bit 3: disable the time-parallel (warp per ball) full-sweep forward kernel;
                                bit 15 / bit 16: forbid / force the broad-phase (candidate list)
-                                      forward kernel;
+                                      forward kernels; bit 18: with bit 16 and lanes_per_ball >= 2, the
+                                      time-parallel (lane = step) variant instead of the lane-split one;
                                bit 19: no hit-state array in the workspace (saves 16 B per ball-step;
                                       the backward then replays collided K-blocks from checkpoints);
                                bit 17: hit log holds the exact closest index at EVERY step (the

@@ -53,13 +53,12 @@ def test_rollout_forward_bitexact_all_lane_counts(sim, cref, lanes, exact, smem)
     assert_bitexact(got["checkpoints"][1, :, :2], ref["traj_x"][15], "ckpt 1")
 
 
-@pytest.mark.parametrize("bpw,legacy", [(1, False), (2, False), (4, False), (8, False), (0, True)])
 @pytest.mark.parametrize("regime", ["reference", "bouncy", "exact", "per_env"])
-def test_time_parallel_kernels_bitexact(sim, cref, bpw, legacy, regime):
-    """Multi-ball time-parallel kernel (P = 1, 2, 4, 8 balls per warp) and the single-ball one:
-    indices, hit flags, states, trajectories and checkpoints bit-exact in every regime."""
+def test_full_sweep_time_parallel_kernel_bitexact(sim, cref, regime):
+    """rollout_fwd_tp_kernel (warp per ball, lane = step, every pair every step): indices, hit flags,
+    states, trajectories and checkpoints bit-exact in every regime."""
     ball_sim, geo = sim
-    n, B = 330, 203  # ragged in balls (not a multiple of 4 warps x P) and in steps (330 = 10 * 32 + 10)
+    n, B = 330, 203  # ragged in balls and in steps (330 = 10 * 32 + 10)
     consts = syn.reference_constants()
     if regime == "per_env":
         segs = syn.make_env_maps(21, B, 67)
@@ -76,8 +75,8 @@ def test_time_parallel_kernels_bitexact(sim, cref, bpw, legacy, regime):
     ref = cref.rollout_fwd(n, np.float32((n / 1000) / n), c, A, segs, x0, v0, want_traj=True)
     assert ref["hit"].sum() > (1500 if regime == "bouncy" else 15)
     got = ball_sim.rollout_history(n / 1000, n, scene, x0, v0, A, consts,
-                                   _opts(ball_sim, balls_per_warp=bpw, single_ball_time_parallel=legacy,
-                                         smem_forward=True, force_exact_sweep=(regime == "exact"), ckpt_every=11),
+                                   _opts(ball_sim, smem_forward=True, force_exact_sweep=(regime == "exact"),
+                                         ckpt_every=11),
                                    want_trajectory=True)
     assert np.array_equal(got["idx"], ref["idx"]), "closest-segment indices"
     assert np.array_equal(got["hit"], ref["hit"]), "hit flags"

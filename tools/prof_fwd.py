@@ -1,6 +1,6 @@
 """Launch one forward-kernel variant a few times (the command ncu wraps).
 
-    python tools/prof_fwd.py <workload> <balls_per_warp|tp1|default> [n_balls] [reps]
+    python tools/prof_fwd.py <workload> <default|nocull|tp1|cullG|tpcG> [n_balls] [reps]
 """
 import ctypes
 import sys
@@ -34,9 +34,11 @@ elif var.startswith("tpc"):
 elif var.startswith("cull"):
     kw = dict(lanes_per_ball=int(var[4:]), broad_phase=True)
 elif var == "tp1":
-    kw = dict(single_ball_time_parallel=True, smem_forward=True)
+    kw = dict(smem_forward=True)
+elif var == "nocull":
+    kw = dict(broad_phase=False)
 else:
-    kw = dict(balls_per_warp=int(var), smem_forward=True)
+    raise SystemExit(f"unknown variant {var}")
 opts = ball_sim.RolloutOptions(**kw)
 desc = ball_sim._make_desc(B, scene, w["sim_time"], n, w["attractor"], w["constants"], opts)
 bufs = ball_sim._Buffers.get(dev, desc)

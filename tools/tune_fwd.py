@@ -1,7 +1,7 @@
-"""Forward-kernel A/B timing under gpurun: multi-ball time-parallel kernel (balls per warp x warps
-per block) vs the single-ball time-parallel kernel vs the default plan.
+"""Forward-kernel A/B timing under gpurun: default plan vs full-sweep kernels vs the broad-phase
+kernels at every lane count.
 
-    python tools/tune_tp2.py c2 [n_balls] [lo hi]
+    python tools/tune_fwd.py c2 [n_balls] [lo hi]
 """
 import ctypes
 import json
@@ -46,9 +46,7 @@ def main():
     tgt = ball_sim._target2(w["target"])
     out = {"workload": name, "B": B, "n_steps": n, "S": int(w["segments"].shape[-3]), "fwd_ms": {}}
     variants = [("default", {}), ("nocull", dict(broad_phase=False))]
-    variants += [(f"tp2_P{P}_w{W}", dict(balls_per_warp=P, warps_per_block=W, smem_forward=True))
-                 for P in (1, 2, 4, 8) for W in (4, 2)]
-    variants += [("tp1", dict(single_ball_time_parallel=True, smem_forward=True))]
+    variants += [("tp1", dict(smem_forward=True))]
     variants += [(f"cull_G{g}", dict(lanes_per_ball=g, broad_phase=True)) for g in (1, 2, 4, 8, 16, 32)]
     variants += [(f"tpc_G{g}", dict(lanes_per_ball=g, broad_phase=True, broad_phase_time_parallel=True)) for g in (2, 4, 8, 16, 32)]
     only = [a[5:] for a in sys.argv if a.startswith("only=")]
@@ -73,7 +71,7 @@ def main():
         out.setdefault("bwd_ms", {})[tag] = bms
         print(f"{name} B={B} {tag:14s} fwd {ms} ms   bwd {bms} ms", flush=True)
     Path("gpurun_out").mkdir(exist_ok=True)
-    Path(f"gpurun_out/tune_tp2_{name}_{B}_{lo}.json").write_text(json.dumps(out, indent=1))
+    Path(f"gpurun_out/tune_fwd_{name}_{B}_{lo}.json").write_text(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":
