@@ -154,6 +154,7 @@ struct FwdParams {
     int64_t B;
     int S, per_env, n_steps, K, force_exact;
     int exact_idx;  // log the exact closest index at every step (default: at collisions only)
+    int stage;      // 1: scene staged in shared memory (TMA); 0: read from global memory / L2 (scene too large)
     Consts c;
     const unsigned char* scene_ws;
     const float2* x0;
@@ -269,19 +270,24 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_cull_kernel(const Fwd
     const int64_t n_scenes = p.per_env ? p.B : 1;
     const SceneLayout L = scene_layout(n_scenes, p.S);
     const int n_local = p.per_env ? BPB : 1;
+    const bool staged = p.stage != 0;  // else the scene is read in place (global memory / L2): any size works,
+                                       // the per-step work touches the short lists only
+    const size_t scene_bytes = staged ? (size_t)n_local * L.S_pad * 20 + 16 : 0;
 
     float4* sq = reinterpret_cast<float4*>(smem);
     float* srl = reinterpret_cast<float*>(smem + (size_t)n_local * L.S_pad * sizeof(float4));
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_local * L.S_pad * 20);
-    unsigned short* list = reinterpret_cast<unsigned short*>(smem + (size_t)n_local * L.S_pad * 20 + 16) + tid;
+    unsigned short* list = reinterpret_cast<unsigned short*>(smem + scene_bytes) + tid;
 
     const int64_t first_ball = (int64_t)blockIdx.x * BPB;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (tid == 0) {
-        int64_t first_scene = p.per_env ? first_ball : 0;
-        int n = p.per_env ? (int)min((int64_t)BPB, p.B - first_ball) : 1;
-        stage_scenes(sq, srl, p.scene_ws, L, first_scene, n, bar);
+    if (staged) {
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            int64_t first_scene = p.per_env ? first_ball : 0;
+            int n = p.per_env ? (int)min((int64_t)BPB, p.B - first_ball) : 1;
+            stage_scenes(sq, srl, p.scene_ws, L, first_scene, n, bar);
+        }
     }
 
     int64_t ball = first_ball + slot;
@@ -291,8 +297,14 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_cull_kernel(const Fwd
     const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off)[p.per_env ? ball : 0];
 
     SceneView sc;
-    sc.q = sq + (size_t)local_scene * L.S_pad;
-    sc.rl = srl + (size_t)local_scene * L.S_pad;
+    if (staged) {
+        sc.q = sq + (size_t)local_scene * L.S_pad;
+        sc.rl = srl + (size_t)local_scene * L.S_pad;
+    } else {
+        const size_t sid = p.per_env ? (size_t)ball : 0;
+        sc.q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) + sid * L.S_pad;
+        sc.rl = reinterpret_cast<const float*>(p.scene_ws + L.rl_off) + sid * L.S_pad;
+    }
     sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
 
     float2 xx = p.x0[ball], vv = p.v0[ball];
@@ -300,7 +312,7 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_cull_kernel(const Fwd
     const Consts c = p.c;
     const bool writer = active && lane == 0;
 
-    mbar_wait(bar, 0);
+    if (staged) mbar_wait(bar, 0);
 
     int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
     float4* ck = p.ckpt ? p.ckpt + ball : nullptr;
@@ -1335,6 +1347,10 @@ constexpr int64_t kTpMaxBalls = 65536;
 // is split over them); per-environment scenes -> lane-split, 8 lanes (16 scenes staged per block).
 constexpr int kLegacyPlanBits = 4 | 8;
 
+// the lane = step kernel needs the scene in shared memory; larger scenes go to the lane-split kernel,
+// which reads them in place
+bool scene_fits_smem(const doper_rollout_desc* d) { return (size_t)scene_layout(1, d->S).S_pad * 20 <= 200 * 1024; }
+
 bool use_cull(const doper_rollout_desc* d) {
     if ((d->flags & (1 << 15)) || (d->flags & 1)) return false;
     if (d->flags & (1 << 16)) return true;
@@ -1345,7 +1361,7 @@ bool use_tpc(const doper_rollout_desc* d) {
     if (!use_cull(d)) return false;
     if (d->lanes_per_ball != 0) return (d->flags & (1 << 18)) != 0 && d->lanes_per_ball >= 2;
     if (d->flags & (1 << 18)) return true;
-    return !d->per_env && d->B <= 8192;
+    return !d->per_env && d->B <= 8192 && scene_fits_smem(d);
 }
 
 int cull_lanes(const doper_rollout_desc* d) {
@@ -1354,6 +1370,7 @@ int cull_lanes(const doper_rollout_desc* d) {
     if (use_tpc(d)) return 16;
     int g = d->B < 32768 ? 4 : 1;
     if (scene_layout(1, d->S).S_pad >= 2048 && g < 2) g = 2;
+    if (!scene_fits_smem(d) && g < 8) g = 8;  // unstaged scene: split the refresh scan (L2 reads) over more lanes
     return g;
 }
 
@@ -1448,9 +1465,11 @@ int launch_fwd(cudaStream_t st, const FwdParams& p, size_t smem) {
 }
 
 template <int G>
-int launch_fwd_cull(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
-    const size_t smem = scene_smem + (size_t)CullCfg<G>::LCAP * kFwdThreads * sizeof(unsigned short);
-    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+int launch_fwd_cull(cudaStream_t st, FwdParams p, size_t scene_smem) {
+    const size_t lists = (size_t)CullCfg<G>::LCAP * kFwdThreads * sizeof(unsigned short);
+    // a scene that does not fit shared memory (next to the lists) is read in place
+    p.stage = (int)(scene_smem + lists) <= max_optin_smem() ? 1 : 0;
+    const size_t smem = (p.stage ? scene_smem : 0) + lists;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(rollout_fwd_cull_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
             cudaSuccess)
@@ -1674,7 +1693,8 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     const int tp_wpb = tp_warps_per_block(d);
     const size_t smem = tp ? (size_t)(d->per_env ? tp_wpb : 1) * scene_layout(1, d->S).S_pad * 20 + 16
                            : fwd_smem_bytes(d, G);
-    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    const bool unstaged_ok = use_cull(d) && !use_tpc(d);  // the lane-split broad-phase kernel can read the scene in place
+    if ((int)smem > max_optin_smem() && !unstaged_ok) return DOPER_ERR_SMEM_LIMIT;
     const int K = resolve_K(d);
     FwdParams p;
     p.hl_st = log_ball_major(d) ? 1 : d->B;  // hit log is ball-major for the time-parallel kernels
@@ -1682,6 +1702,7 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     p.B = d->B; p.S = d->S; p.per_env = d->per_env ? 1 : 0; p.n_steps = d->n_steps; p.K = K;
     p.force_exact = d->flags & 1;
     p.exact_idx = (d->flags >> 17) & 1;
+    p.stage = 1;
     p.c = make_consts(d);
     p.scene_ws = reinterpret_cast<const unsigned char*>(scene_ws);
     p.x0 = reinterpret_cast<const float2*>(x0); p.v0 = reinterpret_cast<const float2*>(v0);

@@ -361,6 +361,25 @@ def test_dense_scene_10k_segments(sim, cref):
     assert_bitexact(h["x_T"], ref["x_T"])
 
 
+def test_scene_larger_than_shared_memory(sim, cref):
+    """20,001 segments (400 KB prepared) do not fit the 227 KB of shared memory: the default plan reads
+    the scene in place (lane-split broad-phase kernel) instead of failing."""
+    ball_sim, _ = sim
+    segs = syn.make_map(77, 6667)
+    x0, v0 = syn.make_init_states(78, 48, segs)
+    n = 80
+    consts = syn.reference_constants()
+    c = onp.make_constants(consts)
+    A, T = np.array(syn.REFERENCE_ATTRACTOR, np.float32), np.array(syn.REFERENCE_TARGET, np.float32)
+    ref = cref.value_and_grad(n, np.float32((n / 1000) / n), c, A, T, segs, x0, v0)
+    h = ball_sim.rollout_history(n / 1000, n, segs, x0, v0, A, consts, _opts(ball_sim, exact_index_log=True))
+    assert np.array_equal(h["idx"], ref["idx"]) and np.array_equal(h["hit"], ref["hit"])
+    assert_bitexact(h["x_T"], ref["x_T"])
+    (_, _), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, segs, x0, v0, T, A, consts,
+                                                _opts(ball_sim, sequential_backward=True))
+    assert_bitexact(gv, ref["grad_v0"])
+
+
 def test_full_size_c2_properties(sim, cref):
     """BASELINE configs[1] at full size: parity on a slice + size-independent properties."""
     ball_sim, _ = sim
