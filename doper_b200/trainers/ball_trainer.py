@@ -10,6 +10,11 @@ action is discarded and the next action starts again from the initial random vel
 
 Multi-GPU: with ``torch.distributed`` initialised, every rank simulates its own
 batch and the controller gradients + loss are all-reduced once per ``optimize_parameters``.
+
+``graphed_iteration`` captures the whole action loop of one iteration — 8 x
+(observation kernel, controller forward, rollout forward + loss + backward, controller backward) +
+gradient clip + Adam — into ONE CUDA graph: at the reference's batch size (16 balls) an iteration is
+launch-bound (~200 small launches), and a graph replay removes the per-launch host cost.
 """
 __all__ = ["BallAttractorTrainer"]
 
@@ -37,7 +42,8 @@ class BallAttractorTrainer:
         self.controller = LinearReLUController(config["model"]).to(self.device)
         self.sim_time = config["sim"]["sim_time"]
         self.n_steps = config["sim"]["n_steps"]
-        self.optimizer = torch.optim.Adam(self.controller.parameters())
+        # capturable: the step counter lives on the device, so the optimiser can run inside a CUDA graph
+        self.optimizer = torch.optim.Adam(self.controller.parameters(), capturable=True)
         self.batch_size = self.config["train"]["batch_size"]
         self.num_actions = self.config["train"]["num_actions"]
         self._reducer = None
@@ -86,3 +92,71 @@ class BallAttractorTrainer:
         torch.nn.utils.clip_grad_norm_(self.controller.parameters(), grad_clip)
         self.optimizer.step()
         return loss_val
+
+    # ------------------------------------------------------------------------------------------
+    # one iteration as ONE CUDA graph
+    # ------------------------------------------------------------------------------------------
+    def _action_loop(self, agent, scene_handler, coordinate_init, velocity_init, grad_clip):
+        """ball_trainer.py:53-75 on device tensors; no host synchronisation anywhere (capturable)."""
+        loss_val = None
+        for action_id in range(self.num_actions):
+            observation = agent.get_observations(coordinate_init, velocity_init, scene_handler)
+            impulse = self.controller(observation)
+            (loss_val, (coord, velocity)), v_grad = vmapped_grad_and_value(
+                self.sim_time, self.n_steps, scene_handler.jax_scene, coordinate_init,
+                (velocity_init + impulse / self.constants["mass"]).detach(),
+                onp.array(self.config["sim"]["coordinate_target"]),
+                onp.array(self.config["sim"]["attractor_coordinate"]),
+                self.constants,
+            )
+            impulse.backward(v_grad)
+            coordinate_init = coord
+        torch.nn.utils.clip_grad_norm_(self.controller.parameters(), grad_clip)
+        self.optimizer.step()
+        return loss_val
+
+    def graphed_iteration(self, agent, scene_handler, grad_clip=5, warmup=3):
+        """-> ``run(coordinate_init [B,2], velocity_init [B,2]) -> loss`` replaying one captured CUDA
+        graph per call (inputs are copied into static buffers; the returned loss is a static 0-dim
+        tensor that the next replay overwrites).  The scene must not change between replays (capture
+        one callable per scene); ``scene_handler.get_init_state`` stays outside the graph (its
+        rejection loop reads a flag on the host)."""
+        B = self.batch_size
+        x_static = torch.zeros((B, 2), dtype=torch.float32, device=self.device)
+        v_static = torch.zeros((B, 2), dtype=torch.float32, device=self.device)
+        x_static.copy_(torch.as_tensor(scene_handler.get_init_state(B), dtype=torch.float32, device=self.device))
+        v_static.uniform_(-1, 2)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        # warm-up on a side stream (allocates the cached rollout buffers, lazily-initialised optimiser
+        # state, cuBLAS workspaces) — the parameter updates of these iterations are rolled back
+        saved = [p.detach().clone() for p in self.controller.parameters()]
+        saved_opt = None
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.optimizer.zero_grad(set_to_none=True)
+                self._action_loop(agent, scene_handler, x_static, v_static, grad_clip)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            loss_static = self._action_loop(agent, scene_handler, x_static, v_static, grad_clip)
+        with torch.no_grad():
+            for p, q in zip(self.controller.parameters(), saved):
+                p.copy_(q)
+        del saved_opt
+        # reset Adam's moments / step in place (the graph holds pointers to these tensors)
+        for st in self.optimizer.state.values():
+            for k, v in st.items():
+                if isinstance(v, torch.Tensor):
+                    v.zero_()
+
+        def run(coordinate_init, velocity_init):
+            x_static.copy_(torch.as_tensor(coordinate_init, dtype=torch.float32, device=self.device))
+            v_static.copy_(torch.as_tensor(velocity_init, dtype=torch.float32, device=self.device))
+            graph.replay()
+            return loss_static
+
+        run.graph = graph
+        return run

@@ -103,3 +103,33 @@ def test_trainer_gradient_handoff_matches_manual_chain_rule():
     (impulse * v_grad).sum().backward()
     for a, b in zip(got, [p.grad for p in ref_tr.controller.parameters()]):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
+def test_graphed_iteration_matches_eager():
+    """the 8-action iteration captured into one CUDA graph updates the controller
+    exactly like the eager loop on the same draws."""
+    from doper_b200.agents import RangeSensingAgent
+    from doper_b200.scenes import SingleScene
+    from doper_b200.sim.jax_geometry import JaxScene
+    from doper_b200.trainers import BallAttractorTrainer
+    cfg = copy.deepcopy(CONFIG)
+    handler = SingleScene(cfg, jax_scene=JaxScene(syn.make_map(1002, 67)))
+    agent = RangeSensingAgent(cfg)
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    draws = [(handler.get_init_state(16, generator=g), -1 + 3 * torch.rand((16, 2), device="cuda", generator=g))
+             for _ in range(3)]
+
+    torch.manual_seed(4)
+    eager = BallAttractorTrainer(copy.deepcopy(cfg))
+    losses_e = []
+    for x0, v0 in draws:
+        eager.optimizer.zero_grad(set_to_none=True)
+        losses_e.append(float(eager._action_loop(agent, handler, x0, v0, 5)))
+
+    torch.manual_seed(4)
+    graphed = BallAttractorTrainer(copy.deepcopy(cfg))
+    run = graphed.graphed_iteration(agent, handler)
+    losses_g = [float(run(x0, v0)) for x0, v0 in draws]
+    assert np.allclose(losses_e, losses_g, rtol=1e-6)
+    for a, b in zip(eager.controller.parameters(), graphed.controller.parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
