@@ -925,7 +925,14 @@ struct BwdParams {
     const float2* vT_bar;  // nullable
     float2* x0_bar;        // nullable
     float2* v0_bar;
+    // hybrid plan of the sequential kernel: a ball that has pulled back more than defer_after collided
+    // steps (sliding contact: a ~2.6 us serial chain per step) appends itself to `deferred` ([0] = count,
+    // then ball ids) and leaves; rollout_bwd_chunked_kernel then redoes those balls 32 chunks in parallel
+    int* deferred;         // nullable
+    int defer_after;
 };
+
+constexpr int kDeferCap = 2048;  // deferred balls per launch; beyond it balls simply stay sequential
 
 // Sequential backward, one thread per ball, bit-exact against the oracle's adjoint.  A step that
 // did not collide is pulled back from its log word alone (step_vjp_free: no state, no replay);
@@ -950,6 +957,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
     const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
 
     const int n_ckpt = (p.n_steps + p.K - 1) / p.K;
+    int collided = 0;
     for (int ck = n_ckpt - 1; ck >= 0; --ck) {
         const int t0 = ck * p.K, t1 = min(p.n_steps, t0 + p.K);
         int have = -1;  // states of steps t0 .. t0 + have are in the stash
@@ -971,6 +979,11 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
                     step_vjp_free_1d(((m_cx >> j) & 1u) != 0u, dk, c, gx, gvx);
                     step_vjp_free_1d(((m_cy >> j) & 1u) != 0u, dk, c, gy, gvy);
                     continue;
+                }
+                if (p.deferred && ++collided > p.defer_after) {
+                    const int slot = atomicAdd(p.deferred, 1);
+                    if (slot < kDeferCap) { p.deferred[1 + slot] = (int)ball; return; }  // redone chunk-parallel
+                    collided = -0x40000000;  // list full: stay sequential
                 }
                 const int32_t h = hl[(size_t)t * p.hl_st];  // collided step: the index is needed (rare reload)
                 float4 st;
@@ -1013,12 +1026,20 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
 // No block-wide synchronisation: a ball's C_pad <= 32 chunks sit in one warp, the fold runs on warp
 // shuffles.  Until a chunk meets a collision its Jacobian is block diagonal (x and y decouple in
 // free flight), so only the four non-zero (position, velocity) pairs are pulled back.
-__global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const BwdParams p, const int C_pad) {
+// With `ball_list` ([0] = count, then ids; hybrid plan of the sequential kernel) the grid covers the
+// listed balls only and `chunk_len` need not be the checkpoint period (the hit-state array is required).
+__global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const BwdParams p, const int C_pad,
+                                                                         const int chunk_len,
+                                                                         const int* __restrict__ ball_list) {
     const int tid = threadIdx.x;
     const int bpb = kBwdThreads / C_pad;
     const int chunk = tid % C_pad, slot = tid / C_pad;
-    const int64_t ball = (int64_t)blockIdx.x * bpb + slot;
-    const int n_ckpt = (p.n_steps + p.K - 1) / p.K;
+    int64_t ball = (int64_t)blockIdx.x * bpb + slot;
+    if (ball_list) {
+        const int count = min(ball_list[0], kDeferCap);
+        ball = ball < count ? (int64_t)ball_list[1 + ball] : p.B;  // p.B = no ball
+    }
+    const int n_ckpt = (p.n_steps + chunk_len - 1) / chunk_len;
     const bool active = ball < p.B && chunk < n_ckpt;
     const Consts c = p.c;
     const float dk = dfric_value(c);
@@ -1032,7 +1053,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const 
         const float4* q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) +
                           (p.per_env ? (size_t)ball * L.S_pad : 0);
         const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
-        const int t0 = chunk * p.K, t1 = min(p.n_steps, t0 + p.K);
+        const int t0 = chunk * chunk_len, t1 = min(p.n_steps, t0 + chunk_len);
         bool coupled = false;  // a collision has mixed x and y
         for (int tb = t1; tb > t0;) {
             const int ta = max(t0, tb - kBwdPrefetch);
@@ -1311,7 +1332,7 @@ int resolve_K(const doper_rollout_desc* d) {
 // The hit-state array is written and read at collided steps only (no bandwidth; it spares the
 // backward every replay); flags bit 19 drops it (memory: 16 B per ball-step) and the backward
 // replays blocks with a collision from their checkpoint instead.
-struct WsLayout { size_t log_off, state_off, total; };
+struct WsLayout { size_t log_off, state_off, defer_off, total; };
 
 WsLayout ws_layout(const doper_rollout_desc* d) {
     const int K = resolve_K(d);
@@ -1326,6 +1347,8 @@ WsLayout ws_layout(const doper_rollout_desc* d) {
         end += (size_t)d->n_steps * (size_t)d->B * sizeof(float4);
         end = (end + 255) / 256 * 256;
     }
+    w.defer_off = end;  // scratch of the hybrid backward: deferred-ball list
+    end += ((size_t)(kDeferCap + 1) * sizeof(int) + 255) / 256 * 256;
     w.total = end + 256;
     return w;
 }
@@ -1791,14 +1814,23 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     p.vT_bar = reinterpret_cast<const float2*>(vT_bar);
     p.x0_bar = reinterpret_cast<float2*>(x0_bar);
     p.v0_bar = reinterpret_cast<float2*>(v0_bar);
+    p.deferred = nullptr; p.defer_after = 0;
     if (d->n_steps == 0) return DOPER_ERR_BAD_SHAPE;
     if (use_chunked(d, K)) {
         int C_pad = 2;
         while (C_pad < (int)n_ckpt) C_pad *= 2;
         const int bpb = kBwdThreads / C_pad;
         const unsigned grid = (unsigned)((d->B + bpb - 1) / bpb);
-        rollout_bwd_chunked_kernel<<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p, C_pad);
+        rollout_bwd_chunked_kernel<<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p, C_pad, K, nullptr);
         return launch_status();
+    }
+    // hybrid: balls in sliding contact leave the sequential kernel and are redone 32 chunks in parallel
+    // (needs the hit-state array; flags bit 1 keeps everything sequential = bit-exact vs the oracle order)
+    const bool hybrid = p.hitstate && !(d->flags & 2) && d->n_steps >= 256;
+    if (hybrid) {
+        p.deferred = reinterpret_cast<int*>(const_cast<unsigned char*>(base) + w.defer_off);
+        p.defer_after = 128;
+        if (cudaMemsetAsync(p.deferred, 0, sizeof(int), (cudaStream_t)stream) != cudaSuccess) return DOPER_ERR_LAUNCH;
     }
     const size_t smem = p.hitstate ? 0 : (size_t)K * kBwdThreads * sizeof(float4);
     if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
@@ -1808,6 +1840,11 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         return DOPER_ERR_SMEM_LIMIT;
     const unsigned grid = (unsigned)((d->B + kBwdThreads - 1) / kBwdThreads);
     rollout_bwd_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(p);
+    if (hybrid && launch_status() == DOPER_OK) {
+        const int chunk_len = (d->n_steps + 31) / 32;
+        rollout_bwd_chunked_kernel<<<kDeferCap / (kBwdThreads / 32), kBwdThreads, 0, (cudaStream_t)stream>>>(
+            p, 32, chunk_len, p.deferred);
+    }
     return launch_status();
 }
 

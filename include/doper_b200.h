@@ -173,7 +173,9 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
                       const float* x0, const float* v0, float* xT, float* vT, float* traj_x,
                       float* traj_v, float* traj_a, void* ws);
 
-/* Backward: cotangents (xT_bar, vT_bar) -> (x0_bar, v0_bar).  vT_bar / x0_bar may be NULL. */
+/* Backward: cotangents (xT_bar, vT_bar) -> (x0_bar, v0_bar).  vT_bar / x0_bar may be NULL.
+ * ws is the forward's workspace; its trailing scratch area (a list of balls handed from the
+ * sequential to the chunk-parallel kernel) is written. */
 int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
                       const void* ws, const float* xT_bar, const float* vT_bar, float* x0_bar,
                       float* v0_bar);

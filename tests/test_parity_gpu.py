@@ -233,6 +233,36 @@ def test_bouncy_regime_many_collisions(sim, cref, lanes):
     assert_bitexact(gv, refg["grad_v0"], "gradient (sequential backward)")
 
 
+def test_hybrid_backward_hands_sliding_balls_to_the_chunk_parallel_kernel(sim, cref):
+    """> 32,768 balls use the sequential backward; balls in sliding contact (hundreds of collided steps: a
+    serial ~2.6 us chain each) are handed to the chunk-parallel kernel.  Gradients stay as accurate as
+    the reference-order fp32 adjoint, and flags bit 1 still gives the bit-exact sequential result."""
+    ball_sim, _ = sim
+    w = syn.make_workload("c2", n_balls=33000)
+    consts = dict(w["constants"]); consts["attractor_strength"] = 2000.0
+    n = 400
+    c = onp.make_constants(consts)
+    dt = np.float32((n / 1000) / n)
+    ref = cref.value_and_grad(n, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+    assert (ref["hit"].sum(0) > 128).sum() > 50  # plenty of balls beyond the hand-over threshold
+    args = (n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], consts)
+    (_, (xT, _)), gv = ball_sim.vmapped_grad_and_value(*args)
+    assert_bitexact(xT, ref["x_T"], "x_T")
+    (_, _), gv_seq = ball_sim.vmapped_grad_and_value(*args, _opts(ball_sim, sequential_backward=True))
+    assert_bitexact(gv_seq, ref["grad_v0"], "sequential backward")
+    # this regime is violent (|gradient| up to 1e35; the reference-order fp32 adjoint itself overflows to NaN
+    # on a few dozen balls): parity is asserted where the oracle gradient is finite and moderate (SURVEY App. D)
+    truth, _ = cref.grad_truth64(n, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+    ok = np.isfinite(ref["grad_v0"]).all(1) & np.isfinite(truth).all(1) & (np.abs(truth).max(1) < 1e12)
+    assert ok.mean() > 0.95 and np.isfinite(gv[ok]).all()
+    e_got, e_seq = grad_rel_err(gv[ok], truth[ok]), grad_rel_err(ref["grad_v0"][ok], truth[ok])
+    assert np.quantile(e_got, 0.99) <= max(GRAD_RTOL, 2 * np.quantile(e_seq, 0.99))
+    assert e_got.max() <= max(2 * e_seq.max(), GRAD_RTOL), (e_got.max(), e_seq.max())
+    heavy = ok & (ref["hit"].sum(0) > 128)
+    assert heavy.sum() > 50 and not np.array_equal(gv[heavy], gv_seq[heavy])  # the hand-over happened (other rounding order)
+    assert_bitexact(gv[ref["hit"].sum(0) == 0], gv_seq[ref["hit"].sum(0) == 0], "balls that never collided")
+
+
 def test_gradient_vs_torch_autograd(sim):
     """Independent gradient truth: torch autograd of the select-form graph (fp32)."""
     ball_sim, _ = sim
