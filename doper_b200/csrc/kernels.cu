@@ -261,8 +261,12 @@ struct CullCfg {
     static constexpr int LCAP = G == 1 ? 48 : (G == 2 ? 32 : (G == 4 ? 16 : 8));  // list entries per lane
 };
 
-template <int G>
-__global__ void __launch_bounds__(kFwdThreads) rollout_fwd_cull_kernel(const FwdParams p) {
+// STAGED = false: the scene does not fit shared memory and is read in place (global memory / L2).
+// One thread per ball (G = 1) is compiled for 7 blocks per SM (72 registers): 131,072 balls, one
+// GPU's share of BASELINE configs[4], are then co-resident in ONE wave (with 96 registers the grid
+// needed two, the second one 38 % full).
+template <int G, bool STAGED>
+__global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED) ? 7 : 1) rollout_fwd_cull_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int BPB = kFwdThreads / G;  // balls per block
     constexpr int LCAP = CullCfg<G>::LCAP;
@@ -270,8 +274,8 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_cull_kernel(const Fwd
     const int64_t n_scenes = p.per_env ? p.B : 1;
     const SceneLayout L = scene_layout(n_scenes, p.S);
     const int n_local = p.per_env ? BPB : 1;
-    const bool staged = p.stage != 0;  // else the scene is read in place (global memory / L2): any size works,
-                                       // the per-step work touches the short lists only
+    constexpr bool staged = STAGED;  // else the scene is read in place (global memory / L2): any size works,
+                                     // the per-step work touches the short lists only
     const size_t scene_bytes = staged ? (size_t)n_local * L.S_pad * 20 + 16 : 0;
 
     float4* sq = reinterpret_cast<float4*>(smem);
@@ -1493,13 +1497,17 @@ int launch_fwd_cull(cudaStream_t st, FwdParams p, size_t scene_smem) {
     // a scene that does not fit shared memory (next to the lists) is read in place
     p.stage = (int)(scene_smem + lists) <= max_optin_smem() ? 1 : 0;
     const size_t smem = (p.stage ? scene_smem : 0) + lists;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(rollout_fwd_cull_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
-        return DOPER_ERR_SMEM_LIMIT;
     const int bpb = kFwdThreads / G;
     const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
-    rollout_fwd_cull_kernel<G><<<grid, kFwdThreads, smem, st>>>(p);
+    if (p.stage) {
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(rollout_fwd_cull_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return DOPER_ERR_SMEM_LIMIT;
+        rollout_fwd_cull_kernel<G, true><<<grid, kFwdThreads, smem, st>>>(p);
+    } else {
+        rollout_fwd_cull_kernel<G, false><<<grid, kFwdThreads, smem, st>>>(p);
+    }
     return launch_status();
 }
 
