@@ -375,6 +375,43 @@ def test_degenerate_segment_nan_semantics(sim, cref):
     assert np.array_equal(idx, i_ref) and np.isnan(dist).all()
 
 
+@pytest.mark.parametrize("n_balls", [203, 9000, 40000])  # lane = step kernel / lane-split 4 lanes / one thread per ball
+def test_default_plan_degenerate_scene_and_non_finite_states(sim, cref, n_balls):
+    """Corner cases of SURVEY Appendix D on the DEFAULT plan (broad-phase kernels): a zero-length segment
+    gives a NaN distance that wins every argmin (so nothing ever collides), and balls whose state
+    overflows to inf / NaN must follow the reference arithmetic too (the kernels drop to the exact
+    sweep for them)."""
+    ball_sim, _ = sim
+    w = syn.make_workload("c2", n_balls=n_balls)
+    n = 60
+    consts = syn.reference_constants()
+    c = onp.make_constants(consts)
+    dt = np.float32((n / 1000) / n)
+    x0, v0 = w["x0"].copy(), w["v0"].copy()
+    x0[5] = np.array([3.0e38, -3.3e38], np.float32)  # -2 (x - A) overflows at once: inf, then NaN
+    v0[5] = np.array([3.0e37, -1.0e38], np.float32)
+    v0[6] = np.array([1.0e20, 2.0e19], np.float32)   # finite but far beyond the filter's range
+    # (a) healthy scene, wild balls
+    ref = cref.rollout_fwd(n, dt, c, w["attractor"], w["segments"], x0, v0, want_traj=True)
+    got = ball_sim.rollout_history(n / 1000, n, w["segments"], x0, v0, w["attractor"], consts,
+                                   _opts(ball_sim, exact_index_log=True), want_trajectory=True)
+    assert not np.isfinite(ref["x_T"][5]).all()
+    assert np.array_equal(got["hit"], ref["hit"]) and np.array_equal(got["idx"], ref["idx"])
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    assert_bitexact(got["trajectory"].velocity, ref["traj_v"], "trajectory v")
+    # (b) degenerate scene: segment 7 collapsed to a point
+    segs = w["segments"].copy()
+    segs[7] = segs[7][0]
+    ref = cref.rollout_fwd(n, dt, c, w["attractor"], segs, x0, v0, want_traj=True)
+    tame = np.ones(n_balls, bool); tame[[5, 6]] = False
+    assert (ref["idx"][:, tame] == 7).all() and not ref["hit"].any()
+    got = ball_sim.rollout_history(n / 1000, n, segs, x0, v0, w["attractor"], consts,
+                                   _opts(ball_sim, exact_index_log=True), want_trajectory=True)
+    assert np.array_equal(got["hit"], ref["hit"]) and np.array_equal(got["idx"], ref["idx"])
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T (degenerate scene)")
+    assert_bitexact(got["trajectory"].coordinate, ref["traj_x"], "trajectory x (degenerate scene)")
+
+
 def test_dense_scene_10k_segments(sim, cref):
     """C4-shaped scene (10,002 segments, 200 KB staged in shared memory), few balls."""
     ball_sim, _ = sim
