@@ -35,7 +35,7 @@ struct SceneHeader {  // 16 B per scene
 };
 
 struct SceneLayout {
-    size_t hdr_off, q_off, rl_off, total;
+    size_t hdr_off, q_off, rl_off, grid_off, total;  // grid_off = 0: no grid (per-environment scenes)
     int S_pad;
 };
 
@@ -48,10 +48,31 @@ __host__ __device__ inline SceneLayout scene_layout(int64_t n_scenes, int S) {
     L.rl_off = L.q_off + (size_t)n_scenes * L.S_pad * sizeof(float4);
     L.total = L.rl_off + (size_t)n_scenes * L.S_pad * sizeof(float);
     L.total = (L.total + 255) / 256 * 256;
+    L.grid_off = 0;
+    if (n_scenes == 1) {  // [GridHeader | cell_start (kGridMaxCells + 1) | items (4 S_pad)]
+        L.grid_off = L.total;
+        L.total += sizeof(GridHeader) + (size_t)(kGridMaxCells + 1) * sizeof(int) + (size_t)4 * L.S_pad * sizeof(int);
+        L.total = (L.total + 255) / 256 * 256;
+    }
     return L;
 }
 
 constexpr float kSentinel = 1.0e18f;  // far-away padding segment: never a candidate
+constexpr int kGridMinSegments = 1024;  // scenes from this size on refresh candidate lists through the grid
+
+__device__ __forceinline__ GridView grid_view(const unsigned char* ws, const SceneLayout& L) {
+    GridView g;
+    g.enabled = 0; g.cell_start = nullptr; g.items = nullptr; g.x0 = g.y0 = g.inv_h = 0.f; g.gx = g.gy = 1;
+    // small scenes: scanning a few hundred staged segments beats the dependent global-memory loads of a grid
+    // walk (measured at S = 201: 0.48 vs 0.29 ms on C2)
+    if (L.grid_off && L.S_pad >= kGridMinSegments) {
+        const GridHeader h = *reinterpret_cast<const GridHeader*>(ws + L.grid_off);
+        g.cell_start = reinterpret_cast<const int*>(ws + L.grid_off + sizeof(GridHeader));
+        g.items = g.cell_start + (kGridMaxCells + 1);
+        g.x0 = h.x0; g.y0 = h.y0; g.inv_h = h.inv_h; g.gx = h.gx; g.gy = h.gy; g.enabled = h.enabled;
+    }
+    return g;
+}
 
 __global__ void __launch_bounds__(128) scene_prepare_kernel(int64_t n_scenes, int S,
                                                             const float4* __restrict__ segs,
@@ -90,6 +111,89 @@ __global__ void __launch_bounds__(128) scene_prepare_kernel(int64_t n_scenes, in
         SceneHeader h;
         h.scale = mx; h.weird = weird; h.S = S; h.S_pad = L.S_pad;
         reinterpret_cast<SceneHeader*>(ws + L.hdr_off)[sc] = h;
+        s_w[0] = weird;
+    }
+    if (L.grid_off == 0) return;
+    // ---- uniform grid over the (single, shared) scene ------------------------------------------------
+    __syncthreads();
+    weird = s_w[0];
+    __shared__ float s_red[4][128];
+    __shared__ int s_cnt[kGridMaxCells];
+    __shared__ int s_cur[kGridMaxCells];
+    __shared__ GridHeader s_g;
+    float lox = 3.0e38f, loy = 3.0e38f, hix = -3.0e38f, hiy = -3.0e38f, ext = 0.0f;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const float4 s = in[i];
+        lox = fminf(lox, fminf(s.x, s.z)); hix = fmaxf(hix, fmaxf(s.x, s.z));
+        loy = fminf(loy, fminf(s.y, s.w)); hiy = fmaxf(hiy, fmaxf(s.y, s.w));
+        ext = fmaxf(ext, fmaxf(fabsf(s.z - s.x), fabsf(s.w - s.y)));
+    }
+    s_red[0][threadIdx.x] = lox; s_red[1][threadIdx.x] = loy; s_red[2][threadIdx.x] = -hix; s_red[3][threadIdx.x] = -hiy;
+    s_mx[threadIdx.x] = ext;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)blockDim.x; ++i) {
+            for (int k = 0; k < 4; ++k) s_red[k][0] = fminf(s_red[k][0], s_red[k][i]);
+            s_mx[0] = fmaxf(s_mx[0], s_mx[i]);
+        }
+        GridHeader g;
+        g.x0 = s_red[0][0]; g.y0 = s_red[1][0];
+        const float wx = -s_red[2][0] - g.x0, wy = -s_red[3][0] - g.y0;
+        float h = s_mx[0] * 1.0001f;
+        g.enabled = (!weird && h > 0.0f && wx >= 0.0f && wy >= 0.0f && wx < 1.0e30f && wy < 1.0e30f) ? 1 : 0;
+        g.gx = g.gy = 1;
+        if (g.enabled) {
+            for (int it = 0; it < 8; ++it) {  // coarsen until the cell count fits
+                g.gx = (int)fminf(floorf(wx / h) + 1.0f, 1.0e6f); g.gy = (int)fminf(floorf(wy / h) + 1.0f, 1.0e6f);
+                if ((long long)g.gx * g.gy <= kGridMaxCells) break;
+                h *= 1.01f * sqrtf((float)g.gx * (float)g.gy / (float)kGridMaxCells);
+            }
+            if ((long long)g.gx * g.gy > kGridMaxCells || g.gx * g.gy < 9) g.enabled = 0;  // too coarse to help
+        }
+        g.inv_h = 1.0f / h;
+        g.n_items = 0; g.pad = 0;
+        s_g = g;
+    }
+    __syncthreads();
+    const GridHeader g = s_g;
+    GridHeader* gh = reinterpret_cast<GridHeader*>(ws + L.grid_off);
+    int* cell_start = reinterpret_cast<int*>(ws + L.grid_off + sizeof(GridHeader));
+    int* items = cell_start + (kGridMaxCells + 1);
+    if (!g.enabled) {
+        if (threadIdx.x == 0) *gh = g;
+        return;
+    }
+    const int ncell = g.gx * g.gy;
+    for (int i = threadIdx.x; i < ncell; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+            const float4 s = in[i];
+            const int ax = grid_cell_coord(fminf(s.x, s.z), g.x0, g.inv_h, g.gx), bx = grid_cell_coord(fmaxf(s.x, s.z), g.x0, g.inv_h, g.gx);
+            const int ay = grid_cell_coord(fminf(s.y, s.w), g.y0, g.inv_h, g.gy), by = grid_cell_coord(fmaxf(s.y, s.w), g.y0, g.inv_h, g.gy);
+            for (int cy = ay; cy <= by; ++cy)
+                for (int cx = ax; cx <= bx; ++cx) {
+                    const int cell = cy * g.gx + cx;
+                    if (pass == 0) atomicAdd(&s_cnt[cell], 1);
+                    else {
+                        const int pos = atomicAdd(&s_cur[cell], 1);
+                        if (pos < 4 * L.S_pad) items[pos] = i;
+                    }
+                }
+        }
+        __syncthreads();
+        if (pass == 0) {
+            if (threadIdx.x == 0) {
+                int acc = 0;
+                for (int cidx = 0; cidx < ncell; ++cidx) { s_cur[cidx] = acc; cell_start[cidx] = acc; acc += s_cnt[cidx]; }
+                cell_start[ncell] = acc;
+                GridHeader out = g;
+                out.n_items = acc;
+                if (acc > 4 * L.S_pad) out.enabled = 0;  // cannot happen (<= 2 x 2 cells per segment); stay safe
+                *gh = out;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -265,8 +369,9 @@ struct CullCfg {
 // One thread per ball (G = 1) is compiled for 7 blocks per SM (72 registers): 131,072 balls, one
 // GPU's share of BASELINE configs[4], are then co-resident in ONE wave (with 96 registers the grid
 // needed two, the second one 38 % full).
-template <int G, bool STAGED>
-__global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED) ? 7 : 1) rollout_fwd_cull_kernel(const FwdParams p) {
+// GRID: dense scenes (>= 1,024 segments) refresh their lists through the scene's uniform grid.
+template <int G, bool STAGED, bool GRID>
+__global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED && !GRID) ? 7 : 1) rollout_fwd_cull_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int BPB = kFwdThreads / G;  // balls per block
     constexpr int LCAP = CullCfg<G>::LCAP;
@@ -329,6 +434,7 @@ __global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED) ? 7 : 1) rollo
     if (__all_sync(0xffffffffu, !sc.weird)) j0 = hint_by_estimate<G>(sc, x, y, lane);
     CullState cs;
     cs.cx = 0.f; cs.cy = 0.f; cs.rho2 = -1.0f; cs.cnt = 0; cs.far2 = 0.f;  // rho2 < 0: no list yet
+    const GridView grid = grid_view(p.scene_ws, L);
     const float rho_min = sc.scale * 0.001953125f, rho_max = sc.scale * 0.125f;
     const bool exact_idx = p.exact_idx != 0;
 
@@ -356,7 +462,7 @@ __global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED) ? 7 : 1) rollo
                 const float sx = px - x, sy = py - y;
                 const float dstep = sqrtf(sx * sx + sy * sy);  // displacement of this step
                 const float rho = fminf(fmaxf(1.25f * (float)kCullPeriod * dstep, rho_min), rho_max);
-                cull_refresh<G, LCAP>(sc, px, py, rho, c.r, lane, j0, list, kFwdThreads, cs);
+                cull_refresh<G, LCAP, GRID>(sc, grid, px, py, rho, c.r, lane, j0, list, kFwdThreads, cs);
             }
         }
         // narrow phase, estimates only: far from every wall -> no collision, nothing exact needed
@@ -418,7 +524,7 @@ __global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED) ? 7 : 1) rollo
 constexpr int kTpcListCap = 64;
 constexpr int kContactSteps = 16;  // sequential steps per round of a ball in contact mode
 
-template <int G>
+template <int G, bool GRID>
 __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int BPB = kFwdThreads / G;  // balls per block
@@ -468,6 +574,7 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
     GroupList gl;
     gl.e = lists + (size_t)slot * kTpcListCap; gl.cap = kTpcListCap; gl.cnt = 0;
     gl.cx = 0.f; gl.cy = 0.f; gl.rho2 = -1.0f; gl.far2 = 0.f;
+    const GridView grid = grid_view(p.scene_ws, L);
     const float rho_min = sc.scale * 0.001953125f, rho_max = sc.scale * 0.125f;
     int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
 
@@ -547,7 +654,7 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
                 if (want) j0 = glist_argmin(sc, x, y, gl, j0);
                 const float dstep = sqrtf(vx * vx + vy * vy) * c.dt;
                 const float rho = fminf(fmaxf(1.25f * (float)(kCullPeriod + 2 * G) * dstep, rho_min), rho_max);
-                glist_refresh<G>(sc, want ? x : 0.f, want ? y : 0.f, rho, c.r, lane, gbase, j0, want, gl);
+                glist_refresh<G, GRID>(sc, grid, want ? x : 0.f, want ? y : 0.f, rho, c.r, lane, gbase, j0, want, gl);
             }
         }
         // ---- (2) free flight: lane k keeps step t + k ---------------------------------------------------
@@ -1396,7 +1503,7 @@ int cull_lanes(const doper_rollout_desc* d) {
     if (d->per_env) return 4;  // read in place (see launch_fwd_cull); measured: C3 5.4 ms vs 8.2 ms staged with 8 lanes
     if (use_tpc(d)) return 16;
     int g = d->B < 32768 ? 4 : 1;
-    if (scene_layout(1, d->S).S_pad >= 2048 && g < 2) g = 2;
+    if (scene_layout(1, d->S).S_pad >= kGridMinSegments) g = 2;  // dense scene (grid refresh): measured best on C4
     if (!scene_fits_smem(d) && g < 8) g = 8;  // unstaged scene: split the refresh scan (L2 reads) over more lanes
     return g;
 }
@@ -1502,30 +1609,33 @@ int launch_fwd_cull(cudaStream_t st, FwdParams p, size_t scene_smem) {
     const size_t smem = (p.stage ? scene_smem : 0) + lists;
     const int bpb = kFwdThreads / G;
     const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
-    if (p.stage) {
+    const bool dense = !p.per_env && scene_layout(1, p.S).S_pad >= kGridMinSegments;
+    auto go = [&](auto kernel) {
         if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(rollout_fwd_cull_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess)
-            return DOPER_ERR_SMEM_LIMIT;
-        rollout_fwd_cull_kernel<G, true><<<grid, kFwdThreads, smem, st>>>(p);
-    } else {
-        rollout_fwd_cull_kernel<G, false><<<grid, kFwdThreads, smem, st>>>(p);
-    }
-    return launch_status();
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return (int)DOPER_ERR_SMEM_LIMIT;
+        kernel<<<grid, kFwdThreads, smem, st>>>(p);
+        return launch_status();
+    };
+    if (p.stage) return dense ? go(rollout_fwd_cull_kernel<G, true, true>) : go(rollout_fwd_cull_kernel<G, true, false>);
+    return dense ? go(rollout_fwd_cull_kernel<G, false, true>) : go(rollout_fwd_cull_kernel<G, false, false>);
 }
 
 template <int G>
 int launch_fwd_tpc(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
     const size_t smem = scene_smem + (size_t)(kFwdThreads / G) * kTpcListCap * sizeof(unsigned short);
     if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(rollout_fwd_tpc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
-        return DOPER_ERR_SMEM_LIMIT;
     const int bpb = kFwdThreads / G;
     const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
-    rollout_fwd_tpc_kernel<G><<<grid, kFwdThreads, smem, st>>>(p);
-    return launch_status();
+    const bool dense = !p.per_env && scene_layout(1, p.S).S_pad >= kGridMinSegments;
+    auto go = [&](auto kernel) {
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return (int)DOPER_ERR_SMEM_LIMIT;
+        kernel<<<grid, kFwdThreads, smem, st>>>(p);
+        return launch_status();
+    };
+    return dense ? go(rollout_fwd_tpc_kernel<G, true>) : go(rollout_fwd_tpc_kernel<G, false>);
 }
 
 template <int G>

@@ -27,6 +27,42 @@ struct SceneView {
     int weird;        // 1: scene has a degenerate / non-finite segment -> exact sweep only
 };
 
+// Uniform grid over a shared scene (built by scene_prepare_kernel): makes the candidate-list refresh
+// O(segments near the ball) instead of O(S).  The cell side is at least the largest segment extent,
+// so a segment's bounding box touches at most 2 x 2 cells; every segment is registered in every cell
+// its box overlaps.  A query for "all segments closer than R to c" visits the cells that the square
+// [c - R, c + R]^2 overlaps: a segment within R of c has a point of its box inside that square, and
+// the coordinate -> cell map is the same monotone function on both sides, so it is registered in a
+// visited cell (a superset is returned; duplicates across cells are dropped by the list builders).
+constexpr int kGridMaxCells = 4096;
+
+struct GridHeader {  // 32 B
+    float x0, y0, inv_h;
+    int gx, gy, enabled, n_items, pad;
+};
+
+struct GridView {
+    const int* cell_start;  // [gx * gy + 1]
+    const int* items;       // segment indices, cell-major
+    float x0, y0, inv_h;
+    int gx, gy, enabled;
+};
+
+__host__ __device__ __forceinline__ int grid_cell_coord(float v, float v0, float inv_h, int g) {
+    const float f = floorf((v - v0) * inv_h);
+    return f < 0.0f ? 0 : (f >= (float)g ? g - 1 : (int)f);  // NaN -> g - 1 branch is never taken: NaN < 0 false, >= false -> (int)NaN
+}
+
+// cells overlapped by the square of half side R around (cx, cy); false when the grid is off, the query
+// is not finite, or it covers so many cells that the plain scan is cheaper
+__device__ __forceinline__ bool grid_range(const GridView& g, float cx, float cy, float R, int& ix0, int& ix1,
+                                           int& iy0, int& iy1) {
+    if (!g.enabled || !(R < 1.0e30f) || !(fabsf(cx) < 1.0e30f) || !(fabsf(cy) < 1.0e30f)) return false;
+    ix0 = grid_cell_coord(cx - R, g.x0, g.inv_h, g.gx); ix1 = grid_cell_coord(cx + R, g.x0, g.inv_h, g.gx);
+    iy0 = grid_cell_coord(cy - R, g.y0, g.inv_h, g.gy); iy1 = grid_cell_coord(cy + R, g.y0, g.inv_h, g.gy);
+    return 2 * (ix1 - ix0 + 1) * (iy1 - iy0 + 1) <= g.gx * g.gy;
+}
+
 constexpr unsigned long long kNoKey = 0xffffffffffffffffull;
 
 // (distance, index) -> totally ordered key; NaN sorts first, then ascending distance, then index.
@@ -219,19 +255,41 @@ struct CullState {
 __device__ __forceinline__ float cull_far2(float radius, float M);
 
 // list entry k of this lane lives at list[k * stride]
-template <int G, int LCAP>
-__device__ __forceinline__ void cull_refresh(const SceneView& sc, float px, float py, float rho, float radius,
-                                             int lane, int j0, unsigned short* list, int stride, CullState& cs) {
+template <int G, int LCAP, bool GRID>
+__device__ __forceinline__ void cull_refresh(const SceneView& sc, const GridView& grid, float px, float py, float rho,
+                                             float radius, int lane, int j0, unsigned short* list, int stride,
+                                             CullState& cs) {
     const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)) + rho);
     const float e = sqrtf(approx_d2(px, py, sc.q[j0], sc.rl[j0])) * kCullUp;
     const float w = __fmaf_rn(kCullDeltaPerM, M, rho + rho);
     const float T = ((e + w) * (e + w)) * kCullUp;
     int cnt = 0;
-    for (int i = lane; i < sc.S_pad; i += G) {
-        const float a = approx_d2(px, py, sc.q[i], sc.rl[i]);
-        if (a <= T) {
-            if (cnt < LCAP) list[cnt * stride] = (unsigned short)i;
-            ++cnt;
+    int ix0, ix1, iy0, iy1;
+    // every kept segment is closer than (e + w) + 49 u M to the centre: the grid cells around it hold them all
+    if (GRID && grid_range(grid, px, py, __fmaf_rn(kCullSafePerM, M, e + w) * kCullUp, ix0, ix1, iy0, iy1)) {
+        for (int cy = iy0; cy <= iy1; ++cy) {
+            const int row = cy * grid.gx;
+            const int k1 = grid.cell_start[row + ix1 + 1];
+            for (int k = grid.cell_start[row + ix0]; k < k1; ++k) {  // the cells of one grid row are contiguous
+                const int i = grid.items[k];
+                if ((i & (G - 1)) != lane) continue;  // this lane owns the segments with i % G == lane
+                if (approx_d2(px, py, sc.q[i], sc.rl[i]) <= T) {
+                    bool dup = false;  // a segment is registered in up to four cells
+                    for (int m = 0; m < min(cnt, LCAP); ++m) dup = dup || list[m * stride] == (unsigned short)i;
+                    if (!dup) {
+                        if (cnt < LCAP) list[cnt * stride] = (unsigned short)i;
+                        ++cnt;
+                    }
+                }
+            }
+        }
+    } else {
+        for (int i = lane; i < sc.S_pad; i += G) {
+            const float a = approx_d2(px, py, sc.q[i], sc.rl[i]);
+            if (a <= T) {
+                if (cnt < LCAP) list[cnt * stride] = (unsigned short)i;
+                ++cnt;
+            }
         }
     }
     cs.cnt = cnt; cs.cx = px; cs.cy = py;
@@ -334,22 +392,56 @@ struct GroupList {
 // Every lane of the warp calls (warp-wide ballots); `doit` is uniform within a group.  Segment
 // i0 + lane of each stride-G slice is tested by lane `lane`; passing indices are appended in
 // ascending order (ballot + popc prefix inside the group).
-template <int G>
-__device__ __forceinline__ void glist_refresh(const SceneView& sc, float px, float py, float rho, float radius,
-                                              int lane, int gbase, int j0, bool doit, GroupList& gl) {
+template <int G, bool GRID>
+__device__ __forceinline__ void glist_refresh(const SceneView& sc, const GridView& grid, float px, float py, float rho,
+                                              float radius, int lane, int gbase, int j0, bool doit, GroupList& gl) {
     const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)) + rho);
     const float e = sqrtf(approx_d2(px, py, sc.q[j0], sc.rl[j0])) * kCullUp;
     const float w = __fmaf_rn(kCullDeltaPerM, M, rho + rho);
     const float T = ((e + w) * (e + w)) * kCullUp;
     const unsigned low = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
     int cnt = 0;
-    for (int i0 = 0; i0 < sc.S_pad; i0 += G) {
-        const int i = i0 + lane;
-        const bool pass = doit && approx_d2(px, py, sc.q[i], sc.rl[i]) <= T;
-        const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> gbase) & low;
-        const int pos = cnt + __popc(gb & ((1u << lane) - 1u));
-        if (pass && pos < gl.cap) gl.e[pos] = (unsigned short)i;
-        cnt += __popc(gb);
+    int ix0 = 0, ix1 = -1, iy0 = 0, iy1 = -1;
+    const bool by_grid = GRID && doit && grid_range(grid, px, py, __fmaf_rn(kCullSafePerM, M, e + w) * kCullUp, ix0, ix1, iy0, iy1);
+    if (GRID && __all_sync(0xffffffffu, by_grid || !doit)) {
+        // every refreshing group walks its own cells (row by row: the cells of a grid row are contiguous);
+        // the warp iterates until the longest walk is done (ballots need every lane)
+        int cy = iy0, k = 0, k1 = 0;
+        bool row_open = false;
+        while (true) {
+            if (doit && !row_open && cy <= iy1) {
+                k = grid.cell_start[cy * grid.gx + ix0]; k1 = grid.cell_start[cy * grid.gx + ix1 + 1];
+                row_open = true;
+            }
+            const bool busy = doit && row_open;
+            if (!__any_sync(0xffffffffu, busy)) break;
+            bool pass = false;
+            int i = 0;
+            if (busy && k + lane < k1) {
+                i = grid.items[k + lane];
+                pass = approx_d2(px, py, sc.q[i], sc.rl[i]) <= T;
+                if (pass)  // a segment is registered in up to four cells: drop what the list already holds
+                    for (int m = 0; m < min(cnt, gl.cap); ++m) pass = pass && gl.e[m] != (unsigned short)i;
+            }
+            const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> gbase) & low;
+            const int pos = cnt + __popc(gb & ((1u << lane) - 1u));
+            if (pass && pos < gl.cap) gl.e[pos] = (unsigned short)i;
+            cnt += __popc(gb);
+            __syncwarp();  // the next round's duplicate check reads what this round appended
+            if (busy) {
+                k += G;
+                if (k >= k1) { row_open = false; ++cy; }
+            }
+        }
+    } else {
+        for (int i0 = 0; i0 < sc.S_pad; i0 += G) {
+            const int i = i0 + lane;
+            const bool pass = doit && approx_d2(px, py, sc.q[i], sc.rl[i]) <= T;
+            const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> gbase) & low;
+            const int pos = cnt + __popc(gb & ((1u << lane) - 1u));
+            if (pass && pos < gl.cap) gl.e[pos] = (unsigned short)i;
+            cnt += __popc(gb);
+        }
     }
     __syncwarp();
     if (doit) {
