@@ -10,7 +10,10 @@ import ctypes
 from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libdoper_b200.so"
+import os
+
+# DOPER_B200_LIB points the binding at another build of the same library (kernel A/B tuning)
+LIB_PATH = Path(os.environ.get("DOPER_B200_LIB") or (Path(__file__).resolve().parent / "_lib" / "libdoper_b200.so"))
 
 ABI_VERSION = 1
 
