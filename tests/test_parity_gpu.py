@@ -288,6 +288,32 @@ def test_gradient_vs_torch_autograd(sim):
     assert abs(loss.item() - loss_ref) <= 1e-5 * abs(loss_ref)
 
 
+def test_cached_host_plan_path(sim, cref):
+    """Host arrays + a JaxScene object take the cached-plan path (what bench.py's e2e leg and a trainer
+    loop hit): repeated calls with new inputs, then new constants, must each match the oracle."""
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=300)
+    scene = geo.JaxScene(w["segments"])
+    n = 200
+    dt = np.float32((n / 1000) / n)
+    opts = _opts(ball_sim, sequential_backward=True)
+    rng = np.random.default_rng(3)
+    for trial in range(3):
+        consts = dict(w["constants"])
+        if trial == 2:
+            consts["walls_elasticity"] = 0.5  # a different plan key
+        v0 = (w["v0"] + rng.normal(0, 1, w["v0"].shape)).astype(np.float32)
+        (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, scene, w["x0"], v0, w["target"], w["attractor"],
+                                                              consts, opts)
+        ref = cref.value_and_grad(n, dt, onp.make_constants(consts), w["attractor"], w["target"], w["segments"],
+                                  w["x0"], v0)
+        assert isinstance(gv, np.ndarray)
+        assert_bitexact(xT, ref["x_T"], "x_T")
+        assert_bitexact(vT, ref["v_T"], "v_T")
+        assert_bitexact(gv, ref["grad_v0"], "dL/dv0")
+        assert abs(float(loss) - ref["loss_per_ball"].sum(dtype=np.float64)) <= 1e-5 * abs(float(loss))
+
+
 def test_device_inputs_stay_on_device(sim, cref):
     ball_sim, _ = sim
     w = syn.make_workload("c1")
