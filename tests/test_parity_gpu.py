@@ -502,3 +502,40 @@ def test_full_size_c2_properties(sim, cref):
                                                         w["constants"])
     assert_bitexact(xT3, xT)
     assert_bitexact(gv3, gv)
+
+
+@pytest.mark.parametrize("name,n_balls", [("c5", 131072), ("c3", 65536), ("c4", 16384)])
+def test_full_size_multi_gpu_configs_properties(sim, cref, name, n_balls):
+    """BASELINE configs[2], [3], [4] at one GPU's full size: size-independent properties (batch
+    independence, determinism, loss = sum of per-ball distances) on the full batch, and bit-exact parity
+    with the oracle on a slice (the oracle would take minutes on the full batch)."""
+    ball_sim, geo = sim
+    w = syn.make_workload(name, n_balls=n_balls)
+    n = w["n_steps"]
+    scene = geo.JaxScene(w["segments"])
+    args = (w["sim_time"], n, scene)
+    (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(*args, w["x0"], w["v0"], w["target"], w["attractor"],
+                                                          w["constants"])
+    assert np.isfinite(xT).all()
+    finite = np.isfinite(gv).all(1)
+    assert finite.mean() > 0.999  # a handful of balls overflow fp32 in the reference arithmetic too (App. D)
+    sl = slice(777, 777 + 96)
+    seg_sl = w["segments"][sl] if w["per_env"] else w["segments"]
+    scene_sl = geo.JaxScene(seg_sl)
+    (l2, (xT2, vT2)), gv2 = ball_sim.vmapped_grad_and_value(w["sim_time"], n, scene_sl, w["x0"][sl], w["v0"][sl],
+                                                           w["target"], w["attractor"], w["constants"])
+    assert_bitexact(xT2, xT[sl], "batch independence: x_T")
+    assert_bitexact(vT2, vT[sl], "batch independence: v_T")
+    c = onp.make_constants(w["constants"])
+    ref = cref.value_and_grad(n, np.float32(w["sim_time"] / n), c, w["attractor"], w["target"], seg_sl,
+                              w["x0"][sl], w["v0"][sl])
+    assert_bitexact(xT2, ref["x_T"], "slice vs oracle: x_T")
+    assert_bitexact(vT2, ref["v_T"], "slice vs oracle: v_T")
+    ok = np.isfinite(ref["grad_v0"]).all(1)
+    e = grad_rel_err(gv[sl][ok], ref["grad_v0"][ok])
+    assert np.quantile(e, 0.9) < 1e-4 and e.max() < 5e-2, (np.quantile(e, 0.9), e.max())
+    assert abs(float(loss) - np.abs(xT - w["target"]).sum(dtype=np.float64)) <= 1e-5 * float(loss)
+    (_, (xT3, _)), gv3 = ball_sim.vmapped_grad_and_value(*args, w["x0"], w["v0"], w["target"], w["attractor"],
+                                                        w["constants"])
+    assert_bitexact(xT3, xT, "determinism: x_T")
+    assert_bitexact(gv3[finite], gv[finite], "determinism: dL/dv0")
