@@ -218,13 +218,41 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const 
         v[0] = gg.x; v[1] = gg.y;
         if (p.vT_bar) { const float2 h = p.vT_bar[ball]; v[2] = h.x; v[3] = h.y; }
     }
-    for (int cc = n_ckpt - 1; cc >= 0; --cc) {
-        float o[4];
+    if (C_pad <= 32) {
+        for (int cc = n_ckpt - 1; cc >= 0; --cc) {
+            float o[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-            o[r] = (v[0] * g[0][r] + v[1] * g[1][r]) + (v[2] * g[2][r] + v[3] * g[3][r]);
+            for (int r = 0; r < 4; ++r)
+                o[r] = (v[0] * g[0][r] + v[1] * g[1][r]) + (v[2] * g[2][r] + v[3] * g[3][r]);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) v[r] = __shfl_sync(0xffffffffu, o[r], cc, C_pad);  // chunk cc's product
+            for (int r = 0; r < 4; ++r) v[r] = __shfl_sync(0xffffffffu, o[r], cc, C_pad);  // chunk cc's product
+        }
+    } else {
+        // a ball's chunks span C_pad / 32 warps: the warp holding the last chunks folds first and relays
+        // the cotangent to the next one through shared memory
+        __shared__ float relay[kBwdThreads / 64][4];
+        const int wpb_ball = C_pad / 32, wi = chunk >> 5;
+        for (int w = wpb_ball - 1; w >= 0; --w) {
+            if (wi == w) {
+                if (w != wpb_ball - 1) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) v[r] = relay[slot][r];
+                }
+                for (int cc = min(n_ckpt, 32 * (w + 1)) - 1; cc >= 32 * w; --cc) {
+                    float o[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        o[r] = (v[0] * g[0][r] + v[1] * g[1][r]) + (v[2] * g[2][r] + v[3] * g[3][r]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) v[r] = __shfl_sync(0xffffffffu, o[r], cc & 31);
+                }
+                if ((chunk & 31) == 0) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) relay[slot][r] = v[r];
+                }
+            }
+            __syncthreads();
+        }
     }
     if (ball < p.B && chunk == 0) {
         p.v0_bar[ball] = make_float2(v[2], v[3]);

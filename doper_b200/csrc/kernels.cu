@@ -72,7 +72,10 @@ bool chunked_eligible(const doper_rollout_desc* d) {
 int resolve_K(const doper_rollout_desc* d) {
     if (d->ckpt_every > 0) return d->ckpt_every;
     if (chunked_eligible(d)) {
-        const int K = (d->n_steps + 31) / 32;
+        // 32 chunks per ball (one warp); small batches with long rollouts take 64 (two warps): more threads
+        // in flight, and the slowest thread — a chunk where the ball collides step after step — is half as long
+        const int n_chunks = (d->B <= 4096 && d->n_steps >= 256) ? 64 : 32;
+        const int K = (d->n_steps + n_chunks - 1) / n_chunks;
         if (K <= kChunkedMaxK) return K < 4 ? 4 : K;
     }
     return 16;  // sequential backward: 32 KB of stash per 128-thread block -> 7 blocks per SM
@@ -170,7 +173,7 @@ int tp_warps_per_block(const doper_rollout_desc* d) {
 
 bool use_chunked(const doper_rollout_desc* d, int K) {
     const int n_ckpt = (d->n_steps + K - 1) / K;
-    return chunked_eligible(d) && n_ckpt <= 32 && n_ckpt >= 2 && K <= kChunkedMaxK;
+    return chunked_eligible(d) && n_ckpt <= 128 && n_ckpt >= 2 && K <= kChunkedMaxK;
 }
 
 int validate_desc(const doper_rollout_desc* d) {

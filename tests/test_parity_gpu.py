@@ -288,6 +288,28 @@ def test_gradient_vs_torch_autograd(sim):
     assert abs(loss.item() - loss_ref) <= 1e-5 * abs(loss_ref)
 
 
+@pytest.mark.parametrize("n_balls,n_steps", [(1, 1), (3, 2), (5, 17), (2, 33), (70000, 3)])
+def test_tiny_rollouts_default_plan(sim, cref, n_balls, n_steps):
+    """Edge shapes: fewer steps than lanes per ball, a single ball, a single step, many balls x few steps."""
+    ball_sim, _ = sim
+    w = syn.make_workload("c2", n_balls=n_balls)
+    c = onp.make_constants(w["constants"])
+    dt = np.float32((n_steps / 1000) / n_steps)
+    ref = cref.value_and_grad(n_steps, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+    h = ball_sim.rollout_history(n_steps / 1000, n_steps, w["segments"], w["x0"], w["v0"], w["attractor"],
+                                 w["constants"], _opts(ball_sim, exact_index_log=True), want_trajectory=True)
+    assert np.array_equal(h["idx"], ref["idx"]) and np.array_equal(h["hit"], ref["hit"])
+    assert_bitexact(h["x_T"], ref["x_T"])
+    (_, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n_steps / 1000, n_steps, w["segments"], w["x0"], w["v0"],
+                                                       w["target"], w["attractor"], w["constants"],
+                                                       _opts(ball_sim, sequential_backward=True))
+    assert_bitexact(vT, ref["v_T"])
+    assert_bitexact(gv, ref["grad_v0"])
+    (_, _), gv2 = ball_sim.vmapped_grad_and_value(n_steps / 1000, n_steps, w["segments"], w["x0"], w["v0"], w["target"],
+                                                 w["attractor"], w["constants"])
+    assert grad_rel_err(gv2, ref["grad_v0"]).max() < 1e-4
+
+
 def test_cached_host_plan_path(sim, cref):
     """Host arrays + a JaxScene object take the cached-plan path (what bench.py's e2e leg and a trainer
     loop hit): repeated calls with new inputs, then new constants, must each match the oracle."""
