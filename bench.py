@@ -380,7 +380,8 @@ def ours(args):
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 4 * B * 4,
                     "d2h_bytes_per_step": (4 + 6 * B) * 4, "ms_per_step": round(float(e2e_ms.item()), 5),
                     "api": "doper_b200.sim.ball_sim.vmapped_grad_and_value(host numpy arrays)"},
-            "gpu_launches": 3 * K,
+            # forward, loss, backward (+ the chunk-parallel pass of the hybrid backward on large batches)
+            "gpu_launches": (3 + lib.doper_rollout_plan_name(dref, 1).decode().count("+")) * K,
             "wall_ms_timed_region": round(wall_ms, 3),
             "roofline": roof,
         }

@@ -441,7 +441,11 @@ int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
 
 const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward) {
     if (validate_desc(d) != DOPER_OK) return "invalid";
-    if (backward) return use_chunked(d, resolve_K(d)) ? "rollout_bwd_chunked_kernel" : "rollout_bwd_kernel";
+    if (backward) {
+        if (use_chunked(d, resolve_K(d))) return "rollout_bwd_chunked_kernel";
+        const bool hybrid = !(d->flags & (1 << 19)) && !(d->flags & 2) && d->n_steps >= 256;
+        return hybrid ? "rollout_bwd_kernel+rollout_bwd_chunked_kernel" : "rollout_bwd_kernel";
+    }
     const int G = auto_lanes(d);
     static const char* const tpc[] = {"rollout_fwd_tpc_kernel<2>", "rollout_fwd_tpc_kernel<4>", "rollout_fwd_tpc_kernel<8>",
                                       "rollout_fwd_tpc_kernel<16>", "rollout_fwd_tpc_kernel<32>"};
