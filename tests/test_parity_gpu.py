@@ -310,6 +310,32 @@ def test_tiny_rollouts_default_plan(sim, cref, n_balls, n_steps):
     assert grad_rel_err(gv2, ref["grad_v0"]).max() < 1e-4
 
 
+@pytest.mark.parametrize("n_balls", [300, 9000, 40000])
+@pytest.mark.parametrize("scale,offset", [(1e-2, 0.0), (1e2, 0.0), (1e4, 0.0), (1.0, 3.0e4), (1.0, -2.0e6)])
+def test_broad_phase_margins_across_magnitudes(sim, cref, n_balls, scale, offset):
+    """The broad-phase and far-from-walls margins are multiples of u * M (M = largest coordinate): scenes
+    shrunk / blown up by 1e-2 .. 1e4, and scenes translated far from the origin (where fp32 spacing is
+    coarse and estimates are poor), must still give the oracle's bits on every plan branch."""
+    ball_sim, _ = sim
+    w = syn.make_workload("c2", n_balls=n_balls)
+    n = 120
+    segs = (w["segments"] * np.float32(scale) + np.float32(offset)).astype(np.float32)
+    x0 = (w["x0"] * np.float32(scale) + np.float32(offset)).astype(np.float32)
+    v0 = (w["v0"] * np.float32(scale)).astype(np.float32)
+    A = (w["attractor"] * np.float32(scale) + np.float32(offset)).astype(np.float32)
+    consts = dict(w["constants"]); consts["radius"] = 0.1 * scale
+    consts["volume"] = 4 * np.pi * consts["radius"] ** 3 / 3; consts["mass"] = consts["volume"] * consts["density"]
+    c = onp.make_constants(consts)
+    ref = cref.rollout_fwd(n, np.float32((n / 1000) / n), c, A, segs, x0, v0, want_traj=True)
+    got = ball_sim.rollout_history(n / 1000, n, segs, x0, v0, A, consts, _opts(ball_sim, exact_index_log=True),
+                                   want_trajectory=True)
+    assert np.array_equal(got["hit"], ref["hit"]) and np.array_equal(got["idx"], ref["idx"])
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    assert_bitexact(got["trajectory"].velocity, ref["traj_v"], "trajectory v")
+    if offset == 0.0:
+        assert ref["hit"].sum() > 0
+
+
 def test_cached_host_plan_path(sim, cref):
     """Host arrays + a JaxScene object take the cached-plan path (what bench.py's e2e leg and a trainer
     loop hit): repeated calls with new inputs, then new constants, must each match the oracle."""
