@@ -180,6 +180,9 @@ int validate_desc(const doper_rollout_desc* d) {
     if (!d) return DOPER_ERR_NULL_PTR;
     if (d->B <= 0 || d->S <= 0 || d->n_steps < 0 || d->ckpt_every < 0) return DOPER_ERR_BAD_SHAPE;
     if (d->ckpt_every > 1024) return DOPER_ERR_BAD_SHAPE;
+    // candidate lists hold 16-bit segment indices, the hit log 29-bit ones: 65,504 segments per scene is the
+    // limit of the rollout kernels (the largest BASELINE scene has 10,002)
+    if (d->S > 65504) return DOPER_ERR_UNSUPPORTED;
     const int g = d->lanes_per_ball;
     if (!(g == 0 || g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32)) return DOPER_ERR_BAD_SHAPE;
     return DOPER_OK;

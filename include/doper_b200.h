@@ -127,7 +127,7 @@ int doper_agent_observations(doper_stream_t stream, int64_t N, int32_t R, int32_
 
 typedef struct {
     int64_t B;           /* balls (= environments when per_env) */
-    int32_t S;           /* segments per scene */
+    int32_t S;           /* segments per scene (<= 65,504: DOPER_ERR_UNSUPPORTED beyond) */
     int32_t per_env;     /* 0: one shared scene; 1: scene b belongs to ball b */
     int32_t n_steps;     /* rollout length */
     int32_t ckpt_every;  /* K: checkpoint period in steps (>= 1); 0 = library default */

@@ -56,6 +56,11 @@ def test_argument_validation_happens_before_any_launch():
     d.B = 4
     assert L.doper_rollout_fwd(None, ctypes.byref(d), None, 8, 8, 8, 8, None, None, None, None) == 2
     assert L.doper_rollout_fwd(None, ctypes.byref(d), 256, 4, 8, 8, 8, None, None, None, None) == 3
+    d.S = 70000  # beyond the 16-bit candidate-list indices
+    assert L.doper_rollout_fwd(None, ctypes.byref(d), 256, 8, 8, 8, 8, None, None, None, None) == 7
+    assert L.doper_rollout_workspace_bytes(ctypes.byref(d)) == 0
+    assert L.doper_range_sensor(None, 4, 0, 201, 8, 8, 256, 1000.0, 8, None, None) == 1   # R <= 0
+    assert L.doper_ray_segment_points(None, 4, 201, 8, 8, 16, 4) == 3                      # points % 8
 
 
 def test_mirror_keeps_reference_signatures():
