@@ -218,6 +218,19 @@ def ours(args):
     # the one exchange step of a data-parallel trainer: controller grads (6,602 fp32,
     # reference controllers.py:12-18) + the scalar loss, summed over ranks
     ar_buf = torch.zeros(6602 + 1, dtype=torch.float32, device=device)
+    peer = None
+    if world > 1 and not args.nccl:
+        from doper_b200.distributed import PeerAllReducer
+        peer = PeerAllReducer(6602 + 1, device)  # one-shot all-reduce over NVLink peer memory (csrc/peer.cuh)
+
+    def exchange():
+        # the optimiser step needs the reduced gradient: the exchange is on the step's critical path
+        ar_buf[6602:].copy_(loss_sum, non_blocking=True)
+        if peer is not None:
+            peer.slot().copy_(ar_buf, non_blocking=True)
+            peer.all_reduce()
+        else:
+            dist.all_reduce(ar_buf)
 
     def fwd():
         check(lib.doper_rollout_fwd(st, dref, ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT), 0, 0, 0,
@@ -253,9 +266,8 @@ def ours(args):
         fwd()
         ev[k][1].record()
         loss_bwd()
-        if world > 1 and not os.environ.get("DOPER_BENCH_NO_ALLREDUCE"):
-            ar_buf[6602:].copy_(loss_sum, non_blocking=True)
-            dist.all_reduce(ar_buf)  # the optimiser step needs the reduced gradient: on the critical path
+        if world > 1:
+            exchange()
         ev[k][2].record()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
@@ -282,6 +294,8 @@ def ours(args):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         (l_e2e, (xT_e2e, _)), gv_e2e = ball_sim.vmapped_grad_and_value(*api_args)
+        if world > 1:
+            exchange()  # the same per-step exchange as in the device-timed loop
     torch.cuda.synchronize()
     e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=device)
     if world > 1:
@@ -369,7 +383,8 @@ def ours(args):
                        ((f" per GPU ({world} GPUs, every rank runs the workload's own seeded batch, "
                          if replicated else
                          f" per GPU ({world} GPUs, a globally seeded batch of {total} balls sliced by rank, ") +
-                        "allreduce of 6,603 fp32 per step)" if world > 1 else ""),
+                        ("one-shot NVLink peer-memory all-reduce" if peer is not None else "NCCL all-reduce") +
+                        " of 6,603 fp32 per step)" if world > 1 else ""),
                        "shards": ("n/a" if world == 1 else ("replicated seeded batch" if replicated else "sliced global batch")),
                        "ms_per_step_fastest_rank": round(ms_per_step_fastest_rank, 5),
                        "l2": "256 MiB buffer rewritten between timed iterations (flush), outside the event pairs",
@@ -389,6 +404,8 @@ def ours(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 
@@ -437,6 +454,7 @@ def main():
     ap.add_argument("--full-sweep", action="store_true",
                     help="forbid the broad-phase kernels: every (ball, segment) pair is evaluated every step")
     ap.add_argument("--strong", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: exchange through NCCL instead of the peer-memory kernel")
     ap.add_argument("--distinct-shards", action="store_true",
                     help="N > 1: slice one globally seeded batch instead of running the workload's batch on every rank")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -12,8 +12,10 @@
 //   bwd.cuh        rollout_bwd_kernel (sequential, bit-exact), rollout_bwd_chunked_kernel
 //   queries.cuh    l1_loss_kernel, closest_segment_kernel, points_inside_kernel, fp32_probe_kernel
 //   sensor.cuh     range-sensor ray casting
+//   peer.cuh       one-shot all-reduce of the policy gradient over NVLink peer memory
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/doper_b200.h"
 #include "physics.cuh"
@@ -25,6 +27,7 @@
 #include "queries.cuh"
 
 #include "sensor.cuh"
+#include "peer.cuh"
 
 // ==========================================================================================
 // C ABI
@@ -640,6 +643,55 @@ int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, con
     rc = doper_l1_loss(stream, d->B, xT, target, loss_per_ball, loss_sum, scratch);
     if (rc) return rc;
     return doper_rollout_bwd(stream, d, scene_ws, ws, scratch, nullptr, x0_bar, v0_bar);
+}
+
+size_t doper_peer_buffer_bytes(int32_t n) { return n > 0 ? peer_buffer_bytes(n) : 0; }
+
+int doper_peer_alloc(int32_t n, void** buffer, unsigned char handle[64]) {
+    if (n <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (!buffer || !handle) return DOPER_ERR_NULL_PTR;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    void* p = nullptr;
+    if (cudaMalloc(&p, peer_buffer_bytes(n)) != cudaSuccess) return DOPER_ERR_WORKSPACE;
+    if (cudaMemset(p, 0, peer_buffer_bytes(n)) != cudaSuccess) { cudaFree(p); return DOPER_ERR_LAUNCH; }
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); return DOPER_ERR_UNSUPPORTED; }
+    memcpy(handle, &h, 64);
+    *buffer = p;
+    return DOPER_OK;
+}
+
+int doper_peer_open(const unsigned char handle[64], void** buffer) {
+    if (!handle || !buffer) return DOPER_ERR_NULL_PTR;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return DOPER_ERR_UNSUPPORTED;
+    *buffer = p;
+    return DOPER_OK;
+}
+
+int doper_peer_close(void* buffer) { return cudaIpcCloseMemHandle(buffer) == cudaSuccess ? DOPER_OK : DOPER_ERR_LAUNCH; }
+
+int doper_peer_free(void* buffer) { return cudaFree(buffer) == cudaSuccess ? DOPER_OK : DOPER_ERR_LAUNCH; }
+
+void* doper_peer_slot(void* buffer, int32_t n, uint32_t seq) {
+    if (!buffer || n <= 0) return nullptr;
+    const size_t n_pad = ((size_t)n + 63) / 64 * 64;
+    return reinterpret_cast<unsigned char*>(buffer) + kPeerFlagBytes + (size_t)(seq & 1u) * n_pad * sizeof(float);
+}
+
+int doper_allreduce_oneshot(doper_stream_t stream, int32_t rank, int32_t world, void* const* buffers, int32_t n,
+                            uint32_t seq, float* out, int32_t* status) {
+    if (world < 1 || world > kPeerMaxRanks || rank < 0 || rank >= world || n <= 0 || seq == 0) return DOPER_ERR_BAD_SHAPE;
+    if (!buffers || !out) return DOPER_ERR_NULL_PTR;
+    PeerPtrs P;
+    for (int r = 0; r < kPeerMaxRanks; ++r) P.base[r] = r < world ? reinterpret_cast<unsigned char*>(buffers[r]) : nullptr;
+    for (int r = 0; r < world; ++r)
+        if (!P.base[r]) return DOPER_ERR_NULL_PTR;
+    const int blocks = (n + 4 * kPeerThreads - 1) / (4 * kPeerThreads);
+    allreduce_oneshot_kernel<<<blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(P, rank, world, n, seq, out, status);
+    return launch_status();
 }
 
 int doper_fp32_probe(doper_stream_t stream, int32_t blocks, int32_t threads, int32_t iters,

@@ -44,13 +44,21 @@ def ball_shard(n_total: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class PolicyGradReducer:
-    """All-reduce(sum) of the controller gradients and the scalar loss in ONE flat buffer."""
+    """All-reduce(sum) of the controller gradients and the scalar loss in ONE flat buffer.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], device: torch.device = None):
+    ``transport``: "nvlink" = the one-shot peer-memory kernel (``PeerAllReducer``; CUDA, one node),
+    "collective" = ``torch.distributed.all_reduce`` (NCCL on GPUs, gloo in the CPU tests), "auto" =
+    nvlink when the parameters are on CUDA and a multi-rank group is initialised, else collective."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], device: torch.device = None, transport: str = "auto"):
         self.params: List[torch.nn.Parameter] = [p for p in params]
         self.numel = sum(p.numel() for p in self.params)
         device = device or (self.params[0].device if self.params else torch.device("cpu"))
         self.buf = torch.zeros(self.numel + 1, dtype=torch.float32, device=device)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if transport == "auto":
+            transport = "nvlink" if (multi and torch.device(device).type == "cuda") else "collective"
+        self.peer = PeerAllReducer(self.numel + 1, torch.device(device)) if (transport == "nvlink" and multi) else None
 
     @torch.no_grad()
     def reduce(self, local_loss) -> torch.Tensor:
@@ -64,7 +72,10 @@ class PolicyGradReducer:
                 self.buf[o:o + n].copy_(p.grad.reshape(-1))
             o += n
         self.buf[o] = float(local_loss) if not isinstance(local_loss, torch.Tensor) else local_loss.to(self.buf.device)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if self.peer is not None:
+            self.peer.slot().copy_(self.buf)
+            self.buf.copy_(self.peer.all_reduce())
+        elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
         o = 0
         for p in self.params:
@@ -75,3 +86,79 @@ class PolicyGradReducer:
                 p.grad.copy_(self.buf[o:o + n].reshape(p.shape))
             o += n
         return self.buf[o].clone()
+
+
+class PeerAllReducer:
+    """One-shot all-reduce(sum) of a small fp32 vector over NVLink peer memory (csrc/peer.cuh):
+    every rank's buffer is mapped into every other rank through CUDA IPC once, and each call is ONE
+    1,024-thread kernel per rank (publish a flag, wait for the peers' flags, sum everybody's slot in
+    rank order).  For the trainer's 26 KB exchange this replaces a NCCL all-reduce whose latency
+    (about 20 us at 2 GPUs, 80 us at 8) is a visible part of a 0.4 ms step.  Needs one process per GPU
+    on ONE node and an initialised ``torch.distributed`` group (used once, to exchange the handles).
+    """
+
+    def __init__(self, numel: int, device: torch.device):
+        import ctypes
+
+        from ._abi import check, lib
+        self._lib, self._check, self._ct = lib, check, ctypes
+        self.n = int(numel)
+        self.device = device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if self.world > 16:
+            raise ValueError("PeerAllReducer: at most 16 ranks")
+        torch.cuda.set_device(device)
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        check(lib.doper_peer_alloc(self.n, ctypes.byref(own), handle), "doper_peer_alloc")
+        self._own = own.value
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine)
+        self._ptrs = (ctypes.c_void_p * self.world)()
+        self._opened = []
+        for r, h in enumerate(gathered):
+            if r == self.rank:
+                self._ptrs[r] = self._own
+                continue
+            p = ctypes.c_void_p()
+            check(lib.doper_peer_open(bytes(h.cpu().tolist()), ctypes.byref(p)), "doper_peer_open")
+            self._ptrs[r] = p.value
+            self._opened.append(p.value)
+        self.seq = 0
+        self.out = torch.empty(self.n, dtype=torch.float32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self._slots = [self._slot_tensor(s) for s in (2, 1)]  # index by seq & 1: seq 2 -> slot 0, seq 1 -> slot 1
+        dist.barrier(device_ids=[device.index])  # every peer mapping exists before the first kernel
+
+    def _slot_tensor(self, seq: int) -> torch.Tensor:
+        addr = self._lib.doper_peer_slot(self._own, self.n, seq)
+
+        class _Mem:  # zero-copy torch view of the cudaMalloc'ed slot
+            __cuda_array_interface__ = {"shape": (self.n,), "typestr": "<f4", "data": (int(addr), False), "version": 3}
+
+        return torch.as_tensor(_Mem(), device=self.device)
+
+    def slot(self) -> torch.Tensor:
+        """The buffer to fill (on the current stream) for the NEXT ``all_reduce`` call."""
+        return self._slots[(self.seq + 1) & 1]
+
+    def all_reduce(self) -> torch.Tensor:
+        """Sum over ranks of what every rank wrote into ``slot()``; returns ``self.out`` (overwritten by
+        the next call).  Enqueued on the current stream; no host synchronisation."""
+        self.seq += 1
+        self._check(self._lib.doper_allreduce_oneshot(torch.cuda.current_stream().cuda_stream, self.rank, self.world,
+                                                      self._ptrs, self.n, self.seq, self.out.data_ptr(),
+                                                      self.status.data_ptr()), "doper_allreduce_oneshot")
+        return self.out
+
+    def close(self) -> None:
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(device_ids=[self.device.index])  # nobody unmaps while a peer may still read
+        for p in self._opened:
+            self._lib.doper_peer_close(p)
+        self._opened = []
+        if self._own:
+            self._lib.doper_peer_free(self._own)
+            self._own = None

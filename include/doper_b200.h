@@ -6,7 +6,8 @@
  * `extern "C"`, takes plain device pointers, sizes and a CUDA stream, returns an
  * int status (0 = ok), never aborts, never synchronises, allocates nothing and
  * keeps no global mutable state: the caller owns every buffer including the
- * workspaces whose sizes the *_bytes() queries return.  All launches go to the
+ * workspaces whose sizes the *_bytes() queries return (one explicit exception:
+ * doper_peer_alloc, because CUDA IPC needs memory from cudaMalloc).  All launches go to the
  * caller's stream; the library is re-entrant (one host thread per GPU is safe).
  *
  * Reference interfaces replaced (file:line in the reference tree):
@@ -191,6 +192,27 @@ int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, con
                          const float* x0, const float* v0, const float target[2], void* ws,
                          float* scratch, float* loss_sum, float* loss_per_ball, float* xT,
                          float* vT, float* v0_bar, float* x0_bar);
+
+/* ---- multi-GPU exchange --------------------------------------- */
+
+/* One-shot all-reduce(sum) of n floats over NVLink peer memory, for the one exchange of the data-parallel
+ * trainer (controller gradients + loss, 26 KB: latency bound).  Every rank (one process per GPU) calls
+ * doper_peer_alloc once (the only allocation the library ever makes: an explicit, caller-owned buffer
+ * that must be cudaMalloc'ed for CUDA IPC), exchanges the 64-byte handles with its peers by any host
+ * channel (the Python binding uses torch.distributed), and opens theirs with doper_peer_open.  Per step:
+ * write the n floats into doper_peer_slot(own buffer, n, seq) on `stream`, then call
+ * doper_allreduce_oneshot with the same seq = 1, 2, 3, ... on every rank: out[i] = sum over ranks in rank
+ * order (the same bits everywhere).  `buffers` is a HOST array of `world` device pointers indexed by
+ * rank (own buffer at [rank]).  A peer that never arrives makes the kernel give up after about two
+ * seconds and set *status (device int, nullable) to 1 instead of spinning for ever. */
+size_t doper_peer_buffer_bytes(int32_t n);
+int doper_peer_alloc(int32_t n, void** buffer, unsigned char handle[64]);
+int doper_peer_open(const unsigned char handle[64], void** buffer);
+int doper_peer_close(void* buffer);
+int doper_peer_free(void* buffer);
+void* doper_peer_slot(void* buffer, int32_t n, uint32_t seq);
+int doper_allreduce_oneshot(doper_stream_t stream, int32_t rank, int32_t world, void* const* buffers, int32_t n,
+                            uint32_t seq, float* out, int32_t* status);
 
 /* ---- measurement helper --------------------------------------------------------------- */
 
