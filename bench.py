@@ -227,8 +227,7 @@ def ours(args):
         # the optimiser step needs the reduced gradient: the exchange is on the step's critical path
         ar_buf[6602:].copy_(loss_sum, non_blocking=True)
         if peer is not None:
-            peer.slot().copy_(ar_buf, non_blocking=True)
-            peer.all_reduce()
+            peer.all_reduce(ar_buf, out=ar_buf)
         else:
             dist.all_reduce(ar_buf)
 

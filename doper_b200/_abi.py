@@ -25,7 +25,7 @@ EXPORTS = (
     "doper_fp32_probe",
     "doper_ray_segment_points", "doper_range_sensor", "doper_agent_observations",
     "doper_peer_buffer_bytes", "doper_peer_alloc", "doper_peer_open", "doper_peer_close", "doper_peer_free",
-    "doper_peer_slot", "doper_allreduce_oneshot",
+    "doper_allreduce_oneshot",
 )
 
 
@@ -98,11 +98,9 @@ def _load() -> ctypes.CDLL:
     lib.doper_peer_open.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
     lib.doper_peer_close.argtypes = [c_void_p]
     lib.doper_peer_free.argtypes = [c_void_p]
-    lib.doper_peer_slot.restype = c_void_p
-    lib.doper_peer_slot.argtypes = [c_void_p, c_int32, ctypes.c_uint32]
-    lib.doper_allreduce_oneshot.argtypes = [vp, c_int32, c_int32, POINTER(c_void_p), c_int32, ctypes.c_uint32, fp, vp]
+    lib.doper_allreduce_oneshot.argtypes = [vp, c_int32, c_int32, POINTER(c_void_p), c_int32, fp, fp, vp]
     for name in EXPORTS:
-        if name not in ("doper_peer_buffer_bytes", "doper_peer_slot","doper_error_string", "doper_scene_workspace_bytes",
+        if name not in ("doper_peer_buffer_bytes", "doper_error_string", "doper_scene_workspace_bytes",
                         "doper_rollout_workspace_bytes", "doper_abi_version", "doper_rollout_ckpt_every",
                         "doper_rollout_log_ball_major", "doper_rollout_plan_name"):
             getattr(lib, name).restype = ctypes.c_int

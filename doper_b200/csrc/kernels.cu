@@ -675,22 +675,16 @@ int doper_peer_close(void* buffer) { return cudaIpcCloseMemHandle(buffer) == cud
 
 int doper_peer_free(void* buffer) { return cudaFree(buffer) == cudaSuccess ? DOPER_OK : DOPER_ERR_LAUNCH; }
 
-void* doper_peer_slot(void* buffer, int32_t n, uint32_t seq) {
-    if (!buffer || n <= 0) return nullptr;
-    const size_t n_pad = ((size_t)n + 63) / 64 * 64;
-    return reinterpret_cast<unsigned char*>(buffer) + kPeerFlagBytes + (size_t)(seq & 1u) * n_pad * sizeof(float);
-}
-
 int doper_allreduce_oneshot(doper_stream_t stream, int32_t rank, int32_t world, void* const* buffers, int32_t n,
-                            uint32_t seq, float* out, int32_t* status) {
-    if (world < 1 || world > kPeerMaxRanks || rank < 0 || rank >= world || n <= 0 || seq == 0) return DOPER_ERR_BAD_SHAPE;
-    if (!buffers || !out) return DOPER_ERR_NULL_PTR;
+                            const float* in, float* out, int32_t* status) {
+    if (world < 1 || world > kPeerMaxRanks || rank < 0 || rank >= world || n <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (!buffers || !in || !out) return DOPER_ERR_NULL_PTR;
     PeerPtrs P;
     for (int r = 0; r < kPeerMaxRanks; ++r) P.base[r] = r < world ? reinterpret_cast<unsigned char*>(buffers[r]) : nullptr;
     for (int r = 0; r < world; ++r)
         if (!P.base[r]) return DOPER_ERR_NULL_PTR;
-    const int blocks = (n + 4 * kPeerThreads - 1) / (4 * kPeerThreads);
-    allreduce_oneshot_kernel<<<blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(P, rank, world, n, seq, out, status);
+    const int blocks = (int)((peer_n4(n) + kPeerThreads - 1) / kPeerThreads);
+    allreduce_oneshot_kernel<<<blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(P, rank, world, n, in, out, status);
     return launch_status();
 }
 

@@ -73,8 +73,7 @@ class PolicyGradReducer:
             o += n
         self.buf[o] = float(local_loss) if not isinstance(local_loss, torch.Tensor) else local_loss.to(self.buf.device)
         if self.peer is not None:
-            self.peer.slot().copy_(self.buf)
-            self.buf.copy_(self.peer.all_reduce())
+            self.peer.all_reduce(self.buf, out=self.buf)
         elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
         o = 0
@@ -91,10 +90,12 @@ class PolicyGradReducer:
 class PeerAllReducer:
     """One-shot all-reduce(sum) of a small fp32 vector over NVLink peer memory (csrc/peer.cuh):
     every rank's buffer is mapped into every other rank through CUDA IPC once, and each call is ONE
-    1,024-thread kernel per rank (publish a flag, wait for the peers' flags, sum everybody's slot in
-    rank order).  For the trainer's 26 KB exchange this replaces a NCCL all-reduce whose latency
-    (about 20 us at 2 GPUs, 80 us at 8) is a visible part of a 0.4 ms step.  Needs one process per GPU
-    on ONE node and an initialised ``torch.distributed`` group (used once, to exchange the handles).
+    small kernel per rank (push the input into every peer with the step number inside each 16-byte
+    store, poll the own buffer for the peers' words, sum in rank order).  For the trainer's 26 KB
+    exchange this replaces a NCCL all-reduce whose latency (25 us at 2 GPUs, 31 us at 8) is a visible
+    part of a 0.4 ms step.  The step counter lives on the device, so ``all_reduce`` can be captured in
+    a CUDA graph.  Needs one process per GPU on ONE node and an initialised ``torch.distributed``
+    group (used once, to exchange the handles).
     """
 
     def __init__(self, numel: int, device: torch.device):
@@ -125,32 +126,23 @@ class PeerAllReducer:
             check(lib.doper_peer_open(bytes(h.cpu().tolist()), ctypes.byref(p)), "doper_peer_open")
             self._ptrs[r] = p.value
             self._opened.append(p.value)
-        self.seq = 0
         self.out = torch.empty(self.n, dtype=torch.float32, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
-        self._slots = [self._slot_tensor(s) for s in (2, 1)]  # index by seq & 1: seq 2 -> slot 0, seq 1 -> slot 1
         dist.barrier(device_ids=[device.index])  # every peer mapping exists before the first kernel
 
-    def _slot_tensor(self, seq: int) -> torch.Tensor:
-        addr = self._lib.doper_peer_slot(self._own, self.n, seq)
-
-        class _Mem:  # zero-copy torch view of the cudaMalloc'ed slot
-            __cuda_array_interface__ = {"shape": (self.n,), "typestr": "<f4", "data": (int(addr), False), "version": 3}
-
-        return torch.as_tensor(_Mem(), device=self.device)
-
-    def slot(self) -> torch.Tensor:
-        """The buffer to fill (on the current stream) for the NEXT ``all_reduce`` call."""
-        return self._slots[(self.seq + 1) & 1]
-
-    def all_reduce(self) -> torch.Tensor:
-        """Sum over ranks of what every rank wrote into ``slot()``; returns ``self.out`` (overwritten by
-        the next call).  Enqueued on the current stream; no host synchronisation."""
-        self.seq += 1
+    def all_reduce(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """Sum over ranks of ``x`` (fp32, ``numel`` elements, contiguous, on this device) -> ``out``
+        (default ``self.out``, overwritten by the next call; ``out`` may be ``x``).  Enqueued on the
+        current stream; no host synchronisation; every rank must make the same sequence of calls."""
+        out = self.out if out is None else out
+        if x.dtype != torch.float32 or x.numel() != self.n or not x.is_contiguous() or x.device != self.out.device:
+            raise ValueError("PeerAllReducer.all_reduce: x must be a contiguous fp32 tensor of numel elements on the device")
+        if out.dtype != torch.float32 or out.numel() != self.n or not out.is_contiguous() or out.device != self.out.device:
+            raise ValueError("PeerAllReducer.all_reduce: bad out tensor")
         self._check(self._lib.doper_allreduce_oneshot(torch.cuda.current_stream().cuda_stream, self.rank, self.world,
-                                                      self._ptrs, self.n, self.seq, self.out.data_ptr(),
+                                                      self._ptrs, self.n, x.data_ptr(), out.data_ptr(),
                                                       self.status.data_ptr()), "doper_allreduce_oneshot")
-        return self.out
+        return out
 
     def close(self) -> None:
         torch.cuda.synchronize(self.device)

@@ -199,20 +199,22 @@ int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, con
  * trainer (controller gradients + loss, 26 KB: latency bound).  Every rank (one process per GPU) calls
  * doper_peer_alloc once (the only allocation the library ever makes: an explicit, caller-owned buffer
  * that must be cudaMalloc'ed for CUDA IPC), exchanges the 64-byte handles with its peers by any host
- * channel (the Python binding uses torch.distributed), and opens theirs with doper_peer_open.  Per step:
- * write the n floats into doper_peer_slot(own buffer, n, seq) on `stream`, then call
- * doper_allreduce_oneshot with the same seq = 1, 2, 3, ... on every rank: out[i] = sum over ranks in rank
- * order (the same bits everywhere).  `buffers` is a HOST array of `world` device pointers indexed by
- * rank (own buffer at [rank]).  A peer that never arrives makes the kernel give up after about two
- * seconds and set *status (device int, nullable) to 1 instead of spinning for ever. */
+ * channel (the Python binding uses torch.distributed), and opens theirs with doper_peer_open.  Per step
+ * every rank calls doper_allreduce_oneshot ONCE (the same number of calls on every rank — the step
+ * counter lives in the buffer, so the arguments never change and the call can sit in a CUDA graph):
+ * out[i] = sum over ranks of in[i], added in rank order (the same bits everywhere).  `in` and `out` are
+ * ordinary device arrays of n floats (they may alias); `buffers` is a HOST array of `world` device
+ * pointers indexed by rank (own buffer at [rank]).  One kernel: it pushes `in` into every peer with the
+ * step number inside each 16-byte store and polls its own buffer for the peers' words (no fence, no
+ * separate flag: one NVLink crossing).  A peer that never arrives makes the kernel give up after about
+ * two seconds and set *status (device int, nullable) to 1 instead of spinning for ever. */
 size_t doper_peer_buffer_bytes(int32_t n);
 int doper_peer_alloc(int32_t n, void** buffer, unsigned char handle[64]);
 int doper_peer_open(const unsigned char handle[64], void** buffer);
 int doper_peer_close(void* buffer);
 int doper_peer_free(void* buffer);
-void* doper_peer_slot(void* buffer, int32_t n, uint32_t seq);
 int doper_allreduce_oneshot(doper_stream_t stream, int32_t rank, int32_t world, void* const* buffers, int32_t n,
-                            uint32_t seq, float* out, int32_t* status);
+                            const float* in, float* out, int32_t* status);
 
 /* ---- measurement helper --------------------------------------------------------------- */
 
