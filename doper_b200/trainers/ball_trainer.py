@@ -47,6 +47,8 @@ class BallAttractorTrainer:
         self.batch_size = self.config["train"]["batch_size"]
         self.num_actions = self.config["train"]["num_actions"]
         self._reducer = None
+        self.reduce_transport = "auto"  # distributed.PolicyGradReducer: "auto" | "nvlink" | "collective"
+        self.data_parallel = True  # False: never exchange, even inside an initialised process group
 
     def forward(self, observation, coordinate_init, velocity_init, scene):
         """Validation rollout of the FIRST ball (ball_trainer.py:31-47): ``(x_T, v_T, trajectory)``."""
@@ -84,14 +86,23 @@ class BallAttractorTrainer:
             impulse.backward(v_grad)  # ball_trainer.py:70-71: dL/dv0 handed to the controller as dL/dimpulse
             coordinate_init = coord
             velocity_init = velocity_init  # sic (ball_trainer.py:73)
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and \
-                torch.distributed.get_world_size() > 1:
-            if self._reducer is None:
-                self._reducer = PolicyGradReducer(self.controller.parameters(), self.device)
-            loss_val = self._reducer.reduce(loss_val)
+        loss_val = self._exchange(loss_val)
         torch.nn.utils.clip_grad_norm_(self.controller.parameters(), grad_clip)
         self.optimizer.step()
         return loss_val
+
+    def _exchange(self, loss_val):
+        """Data-parallel ranks (one process per GPU, each with its own balls): sum the controller
+        gradients and the loss over ranks — one small kernel over NVLink peer memory
+        (``distributed.PeerAllReducer``), capturable in the iteration's CUDA graph."""
+        if not (self.data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1):
+            return loss_val
+        if self._reducer is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("BallAttractorTrainer: the gradient reducer must exist before graph capture")
+            self._reducer = PolicyGradReducer(self.controller.parameters(), self.device, self.reduce_transport)
+        return self._reducer.reduce(loss_val)
 
     # ------------------------------------------------------------------------------------------
     # one iteration as ONE CUDA graph (SURVEY.md §8f rank 4)
@@ -111,6 +122,7 @@ class BallAttractorTrainer:
             )
             impulse.backward(v_grad)
             coordinate_init = coord
+        loss_val = self._exchange(loss_val)
         torch.nn.utils.clip_grad_norm_(self.controller.parameters(), grad_clip)
         self.optimizer.step()
         return loss_val
@@ -126,6 +138,9 @@ class BallAttractorTrainer:
         v_static = torch.zeros((B, 2), dtype=torch.float32, device=self.device)
         x_static.copy_(torch.as_tensor(scene_handler.get_init_state(B), dtype=torch.float32, device=self.device))
         v_static.uniform_(-1, 2)
+        if self._reducer is None and self.data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:  # peer buffers are mapped outside the capture
+            self._reducer = PolicyGradReducer(self.controller.parameters(), self.device, self.reduce_transport)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         # warm-up on a side stream (allocates the cached rollout buffers, lazily-initialised optimiser

@@ -75,3 +75,18 @@ def test_two_ranks_match_nccl():
     line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["values_match_nccl"] and line["same_bits_on_every_rank"] and line["graph_replay_ok"]
     assert line["status"] == 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one node")
+def test_data_parallel_iteration_graph_with_peer_exchange():
+    """tools/trainer_multi_gpu_check.py: the 8-action iteration as one CUDA graph per rank with the
+    peer-memory exchange captured inside == the eager loop with NCCL == one GPU with all the balls."""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29549",
+                          str(ROOT / "tools/trainer_multi_gpu_check.py")],
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["graph_equals_eager_nccl"] and line["same_bits_on_every_rank"] and line["peer_status"] == 0
+    assert line["first_iteration_grad_vs_single_gpu_big_batch_rel_err"] < 1e-4  # fp32 sums in a different order
+    assert line["loss_rel_err"] < 1e-5
