@@ -189,13 +189,14 @@ def ours(args):
     # seeded batch of world x per_gpu balls instead: the synchronous step then waits for the rank that
     # drew the ball with the longest collision chain (DESIGN.md "stragglers"), a property of the inputs.
     # c3 / c5 are DEFINED as global batches and are always sliced.
+    sigma = 0.0 if args.reference_regime else 10.0
     replicated = world > 1 and name in ("c1", "c2", "c4") and not args.distinct_shards
     if replicated:
         lo, hi = 0, per_gpu
-        w = syn.make_workload(name, n_balls=per_gpu)
+        w = syn.make_workload(name, n_balls=per_gpu, impulse_sigma=sigma)
     else:
         lo, hi = ball_shard(total, rank, world)  # contiguous slice of the globally seeded batch
-        w = syn.make_workload(name, n_balls=total, lo=lo, hi=hi)
+        w = syn.make_workload(name, n_balls=total, lo=lo, hi=hi, impulse_sigma=sigma)
     B, n_steps = per_gpu, (args.sim_steps or w["n_steps"])
     w["n_steps"], w["sim_time"] = n_steps, n_steps / 1000.0
     S = int(w["segments"].shape[-3])
@@ -379,6 +380,7 @@ def ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_label(name, B, S, n_steps, bool(w["per_env"])) +
+                       (" [reference regime: v0 = U(-1,2)^2, no impulse stand-in]" if args.reference_regime else "") +
                        ((f" per GPU ({world} GPUs, every rank runs the workload's own seeded batch, "
                          if replicated else
                          f" per GPU ({world} GPUs, a globally seeded batch of {total} balls sliced by rank, ") +
@@ -416,7 +418,7 @@ def reference(args):
 
     name = args.workload
     per_gpu = args.balls or syn.WORKLOADS[name][0]
-    w = syn.make_workload(name, n_balls=per_gpu)
+    w = syn.make_workload(name, n_balls=per_gpu, impulse_sigma=0.0 if args.reference_regime else 10.0)
     if args.sim_steps:
         w["n_steps"], w["sim_time"] = args.sim_steps, args.sim_steps / 1000.0
     sample, what = bounded_sample(w)
@@ -427,7 +429,8 @@ def reference(args):
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(1, min(args.warmup, 3)),
         "ms_per_step": round(r["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_label(name, per_gpu, S, w["n_steps"], bool(w["per_env"]))},
+        "config": {"workload": workload_label(name, per_gpu, S, w["n_steps"], bool(w["per_env"])) +
+                   (" [reference regime: v0 = U(-1,2)^2, no impulse stand-in]" if args.reference_regime else "")},
         "cpu_baseline": {"value": round(r["value"], 1), "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": f"each step = {what}; oracle/ball_sim_ref.c {r['flavour']} + OpenMP on all host "
                                    f"cores (restated reference: the reference is JAX/XLA:CPU, not installable here)"},
@@ -453,6 +456,8 @@ def main():
     ap.add_argument("--full-sweep", action="store_true",
                     help="forbid the broad-phase kernels: every (ball, segment) pair is evaluated every step")
     ap.add_argument("--strong", action="store_true")
+    ap.add_argument("--reference-regime", action="store_true",
+                    help="v0 = U(-1,2)^2 only (SURVEY 8d: the trainer's draw without the impulse stand-in): slow balls, rare collisions")
     ap.add_argument("--nccl", action="store_true", help="N > 1: exchange through NCCL instead of the peer-memory kernel")
     ap.add_argument("--distinct-shards", action="store_true",
                     help="N > 1: slice one globally seeded batch instead of running the workload's batch on every rank")

@@ -316,32 +316,23 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
         }
         // ---- (2) free flight: lane k keeps step t + k ---------------------------------------------------
         const int Tq = alive ? min(T, n - t) : 0;
-        const int Tmax = __reduce_max_sync(0xffffffffu, Tq);
-        float sx = x, sy = y, svx = vx, svy = vy;  // state at the START of my step
+        // every lane integrates from the round's start state up to ITS step (redundantly: the chain is
+        // serial); the division range test is one min / max pair over the whole chain
         State my; my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
-        bool ok = true;
+        const int last = min(lane, Tq - 1);
         {
-            float cx = x, cy = y, cvx = vx, cvy = vy;
-            const int last = min(lane, Tq - 1);
-            for (int k = 0; k < Tmax; ++k) {
-                if (k <= last) {
-                    sx = cx; sy = cy; svx = cvx; svy = cvy;
-                    ok = free_step_fast(cx, cy, cvx, cvy, c, my) && ok;
-                    cx = my.x; cy = my.y; cvx = my.vx; cvy = my.vy;
-                }
+            float nmin = __int_as_float(0x7f800000), nmax = 0.0f;
+            for (int k = 0; k <= last; ++k) free_step_acc(my.x, my.y, my.vx, my.vy, c, my, nmin, nmax);
+            const bool ok = div_range_ok(nmin, nmax, c);
+            if (__any_sync(0xffffffffu, !ok)) {  // a numerator left the range of the fast division: redo exactly
+                my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
+                for (int k = 0; k <= last; ++k) free_step(my.x, my.y, my.vx, my.vy, c, my);
             }
         }
-        if (__any_sync(0xffffffffu, !ok)) {  // a numerator left the range of the fast division: redo exactly
-            float cx = x, cy = y, cvx = vx, cvy = vy;
-            const int last = min(lane, Tq - 1);
-            for (int k = 0; k < Tmax; ++k) {
-                if (k <= last) {
-                    sx = cx; sy = cy; svx = cvx; svy = cvy;
-                    free_step(cx, cy, cvx, cvy, c, my);
-                    cx = my.x; cy = my.y; cvx = my.vx; cvy = my.vy;
-                }
-            }
-        }
+        // state at the START of my step = the end state of the lane before me
+        float sx = __shfl_up_sync(0xffffffffu, my.x, 1, G), sy = __shfl_up_sync(0xffffffffu, my.y, 1, G);
+        float svx = __shfl_up_sync(0xffffffffu, my.vx, 1, G), svy = __shfl_up_sync(0xffffffffu, my.vy, 1, G);
+        if (lane == 0) { sx = x; sy = y; svx = vx; svy = vy; }
         // ---- (3) my step against the list -------------------------------------------------------------------
         const bool valid = lane < Tq;
         const float px = valid ? my.x : x, py = valid ? my.y : y;

@@ -157,13 +157,15 @@ WORKLOADS = {
 }
 
 
-def make_workload(name: str, n_balls: int = None, lo: int = 0, hi: int = None):
+def make_workload(name: str, n_balls: int = None, lo: int = 0, hi: int = None, impulse_sigma: float = 10.0):
     """Inputs of a named workload; ``[lo:hi)`` slices balls/envs (rank sharding keeps
-    results independent of the GPU count: global arrays are generated, then sliced)."""
+    results independent of the GPU count: global arrays are generated, then sliced).
+    ``impulse_sigma=0`` is SURVEY.md §8d's "reference regime": v0 = U(-1,2)^2 only, as
+    ``ball_trainer.py:52`` draws it before the controller's impulse."""
     balls, tri, n_steps, per_env, map_seed, state_seed = WORKLOADS[name]
     balls = n_balls or balls
     segs = make_env_maps(map_seed, balls, tri) if per_env else make_map(map_seed, tri)
-    x0, v0 = make_init_states(state_seed, balls, segs)
+    x0, v0 = make_init_states(state_seed, balls, segs, impulse_sigma=impulse_sigma)
     hi = balls if hi is None else hi
     if per_env:
         segs = segs[lo:hi]
