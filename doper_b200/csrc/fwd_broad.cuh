@@ -114,12 +114,13 @@ __global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED && !GRID) ? 7 :
         const float ddx = px - cs.cx, ddy = py - cs.cy;
         const bool stale = fast && !(ddx * ddx + ddy * ddy <= cs.rho2);
         if (__any_sync(0xffffffffu, stale)) {  // warp-uniform refresh
-            j0 = list_argmin<G, LCAP>(sc, fast ? px : 0.f, fast ? py : 0.f, lane, list, kFwdThreads, cs, j0);  // cnt = 0 before the first list
+            // seed of an argmin list (exact index log only; a hit list has no seed)
+            if (exact_idx) j0 = list_argmin<G, LCAP>(sc, fast ? px : 0.f, fast ? py : 0.f, lane, list, kFwdThreads, cs, j0);  // cnt = 0 before the first list
             if (fast) {
                 const float sx = px - x, sy = py - y;
                 const float dstep = sqrtf(sx * sx + sy * sy);  // displacement of this step
                 const float rho = fminf(fmaxf(1.25f * (float)kCullPeriod * dstep, rho_min), rho_max);
-                cull_refresh<G, LCAP, GRID>(sc, grid, px, py, rho, c.r, lane, j0, list, kFwdThreads, cs);
+                cull_refresh<G, LCAP, GRID>(sc, grid, px, py, rho, c.r, lane, j0, list, kFwdThreads, cs, exact_idx);
             }
         }
         // narrow phase, estimates only: far from every wall -> no collision, nothing exact needed
@@ -181,10 +182,18 @@ __global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED && !GRID) ? 7 :
 constexpr int kTpcListCap = 64;
 constexpr int kContactSteps = 16;  // sequential steps per round of a ball in contact mode
 
-template <int G, bool GRID>
-__global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdParams p) {
+// Debug build only (-DDOPER_PHASE_TIMERS, tools/phase_timers.py): per-phase clock64() totals of lane 0 of
+// every warp, added into the buffer passed as traj_a (which then receives no trajectory).
+#ifdef DOPER_PHASE_TIMERS
+#define DOPER_PHASE(k) { const long long now_ = clock64(); phase_t[phase_cur] += now_ - phase_t0; phase_t0 = now_; phase_cur = (k); }
+#else
+#define DOPER_PHASE(k)
+#endif
+
+template <int G, bool GRID, int THREADS>
+__global__ void __launch_bounds__(THREADS) rollout_fwd_tpc_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int BPB = kFwdThreads / G;  // balls per block
+    constexpr int BPB = THREADS / G;  // balls per block
     constexpr unsigned kLow = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
     const int tid = threadIdx.x, lane = tid % G, slot = tid / G, gbase = (tid & 31) - lane;
     const int64_t n_scenes = p.per_env ? p.B : 1;
@@ -220,6 +229,7 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
     float x = xx.x, y = xx.y, vx = vv.x, vy = vv.y;  // state at step t (uniform within the group)
     const Consts c = p.c;
     const int n = p.n_steps, K = p.K;
+    const int kshift = (K > 0 && (K & (K - 1)) == 0) ? (31 - __clz(K)) : -1;
     const bool exact_idx = p.exact_idx != 0;
     mbar_wait(bar, 0);
 
@@ -230,12 +240,21 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
     if (__all_sync(0xffffffffu, !sc.weird)) j0 = hint_by_estimate<G>(sc, x, y, lane);
     GroupList gl;
     gl.e = lists + (size_t)slot * kTpcListCap; gl.cap = kTpcListCap; gl.cnt = 0;
-    gl.cx = 0.f; gl.cy = 0.f; gl.rho2 = -1.0f; gl.far2 = 0.f;
+    gl.cx = 0.f; gl.cy = 0.f; gl.rho2 = -1.0f; gl.far2 = 0.f; gl.safe2 = -1.0f;
     const GridView grid = grid_view(p.scene_ws, L);
     const float rho_min = sc.scale * 0.001953125f, rho_max = sc.scale * 0.125f;
     int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
+#ifdef DOPER_PHASE_TIMERS
+    long long phase_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long phase_t0 = clock64();
+    int phase_cur = 7;
+    float2* const traj_a_real = nullptr;
+#else
+    float2* const traj_a_real = p.traj_a;
+#endif
 
     while (__any_sync(0xffffffffu, t < n)) {
+        DOPER_PHASE(0)
         // ---- (0) contact mode --------------------------------------------------------------------------
         // A ball that collided at the first step of its last round (resting / sliding contact) gains
         // nothing from speculation: it runs up to kContactSteps plain sequential steps here, every lane
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
                     const size_t o = (size_t)t * p.B + ball;
                     if (p.traj_x) p.traj_x[o] = make_float2(x, y);
                     if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
-                    if (p.traj_a) p.traj_a[o] = make_float2(s1.ax, s1.ay);
+                    if (traj_a_real) traj_a_real[o] = make_float2(s1.ax, s1.ay);
                 }
                 ++t;
                 sat_out = true;
@@ -301,6 +320,7 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
             }
         }
         const bool alive = t < n && !sat_out;
+        DOPER_PHASE(1)
         // ---- (1) list refresh at the current position -------------------------------------------------
         {
             const float M0 = fmaxf(sc.scale, fmaxf(fabsf(x), fabsf(y)));
@@ -308,12 +328,13 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
             const float ddx = x - gl.cx, ddy = y - gl.cy;
             const bool want = alive && fast0 && (trouble == 1 || !(ddx * ddx + ddy * ddy <= 0.25f * gl.rho2));
             if (__any_sync(0xffffffffu, want)) {
-                if (want) j0 = glist_argmin(sc, x, y, gl, j0);
+                if (want && exact_idx) j0 = glist_argmin(sc, x, y, gl, j0);  // seed of an argmin list
                 const float dstep = sqrtf(vx * vx + vy * vy) * c.dt;
                 const float rho = fminf(fmaxf(1.25f * (float)(kCullPeriod + 2 * G) * dstep, rho_min), rho_max);
-                glist_refresh<G, GRID>(sc, grid, want ? x : 0.f, want ? y : 0.f, rho, c.r, lane, gbase, j0, want, gl);
+                glist_refresh<G, GRID>(sc, grid, want ? x : 0.f, want ? y : 0.f, rho, c.r, lane, gbase, j0, want, gl, exact_idx);
             }
         }
+        DOPER_PHASE(2)
         // ---- (2) free flight: lane k keeps step t + k ---------------------------------------------------
         const int Tq = alive ? min(T, n - t) : 0;
         // every lane integrates from the round's start state up to ITS step (redundantly: the chain is
@@ -333,15 +354,18 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
         float sx = __shfl_up_sync(0xffffffffu, my.x, 1, G), sy = __shfl_up_sync(0xffffffffu, my.y, 1, G);
         float svx = __shfl_up_sync(0xffffffffu, my.vx, 1, G), svy = __shfl_up_sync(0xffffffffu, my.vy, 1, G);
         if (lane == 0) { sx = x; sy = y; svx = vx; svy = vy; }
+        DOPER_PHASE(3)
         // ---- (3) my step against the list -------------------------------------------------------------------
         const bool valid = lane < Tq;
         const float px = valid ? my.x : x, py = valid ? my.y : y;
         const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)));
         const bool fast = !sc.weird && M <= 1.0e15f && trouble != 2;  // false for NaN / inf points
         const float ddx = px - gl.cx, ddy = py - gl.cy;
-        const bool stale = fast && !(ddx * ddx + ddy * ddy <= gl.rho2);
-        const float amin = (fast && !stale) ? glist_min(sc, px, py, gl) : 0.0f;
-        const bool near = !fast || exact_idx || !(amin > gl.far2);
+        const float dd2 = ddx * ddx + ddy * ddy;
+        const bool stale = fast && !(dd2 <= gl.rho2);
+        const bool safe = fast && !exact_idx && dd2 <= gl.safe2;  // inside the safe disc: no segment can be within r
+        const float amin = (fast && !stale && !safe) ? glist_min(sc, px, py, gl) : 0.0f;
+        const bool near = !safe && (!fast || exact_idx || !(amin > gl.far2));
         int idx = 0;
         float dist = __int_as_float(0x7f800000);
         if (valid && near && !stale) {  // exact distance and index for my own step (no warp primitives inside)
@@ -351,6 +375,7 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
             unpack_key(key, idx, dist);
         }
         const bool hit = valid && !stale && (dist <= c.r);  // NaN -> false (ball_sim.py:164)
+        DOPER_PHASE(4)
         // ---- (4) first event of the group, commit ---------------------------------------------------------
         const unsigned evb = (__ballot_sync(0xffffffffu, valid && (stale || hit)) >> gbase) & kLow;
         const int f = evb ? (__ffs(evb) - 1) : Tq;       // lanes < f: free flight, final
@@ -376,19 +401,24 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
             }
         }
         const int n_commit = f + (ev_hit ? 1 : 0);
+        DOPER_PHASE(5)
         if (active && lane < n_commit) {
             const int ts = t + lane;
             const bool h = ev_hit && lane == f;
             if (hl) hl[(int64_t)ts * p.hl_st] = pack_log((h || exact_idx) ? idx : 0, h, clip_bits(svx, svy));
             if (h && p.hitstate) p.hitstate[(size_t)ts * p.B + ball] = make_float4(sx, sy, svx, svy);
-            if (p.ckpt && (ts % K) == 0) p.ckpt[(size_t)(ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
+            if (p.ckpt) {  // K is usually a power of two: shift and mask instead of two integer divisions
+                const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
+                if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
+            }
             const size_t o = (size_t)ts * p.B + ball;
             if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
             if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
-            if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+            if (traj_a_real) traj_a_real[o] = make_float2(out.ax, out.ay);
         }
         x = nx; y = ny; vx = nvx; vy = nvy;
         t += n_commit;
+        DOPER_PHASE(6)
         // ---- (5) speculation length / trouble handling for the next round ---------------------------
         if (sat_out) {
             // contact mode this round: T / trouble were set there
@@ -407,6 +437,13 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_tpc_kernel(const FwdP
         p.xT[ball] = make_float2(x, y);
         p.vT[ball] = make_float2(vx, vy);
     }
+#ifdef DOPER_PHASE_TIMERS
+    DOPER_PHASE(7)
+    if ((threadIdx.x & 31) == 0 && p.traj_a) {
+        unsigned long long* phase_out = reinterpret_cast<unsigned long long*>(p.traj_a);
+        for (int k = 0; k < 8; ++k) atomicAdd(phase_out + k, (unsigned long long)phase_t[k]);
+    }
+#endif
 }
 
 

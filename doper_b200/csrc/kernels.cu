@@ -17,6 +17,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "../../include/doper_b200.h"
 #include "physics.cuh"
 #include "sweep.cuh"
@@ -44,6 +46,13 @@ int max_optin_smem() {
     int dev = 0, v = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+    return v;
+}
+
+int sm_count() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
     return v;
 }
 
@@ -271,19 +280,31 @@ int launch_fwd_cull(cudaStream_t st, FwdParams p, size_t scene_smem) {
 
 template <int G>
 int launch_fwd_tpc(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
-    const size_t smem = scene_smem + (size_t)(kFwdThreads / G) * kTpcListCap * sizeof(unsigned short);
-    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
-    const int bpb = kFwdThreads / G;
-    const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
-    const bool dense = !p.per_env && scene_layout(1, p.S).S_pad >= kGridMinSegments;
-    auto go = [&](auto kernel) {
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return (int)DOPER_ERR_SMEM_LIMIT;
-        kernel<<<grid, kFwdThreads, smem, st>>>(p);
-        return launch_status();
+    // Block size.  This kernel runs small batches (a few thousand balls, fewer resident warps than the
+    // SMs could hold), so what matters is how evenly the balls spread over the 148 SMs: 4,096 balls in
+    // blocks of 8 are 512 blocks = 4 blocks on some SMs and 3 on others (32 vs 24 balls, and the busy
+    // SMs set the kernel time); blocks of 64 threads halve the granularity (28 vs 24).
+    const bool small_blocks = G <= 16 && !p.per_env && (p.B + 128 / G - 1) / (128 / G) < 8 * (int64_t)sm_count();
+    auto run = [&](auto threads_tag) {
+        constexpr int THREADS = decltype(threads_tag)::value;
+        const size_t smem = scene_smem + (size_t)(THREADS / G) * kTpcListCap * sizeof(unsigned short);
+        if ((int)smem > max_optin_smem()) return (int)DOPER_ERR_SMEM_LIMIT;
+        const int bpb = THREADS / G;
+        const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
+        const bool dense = !p.per_env && scene_layout(1, p.S).S_pad >= kGridMinSegments;
+        auto go = [&](auto kernel) {
+            if (smem > 48 * 1024 &&
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return (int)DOPER_ERR_SMEM_LIMIT;
+            kernel<<<grid, THREADS, smem, st>>>(p);
+            return launch_status();
+        };
+        return dense ? go(rollout_fwd_tpc_kernel<G, true, THREADS>) : go(rollout_fwd_tpc_kernel<G, false, THREADS>);
     };
-    return dense ? go(rollout_fwd_tpc_kernel<G, true>) : go(rollout_fwd_tpc_kernel<G, false>);
+    if constexpr (G <= 16) {
+        if (small_blocks) return run(std::integral_constant<int, 64>{});
+    }
+    return run(std::integral_constant<int, 128>{});
 }
 
 template <int G>

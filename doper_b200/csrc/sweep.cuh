@@ -239,6 +239,16 @@ __device__ __forceinline__ int hint_by_estimate(const SceneView& sc, float px, f
 // original indices, so the result is bit-identical to the full sweep.  M bounds the scene and every
 // point of the list's lifetime.  A lane whose share overflows its capacity sweeps all its
 // segments until the next refresh (always correct).
+//
+// Hit lists (the default; `need_argmin` = false).  The winning index is consumed at COLLISIONS only, and a
+// step collides iff some d_ref_j(p) <= r.  For |p - c| <= rho such a j has
+//     e_j <= D_j(c) + 49uM <= D_j(p) + rho + 49uM <= d_ref_j(p) + rho + 87uM <= r + rho + 87 u M,
+// so the list {j : e_j <= rho + r + 128 u M} holds every segment that can touch the ball anywhere in
+// the disc — the argmin of a colliding step and all its exact ties included — and a segment outside
+// the list has d_ref_j(p) > r + 41uM at every point of the disc.  Its radius rho + r does not depend on
+// the distance to the nearest wall (the argmin list needs e_j0 + 2 rho), so in open space it is
+// short or empty.  `need_argmin` (exact index log: the index of EVERY step is wanted) keeps the
+// argmin list.
 constexpr float kCullDeltaPerM = 256.0f * 5.9604644775390625e-08f;  // 256 u, u = 2^-24
 constexpr float kCullUp = 1.0f + 9.5367431640625e-07f;              // 1 + 2^-20: covers the roundings of T
 constexpr float kCullRhoCheck = 0.98f;                              // the guard compares against (0.98 rho)^2
@@ -254,19 +264,29 @@ struct CullState {
 
 __device__ __forceinline__ float cull_far2(float radius, float M);
 
+// Largest estimate a list entry may have (see above): e_j0 + 2 rho + 256 u M for an argmin list,
+// rho + r + 128 u M for a hit list; rounded up.
+__device__ __forceinline__ float list_reach(const SceneView& sc, float px, float py, float rho, float radius, float M,
+                                            int j0, bool need_argmin) {
+    if (need_argmin) {
+        const float e = sqrtf(approx_d2(px, py, sc.q[j0], sc.rl[j0])) * kCullUp;
+        return e + __fmaf_rn(kCullDeltaPerM, M, rho + rho);
+    }
+    return __fmaf_rn(kCullSafePerM, M, rho + radius) * kCullUp;
+}
+
 // list entry k of this lane lives at list[k * stride]
 template <int G, int LCAP, bool GRID>
 __device__ __forceinline__ void cull_refresh(const SceneView& sc, const GridView& grid, float px, float py, float rho,
                                              float radius, int lane, int j0, unsigned short* list, int stride,
-                                             CullState& cs) {
+                                             CullState& cs, bool need_argmin) {
     const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)) + rho);
-    const float e = sqrtf(approx_d2(px, py, sc.q[j0], sc.rl[j0])) * kCullUp;
-    const float w = __fmaf_rn(kCullDeltaPerM, M, rho + rho);
-    const float T = ((e + w) * (e + w)) * kCullUp;
+    const float reach = list_reach(sc, px, py, rho, radius, M, j0, need_argmin);  // kept: e_j <= reach
+    const float T = (reach * reach) * kCullUp;
     int cnt = 0;
     int ix0, ix1, iy0, iy1;
     // every kept segment is closer than (e + w) + 49 u M to the centre: the grid cells around it hold them all
-    if (GRID && grid_range(grid, px, py, __fmaf_rn(kCullSafePerM, M, e + w) * kCullUp, ix0, ix1, iy0, iy1)) {
+    if (GRID && grid_range(grid, px, py, __fmaf_rn(kCullSafePerM, M, reach) * kCullUp, ix0, ix1, iy0, iy1)) {
         for (int cy = iy0; cy <= iy1; ++cy) {
             const int row = cy * grid.gx;
             const int k1 = grid.cell_start[row + ix1 + 1];
@@ -387,6 +407,13 @@ struct GroupList {
     int cap;
     int cnt;            // > cap = overflow: sweep every segment
     float cx, cy, rho2, far2;  // as CullState
+    // Safe disc: with e_min = the smallest estimate over EVERY segment at the centre, a point p of the
+    // list's lifetime has d_ref_j(p) >= D_j(p) - 38uM >= D_j(c) - |p - c| - 38uM >= e_min - |p - c| - 87uM
+    // for all j, so |p - c| < e_min - r - 87uM proves "no collision at p" from the displacement alone —
+    // the list is not even read.  safe2 = (sqrt(min estimate^2) - (r + 128 u M))^2 (the 41uM of extra
+    // slack cover the roundings of the square root, of the difference and of |p - c|^2), capped by
+    // rho2 (M bounds only points within rho of the centre); negative = no safe disc.
+    float safe2;
 };
 
 // Every lane of the warp calls (warp-wide ballots); `doit` is uniform within a group.  Segment
@@ -394,15 +421,17 @@ struct GroupList {
 // ascending order (ballot + popc prefix inside the group).
 template <int G, bool GRID>
 __device__ __forceinline__ void glist_refresh(const SceneView& sc, const GridView& grid, float px, float py, float rho,
-                                              float radius, int lane, int gbase, int j0, bool doit, GroupList& gl) {
+                                              float radius, int lane, int gbase, int j0, bool doit, GroupList& gl,
+                                              bool need_argmin) {
     const float M = fmaxf(sc.scale, fmaxf(fabsf(px), fabsf(py)) + rho);
-    const float e = sqrtf(approx_d2(px, py, sc.q[j0], sc.rl[j0])) * kCullUp;
-    const float w = __fmaf_rn(kCullDeltaPerM, M, rho + rho);
-    const float T = ((e + w) * (e + w)) * kCullUp;
+    const float reach = list_reach(sc, px, py, rho, radius, M, j0, need_argmin);
+    const float T = (reach * reach) * kCullUp;
     const unsigned low = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
     int cnt = 0;
+    float e2min = __int_as_float(0x7f800000);  // smallest squared estimate over all segments (full scan only)
+    bool scanned_all = false;
     int ix0 = 0, ix1 = -1, iy0 = 0, iy1 = -1;
-    const bool by_grid = GRID && doit && grid_range(grid, px, py, __fmaf_rn(kCullSafePerM, M, e + w) * kCullUp, ix0, ix1, iy0, iy1);
+    const bool by_grid = GRID && doit && grid_range(grid, px, py, __fmaf_rn(kCullSafePerM, M, reach) * kCullUp, ix0, ix1, iy0, iy1);
     if (GRID && __all_sync(0xffffffffu, by_grid || !doit)) {
         // every refreshing group walks its own cells (row by row: the cells of a grid row are contiguous);
         // the warp iterates until the longest walk is done (ballots need every lane)
@@ -434,20 +463,39 @@ __device__ __forceinline__ void glist_refresh(const SceneView& sc, const GridVie
             }
         }
     } else {
-        for (int i0 = 0; i0 < sc.S_pad; i0 += G) {
-            const int i = i0 + lane;
-            const bool pass = doit && approx_d2(px, py, sc.q[i], sc.rl[i]) <= T;
-            const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> gbase) & low;
-            const int pos = cnt + __popc(gb & ((1u << lane) - 1u));
-            if (pass && pos < gl.cap) gl.e[pos] = (unsigned short)i;
-            cnt += __popc(gb);
+        // four slices of G segments per round: the four estimates (shared-memory loads + a 9-deep FP chain
+        // each) and the four ballots are independent, so their latencies overlap
+        constexpr int U = 4;
+        const unsigned below = (1u << lane) - 1u;
+        for (int i0 = 0; i0 < sc.S_pad; i0 += U * G) {
+            float a[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * G + lane;
+                a[u] = __int_as_float(0x7f800000);
+                if (doit && i < sc.S_pad) a[u] = approx_d2(px, py, sc.q[i], sc.rl[i]);
+            }
+            unsigned gb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) gb[u] = (__ballot_sync(0xffffffffu, a[u] <= T) >> gbase) & low;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int pos = cnt + __popc(gb[u] & below);
+                if (a[u] <= T && pos < gl.cap) gl.e[pos] = (unsigned short)(i0 + u * G + lane);
+                cnt += __popc(gb[u]);
+                e2min = fminf(e2min, a[u]);
+            }
         }
+        e2min = group_min_f<G>(e2min);
+        scanned_all = true;
     }
     __syncwarp();
     if (doit) {
         gl.cnt = cnt; gl.cx = px; gl.cy = py;
         gl.rho2 = (kCullRhoCheck * rho) * (kCullRhoCheck * rho);
         gl.far2 = cull_far2(radius, M);
+        const float sigma = sqrtf(e2min) - __fmaf_rn(kCullSafePerM, M, radius) * kCullUp;
+        gl.safe2 = (scanned_all && sigma > 0.0f) ? fminf((sigma * sigma) * (1.0f - 9.5367431640625e-07f), gl.rho2) : -1.0f;
     }
 }
 

@@ -46,7 +46,12 @@ def main():
     ls = torch.empty(1, device=dev)
     out = {"workload": name, "B": B, "n_steps": n}
     x0h, v0h = w["x0"].copy(), w["v0"].copy()
-    for tag in ("as_is", "without_sliding_balls"):
+    # optional third argument: hit-count thresholds, e.g. "8,4,2,0": after the run as is, balls with more
+    # collisions than each threshold are replaced by copies of a ball that never collides
+    thresholds = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else None
+    tags = ("as_is", "without_sliding_balls") if thresholds is None else ("as_is",) + tuple(f"max_{h}_collisions_per_ball" for h in thresholds)
+    per_ball = None
+    for tag in tags:
         x0, v0 = torch.tensor(x0h, device=dev), torch.tensor(v0h, device=dev)
         fwd = lambda: check(lib.doper_rollout_fwd(st, ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT),
                                                   0, 0, 0, ptr(bufs.ws)), "fwd")
@@ -55,6 +60,8 @@ def main():
         b_ms = time_ms(lambda: check(lib.doper_rollout_bwd(st, ctypes.byref(desc), ptr(sws), ptr(bufs.ws), ptr(bar), 0,
                                                            ptr(gx), ptr(gv)), "bwd"))
         out[tag] = {"fwd_ms": round(f_ms, 4), "bwd_ms": round(b_ms, 4)}
+        if tag != "as_is" and thresholds is not None:
+            pass
         if tag == "as_is":
             h = ball_sim.rollout_history(w["sim_time"], n, scene, x0h, v0h, w["attractor"], w["constants"])["hit"]
             per_ball = h.sum(0)
@@ -63,7 +70,17 @@ def main():
             out["max_collisions_per_ball"] = int(per_ball.max())
             out["total_collisions"] = int(per_ball.sum())
             donor = int(np.argmin(per_ball))
-            x0h[heavy], v0h[heavy] = x0h[donor], v0h[donor]
+            if thresholds is None:
+                x0h[heavy], v0h[heavy] = x0h[donor], v0h[donor]
+        if thresholds is not None:
+            k = tags.index(tag)
+            if k < len(thresholds):
+                sel = np.nonzero(per_ball > thresholds[k])[0]
+                # donors: random balls that never collide (same speed distribution, unlike one fixed donor)
+                free = np.nonzero(per_ball == 0)[0]
+                pick = np.random.default_rng(7).choice(free, size=len(sel))
+                x0h[sel], v0h[sel] = w["x0"][pick], w["v0"][pick]
+                out.setdefault("replaced", {})[str(thresholds[k])] = int(len(sel))
         print(tag, out[tag], flush=True)
     print(json.dumps(out))
     Path("gpurun_out").mkdir(exist_ok=True)
