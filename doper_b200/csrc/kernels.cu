@@ -86,7 +86,8 @@ int resolve_K(const doper_rollout_desc* d) {
     if (chunked_eligible(d)) {
         // 32 chunks per ball (one warp); small batches with long rollouts take 64 (two warps): more threads
         // in flight, and the slowest thread — a chunk where the ball collides step after step — is half as long
-        const int n_chunks = (d->B <= 4096 && d->n_steps >= 256) ? 64 : 32;
+        // (4,096 balls x 500 steps measured 0.070 ms with 32 chunks, 0.072 with 64, 0.103 with 128)
+        const int n_chunks = (d->B <= 2048 && d->n_steps >= 256) ? 64 : 32;
         const int K = (d->n_steps + n_chunks - 1) / n_chunks;
         if (K <= kChunkedMaxK) return K < 4 ? 4 : K;
     }
@@ -155,7 +156,9 @@ bool use_tpc(const doper_rollout_desc* d) {
 int cull_lanes(const doper_rollout_desc* d) {
     if (d->lanes_per_ball != 0) return d->lanes_per_ball;
     if (d->per_env) return 4;  // read in place (see launch_fwd_cull); measured: C3 5.4 ms vs 8.2 ms staged with 8 lanes
-    if (use_tpc(d)) return 16;
+    // lane = time step: one ball per warp while the batch is too small to fill the SMs otherwise (measured on
+    // C2-like scenes: 1,024 balls 0.105 ms with 32 lanes vs 0.132 with 16; 4,096 balls 0.189 vs 0.176)
+    if (use_tpc(d)) return d->B <= 2048 ? 32 : 16;
     int g = d->B < 32768 ? 4 : 1;
     if (scene_layout(1, d->S).S_pad >= kGridMinSegments) g = 2;  // dense scene (grid refresh): measured best on C4
     if (!scene_fits_smem(d) && g < 8) g = 8;  // unstaged scene: split the refresh scan (L2 reads) over more lanes
@@ -284,7 +287,7 @@ int launch_fwd_tpc(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
     // SMs could hold), so what matters is how evenly the balls spread over the 148 SMs: 4,096 balls in
     // blocks of 8 are 512 blocks = 4 blocks on some SMs and 3 on others (32 vs 24 balls, and the busy
     // SMs set the kernel time); blocks of 64 threads halve the granularity (28 vs 24).
-    const bool small_blocks = G <= 16 && !p.per_env && (p.B + 128 / G - 1) / (128 / G) < 8 * (int64_t)sm_count();
+    const bool small_blocks = !p.per_env && (p.B + 128 / G - 1) / (128 / G) < 8 * (int64_t)sm_count();
     auto run = [&](auto threads_tag) {
         constexpr int THREADS = decltype(threads_tag)::value;
         const size_t smem = scene_smem + (size_t)(THREADS / G) * kTpcListCap * sizeof(unsigned short);
@@ -301,9 +304,7 @@ int launch_fwd_tpc(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
         };
         return dense ? go(rollout_fwd_tpc_kernel<G, true, THREADS>) : go(rollout_fwd_tpc_kernel<G, false, THREADS>);
     };
-    if constexpr (G <= 16) {
-        if (small_blocks) return run(std::integral_constant<int, 64>{});
-    }
+    if (small_blocks) return run(std::integral_constant<int, 64>{});
     return run(std::integral_constant<int, 128>{});
 }
 

@@ -269,8 +269,36 @@ __device__ __forceinline__ HitFwd hit_forward(float x, float y, float vx, float 
 }
 
 // reverse pass of the collision part for ONE output cotangent (gx, gy, gvx, gvy)
+//   RCP = false: IEEE divisions in the oracle's order (bit-identical to oracle/ball_sim_step.inc on the same history)
+//   RCP = true : every division by a quantity of the forward pass becomes a multiplication by its
+//                reciprocal, taken once per collided step (HitRcp).  The chunk-parallel backward, which
+//                re-associates the chain of step Jacobians anyway and is compared to the oracle within a
+//                tolerance, uses this: a dozen divisions per cotangent were most of its collision path.
+struct HitRcp {
+    float m, o2d, od, den, L;
+};
+
+__device__ __forceinline__ HitRcp hit_reciprocals(const HitFwd& f, const float4& seg, const Consts& c) {
+    HitRcp r;
+    r.m = c.rcp_m;
+    r.o2d = 1.0f / f.o2d; r.od = 1.0f / f.od; r.den = 1.0f / f.den;
+    r.L = 1.0f / (seg.z * seg.z + seg.w * seg.w);
+    return r;
+}
+
+template <bool RCP>
+__device__ __forceinline__ float hdiv(float a, float b, float rb) { return RCP ? a * rb : a / b; }
+
+template <bool RCP>
+__device__ __forceinline__ void proj_vjp_r(const float4& q, float t, float wx, float wy, float rL, float& gx, float& gy) {
+    if (!RCP) { proj_vjp(q, t, wx, wy, gx, gy); return; }
+    const float s = (t > 0.0f && t < 1.0f) ? (wx * q.z + wy * q.w) * rL : 0.0f;
+    gx = s * q.z; gy = s * q.w;
+}
+
+template <bool RCP = false>
 __device__ __forceinline__ HitAdj hit_reverse(const HitFwd& f, const float4& seg, const Consts& c,
-                                              float gx, float gy, float gvx, float gvy) {
+                                              float gx, float gy, float gvx, float gvy, const HitRcp rc = HitRcp()) {
     float bx = 0.f, by = 0.f, bvx = 0.f, bvy = 0.f, bax = 0.f, bay = 0.f;
     float b1x, b1y, b1vx, b1vy;
     float gvbx = gvx + gx * f.tau, gvby = gvy + gy * f.tau;
@@ -278,8 +306,8 @@ __device__ __forceinline__ HitAdj hit_reverse(const HitFwd& f, const float4& seg
     float gtau = (gx * f.vbx + gy * f.vby) + (gvbx * f.abx + gvby * f.aby);
     float gvax = gvbx, gvay = gvby;
     float gabx = gvbx * f.tau, gaby = gvby * f.tau;
-    gxsx += -2.0f * (gabx / c.m); gxsy += -2.0f * (gaby / c.m);
-    gvax += (gabx / c.m) * dfric(f.vax, c); gvay += (gaby / c.m) * dfric(f.vay, c);
+    gxsx += -2.0f * hdiv<RCP>(gabx, c.m, rc.m); gxsy += -2.0f * hdiv<RCP>(gaby, c.m, rc.m);
+    gvax += hdiv<RCP>(gabx, c.m, rc.m) * dfric(f.vax, c); gvay += hdiv<RCP>(gaby, c.m, rc.m) * dfric(f.vay, c);
     float gtoi = -gtau;
     float gvsx = gvax, gvsy = gvay;
     float gvnx = -(1.0f + c.e) * gvax, gvny = -(1.0f + c.e) * gvay;
@@ -287,9 +315,9 @@ __device__ __forceinline__ HitAdj hit_reverse(const HitFwd& f, const float4& seg
     float gn2x = gvnx * f.k + gk * f.vsx, gn2y = gvny * f.k + gk * f.vsy;
     gvsx += gk * f.n2x; gvsy += gk * f.n2y;
     float nd = f.n2x * gn2x + f.n2y * gn2y;
-    float go2x = (gn2x - f.n2x * nd) / f.o2d, go2y = (gn2y - f.n2y * nd) / f.o2d;
+    float go2x = hdiv<RCP>(gn2x - f.n2x * nd, f.o2d, rc.o2d), go2y = hdiv<RCP>(gn2y - f.n2y * nd, f.o2d, rc.o2d);
     float jx, jy;
-    proj_vjp(seg, f.t2, go2x, go2y, jx, jy);
+    proj_vjp_r<RCP>(seg, f.t2, go2x, go2y, rc.L, jx, jy);
     gxsx += jx - go2x; gxsy += jy - go2y;
     bx += gxsx; by += gxsy;
     gvsx += gxsx * f.toi; gvsy += gxsy * f.toi;
@@ -298,16 +326,16 @@ __device__ __forceinline__ HitAdj hit_reverse(const HitFwd& f, const float4& seg
     bax += gvsx * f.toi; bay += gvsy * f.toi;
     gtoi += gvsx * f.s1ax + gvsy * f.s1ay;
     float graw = (f.toi_raw > 0.0f && f.toi_raw < c.dt) ? gtoi : 0.0f;
-    float gnum = graw / f.den;
-    float gden = -(graw * f.toi_raw) / f.den;
+    float gnum = hdiv<RCP>(graw, f.den, rc.den);
+    float gden = hdiv<RCP>(-(graw * f.toi_raw), f.den, rc.den);
     float god = gnum * sgnf(f.od - c.r);
     float gs = gden * sgnf(f.s);
     float gnx = gs * f.s1vx, gny = gs * f.s1vy;
     b1vx = gs * f.nx; b1vy = gs * f.ny;
     float nd1 = f.nx * gnx + f.ny * gny;
-    float gox = (gnx - f.nx * nd1) / f.od + god * f.nx, goy = (gny - f.ny * nd1) / f.od + god * f.ny;
+    float gox = hdiv<RCP>(gnx - f.nx * nd1, f.od, rc.od) + god * f.nx, goy = hdiv<RCP>(gny - f.ny * nd1, f.od, rc.od) + god * f.ny;
     bx -= gox; by -= goy;
-    proj_vjp(seg, f.t1, gox, goy, b1x, b1y);
+    proj_vjp_r<RCP>(seg, f.t1, gox, goy, rc.L, b1x, b1y);
     HitAdj r;
     r.bx = bx; r.by = by; r.bvx = bvx; r.bvy = bvy; r.bax = bax; r.bay = bay;
     r.b1x = b1x; r.b1y = b1y; r.b1vx = b1vx; r.b1vy = b1vy;
@@ -322,6 +350,7 @@ __device__ __noinline__ HitAdj step_vjp_hit(float x, float y, float vx, float vy
 
 // free-flight part of the step adjoint, common to both branches (x1 = x + v1 dt, v1 = v + a dt, a = ...):
 // consumes the collision part's result (or the plain output cotangent) -> cotangent of the step input
+template <bool RCP = false>
 __device__ __forceinline__ void step_vjp_tail(const HitAdj& r, float vx, float vy, const Consts& c, float& gx,
                                               float& gy, float& gvx, float& gvy) {
     float bx = r.bx, by = r.by, bvx = r.bvx, bvy = r.bvy, bax = r.bax, bay = r.bay;
@@ -329,7 +358,7 @@ __device__ __forceinline__ void step_vjp_tail(const HitAdj& r, float vx, float v
     bx += r.b1x; by += r.b1y;
     bvx += tvx; bvy += tvy;
     bax += tvx * c.dt; bay += tvy * c.dt;
-    float amx = bax / c.m, amy = bay / c.m;
+    float amx = hdiv<RCP>(bax, c.m, c.rcp_m), amy = hdiv<RCP>(bay, c.m, c.rcp_m);
     bx += -2.0f * (c.ks * amx); by += -2.0f * (c.ks * amy);
     bvx += amx * dfric(vx, c); bvy += amy * dfric(vy, c);
     gx = bx; gy = by; gvx = bvx; gvy = bvy;
@@ -341,10 +370,11 @@ template <int N>
 __device__ __noinline__ void step_vjp_hit_n(float x, float y, float vx, float vy, float4 seg, const Consts c,
                                             float (&g)[N][4]) {
     const HitFwd f = hit_forward(x, y, vx, vy, seg, c);
+    const HitRcp rc = hit_reciprocals(f, seg, c);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const HitAdj r = hit_reverse(f, seg, c, g[k][0], g[k][1], g[k][2], g[k][3]);
-        step_vjp_tail(r, vx, vy, c, g[k][0], g[k][1], g[k][2], g[k][3]);
+        const HitAdj r = hit_reverse<true>(f, seg, c, g[k][0], g[k][1], g[k][2], g[k][3], rc);
+        step_vjp_tail<true>(r, vx, vy, c, g[k][0], g[k][1], g[k][2], g[k][3]);
     }
 }
 
