@@ -57,6 +57,11 @@ class RolloutOptions:
         # at collisions only); False: the backward replays from the K-step checkpoints instead
         self.hit_state_array = bool(hit_state_array)
 
+    def key(self) -> tuple:
+        return (self.ckpt_every, self.lanes_per_ball, self.force_exact_sweep, self.sequential_backward, self.smem_forward,
+                self.time_parallel, self.broad_phase, self.exact_index_log, self.broad_phase_time_parallel,
+                self.hit_state_array)
+
 
 _DEFAULT_OPTIONS = RolloutOptions()
 
@@ -267,16 +272,30 @@ class _HostPlan:
                      ptr(self.bufs.scratch), ptr(o[0:1]), ptr(o[4 + 8 * B:4 + 9 * B]), ptr(o[4:4 + 2 * B]),
                      ptr(o[4 + 2 * B:4 + 4 * B]), ptr(o[4 + 4 * B:4 + 6 * B]), ptr(o[4 + 6 * B:4 + 8 * B]))
 
+    _last: "_HostPlan" = None  # the previous call's plan + a cheap fingerprint of its arguments
+
     @classmethod
     def get(cls, device, scene, B, sim_time, n_steps, attractor, constants, target, opts):
+        # fast path: the same call as last time (the trainer's action loop) — compare values, not identities
+        # (a dict or array mutated in place must not hit), without building the full cache key
+        lp = cls._last
+        fp = (B, sim_time, n_steps, opts.key(), np.asarray(attractor).tobytes(), np.asarray(target).tobytes())
+        if lp is not None and lp.scene is scene and lp._fp == fp and lp._constants == constants and \
+                lp._device == device.index:
+            return lp
+        plan = cls._lookup(device, scene, B, sim_time, n_steps, attractor, constants, target, opts)
+        plan._fp, plan._constants, plan._device = fp, dict(constants), device.index
+        cls._last = plan
+        return plan
+
+    @classmethod
+    def _lookup(cls, device, scene, B, sim_time, n_steps, attractor, constants, target, opts):
         c = constants
         key = (device.index, id(scene), B, float(sim_time), int(n_steps),
                tuple(float(c[k]) if k in c else None for k in _CONST_KEYS), float(c.get("density", 0.0)),
                tuple(np.asarray(attractor, dtype=np.float64).ravel().tolist()),
                tuple(np.asarray(target, dtype=np.float64).ravel().tolist()),
-               opts.ckpt_every, opts.lanes_per_ball, opts.force_exact_sweep, opts.sequential_backward, opts.smem_forward,
-               opts.time_parallel, opts.broad_phase, opts.exact_index_log, opts.broad_phase_time_parallel,
-               opts.hit_state_array)
+               opts.key())
         plan = cls._cache.get(key)
         if plan is None or plan.scene is not scene:
             if len(cls._cache) > 16:
