@@ -6,7 +6,9 @@ import sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-H, U, V = rows[0], rows[1], rows[2]
+H, U = rows[0], rows[1]
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # which profiled launch of the report
+V = rows[2 + K]
 want = [
     "Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
     "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
