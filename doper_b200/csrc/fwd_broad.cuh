@@ -240,12 +240,13 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_tpc_kernel(const FwdParam
     if (__all_sync(0xffffffffu, !sc.weird)) j0 = hint_by_estimate<G>(sc, x, y, lane);
     GroupList gl;
     gl.e = lists + (size_t)slot * kTpcListCap; gl.cap = kTpcListCap; gl.cnt = 0;
-    gl.cx = 0.f; gl.cy = 0.f; gl.rho2 = -1.0f; gl.far2 = 0.f; gl.safe2 = -1.0f;
+    gl.cx = 0.f; gl.cy = 0.f; gl.rho2 = -1.0f; gl.far2 = 0.f; gl.safe2 = -1.0f; gl.emin = 0.f;
     const GridView grid = grid_view(p.scene_ws, L);
     const float rho_min = sc.scale * 0.001953125f, rho_max = sc.scale * 0.125f;
     int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
 #ifdef DOPER_PHASE_TIMERS
     long long phase_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long n_rounds = 0, n_refresh = 0;
     long long phase_t0 = clock64();
     int phase_cur = 7;
     float2* const traj_a_real = nullptr;
@@ -255,6 +256,9 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_tpc_kernel(const FwdParam
 
     while (__any_sync(0xffffffffu, t < n)) {
         DOPER_PHASE(0)
+#ifdef DOPER_PHASE_TIMERS
+        ++n_rounds;
+#endif
         // ---- (0) contact mode --------------------------------------------------------------------------
         // A ball that collided at the first step of its last round (resting / sliding contact) gains
         // nothing from speculation: it runs up to kContactSteps plain sequential steps here, every lane
@@ -328,9 +332,17 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_tpc_kernel(const FwdParam
             const float ddx = x - gl.cx, ddy = y - gl.cy;
             const bool want = alive && fast0 && (trouble == 1 || !(ddx * ddx + ddy * ddy <= 0.25f * gl.rho2));
             if (__any_sync(0xffffffffu, want)) {
+#ifdef DOPER_PHASE_TIMERS
+                ++n_refresh;
+#endif
                 if (want && exact_idx) j0 = glist_argmin(sc, x, y, gl, j0);  // seed of an argmin list
                 const float dstep = sqrtf(vx * vx + vy * vy) * c.dt;
-                const float rho = fminf(fmaxf(1.25f * (float)(kCullPeriod + 2 * G) * dstep, rho_min), rho_max);
+                float rho = 1.25f * (float)(kCullPeriod + 2 * G) * dstep;  // room for this many steps at the current speed
+                // ... or, in open space, most of the way to the nearest wall (known from the last scan, less what
+                // the ball has moved since): the hit list of such a disc is empty, the whole disc is safe, and
+                // the next scan is that much later.  Any rho is valid; this only picks a cheaper one.
+                if (!exact_idx) rho = fmaxf(rho, 0.7f * ((gl.emin - sqrtf(ddx * ddx + ddy * ddy)) - c.r));
+                rho = fminf(fmaxf(rho, rho_min), rho_max);
                 glist_refresh<G, GRID>(sc, grid, want ? x : 0.f, want ? y : 0.f, rho, c.r, lane, gbase, j0, want, gl, exact_idx);
             }
         }
@@ -442,6 +454,16 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_tpc_kernel(const FwdParam
     if ((threadIdx.x & 31) == 0 && p.traj_a) {
         unsigned long long* phase_out = reinterpret_cast<unsigned long long*>(p.traj_a);
         for (int k = 0; k < 8; ++k) atomicAdd(phase_out + k, (unsigned long long)phase_t[k]);
+        atomicAdd(phase_out + 8, (unsigned long long)n_rounds);
+        atomicAdd(phase_out + 9, (unsigned long long)n_refresh);
+        // per-warp record: [total cycles, rounds, refresh passes, list-refresh cycles]
+        const long long wid = ((long long)blockIdx.x * THREADS + threadIdx.x) >> 5;
+        long long tot = 0;
+        for (int k = 0; k < 8; ++k) tot += phase_t[k];
+        phase_out[16 + 4 * wid + 0] = (unsigned long long)tot;
+        phase_out[16 + 4 * wid + 1] = (unsigned long long)n_rounds;
+        phase_out[16 + 4 * wid + 2] = (unsigned long long)n_refresh;
+        phase_out[16 + 4 * wid + 3] = (unsigned long long)phase_t[1];
     }
 #endif
 }

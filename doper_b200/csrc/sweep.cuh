@@ -414,6 +414,7 @@ struct GroupList {
     // slack cover the roundings of the square root, of the difference and of |p - c|^2), capped by
     // rho2 (M bounds only points within rho of the centre); negative = no safe disc.
     float safe2;
+    float emin;  // that smallest estimate (0 before the first full scan): sizes the NEXT disc, a heuristic only
 };
 
 // Every lane of the warp calls (warp-wide ballots); `doit` is uniform within a group.  Segment
@@ -494,7 +495,9 @@ __device__ __forceinline__ void glist_refresh(const SceneView& sc, const GridVie
         gl.cnt = cnt; gl.cx = px; gl.cy = py;
         gl.rho2 = (kCullRhoCheck * rho) * (kCullRhoCheck * rho);
         gl.far2 = cull_far2(radius, M);
-        const float sigma = sqrtf(e2min) - __fmaf_rn(kCullSafePerM, M, radius) * kCullUp;
+        const float emin = sqrtf(e2min);
+        const float sigma = emin - __fmaf_rn(kCullSafePerM, M, radius) * kCullUp;
+        gl.emin = scanned_all ? emin : 0.0f;
         gl.safe2 = (scanned_all && sigma > 0.0f) ? fminf((sigma * sigma) * (1.0f - 9.5367431640625e-07f), gl.rho2) : -1.0f;
     }
 }

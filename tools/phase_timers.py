@@ -48,7 +48,7 @@ for regime, sigma in (("default", 10.0), ("reference_regime", 0.0)):
     desc = ball_sim._make_desc(B, scene, w["sim_time"], n, w["attractor"], w["constants"], ball_sim.RolloutOptions())
     bufs = ball_sim._Buffers.get(dev, desc)
     xT = torch.empty((B, 2), device=dev); vT = torch.empty((B, 2), device=dev)
-    dbg = torch.zeros(8, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(16 + 4 * ((B + 1) // 2 + 64), dtype=torch.int64, device=dev)
     for rep in range(3):
         dbg.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -57,10 +57,28 @@ for regime, sigma in (("default", 10.0), ("reference_regime", 0.0)):
                                     ptr(bufs.ws)), "fwd")
         b.record()
         torch.cuda.synchronize()
-    cyc = dbg.cpu().numpy().astype(np.float64)
+    raw = dbg.cpu().numpy().astype(np.float64)
+    cyc = raw[:8]
+    n_warps = (B + 1) // 2
+    per = raw[16:16 + 4 * n_warps].reshape(n_warps, 4)
+    hist = ball_sim.rollout_history(w["sim_time"], n, scene, w["x0"], w["v0"], w["attractor"], w["constants"])["hit"].sum(0)
+    speed = np.linalg.norm(w["v0"], axis=1)
+    order = np.argsort(-per[:, 0])[:12]
+    slow = [{"warp": int(k), "cycles": int(per[k, 0]), "rounds": int(per[k, 1]), "refresh_passes": int(per[k, 2]),
+             "refresh_cycles": int(per[k, 3]), "hits": [int(hist[2 * k]), int(hist[min(2 * k + 1, B - 1)])],
+             "speed": [round(float(speed[2 * k]), 1), round(float(speed[min(2 * k + 1, B - 1)]), 1)]} for k in order]
+    q = np.quantile(per[:, 0], [0.5, 0.9, 0.99, 1.0])
+    np.save(f"gpurun_out/phase_per_warp_{name}_{regime}.npy", per)
+    np.save(f"gpurun_out/phase_hits_{name}_{regime}.npy", hist)
     out[regime] = {"kernel_ms_with_timers": round(a.elapsed_time(b), 4),
                    "share_of_warp_cycles": {PHASES[k]: round(float(cyc[k] / cyc.sum()), 4) for k in range(8)},
-                   "mean_warp_cycles": round(float(cyc.sum() / ((B + 1) // 2)), 1)}
+                   "mean_warp_cycles": round(float(cyc.sum() / n_warps), 1),
+                   "warp_cycles_quantiles_50_90_99_100": [int(v) for v in q], "slowest_warps": slow,
+                   "corr_cycles_vs": {"rounds": round(float(np.corrcoef(per[:, 0], per[:, 1])[0, 1]), 3),
+                                      "refresh_passes": round(float(np.corrcoef(per[:, 0], per[:, 2])[0, 1]), 3),
+                                      "hits": round(float(np.corrcoef(per[:, 0], hist[0:2 * n_warps:2] + hist[1:2 * n_warps:2])[0, 1]), 3),
+                                      "speed": round(float(np.corrcoef(per[:, 0], speed[0:2 * n_warps:2] + speed[1:2 * n_warps:2])[0, 1]), 3)},
+                   "rounds_per_warp": round(float(raw[8] / n_warps), 2), "refresh_passes_per_warp": round(float(raw[9] / n_warps), 2)}
 print(json.dumps(out, indent=1))
 Path("gpurun_out").mkdir(exist_ok=True)
 Path(f"gpurun_out/phase_timers_{name}.json").write_text(json.dumps(out))
