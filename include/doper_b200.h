@@ -148,13 +148,15 @@ typedef struct {
                                       the backward then replays collided K-blocks from checkpoints);
                                bit 17: hit log holds the exact closest index at EVERY step (the
                                       broad-phase kernel otherwise logs it at collisions only and 0
-                                      elsewhere: the index is consumed at collisions only).
+                                      elsewhere: the index is consumed at collisions only); the
+                                      candidate lists then hold the argmin of every point of their
+                                      disc instead of just the segments the ball can touch (slower).
                                None of these changes x_T, v_T, trajectories, hit flags, collision
                                indices or gradients. */
 } doper_rollout_desc;
 
 /* The checkpoint period the library will use for this rollout (ckpt_every if > 0, else chosen
- * from B and n_steps: small batches get <= 32 chunks per ball for the chunk-parallel backward). */
+ * from B and n_steps: small batches get 32 or 64 chunks per ball for the chunk-parallel backward). */
 int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d);
 
 /* Layout of the hit log inside the workspace: 0 = [n_steps][B] (step-major), 1 = [B][n_steps]
