@@ -222,7 +222,12 @@ def ours(args):
     peer = None
     if world > 1 and not args.nccl:
         from doper_b200.distributed import PeerAllReducer
-        peer = PeerAllReducer(6602 + 1, device)  # one-shot all-reduce over NVLink peer memory (csrc/peer.cuh)
+        try:
+            peer = PeerAllReducer(6602 + 1, device)  # one-shot all-reduce over NVLink peer memory (csrc/peer.cuh)
+        except RuntimeError as e:  # no CUDA IPC between these GPUs (raised on every rank together): NCCL
+            if rank == 0:
+                print(f"bench: peer-memory all-reduce unavailable, using NCCL ({e})", file=sys.stderr)
+            peer = None
 
     def exchange():
         # the optimiser step needs the reduced gradient: the exchange is on the step's critical path

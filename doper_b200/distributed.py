@@ -57,8 +57,14 @@ class PolicyGradReducer:
         self.buf = torch.zeros(self.numel + 1, dtype=torch.float32, device=device)
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if transport == "auto":
-            transport = "nvlink" if (multi and torch.device(device).type == "cuda") else "collective"
-        self.peer = PeerAllReducer(self.numel + 1, torch.device(device)) if (transport == "nvlink" and multi) else None
+            transport = "auto-nvlink" if (multi and torch.device(device).type == "cuda") else "collective"  # falls back
+        self.peer = None
+        if transport in ("nvlink", "auto-nvlink") and multi:
+            try:
+                self.peer = PeerAllReducer(self.numel + 1, torch.device(device))
+            except RuntimeError:
+                if transport == "nvlink":  # asked for explicitly: do not fall back silently
+                    raise
 
     @torch.no_grad()
     def reduce(self, local_loss) -> torch.Tensor:
@@ -109,23 +115,39 @@ class PeerAllReducer:
         if self.world > 16:
             raise ValueError("PeerAllReducer: at most 16 ranks")
         torch.cuda.set_device(device)
-        own = ctypes.c_void_p()
+        self._own, self._opened = None, []
+        self._ptrs = (ctypes.c_void_p * self.world)()
         handle = ctypes.create_string_buffer(64)
-        check(lib.doper_peer_alloc(self.n, ctypes.byref(own), handle), "doper_peer_alloc")
-        self._own = own.value
+        err = None
+        try:
+            own = ctypes.c_void_p()
+            check(lib.doper_peer_alloc(self.n, ctypes.byref(own), handle), "doper_peer_alloc")
+            self._own = own.value
+        except Exception as e:  # still take part in the collectives below: the group must fail together
+            err = e
         mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
         gathered = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(gathered, mine)
-        self._ptrs = (ctypes.c_void_p * self.world)()
-        self._opened = []
-        for r, h in enumerate(gathered):
-            if r == self.rank:
-                self._ptrs[r] = self._own
-                continue
-            p = ctypes.c_void_p()
-            check(lib.doper_peer_open(bytes(h.cpu().tolist()), ctypes.byref(p)), "doper_peer_open")
-            self._ptrs[r] = p.value
-            self._opened.append(p.value)
+        if err is None:
+            try:
+                if os.environ.get("DOPER_PEER_FORCE_FAIL") == str(self.rank):
+                    raise RuntimeError("forced failure (DOPER_PEER_FORCE_FAIL)")
+                for r, h in enumerate(gathered):
+                    if r == self.rank:
+                        self._ptrs[r] = self._own
+                        continue
+                    p = ctypes.c_void_p()
+                    check(lib.doper_peer_open(bytes(h.cpu().tolist()), ctypes.byref(p)), "doper_peer_open")
+                    self._ptrs[r] = p.value
+                    self._opened.append(p.value)
+            except Exception as e:
+                err = e
+        # every rank learns whether EVERY rank mapped all its peers; otherwise all of them give up together
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            self.close(barrier=False)
+            raise RuntimeError(f"PeerAllReducer: peer memory is not available on every rank ({err or 'another rank failed'})")
         self.out = torch.empty(self.n, dtype=torch.float32, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         dist.barrier(device_ids=[device.index])  # every peer mapping exists before the first kernel
@@ -144,9 +166,9 @@ class PeerAllReducer:
                                                       self.status.data_ptr()), "doper_allreduce_oneshot")
         return out
 
-    def close(self) -> None:
+    def close(self, barrier: bool = True) -> None:
         torch.cuda.synchronize(self.device)
-        if dist.is_initialized():
+        if barrier and dist.is_initialized():
             dist.barrier(device_ids=[self.device.index])  # nobody unmaps while a peer may still read
         for p in self._opened:
             self._lib.doper_peer_close(p)
