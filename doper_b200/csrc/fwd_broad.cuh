@@ -179,6 +179,13 @@ __global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED && !GRID) ? 7 :
 // round starts after it.  The per-step critical path is the free-flight chain (~100 cycles)
 // instead of chain + sweep + reduction.  A ball that keeps colliding shrinks its speculation
 // length to one step.  Results are bit-identical to every other forward kernel.
+// The list is rebuilt once the ball has drifted sqrt(kTpcRefreshAt) * 0.98 rho from its centre: the disc is
+// sized for kCullPeriod + 2 G steps, so at 0.67 of it there are still ~1.3 G steps of room for the round that
+// is about to be speculated (a round that runs out of the disc is wasted).
+#ifndef DOPER_TPC_REFRESH_AT
+#define DOPER_TPC_REFRESH_AT 0.45f
+#endif
+constexpr float kTpcRefreshAt = DOPER_TPC_REFRESH_AT;
 constexpr int kTpcListCap = 64;
 constexpr int kContactSteps = 16;  // sequential steps per round of a ball in contact mode
 
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_tpc_kernel(const FwdParam
             const float M0 = fmaxf(sc.scale, fmaxf(fabsf(x), fabsf(y)));
             const bool fast0 = !sc.weird && M0 <= 1.0e15f;
             const float ddx = x - gl.cx, ddy = y - gl.cy;
-            const bool want = alive && fast0 && (trouble == 1 || !(ddx * ddx + ddy * ddy <= 0.25f * gl.rho2));
+            const bool want = alive && fast0 && (trouble == 1 || !(ddx * ddx + ddy * ddy <= kTpcRefreshAt * gl.rho2));
             if (__any_sync(0xffffffffu, want)) {
 #ifdef DOPER_PHASE_TIMERS
                 ++n_refresh;
