@@ -329,11 +329,15 @@ __device__ __forceinline__ float cull_far2(float radius, float M) {
 // min of a non-negative float over the G lanes of a group (every lane of the warp calls)
 template <int G>
 __device__ __forceinline__ float group_min_f(float v) {
-    if (G == 1) return v;
-    if (G == 32) return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));  // v >= +0: bit order = value order
+    if constexpr (G == 1) {
+        return v;
+    } else if constexpr (G == 32) {
+        return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));  // v >= +0: bit order = value order
+    } else {
 #pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, off));
-    return v;
+        for (int off = G / 2; off > 0; off >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, off));
+        return v;
+    }
 }
 
 // smallest estimate over this lane's share of the list (all its segments when the share overflowed)
