@@ -40,6 +40,14 @@ def workload_label(name, B, S, n_steps, per_env):
     return f"{name}: {B} balls x {n_steps} steps, {scene}, rollout fwd + L1 loss + bwd"
 
 
+def config_block(name, B, S, n_steps, per_env, args):
+    """`config` of the JSON line: the workload only, identical for both arms of one command line."""
+    return {"workload": workload_label(name, B, S, n_steps, per_env) +
+            (" [reference regime: v0 = U(-1,2)^2, no impulse stand-in]" if args.reference_regime else ""),
+            "balls_per_gpu": int(B), "sim_steps": int(n_steps), "segments": int(S), "per_env_maps": bool(per_env),
+            "l2": "256 MiB buffer rewritten between timed iterations (flush), outside the event pairs"}
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's C restatement on the host cores
 # ------------------------------------------------------------------------------------------------
@@ -243,7 +251,7 @@ def ours(args):
 
     def loss_bwd():
         check(lib.doper_l1_loss(st, B, ptr(xT), tgt, ptr(lpb), ptr(loss_sum), ptr(bufs.scratch)), "loss")
-        check(lib.doper_rollout_bwd(st, dref, ptr(sws), ptr(bufs.ws), ptr(bufs.scratch), 0, ptr(gx), ptr(gv)),
+        check(lib.doper_rollout_bwd(st, dref, ptr(sws), ptr(bufs.ws), ptr(bufs.bwd_scratch), ptr(bufs.scratch), 0, ptr(gx), ptr(gv)),
               "bwd")
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
@@ -428,14 +436,15 @@ def reference(args):
         w["n_steps"], w["sim_time"] = args.sim_steps, args.sim_steps / 1000.0
     sample, what = bounded_sample(w)
     S = int(w["segments"].shape[-3])
-    r = cpu_reference_run(sample, steps=args.steps, warmup=max(1, min(args.warmup, 3)))
+    r = cpu_reference_run(sample, steps=args.steps, warmup=args.warmup)  # exactly --warmup untimed, --steps timed
     line = {
         "impl": "reference", "metric": METRIC, "value": round(r["value"], 1), "unit": UNIT,
-        "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(1, min(args.warmup, 3)),
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
         "ms_per_step": round(r["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_label(name, per_gpu, S, w["n_steps"], bool(w["per_env"])) +
-                   (" [reference regime: v0 = U(-1,2)^2, no impulse stand-in]" if args.reference_regime else "")},
+        # the same `config` object as the product arm prints for this command line (kernel-plan details of
+        # the product arm live under its own `plan` key)
+        "config": config_block(name, per_gpu, S, w["n_steps"], bool(w["per_env"]), args),
         "cpu_baseline": {"value": round(r["value"], 1), "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": f"each step = {what}; oracle/ball_sim_ref.c {r['flavour']} + OpenMP on all host "
                                    f"cores (restated reference: the reference is JAX/XLA:CPU, not installable here)"},

@@ -15,12 +15,12 @@ import os
 # DOPER_B200_LIB points the binding at another build of the same library (kernel A/B tuning)
 LIB_PATH = Path(os.environ.get("DOPER_B200_LIB") or (Path(__file__).resolve().parent / "_lib" / "libdoper_b200.so"))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "doper_abi_version", "doper_error_string", "doper_scene_workspace_bytes", "doper_scene_prepare",
     "doper_closest_segment", "doper_points_inside", "doper_rollout_ckpt_every", "doper_rollout_log_ball_major",
-    "doper_rollout_workspace_bytes", "doper_rollout_plan_name",
+    "doper_rollout_workspace_bytes", "doper_rollout_bwd_scratch_bytes", "doper_rollout_plan_name",
     "doper_rollout_fwd", "doper_rollout_bwd", "doper_l1_loss", "doper_value_and_grad",
     "doper_fp32_probe",
     "doper_ray_segment_points", "doper_range_sensor", "doper_agent_observations",
@@ -43,6 +43,7 @@ class RolloutDesc(ctypes.Structure):
         ("attractor", c_float * 2),
         ("lanes_per_ball", c_int32),
         ("flags", c_int32),
+        ("hit_capacity", c_int64),
     ]
 
 
@@ -82,10 +83,12 @@ def _load() -> ctypes.CDLL:
     lib.doper_rollout_plan_name.argtypes = [POINTER(RolloutDesc), c_int32]
     lib.doper_rollout_workspace_bytes.restype = c_size_t
     lib.doper_rollout_workspace_bytes.argtypes = [POINTER(RolloutDesc)]
+    lib.doper_rollout_bwd_scratch_bytes.restype = c_size_t
+    lib.doper_rollout_bwd_scratch_bytes.argtypes = [POINTER(RolloutDesc)]
     lib.doper_rollout_fwd.argtypes = [vp, POINTER(RolloutDesc), vp, fp, fp, fp, fp, fp, fp, fp, vp]
-    lib.doper_rollout_bwd.argtypes = [vp, POINTER(RolloutDesc), vp, vp, fp, fp, fp, fp]
+    lib.doper_rollout_bwd.argtypes = [vp, POINTER(RolloutDesc), vp, vp, vp, fp, fp, fp, fp]
     lib.doper_l1_loss.argtypes = [vp, c_int64, fp, POINTER(c_float), fp, fp, fp]
-    lib.doper_value_and_grad.argtypes = [vp, POINTER(RolloutDesc), vp, fp, fp, POINTER(c_float), vp, fp,
+    lib.doper_value_and_grad.argtypes = [vp, POINTER(RolloutDesc), vp, fp, fp, POINTER(c_float), vp, vp, fp,
                                          fp, fp, fp, fp, fp, fp]
     lib.doper_fp32_probe.argtypes = [vp, c_int32, c_int32, c_int32, c_int32, fp]
     lib.doper_ray_segment_points.argtypes = [vp, c_int64, c_int32, fp, fp, fp, fp]
@@ -101,7 +104,7 @@ def _load() -> ctypes.CDLL:
     lib.doper_allreduce_oneshot.argtypes = [vp, c_int32, c_int32, POINTER(c_void_p), c_int32, fp, fp, vp]
     for name in EXPORTS:
         if name not in ("doper_peer_buffer_bytes", "doper_error_string", "doper_scene_workspace_bytes",
-                        "doper_rollout_workspace_bytes", "doper_abi_version", "doper_rollout_ckpt_every",
+                        "doper_rollout_workspace_bytes", "doper_rollout_bwd_scratch_bytes", "doper_abi_version", "doper_rollout_ckpt_every",
                         "doper_rollout_log_ball_major", "doper_rollout_plan_name"):
             getattr(lib, name).restype = ctypes.c_int
     if lib.doper_abi_version() != ABI_VERSION:

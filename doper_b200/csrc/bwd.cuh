@@ -1,12 +1,26 @@
-// bwd.cuh: backward rollout kernels (sequential, chunk-parallel) — part of the doper_b200 CUDA translation unit (included by kernels.cu).
+// bwd.cuh: backward rollout kernels — part of the doper_b200 CUDA translation unit (included by kernels.cu).
+//
+//   rollout_bwd_kernel           sequential, one thread per ball, fp32 in the oracle's operation order
+//                                (bit-exact vs oracle/ball_sim_step.inc:step_vjp); flags bit 1
+//   rollout_bwd_jacobian_kernel  default plan, pass 1: one thread per COLLISION RECORD -> the 4x4 transposed
+//   rollout_bwd_fold_kernel      Jacobian of that step in binary64; pass 2: one thread per (ball, chunk of
+//                                steps) multiplies the chunk's step Jacobians in binary64 (free-flight steps
+//                                from the two clip bits of the log word alone, collided steps from pass 1),
+//                                then the chunks of a ball are folded onto the output cotangent.
+//
+// Why binary64 for the default plan.  Re-associating the chain of step Jacobians (which any time-parallel
+// backward must do) changes the rounding order, so an fp32 chunked product can be neither bit-identical to
+// the reference-order fp32 adjoint nor provably closer to the true derivative than it.  In binary64 the
+// product is the adjoint of the real-arithmetic step evaluated on the fp32 trajectory to ~1e-15 — the
+// quantity oracle_grad_truth64 (oracle/ball_sim_ref.c) defines as gradient truth — so its distance from the
+// reference-order fp32 adjoint IS that adjoint's own rounding error, and it is never further from truth
+// than the reference's arithmetic is.  B200 issues 64 DFMA per SM per clock (half the FP32 rate): the whole
+// C2 backward is ~50 M DFMA, microseconds of pipe time.
 #pragma once
 #include "scene.cuh"
 
 namespace doper {
 
-// ------------------------------------------------------------------------------------------
-// backward rollout
-// ------------------------------------------------------------------------------------------
 constexpr int kBwdThreads = 128;
 
 struct BwdParams {
@@ -14,38 +28,62 @@ struct BwdParams {
     int S, per_env, n_steps, K;
     Consts c;
     const unsigned char* scene_ws;
-    const float4* ckpt;
-    const float4* hitstate;  // nullable: [n_steps][B] states at the start of collided steps
-    const int32_t* hitlog;  // element (t, ball) at t * hl_st + ball * hl_sb
+    const float4* ckpt;      // [n_ckpt][B] state at the start of step k K (replay fallback only)
+    const HitRecord* rec;    // collision records appended by the forward (nullable)
+    const int* rec_count;    // device counter of the forward
+    int rec_cap;
+    double* jac;             // [rec_cap][16] pass-1 output: row-major 4x4, new_g = Jt g (caller's bwd scratch)
+    const int32_t* hitlog;   // element (t, ball) at t * hl_st + ball * hl_sb
     int64_t hl_st, hl_sb;
     const float2* xT_bar;
     const float2* vT_bar;  // nullable
     float2* x0_bar;        // nullable
     float2* v0_bar;
-    // hybrid plan of the sequential kernel: a ball that has pulled back more than defer_after collided
-    // steps (sliding contact: a ~2.6 us serial chain per step) appends itself to `deferred` ([0] = count,
-    // then ball ids) and leaves; rollout_bwd_chunked_kernel then redoes those balls 32 chunks in parallel
-    int* deferred;         // nullable
-    int defer_after;
 };
 
-constexpr int kDeferCap = 2048;  // deferred balls per launch; beyond it balls simply stay sequential
+__device__ __forceinline__ const float4* scene_q(const BwdParams& p, int64_t ball) {
+    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
+    return reinterpret_cast<const float4*>(p.scene_ws + L.q_off) + (p.per_env ? (size_t)ball * L.S_pad : 0);
+}
 
-// Sequential backward, one thread per ball, bit-exact against the oracle's adjoint.  A step that
-// did not collide is pulled back from its log word alone (step_vjp_free: no state, no replay);
-// only a K-block that contains a collision is replayed from its checkpoint (with the logged
-// indices), up to its last collision, into the shared-memory stash.
+__device__ __forceinline__ const float2* scene_s1(const BwdParams& p, int64_t ball) {
+    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
+    return reinterpret_cast<const float2*>(p.scene_ws + L.s1_off) + (p.per_env ? (size_t)ball * L.S_pad : 0);
+}
+
+// segment index of a collided step from its log word
+__device__ __forceinline__ int hit_segment(const BwdParams& p, int32_t h) {
+    const uint32_t w = (uint32_t)h;
+    return (w & kLogNoRecord) ? (int)(w & kLogSeg) : p.rec[w & kLogSeg].idx;
+}
+
+// State at the start of step t of `ball`, replayed from the last checkpoint at or before t (bit-identical
+// to the forward: same device functions, logged segment indices).  Slow path: used only for collided steps
+// whose record could not be stored.
+__device__ __noinline__ float4 replay_state(const BwdParams& p, int64_t ball, int t, const float4* q) {
+    const int ck = t / p.K;
+    float4 s = p.ckpt[(size_t)ck * p.B + ball];
+    const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
+    for (int u = ck * p.K; u < t; ++u) {
+        const int32_t hu = hl[(size_t)u * p.hl_st];
+        State s1;
+        free_step(s.x, s.y, s.z, s.w, p.c, s1);
+        if (hu < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + hit_segment(p, hu)), p.c);
+        s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// sequential backward (oracle order, bit-exact)
+// ------------------------------------------------------------------------------------------
 constexpr int kBwdPrefetch = 16;  // log words fetched ahead per thread (independent loads in flight)
 
 __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    float4* stash = reinterpret_cast<float4*>(smem);  // [K][kBwdThreads], replay fallback only
     const int tid = threadIdx.x;
     const int64_t ball = (int64_t)blockIdx.x * kBwdThreads + tid;
     if (ball >= p.B) return;
-    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
-    const float4* q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) +
-                      (p.per_env ? (size_t)ball * L.S_pad : 0);
+    const float4* q = scene_q(p, ball);
     const Consts c = p.c;
     const float dk = dfric_value(c);
     float2 g = p.xT_bar[ball];
@@ -53,15 +91,218 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
     if (p.vT_bar) { float2 h = p.vT_bar[ball]; gvx = h.x; gvy = h.y; }
     const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
 
-    const int n_ckpt = (p.n_steps + p.K - 1) / p.K;
-    int collided = 0;
-    for (int ck = n_ckpt - 1; ck >= 0; --ck) {
-        const int t0 = ck * p.K, t1 = min(p.n_steps, t0 + p.K);
-        int have = -1;  // states of steps t0 .. t0 + have are in the stash
+    for (int tb = p.n_steps; tb > 0;) {
+        // the log words of steps [ta, tb): kBwdPrefetch independent loads, then a latency-free loop
+        const int ta = max(0, tb - kBwdPrefetch);
+        // condensed into three bit masks (bit j = step ta + j), so the processing loop stays compact
+        unsigned m_hit = 0u, m_cx = 0u, m_cy = 0u;
+#pragma unroll
+        for (int j = 0; j < kBwdPrefetch; ++j) {
+            const uint32_t w = (ta + j < tb) ? (uint32_t)hl[(size_t)(ta + j) * p.hl_st] : 0u;
+            m_hit |= (w >> 31) << j;
+            m_cx |= ((w >> 29) & 1u) << j;
+            m_cy |= ((w >> 30) & 1u) << j;
+        }
+        for (int t = tb - 1; t >= ta; --t) {
+            const int j = t - ta;
+            if (!((m_hit >> j) & 1u)) {
+                step_vjp_free_1d(((m_cx >> j) & 1u) != 0u, dk, c, gx, gvx);
+                step_vjp_free_1d(((m_cy >> j) & 1u) != 0u, dk, c, gy, gvy);
+                continue;
+            }
+            const uint32_t h = (uint32_t)hl[(size_t)t * p.hl_st];  // collided step: the payload is needed (rare reload)
+            float4 st;
+            int idx;
+            if (h & kLogNoRecord) {
+                idx = (int)(h & kLogSeg);
+                st = replay_state(p, ball, t, q);
+            } else {
+                const float4* r = reinterpret_cast<const float4*>(p.rec + (h & kLogSeg));
+                st = r[0];
+                idx = reinterpret_cast<const int4*>(r)[1].z;
+            }
+            step_vjp(st.x, st.y, st.z, st.w, true, __ldg(q + idx), c, gx, gy, gvx, gvy);
+        }
+        tb = ta;
+    }
+    p.v0_bar[ball] = make_float2(gvx, gvy);
+    if (p.x0_bar) p.x0_bar[ball] = make_float2(gx, gy);
+}
+
+// ------------------------------------------------------------------------------------------
+// binary64 adjoint of a collided step
+// ------------------------------------------------------------------------------------------
+struct ConstsD {
+    double r, m, f, e, ks, g, ax, ay, dt;
+    double dk;    // d fric / d v inside the clip: -(((m g) f) / r)
+    double a_p;   // free flight, per axis: gp' = gp + a_p tv,  a_p = -2 ks dt / m
+    double a_v;   // gv' = tv + (clip active ? a_v : 0) tv,     a_v = dk dt / m
+};
+
+__device__ __forceinline__ ConstsD make_consts_d(const Consts& c) {
+    ConstsD d;
+    d.r = c.r; d.m = c.m; d.f = c.f; d.e = c.e; d.ks = c.ks; d.g = (double)9.8f;  // the reference's literal, as f32
+    d.ax = c.ax; d.ay = c.ay; d.dt = c.dt;
+    d.dk = -(((d.m * d.g) * d.f) / d.r);
+    d.a_p = -2.0 * d.ks * (d.dt / d.m);
+    d.a_v = d.dk * (d.dt / d.m);
+    return d;
+}
+
+__device__ __forceinline__ double clip_d(double x, double lo, double hi) {
+    if (x != x) return x;
+    x = x < lo ? lo : x;
+    return x > hi ? hi : x;
+}
+
+__device__ __forceinline__ double fric_d(double v, const ConstsD& c) {
+    return ((((-clip_d(v, -1.0, 1.0)) * c.m) * c.g) * c.f) / c.r;
+}
+
+__device__ __forceinline__ double sgn_d(double a) { return a > 0.0 ? 1.0 : (a < 0.0 ? -1.0 : 0.0); }
+
+// Jt (row-major 4x4 over (x, y, vx, vy)): cotangent of the step OUTPUT -> cotangent of the step INPUT, for a
+// step that collided with the segment s0 = (q.x, q.y) -> s1, starting from the fp32 state st.  The formulas of
+// oracle/ball_sim_step.inc:step_vjp in binary64, the segment direction included
+// (s1 - s0 in binary64, like oracle_grad_truth64); column k = the pull-back of e_k.
+__device__ __noinline__ void hit_jacobian_d(const float4 st, const float4 q, const float2 s1, const ConstsD c,
+                                            double* __restrict__ Jt) {
+    const double x = st.x, y = st.y, vx = st.z, vy = st.w;
+    const double s0x = q.x, s0y = q.y, svx = (double)s1.x - (double)q.x, svy = (double)s1.y - (double)q.y;
+    const double L = svx * svx + svy * svy;
+    // free-flight candidate (ball_sim.py:192-202)
+    const double ppx = -(2.0 * (x - c.ax)), ppy = -(2.0 * (y - c.ay));
+    const double a1x = (c.ks * ppx + fric_d(vx, c)) / c.m, a1y = (c.ks * ppy + fric_d(vy, c)) / c.m;
+    const double v1x = vx + a1x * c.dt, v1y = vy + a1y * c.dt;
+    const double x1x = x + v1x * c.dt, x1y = y + v1y * c.dt;
+    // resolve_collision internals (ball_sim.py:97-132)
+    const double t1 = clip_d(((x1x - s0x) * svx + (x1y - s0y) * svy) / L, 0.0, 1.0);
+    const double ox = (s0x + t1 * svx) - x, oy = (s0y + t1 * svy) - y;
+    const double od = sqrt(ox * ox + oy * oy);
+    const double nx = ox / od, ny = oy / od;
+    const double s = nx * v1x + ny * v1y;
+    const double den = fabs(s);
+    const double toi_raw = fabs(od - c.r) / den;
+    const double toi = clip_d(toi_raw, 0.0, c.dt);
+    const double vsx = vx + a1x * toi, vsy = vy + a1y * toi;
+    const double xsx = x + vsx * toi, xsy = y + vsy * toi;
+    const double t2 = clip_d(((xsx - s0x) * svx + (xsy - s0y) * svy) / L, 0.0, 1.0);
+    const double o2x = (s0x + t2 * svx) - xsx, o2y = (s0y + t2 * svy) - xsy;
+    const double o2d = sqrt(o2x * o2x + o2y * o2y);
+    const double n2x = o2x / o2d, n2y = o2y / o2d;
+    const double k = n2x * vsx + n2y * vsy;
+    const double vnx = n2x * k, vny = n2y * k;
+    const double vax = (vsx - vnx) - c.e * vnx, vay = (vsy - vny) - c.e * vny;
+    const double pbx = -(2.0 * (xsx - c.ax)), pby = -(2.0 * (xsy - c.ay));
+    const double abx = (pbx + fric_d(vax, c)) / c.m, aby = (pby + fric_d(vay, c)) / c.m;
+    const double tau = c.dt - toi;
+    const double vbx = vax + abx * tau, vby = vay + aby * tau;
+    const double dfax = (vax > -1.0 && vax < 1.0) ? c.dk : 0.0, dfay = (vay > -1.0 && vay < 1.0) ? c.dk : 0.0;
+    const double dfx = (vx > -1.0 && vx < 1.0) ? c.dk : 0.0, dfy = (vy > -1.0 && vy < 1.0) ? c.dk : 0.0;
+    const bool in1 = t1 > 0.0 && t1 < 1.0, in2 = t2 > 0.0 && t2 < 1.0, raw_in = toi_raw > 0.0 && toi_raw < c.dt;
+    const double sg_od = sgn_d(od - c.r), sg_s = sgn_d(s);
+#pragma unroll 1
+    for (int col = 0; col < 4; ++col) {
+        const double gx = col == 0 ? 1.0 : 0.0, gy = col == 1 ? 1.0 : 0.0;
+        const double gvx = col == 2 ? 1.0 : 0.0, gvy = col == 3 ? 1.0 : 0.0;
+        double bx = 0.0, by = 0.0, bvx = 0.0, bvy = 0.0, bax = 0.0, bay = 0.0;
+        const double gvbx = gvx + gx * tau, gvby = gvy + gy * tau;
+        double gxsx = gx, gxsy = gy;
+        const double gtau = (gx * vbx + gy * vby) + (gvbx * abx + gvby * aby);
+        double gvax = gvbx, gvay = gvby;
+        const double gabx = gvbx * tau, gaby = gvby * tau;
+        gxsx += -2.0 * (gabx / c.m); gxsy += -2.0 * (gaby / c.m);
+        gvax += (gabx / c.m) * dfax; gvay += (gaby / c.m) * dfay;
+        double gtoi = -gtau;
+        double gvsx = gvax, gvsy = gvay;
+        const double gvnx = -(1.0 + c.e) * gvax, gvny = -(1.0 + c.e) * gvay;
+        const double gk = gvnx * n2x + gvny * n2y;
+        const double gn2x = gvnx * k + gk * vsx, gn2y = gvny * k + gk * vsy;
+        gvsx += gk * n2x; gvsy += gk * n2y;
+        const double nd = n2x * gn2x + n2y * gn2y;
+        const double go2x = (gn2x - n2x * nd) / o2d, go2y = (gn2y - n2y * nd) / o2d;
+        const double j2 = in2 ? (go2x * svx + go2y * svy) / L : 0.0;
+        gxsx += j2 * svx - go2x; gxsy += j2 * svy - go2y;
+        bx += gxsx; by += gxsy;
+        gvsx += gxsx * toi; gvsy += gxsy * toi;
+        gtoi += gxsx * vsx + gxsy * vsy;
+        bvx += gvsx; bvy += gvsy;
+        bax += gvsx * toi; bay += gvsy * toi;
+        gtoi += gvsx * a1x + gvsy * a1y;
+        const double graw = raw_in ? gtoi : 0.0;
+        const double gnum = graw / den;
+        const double gden = -(graw * toi_raw) / den;
+        const double god = gnum * sg_od;
+        const double gs = gden * sg_s;
+        const double gnx = gs * v1x, gny = gs * v1y;
+        const double b1vx = gs * nx, b1vy = gs * ny;
+        const double nd1 = nx * gnx + ny * gny;
+        const double gox = (gnx - nx * nd1) / od + god * nx, goy = (gny - ny * nd1) / od + god * ny;
+        bx -= gox; by -= goy;
+        const double j1 = in1 ? (gox * svx + goy * svy) / L : 0.0;
+        const double b1x = j1 * svx, b1y = j1 * svy;
+        // common tail: x1 = x + v1 dt ; v1 = v + a dt ; a = (ks pot + fric(v)) / m
+        const double tvx = b1vx + b1x * c.dt, tvy = b1vy + b1y * c.dt;
+        bx += b1x; by += b1y;
+        bvx += tvx; bvy += tvy;
+        bax += tvx * c.dt; bay += tvy * c.dt;
+        const double amx = bax / c.m, amy = bay / c.m;
+        bx += -2.0 * (c.ks * amx); by += -2.0 * (c.ks * amy);
+        bvx += amx * dfx; bvy += amy * dfy;
+        Jt[0 * 4 + col] = bx; Jt[1 * 4 + col] = by; Jt[2 * 4 + col] = bvx; Jt[3 * 4 + col] = bvy;
+    }
+}
+
+// pass 1: one thread per collision record (grid-stride)
+__global__ void __launch_bounds__(128) rollout_bwd_jacobian_kernel(const BwdParams p) {
+    const int n = min(*p.rec_count, p.rec_cap);
+    const ConstsD cd = make_consts_d(p.c);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4* r = reinterpret_cast<const float4*>(p.rec + i);
+        const float4 st = r[0];
+        const int4 m = reinterpret_cast<const int4*>(r)[1];
+        const int64_t ball = ((int64_t)m.w << 32) | (uint32_t)m.x;
+        double J[16];
+        hit_jacobian_d(st, __ldg(scene_q(p, ball) + m.z), __ldg(scene_s1(p, ball) + m.z), cd, J);
+        double2* out = reinterpret_cast<double2*>(p.jac + (size_t)i * 16);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k] = make_double2(J[2 * k], J[2 * k + 1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pass 2: chunk products + fold
+// ------------------------------------------------------------------------------------------
+// Thread (lane = ball, warp = chunk): pulls the four basis cotangents e_0..e_3 back through its chunk of
+// `chunk_len` steps, g[k] <- J_t^T g[k] for t descending, which leaves column k of the chunk's transposed
+// Jacobian P_c in g[k].  Until the chunk meets a collision, x and y are decoupled (free flight acts on the
+// (position, velocity) pair of each axis separately), so only the 8 entries that can be non-zero are updated:
+// 12 DFMA per step; 24 once a collision has coupled the axes; a collided step is one 4x4 x 4x4 product with
+// the matrix of pass 1.  The block then folds v <- P_c v from the last chunk to the first through shared
+// memory (warp 0, one lane per ball).  With lane = ball the loads of a step-major hit log ([n_steps][B], the
+// lane-split forward kernels) are coalesced; a ball-major log ([B][n_steps], lane = step forward kernels) is
+// read in per-lane runs that the L1 keeps.
+constexpr int kFoldMaxChunks = 16;  // 512 threads per block: 128 registers per thread (the 4x4 binary64 product needs ~90)
+
+__global__ void __launch_bounds__(32 * kFoldMaxChunks) rollout_bwd_fold_kernel(const BwdParams p, const int n_chunks,
+                                                                              const int chunk_len) {
+    extern __shared__ __align__(16) unsigned char fold_smem[];
+    double* sm = reinterpret_cast<double*>(fold_smem);  // [n_chunks][16][32]
+    const int lane = threadIdx.x & 31, chunk = threadIdx.x >> 5;
+    const int64_t ball = (int64_t)blockIdx.x * 32 + lane;
+    const bool active = ball < p.B;
+    const ConstsD cd = make_consts_d(p.c);
+    double g[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0 : 0.0;
+    const int t0 = chunk * chunk_len, t1 = min(p.n_steps, t0 + chunk_len);
+    if (active && t0 < t1) {
+        const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
+        bool coupled = false;
         for (int tb = t1; tb > t0;) {
-            // the log words of steps [ta, tb): kBwdPrefetch independent loads, then a latency-free loop
             const int ta = max(t0, tb - kBwdPrefetch);
-            // condensed into three bit masks (bit j = step ta + j), so the processing loop stays compact
             unsigned m_hit = 0u, m_cx = 0u, m_cy = 0u;
 #pragma unroll
             for (int j = 0; j < kBwdPrefetch; ++j) {
@@ -73,192 +314,76 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const BwdParam
             for (int t = tb - 1; t >= ta; --t) {
                 const int j = t - ta;
                 if (!((m_hit >> j) & 1u)) {
-                    step_vjp_free_1d(((m_cx >> j) & 1u) != 0u, dk, c, gx, gvx);
-                    step_vjp_free_1d(((m_cy >> j) & 1u) != 0u, dk, c, gy, gvy);
+                    const double avx = ((m_cx >> j) & 1u) ? cd.a_v : 0.0, avy = ((m_cy >> j) & 1u) ? cd.a_v : 0.0;
+                    if (!coupled) {
+#pragma unroll
+                        for (int k = 0; k < 4; k += 2) {  // columns 0, 2 live on (x, vx); columns 1, 3 on (y, vy)
+                            const double tx = fma(g[k][0], cd.dt, g[k][2]);
+                            g[k][0] = fma(cd.a_p, tx, g[k][0]);
+                            g[k][2] = fma(tx, avx, tx);
+                            const double ty = fma(g[k + 1][1], cd.dt, g[k + 1][3]);
+                            g[k + 1][1] = fma(cd.a_p, ty, g[k + 1][1]);
+                            g[k + 1][3] = fma(ty, avy, ty);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const double tx = fma(g[k][0], cd.dt, g[k][2]);
+                            g[k][0] = fma(cd.a_p, tx, g[k][0]);
+                            g[k][2] = fma(tx, avx, tx);
+                            const double ty = fma(g[k][1], cd.dt, g[k][3]);
+                            g[k][1] = fma(cd.a_p, ty, g[k][1]);
+                            g[k][3] = fma(ty, avy, ty);
+                        }
+                    }
                     continue;
                 }
-                if (p.deferred && ++collided > p.defer_after) {
-                    const int slot = atomicAdd(p.deferred, 1);
-                    if (slot < kDeferCap) { p.deferred[1 + slot] = (int)ball; return; }  // redone chunk-parallel
-                    collided = -0x40000000;  // list full: stay sequential
-                }
-                const int32_t h = hl[(size_t)t * p.hl_st];  // collided step: the index is needed (rare reload)
-                float4 st;
-                if (p.hitstate) {
-                    st = p.hitstate[(size_t)t * p.B + ball];  // the forward kept the state of every collided step
+                const uint32_t h = (uint32_t)hl[(size_t)t * p.hl_st];
+                double Jl[16];
+                const double* J;
+                if (h & kLogNoRecord) {  // no record: replay the state from the checkpoint, Jacobian in place (slow path)
+                    const float4* q = scene_q(p, ball);
+                    const float4 st = replay_state(p, ball, t, q);
+                    hit_jacobian_d(st, __ldg(q + (h & kLogSeg)), __ldg(scene_s1(p, ball) + (h & kLogSeg)), cd, Jl);
+                    J = Jl;
                 } else {
-                    if (have < 0) {  // first (= latest) collision of the block: replay t0 .. t, bit-identical states
-                        float4 s = p.ckpt[(size_t)ck * p.B + ball];
-                        for (int u = t0; u <= t; ++u) {
-                            stash[(size_t)(u - t0) * kBwdThreads + tid] = s;
-                            if (u < t) {
-                                const int32_t hu = hl[(size_t)u * p.hl_st];
-                                State s1;
-                                free_step(s.x, s.y, s.z, s.w, c, s1);
-                                if (hu < 0) s1 = resolve(s.x, s.y, s.z, s.w, s1, __ldg(q + (hu & kLogIdx)), c);
-                                s = make_float4(s1.x, s1.y, s1.vx, s1.vy);
-                            }
-                        }
-                        have = t - t0;
-                    }
-                    st = stash[(size_t)(t - t0) * kBwdThreads + tid];
+                    J = p.jac + (size_t)(h & kLogSeg) * 16;
                 }
-                const float4 seg = __ldg(q + (h & kLogIdx));
-                step_vjp(st.x, st.y, st.z, st.w, true, seg, c, gx, gy, gvx, gvy);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double a0 = g[k][0], a1 = g[k][1], a2 = g[k][2], a3 = g[k][3];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        g[k][r] = fma(J[4 * r + 0], a0, fma(J[4 * r + 1], a1, fma(J[4 * r + 2], a2, J[4 * r + 3] * a3)));
+                }
+                coupled = true;
             }
             tb = ta;
         }
     }
-    p.v0_bar[ball] = make_float2(gvx, gvy);
-    if (p.x0_bar) p.x0_bar[ball] = make_float2(gx, gy);
-}
-
-// Chunk-parallel backward for small batches (few balls cannot fill 148 SMs with one thread per
-// ball): thread (ball, chunk) pulls the four basis cotangents e_0..e_3 back through its K-step
-// chunk, which yields the chunk's transposed Jacobian M_c = J_t0^T ... J_t1-1^T (4x4; the step
-// adjoint is linear in the cotangent).  Free-flight steps come from the log word alone; a chunk
-// with a collision is replayed from its checkpoint first.  One thread per ball then folds
-// g <- M_c g from the last chunk to the first.  Same mathematics as the sequential kernel,
-// different rounding order (tolerance-checked, not bit-exact).
-// No block-wide synchronisation: a ball's C_pad <= 32 chunks sit in one warp, the fold runs on warp
-// shuffles.  Until a chunk meets a collision its Jacobian is block diagonal (x and y decouple in
-// free flight), so only the four non-zero (position, velocity) pairs are pulled back.
-// With `ball_list` ([0] = count, then ids; hybrid plan of the sequential kernel) the grid covers the
-// listed balls only and `chunk_len` need not be the checkpoint period (the hit-state array is required).
-__global__ void __launch_bounds__(kBwdThreads) rollout_bwd_chunked_kernel(const BwdParams p, const int C_pad,
-                                                                         const int chunk_len,
-                                                                         const int* __restrict__ ball_list) {
-    const int tid = threadIdx.x;
-    const int bpb = kBwdThreads / C_pad;
-    const int chunk = tid % C_pad, slot = tid / C_pad;
-    int64_t ball = (int64_t)blockIdx.x * bpb + slot;
-    if (ball_list) {
-        const int count = min(ball_list[0], kDeferCap);
-        ball = ball < count ? (int64_t)ball_list[1 + ball] : p.B;  // p.B = no ball
-    }
-    const int n_ckpt = (p.n_steps + chunk_len - 1) / chunk_len;
-    const bool active = ball < p.B && chunk < n_ckpt;
-    const Consts c = p.c;
-    const float dk = dfric_value(c);
-    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
-    float g[4][4];  // g[k] = pull-back of e_k through this thread's chunk
+    // fold: v <- P_c v for c = n_chunks - 1 .. 0, P_c column k = g[k] of thread (ball, c)
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0f : 0.0f;
-    if (active) {
-        const float4* q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) +
-                          (p.per_env ? (size_t)ball * L.S_pad : 0);
-        const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
-        const int t0 = chunk * chunk_len, t1 = min(p.n_steps, t0 + chunk_len);
-        bool coupled = false;  // a collision has mixed x and y
-        for (int tb = t1; tb > t0;) {
-            const int ta = max(t0, tb - kBwdPrefetch);
-            unsigned m_hit = 0u, m_cx = 0u, m_cy = 0u;
-#pragma unroll
-            for (int j = 0; j < kBwdPrefetch; ++j) {
-                const uint32_t w = (ta + j < tb) ? (uint32_t)hl[(size_t)(ta + j) * p.hl_st] : 0u;
-                m_hit |= (w >> 31) << j;
-                m_cx |= ((w >> 29) & 1u) << j;
-                m_cy |= ((w >> 30) & 1u) << j;
-            }
-            if (m_hit == 0u && !coupled) {  // free flight, decoupled: 4 (position, velocity) pairs per step
-                for (int j = tb - ta - 1; j >= 0; --j) {
-                    const bool cx = ((m_cx >> j) & 1u) != 0u, cy = ((m_cy >> j) & 1u) != 0u;
-                    step_vjp_free_1d(cx, dk, c, g[0][0], g[0][2]);
-                    step_vjp_free_1d(cx, dk, c, g[2][0], g[2][2]);
-                    step_vjp_free_1d(cy, dk, c, g[1][1], g[1][3]);
-                    step_vjp_free_1d(cy, dk, c, g[3][1], g[3][3]);
-                }
-            } else {
-                for (int t = tb - 1; t >= ta; --t) {
-                    const int32_t h = hl[(size_t)t * p.hl_st];
-                    if (h >= 0) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) step_vjp_free((uint32_t)h, dk, c, g[k][0], g[k][1], g[k][2], g[k][3]);
-                        continue;
-                    }
-                    float4 st;
-                    if (p.hitstate) {
-                        st = p.hitstate[(size_t)t * p.B + ball];
-                    } else {  // no hit-state array: replay t0 .. t from the chunk's checkpoint (<= K steps)
-                        st = p.ckpt[(size_t)chunk * p.B + ball];
-                        for (int u = t0; u < t; ++u) {
-                            const int32_t hu = hl[(size_t)u * p.hl_st];
-                            State s1;
-                            free_step(st.x, st.y, st.z, st.w, c, s1);
-                            if (hu < 0) s1 = resolve(st.x, st.y, st.z, st.w, s1, __ldg(q + (hu & kLogIdx)), c);
-                            st = make_float4(s1.x, s1.y, s1.vx, s1.vy);
-                        }
-                    }
-                    const float4 seg = __ldg(q + (h & kLogIdx));
-                    {   // through a copy: the out-of-line call takes its array by reference (local memory), and
-                        // g itself must stay in registers for the straight-line free-flight path
-                        float tmp[4][4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-#pragma unroll
-                            for (int r2 = 0; r2 < 4; ++r2) tmp[k][r2] = g[k][r2];
-                        step_vjp_hit_n<4>(st.x, st.y, st.z, st.w, seg, c, tmp);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-#pragma unroll
-                            for (int r2 = 0; r2 < 4; ++r2) g[k][r2] = tmp[k][r2];
-                    }
-                    coupled = true;
-                }
-            }
-            tb = ta;
-        }
-    }
-    // fold g <- M_c g from the last chunk to the first; lane `chunk` of the ball's C_pad lanes holds M_c
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ball < p.B) {
+        for (int r = 0; r < 4; ++r) sm[((size_t)chunk * 16 + (k * 4 + r)) * 32 + lane] = g[k][r];
+    __syncthreads();
+    if (chunk == 0 && active) {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
         const float2 gg = p.xT_bar[ball];
         v[0] = gg.x; v[1] = gg.y;
         if (p.vT_bar) { const float2 h = p.vT_bar[ball]; v[2] = h.x; v[3] = h.y; }
-    }
-    if (C_pad <= 32) {
-        for (int cc = n_ckpt - 1; cc >= 0; --cc) {
-            float o[4];
+        for (int cc = n_chunks - 1; cc >= 0; --cc) {
+            const double* P = sm + (size_t)cc * 16 * 32 + lane;
+            double o[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                o[r] = (v[0] * g[0][r] + v[1] * g[1][r]) + (v[2] * g[2][r] + v[3] * g[3][r]);
+                o[r] = fma(v[0], P[(0 * 4 + r) * 32], fma(v[1], P[(1 * 4 + r) * 32], fma(v[2], P[(2 * 4 + r) * 32], v[3] * P[(3 * 4 + r) * 32])));
 #pragma unroll
-            for (int r = 0; r < 4; ++r) v[r] = __shfl_sync(0xffffffffu, o[r], cc, C_pad);  // chunk cc's product
+            for (int r = 0; r < 4; ++r) v[r] = o[r];
         }
-    } else {
-        // a ball's chunks span C_pad / 32 warps: the warp holding the last chunks folds first and relays
-        // the cotangent to the next one through shared memory
-        __shared__ float relay[kBwdThreads / 64][4];
-        const int wpb_ball = C_pad / 32, wi = chunk >> 5;
-        for (int w = wpb_ball - 1; w >= 0; --w) {
-            if (wi == w) {
-                if (w != wpb_ball - 1) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) v[r] = relay[slot][r];
-                }
-                for (int cc = min(n_ckpt, 32 * (w + 1)) - 1; cc >= 32 * w; --cc) {
-                    float o[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        o[r] = (v[0] * g[0][r] + v[1] * g[1][r]) + (v[2] * g[2][r] + v[3] * g[3][r]);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) v[r] = __shfl_sync(0xffffffffu, o[r], cc & 31);
-                }
-                if ((chunk & 31) == 0) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) relay[slot][r] = v[r];
-                }
-            }
-            __syncthreads();
-        }
-    }
-    if (ball < p.B && chunk == 0) {
-        p.v0_bar[ball] = make_float2(v[2], v[3]);
-        if (p.x0_bar) p.x0_bar[ball] = make_float2(v[0], v[1]);
+        p.v0_bar[ball] = make_float2((float)v[2], (float)v[3]);
+        if (p.x0_bar) p.x0_bar[ball] = make_float2((float)v[0], (float)v[1]);
     }
 }
-
 
 }  // namespace doper

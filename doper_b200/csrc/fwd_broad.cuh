@@ -148,15 +148,16 @@ __global__ void __launch_bounds__(kFwdThreads, (G == 1 && STAGED && !GRID) ? 7 :
             }
         }
         const uint32_t clipb = clip_bits(vx, vy);
+        int payload = idx;
         if (hit) {
-            if (writer && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
+            if (writer) payload = record_collision(p.sink, ball, t, x, y, vx, vy, idx);
             s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c);
             x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
         } else {
             x = px; y = py; vx = s1.vx; vy = s1.vy;
         }
         if (writer) {
-            if (hl) { *hl = pack_log(idx, hit, clipb); hl += p.hl_st; }
+            if (hl) { *hl = pack_log(payload, hit, clipb); hl += p.hl_st; }
             if (tx) { *tx = make_float2(x, y); tx += p.B; }
             if (tv) { *tv = make_float2(vx, vy); tv += p.B; }
             if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += p.B; }
@@ -311,14 +312,15 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_tpc_kernel(const FwdParam
                     }
                 }
                 const uint32_t clipb = clip_bits(vx, vy);
+                int payload = (hit || exact_idx) ? idx : 0;
                 if (active && lane == 0) {
                     if (p.ckpt && (t % K) == 0) p.ckpt[(size_t)(t / K) * p.B + ball] = make_float4(x, y, vx, vy);
-                    if (hit && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
+                    if (hit) payload = record_collision(p.sink, ball, t, x, y, vx, vy, idx);
                 }
                 if (hit) { s1 = resolve_inline(x, y, vx, vy, s1, sc.q[idx], c); cj = idx; }
                 x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
                 if (active && lane == 0) {
-                    if (hl) hl[(int64_t)t * p.hl_st] = pack_log((hit || exact_idx) ? idx : 0, hit, clipb);
+                    if (hl) hl[(int64_t)t * p.hl_st] = pack_log(payload, hit, clipb);
                     const size_t o = (size_t)t * p.B + ball;
                     if (p.traj_x) p.traj_x[o] = make_float2(x, y);
                     if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
@@ -424,8 +426,8 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_tpc_kernel(const FwdParam
         if (active && lane < n_commit) {
             const int ts = t + lane;
             const bool h = ev_hit && lane == f;
-            if (hl) hl[(int64_t)ts * p.hl_st] = pack_log((h || exact_idx) ? idx : 0, h, clip_bits(svx, svy));
-            if (h && p.hitstate) p.hitstate[(size_t)ts * p.B + ball] = make_float4(sx, sy, svx, svy);
+            const int payload = h ? record_collision(p.sink, ball, ts, sx, sy, svx, svy, idx) : (exact_idx ? idx : 0);
+            if (hl) hl[(int64_t)ts * p.hl_st] = pack_log(payload, h, clip_bits(svx, svy));
             if (p.ckpt) {  // K is usually a power of two: shift and mask instead of two integer divisions
                 const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
                 if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);

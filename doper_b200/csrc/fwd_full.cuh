@@ -24,7 +24,7 @@ struct FwdParams {
     float2* traj_v;
     float2* traj_a;
     float4* ckpt;     // [n_ckpt][B]
-    float4* hitstate; // [n_steps][B], written at collided steps only: the state at the START of the step
+    HitSink sink;     // collision records (state at the START of each collided step + segment index), appended
     int32_t* hitlog;  // element (t, ball) at t * hl_st + ball * hl_sb
     int64_t hl_st, hl_sb;
 };
@@ -89,11 +89,11 @@ __global__ void __launch_bounds__(kFwdThreads) rollout_fwd_kernel(const FwdParam
         sweep_any<G>(sc, s1.x, s1.y, lane, prev_idx, idx, dist);
         prev_idx = idx;
         const bool hit = dist <= c.r;  // NaN -> false (ball_sim.py:164)
-        if (hit && writer && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
+        const int payload = (hit && writer) ? record_collision(p.sink, ball, t, x, y, vx, vy, idx) : idx;
         if (hit) s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c);
         x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
         if (writer) {
-            if (hl) { *hl = pack_log(idx, hit, clipb); hl += p.hl_st; }
+            if (hl) { *hl = pack_log(payload, hit, clipb); hl += p.hl_st; }
             if (tx) { *tx = make_float2(x, y); tx += p.B; }
             if (tv) { *tv = make_float2(vx, vy); tv += p.B; }
             if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += p.B; }
@@ -207,11 +207,11 @@ rollout_fwd_reg_kernel(const FwdParams p) {
         unpack_key(key, idx, dist);
         prev_idx = idx;
         const bool hit = dist <= c.r;  // NaN -> false (ball_sim.py:164)
-        if (hit && writer && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
+        const int payload = (hit && writer) ? record_collision(p.sink, ball, t, x, y, vx, vy, idx) : idx;
         if (hit) s1 = resolve(x, y, vx, vy, s1, __ldg(gq + idx), c);
         x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
         if (writer) {
-            if (hl) { *hl = pack_log(idx, hit, clipb); hl += p.hl_st; }
+            if (hl) { *hl = pack_log(payload, hit, clipb); hl += p.hl_st; }
             if (tx) { *tx = make_float2(x, y); tx += stride; }
             if (tv) { *tv = make_float2(vx, vy); tv += stride; }
             if (ta) { *ta = make_float2(s1.ax, s1.ay); ta += stride; }
@@ -284,12 +284,12 @@ __global__ void __launch_bounds__(1024) rollout_fwd_tp_kernel(const FwdParams p)
             sweep_any<32>(sc, s1.x, s1.y, lane, prev_idx, idx, dist);
             prev_idx = idx;
             const bool hit = dist <= c.r;
-            if (hit && lane == 0 && p.hitstate) p.hitstate[(size_t)t * p.B + ball] = make_float4(x, y, vx, vy);
+            const int payload = (hit && lane == 0) ? record_collision(p.sink, ball, t, x, y, vx, vy, idx) : idx;
             if (hit) { s1 = resolve(x, y, vx, vy, s1, sc.q[idx], c); seq_left = kTpSeqSteps; }
             x = s1.x; y = s1.y; vx = s1.vx; vy = s1.vy;
             if (lane == 0) {
                 const size_t o = (size_t)t * p.B + ball;
-                if (hl) hl[(size_t)t * p.hl_st] = pack_log(idx, hit, clipb);
+                if (hl) hl[(size_t)t * p.hl_st] = pack_log(payload, hit, clipb);
                 if (p.traj_x) p.traj_x[o] = make_float2(x, y);
                 if (p.traj_v) p.traj_v[o] = make_float2(vx, vy);
                 if (p.traj_a) p.traj_a[o] = make_float2(s1.ax, s1.ay);
@@ -346,8 +346,8 @@ __global__ void __launch_bounds__(1024) rollout_fwd_tp_kernel(const FwdParams p)
         prev_idx = __shfl_sync(0xffffffffu, idx, n_commit - 1);
         if (lane < n_commit) {
             const int ts = t + lane;
-            if (hl) hl[(size_t)ts * p.hl_st] = pack_log(idx, lane == first, clip_bits(svx, svy));
-            if (lane == first && p.hitstate) p.hitstate[(size_t)ts * p.B + ball] = make_float4(sx, sy, svx, svy);
+            const int payload = (lane == first) ? record_collision(p.sink, ball, ts, sx, sy, svx, svy, idx) : idx;
+            if (hl) hl[(size_t)ts * p.hl_st] = pack_log(payload, lane == first, clip_bits(svx, svy));
             if (p.ckpt && (ts % K) == 0) p.ckpt[(size_t)(ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
             const size_t o = (size_t)ts * p.B + ball;
             if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);

@@ -9,7 +9,7 @@
 //   scene.cuh      prepared-scene layout, scene_prepare_kernel (+ uniform grid), TMA staging
 //   fwd_full.cuh   full-sweep forward kernels (every pair every step)
 //   fwd_broad.cuh  broad-phase forward kernels: rollout_fwd_cull_kernel, rollout_fwd_tpc_kernel (default plan)
-//   bwd.cuh        rollout_bwd_kernel (sequential, bit-exact), rollout_bwd_chunked_kernel
+//   bwd.cuh        rollout_bwd_kernel (sequential fp32, bit-exact), rollout_bwd_jacobian_kernel + rollout_bwd_fold_kernel (binary64, default)
 //   queries.cuh    l1_loss_kernel, closest_segment_kernel, points_inside_kernel, fp32_probe_kernel
 //   sensor.cuh     range-sensor ray casting
 //   peer.cuh       one-shot all-reduce of the policy gradient over NVLink peer memory
@@ -71,54 +71,50 @@ Consts make_consts(const doper_rollout_desc* d) {
     return c;
 }
 
-// Backward plan. Small batches use the chunk-parallel kernel (<= 32 chunks per ball, one thread
-// each); large batches have enough balls for one thread per ball and use the sequential kernel
-// (bit-identical to the oracle's adjoint). flags bit 1 forces the sequential kernel.
-constexpr int64_t kChunkedMaxBalls = 32768;
-constexpr int kChunkedMaxK = 96;  // stash of K x 128 float4 + matrices must fit in shared memory
+// Checkpoint period.  Checkpoints only serve the replay fallback of the backward (a collided step whose
+// record could not be stored: record area full or disabled), so K trades 16/K bytes per ball-step against a
+// replay of at most K steps.
+int resolve_K(const doper_rollout_desc* d) { return d->ckpt_every > 0 ? d->ckpt_every : 32; }
 
-bool chunked_eligible(const doper_rollout_desc* d) {
-    return !(d->flags & 2) && d->B <= kChunkedMaxBalls && d->n_steps >= 64;
+// Collision records kept by the forward for the backward (state at the start of the step + segment index,
+// 32 B each; the backward's scratch holds one 4x4 binary64 Jacobian, 128 B, per record).  Default capacity:
+// one record per 64 ball-steps (the seeded BASELINE batches collide on 1 step in 500 to 1,000) and never
+// fewer than 65,536; a forward that runs out of room flags the remaining collisions in the hit log and
+// the backward replays those from the checkpoints (slower, same results).  flags bit 19 = no records.
+int64_t record_capacity(const doper_rollout_desc* d) {
+    if (d->flags & ((1 << 19) | (1 << 17))) return 0;  // bit 17: the log payload is the exact index at every step
+    const int64_t steps = d->B * (int64_t)d->n_steps;
+    int64_t cap = d->hit_capacity > 0 ? d->hit_capacity : (steps / 64 > 65536 ? steps / 64 : 65536);
+    if (cap > steps) cap = steps;
+    if (cap > (int64_t)kLogSeg) cap = (int64_t)kLogSeg;
+    return cap;
 }
 
-int resolve_K(const doper_rollout_desc* d) {
-    if (d->ckpt_every > 0) return d->ckpt_every;
-    if (chunked_eligible(d)) {
-        // 32 chunks per ball (one warp); small batches with long rollouts take 64 (two warps): more threads
-        // in flight, and the slowest thread — a chunk where the ball collides step after step — is half as long
-        // (4,096 balls x 500 steps measured 0.072 ms with 64 chunks, 0.070 with 32, 0.103 with 128; the
-        // chunk count fixes the rounding order of the fold, so one rule covers every batch up to 4,096:
-        // a slice of such a batch run alone returns the same gradient bits)
-        const int n_chunks = (d->B <= 4096 && d->n_steps >= 256) ? 64 : 32;
-        const int K = (d->n_steps + n_chunks - 1) / n_chunks;
-        if (K <= kChunkedMaxK) return K < 4 ? 4 : K;
-    }
-    return 16;  // sequential backward: 32 KB of stash per 128-thread block -> 7 blocks per SM
-}
-
-// Backward workspace: [checkpoints n_ckpt x B x 16 B | hit log n x B x 4 B | hit states n x B x 16 B].
-// The hit-state array is written and read at collided steps only (no bandwidth; it spares the
-// backward every replay); flags bit 19 drops it (memory: 16 B per ball-step) and the backward
-// replays blocks with a collision from their checkpoint instead.
-struct WsLayout { size_t log_off, state_off, defer_off, total; };
+// Forward workspace: [header 256 B: int record count | checkpoints n_ckpt x B x 16 B | hit log n x B x 4 B |
+// collision records cap x 32 B].  Backward scratch (separate, caller-owned, written by doper_rollout_bwd):
+// [cap x 16 doubles].
+struct WsLayout { size_t ckpt_off, log_off, rec_off, total; int64_t cap; };
 
 WsLayout ws_layout(const doper_rollout_desc* d) {
     const int K = resolve_K(d);
     const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
     WsLayout w;
-    w.log_off = (n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
-    size_t end = w.log_off + (size_t)d->n_steps * (size_t)d->B * sizeof(int32_t);
-    end = (end + 255) / 256 * 256;
-    w.state_off = 0;
-    if (!(d->flags & (1 << 19))) {
-        w.state_off = end;
-        end += (size_t)d->n_steps * (size_t)d->B * sizeof(float4);
-        end = (end + 255) / 256 * 256;
-    }
-    w.defer_off = end;  // scratch of the hybrid backward: deferred-ball list
-    end += ((size_t)(kDeferCap + 1) * sizeof(int) + 255) / 256 * 256;
-    w.total = end + 256;
+    w.cap = record_capacity(d);
+    w.ckpt_off = 256;
+    w.log_off = (w.ckpt_off + n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
+    w.rec_off = (w.log_off + (size_t)d->n_steps * (size_t)d->B * sizeof(int32_t) + 255) / 256 * 256;
+    w.total = (w.rec_off + (size_t)w.cap * sizeof(HitRecord) + 255) / 256 * 256 + 256;
     return w;
+}
+
+// Chunks per ball of the binary64 backward: enough (ball, chunk) threads to fill the SMs, at most kFoldMaxChunks.
+void fold_plan(const doper_rollout_desc* d, int* n_chunks, int* chunk_len) {
+    int c = 1;
+    while (c < kFoldMaxChunks && d->B * c < (int64_t)148 * 2048) c *= 2;
+    while (c > 1 && d->n_steps / c < 8) c /= 2;
+    const int len = (d->n_steps + c - 1) / c;
+    *chunk_len = len;
+    *n_chunks = (d->n_steps + len - 1) / len;
 }
 
 // Forward plan: time-parallel kernel (one warp per ball) unless the caller pinned a lane count,
@@ -188,14 +184,10 @@ int tp_warps_per_block(const doper_rollout_desc* d) {
     return 32;
 }
 
-bool use_chunked(const doper_rollout_desc* d, int K) {
-    const int n_ckpt = (d->n_steps + K - 1) / K;
-    return chunked_eligible(d) && n_ckpt <= 128 && n_ckpt >= 2 && K <= kChunkedMaxK;
-}
-
 int validate_desc(const doper_rollout_desc* d) {
     if (!d) return DOPER_ERR_NULL_PTR;
-    if (d->B <= 0 || d->S <= 0 || d->n_steps < 0 || d->ckpt_every < 0) return DOPER_ERR_BAD_SHAPE;
+    if (d->B <= 0 || d->S <= 0 || d->n_steps < 0 || d->ckpt_every < 0 || d->hit_capacity < 0) return DOPER_ERR_BAD_SHAPE;
+    if (d->B * (int64_t)d->n_steps > ((int64_t)1 << 40)) return DOPER_ERR_UNSUPPORTED;
     if (d->ckpt_every > 1024) return DOPER_ERR_BAD_SHAPE;
     // candidate lists hold 16-bit segment indices, the hit log 29-bit ones: 65,504 segments per scene is the
     // limit of the rollout kernels (the largest BASELINE scene has 10,002)
@@ -471,11 +463,7 @@ int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
 
 const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward) {
     if (validate_desc(d) != DOPER_OK) return "invalid";
-    if (backward) {
-        if (use_chunked(d, resolve_K(d))) return "rollout_bwd_chunked_kernel";
-        const bool hybrid = !(d->flags & (1 << 19)) && !(d->flags & 2) && d->n_steps >= 256;
-        return hybrid ? "rollout_bwd_kernel+rollout_bwd_chunked_kernel" : "rollout_bwd_kernel";
-    }
+    if (backward) return (d->flags & 2) ? "rollout_bwd_kernel" : "rollout_bwd_jacobian_kernel+rollout_bwd_fold_kernel";
     const int G = auto_lanes(d);
     static const char* const tpc[] = {"rollout_fwd_tpc_kernel<2>", "rollout_fwd_tpc_kernel<4>", "rollout_fwd_tpc_kernel<8>",
                                       "rollout_fwd_tpc_kernel<16>", "rollout_fwd_tpc_kernel<32>"};
@@ -529,15 +517,18 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     p.xT = reinterpret_cast<float2*>(xT); p.vT = reinterpret_cast<float2*>(vT);
     p.traj_x = reinterpret_cast<float2*>(traj_x); p.traj_v = reinterpret_cast<float2*>(traj_v);
     p.traj_a = reinterpret_cast<float2*>(traj_a);
-    p.ckpt = nullptr; p.hitlog = nullptr; p.hitstate = nullptr;
+    p.ckpt = nullptr; p.hitlog = nullptr; p.sink.rec = nullptr; p.sink.count = nullptr; p.sink.cap = 0;
+    cudaStream_t st = (cudaStream_t)stream;
     if (ws) {
         const WsLayout w = ws_layout(d);
         unsigned char* base = reinterpret_cast<unsigned char*>(ws);
-        p.ckpt = reinterpret_cast<float4*>(base);
+        p.ckpt = reinterpret_cast<float4*>(base + w.ckpt_off);
         p.hitlog = reinterpret_cast<int32_t*>(base + w.log_off);
-        if (w.state_off) p.hitstate = reinterpret_cast<float4*>(base + w.state_off);
+        p.sink.rec = reinterpret_cast<HitRecord*>(base + w.rec_off);
+        p.sink.count = reinterpret_cast<int*>(base);
+        p.sink.cap = (int)w.cap;
+        if (cudaMemsetAsync(base, 0, 256, st) != cudaSuccess) return DOPER_ERR_LAUNCH;  // record counter
     }
-    cudaStream_t st = (cudaStream_t)stream;
     if (tp) {
         if (smem > 48 * 1024 &&
             cudaFuncSetAttribute(rollout_fwd_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
@@ -585,63 +576,64 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     }
 }
 
+size_t doper_rollout_bwd_scratch_bytes(const doper_rollout_desc* d) {
+    if (validate_desc(d) != DOPER_OK) return 0;
+    return (size_t)record_capacity(d) * 16 * sizeof(double) + 256;
+}
+
 int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
-                      const void* ws, const float* xT_bar, const float* vT_bar, float* x0_bar,
-                      float* v0_bar) {
+                      const void* ws, void* bwd_scratch, const float* xT_bar, const float* vT_bar,
+                      float* x0_bar, float* v0_bar) {
     int rc = validate_desc(d);
     if (rc) return rc;
     if (!scene_ws || !ws || !xT_bar || !v0_bar) return DOPER_ERR_NULL_PTR;
     if (!aligned(scene_ws, 256) || !aligned(ws, 256) || !aligned(xT_bar, 8) || !aligned(v0_bar, 8) ||
-        (vT_bar && !aligned(vT_bar, 8)) || (x0_bar && !aligned(x0_bar, 8)))
+        (vT_bar && !aligned(vT_bar, 8)) || (x0_bar && !aligned(x0_bar, 8)) || (bwd_scratch && !aligned(bwd_scratch, 256)))
         return DOPER_ERR_MISALIGNED;
+    if (d->n_steps == 0) return DOPER_ERR_BAD_SHAPE;
     const int K = resolve_K(d);
+    const WsLayout w = ws_layout(d);
+    const bool sequential = (d->flags & 2) != 0;
+    if (!sequential && w.cap > 0 && !bwd_scratch) return DOPER_ERR_NULL_PTR;
     BwdParams p;
     p.B = d->B; p.S = d->S; p.per_env = d->per_env ? 1 : 0; p.n_steps = d->n_steps; p.K = K;
     p.c = make_consts(d);
     p.scene_ws = reinterpret_cast<const unsigned char*>(scene_ws);
-    const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
-    const WsLayout w = ws_layout(d);
     const unsigned char* base = reinterpret_cast<const unsigned char*>(ws);
-    p.ckpt = reinterpret_cast<const float4*>(base);
+    p.ckpt = reinterpret_cast<const float4*>(base + w.ckpt_off);
     p.hitlog = reinterpret_cast<const int32_t*>(base + w.log_off);
-    p.hitstate = w.state_off ? reinterpret_cast<const float4*>(base + w.state_off) : nullptr;
+    p.rec = reinterpret_cast<const HitRecord*>(base + w.rec_off);
+    p.rec_count = reinterpret_cast<const int*>(base);
+    p.rec_cap = (int)w.cap;
+    p.jac = reinterpret_cast<double*>(bwd_scratch);
     p.hl_st = log_ball_major(d) ? 1 : d->B;
     p.hl_sb = log_ball_major(d) ? d->n_steps : 1;
     p.xT_bar = reinterpret_cast<const float2*>(xT_bar);
     p.vT_bar = reinterpret_cast<const float2*>(vT_bar);
     p.x0_bar = reinterpret_cast<float2*>(x0_bar);
     p.v0_bar = reinterpret_cast<float2*>(v0_bar);
-    p.deferred = nullptr; p.defer_after = 0;
-    if (d->n_steps == 0) return DOPER_ERR_BAD_SHAPE;
-    if (use_chunked(d, K)) {
-        int C_pad = 2;
-        while (C_pad < (int)n_ckpt) C_pad *= 2;
-        const int bpb = kBwdThreads / C_pad;
-        const unsigned grid = (unsigned)((d->B + bpb - 1) / bpb);
-        rollout_bwd_chunked_kernel<<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(p, C_pad, K, nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sequential) {  // fp32 in the oracle's operation order (bit-exact), one thread per ball
+        const unsigned grid = (unsigned)((d->B + kBwdThreads - 1) / kBwdThreads);
+        rollout_bwd_kernel<<<grid, kBwdThreads, 0, st>>>(p);
         return launch_status();
     }
-    // hybrid: balls in sliding contact leave the sequential kernel and are redone 32 chunks in parallel
-    // (needs the hit-state array; flags bit 1 keeps everything sequential = bit-exact vs the oracle order)
-    const bool hybrid = p.hitstate && !(d->flags & 2) && d->n_steps >= 256;
-    if (hybrid) {
-        p.deferred = reinterpret_cast<int*>(const_cast<unsigned char*>(base) + w.defer_off);
-        p.defer_after = 128;
-        if (cudaMemsetAsync(p.deferred, 0, sizeof(int), (cudaStream_t)stream) != cudaSuccess) return DOPER_ERR_LAUNCH;
+    // binary64 plan: Jacobians of the collided steps, then chunk products + fold
+    if (w.cap > 0) {
+        int64_t blocks = (w.cap + 127) / 128;
+        const int64_t max_blocks = (int64_t)sm_count() * 8;
+        if (blocks > max_blocks) blocks = max_blocks;
+        rollout_bwd_jacobian_kernel<<<(unsigned)blocks, 128, 0, st>>>(p);
+        if (launch_status() != DOPER_OK) return DOPER_ERR_LAUNCH;
     }
-    const size_t smem = p.hitstate ? 0 : (size_t)K * kBwdThreads * sizeof(float4);
-    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    int n_chunks, chunk_len;
+    fold_plan(d, &n_chunks, &chunk_len);
+    const size_t smem = (size_t)n_chunks * 16 * 32 * sizeof(double);
     if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(rollout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
+        cudaFuncSetAttribute(rollout_bwd_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DOPER_ERR_SMEM_LIMIT;
-    const unsigned grid = (unsigned)((d->B + kBwdThreads - 1) / kBwdThreads);
-    rollout_bwd_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(p);
-    if (hybrid && launch_status() == DOPER_OK) {
-        const int chunk_len = (d->n_steps + 31) / 32;
-        rollout_bwd_chunked_kernel<<<kDeferCap / (kBwdThreads / 32), kBwdThreads, 0, (cudaStream_t)stream>>>(
-            p, 32, chunk_len, p.deferred);
-    }
+    const unsigned grid = (unsigned)((d->B + 31) / 32);
+    rollout_bwd_fold_kernel<<<grid, 32 * n_chunks, smem, st>>>(p, n_chunks, chunk_len);
     return launch_status();
 }
 
@@ -658,7 +650,7 @@ int doper_l1_loss(doper_stream_t stream, int64_t B, const float* xT, const float
 }
 
 int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
-                         const float* x0, const float* v0, const float target[2], void* ws,
+                         const float* x0, const float* v0, const float target[2], void* ws, void* bwd_scratch,
                          float* scratch, float* loss_sum, float* loss_per_ball, float* xT,
                          float* vT, float* v0_bar, float* x0_bar) {
     if (!ws || !scratch || !target) return DOPER_ERR_NULL_PTR;
@@ -666,7 +658,7 @@ int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, con
     if (rc) return rc;
     rc = doper_l1_loss(stream, d->B, xT, target, loss_per_ball, loss_sum, scratch);
     if (rc) return rc;
-    return doper_rollout_bwd(stream, d, scene_ws, ws, scratch, nullptr, x0_bar, v0_bar);
+    return doper_rollout_bwd(stream, d, scene_ws, ws, bwd_scratch, scratch, nullptr, x0_bar, v0_bar);
 }
 
 size_t doper_peer_buffer_bytes(int32_t n) { return n > 0 ? peer_buffer_bytes(n) : 0; }

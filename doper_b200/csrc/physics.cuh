@@ -85,7 +85,40 @@ __device__ __forceinline__ float seg_dist2(float px, float py, const float4& q) 
 //              adjoint of a free-flight step depends on (the friction clip's derivative,
 //              ball_sim.py:43), so the backward needs no state for the steps that did not collide
 //   bits 0-28  closest-segment index (consumed at collisions only)
+//   bits 0-28  payload.  Step without a collision: the closest-segment index (0 unless the exact index log,
+//              flags bit 17, was asked for).  Collided step: the slot of the step's COLLISION RECORD (below),
+//              or, with bit 28 set (kLogNoRecord), the segment index itself: no record could be appended
+//              (record area full or disabled) and the backward replays the step from its checkpoint.
 constexpr uint32_t kLogHit = 0x80000000u, kLogClipY = 0x40000000u, kLogClipX = 0x20000000u, kLogIdx = 0x1fffffffu;
+constexpr uint32_t kLogNoRecord = 0x10000000u, kLogSeg = 0x0fffffffu;
+
+// Collision record: everything the backward needs about one collided step (the state at its START and the
+// segment), appended by the forward kernels in arrival order (one atomic per collision; the slot goes
+// into the step's log word, so the order does not matter).  32 bytes.
+struct HitRecord {
+    float x, y, vx, vy;
+    int32_t ball_lo, t, idx, ball_hi;
+};
+
+struct HitSink {
+    HitRecord* rec;  // nullable
+    int* count;      // records appended so far (may exceed cap: the excess was not stored)
+    int cap;
+};
+
+__device__ __forceinline__ int record_collision(const HitSink& s, int64_t ball, int t, float x, float y, float vx,
+                                                float vy, int idx) {
+    if (s.rec != nullptr && s.cap > 0) {
+        const int slot = atomicAdd(s.count, 1);
+        if (slot < s.cap) {
+            float4* dst = reinterpret_cast<float4*>(s.rec + slot);
+            dst[0] = make_float4(x, y, vx, vy);
+            reinterpret_cast<int4*>(dst)[1] = make_int4((int)(ball & 0xffffffffll), t, idx, (int)(ball >> 32));
+            return slot;
+        }
+    }
+    return (int)((uint32_t)idx | kLogNoRecord);
+}
 
 __device__ __forceinline__ uint32_t clip_bits(float vx, float vy) {
     return ((vx > -1.0f && vx < 1.0f) ? kLogClipX : 0u) | ((vy > -1.0f && vy < 1.0f) ? kLogClipY : 0u);

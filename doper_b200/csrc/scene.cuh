@@ -18,7 +18,7 @@ struct SceneHeader {  // 16 B per scene
 };
 
 struct SceneLayout {
-    size_t hdr_off, q_off, rl_off, grid_off, total;  // grid_off = 0: no grid (per-environment scenes)
+    size_t hdr_off, q_off, rl_off, s1_off, grid_off, total;  // grid_off = 0: no grid (per-environment scenes)
     int S_pad;
 };
 
@@ -29,7 +29,10 @@ __host__ __device__ inline SceneLayout scene_layout(int64_t n_scenes, int S) {
     size_t hdr = (size_t)n_scenes * sizeof(SceneHeader);
     L.q_off = (hdr + 255) / 256 * 256;
     L.rl_off = L.q_off + (size_t)n_scenes * L.S_pad * sizeof(float4);
-    L.total = L.rl_off + (size_t)n_scenes * L.S_pad * sizeof(float);
+    L.s1_off = (L.rl_off + (size_t)n_scenes * L.S_pad * sizeof(float) + 255) / 256 * 256;
+    // raw end points s1 [n_scenes][S_pad] float2: read by the binary64 backward only (its segment direction is
+    // s1 - s0 in binary64, as in oracle_grad_truth64, not the fp32-rounded sv of q); never staged
+    L.total = L.s1_off + (size_t)n_scenes * L.S_pad * sizeof(float2);
     L.total = (L.total + 255) / 256 * 256;
     L.grid_off = 0;
     if (n_scenes == 1) {  // [GridHeader | cell_start (kGridMaxCells + 1) | items (4 S_pad)]
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(128) scene_prepare_kernel(int64_t n_scenes, in
     const float4* in = segs + sc * (int64_t)S;
     float4* q = reinterpret_cast<float4*>(ws + L.q_off) + sc * (int64_t)L.S_pad;
     float* rl = reinterpret_cast<float*>(ws + L.rl_off) + sc * (int64_t)L.S_pad;
+    float2* e1 = reinterpret_cast<float2*>(ws + L.s1_off) + sc * (int64_t)L.S_pad;
     float mx = 0.0f;
     int weird = 0;
     for (int i = threadIdx.x; i < L.S_pad; i += blockDim.x) {
@@ -74,6 +78,7 @@ __global__ void __launch_bounds__(128) scene_prepare_kernel(int64_t n_scenes, in
             float len2 = svx * svx + svy * svy;      // :133
             q[i] = make_float4(s.x, s.y, svx, svy);
             rl[i] = 1.0f / len2;
+            e1[i] = make_float2(s.z, s.w);
             float m = fmaxf(fmaxf(fabsf(s.x), fabsf(s.y)), fmaxf(fabsf(s.z), fabsf(s.w)));
             mx = fmaxf(mx, m);
             // the filtered sweep's error analysis needs a normal, finite, non-degenerate segment
@@ -82,6 +87,7 @@ __global__ void __launch_bounds__(128) scene_prepare_kernel(int64_t n_scenes, in
         } else {
             q[i] = make_float4(kSentinel, kSentinel, 0.0f, 0.0f);
             rl[i] = 0.0f;
+            e1[i] = make_float2(kSentinel, kSentinel);
         }
     }
     __shared__ float s_mx[128];

@@ -40,7 +40,7 @@ class RolloutOptions:
     def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False,
                  sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True,
                  broad_phase: bool = None, exact_index_log: bool = False,
-                 broad_phase_time_parallel: bool = False, hit_state_array: bool = True):
+                 broad_phase_time_parallel: bool = False, hit_records: bool = True, hit_capacity: int = 0):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
@@ -53,14 +53,16 @@ class RolloutOptions:
         # collisions only, which is all the backward and the reference's outputs depend on)
         self.exact_index_log = bool(exact_index_log)
         self.broad_phase_time_parallel = bool(broad_phase_time_parallel)  # lane = time step variant
-        # keep the state of every collided step for the backward (16 B per ball-step of workspace, touched
-        # at collisions only); False: the backward replays from the K-step checkpoints instead
-        self.hit_state_array = bool(hit_state_array)
+        # collision records (state at the start of every collided step + segment, 32 B each) for the backward;
+        # False: the backward replays collided steps from the K-step checkpoints instead.  hit_capacity:
+        # records the workspace can hold (0 = library default); collisions beyond it are replayed as well
+        self.hit_records = bool(hit_records)
+        self.hit_capacity = int(hit_capacity)
 
     def key(self) -> tuple:
         return (self.ckpt_every, self.lanes_per_ball, self.force_exact_sweep, self.sequential_backward, self.smem_forward,
                 self.time_parallel, self.broad_phase, self.exact_index_log, self.broad_phase_time_parallel,
-                self.hit_state_array)
+                self.hit_records, self.hit_capacity)
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -103,7 +105,8 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
                ((1 << 16) if opts.broad_phase else 0) | ((1 << 15) if opts.broad_phase is False else 0) |
                ((1 << 17) if opts.exact_index_log else 0) |
                ((1 << 18) if opts.broad_phase_time_parallel else 0) |
-               (0 if opts.hit_state_array else (1 << 19)))
+               (0 if opts.hit_records else (1 << 19)))
+    d.hit_capacity = opts.hit_capacity
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d
@@ -124,6 +127,8 @@ class _Buffers:
         B = desc.B
         self.ws = torch.empty(lib.doper_rollout_workspace_bytes(ctypes.byref(desc)), dtype=torch.uint8,
                               device=device)
+        self.bwd_scratch = torch.empty(lib.doper_rollout_bwd_scratch_bytes(ctypes.byref(desc)), dtype=torch.uint8,
+                                       device=device)
         self.scratch = torch.empty(2 * B, dtype=torch.float32, device=device)
         # packed [loss_sum (4 floats, 16-B slot) | xT 2B | vT 2B | v0_bar 2B | x0_bar 2B | loss_pb B]
         self.out = torch.empty(4 + 9 * B, dtype=torch.float32, device=device)
@@ -131,7 +136,7 @@ class _Buffers:
 
     @classmethod
     def get(cls, device, desc: RolloutDesc) -> "_Buffers":
-        key = (device.index, desc.B, desc.S, desc.per_env, desc.n_steps, desc.ckpt_every, desc.flags)
+        key = (device.index, desc.B, desc.S, desc.per_env, desc.n_steps, desc.ckpt_every, desc.flags, desc.hit_capacity)
         b = cls._cache.get(key)
         if b is None:
             if len(cls._cache) > 8:
@@ -215,7 +220,7 @@ def _value_and_grad_raw(sim_time, n_steps, scene, coordinate_init, velocity_init
     st = stream_ptr()
     if want_grad:
         check(lib.doper_value_and_grad(st, ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), tgt, ptr(bufs.ws),
-                                       ptr(bufs.scratch), ptr(loss_sum), ptr(lpb), ptr(xT), ptr(vT), ptr(gv),
+                                       ptr(bufs.bwd_scratch), ptr(bufs.scratch), ptr(loss_sum), ptr(lpb), ptr(xT), ptr(vT), ptr(gv),
                                        ptr(gx)), "doper_value_and_grad")
     else:
         check(lib.doper_rollout_fwd(st, ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT), 0, 0,
@@ -269,7 +274,7 @@ class _HostPlan:
         self.in_np, self.out_np = self.pin_in.numpy(), self.pin_out.numpy()
         inp = self.bufs.inp
         self.args = (ctypes.byref(self.desc), ptr(sws), ptr(inp[: 2 * B]), ptr(inp[2 * B:]), self.tgt, ptr(self.bufs.ws),
-                     ptr(self.bufs.scratch), ptr(o[0:1]), ptr(o[4 + 8 * B:4 + 9 * B]), ptr(o[4:4 + 2 * B]),
+                     ptr(self.bufs.bwd_scratch), ptr(self.bufs.scratch), ptr(o[0:1]), ptr(o[4 + 8 * B:4 + 9 * B]), ptr(o[4:4 + 2 * B]),
                      ptr(o[4 + 2 * B:4 + 4 * B]), ptr(o[4 + 4 * B:4 + 6 * B]), ptr(o[4 + 6 * B:4 + 8 * B]))
 
     _last: "_HostPlan" = None  # the previous call's plan + a cheap fingerprint of its arguments
@@ -391,7 +396,8 @@ class _RolloutFn(torch.autograd.Function):
             g_xT.to(torch.float32).contiguous()
         gv = None if g_vT is None else g_vT.to(torch.float32).contiguous()
         bar = torch.empty((2, B, 2), dtype=torch.float32, device=device)
-        check(lib.doper_rollout_bwd(stream_ptr(), ctypes.byref(desc), ptr(sws), ptr(ctx.ws), ptr(gx), ptr(gv),
+        scratch = torch.empty(lib.doper_rollout_bwd_scratch_bytes(ctypes.byref(desc)), dtype=torch.uint8, device=device)
+        check(lib.doper_rollout_bwd(stream_ptr(), ctypes.byref(desc), ptr(sws), ptr(ctx.ws), ptr(scratch), ptr(gx), ptr(gv),
                                     ptr(bar[0]), ptr(bar[1])), "doper_rollout_bwd")
         return bar[0], bar[1], None, None
 
@@ -432,17 +438,37 @@ def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, at
     tp = [ptr(traj[i]) for i in range(3)] if want_trajectory else [0, 0, 0]
     check(lib.doper_rollout_fwd(stream_ptr(), ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), ptr(out[0]),
                                 ptr(out[1]), tp[0], tp[1], tp[2], ptr(ws)), "doper_rollout_fwd")
+    # workspace layout (include/doper_b200.h): [256 B header | checkpoints | hit log | collision records]
+    r256 = lambda v: (v + 255) // 256 * 256
     ck_bytes = n_ckpt * B * 16
-    off = (ck_bytes + 255) // 256 * 256
-    ckpt = ws[:ck_bytes].view(torch.float32).view(n_ckpt, B, 4).cpu().numpy()
-    hl = ws[off:off + n * B * 4].view(torch.int32)
+    log_off = r256(256 + ck_bytes)
+    rec_off = r256(log_off + n * B * 4)
+    ckpt = ws[256:256 + ck_bytes].view(torch.float32).view(n_ckpt, B, 4).cpu().numpy()
+    hl = ws[log_off:log_off + n * B * 4].view(torch.int32)
     if lib.doper_rollout_log_ball_major(ctypes.byref(desc)):
         hl = hl.view(B, n).t().contiguous().cpu().numpy()
     else:
         hl = hl.view(n, B).cpu().numpy()
+    n_rec_seen = int(ws[:4].view(torch.int32).item())
+    cap = (ws.numel() - 256 - rec_off) // 32
+    n_rec = min(n_rec_seen, cap)
+    rec = ws[rec_off:rec_off + n_rec * 32].view(torch.int32).view(n_rec, 8).cpu().numpy()
+    hit = hl < 0
+    payload = hl & 0x1FFFFFFF
+    idx = payload & 0x0FFFFFFF
+    # collided steps: the payload is the slot of the step's collision record unless bit 28 is set
+    via_rec = hit & ((payload & 0x10000000) == 0)
+    if via_rec.any():
+        idx = idx.copy()
+        slots = payload[via_rec]
+        idx[via_rec] = rec[slots, 6]
+        tt, bb = np.nonzero(via_rec)
+        assert np.array_equal(rec[slots, 5], tt) and np.array_equal(rec[slots, 4], bb), "collision records do not match the log"
     t = None
     if want_trajectory:
         th = traj.cpu().numpy()
         t = BallState(th[0], th[1], th[2])
-    return {"x_T": out[0].cpu().numpy(), "v_T": out[1].cpu().numpy(), "idx": hl & 0x1FFFFFFF, "hit": hl < 0,
-            "hitlog": hl, "checkpoints": ckpt, "trajectory": t}
+    return {"x_T": out[0].cpu().numpy(), "v_T": out[1].cpu().numpy(), "idx": idx, "hit": hit,
+            "hitlog": hl, "checkpoints": ckpt, "trajectory": t, "records": rec, "records_seen": n_rec_seen,
+            "record_capacity": cap,
+            "record_states": rec[:, :4].copy().view(np.float32) if n_rec else np.zeros((0, 4), np.float32)}

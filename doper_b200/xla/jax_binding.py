@@ -63,6 +63,12 @@ def _ws_bytes(B, S, per_env, n_steps, ckpt_every):  # pragma: no cover
     return int(lib.doper_rollout_workspace_bytes(ctypes.byref(d)))
 
 
+def _scratch_bytes(B, S, per_env, n_steps, ckpt_every):  # pragma: no cover
+    d = RolloutDesc()
+    d.B, d.S, d.per_env, d.n_steps, d.ckpt_every = B, S, per_env, n_steps, ckpt_every
+    return int(lib.doper_rollout_bwd_scratch_bytes(ctypes.byref(d)))
+
+
 def prepare_scene(segments):  # pragma: no cover
     per_env = segments.ndim == 4
     n, S = (segments.shape[0], segments.shape[1]) if per_env else (1, segments.shape[0])
@@ -88,8 +94,9 @@ def _bwd(S, per_env, n_steps, ckpt_every, dt, constants_tuple, attractor, res, c
     scene_ws, ws = res
     xT_bar, vT_bar = cot
     B = xT_bar.shape[0]
-    out = (jax.ShapeDtypeStruct((B, 2), jnp.float32), jax.ShapeDtypeStruct((B, 2), jnp.float32))
-    x0_bar, v0_bar = jax.ffi.ffi_call("doper_rollout_bwd_ffi", out)(
+    out = (jax.ShapeDtypeStruct((B, 2), jnp.float32), jax.ShapeDtypeStruct((B, 2), jnp.float32),
+           jax.ShapeDtypeStruct((_scratch_bytes(B, S, per_env, n_steps, ckpt_every),), jnp.uint8))
+    x0_bar, v0_bar, _scratch = jax.ffi.ffi_call("doper_rollout_bwd_ffi", out)(
         scene_ws, ws, xT_bar, vT_bar, **_attrs(S, per_env, n_steps, ckpt_every, dt, dict(constants_tuple), attractor))
     return None, x0_bar, v0_bar  # no gradient w.r.t. the scene (reference: argnums=4 only)
 

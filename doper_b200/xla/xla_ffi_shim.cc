@@ -12,7 +12,9 @@
 // Handlers (all launch on XLA's stream, allocate nothing, never synchronise):
 //   doper_scene_prepare_ffi   segments f32[n_scenes,S,2,2]            -> scene_ws u8[W]
 //   doper_rollout_fwd_ffi     scene_ws, x0, v0 f32[B,2]               -> xT, vT f32[B,2], ws u8[R]
-//   doper_rollout_bwd_ffi     scene_ws, ws, xT_bar, vT_bar f32[B,2]   -> x0_bar, v0_bar f32[B,2]
+//   doper_rollout_bwd_ffi     scene_ws, ws, xT_bar, vT_bar f32[B,2]   -> x0_bar, v0_bar f32[B,2], scratch u8[Q]
+//                             (ws is an immutable XLA input: everything the backward writes goes to its own
+//                             result buffers; `scratch` is sized by doper_rollout_bwd_scratch_bytes and dropped)
 // Attributes: S, per_env, n_steps, ckpt_every (i32), dt, radius, mass, friction, elasticity,
 // attractor_strength, attractor_x, attractor_y (f32).
 #if defined(__has_include)
@@ -45,7 +47,7 @@ doper_rollout_desc MakeDesc(int64_t B, int32_t S, int32_t per_env, int32_t n_ste
     d.B = B; d.S = S; d.per_env = per_env; d.n_steps = n_steps; d.ckpt_every = ckpt_every; d.dt = dt;
     d.consts[0] = radius; d.consts[1] = mass; d.consts[2] = friction; d.consts[3] = elasticity; d.consts[4] = ks;
     d.attractor[0] = ax; d.attractor[1] = ay;
-    d.lanes_per_ball = 0; d.flags = 0;
+    d.lanes_per_ball = 0; d.flags = 0; d.hit_capacity = 0;
     return d;
 }
 
@@ -78,14 +80,17 @@ ffi::Error RolloutFwdImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> scene_ws, ff
 
 ffi::Error RolloutBwdImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> scene_ws, ffi::Buffer<ffi::U8> ws,
                           ffi::Buffer<ffi::F32> xT_bar, ffi::Buffer<ffi::F32> vT_bar,
-                          ffi::ResultBuffer<ffi::F32> x0_bar, ffi::ResultBuffer<ffi::F32> v0_bar, int32_t S,
-                          int32_t per_env, int32_t n_steps, int32_t ckpt_every, float dt, float radius,
+                          ffi::ResultBuffer<ffi::F32> x0_bar, ffi::ResultBuffer<ffi::F32> v0_bar,
+                          ffi::ResultBuffer<ffi::U8> scratch, int32_t S, int32_t per_env, int32_t n_steps, int32_t ckpt_every, float dt, float radius,
                           float mass, float friction, float elasticity, float ks, float ax, float ay) {
     const int64_t B = xT_bar.dimensions()[0];
     doper_rollout_desc d = MakeDesc(B, S, per_env, n_steps, ckpt_every, dt, radius, mass, friction, elasticity, ks,
                                     ax, ay);
-    return Status(doper_rollout_bwd(stream, &d, scene_ws.typed_data(), ws.typed_data(), xT_bar.typed_data(),
-                                    vT_bar.typed_data(), x0_bar->typed_data(), v0_bar->typed_data()),
+    if (scratch->element_count() < doper_rollout_bwd_scratch_bytes(&d)) return Status(DOPER_ERR_WORKSPACE, "rollout_bwd");
+    const void* ws_in = ws.typed_data();  // const: the forward's workspace is read only
+    return Status(doper_rollout_bwd(stream, &d, scene_ws.typed_data(), ws_in, scratch->typed_data(),
+                                    xT_bar.typed_data(), vT_bar.typed_data(), x0_bar->typed_data(),
+                                    v0_bar->typed_data()),
                   "doper_rollout_bwd");
 }
 
@@ -121,7 +126,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(doper_rollout_bwd_ffi, RolloutBwdImpl,
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>() DOPER_ROLLOUT_ATTRS());
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>() DOPER_ROLLOUT_ATTRS());
 #else
 // jaxlib's FFI headers are not available: nothing to build (see the note at the top).
 extern "C" int doper_xla_ffi_shim_unavailable(void) { return 1; }

@@ -34,11 +34,21 @@
  *   trajectory (optional)  traj_x, traj_v, traj_a  [n_steps][B][2]
  *   hit log   int32 : bit 31 = the step collided; bits 30 / 29 = |v_y| < 1 / |v_x| < 1 at the start
  *             of the step (the friction clip's derivative: all the adjoint of a free-flight step
- *             needs); bits 0-28 = closest segment index (valid at collisions; at every step with
- *             flags bit 17).  [n_steps][B] or [B][n_steps] (see doper_rollout_log_ball_major)
- *   hit states [n_steps][B][4] = (x,y,vx,vy) at the START of each collided step; other entries are
- *             never written nor read
+ *             needs); bits 0-28 = payload.  Step without a collision: closest segment index with
+ *             flags bit 17, else 0.  Collided step: slot of the step's collision record, or, with
+ *             bit 28 set, the segment index itself (no record could be stored; the backward then
+ *             replays the step from its checkpoint).
+ *             [n_steps][B] or [B][n_steps] (see doper_rollout_log_ball_major)
+ *   collision records  32 B each, appended by the forward in arrival order: float (x,y,vx,vy) at the
+ *             START of the collided step, then int32 (ball low word, step, segment index, ball high
+ *             word).  The record count is the int32 at offset 0 of the workspace.
  *   checkpoints [ceil(n_steps/ckpt_every)][B][4] = (x,y,vx,vy) at the START of step k*ckpt_every
+ *   workspace (doper_rollout_workspace_bytes): [256 B header | checkpoints | hit log | records], each
+ *             part 256-B aligned; written by doper_rollout_fwd only.
+ *   backward scratch (doper_rollout_bwd_scratch_bytes): one 4x4 binary64 Jacobian per record
+ *             capacity; written by doper_rollout_bwd (so that the forward's workspace stays
+ *             read-only for the backward: XLA input buffers are immutable, and two backward calls
+ *             may share one forward on different streams with different scratch buffers).
  *   consts    host float[5] = {radius, mass, rolling_friction_coefficient,
  *             walls_elasticity, attractor_strength}  (reference constants dict,
  *             doper/sim/ball_sim.py:104,119,127-129,195-200); g = 9.8f is the literal
@@ -68,7 +78,7 @@ enum {
     DOPER_ERR_UNSUPPORTED = 7  /* e.g. S >= 2^31, triangle count mismatch */
 };
 
-#define DOPER_ABI_VERSION 1
+#define DOPER_ABI_VERSION 2
 
 int doper_abi_version(void);
 const char* doper_error_string(int code);
@@ -137,26 +147,31 @@ typedef struct {
     float attractor[2];
     int32_t lanes_per_ball; /* 0 = auto; else 1,2,4,8,16,32 lanes cooperating on one ball's sweep */
     int32_t flags;          /* bit 0: force the exact (unfiltered) sweep;
-                               bit 1: force the sequential (oracle-order, bit-exact) backward;
+                               bit 1: the sequential backward: fp32 in the reference's operation
+                                      order, one thread per ball (bit-identical to the oracle's
+                                      adjoint).  Default: the binary64 chunk-parallel backward (the
+                                      adjoint of the real-arithmetic step on the fp32 trajectory,
+                                      rounded once to fp32 at the end);
                                bit 2: force the shared-memory lane-split forward kernel over the
                                       register-resident one (only with lanes_per_ball != 0);
                                bit 3: disable the time-parallel (warp per ball) full-sweep forward kernel;
                                bit 15 / bit 16: forbid / force the broad-phase (candidate list)
                                       forward kernels; bit 18: with bit 16 and lanes_per_ball >= 2, the
                                       time-parallel (lane = step) variant instead of the lane-split one;
-                               bit 19: no hit-state array in the workspace (saves 16 B per ball-step;
-                                      the backward then replays collided K-blocks from checkpoints);
+                               bit 19: no collision records (the backward replays every collided
+                                      step from its checkpoint: slower, same results);
                                bit 17: hit log holds the exact closest index at EVERY step (the
                                       broad-phase kernel otherwise logs it at collisions only and 0
                                       elsewhere: the index is consumed at collisions only); the
                                       candidate lists then hold the argmin of every point of their
                                       disc instead of just the segments the ball can touch (slower).
-                               None of these changes x_T, v_T, trajectories, hit flags, collision
-                               indices or gradients. */
+                               None of these changes x_T, v_T, trajectories, hit flags or collision
+                               indices; bit 1 selects the rounding of the gradient (see above). */
+    int64_t hit_capacity;   /* collision records the workspace can hold; 0 = library default
+                               (max(65,536, B n_steps / 64), at most B n_steps) */
 } doper_rollout_desc;
 
-/* The checkpoint period the library will use for this rollout (ckpt_every if > 0, else chosen
- * from B and n_steps: small batches get 32 or 64 chunks per ball for the chunk-parallel backward). */
+/* The checkpoint period the library will use for this rollout (ckpt_every if > 0, else 32). */
 int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d);
 
 /* Layout of the hit log inside the workspace: 0 = [n_steps][B] (step-major), 1 = [B][n_steps]
@@ -168,8 +183,11 @@ int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d);
  * a static string, for benchmark / profile reports. */
 const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward);
 
-/* Bytes of the backward workspace (checkpoints + hit log + hit states) for this rollout. */
+/* Bytes of the forward's workspace (header + checkpoints + hit log + collision records). */
 size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d);
+
+/* Bytes of the backward's scratch buffer (256-B aligned device memory, contents undefined on entry). */
+size_t doper_rollout_bwd_scratch_bytes(const doper_rollout_desc* d);
 
 /* Forward rollout.  traj_* and ws may be NULL (no trajectory / no backward wanted). */
 int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
@@ -177,11 +195,11 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
                       float* traj_v, float* traj_a, void* ws);
 
 /* Backward: cotangents (xT_bar, vT_bar) -> (x0_bar, v0_bar).  vT_bar / x0_bar may be NULL.
- * ws is the forward's workspace; its trailing scratch area (a list of balls handed from the
- * sequential to the chunk-parallel kernel) is written. */
+ * ws is the forward's workspace (read only); bwd_scratch is written (it may be NULL with flags
+ * bit 1, bit 17 or bit 19, where doper_rollout_bwd_scratch_bytes has nothing to hold). */
 int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
-                      const void* ws, const float* xT_bar, const float* vT_bar, float* x0_bar,
-                      float* v0_bar);
+                      const void* ws, void* bwd_scratch, const float* xT_bar, const float* vT_bar,
+                      float* x0_bar, float* v0_bar);
 
 /* loss_per_ball[b] = |xT[b].x - t.x| + |xT[b].y - t.y|; *loss_sum = sum_b (deterministic order);
  * xT_bar[b] = sign(xT[b] - t) (the seed of the backward).  loss_per_ball / xT_bar nullable. */
@@ -191,7 +209,7 @@ int doper_l1_loss(doper_stream_t stream, int64_t B, const float* xT, const float
 /* vmapped_grad_and_value in one call: fwd -> loss -> bwd on `stream`.
  * scratch: device float[2*B] (holds xT_bar).  x0_bar nullable. */
 int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
-                         const float* x0, const float* v0, const float target[2], void* ws,
+                         const float* x0, const float* v0, const float target[2], void* ws, void* bwd_scratch,
                          float* scratch, float* loss_sum, float* loss_per_ball, float* xT,
                          float* vT, float* v0_bar, float* x0_bar);
 

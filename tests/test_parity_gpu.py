@@ -153,7 +153,7 @@ def test_value_and_grad_sequential_backward_bitexact(sim, cref, n_balls, n_steps
                               w["segments"], w["x0"], w["v0"])
     (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(
         n_steps / 1000, n_steps, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], w["constants"],
-        _opts(ball_sim, ckpt_every=K, sequential_backward=True, hit_state_array=hit_states))
+        _opts(ball_sim, ckpt_every=K, sequential_backward=True, hit_records=hit_states))
     assert isinstance(gv, np.ndarray) and gv.shape == (n_balls, 2)  # host in -> host out
     assert_bitexact(xT, ref["x_T"], "x_T")
     assert_bitexact(vT, ref["v_T"], "v_T")
@@ -162,26 +162,32 @@ def test_value_and_grad_sequential_backward_bitexact(sim, cref, n_balls, n_steps
     assert_bitexact(gv, ref["grad_v0"], "dL/dv0 vs C adjoint")
 
 
-# End-of-rollout gradient tolerance.  BASELINE.json's north_star asks for ~1e-4; measured against
-# the float64 adjoint evaluated on the same fp32 trajectory ("truth64", oracle_grad_truth64), the
-# reference-order fp32 adjoint ITSELF (the oracle's C adjoint, and equally torch autograd) is off
-# by up to 3e-4 (500 steps), 7e-4 (1,000) and 2e-3 (2,000 steps) on its worst ball out of ~2,000
-# (median 2e-7): bounces amplify rounding.  So the chunk-parallel backward is held to: its 99th
-# percentile and its worst case must each be within max(GRAD_RTOL, 2x the reference-order fp32
-# adjoint's own figure) of truth64.  Errors are relative to the per-ball gradient norm.
+# End-of-rollout gradient tolerance.  BASELINE.json's north_star asks for ~1e-4 against the reference's
+# (reference-order, fp32) adjoint.  Measured against the float64 adjoint evaluated on the same fp32
+# trajectory ("truth64", oracle_grad_truth64), that fp32 adjoint ITSELF (the oracle's C adjoint, and equally
+# torch autograd) is off by up to 3e-4 (500 steps), 7e-4 (1,000) and 2e-3 (2,000 steps) on its worst ball out
+# of ~2,000 (median 2e-7): bounces amplify rounding.  The default backward evaluates the adjoint in binary64
+# and rounds once at the end, so it is held to truth64 at fp32 resolution (TRUTH_RTOL, relative to the
+# per-ball gradient norm), and its distance from the reference-order fp32 adjoint is bounded by that
+# adjoint's own error: within GRAD_RTOL on >= 99.9 % of the balls, never more than the fp32 adjoint's own
+# distance from truth64 (+ TRUTH_RTOL).
 GRAD_RTOL = 1e-4
+TRUTH_RTOL = 1e-6
 
 
-def check_grad_against_truth(gv, cref, w, n_steps, c):
+def check_grad_against_truth(gv, cref, w, n_steps, c, consts=None):
     dt = np.float32((n_steps / 1000) / n_steps)
     args = (n_steps, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
     truth, _ = cref.grad_truth64(*args)
     seq = cref.value_and_grad(*args)["grad_v0"]
-    e_got, e_seq = grad_rel_err(gv, truth), grad_rel_err(seq, truth)
-    assert np.isfinite(gv).all()
-    q_got, q_seq = np.quantile(e_got, 0.99), np.quantile(e_seq, 0.99)
-    assert q_got <= max(GRAD_RTOL, 2 * q_seq), (q_got, q_seq)
-    assert e_got.max() <= max(2 * e_seq.max(), GRAD_RTOL), (e_got.max(), e_seq.max())
+    # parity is asserted where the oracle gradient is finite and representable
+    ok = np.isfinite(seq).all(1) & np.isfinite(truth).all(1) & (np.abs(truth).max(1) < 1e30)
+    assert ok.mean() > 0.95 and np.isfinite(gv[ok]).all()
+    e_got, e_seq = grad_rel_err(gv[ok], truth[ok]), grad_rel_err(seq[ok], truth[ok])
+    assert e_got.max() <= TRUTH_RTOL, ("default backward vs float64 truth", e_got.max())
+    d = grad_rel_err(gv[ok], seq[ok].astype(np.float64))  # distance from the reference-order fp32 adjoint
+    assert np.quantile(d, 0.999) <= max(GRAD_RTOL, 2 * np.quantile(e_seq, 0.999)), (np.quantile(d, 0.999), np.quantile(e_seq, 0.999))
+    assert d.max() <= 1.01 * e_seq.max() + 2 * TRUTH_RTOL, (d.max(), e_seq.max())
     return e_got.max(), e_seq.max()
 
 
@@ -189,8 +195,8 @@ def check_grad_against_truth(gv, cref, w, n_steps, c):
 @pytest.mark.parametrize("n_balls,n_steps,K", [(1, 300, 0), (16, 300, 0), (257, 500, 0), (1024, 130, 0),
                                                (333, 500, 25), (2048, 1000, 0), (1024, 2000, 0)])
 def test_value_and_grad_default_backward(sim, cref, n_balls, n_steps, K, hit_states):
-    """Default plan (chunk-parallel backward for small batches): forward bit-exact, gradient as
-    accurate as the reference-order fp32 adjoint (same mathematics, different summation order)."""
+    """Default plan (binary64 chunk-parallel backward): forward bit-exact, gradient = the float64 adjoint of
+    the fp32 trajectory rounded to fp32; hit_states False: every collided step replayed from checkpoints."""
     ball_sim, _ = sim
     w = syn.make_workload("c2", n_balls=n_balls)
     c = onp.make_constants(w["constants"])
@@ -198,7 +204,7 @@ def test_value_and_grad_default_backward(sim, cref, n_balls, n_steps, K, hit_sta
                               w["segments"], w["x0"], w["v0"])
     (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(
         n_steps / 1000, n_steps, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], w["constants"],
-        _opts(ball_sim, ckpt_every=K, hit_state_array=hit_states))
+        _opts(ball_sim, ckpt_every=K, hit_records=hit_states))
     assert_bitexact(xT, ref["x_T"], "x_T")
     assert_bitexact(vT, ref["v_T"], "v_T")
     check_grad_against_truth(gv, cref, w, n_steps, c)
@@ -227,16 +233,18 @@ def test_bouncy_regime_many_collisions(sim, cref, lanes):
     (loss, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"],
                                                           w["attractor"], consts,
                                                           _opts(ball_sim, lanes_per_ball=lanes, sequential_backward=True,
-                                                                hit_state_array=(lanes != 8)))
+                                                                hit_records=(lanes != 8)))
     refg = cref.value_and_grad(n, np.float32((n / 1000) / n), c, w["attractor"], w["target"], w["segments"],
                                w["x0"], w["v0"])
     assert_bitexact(gv, refg["grad_v0"], "gradient (sequential backward)")
 
 
-def test_hybrid_backward_hands_sliding_balls_to_the_chunk_parallel_kernel(sim, cref):
-    """> 32,768 balls use the sequential backward; balls in sliding contact (hundreds of collided steps: a
-    serial ~2.6 us chain each) are handed to the chunk-parallel kernel.  Gradients stay as accurate as
-    the reference-order fp32 adjoint, and flags bit 1 still gives the bit-exact sequential result."""
+@pytest.mark.parametrize("capacity", [0, 4096])
+def test_default_backward_sliding_contact_large_batch(sim, cref, capacity):
+    """33,000 balls pressed against the obstacles by a strong attractor (hundreds of collided steps per ball,
+    > 1e6 collision records).  capacity 4096: the record area overflows at once, so almost every collided
+    step takes the replay-from-checkpoint path; same gradients either way.  flags bit 1 still gives the
+    bit-exact sequential result."""
     ball_sim, _ = sim
     w = syn.make_workload("c2", n_balls=33000)
     consts = dict(w["constants"]); consts["attractor_strength"] = 2000.0
@@ -244,23 +252,44 @@ def test_hybrid_backward_hands_sliding_balls_to_the_chunk_parallel_kernel(sim, c
     c = onp.make_constants(consts)
     dt = np.float32((n / 1000) / n)
     ref = cref.value_and_grad(n, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
-    assert (ref["hit"].sum(0) > 128).sum() > 50  # plenty of balls beyond the hand-over threshold
+    assert (ref["hit"].sum(0) > 128).sum() > 50
     args = (n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], consts)
-    (_, (xT, _)), gv = ball_sim.vmapped_grad_and_value(*args)
+    (_, (xT, _)), gv = ball_sim.vmapped_grad_and_value(*args, _opts(ball_sim, hit_capacity=capacity))
     assert_bitexact(xT, ref["x_T"], "x_T")
-    (_, _), gv_seq = ball_sim.vmapped_grad_and_value(*args, _opts(ball_sim, sequential_backward=True))
+    (_, _), gv_seq = ball_sim.vmapped_grad_and_value(*args, _opts(ball_sim, sequential_backward=True, hit_capacity=capacity))
     assert_bitexact(gv_seq, ref["grad_v0"], "sequential backward")
     # this regime is violent (|gradient| up to 1e35; the reference-order fp32 adjoint itself overflows to NaN
     # on a few dozen balls): parity is asserted where the oracle gradient is finite and moderate
     truth, _ = cref.grad_truth64(n, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
     ok = np.isfinite(ref["grad_v0"]).all(1) & np.isfinite(truth).all(1) & (np.abs(truth).max(1) < 1e12)
     assert ok.mean() > 0.95 and np.isfinite(gv[ok]).all()
-    e_got, e_seq = grad_rel_err(gv[ok], truth[ok]), grad_rel_err(ref["grad_v0"][ok], truth[ok])
-    assert np.quantile(e_got, 0.99) <= max(GRAD_RTOL, 2 * np.quantile(e_seq, 0.99))
-    assert e_got.max() <= max(2 * e_seq.max(), GRAD_RTOL), (e_got.max(), e_seq.max())
-    heavy = ok & (ref["hit"].sum(0) > 128)
-    assert heavy.sum() > 50 and not np.array_equal(gv[heavy], gv_seq[heavy])  # the hand-over happened (other rounding order)
-    assert_bitexact(gv[ref["hit"].sum(0) == 0], gv_seq[ref["hit"].sum(0) == 0], "balls that never collided")
+    e_got = grad_rel_err(gv[ok], truth[ok])
+    assert e_got.max() <= TRUTH_RTOL, e_got.max()
+    if capacity:
+        h = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], consts,
+                                     _opts(ball_sim, hit_capacity=capacity))
+        assert h["records_seen"] > 100 * capacity and h["record_capacity"] == capacity
+        assert np.array_equal(h["hit"], ref["hit"]) and np.array_equal(h["idx"][ref["hit"]], ref["idx"][ref["hit"]])
+
+
+def test_c2_default_vs_reference_order_gradient_distribution(sim, cref):
+    """The benchmarked configuration (C2: 4,096 balls x 500 steps): the default backward against the
+    reference-order fp32 adjoint over ALL balls, and both against float64 truth."""
+    ball_sim, _ = sim
+    w = syn.make_workload("c2")
+    n = w["n_steps"]
+    c = onp.make_constants(w["constants"])
+    (_, _), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"],
+                                                 w["attractor"], w["constants"])
+    (_, _), gv_seq = ball_sim.vmapped_grad_and_value(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"],
+                                                     w["attractor"], w["constants"], _opts(ball_sim, sequential_backward=True))
+    ref = cref.value_and_grad(n, np.float32((n / 1000) / n), c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+    assert_bitexact(gv_seq, ref["grad_v0"], "sequential backward vs oracle order")
+    e_got, e_seq = check_grad_against_truth(gv, cref, w, n, c)
+    d = grad_rel_err(gv, gv_seq.astype(np.float64))
+    assert (d <= GRAD_RTOL).mean() >= 0.999, (d > GRAD_RTOL).sum()
+    print(f"C2 default-vs-reference-order: median {np.median(d):.2e} q999 {np.quantile(d, 0.999):.2e} max {d.max():.2e}; "
+          f"vs truth64: default {e_got:.2e}, reference order {e_seq:.2e}")
 
 
 def test_gradient_vs_torch_autograd(sim):
@@ -579,9 +608,10 @@ def test_full_size_multi_gpu_configs_properties(sim, cref, name, n_balls):
                               w["x0"][sl], w["v0"][sl])
     assert_bitexact(xT2, ref["x_T"], "slice vs oracle: x_T")
     assert_bitexact(vT2, ref["v_T"], "slice vs oracle: v_T")
-    ok = np.isfinite(ref["grad_v0"]).all(1)
-    e = grad_rel_err(gv[sl][ok], ref["grad_v0"][ok])
-    assert np.quantile(e, 0.9) < 1e-4 and e.max() < 5e-2, (np.quantile(e, 0.9), e.max())
+    # gradients of the slice, taken from the FULL-batch run: float64 truth at fp32 resolution, and no further
+    # from the reference-order fp32 adjoint than that adjoint is from truth (same rule as the C2 test)
+    ws = dict(w); ws["x0"], ws["v0"], ws["segments"] = w["x0"][sl], w["v0"][sl], seg_sl
+    check_grad_against_truth(gv[sl], cref, ws, n, c)
     assert abs(float(loss) - np.abs(xT - w["target"]).sum(dtype=np.float64)) <= 1e-5 * float(loss)
     (_, (xT3, _)), gv3 = ball_sim.vmapped_grad_and_value(*args, w["x0"], w["v0"], w["target"], w["attractor"],
                                                         w["constants"])

@@ -50,6 +50,6 @@ for _ in range(reps):
     check(lib.doper_rollout_fwd(st, ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT), 0, 0, 0,
                                 ptr(bufs.ws)), "fwd")
     check(lib.doper_l1_loss(st, B, ptr(xT), tgt, 0, ptr(ls), ptr(bar)), "loss")
-    check(lib.doper_rollout_bwd(st, ctypes.byref(desc), ptr(sws), ptr(bufs.ws), ptr(bar), 0, ptr(gx), ptr(gv)), "bwd")
+    check(lib.doper_rollout_bwd(st, ctypes.byref(desc), ptr(sws), ptr(bufs.ws), ptr(bufs.bwd_scratch), ptr(bar), 0, ptr(gx), ptr(gv)), "bwd")
 torch.cuda.synchronize()
 print("ok", name, var, B, n, float(ls))

@@ -57,7 +57,7 @@ def main():
                                                   0, 0, 0, ptr(bufs.ws)), "fwd")
         f_ms = time_ms(fwd)
         check(lib.doper_l1_loss(st, B, ptr(xT), tgt, 0, ptr(ls), ptr(bar)), "loss")
-        b_ms = time_ms(lambda: check(lib.doper_rollout_bwd(st, ctypes.byref(desc), ptr(sws), ptr(bufs.ws), ptr(bar), 0,
+        b_ms = time_ms(lambda: check(lib.doper_rollout_bwd(st, ctypes.byref(desc), ptr(sws), ptr(bufs.ws), ptr(bufs.bwd_scratch), ptr(bar), 0,
                                                            ptr(gx), ptr(gv)), "bwd"))
         out[tag] = {"fwd_ms": round(f_ms, 4), "bwd_ms": round(b_ms, 4)}
         if tag != "as_is" and thresholds is not None:

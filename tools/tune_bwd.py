@@ -32,5 +32,5 @@ for K, seq in ((0, False), (32, False), (16, False), (8, False), (4, False), (0,
     ls = torch.empty(1, device=dev)
     check(lib.doper_rollout_fwd(st, ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT), 0, 0, 0, ptr(bufs.ws)), "fwd")
     check(lib.doper_l1_loss(st, B, ptr(xT), tgt, 0, ptr(ls), ptr(bar)), "loss")
-    ms = time_ms(lambda: check(lib.doper_rollout_bwd(st, ctypes.byref(desc), ptr(sws), ptr(bufs.ws), ptr(bar), 0, ptr(gx), ptr(gv)), "bwd"))
+    ms = time_ms(lambda: check(lib.doper_rollout_bwd(st, ctypes.byref(desc), ptr(sws), ptr(bufs.ws), ptr(bufs.bwd_scratch), ptr(bar), 0, ptr(gx), ptr(gv)), "bwd"))
     print(f"{name} B={B} K={lib.doper_rollout_ckpt_every(ctypes.byref(desc))} sequential={seq} kernel={lib.doper_rollout_plan_name(ctypes.byref(desc), 1).decode()}: bwd {ms:.4f} ms", flush=True)

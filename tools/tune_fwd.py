@@ -63,7 +63,7 @@ def main():
             ms = time_ms(lambda: check(lib.doper_rollout_fwd(st, ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0),
                                                               ptr(xT), ptr(vT), 0, 0, 0, ptr(bufs.ws)), "fwd"))
             check(lib.doper_l1_loss(st, B, ptr(xT), tgt, 0, ptr(ls), ptr(bar)), "loss")
-            bms = time_ms(lambda: check(lib.doper_rollout_bwd(st, ctypes.byref(desc), ptr(sws), ptr(bufs.ws), ptr(bar),
+            bms = time_ms(lambda: check(lib.doper_rollout_bwd(st, ctypes.byref(desc), ptr(sws), ptr(bufs.ws), ptr(bufs.bwd_scratch), ptr(bar),
                                                                0, ptr(gx), ptr(gv)), "bwd"))
         except Exception as e:
             ms, bms = repr(e), None
