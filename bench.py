@@ -214,7 +214,7 @@ def ours(args):
                                    broad_phase=(False if args.full_sweep else None))
     scene = JaxScene(w["segments"])
     desc = ball_sim._make_desc(B, scene, w["sim_time"], n_steps, w["attractor"], w["constants"], opts)
-    _, sws = scene.prepared(device)
+    _, sws = scene.prepared(device, float(desc.consts[0]))
     x0 = torch.tensor(w["x0"], device=device)
     v0 = torch.tensor(w["v0"], device=device)
     bufs = ball_sim._Buffers.get(device, desc)

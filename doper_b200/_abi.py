@@ -72,7 +72,7 @@ def _load() -> ctypes.CDLL:
     lib.doper_error_string.argtypes = [ctypes.c_int]
     lib.doper_scene_workspace_bytes.restype = c_size_t
     lib.doper_scene_workspace_bytes.argtypes = [c_int64, c_int32]
-    lib.doper_scene_prepare.argtypes = [vp, c_int64, c_int32, fp, vp]
+    lib.doper_scene_prepare.argtypes = [vp, c_int64, c_int32, fp, c_float, vp]
     lib.doper_closest_segment.argtypes = [vp, c_int64, c_int32, fp, fp, vp, vp, fp, fp]
     lib.doper_points_inside.argtypes = [vp, c_int64, c_int32, fp, fp, vp]
     lib.doper_rollout_ckpt_every.restype = c_int32
@@ -101,7 +101,7 @@ def _load() -> ctypes.CDLL:
     lib.doper_peer_open.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
     lib.doper_peer_close.argtypes = [c_void_p]
     lib.doper_peer_free.argtypes = [c_void_p]
-    lib.doper_allreduce_oneshot.argtypes = [vp, c_int32, c_int32, POINTER(c_void_p), c_int32, fp, fp, vp]
+    lib.doper_allreduce_oneshot.argtypes = [vp, c_int32, c_int32, POINTER(c_void_p), c_int32, fp, fp, vp, ctypes.c_double]
     for name in EXPORTS:
         if name not in ("doper_peer_buffer_bytes", "doper_error_string", "doper_scene_workspace_bytes",
                         "doper_rollout_workspace_bytes", "doper_rollout_bwd_scratch_bytes", "doper_abi_version", "doper_rollout_ckpt_every",

@@ -1,0 +1,218 @@
+// fwd_baked.cuh: forward rollout over the BAKED broad phase (static per-cell candidate lists, scene.cuh) —
+// part of the doper_b200 CUDA translation unit (included by kernels.cu).
+//
+// The per-ball candidate lists of fwd_broad.cuh are rebuilt every ~35 steps by a scan of the whole scene
+// (28 % of the C2 forward's warp cycles, plus the displacement guards, the "trouble" states and the
+// warp-uniform refresh that makes one stale ball stall 31 others in the one-thread-per-ball kernel).  For a
+// shared scene none of that depends on the ball: scene_bake_kernel builds, once per scene, the hit list of
+// every cell of a uniform grid, and a step only looks its point's cell up:
+//     empty cell            -> no segment within r of any point of the cell: no collision, no arithmetic
+//     cell with a list      -> the estimate of every list entry (9 FMAs each); all above far2 -> no collision;
+//                              else the reference arithmetic for the entries the filter keeps (sweep.cuh)
+//     outside the grid      -> further than r_max + h from every segment: no collision
+//     |point| > 2 M, NaN / inf, degenerate scene, r > r_max -> reference arithmetic over every segment
+// The proof obligations are those of the per-ball hit lists (sweep.cuh) with the cell centre as list centre
+// and rho = half diagonal / 0.98; results are bit-identical to every other forward kernel (same tests).
+//
+// Organisation: G lanes per ball, LANE = TIME STEP as in rollout_fwd_tpc_kernel (chain of up to G free-flight
+// steps, every lane tests its own step, ballot for the first collision, commit, resolve), with nothing else
+// left in the round: the critical path per step is the free-flight chain plus 1/G of a cell look-up and a
+// vote.  G = 1 is one thread per ball (large batches): chain, look-up, commit per step, no warp-wide
+// primitive at all.  The scene and the baked arrays are staged into shared memory by 1-D TMA bulk copies
+// when they fit (STAGED), else read in place (L2).
+#pragma once
+#include "fwd_broad.cuh"
+
+namespace doper {
+
+struct BakeView {
+    const uint32_t* cell_start;
+    const unsigned short* items;
+    float x0, y0, inv_h, fnx, fny, far2, M2;  // M2 = 2 M: beyond it a point takes the exact path
+    int nx, ok;
+};
+
+// (hit, idx) of ONE point against the baked lists; reference semantics: hit = (min_j d_ref_j <= r), idx = its
+// first index (valid only when hit).
+__device__ __forceinline__ bool baked_hit(const SceneView& sc, const BakeView& bk, float px, float py, float r, int& idx) {
+    const float M = fmaxf(fabsf(px), fabsf(py));
+    idx = 0;
+    if (!bk.ok || !(M <= bk.M2)) {  // NaN / far-away point, degenerate scene, r > r_max: every pair, reference arithmetic
+        float dist;
+        unpack_key(lane_exact<1>(sc, px, py, 0), idx, dist);
+        return dist <= r;
+    }
+    const float fx = (px - bk.x0) * bk.inv_h, fy = (py - bk.y0) * bk.inv_h;
+    if (!(fx >= 0.0f && fx < bk.fnx && fy >= 0.0f && fy < bk.fny)) return false;  // outside the grid: far from everything
+    const int cell = (int)fy * bk.nx + (int)fx;
+    const int k0 = (int)bk.cell_start[cell], k1 = (int)bk.cell_start[cell + 1];
+    if (k0 == k1) return false;
+    float amin = __int_as_float(0x7f800000);
+    for (int k = k0; k < k1; ++k) {
+        const int i = bk.items[k];
+        amin = fminf(amin, approx_d2(px, py, sc.q[i], sc.rl[i]));
+    }
+    if (amin > bk.far2) return false;  // every list entry provably further than r
+    const float Mq = fmaxf(sc.scale, M);
+    const float thr = __fmaf_rn(amin, kFilterOneEps, kFilterKappaPerM2 * Mq * Mq);
+    unsigned long long key = kNoKey;
+    for (int k = k0; k < k1; ++k) {
+        const int i = bk.items[k];
+        const float4 q = sc.q[i];
+        if (approx_d2(px, py, q, sc.rl[i]) <= thr) {
+            const unsigned long long kk = make_key(cand_dist(px, py, q), i);
+            key = kk < key ? kk : key;
+        }
+    }
+    float dist;
+    unpack_key(key, idx, dist);
+    return dist <= r;  // NaN -> false (ball_sim.py:164)
+}
+
+template <int G, bool STAGED, int THREADS>
+__global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int BPB = THREADS / G;  // balls per block
+    constexpr unsigned kLow = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    const int tid = threadIdx.x, lane = tid % G, gbase = (tid & 31) - lane;
+    const SceneLayout L = scene_layout(1, p.S);
+    const SceneHeader hdr = *reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off);
+    const BakeHeader bh = *reinterpret_cast<const BakeHeader*>(p.scene_ws + L.bake_off);
+
+    SceneView sc;
+    BakeView bk;
+    if (STAGED) {
+        float4* sq = reinterpret_cast<float4*>(smem);
+        float* srl = reinterpret_cast<float*>(smem + (size_t)L.S_pad * sizeof(float4));
+        unsigned char* sbake = smem + (size_t)L.S_pad * 20;  // 16-byte aligned: S_pad is a multiple of 32
+        const uint32_t bbytes = (uint32_t)(bake_bytes(L.S_pad) - sizeof(BakeHeader));
+        uint64_t* bar = reinterpret_cast<uint64_t*>(sbake + bbytes);
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t qb = (uint32_t)L.S_pad * sizeof(float4), rb = (uint32_t)L.S_pad * sizeof(float);
+            mbar_expect_tx(bar, qb + rb + bbytes);
+            const unsigned char* gq = p.scene_ws + L.q_off;
+            const unsigned char* gr = p.scene_ws + L.rl_off;
+            const unsigned char* gb = p.scene_ws + L.bake_off + sizeof(BakeHeader);
+            for (uint32_t o = 0; o < qb; o += kTmaChunk) tma_load_1d(reinterpret_cast<unsigned char*>(sq) + o, gq + o, min(kTmaChunk, qb - o), bar);
+            for (uint32_t o = 0; o < rb; o += kTmaChunk) tma_load_1d(reinterpret_cast<unsigned char*>(srl) + o, gr + o, min(kTmaChunk, rb - o), bar);
+            for (uint32_t o = 0; o < bbytes; o += kTmaChunk) tma_load_1d(sbake + o, gb + o, min(kTmaChunk, bbytes - o), bar);
+        }
+        sc.q = sq; sc.rl = srl;
+        bk.cell_start = reinterpret_cast<const uint32_t*>(sbake);
+        bk.items = reinterpret_cast<const unsigned short*>(sbake + (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t));
+        sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
+        mbar_wait(bar, 0);
+    } else {
+        sc.q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off);
+        sc.rl = reinterpret_cast<const float*>(p.scene_ws + L.rl_off);
+        bk.cell_start = reinterpret_cast<const uint32_t*>(p.scene_ws + L.bake_off + sizeof(BakeHeader));
+        bk.items = reinterpret_cast<const unsigned short*>(bk.cell_start + (kBakeMaxCells + 16));
+        sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
+    }
+    const Consts c = p.c;
+    bk.x0 = bh.x0; bk.y0 = bh.y0; bk.inv_h = bh.inv_h; bk.fnx = bh.fnx; bk.fny = bh.fny; bk.nx = bh.nx;
+    bk.far2 = bh.far2; bk.M2 = 2.0f * bh.M;
+    bk.ok = bh.enabled && !sc.weird && c.r <= bh.r_max;
+
+    int64_t ball = (int64_t)blockIdx.x * BPB + tid / G;
+    const bool active = ball < p.B;
+    if (!active) ball = p.B - 1;  // absent ball: reads the last ball's inputs, never advances, writes nothing
+    const float2 xx = p.x0[ball], vv = p.v0[ball];
+    float x = xx.x, y = xx.y, vx = vv.x, vy = vv.y;  // state at step t (uniform within the group)
+    const int n = p.n_steps, K = p.K;
+    const int kshift = (K > 0 && (K & (K - 1)) == 0) ? (31 - __clz(K)) : -1;
+    int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
+    int t = active ? 0 : n;
+    int T = G;  // speculation length of the next round (1 after a collision at the round's first step)
+
+    while (__any_sync(0xffffffffu, t < n)) {
+        // ---- (1) free flight: lane k keeps step t + k ---------------------------------------------------
+        const int Tq = t < n ? min(T, n - t) : 0;
+        State my; my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
+        const int last = min(lane, Tq - 1);
+        {
+            float nmin = __int_as_float(0x7f800000), nmax = 0.0f;
+            for (int k = 0; k <= last; ++k) free_step_acc(my.x, my.y, my.vx, my.vy, c, my, nmin, nmax);
+            const bool ok = div_range_ok(nmin, nmax, c);
+            if (__any_sync(0xffffffffu, !ok)) {  // a numerator left the range of the fast division: redo exactly
+                my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
+                for (int k = 0; k <= last; ++k) free_step(my.x, my.y, my.vx, my.vy, c, my);
+            }
+        }
+        // state at the START of my step = the end state of the lane before me
+        float sx = x, sy = y, svx = vx, svy = vy;
+        if (G > 1) {
+            const float ux = __shfl_up_sync(0xffffffffu, my.x, 1, G), uy = __shfl_up_sync(0xffffffffu, my.y, 1, G);
+            const float uvx = __shfl_up_sync(0xffffffffu, my.vx, 1, G), uvy = __shfl_up_sync(0xffffffffu, my.vy, 1, G);
+            if (lane != 0) { sx = ux; sy = uy; svx = uvx; svy = uvy; }
+        }
+        // ---- (2) my step against the baked list of my point's cell -------------------------------------
+        const bool valid = lane < Tq;
+        int idx = 0;
+        const bool hit = valid && baked_hit(sc, bk, my.x, my.y, c.r, idx);
+        // ---- (3) first collision of the group, commit ---------------------------------------------------
+        int f = Tq;
+        bool ev_hit = false;
+        State out = my;
+        float nx = my.x, ny = my.y, nvx = my.vx, nvy = my.vy;  // G == 1: the state after my only step
+        if (G > 1) {
+            const unsigned evb = (__ballot_sync(0xffffffffu, hit) >> gbase) & kLow;
+            f = evb ? (__ffs(evb) - 1) : Tq;  // lanes < f: free flight, final
+            ev_hit = f < Tq;
+            const int src = f > 0 ? f - 1 : 0;
+            nx = __shfl_sync(0xffffffffu, my.x, src, G); ny = __shfl_sync(0xffffffffu, my.y, src, G);
+            nvx = __shfl_sync(0xffffffffu, my.vx, src, G); nvy = __shfl_sync(0xffffffffu, my.vy, src, G);
+            if (f == 0) { nx = x; ny = y; nvx = vx; nvy = vy; }
+            if (__any_sync(0xffffffffu, ev_hit)) {  // resolve the collision of step t + f (all lanes of the group, redundantly)
+                const int s = ev_hit ? f : 0;
+                const float bx = __shfl_sync(0xffffffffu, sx, s, G), by = __shfl_sync(0xffffffffu, sy, s, G);
+                const float bvx = __shfl_sync(0xffffffffu, svx, s, G), bvy = __shfl_sync(0xffffffffu, svy, s, G);
+                State b1;
+                b1.x = __shfl_sync(0xffffffffu, my.x, s, G); b1.y = __shfl_sync(0xffffffffu, my.y, s, G);
+                b1.vx = __shfl_sync(0xffffffffu, my.vx, s, G); b1.vy = __shfl_sync(0xffffffffu, my.vy, s, G);
+                b1.ax = __shfl_sync(0xffffffffu, my.ax, s, G); b1.ay = __shfl_sync(0xffffffffu, my.ay, s, G);
+                const int hidx = __shfl_sync(0xffffffffu, idx, s, G);
+                if (ev_hit) {
+                    const State r = resolve(bx, by, bvx, bvy, b1, sc.q[hidx], c);
+                    if (lane == f) out = r;
+                    nx = r.x; ny = r.y; nvx = r.vx; nvy = r.vy;
+                }
+            }
+        } else {
+            ev_hit = hit;
+            f = hit ? 0 : Tq;
+            if (hit) {
+                out = resolve(x, y, vx, vy, my, sc.q[idx], c);
+                nx = out.x; ny = out.y; nvx = out.vx; nvy = out.vy;
+            }
+        }
+        const int n_commit = f + (ev_hit ? 1 : 0);
+        if (active && lane < n_commit) {
+            const int ts = t + lane;
+            const bool h = ev_hit && lane == f;
+            const int payload = h ? record_collision(p.sink, ball, ts, sx, sy, svx, svy, idx) : 0;
+            if (hl) hl[(int64_t)ts * p.hl_st] = pack_log(payload, h, clip_bits(svx, svy));
+            if (p.ckpt) {  // K is usually a power of two: shift and mask instead of two integer divisions
+                const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
+                if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
+            }
+            const size_t o = (size_t)ts * p.B + ball;
+            if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
+            if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
+            if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+        }
+        if (Tq > 0) { x = nx; y = ny; vx = nvx; vy = nvy; }
+        t += n_commit;
+        // colliding step after step (resting / sliding contact): speculation is wasted, one step per round
+        // until the ball leaves the wall
+        if (G > 1) T = (ev_hit && f == 0) ? 1 : min(2 * T, G);
+    }
+    if (active && lane == 0) {
+        p.xT[ball] = make_float2(x, y);
+        p.vT[ball] = make_float2(vx, vy);
+    }
+}
+
+}  // namespace doper

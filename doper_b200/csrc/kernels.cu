@@ -8,7 +8,8 @@
 //   sweep.cuh      narrow phase (filtered exact sweep), broad phase (candidate lists), grid queries
 //   scene.cuh      prepared-scene layout, scene_prepare_kernel (+ uniform grid), TMA staging
 //   fwd_full.cuh   full-sweep forward kernels (every pair every step)
-//   fwd_broad.cuh  broad-phase forward kernels: rollout_fwd_cull_kernel, rollout_fwd_tpc_kernel (default plan)
+//   fwd_broad.cuh  broad-phase forward kernels with per-ball candidate lists: rollout_fwd_cull_kernel, rollout_fwd_tpc_kernel
+//   fwd_baked.cuh  rollout_fwd_baked_kernel: static per-cell candidate lists baked into the prepared scene (default plan, shared scenes)
 //   bwd.cuh        rollout_bwd_kernel (sequential fp32, bit-exact), rollout_bwd_jacobian_kernel + rollout_bwd_fold_kernel (binary64, default)
 //   queries.cuh    l1_loss_kernel, closest_segment_kernel, points_inside_kernel, fp32_probe_kernel
 //   sensor.cuh     range-sensor ray casting
@@ -25,6 +26,7 @@
 #include "scene.cuh"
 #include "fwd_full.cuh"
 #include "fwd_broad.cuh"
+#include "fwd_baked.cuh"
 #include "bwd.cuh"
 #include "queries.cuh"
 
@@ -133,15 +135,38 @@ constexpr int64_t kTpMaxBalls = 65536;
 // more -> one thread per ball; dense scenes (>= 2,048 segments) at least 2 lanes (the refresh scan
 // is split over them); per-environment scenes -> lane-split, 4 lanes, scenes read in place.
 constexpr int kLegacyPlanBits = 4 | 8;
+bool use_baked(const doper_rollout_desc* d);
 
 // the lane = step kernel needs the scene in shared memory; larger scenes go to the lane-split kernel,
 // which reads them in place
 bool scene_fits_smem(const doper_rollout_desc* d) { return (size_t)scene_layout(1, d->S).S_pad * 20 <= 200 * 1024; }
 
 bool use_cull(const doper_rollout_desc* d) {
+    if (use_baked(d)) return false;
     if ((d->flags & (1 << 15)) || (d->flags & 1)) return false;
     if (d->flags & (1 << 16)) return true;
     return d->lanes_per_ball == 0 && !(d->flags & kLegacyPlanBits);
+}
+
+// Baked broad phase (static per-cell lists, fwd_baked.cuh): shared scenes under the default plan.  Not with the
+// exact index log (bit 17: the cell lists are hit lists), a forced exact sweep (bit 0), pinned lane counts /
+// legacy kernels, or flags bit 20 (which keeps the per-ball candidate-list kernels).
+bool use_baked(const doper_rollout_desc* d) {
+    return !d->per_env && d->lanes_per_ball == 0 && !(d->flags & (1 | kLegacyPlanBits | (1 << 15) | (1 << 16) | (1 << 17) | (1 << 18) | (1 << 20)));
+}
+
+// lanes (= speculated time steps) per ball of the baked kernel: small batches need them to fill the SMs
+int baked_lanes(const doper_rollout_desc* d) {
+    if (d->B <= 1024) return 16;
+    if (d->B <= 4096) return 8;
+    if (d->B <= 16384) return 4;
+    if (d->B <= 49152) return 2;
+    return 1;
+}
+
+bool baked_staged(const doper_rollout_desc* d) {
+    const int S_pad = scene_layout(1, d->S).S_pad;
+    return (size_t)S_pad * 20 + bake_bytes(S_pad) + 64 <= 96 * 1024;
 }
 
 bool use_tpc(const doper_rollout_desc* d) {
@@ -164,16 +189,16 @@ int cull_lanes(const doper_rollout_desc* d) {
 }
 
 bool plan_reg8(const doper_rollout_desc* d) {
-    return d->lanes_per_ball == 0 && !d->per_env && !(d->flags & 4) && scene_layout(1, d->S).S_pad <= 256 &&
+    return !use_baked(d) && d->lanes_per_ball == 0 && !d->per_env && !(d->flags & 4) && scene_layout(1, d->S).S_pad <= 256 &&
            d->B >= 1536 && d->B <= 6144 && !use_cull(d);
 }
 
 bool use_tp(const doper_rollout_desc* d) {
-    return d->lanes_per_ball == 0 && !(d->flags & 8) && d->B <= kTpMaxBalls && !plan_reg8(d) && !use_cull(d);
+    return !use_baked(d) && d->lanes_per_ball == 0 && !(d->flags & 8) && d->B <= kTpMaxBalls && !plan_reg8(d) && !use_cull(d);
 }
 
 // lane = time step kernels write [B][n_steps] so that a group's stores are contiguous
-bool log_ball_major(const doper_rollout_desc* d) { return use_tp(d) || use_tpc(d); }
+bool log_ball_major(const doper_rollout_desc* d) { return use_tp(d) || use_tpc(d) || (use_baked(d) && baked_lanes(d) > 1); }
 
 int tp_warps_per_block(const doper_rollout_desc* d) {
     if (d->per_env) return 4;
@@ -303,6 +328,23 @@ int launch_fwd_tpc(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
 }
 
 template <int G>
+int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
+    constexpr int THREADS = G >= 8 ? 64 : 128;
+    const int S_pad = scene_layout(1, p.S).S_pad;
+    const size_t smem = staged ? (size_t)S_pad * 20 + (bake_bytes(S_pad) - sizeof(BakeHeader)) + 16 : 0;
+    const int bpb = THREADS / G;
+    const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
+    auto go = [&](auto kernel) {
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return (int)DOPER_ERR_SMEM_LIMIT;
+        kernel<<<grid, THREADS, smem, st>>>(p);
+        return launch_status();
+    };
+    return staged ? go(rollout_fwd_baked_kernel<G, true, THREADS>) : go(rollout_fwd_baked_kernel<G, false, THREADS>);
+}
+
+template <int G>
 int launch_closest(cudaStream_t st, int64_t N, int S, const float* pts, const float* segs, const void* ws,
                    int32_t* idx, float* dist, float* seg_out, size_t smem) {
     if (smem > 48 * 1024 &&
@@ -363,12 +405,16 @@ size_t doper_scene_workspace_bytes(int64_t n_scenes, int32_t S) {
 }
 
 int doper_scene_prepare(doper_stream_t stream, int64_t n_scenes, int32_t S, const float* segments,
-                        void* scene_ws) {
+                        float max_radius, void* scene_ws) {
     if (n_scenes <= 0 || S <= 0 || n_scenes > 0x7fffffff) return DOPER_ERR_BAD_SHAPE;
     if (!segments || !scene_ws) return DOPER_ERR_NULL_PTR;
     if (!aligned(segments, 16) || !aligned(scene_ws, 256)) return DOPER_ERR_MISALIGNED;
     scene_prepare_kernel<<<(unsigned)n_scenes, 128, 0, (cudaStream_t)stream>>>(
         n_scenes, S, reinterpret_cast<const float4*>(segments), reinterpret_cast<unsigned char*>(scene_ws));
+    if (launch_status() != DOPER_OK) return DOPER_ERR_LAUNCH;
+    if (n_scenes == 1)  // shared scene: bake the per-cell candidate lists (max_radius <= 0 or NaN: marked absent)
+        scene_bake_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(S, max_radius > 0.0f ? max_radius : 0.0f,
+                                                               reinterpret_cast<unsigned char*>(scene_ws));
     return launch_status();
 }
 
@@ -464,6 +510,13 @@ int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
 const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward) {
     if (validate_desc(d) != DOPER_OK) return "invalid";
     if (backward) return (d->flags & 2) ? "rollout_bwd_kernel" : "rollout_bwd_jacobian_kernel+rollout_bwd_fold_kernel";
+    if (use_baked(d)) {
+        static const char* const baked[] = {"rollout_fwd_baked_kernel<1>", "rollout_fwd_baked_kernel<2>", "rollout_fwd_baked_kernel<4>",
+                                            "rollout_fwd_baked_kernel<8>", "rollout_fwd_baked_kernel<16>"};
+        int lg = 0;
+        while ((1 << lg) < baked_lanes(d)) ++lg;
+        return baked[lg];
+    }
     const int G = auto_lanes(d);
     static const char* const tpc[] = {"rollout_fwd_tpc_kernel<2>", "rollout_fwd_tpc_kernel<4>", "rollout_fwd_tpc_kernel<8>",
                                       "rollout_fwd_tpc_kernel<16>", "rollout_fwd_tpc_kernel<32>"};
@@ -501,7 +554,7 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     const int tp_wpb = tp_warps_per_block(d);
     const size_t smem = tp ? (size_t)(d->per_env ? tp_wpb : 1) * scene_layout(1, d->S).S_pad * 20 + 16
                            : fwd_smem_bytes(d, G);
-    const bool unstaged_ok = use_cull(d) && !use_tpc(d);  // the lane-split broad-phase kernel can read the scene in place
+    const bool unstaged_ok = (use_cull(d) && !use_tpc(d)) || use_baked(d);  // these kernels can read the scene in place
     if ((int)smem > max_optin_smem() && !unstaged_ok) return DOPER_ERR_SMEM_LIMIT;
     const int K = resolve_K(d);
     FwdParams p;
@@ -528,6 +581,15 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         p.sink.count = reinterpret_cast<int*>(base);
         p.sink.cap = (int)w.cap;
         if (cudaMemsetAsync(base, 0, 256, st) != cudaSuccess) return DOPER_ERR_LAUNCH;  // record counter
+    }
+    if (use_baked(d)) {
+        switch (baked_lanes(d)) {
+            case 1: return launch_fwd_baked<1>(st, p, baked_staged(d));
+            case 2: return launch_fwd_baked<2>(st, p, baked_staged(d));
+            case 4: return launch_fwd_baked<4>(st, p, baked_staged(d));
+            case 8: return launch_fwd_baked<8>(st, p, baked_staged(d));
+            default: return launch_fwd_baked<16>(st, p, baked_staged(d));
+        }
     }
     if (tp) {
         if (smem > 48 * 1024 &&
@@ -692,7 +754,7 @@ int doper_peer_close(void* buffer) { return cudaIpcCloseMemHandle(buffer) == cud
 int doper_peer_free(void* buffer) { return cudaFree(buffer) == cudaSuccess ? DOPER_OK : DOPER_ERR_LAUNCH; }
 
 int doper_allreduce_oneshot(doper_stream_t stream, int32_t rank, int32_t world, void* const* buffers, int32_t n,
-                            const float* in, float* out, int32_t* status) {
+                            const float* in, float* out, int32_t* status, double timeout_seconds) {
     if (world < 1 || world > kPeerMaxRanks || rank < 0 || rank >= world || n <= 0) return DOPER_ERR_BAD_SHAPE;
     if (!buffers || !in || !out) return DOPER_ERR_NULL_PTR;
     PeerPtrs P;
@@ -700,7 +762,10 @@ int doper_allreduce_oneshot(doper_stream_t stream, int32_t rank, int32_t world, 
     for (int r = 0; r < world; ++r)
         if (!P.base[r]) return DOPER_ERR_NULL_PTR;
     const int blocks = (int)((peer_n4(n) + kPeerThreads - 1) / kPeerThreads);
-    allreduce_oneshot_kernel<<<blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(P, rank, world, n, in, out, status);
+    // SM clocks: ~2 GHz; <= 0 selects the default of one minute
+    const double secs = timeout_seconds > 0.0 ? (timeout_seconds < 3600.0 ? timeout_seconds : 3600.0) : 60.0;
+    allreduce_oneshot_kernel<<<blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(P, rank, world, n, in, out, status,
+                                                                               (long long)(secs * 2.0e9));
     return launch_status();
 }
 

@@ -17,7 +17,17 @@
 // by step parity, which makes a trailing barrier unnecessary: a rank can be at most one step ahead of
 // the slowest one (it needs everybody's words of step s+1 before it can start step s+2, and a peer
 // sends those only after its own step s has finished reading).  A peer that never arrives makes the
-// kernel give up after about two seconds and raise the status word instead of hanging the GPU.
+// kernel give up after `timeout_cycles` SM clocks (default ~60 s), raise the status word and fill its part
+// of `out` with NaN (a visible failure: the caller must not step the optimiser on a partial sum) instead of
+// hanging the GPU.
+//
+// MEMORY-MODEL ASSUMPTION (not guaranteed by the PTX memory model; holds on the NVLink 5 / NVSwitch
+// systems this was measured on, and is what the 2-rank self-check of bench.py --gpus N verifies against
+// NCCL on every run): a 16-byte st.volatile.global.v4 to peer memory becomes visible to the peer's
+// ld.volatile.global.v4 in units of at least 8 aligned bytes, i.e. a {value, seq} half is never torn.  The
+// PTX model only guarantees single-copy atomicity per 32-bit element of a vector access; hardware splits
+// vector stores at 8- / 16-byte granularity at most.  A platform that tears a half would show up as a
+// wrong sum with matching sequence numbers; the fallback there is the NCCL transport (`--nccl`).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -53,7 +63,7 @@ __device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
 __global__ void __launch_bounds__(kPeerThreads) allreduce_oneshot_kernel(PeerPtrs P, int rank, int world, int n,
                                                                         const float* __restrict__ in,
                                                                         float* __restrict__ out,
-                                                                        int* __restrict__ status) {
+                                                                        int* __restrict__ status, long long timeout_cycles) {
     uint32_t* hdr = reinterpret_cast<uint32_t*>(P.base[rank]);
     const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(hdr) + 1u;  // bumped only after every block has read it
     const size_t n4 = peer_n4(n);
@@ -92,7 +102,7 @@ __global__ void __launch_bounds__(kPeerThreads) allreduce_oneshot_kernel(PeerPtr
             for (int r = 0; r < kPeerMaxRanks; ++r)
                 if (((pending >> r) & 1u) && a[r].y == seq && a[r].w == seq && b[r].y == seq && b[r].w == seq)
                     pending &= ~(1u << r);
-            if (pending && clock64() - t0 > 4000000000ll) { failed = true; break; }  // ~2 s: a peer never arrived
+            if (pending && clock64() - t0 > timeout_cycles) { failed = true; break; }  // a peer never arrived
         }
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -101,11 +111,9 @@ __global__ void __launch_bounds__(kPeerThreads) allreduce_oneshot_kernel(PeerPtr
                 acc[0] += __uint_as_float(a[r].x); acc[1] += __uint_as_float(a[r].z);
                 acc[2] += __uint_as_float(b[r].x); acc[3] += __uint_as_float(b[r].z);
             }
-        if (!failed) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (4 * g + k < (size_t)n) out[4 * g + k] = acc[k];
-        }
+        for (int k = 0; k < 4; ++k)
+            if (4 * g + k < (size_t)n) out[4 * g + k] = failed ? __int_as_float(0x7fc00000) : acc[k];
     }
     if (failed && status) *status = 1;
     // the last block to get here publishes the new sequence number (even after a failure: the ranks stay in step)

@@ -18,9 +18,38 @@ struct SceneHeader {  // 16 B per scene
 };
 
 struct SceneLayout {
-    size_t hdr_off, q_off, rl_off, s1_off, grid_off, total;  // grid_off = 0: no grid (per-environment scenes)
+    size_t hdr_off, q_off, rl_off, s1_off, grid_off, bake_off, total;  // grid_off / bake_off = 0: none (per-environment scenes)
+    int bake_cap;  // item capacity of the baked cell lists
     int S_pad;
 };
+
+// ------------------------------------------------------------------------------------------
+// baked broad phase: static per-cell candidate lists of a shared scene
+// ------------------------------------------------------------------------------------------
+// A uniform grid over the scene's bounding box (+ margin); cell k holds the hit list (sweep.cuh, "hit
+// lists") of the disc that circumscribes it: every segment that a ball of radius <= r_max can touch from
+// ANY point of the cell.  A rollout then never scans the scene: the list of the cell a point falls in is
+// valid for that point by the same proof as a per-ball list built around the cell centre with
+// rho = half diagonal / 0.98, and an empty cell proves "no collision" with no arithmetic at all.  Built
+// once per (scene, r_max) by scene_bake_kernel; read by rollout_fwd_baked_kernel.
+constexpr int kBakeMaxCells = 4096;
+constexpr int kBakeItemsPerSeg = 32;
+
+struct BakeHeader {  // 64 B
+    float x0, y0, h, inv_h;   // cell (ix, iy) = [x0 + ix h, x0 + (ix + 1) h) x ...
+    int nx, ny, n_items, enabled;
+    float r_max;   // lists are valid for ball radii <= r_max
+    float M;       // bound on |coordinate| of the scene and of every point inside the grid (+ rho)
+    float far2;    // cull_far2(r_max, M): estimates^2 above it prove "no collision"
+    float rho;     // radius of the disc a cell list was built for
+    float fnx, fny;  // (float)nx, (float)ny
+    int pad[2];
+};
+
+__host__ __device__ inline size_t bake_bytes(int S_pad) {
+    size_t b = sizeof(BakeHeader) + (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t) + (size_t)kBakeItemsPerSeg * S_pad * sizeof(unsigned short);
+    return (b + 15) / 16 * 16;
+}
 
 __host__ __device__ inline SceneLayout scene_layout(int64_t n_scenes, int S) {
     SceneLayout L;
@@ -38,6 +67,13 @@ __host__ __device__ inline SceneLayout scene_layout(int64_t n_scenes, int S) {
     if (n_scenes == 1) {  // [GridHeader | cell_start (kGridMaxCells + 1) | items (4 S_pad)]
         L.grid_off = L.total;
         L.total += sizeof(GridHeader) + (size_t)(kGridMaxCells + 1) * sizeof(int) + (size_t)4 * L.S_pad * sizeof(int);
+        L.total = (L.total + 255) / 256 * 256;
+    }
+    L.bake_off = 0; L.bake_cap = 0;
+    if (n_scenes == 1) {  // [BakeHeader 64 B | cell_start u32 (kBakeMaxCells + 16) | items u16 (bake_cap)]
+        L.bake_off = L.total;
+        L.bake_cap = kBakeItemsPerSeg * L.S_pad;
+        L.total += bake_bytes(L.S_pad);
         L.total = (L.total + 255) / 256 * 256;
     }
     return L;
@@ -184,6 +220,148 @@ __global__ void __launch_bounds__(128) scene_prepare_kernel(int64_t n_scenes, in
             __syncthreads();
         }
     }
+}
+
+// One block.  Segment-driven: each segment visits the cells whose centre can be within `reach` of it
+// (its bounding box grown by reach, plus one cell of slack) and applies the list test of sweep.cuh
+// (estimate at the cell centre <= reach, on squares with upward slack); counting sort into CSR; the items
+// of a cell are then sorted ascending so that the layout is deterministic.  If the lists overflow the
+// item capacity the cell size grows by 1.5x and the pass repeats (a single cell always fits).
+__global__ void __launch_bounds__(256) scene_bake_kernel(int S, float r_max, unsigned char* __restrict__ ws) {
+    const SceneLayout L = scene_layout(1, S);
+    const SceneHeader sh = *reinterpret_cast<const SceneHeader*>(ws + L.hdr_off);
+    const float4* q = reinterpret_cast<const float4*>(ws + L.q_off);
+    const float* rl = reinterpret_cast<const float*>(ws + L.rl_off);
+    const float2* e1 = reinterpret_cast<const float2*>(ws + L.s1_off);
+    BakeHeader* bh = reinterpret_cast<BakeHeader*>(ws + L.bake_off);
+    uint32_t* cell_start = reinterpret_cast<uint32_t*>(ws + L.bake_off + sizeof(BakeHeader));
+    unsigned short* items = reinterpret_cast<unsigned short*>(cell_start + (kBakeMaxCells + 16));
+    __shared__ float s_red[4][256];
+    __shared__ int s_cnt[kBakeMaxCells];
+    __shared__ int s_tot;
+    __shared__ BakeHeader s_b;
+    const int tid = threadIdx.x;
+    float lox = 3.0e38f, loy = 3.0e38f, hix = -3.0e38f, hiy = -3.0e38f;
+    for (int i = tid; i < S; i += blockDim.x) {
+        const float4 a = q[i];
+        const float2 b = e1[i];
+        lox = fminf(lox, fminf(a.x, b.x)); hix = fmaxf(hix, fmaxf(a.x, b.x));
+        loy = fminf(loy, fminf(a.y, b.y)); hiy = fmaxf(hiy, fmaxf(a.y, b.y));
+    }
+    s_red[0][tid] = lox; s_red[1][tid] = loy; s_red[2][tid] = -hix; s_red[3][tid] = -hiy;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < (int)blockDim.x; ++i)
+            for (int k = 0; k < 4; ++k) s_red[k][0] = fminf(s_red[k][0], s_red[k][i]);
+        BakeHeader b;
+        b.enabled = 0; b.nx = b.ny = 1; b.n_items = 0; b.r_max = r_max; b.x0 = b.y0 = 0.f; b.h = b.inv_h = 1.f;
+        b.M = sh.scale; b.far2 = 0.f; b.rho = 0.f; b.fnx = b.fny = 1.f; b.pad[0] = b.pad[1] = 0;
+        const float W = -s_red[2][0] - s_red[0][0], H = -s_red[3][0] - s_red[1][0];
+        const bool ok = !sh.weird && r_max > 0.0f && r_max <= 1.0e15f && W >= 0.0f && H >= 0.0f && W <= 1.0e15f && H <= 1.0e15f &&
+                        S <= 65535;
+        if (ok) {
+            b.enabled = 1;
+            // first guess: kBakeMaxCells square cells over the box + margins, never finer than 2^-10 of the
+            // coordinate scale (the cell lookup's rounding must stay far inside the 2 % slack of rho)
+            const float Wm = W + 2.0f * r_max, Hm = H + 2.0f * r_max;
+            b.h = fmaxf(sqrtf((Wm * Hm) / (float)kBakeMaxCells) * 1.05f, fmaxf(sh.scale, r_max) * 0.0009765625f);
+            b.x0 = s_red[0][0]; b.y0 = s_red[1][0];  // box corner; the margin is applied per attempt (depends on h)
+        }
+        s_b = b;
+        s_red[0][1] = W; s_red[1][1] = H;
+    }
+    __syncthreads();
+    if (!s_b.enabled) {
+        if (tid == 0) *bh = s_b;
+        return;
+    }
+    const float bx0 = s_b.x0, by0 = s_b.y0, W = s_red[0][1], H = s_red[1][1];
+    for (int attempt = 0; attempt < 64; ++attempt) {
+        __syncthreads();
+        if (tid == 0) {
+            BakeHeader b = s_b;
+            if (attempt > 0) b.h *= 1.5f;
+            // grid rectangle = box grown by mg = r_max + h on every side: a point outside the rectangle is
+            // further than r_max + h - (rounding) from every segment
+            const float mg = r_max + b.h;
+            b.nx = (int)fminf(ceilf((W + 2.0f * mg) / b.h) + 1.0f, 1.0e6f);
+            b.ny = (int)fminf(ceilf((H + 2.0f * mg) / b.h) + 1.0f, 1.0e6f);
+            while ((long long)b.nx * b.ny > kBakeMaxCells) {
+                b.h *= 1.25f;
+                const float mg2 = r_max + b.h;
+                b.nx = (int)fminf(ceilf((W + 2.0f * mg2) / b.h) + 1.0f, 1.0e6f);
+                b.ny = (int)fminf(ceilf((H + 2.0f * mg2) / b.h) + 1.0f, 1.0e6f);
+            }
+            const float mgf = r_max + b.h;
+            b.x0 = bx0 - mgf; b.y0 = by0 - mgf;
+            b.inv_h = 1.0f / b.h;
+            b.fnx = (float)b.nx; b.fny = (float)b.ny;
+            b.rho = (b.h * 0.70710678f) * (1.0f / kCullRhoCheck) * 1.0001f;  // half diagonal / 0.98, rounded up
+            const float ext = fmaxf(fmaxf(fabsf(b.x0), fabsf(b.x0 + b.h * b.fnx)), fmaxf(fabsf(b.y0), fabsf(b.y0 + b.h * b.fny)));
+            b.M = fmaxf(sh.scale, ext + b.rho) * 1.0001f;
+            b.far2 = cull_far2(r_max, b.M);
+            s_b = b;
+            s_tot = 0;
+        }
+        __syncthreads();
+        const BakeHeader b = s_b;
+        const int ncell = b.nx * b.ny;
+        for (int i = tid; i < ncell; i += blockDim.x) s_cnt[i] = 0;
+        __syncthreads();
+        const float reach = __fmaf_rn(kCullSafePerM, b.M, b.rho + r_max) * kCullUp;  // list_reach(), hit list
+        const float T = (reach * reach) * kCullUp;
+        const float R = reach * 1.01f + b.h;  // a cell centre within reach (+ 49 u M) of the segment lies in its box grown by R
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int i = tid; i < S; i += blockDim.x) {
+                const float4 a = q[i];
+                const float r1 = rl[i];
+                const float2 e = e1[i];
+                const int ax = max(0, (int)floorf((fminf(a.x, e.x) - R - b.x0) * b.inv_h) - 1);
+                const int cx1 = min(b.nx - 1, (int)floorf((fmaxf(a.x, e.x) + R - b.x0) * b.inv_h) + 1);
+                const int ay = max(0, (int)floorf((fminf(a.y, e.y) - R - b.y0) * b.inv_h) - 1);
+                const int cy1 = min(b.ny - 1, (int)floorf((fmaxf(a.y, e.y) + R - b.y0) * b.inv_h) + 1);
+                for (int cy = ay; cy <= cy1; ++cy)
+                    for (int cx = ax; cx <= cx1; ++cx) {
+                        const float ccx = __fmaf_rn((float)cx + 0.5f, b.h, b.x0), ccy = __fmaf_rn((float)cy + 0.5f, b.h, b.y0);
+                        if (!(approx_d2(ccx, ccy, a, r1) <= T)) continue;
+                        const int cell = cy * b.nx + cx;
+                        if (pass == 0) {
+                            atomicAdd(&s_cnt[cell], 1);
+                        } else {
+                            const int pos = atomicAdd(&s_cnt[cell], 1);  // cursor (re-initialised to the cell's start)
+                            items[pos] = (unsigned short)i;
+                        }
+                    }
+            }
+            __syncthreads();
+            if (pass == 0) {
+                if (tid == 0) {
+                    int acc = 0;
+                    for (int c = 0; c < ncell; ++c) { const int n = s_cnt[c]; s_cnt[c] = acc; cell_start[c] = (uint32_t)acc; acc += n; }
+                    for (int c = ncell; c < kBakeMaxCells + 16; ++c) cell_start[c] = (uint32_t)acc;
+                    s_tot = acc;
+                }
+                __syncthreads();
+                if (s_tot > L.bake_cap) break;  // too many items for this cell size: coarser grid
+            }
+        }
+        __syncthreads();
+        if (s_tot <= L.bake_cap) {
+            // deterministic layout: ascending segment index inside every cell
+            for (int c = tid; c < ncell; c += blockDim.x) {
+                const int k0 = (int)cell_start[c], k1 = (int)cell_start[c + 1];
+                for (int k = k0 + 1; k < k1; ++k) {
+                    const unsigned short v = items[k];
+                    int m = k - 1;
+                    while (m >= k0 && items[m] > v) { items[m + 1] = items[m]; --m; }
+                    items[m + 1] = v;
+                }
+            }
+            if (tid == 0) { BakeHeader out = s_b; out.n_items = s_tot; *bh = out; }
+            return;
+        }
+    }
+    if (tid == 0) { BakeHeader out = s_b; out.enabled = 0; *bh = out; }  // unreachable in practice
 }
 
 // ------------------------------------------------------------------------------------------

@@ -80,6 +80,8 @@ class PolicyGradReducer:
         self.buf[o] = float(local_loss) if not isinstance(local_loss, torch.Tensor) else local_loss.to(self.buf.device)
         if self.peer is not None:
             self.peer.all_reduce(self.buf, out=self.buf)
+            if not torch.cuda.is_current_stream_capturing():
+                self.peer.check()  # eager call: one 4-byte read; captured calls are checked by the graph's runner
         elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
         o = 0
@@ -104,13 +106,14 @@ class PeerAllReducer:
     group (used once, to exchange the handles).
     """
 
-    def __init__(self, numel: int, device: torch.device):
+    def __init__(self, numel: int, device: torch.device, timeout_seconds: float = 60.0):
         import ctypes
 
         from ._abi import check, lib
         self._lib, self._check, self._ct = lib, check, ctypes
         self.n = int(numel)
         self.device = device
+        self.timeout_seconds = float(timeout_seconds)  # a peer that never arrives: give up, flag, NaN (see check())
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         if self.world > 16:
             raise ValueError("PeerAllReducer: at most 16 ranks")
@@ -163,8 +166,19 @@ class PeerAllReducer:
             raise ValueError("PeerAllReducer.all_reduce: bad out tensor")
         self._check(self._lib.doper_allreduce_oneshot(torch.cuda.current_stream().cuda_stream, self.rank, self.world,
                                                       self._ptrs, self.n, x.data_ptr(), out.data_ptr(),
-                                                      self.status.data_ptr()), "doper_allreduce_oneshot")
+                                                      self.status.data_ptr(), self.timeout_seconds),
+                    "doper_allreduce_oneshot")
         return out
+
+    def check(self) -> None:
+        """Host synchronisation point: raises if any call since the last check timed out waiting for a
+        peer (that call's result is NaN on this rank while the peers may hold a full sum: the ranks'
+        parameters have diverged and must be re-broadcast before training continues)."""
+        if int(self.status.item()) != 0:
+            self.status.zero_()
+            raise RuntimeError("PeerAllReducer: a peer did not arrive within "
+                               f"{self.timeout_seconds:g} s; this rank's result was NaN-filled. Re-synchronise "
+                               "the parameters (broadcast from rank 0) before the next optimiser step.")
 
     def close(self, barrier: bool = True) -> None:
         torch.cuda.synchronize(self.device)

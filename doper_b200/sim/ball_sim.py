@@ -40,7 +40,8 @@ class RolloutOptions:
     def __init__(self, ckpt_every: int = 0, lanes_per_ball: int = 0, force_exact_sweep: bool = False,
                  sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True,
                  broad_phase: bool = None, exact_index_log: bool = False,
-                 broad_phase_time_parallel: bool = False, hit_records: bool = True, hit_capacity: int = 0):
+                 broad_phase_time_parallel: bool = False, hit_records: bool = True, hit_capacity: int = 0,
+                 baked_broad_phase: bool = True):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
@@ -58,11 +59,14 @@ class RolloutOptions:
         # records the workspace can hold (0 = library default); collisions beyond it are replayed as well
         self.hit_records = bool(hit_records)
         self.hit_capacity = int(hit_capacity)
+        # shared scenes: the static per-cell candidate lists baked into the prepared scene (default plan);
+        # False keeps the kernels with per-ball candidate lists
+        self.baked_broad_phase = bool(baked_broad_phase)
 
     def key(self) -> tuple:
         return (self.ckpt_every, self.lanes_per_ball, self.force_exact_sweep, self.sequential_backward, self.smem_forward,
                 self.time_parallel, self.broad_phase, self.exact_index_log, self.broad_phase_time_parallel,
-                self.hit_records, self.hit_capacity)
+                self.hit_records, self.hit_capacity, self.baked_broad_phase)
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -105,7 +109,7 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
                ((1 << 16) if opts.broad_phase else 0) | ((1 << 15) if opts.broad_phase is False else 0) |
                ((1 << 17) if opts.exact_index_log else 0) |
                ((1 << 18) if opts.broad_phase_time_parallel else 0) |
-               (0 if opts.hit_records else (1 << 19)))
+               (0 if opts.hit_records else (1 << 19)) | (0 if opts.baked_broad_phase else (1 << 20)))
     d.hit_capacity = opts.hit_capacity
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
@@ -122,6 +126,10 @@ class _Buffers:
     """Per-(device, shape) reusable device buffers: backward workspace, scratch, packed outputs."""
 
     _cache: Dict[tuple, "_Buffers"] = {}
+    # buffers handed out while a CUDA graph was being captured: the graph bakes their addresses in, so the
+    # capturing code (BallAttractorTrainer.graphed_iteration) takes strong references from this log; evicting
+    # the cache entry then cannot free memory a live graph still writes
+    _capture_log: list = []
 
     def __init__(self, device, desc: RolloutDesc):
         B = desc.B
@@ -143,6 +151,8 @@ class _Buffers:
                 cls._cache.clear()
             b = cls(device, desc)
             cls._cache[key] = b
+        if torch.cuda.is_current_stream_capturing():
+            cls._capture_log.append(b)
         return b
 
 
@@ -188,7 +198,7 @@ def run_sim(sim_time, n_steps, scene, coordinate_init, velocity_init, attractor,
                     else coordinate_init.shape) == 1
     B = _batch_of(coordinate_init)
     desc = _make_desc(B, scene, sim_time, n_steps, attractor, constants, opts)
-    _, sws = scene.prepared(device)
+    _, sws = scene.prepared(device, float(desc.consts[0]))
     x0, v0, host = _stage_inputs(coordinate_init, velocity_init, device, None)
     n = desc.n_steps
     out = torch.empty((2, B, 2), dtype=torch.float32, device=device)
@@ -210,7 +220,7 @@ def _value_and_grad_raw(sim_time, n_steps, scene, coordinate_init, velocity_init
     scene = _as_scene(scene)
     B = _batch_of(coordinate_init)
     desc = _make_desc(B, scene, sim_time, n_steps, attractor, constants, opts)
-    _, sws = scene.prepared(device)
+    _, sws = scene.prepared(device, float(desc.consts[0]))
     bufs = _Buffers.get(device, desc)
     x0, v0, host = _stage_inputs(coordinate_init, velocity_init, device, bufs)
     o = bufs.out
@@ -263,7 +273,7 @@ class _HostPlan:
     def __init__(self, device, scene, B, sim_time, n_steps, attractor, constants, target, opts):
         self.B = B
         self.desc = _make_desc(B, scene, sim_time, n_steps, attractor, constants, opts)
-        _, sws = scene.prepared(device)
+        _, sws = scene.prepared(device, float(self.desc.consts[0]))
         self.scene = scene  # keeps the prepared workspace alive
         self.bufs = _Buffers.get(device, self.desc)
         self.tgt = _target2(target)
@@ -376,7 +386,7 @@ class _RolloutFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x0, v0, scene, desc):
         device = x0.device
-        _, sws = scene.prepared(device)
+        _, sws = scene.prepared(device, float(desc.consts[0]))
         x0c = as_f32_device(x0, device).reshape(-1, 2)
         v0c = as_f32_device(v0, device).reshape(-1, 2)
         B = desc.B
@@ -390,7 +400,7 @@ class _RolloutFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_xT, g_vT):
         desc, device = ctx.desc, ctx.ws.device
-        _, sws = ctx.scene.prepared(device)
+        _, sws = ctx.scene.prepared(device, float(desc.consts[0]))
         B = desc.B
         gx = torch.zeros((B, 2), dtype=torch.float32, device=device) if g_xT is None else \
             g_xT.to(torch.float32).contiguous()
@@ -426,7 +436,7 @@ def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, at
     scene = _as_scene(scene)
     B = _batch_of(coordinate_init)
     desc = _make_desc(B, scene, sim_time, n_steps, attractor, constants, opts)
-    _, sws = scene.prepared(device)
+    _, sws = scene.prepared(device, float(desc.consts[0]))
     x0 = as_f32_device(coordinate_init, device).reshape(-1, 2)
     v0 = as_f32_device(velocity_init, device).reshape(-1, 2)
     n = desc.n_steps

@@ -68,23 +68,32 @@ class JaxScene:
     def n_scenes(self) -> int:
         return int(self.segments.shape[0]) if self.per_env else 1
 
-    def prepared(self, device: torch.device = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(raw segments f32 on device ``[..., S, 4]``, prepared workspace bytes)."""
+    def prepared(self, device: torch.device = None, radius: float = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(raw segments f32 on device ``[..., S, 4]``, prepared workspace bytes).
+
+        ``radius``: the ball radius of the rollout that is about to use the workspace.  A shared scene carries
+        baked per-cell candidate lists valid for radii up to the one it was prepared with
+        (``doper_scene_prepare(max_radius)``); asking for a larger one re-bakes in place, stream-ordered."""
         device = device or require_cuda()
         key = (device.type, device.index)
         hit = self._dev.get(key)
-        if hit is not None:
-            return hit
-        raw = as_f32_device(self.segments, device)
-        if raw.shape[-2:] != (2, 2) or raw.dim() not in (3, 4):
-            raise ValueError(f"segments must be [S,2,2] or [E,S,2,2], got {tuple(raw.shape)}")
-        S = int(raw.shape[-3])
-        n = int(raw.shape[0]) if raw.dim() == 4 else 1
-        raw = raw.reshape(*raw.shape[:-2], 4).contiguous()
-        nbytes = lib.doper_scene_workspace_bytes(n, S)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        check(lib.doper_scene_prepare(stream_ptr(), n, S, ptr(raw), ptr(ws)), "doper_scene_prepare")
-        self._dev[key] = (raw, ws)
+        if hit is not None and (radius is None or self.per_env or (hit[2] is not None and radius <= hit[2])):
+            return hit[0], hit[1]
+        if hit is None:
+            raw = as_f32_device(self.segments, device)
+            if raw.shape[-2:] != (2, 2) or raw.dim() not in (3, 4):
+                raise ValueError(f"segments must be [S,2,2] or [E,S,2,2], got {tuple(raw.shape)}")
+            raw = raw.reshape(*raw.shape[:-2], 4).contiguous()
+            S = int(raw.shape[-2])
+            n = int(raw.shape[0]) if raw.dim() == 3 else 1
+            ws = torch.empty(lib.doper_scene_workspace_bytes(n, S), dtype=torch.uint8, device=device)
+        else:
+            raw, ws = hit[0], hit[1]
+            S = int(raw.shape[-2])
+            n = int(raw.shape[0]) if raw.dim() == 3 else 1
+        r = float(radius) if radius is not None else 0.0
+        check(lib.doper_scene_prepare(stream_ptr(), n, S, ptr(raw), r, ptr(ws)), "doper_scene_prepare")
+        self._dev[key] = (raw, ws, (r if r > 0.0 else None))
         return raw, ws
 
 

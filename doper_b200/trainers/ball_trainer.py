@@ -146,7 +146,11 @@ class BallAttractorTrainer:
         # warm-up on a side stream (allocates the cached rollout buffers, lazily-initialised optimiser
         # state, cuBLAS workspaces) — the parameter updates of these iterations are rolled back
         saved = [p.detach().clone() for p in self.controller.parameters()]
-        saved_opt = None
+        # optimiser state that already exists (a trainer that was trained eagerly first) survives the capture
+        saved_opt = {id(t): t.detach().clone() for st in self.optimizer.state.values() for t in st.values()
+                     if isinstance(t, torch.Tensor)}
+        from ..sim.ball_sim import _Buffers
+        log_start = len(_Buffers._capture_log)
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self.optimizer.zero_grad(set_to_none=True)
@@ -160,18 +164,38 @@ class BallAttractorTrainer:
         with torch.no_grad():
             for p, q in zip(self.controller.parameters(), saved):
                 p.copy_(q)
+        # Adam's moments / step, in place (the graph holds pointers to these tensors): back to what they were
+        # before the warm-up, zero where the warm-up created them
+        with torch.no_grad():
+            for st in self.optimizer.state.values():
+                for k, v in st.items():
+                    if isinstance(v, torch.Tensor):
+                        if id(v) in saved_opt:
+                            v.copy_(saved_opt[id(v)])
+                        else:
+                            v.zero_()
         del saved_opt
-        # reset Adam's moments / step in place (the graph holds pointers to these tensors)
-        for st in self.optimizer.state.values():
-            for k, v in st.items():
-                if isinstance(v, torch.Tensor):
-                    v.zero_()
+        # the graph holds raw pointers into the cached rollout buffers: keep them (and the scene whose
+        # prepared workspace was captured) alive for as long as the runner lives, whatever the cache evicts
+        held = list(_Buffers._capture_log[log_start:])
+        del _Buffers._capture_log[log_start:]
+        scene_captured = scene_handler.jax_scene
+        peer = self._reducer.peer if self._reducer is not None else None
+        replays = [0]
 
         def run(coordinate_init, velocity_init):
+            if scene_handler.jax_scene is not scene_captured:
+                raise RuntimeError("graphed_iteration: the scene handler switched to another scene; the graph was "
+                                   "captured for one scene (capture one runner per SingleScene)")
             x_static.copy_(torch.as_tensor(coordinate_init, dtype=torch.float32, device=self.device))
             v_static.copy_(torch.as_tensor(velocity_init, dtype=torch.float32, device=self.device))
             graph.replay()
+            replays[0] += 1
+            if peer is not None and replays[0] % run.check_every == 0:
+                peer.check()  # a timed-out exchange left NaN gradients on this rank: stop before the ranks drift
             return loss_static
 
         run.graph = graph
+        run.buffers = held
+        run.check_every = 16
         return run

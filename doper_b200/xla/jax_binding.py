@@ -69,11 +69,11 @@ def _scratch_bytes(B, S, per_env, n_steps, ckpt_every):  # pragma: no cover
     return int(lib.doper_rollout_bwd_scratch_bytes(ctypes.byref(d)))
 
 
-def prepare_scene(segments):  # pragma: no cover
+def prepare_scene(segments, max_radius=0.0):  # pragma: no cover
     per_env = segments.ndim == 4
     n, S = (segments.shape[0], segments.shape[1]) if per_env else (1, segments.shape[0])
     nbytes = int(lib.doper_scene_workspace_bytes(n, S))
-    return jax.ffi.ffi_call("doper_scene_prepare_ffi", jax.ShapeDtypeStruct((nbytes,), jnp.uint8))(segments)
+    return jax.ffi.ffi_call("doper_scene_prepare_ffi", jax.ShapeDtypeStruct((nbytes,), jnp.uint8))(segments, max_radius=np.float32(max_radius))
 
 
 @partial(jax.custom_vjp, nondiff_argnums=(3, 4, 5, 6, 7, 8, 9))  # pragma: no cover

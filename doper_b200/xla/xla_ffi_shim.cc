@@ -10,7 +10,7 @@
 // binding; this shim adds no compute.
 //
 // Handlers (all launch on XLA's stream, allocate nothing, never synchronise):
-//   doper_scene_prepare_ffi   segments f32[n_scenes,S,2,2]            -> scene_ws u8[W]
+//   doper_scene_prepare_ffi   segments f32[n_scenes,S,2,2] (attr max_radius) -> scene_ws u8[W]
 //   doper_rollout_fwd_ffi     scene_ws, x0, v0 f32[B,2]               -> xT, vT f32[B,2], ws u8[R]
 //   doper_rollout_bwd_ffi     scene_ws, ws, xT_bar, vT_bar f32[B,2]   -> x0_bar, v0_bar f32[B,2], scratch u8[Q]
 //                             (ws is an immutable XLA input: everything the backward writes goes to its own
@@ -52,14 +52,14 @@ doper_rollout_desc MakeDesc(int64_t B, int32_t S, int32_t per_env, int32_t n_ste
 }
 
 ffi::Error ScenePrepareImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> segments,
-                            ffi::ResultBuffer<ffi::U8> scene_ws) {
+                            ffi::ResultBuffer<ffi::U8> scene_ws, float max_radius) {
     auto dims = segments.dimensions();  // [S,2,2] or [E,S,2,2]
     const bool per_env = dims.size() == 4;
     const int64_t n = per_env ? dims[0] : 1;
     const int32_t S = static_cast<int32_t>(per_env ? dims[1] : dims[0]);
     if (scene_ws->element_count() < doper_scene_workspace_bytes(n, S))
         return Status(DOPER_ERR_WORKSPACE, "doper_scene_prepare");
-    return Status(doper_scene_prepare(stream, n, S, segments.typed_data(), scene_ws->typed_data()),
+    return Status(doper_scene_prepare(stream, n, S, segments.typed_data(), max_radius, scene_ws->typed_data()),
                   "doper_scene_prepare");
 }
 
@@ -106,7 +106,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(doper_scene_prepare_ffi, ScenePrepareImpl,
                               ffi::Ffi::Bind()
                                   .Ctx<ffi::PlatformStream<cudaStream_t>>()
                                   .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::U8>>());
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Attr<float>("max_radius"));
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(doper_rollout_fwd_ffi, RolloutFwdImpl,
                               ffi::Ffi::Bind()

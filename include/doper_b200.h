@@ -90,12 +90,17 @@ const char* doper_error_string(int code);
 size_t doper_scene_workspace_bytes(int64_t n_scenes, int32_t S);
 
 /* Pre-digest raw segments into the kernels' staging layout: per segment (s0x,s0y,svx,svy) and
- * 1/|sv|^2, padded to a multiple of 32 with far-away sentinels, plus a per-scene header (max
- * |coordinate|, degenerate-segment flag).  Bit-identical to computing sv/L per pair as the
- * reference does (jax_geometry.py:132-133): both are ball-independent.  n_scenes = 1 for a
- * shared scene (reference semantics, ball_sim.py:332) or E for per-environment scenes. */
+ * 1/|sv|^2, padded to a multiple of 32 with far-away sentinels, the raw end points (read by the binary64
+ * backward), plus a per-scene header (max |coordinate|, degenerate-segment flag).  Bit-identical to
+ * computing sv/L per pair as the reference does (jax_geometry.py:132-133): both are ball-independent.
+ * n_scenes = 1 for a shared scene (reference semantics, ball_sim.py:332) or E for per-environment scenes.
+ * max_radius > 0 (shared scenes): also bake the broad phase — a uniform grid over the scene whose cells
+ * hold every segment a ball of radius <= max_radius can touch from anywhere in the cell — which the
+ * default forward kernel of shared scenes reads instead of scanning the scene.  A rollout whose radius
+ * exceeds max_radius (or max_radius <= 0) still returns the same results, through the reference
+ * arithmetic over every segment (slow): prepare the scene with the radius you roll out with. */
 int doper_scene_prepare(doper_stream_t stream, int64_t n_scenes, int32_t S, const float* segments,
-                        void* scene_ws);
+                        float max_radius, void* scene_ws);
 
 /* ---- geometry queries ----------------------------------------------------------------- */
 
@@ -158,6 +163,8 @@ typedef struct {
                                bit 15 / bit 16: forbid / force the broad-phase (candidate list)
                                       forward kernels; bit 18: with bit 16 and lanes_per_ball >= 2, the
                                       time-parallel (lane = step) variant instead of the lane-split one;
+                               bit 20: keep the per-ball candidate-list kernels for a shared scene
+                                      (default there: the baked per-cell lists of doper_scene_prepare);
                                bit 19: no collision records (the backward replays every collided
                                       step from its checkpoint: slower, same results);
                                bit 17: hit log holds the exact closest index at EVERY step (the
@@ -226,15 +233,20 @@ int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, con
  * ordinary device arrays of n floats (they may alias); `buffers` is a HOST array of `world` device
  * pointers indexed by rank (own buffer at [rank]).  One kernel: it pushes `in` into every peer with the
  * step number inside each 16-byte store and polls its own buffer for the peers' words (no fence, no
- * separate flag: one NVLink crossing).  A peer that never arrives makes the kernel give up after about
- * two seconds and set *status (device int, nullable) to 1 instead of spinning for ever. */
+ * separate flag: one NVLink crossing).  A peer that never arrives makes the kernel give up after
+ * timeout_seconds (<= 0: one minute), set *status (device int, nullable) to 1 and fill `out` with NaN instead
+ * of spinning for ever; the caller must check *status at a synchronisation point before trusting parameters
+ * updated from `out` (the Python binding does: distributed.PeerAllReducer.check()).
+ * Memory-model assumption (csrc/peer.cuh): the {value, step} halves of a 16-byte volatile vector store to
+ * peer memory are observed untorn (8-byte granularity) by the peer's 16-byte volatile loads.  True on NVLink 5 /
+ * NVSwitch (verified against NCCL by bench.py's multi-GPU self-check on every run), not promised by PTX. */
 size_t doper_peer_buffer_bytes(int32_t n);
 int doper_peer_alloc(int32_t n, void** buffer, unsigned char handle[64]);
 int doper_peer_open(const unsigned char handle[64], void** buffer);
 int doper_peer_close(void* buffer);
 int doper_peer_free(void* buffer);
 int doper_allreduce_oneshot(doper_stream_t stream, int32_t rank, int32_t world, void* const* buffers, int32_t n,
-                            const float* in, float* out, int32_t* status);
+                            const float* in, float* out, int32_t* status, double timeout_seconds);
 
 /* ---- measurement helper --------------------------------------------------------------- */
 

@@ -46,9 +46,9 @@ def test_argument_validation_happens_before_any_launch():
     """Bad arguments are rejected with distinct codes and never reach CUDA (safe without a GPU)."""
     from doper_b200 import _abi
     L = _abi.lib
-    assert L.doper_scene_prepare(None, 0, 201, None, None) == 1  # BAD_SHAPE
-    assert L.doper_scene_prepare(None, 1, 201, None, None) == 2  # NULL_PTR
-    assert L.doper_scene_prepare(None, 1, 201, 24, 256) == 3  # MISALIGNED (segments % 16)
+    assert L.doper_scene_prepare(None, 0, 201, None, 0.1, None) == 1  # BAD_SHAPE
+    assert L.doper_scene_prepare(None, 1, 201, None, 0.1, None) == 2  # NULL_PTR
+    assert L.doper_scene_prepare(None, 1, 201, 24, 0.1, 256) == 3  # MISALIGNED (segments % 16)
     assert L.doper_points_inside(None, 4, 200, 8, 16, 1) == 7  # S % 3 != 0 -> UNSUPPORTED
     d = _abi.RolloutDesc()
     d.B, d.S, d.n_steps = 0, 201, 10

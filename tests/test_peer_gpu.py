@@ -37,7 +37,7 @@ def test_single_rank_identity_and_graph_replay(n):
         for step in range(5):  # both slots, several values of the device-side step counter
             x = torch.randn(n, device=dev)
             check(lib.doper_allreduce_oneshot(torch.cuda.current_stream().cuda_stream, 0, 1, ptrs, n, x.data_ptr(),
-                                              out.data_ptr(), status.data_ptr()), "doper_allreduce_oneshot")
+                                              out.data_ptr(), status.data_ptr(), 5.0), "doper_allreduce_oneshot")
             assert torch.equal(out, x), step
         # in place, replayed from a CUDA graph
         x = torch.randn(n, device=dev)
@@ -45,7 +45,7 @@ def test_single_rank_identity_and_graph_replay(n):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             check(lib.doper_allreduce_oneshot(torch.cuda.current_stream().cuda_stream, 0, 1, ptrs, n, y.data_ptr(),
-                                              y.data_ptr(), status.data_ptr()), "doper_allreduce_oneshot")
+                                              y.data_ptr(), status.data_ptr(), 5.0), "doper_allreduce_oneshot")
         for _ in range(3):
             y.copy_(x)
             graph.replay()
@@ -59,9 +59,9 @@ def test_single_rank_identity_and_graph_replay(n):
 def test_argument_validation():
     from doper_b200._abi import lib
     ptrs = (ctypes.c_void_p * 1)(None)
-    assert lib.doper_allreduce_oneshot(None, 0, 1, ptrs, 8, 16, 16, None) != 0   # null peer buffer
-    assert lib.doper_allreduce_oneshot(None, 0, 17, ptrs, 8, 16, 16, None) != 0  # more than 16 ranks
-    assert lib.doper_allreduce_oneshot(None, 1, 1, ptrs, 8, 16, 16, None) != 0   # rank outside the group
+    assert lib.doper_allreduce_oneshot(None, 0, 1, ptrs, 8, 16, 16, None, 0.0) != 0   # null peer buffer
+    assert lib.doper_allreduce_oneshot(None, 0, 17, ptrs, 8, 16, 16, None, 0.0) != 0  # more than 16 ranks
+    assert lib.doper_allreduce_oneshot(None, 1, 1, ptrs, 8, 16, 16, None, 0.0) != 0   # rank outside the group
     assert lib.doper_peer_buffer_bytes(0) == 0
 
 

@@ -42,7 +42,7 @@ for regime, sigma in (("default", 10.0), ("reference_regime", 0.0)):
     w = syn.make_workload(name, n_balls=balls, impulse_sigma=sigma)
     B, n = w["x0"].shape[0], w["n_steps"]
     scene = JaxScene(w["segments"])
-    _, sws = scene.prepared(dev)
+    _, sws = scene.prepared(dev, 0.1)
     x0, v0 = torch.tensor(w["x0"], device=dev), torch.tensor(w["v0"], device=dev)
     st = torch.cuda.current_stream().cuda_stream
     desc = ball_sim._make_desc(B, scene, w["sim_time"], n, w["attractor"], w["constants"], ball_sim.RolloutOptions())

@@ -24,7 +24,7 @@ w = syn.make_workload(name, n_balls=balls, lo=lo, hi=hi)
 B, n = w["x0"].shape[0], w["n_steps"]
 dev = torch.device("cuda", 0)
 scene = JaxScene(w["segments"])
-_, sws = scene.prepared(dev)
+_, sws = scene.prepared(dev, 0.1)
 x0, v0 = torch.tensor(w["x0"], device=dev), torch.tensor(w["v0"], device=dev)
 st = torch.cuda.current_stream().cuda_stream
 if var == "default":

@@ -36,7 +36,7 @@ def main():
     B, n = w["x0"].shape[0], w["n_steps"]
     dev = torch.device("cuda", 0)
     scene = JaxScene(w["segments"])
-    _, sws = scene.prepared(dev)
+    _, sws = scene.prepared(dev, 0.1)
     st = torch.cuda.current_stream().cuda_stream
     tgt = ball_sim._target2(w["target"])
     desc = ball_sim._make_desc(B, scene, w["sim_time"], n, w["attractor"], w["constants"], ball_sim.RolloutOptions())
