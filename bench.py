@@ -144,6 +144,59 @@ def physical_gpu_index(local_index):
 
 
 # ------------------------------------------------------------------------------------------------
+# parity of the timed plan, measured on the timed workload (untimed, product code only)
+# ------------------------------------------------------------------------------------------------
+def parity_block(ball_sim, lib, check, ptr, st, desc, sws, bufs, w, scene, opts, gv_default, B, n_steps):
+    """(a) the benchmarked backward (binary64 chunk-parallel) against the sequential reference-order fp32
+    backward (flags bit 1: bit-identical to the oracle's adjoint, tests/test_parity_gpu.py) on the SAME
+    forward workspace, over ALL balls; (b) the benchmarked forward against the exact full sweep (every
+    (ball, segment) pair through the reference arithmetic, exact index log): hit flags at every step,
+    segment index at every collision, final states bit for bit."""
+    import copy
+    import ctypes
+
+    import torch
+
+    d2 = copy.copy(desc)
+    d2.flags = int(desc.flags) | 2
+    gx2 = torch.empty(2 * B, dtype=torch.float32, device=gv_default.device)
+    gv2 = torch.empty(2 * B, dtype=torch.float32, device=gv_default.device)
+    check(lib.doper_rollout_bwd(st, ctypes.byref(d2), ptr(sws), ptr(bufs.ws), 0, ptr(bufs.scratch), 0, ptr(gx2), ptr(gv2)),
+          "bwd (sequential)")
+    torch.cuda.synchronize()
+    a = gv_default.double().view(B, 2).cpu().numpy()
+    b = gv2.double().view(B, 2).cpu().numpy()
+    fin = np.isfinite(a).all(1) & np.isfinite(b).all(1)
+    nrm = np.maximum(np.linalg.norm(b[fin], axis=1), 1e-30)
+    e = np.abs(a[fin] - b[fin]).max(axis=1) / nrm
+    back = {"compared_to": "sequential backward (fp32, the reference's operation order; bit-exact vs the oracle adjoint in tests)",
+            "balls": int(B), "balls_finite_in_both": int(fin.sum()),
+            "balls_nonfinite_in_exactly_one": int((np.isfinite(a).all(1) != np.isfinite(b).all(1)).sum()),
+            "rel_err_vs_ball_gradient_norm": {"median": float(np.median(e)), "q99": float(np.quantile(e, 0.99)),
+                                              "q999": float(np.quantile(e, 0.999)), "max": float(e.max())},
+            "fraction_within_1e-4": float((e <= 1e-4).mean()),
+            "note": "the default backward is the float64 adjoint of the fp32 trajectory rounded once to fp32 "
+                    "(within 1e-6 of oracle_grad_truth64 in tests); this gap is the fp32 reference-order adjoint's own rounding error"}
+    cap = 8192 if B * n_steps > 64_000_000 else B
+    sl = slice(0, cap)
+    seg = w["segments"][sl] if w["per_env"] else w["segments"]
+    args_h = (w["sim_time"], n_steps, seg, w["x0"][sl], w["v0"][sl], w["attractor"], w["constants"])
+    h_def = ball_sim.rollout_history(*args_h, opts)
+    h_ex = ball_sim.rollout_history(*args_h, ball_sim.RolloutOptions(force_exact_sweep=True, broad_phase=False,
+                                                                    exact_index_log=True))
+    hit = h_ex["hit"]
+    fwd = {"compared_to": "exact full sweep: every (ball, segment) pair through the reference arithmetic, index logged at every step",
+           "balls_compared": int(cap), "ball_steps_compared": int(cap) * int(n_steps), "collisions": int(hit.sum()),
+           "hit_flag_mismatches": int((h_def["hit"] != hit).sum()),
+           "collision_index_mismatches": int((h_def["idx"][hit] != h_ex["idx"][hit]).sum()),
+           "final_state_bit_mismatches": int((h_def["x_T"].view(np.uint32) != h_ex["x_T"].view(np.uint32)).sum() +
+                                             (h_def["v_T"].view(np.uint32) != h_ex["v_T"].view(np.uint32)).sum())}
+    if cap != B:
+        fwd["note"] = f"first {cap} balls of the batch (per-ball results do not depend on the batch: tests)"
+    return {"backward": back, "forward": fwd}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def ours(args):
@@ -219,19 +272,22 @@ def ours(args):
     v0 = torch.tensor(w["v0"], device=device)
     bufs = ball_sim._Buffers.get(device, desc)
     o = bufs.out
-    loss_sum, xT, vT = o[0:1], o[4:4 + 2 * B], o[4 + 2 * B:4 + 4 * B]
+    # the one exchange step of a data-parallel trainer: controller grads (6,602 fp32,
+    # reference controllers.py:12-18) + the scalar loss, summed over ranks.  The loss kernel writes its sum
+    # straight into slot 6,602 of the exchange buffer (no copy launch between backward and exchange).
+    ar_buf = torch.zeros(6602 + 2, dtype=torch.float32, device=device)
+    loss_sum, xT, vT = ar_buf[6602:6603], o[4:4 + 2 * B], o[4 + 2 * B:4 + 4 * B]
     gv, gx, lpb = o[4 + 4 * B:4 + 6 * B], o[4 + 6 * B:4 + 8 * B], o[4 + 8 * B:4 + 9 * B]
     tgt = ball_sim._target2(w["target"])
-    st = torch.cuda.current_stream().cuda_stream
+    cur = lambda: torch.cuda.current_stream().cuda_stream  # launches follow torch's current stream (graph capture)
+    st = cur()
     dref = ctypes.byref(desc)
-    # the one exchange step of a data-parallel trainer: controller grads (6,602 fp32,
-    # reference controllers.py:12-18) + the scalar loss, summed over ranks
-    ar_buf = torch.zeros(6602 + 1, dtype=torch.float32, device=device)
+    ar_out = torch.zeros(6602 + 2, dtype=torch.float32, device=device)
     peer = None
     if world > 1 and not args.nccl:
         from doper_b200.distributed import PeerAllReducer
         try:
-            peer = PeerAllReducer(6602 + 1, device)  # one-shot all-reduce over NVLink peer memory (csrc/peer.cuh)
+            peer = PeerAllReducer(6602 + 2, device)  # one-shot all-reduce over NVLink peer memory (csrc/peer.cuh)
         except RuntimeError as e:  # no CUDA IPC between these GPUs (raised on every rank together): NCCL
             if rank == 0:
                 print(f"bench: peer-memory all-reduce unavailable, using NCCL ({e})", file=sys.stderr)
@@ -239,19 +295,19 @@ def ours(args):
 
     def exchange():
         # the optimiser step needs the reduced gradient: the exchange is on the step's critical path
-        ar_buf[6602:].copy_(loss_sum, non_blocking=True)
         if peer is not None:
-            peer.all_reduce(ar_buf, out=ar_buf)
+            peer.all_reduce(ar_buf, out=ar_out)
         else:
-            dist.all_reduce(ar_buf)
+            ar_out.copy_(ar_buf, non_blocking=True)
+            dist.all_reduce(ar_out)
 
     def fwd():
-        check(lib.doper_rollout_fwd(st, dref, ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT), 0, 0, 0,
+        check(lib.doper_rollout_fwd(cur(), dref, ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT), 0, 0, 0,
                                     ptr(bufs.ws)), "fwd")
 
     def loss_bwd():
-        check(lib.doper_l1_loss(st, B, ptr(xT), tgt, ptr(lpb), ptr(loss_sum), ptr(bufs.scratch)), "loss")
-        check(lib.doper_rollout_bwd(st, dref, ptr(sws), ptr(bufs.ws), ptr(bufs.bwd_scratch), ptr(bufs.scratch), 0, ptr(gx), ptr(gv)),
+        check(lib.doper_l1_loss(cur(), B, ptr(xT), tgt, ptr(lpb), ptr(loss_sum), ptr(bufs.scratch)), "loss")
+        check(lib.doper_rollout_bwd(cur(), dref, ptr(sws), ptr(bufs.ws), ptr(bufs.bwd_scratch), ptr(bufs.scratch), 0, ptr(gx), ptr(gv)),
               "bwd")
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
@@ -261,9 +317,33 @@ def ours(args):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    def one_step():
         fwd(); loss_bwd()
+        if world > 1:
+            exchange()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
     barrier()
+    # The timed loop replays ONE CUDA graph per step (memset + forward + loss + backward (2 kernels) + exchange):
+    # the same kernels on the same buffers, without the host's per-launch gaps.  --no-graph launches eagerly.
+    step_graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            one_step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize()
+        step_graph, fwd_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(step_graph, stream=side):
+            one_step()
+        with torch.cuda.graph(fwd_graph, stream=side):
+            fwd()
+        torch.cuda.synchronize()
+        for _ in range(3):
+            step_graph.replay()
+        barrier()
 
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
@@ -276,18 +356,30 @@ def ours(args):
     for k in range(K):
         flush.fill_(k & 0xFF)  # L2 flush between timed iterations (untimed: outside the event pairs)
         ev[k][0].record()
-        fwd()
-        ev[k][1].record()
-        loss_bwd()
-        if world > 1:
-            exchange()
+        if step_graph is not None:
+            step_graph.replay()
+        else:
+            fwd()
+            ev[k][1].record()
+            loss_bwd()
+            if world > 1:
+                exchange()
         ev[k][2].record()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
-    fwd_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    if step_graph is not None:
+        # the forward kernel alone (the roofline's dominant kernel), same buffers, after an L2 flush each
+        fev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(min(K, 20))]
+        for a, b in fev:
+            flush.fill_(1)
+            a.record(); fwd_graph.replay(); b.record()
+        torch.cuda.synchronize()
+        fwd_ms = np.array([a.elapsed_time(b) for a, b in fev])
+    else:
+        fwd_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
     tot = torch.tensor([step_ms.sum()], dtype=torch.float64, device=device)
     tot_min = tot.clone()
     if world > 1:
@@ -315,6 +407,29 @@ def ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B * n_steps / (float(e2e_ms.item()) * 1e-3)
 
+    # ---- parity of the timed plan on the timed workload (untimed) -----------------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        one_step()  # eager, so that gv / the workspace are those of this exact workload
+        torch.cuda.synchronize()
+        parity = parity_block(ball_sim, lib, check, ptr, cur(), desc, sws, bufs, w, scene, opts, gv, B, n_steps)
+    # ---- N > 1: the peer-memory exchange against NCCL on the same vectors (every run) ---------
+    exch_check = None
+    if world > 1 and peer is not None:
+        g = torch.Generator(device=device); g.manual_seed(1234 + rank)
+        worst, bits_equal = 0.0, True
+        for _ in range(20):
+            v = torch.randn(6602 + 2, device=device, generator=g) * 100.0
+            ref_v = v.clone(); dist.all_reduce(ref_v)
+            got_v = peer.all_reduce(v).clone()
+            worst = max(worst, float(((got_v - ref_v).abs() / ref_v.abs().clamp_min(1e-3)).max()))
+            gathered = [torch.empty_like(got_v) for _ in range(world)]
+            dist.all_gather(gathered, got_v)
+            bits_equal = bits_equal and all(torch.equal(gathered[0].view(torch.int32), t.view(torch.int32)) for t in gathered)
+        peer.check()
+        exch_check = {"vectors": 20, "max_rel_diff_vs_nccl": worst, "bit_identical_across_ranks": bool(bits_equal),
+                      "what": "doper_allreduce_oneshot vs torch.distributed.all_reduce (NCCL) on the same random vectors"}
+    barrier()
     # ---- roofline of the dominant kernel -----------------------------------------------------
     roof = None
     cpu = None
@@ -357,7 +472,22 @@ def ours(args):
                 prof = json.loads(tp.read_text()).get("kernels", {}).get(fwd_kernel, {})
             except Exception:
                 prof = {}
-        pruned = "cull" in fwd_kernel or "tpc" in fwd_kernel
+        pruned = "cull" in fwd_kernel or "tpc" in fwd_kernel or "baked" in fwd_kernel
+        # executed work (what the silicon did, from the committed ncu capture of this kernel on this workload)
+        executed = None
+        wi = prof.get("warp_instructions_per_launch") if (not args.balls and not args.sim_steps and prof.get("workload") == name) else None
+        sm_mhz = (sampler.summary().get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        chain_cycles = 88  # dependent chain of one free-flight step: 22 FP32 operations x 4 cycles (physics.cuh:free_step)
+        if wi:
+            kernel_cycles = float(fwd_ms.mean()) * 1e-3 * sm_mhz * 1e6
+            executed = {
+                "warp_instructions_per_ball_step": round(wi / (B * n_steps), 2),
+                "active_lanes_per_warp_instruction": prof.get("active_lanes_per_instruction"),
+                "fp32_lane_ops_per_ball_step": prof.get("fp32_lane_ops_per_ball_step"),
+                "issue_slots_used": round(wi / (kernel_cycles * 148 * 4), 4),
+                "lane_issue_slots_used": round(wi * (prof.get("active_lanes_per_instruction") or 32) / (kernel_cycles * 148 * 4 * 32), 4),
+                "source": prof.get("report"),
+            }
         roof = {
             "kernel": fwd_kernel, "backward_kernel": bwd_kernel, "bound": "fp32", "achieved": round(achieved, 3),
             "peak": round(peak, 3), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
@@ -373,9 +503,13 @@ def ours(args):
             "frac_of_fma_peak": round(fwd_flops / (float(fwd_ms.mean()) * 1e-3) / (2 * rates[1]), 4),
             "fma_peak_tflops": round(2 * rates[1] / 1e12, 3),
             "kernel_ms": round(float(fwd_ms.mean()), 4),
-            "kernel_share_of_step": round(float(fwd_ms.sum() / step_ms.sum()), 4),
+            "kernel_share_of_step": round(float(fwd_ms.mean() / step_ms.mean()), 4),
             "algorithmic_flops_per_launch": fwd_flops,
             "traffic": traffic,
+            "executed": executed,
+            "serial_floor_us": round(n_steps * chain_cycles / sm_mhz, 2),
+            "serial_floor_definition": "n_steps x the dependent FP32 chain of one free-flight step (22 operations x 4 cycles): "
+                                       "a ball's steps cannot overlap, so no forward kernel can be faster than this",
             "hbm": {"achieved": round(ws_bytes / (float(fwd_ms.mean()) * 1e-3) / 1e9, 2), "peak": hbm_peak,
                     "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "algorithmic_bytes_per_launch": ws_bytes},
@@ -392,30 +526,34 @@ def ours(args):
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_label(name, B, S, n_steps, bool(w["per_env"])) +
-                       (" [reference regime: v0 = U(-1,2)^2, no impulse stand-in]" if args.reference_regime else "") +
-                       ((f" per GPU ({world} GPUs, every rank runs the workload's own seeded batch, "
-                         if replicated else
-                         f" per GPU ({world} GPUs, a globally seeded batch of {total} balls sliced by rank, ") +
-                        ("one-shot NVLink peer-memory all-reduce" if peer is not None else "NCCL all-reduce") +
-                        " of 6,603 fp32 per step)" if world > 1 else ""),
-                       "shards": ("n/a" if world == 1 else ("replicated seeded batch" if replicated else "sliced global batch")),
-                       "ms_per_step_fastest_rank": round(ms_per_step_fastest_rank, 5),
-                       "l2": "256 MiB buffer rewritten between timed iterations (flush), outside the event pairs",
-                       "lanes_per_ball": int(desc.lanes_per_ball) or "auto", "ckpt_every": int(lib.doper_rollout_ckpt_every(dref)),
-                       "sweep": "exact" if args.exact else ("filtered+exact, every pair" if args.full_sweep else
-                                                          "broad phase (candidate lists) + filtered + exact")},
+            "config": config_block(name, B, S, n_steps, bool(w["per_env"]), args),
+            "plan": {"forward_kernel": lib.doper_rollout_plan_name(dref, 0).decode(),
+                     "backward_kernel": lib.doper_rollout_plan_name(dref, 1).decode(),
+                     "ckpt_every": int(lib.doper_rollout_ckpt_every(dref)),
+                     "sweep": "exact" if args.exact else ("filtered+exact, every pair" if args.full_sweep else
+                                                        "broad phase (baked per-cell lists / per-ball lists) + exact"),
+                     "launch": "eager" if args.no_graph else "one CUDA graph per step",
+                     "shards": ("n/a" if world == 1 else ("every rank runs the workload's own seeded batch" if replicated
+                                                          else f"a globally seeded batch of {total} balls sliced by rank")),
+                     "exchange": ("none" if world == 1 else
+                                  ("one-shot NVLink peer-memory all-reduce kernel (csrc/peer.cuh)" if peer is not None else "NCCL all-reduce")
+                                  + " of 6,604 fp32 (controller gradients + loss) per step, inside the timed region"),
+                     "ms_per_step_fastest_rank": round(ms_per_step_fastest_rank, 5)},
             "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 4 * B * 4,
                     "d2h_bytes_per_step": (4 + 6 * B) * 4, "ms_per_step": round(float(e2e_ms.item()), 5),
                     "api": "doper_b200.sim.ball_sim.vmapped_grad_and_value(host numpy arrays)"},
-            # forward, loss, backward (+ the chunk-parallel pass of the hybrid backward on large batches)
-            "gpu_launches": (3 + lib.doper_rollout_plan_name(dref, 1).decode().count("+")) * K,
+            # kernels of this repository per step: forward, loss, backward (1 or 2), exchange (N > 1, peer kernel)
+            "gpu_launches": (3 + lib.doper_rollout_plan_name(dref, 1).decode().count("+") + (1 if peer is not None else 0)) * K,
             "wall_ms_timed_region": round(wall_ms, 3),
             "roofline": roof,
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if parity:
+            line["parity"] = parity
+        if exch_check:
+            line["exchange_self_check"] = exch_check
         print(json.dumps(line), flush=True)
     if world > 1:
         if peer is not None:
@@ -476,6 +614,8 @@ def main():
     ap.add_argument("--distinct-shards", action="store_true",
                     help="N > 1: slice one globally seeded batch instead of running the workload's batch on every rank")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch the timed steps eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) parity block")
     args = ap.parse_args()
     if args.impl == "reference":
         reference(args)

@@ -10,7 +10,7 @@
 //     cell with a list      -> the estimate of every list entry (9 FMAs each); all above far2 -> no collision;
 //                              else the reference arithmetic for the entries the filter keeps (sweep.cuh)
 //     outside the grid      -> further than r_max + h from every segment: no collision
-//     |point| > 2 M, NaN / inf, degenerate scene, r > r_max -> reference arithmetic over every segment
+//     NaN / inf point, degenerate scene, r > r_max -> reference arithmetic over every segment
 // The proof obligations are those of the per-ball hit lists (sweep.cuh) with the cell centre as list centre
 // and rho = half diagonal / 0.98; results are bit-identical to every other forward kernel (same tests).
 //
@@ -28,42 +28,47 @@ namespace doper {
 struct BakeView {
     const uint32_t* cell_start;
     const unsigned short* items;
-    float x0, y0, inv_h, fnx, fny, far2, M2;  // M2 = 2 M: beyond it a point takes the exact path
+    float x0, y0, h, inv_h, fnx, fny, far2;
+    float rho2chk;  // (0.98 rho)^2: a cell's list is valid for every point this close to the cell centre
+    float M;        // bound on |coordinate| of the scene and of every point within rho of a cell centre
     int nx, ok;
 };
 
 // (hit, idx) of ONE point against the baked lists; reference semantics: hit = (min_j d_ref_j <= r), idx = its
-// first index (valid only when hit).
+// first index (valid only when hit).  One pass over the cell's list: an entry whose estimate^2 exceeds far2
+// has d_ref > r (cull_far2's proof) and can neither collide nor tie with a colliding segment, so the
+// reference arithmetic runs for the other entries only (the segments within ~r of the point: usually none,
+// one, or the two that share a vertex), and the lexicographic (distance, index) minimum over those IS the
+// reference's argmin whenever the step collides.
 __device__ __forceinline__ bool baked_hit(const SceneView& sc, const BakeView& bk, float px, float py, float r, int& idx) {
     const float M = fmaxf(fabsf(px), fabsf(py));
     idx = 0;
-    if (!bk.ok || !(M <= bk.M2)) {  // NaN / far-away point, degenerate scene, r > r_max: every pair, reference arithmetic
+    if (!bk.ok || !(M <= 1.0e15f)) {  // NaN / inf point, degenerate scene, r > r_max: every pair, reference arithmetic
         float dist;
         unpack_key(lane_exact<1>(sc, px, py, 0), idx, dist);
         return dist <= r;
     }
+    // Outside the grid (box of the scene grown by r_max + h): the real distance to every segment is at least
+    // r_max + h - (rounding of the look-up), and at least |p| / 2 once |p| > 2 M; d_ref >= D - 38 u max(M, |p|) > r.
     const float fx = (px - bk.x0) * bk.inv_h, fy = (py - bk.y0) * bk.inv_h;
-    if (!(fx >= 0.0f && fx < bk.fnx && fy >= 0.0f && fy < bk.fny)) return false;  // outside the grid: far from everything
+    if (!(fx >= 0.0f && fx < bk.fnx && fy >= 0.0f && fy < bk.fny)) return false;
     const int cell = (int)fy * bk.nx + (int)fx;
-    const int k0 = (int)bk.cell_start[cell], k1 = (int)bk.cell_start[cell + 1];
-    if (k0 == k1) return false;
-    float amin = __int_as_float(0x7f800000);
-    for (int k = k0; k < k1; ++k) {
-        const int i = bk.items[k];
-        amin = fminf(amin, approx_d2(px, py, sc.q[i], sc.rl[i]));
-    }
-    if (amin > bk.far2) return false;  // every list entry provably further than r
-    const float Mq = fmaxf(sc.scale, M);
-    const float thr = __fmaf_rn(amin, kFilterOneEps, kFilterKappaPerM2 * Mq * Mq);
+    int k = (int)bk.cell_start[cell];
+    const int k1 = (int)bk.cell_start[cell + 1];
     unsigned long long key = kNoKey;
-    for (int k = k0; k < k1; ++k) {
-        const int i = bk.items[k];
-        const float4 q = sc.q[i];
-        if (approx_d2(px, py, q, sc.rl[i]) <= thr) {
-            const unsigned long long kk = make_key(cand_dist(px, py, q), i);
-            key = kk < key ? kk : key;
-        }
+    for (; k + 1 < k1; k += 2) {  // two entries per trip: their loads and estimates overlap
+        const int i0 = bk.items[k], i1 = bk.items[k + 1];
+        const float4 q0 = sc.q[i0], q1 = sc.q[i1];
+        const float a0 = approx_d2(px, py, q0, sc.rl[i0]), a1 = approx_d2(px, py, q1, sc.rl[i1]);
+        if (!(a0 > bk.far2)) { const unsigned long long kk = make_key(cand_dist(px, py, q0), i0); key = kk < key ? kk : key; }
+        if (!(a1 > bk.far2)) { const unsigned long long kk = make_key(cand_dist(px, py, q1), i1); key = kk < key ? kk : key; }
     }
+    if (k < k1) {
+        const int i0 = bk.items[k];
+        const float4 q0 = sc.q[i0];
+        if (!(approx_d2(px, py, q0, sc.rl[i0]) > bk.far2)) { const unsigned long long kk = make_key(cand_dist(px, py, q0), i0); key = kk < key ? kk : key; }
+    }
+    if (key == kNoKey) return false;
     float dist;
     unpack_key(key, idx, dist);
     return dist <= r;  // NaN -> false (ball_sim.py:164)
@@ -112,8 +117,9 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
         sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
     }
     const Consts c = p.c;
-    bk.x0 = bh.x0; bk.y0 = bh.y0; bk.inv_h = bh.inv_h; bk.fnx = bh.fnx; bk.fny = bh.fny; bk.nx = bh.nx;
-    bk.far2 = bh.far2; bk.M2 = 2.0f * bh.M;
+    bk.x0 = bh.x0; bk.y0 = bh.y0; bk.h = bh.h; bk.inv_h = bh.inv_h; bk.fnx = bh.fnx; bk.fny = bh.fny; bk.nx = bh.nx;
+    bk.far2 = bh.far2; bk.M = bh.M;
+    bk.rho2chk = (kCullRhoCheck * bh.rho) * (kCullRhoCheck * bh.rho);
     bk.ok = bh.enabled && !sc.weird && c.r <= bh.r_max;
 
     int64_t ball = (int64_t)blockIdx.x * BPB + tid / G;
@@ -151,7 +157,8 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
         // ---- (2) my step against the baked list of my point's cell -------------------------------------
         const bool valid = lane < Tq;
         int idx = 0;
-        const bool hit = valid && baked_hit(sc, bk, my.x, my.y, c.r, idx);
+        bool hit = false;
+        hit = valid && baked_hit(sc, bk, my.x, my.y, c.r, idx);
         // ---- (3) first collision of the group, commit ---------------------------------------------------
         int f = Tq;
         bool ev_hit = false;

@@ -152,11 +152,13 @@ bool use_cull(const doper_rollout_desc* d) {
 // exact index log (bit 17: the cell lists are hit lists), a forced exact sweep (bit 0), pinned lane counts /
 // legacy kernels, or flags bit 20 (which keeps the per-ball candidate-list kernels).
 bool use_baked(const doper_rollout_desc* d) {
+    if (!d->per_env && (d->flags & (1 << 21)) && d->lanes_per_ball >= 1 && d->lanes_per_ball <= 16) return true;  // pinned G
     return !d->per_env && d->lanes_per_ball == 0 && !(d->flags & (1 | kLegacyPlanBits | (1 << 15) | (1 << 16) | (1 << 17) | (1 << 18) | (1 << 20)));
 }
 
 // lanes (= speculated time steps) per ball of the baked kernel: small batches need them to fill the SMs
 int baked_lanes(const doper_rollout_desc* d) {
+    if (d->flags & (1 << 21)) return d->lanes_per_ball;
     if (d->B <= 1024) return 16;
     if (d->B <= 4096) return 8;
     if (d->B <= 16384) return 4;

@@ -41,7 +41,7 @@ class RolloutOptions:
                  sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True,
                  broad_phase: bool = None, exact_index_log: bool = False,
                  broad_phase_time_parallel: bool = False, hit_records: bool = True, hit_capacity: int = 0,
-                 baked_broad_phase: bool = True):
+                 baked_broad_phase: bool = True, baked_lanes: int = 0):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
@@ -62,11 +62,12 @@ class RolloutOptions:
         # shared scenes: the static per-cell candidate lists baked into the prepared scene (default plan);
         # False keeps the kernels with per-ball candidate lists
         self.baked_broad_phase = bool(baked_broad_phase)
+        self.baked_lanes = int(baked_lanes)  # 0 = chosen from the batch size; else lanes (speculated steps) per ball
 
     def key(self) -> tuple:
         return (self.ckpt_every, self.lanes_per_ball, self.force_exact_sweep, self.sequential_backward, self.smem_forward,
                 self.time_parallel, self.broad_phase, self.exact_index_log, self.broad_phase_time_parallel,
-                self.hit_records, self.hit_capacity, self.baked_broad_phase)
+                self.hit_records, self.hit_capacity, self.baked_broad_phase, self.baked_lanes)
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -111,6 +112,9 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
                ((1 << 18) if opts.broad_phase_time_parallel else 0) |
                (0 if opts.hit_records else (1 << 19)) | (0 if opts.baked_broad_phase else (1 << 20)))
     d.hit_capacity = opts.hit_capacity
+    if opts.baked_lanes:
+        d.lanes_per_ball = opts.baked_lanes
+        d.flags |= 1 << 21
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d

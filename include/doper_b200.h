@@ -163,6 +163,8 @@ typedef struct {
                                bit 15 / bit 16: forbid / force the broad-phase (candidate list)
                                       forward kernels; bit 18: with bit 16 and lanes_per_ball >= 2, the
                                       time-parallel (lane = step) variant instead of the lane-split one;
+                               bit 21: with lanes_per_ball = 1, 2, 4, 8 or 16: the baked kernel with that many
+                                      lanes (speculated steps) per ball instead of the batch-size rule;
                                bit 20: keep the per-ball candidate-list kernels for a shared scene
                                       (default there: the baked per-cell lists of doper_scene_prepare);
                                bit 19: no collision records (the backward replays every collided

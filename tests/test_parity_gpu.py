@@ -300,8 +300,10 @@ def test_c2_default_vs_reference_order_gradient_distribution(sim, cref):
           f"vs truth64: default {e_got:.2e}, reference order {e_seq:.2e}")
 
 
-def test_gradient_vs_torch_autograd(sim):
-    """Independent gradient truth: torch autograd of the select-form graph (fp32)."""
+def test_gradient_vs_torch_autograd(sim, cref):
+    """Independent check: torch autograd of the select-form graph (fp32, its own summation order).  Like the
+    oracle's C adjoint it is an fp32 evaluation whose worst ball is a few 1e-4 from float64 truth; the default
+    backward must be no further from it than it is from truth."""
     ball_sim, _ = sim
     w = syn.make_workload("c2", n_balls=512)
     n = 500
@@ -318,10 +320,19 @@ def test_gradient_vs_torch_autograd(sim):
     assert_bitexact(xT.detach().cpu().numpy(), xT_ref, "x_T")
     finite = np.isfinite(gv_ref).all(axis=1)
     assert finite.mean() > 0.99
-    e = grad_rel_err(v0.grad.cpu().numpy()[finite], gv_ref[finite])
-    assert e.max() < 1e-4, e.max()
-    ex = grad_rel_err(x0.grad.cpu().numpy()[finite], aux["grad_x0"][finite])
-    assert ex.max() < 1e-3, ex.max()  # dL/dx0 is an extension (reference: argnums=4 only)
+    truth, truth_x = cref.grad_truth64(n, np.float32((n / 1000) / n), c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+    ours = v0.grad.cpu().numpy()
+    assert grad_rel_err(ours[finite], truth[finite]).max() <= TRUTH_RTOL
+    e_torch = grad_rel_err(gv_ref[finite], truth[finite])  # torch's own distance from truth
+    e = np.abs(ours[finite] - gv_ref[finite]).max(-1) / np.maximum(np.linalg.norm(truth[finite], axis=-1), 1e-30)
+    assert (e <= 1.001 * e_torch + 2 * TRUTH_RTOL).all(), (e.max(), e_torch.max())
+    assert np.quantile(e, 0.99) < GRAD_RTOL
+    # dL/dx0 is an extension (reference: argnums=4 only): same rule
+    ours_x = x0.grad.cpu().numpy()
+    assert grad_rel_err(ours_x[finite], truth_x[finite]).max() <= TRUTH_RTOL
+    ex_torch = grad_rel_err(aux["grad_x0"][finite], truth_x[finite])
+    ex = np.abs(ours_x[finite] - aux["grad_x0"][finite]).max(-1) / np.maximum(np.linalg.norm(truth_x[finite], axis=-1), 1e-30)
+    assert (ex <= 1.001 * ex_torch + 2 * TRUTH_RTOL).all(), (ex.max(), ex_torch.max())
     assert abs(loss.item() - loss_ref) <= 1e-5 * abs(loss_ref)
 
 
