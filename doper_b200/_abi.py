@@ -18,7 +18,7 @@ LIB_PATH = Path(os.environ.get("DOPER_B200_LIB") or (Path(__file__).resolve().pa
 ABI_VERSION = 2
 
 EXPORTS = (
-    "doper_abi_version", "doper_error_string", "doper_scene_workspace_bytes", "doper_scene_prepare",
+    "doper_abi_version", "doper_fp_policy", "doper_error_string", "doper_scene_workspace_bytes", "doper_scene_prepare",
     "doper_closest_segment", "doper_points_inside", "doper_rollout_ckpt_every", "doper_rollout_log_ball_major",
     "doper_rollout_workspace_bytes", "doper_rollout_bwd_scratch_bytes", "doper_rollout_plan_name",
     "doper_rollout_fwd", "doper_rollout_bwd", "doper_l1_loss", "doper_value_and_grad",
@@ -68,6 +68,7 @@ def _load() -> ctypes.CDLL:
         raise ImportError(f"doper_b200: {LIB_PATH} lacks symbols {missing}")
     vp, fp = c_void_p, c_void_p  # device pointers are passed as integers
     lib.doper_abi_version.restype = ctypes.c_int
+    lib.doper_fp_policy.restype = ctypes.c_int
     lib.doper_error_string.restype = c_char_p
     lib.doper_error_string.argtypes = [ctypes.c_int]
     lib.doper_scene_workspace_bytes.restype = c_size_t

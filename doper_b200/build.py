@@ -27,30 +27,49 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "doper_b200.h"]
+    inc = ROOT.parent / "include"
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [inc / "doper_b200.h", inc / "doper_fp_policy.h"]
 
 
-def _digest() -> str:
+def _digest(extra=()) -> str:
     h = hashlib.sha256()
     for s in _sources():
         h.update(s.name.encode())
         h.update(s.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join([*NVCC_FLAGS, *extra]).encode())
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def lib_path(policy: int | None = None) -> Path:
+    """``policy``: floating-point contraction mask (include/doper_fp_policy.h); None = the header's default.
+    Other masks build side by side as ``libdoper_b200_p<mask>.so`` (selected with DOPER_B200_LIB)."""
+    return LIB if policy is None else OUT_DIR / f"libdoper_b200_p{int(policy)}.so"
+
+
+def build(force: bool = False, verbose: bool = False, policy: int | None = None, wait: bool = True):
     OUT_DIR.mkdir(exist_ok=True)
-    dig = _digest()
-    if LIB.exists() and STAMP.exists() and STAMP.read_text() == dig and not force:
-        return LIB
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "kernels.cu")]
+    extra = [] if policy is None else [f"-DDOPER_FP_POLICY={int(policy)}"]
+    lib = lib_path(policy)
+    stamp = STAMP if policy is None else OUT_DIR / f"build_p{int(policy)}.stamp"
+    dig = _digest(extra)
+    if lib.exists() and stamp.exists() and stamp.read_text() == dig and not force:
+        return lib
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-o", str(lib), str(CSRC / "kernels.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
+    if not wait:  # caller overlaps several builds: returns (process, finish)
+        proc = subprocess.Popen(cmd)
+
+        def finish():
+            if proc.wait() != 0:
+                raise subprocess.CalledProcessError(proc.returncode, cmd)
+            stamp.write_text(dig)
+            return lib
+        return finish
     subprocess.run(cmd, check=True)
-    STAMP.write_text(dig)
-    return LIB
+    stamp.write_text(dig)
+    return lib
 
 
 if __name__ == "__main__":

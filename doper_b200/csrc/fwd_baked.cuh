@@ -40,21 +40,31 @@ struct BakeView {
 // reference arithmetic runs for the other entries only (the segments within ~r of the point: usually none,
 // one, or the two that share a vertex), and the lexicographic (distance, index) minimum over those IS the
 // reference's argmin whenever the step collides.
-__device__ __forceinline__ bool baked_hit(const SceneView& sc, const BakeView& bk, float px, float py, float r, int& idx) {
+// Part 1, the cell look-up: 0 = no collision possible (outside the grid, or an empty cell), 1 = the cell's list is
+// items[k0 .. k1), 2 = the baked lists do not apply to this point (NaN / inf point, degenerate scene, r > r_max).
+__device__ __forceinline__ int baked_cell(const BakeView& bk, float px, float py, int& k0, int& k1) {
     const float M = fmaxf(fabsf(px), fabsf(py));
+    k0 = k1 = 0;
+    if (!bk.ok || !(M <= 1.0e15f)) return 2;
+    // Outside the grid (box of the scene grown by r_max + h): the real distance to every segment is at least
+    // r_max + h - (rounding of the look-up), and at least |p| / 2 once |p| > 2 M; d_ref >= D - 38 u max(M, |p|) > r.
+    const float fx = (px - bk.x0) * bk.inv_h, fy = (py - bk.y0) * bk.inv_h;
+    if (!(fx >= 0.0f && fx < bk.fnx && fy >= 0.0f && fy < bk.fny)) return 0;
+    const int cell = (int)fy * bk.nx + (int)fx;
+    k0 = (int)bk.cell_start[cell];
+    k1 = (int)bk.cell_start[cell + 1];
+    return k1 > k0 ? 1 : 0;
+}
+
+// Part 2, the narrow phase over the cell's list (kind 1) or over the whole scene (kind 2).
+__device__ __forceinline__ bool baked_list_hit(const SceneView& sc, const BakeView& bk, float px, float py, float r, int kind,
+                                               int k, const int k1, int& idx) {
     idx = 0;
-    if (!bk.ok || !(M <= 1.0e15f)) {  // NaN / inf point, degenerate scene, r > r_max: every pair, reference arithmetic
+    if (kind == 2) {  // every pair, reference arithmetic
         float dist;
         unpack_key(lane_exact<1>(sc, px, py, 0), idx, dist);
         return dist <= r;
     }
-    // Outside the grid (box of the scene grown by r_max + h): the real distance to every segment is at least
-    // r_max + h - (rounding of the look-up), and at least |p| / 2 once |p| > 2 M; d_ref >= D - 38 u max(M, |p|) > r.
-    const float fx = (px - bk.x0) * bk.inv_h, fy = (py - bk.y0) * bk.inv_h;
-    if (!(fx >= 0.0f && fx < bk.fnx && fy >= 0.0f && fy < bk.fny)) return false;
-    const int cell = (int)fy * bk.nx + (int)fx;
-    int k = (int)bk.cell_start[cell];
-    const int k1 = (int)bk.cell_start[cell + 1];
     unsigned long long key = kNoKey;
     for (; k + 1 < k1; k += 2) {  // two entries per trip: their loads and estimates overlap
         const int i0 = bk.items[k], i1 = bk.items[k + 1];
@@ -72,6 +82,14 @@ __device__ __forceinline__ bool baked_hit(const SceneView& sc, const BakeView& b
     float dist;
     unpack_key(key, idx, dist);
     return dist <= r;  // NaN -> false (ball_sim.py:164)
+}
+
+__device__ __forceinline__ bool baked_hit(const SceneView& sc, const BakeView& bk, float px, float py, float r, int& idx) {
+    int k0, k1;
+    idx = 0;
+    const int kind = baked_cell(bk, px, py, k0, k1);
+    if (kind == 0) return false;
+    return baked_list_hit(sc, bk, px, py, r, kind, k0, k1, idx);
 }
 
 template <int G, bool STAGED, int THREADS>

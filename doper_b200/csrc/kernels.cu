@@ -10,6 +10,8 @@
 //   fwd_full.cuh   full-sweep forward kernels (every pair every step)
 //   fwd_broad.cuh  broad-phase forward kernels with per-ball candidate lists: rollout_fwd_cull_kernel, rollout_fwd_tpc_kernel
 //   fwd_baked.cuh  rollout_fwd_baked_kernel: static per-cell candidate lists baked into the prepared scene (default plan, shared scenes)
+//   fwd_pipe.cuh   rollout_fwd_pipe_kernel: producer warp (free-flight chain, lane = (ball, axis)) + consumer warp (baked look-ups,
+//                  log, collisions) per 16 balls; default plan of shared scenes up to kPipeMaxBalls balls
 //   bwd.cuh        rollout_bwd_kernel (sequential fp32, bit-exact), rollout_bwd_jacobian_kernel + rollout_bwd_fold_kernel (binary64, default)
 //   queries.cuh    l1_loss_kernel, closest_segment_kernel, points_inside_kernel, fp32_probe_kernel
 //   sensor.cuh     range-sensor ray casting
@@ -27,6 +29,7 @@
 #include "fwd_full.cuh"
 #include "fwd_broad.cuh"
 #include "fwd_baked.cuh"
+#include "fwd_pipe.cuh"
 #include "bwd.cuh"
 #include "queries.cuh"
 
@@ -151,24 +154,43 @@ bool use_cull(const doper_rollout_desc* d) {
 // Baked broad phase (static per-cell lists, fwd_baked.cuh): shared scenes under the default plan.  Not with the
 // exact index log (bit 17: the cell lists are hit lists), a forced exact sweep (bit 0), pinned lane counts /
 // legacy kernels, or flags bit 20 (which keeps the per-ball candidate-list kernels).
+constexpr int kBakedOffBits = 1 | kLegacyPlanBits | (1 << 15) | (1 << 16) | (1 << 17) | (1 << 18) | (1 << 20);
+
+bool baked_staged(const doper_rollout_desc* d) {
+    const int S_pad = scene_layout(1, d->S).S_pad;
+    return (size_t)S_pad * 20 + bake_bytes(S_pad) + 64 <= 96 * 1024;
+}
+
+// Pipelined kernel (fwd_pipe.cuh: producer / consumer warp pairs over the baked lists): the default of shared
+// scenes that fit shared memory up to kPipeMaxBalls balls (beyond, one thread per ball fills the machine and
+// executes fewer instructions per ball-step).  flags bit 22 forbids it; bit 23 with lanes_per_ball = 4, 8 or 16
+// pins it with that window length.
+constexpr int64_t kPipeMaxBalls = 16384;
+bool pipe_pinned(const doper_rollout_desc* d) {
+    return !d->per_env && (d->flags & (1 << 23)) && !(d->flags & kBakedOffBits) &&
+           (d->lanes_per_ball == 4 || d->lanes_per_ball == 8 || d->lanes_per_ball == 16);
+}
+bool use_pipe(const doper_rollout_desc* d) {
+    if (d->per_env || d->n_steps < 1 || !baked_staged(d)) return false;
+    if (pipe_pinned(d)) return true;
+    return d->lanes_per_ball == 0 && !(d->flags & (kBakedOffBits | (1 << 21) | (1 << 22) | (1 << 23))) && d->B <= kPipeMaxBalls;
+}
+int pipe_window(const doper_rollout_desc* d) { return pipe_pinned(d) ? d->lanes_per_ball : 8; }
+
 bool use_baked(const doper_rollout_desc* d) {
+    if (use_pipe(d)) return true;  // same lists; the lane = step kernel serves the calls the pipelined one does not (trajectory output)
     if (!d->per_env && (d->flags & (1 << 21)) && d->lanes_per_ball >= 1 && d->lanes_per_ball <= 16) return true;  // pinned G
-    return !d->per_env && d->lanes_per_ball == 0 && !(d->flags & (1 | kLegacyPlanBits | (1 << 15) | (1 << 16) | (1 << 17) | (1 << 18) | (1 << 20)));
+    return !d->per_env && d->lanes_per_ball == 0 && !(d->flags & kBakedOffBits);
 }
 
 // lanes (= speculated time steps) per ball of the baked kernel: small batches need them to fill the SMs
 int baked_lanes(const doper_rollout_desc* d) {
-    if (d->flags & (1 << 21)) return d->lanes_per_ball;
+    if ((d->flags & (1 << 21)) && !pipe_pinned(d)) return d->lanes_per_ball;
     if (d->B <= 1024) return 16;
     if (d->B <= 4096) return 8;
     if (d->B <= 16384) return 4;
     if (d->B <= 49152) return 2;
     return 1;
-}
-
-bool baked_staged(const doper_rollout_desc* d) {
-    const int S_pad = scene_layout(1, d->S).S_pad;
-    return (size_t)S_pad * 20 + bake_bytes(S_pad) + 64 <= 96 * 1024;
 }
 
 bool use_tpc(const doper_rollout_desc* d) {
@@ -200,7 +222,7 @@ bool use_tp(const doper_rollout_desc* d) {
 }
 
 // lane = time step kernels write [B][n_steps] so that a group's stores are contiguous
-bool log_ball_major(const doper_rollout_desc* d) { return use_tp(d) || use_tpc(d) || (use_baked(d) && baked_lanes(d) > 1); }
+bool log_ball_major(const doper_rollout_desc* d) { return use_tp(d) || use_tpc(d) || use_pipe(d) || (use_baked(d) && baked_lanes(d) > 1); }
 
 int tp_warps_per_block(const doper_rollout_desc* d) {
     if (d->per_env) return 4;
@@ -346,6 +368,19 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
     return staged ? go(rollout_fwd_baked_kernel<G, true, THREADS>) : go(rollout_fwd_baked_kernel<G, false, THREADS>);
 }
 
+template <int U, int CW>
+int launch_fwd_pipe(cudaStream_t st, const FwdParams& p) {
+    const int S_pad = scene_layout(1, p.S).S_pad;
+    const size_t smem = (size_t)S_pad * 20 + (bake_bytes(S_pad) - sizeof(BakeHeader)) + 16 + kPipeGroups * sizeof(PipeShared<U>);
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(rollout_fwd_pipe_kernel<U, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DOPER_ERR_SMEM_LIMIT;
+    const int bpb = kPipeGroups * kPipeBalls;
+    const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
+    rollout_fwd_pipe_kernel<U, CW><<<grid, 32 * (1 + CW) * kPipeGroups, smem, st>>>(p);
+    return launch_status();
+}
+
 template <int G>
 int launch_closest(cudaStream_t st, int64_t N, int S, const float* pts, const float* segs, const void* ws,
                    int32_t* idx, float* dist, float* seg_out, size_t smem) {
@@ -386,6 +421,8 @@ int launch_range_sensor(cudaStream_t st, int64_t N, int R, int S, const float* p
 extern "C" {
 
 int doper_abi_version(void) { return DOPER_ABI_VERSION; }
+
+int doper_fp_policy(void) { return DOPER_FP_POLICY; }
 
 const char* doper_error_string(int code) {
     switch (code) {
@@ -512,6 +549,10 @@ int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
 const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward) {
     if (validate_desc(d) != DOPER_OK) return "invalid";
     if (backward) return (d->flags & 2) ? "rollout_bwd_kernel" : "rollout_bwd_jacobian_kernel+rollout_bwd_fold_kernel";
+    if (use_pipe(d)) {
+        const int u = pipe_window(d);
+        return u == 4 ? "rollout_fwd_pipe_kernel<4>" : (u == 16 ? "rollout_fwd_pipe_kernel<16>" : "rollout_fwd_pipe_kernel<8>");
+    }
     if (use_baked(d)) {
         static const char* const baked[] = {"rollout_fwd_baked_kernel<1>", "rollout_fwd_baked_kernel<2>", "rollout_fwd_baked_kernel<4>",
                                             "rollout_fwd_baked_kernel<8>", "rollout_fwd_baked_kernel<16>"};
@@ -583,6 +624,13 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         p.sink.count = reinterpret_cast<int*>(base);
         p.sink.cap = (int)w.cap;
         if (cudaMemsetAsync(base, 0, 256, st) != cudaSuccess) return DOPER_ERR_LAUNCH;  // record counter
+    }
+    if (use_pipe(d) && !traj_x && !traj_v && !traj_a) {
+        switch (pipe_window(d)) {
+            case 4: return launch_fwd_pipe<4, 2>(st, p);
+            case 16: return launch_fwd_pipe<16, 4>(st, p);
+            default: return launch_fwd_pipe<8, 4>(st, p);
+        }
     }
     if (use_baked(d)) {
         switch (baked_lanes(d)) {

@@ -3,15 +3,20 @@
 //
 // This translation unit is compiled with -fmad=false, IEEE division / sqrt (-prec-div=true
 // -prec-sqrt=true, no -use_fast_math, denormals kept), so every `a*b + c` below is two
-// roundings exactly as written; the only single-rounding fused multiply-adds are the explicit
-// __fmaf_rn calls: get_new_state's coordinate update (reference ball_sim.py:76), which the
-// reference's recorded output pins as contracted, and the sweep's candidate
-// filter (sweep.cuh), which never decides a result.
+// roundings exactly as written.  WHICH mul+add pairs of the reference's forward arithmetic are
+// single-rounding fused multiply-adds is decided in one header shared with the CPU oracle,
+// include/doper_fp_policy.h (DOPER_POS_UPDATE / VEL_UPDATE / LERP / DOT2 / FORCE_SUM / REFLECT;
+// default: only get_new_state's coordinate update, ball_sim.py:76, which the reference's recorded
+// output pins as contracted).  The other explicit __fmaf_rn calls are the exact
+// divisions by loop invariants (Markstein) and the sweep's candidate filter (sweep.cuh), which never
+// decides a result.
 //
 // Reference: doper/sim/ball_sim.py:15-132,171-209 ; doper/sim/jax_geometry.py:119-138.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "../../include/doper_fp_policy.h"
 
 namespace doper {
 
@@ -58,17 +63,21 @@ __device__ __forceinline__ float fric(float v, const Consts& c) {
 }
 
 // get_new_state coordinate update, ball_sim.py:76 (single rounding, see header comment)
-__device__ __forceinline__ float pos_update(float v, float dt, float x) { return __fmaf_rn(v, dt, x); }
+__device__ __forceinline__ float pos_update(float v, float dt, float x) { return DOPER_POS_UPDATE(v, dt, x); }
+// get_new_state velocity update v + a dt, ball_sim.py:75 (:109, :131)
+__device__ __forceinline__ float vel_update(float a, float dt, float v) { return DOPER_VEL_UPDATE(a, dt, v); }
+// 2-vector dot product / squared norm a0 b0 + a1 b1
+__device__ __forceinline__ float dot2(float a0, float b0, float a1, float b1) { return DOPER_DOT2(a0, b0, a1, b1); }
 
 // jax_geometry.py:132-136 on a pre-digested segment q = (s0x, s0y, svx, svy).
 // sv = s1 - s0 is ball-independent, so reading it is bit-identical to recomputing it.
 __device__ __forceinline__ void proj(float px, float py, const float4& q, float& cx, float& cy,
                                      float& t) {
-    float L = q.z * q.z + q.w * q.w;
+    float L = dot2(q.z, q.z, q.w, q.w);
     float pvx = px - q.x, pvy = py - q.y;
-    t = clip_nan((pvx * q.z + pvy * q.w) / L, 0.0f, 1.0f);
-    cx = q.x + t * q.z;
-    cy = q.y + t * q.w;
+    t = clip_nan(dot2(pvx, q.z, pvy, q.w) / L, 0.0f, 1.0f);
+    cx = DOPER_LERP(q.x, t, q.z);
+    cy = DOPER_LERP(q.y, t, q.w);
 }
 
 // squared distance exactly as the reference computes it before the sqrt (jax_geometry.py:151-152)
@@ -76,7 +85,7 @@ __device__ __forceinline__ float seg_dist2(float px, float py, const float4& q) 
     float cx, cy, t;
     proj(px, py, q, cx, cy, t);
     float dx = px - cx, dy = py - cy;
-    return dx * dx + dy * dy;
+    return dot2(dx, dx, dy, dy);
 }
 
 // Hit-log word (one per ball-step, written by every forward kernel, read by the backward kernels):
@@ -133,8 +142,8 @@ __device__ __forceinline__ void free_step(float x, float y, float vx, float vy, 
                                           State& o) {
     float px = -(2.0f * (x - c.ax)), py = -(2.0f * (y - c.ay));
     float fx = fric(vx, c), fy = fric(vy, c);
-    float ax = div_invariant(c.ks * px + fx, c.m, c.rcp_m, c), ay = div_invariant(c.ks * py + fy, c.m, c.rcp_m, c);
-    float v1x = vx + ax * c.dt, v1y = vy + ay * c.dt;
+    float ax = div_invariant(DOPER_FORCE_SUM(c.ks, px, fx), c.m, c.rcp_m, c), ay = div_invariant(DOPER_FORCE_SUM(c.ks, py, fy), c.m, c.rcp_m, c);
+    float v1x = vel_update(ax, c.dt, vx), v1y = vel_update(ay, c.dt, vy);
     o.x = pos_update(v1x, c.dt, x);
     o.y = pos_update(v1y, c.dt, y);
     o.vx = v1x; o.vy = v1y; o.ax = ax; o.ay = ay;
@@ -161,9 +170,9 @@ __device__ __forceinline__ void free_step_acc(float x, float y, float vx, float 
     const float nfx = (((-clip_nan(vx, -1.0f, 1.0f)) * c.m) * 9.8f) * c.f;
     const float nfy = (((-clip_nan(vy, -1.0f, 1.0f)) * c.m) * 9.8f) * c.f;
     const float fx = div_markstein(nfx, c.r, c.rcp_r), fy = div_markstein(nfy, c.r, c.rcp_r);
-    const float nax = c.ks * px + fx, nay = c.ks * py + fy;
+    const float nax = DOPER_FORCE_SUM(c.ks, px, fx), nay = DOPER_FORCE_SUM(c.ks, py, fy);
     const float ax = div_markstein(nax, c.m, c.rcp_m), ay = div_markstein(nay, c.m, c.rcp_m);
-    const float v1x = vx + ax * c.dt, v1y = vy + ay * c.dt;
+    const float v1x = vel_update(ax, c.dt, vx), v1y = vel_update(ay, c.dt, vy);
     o.x = pos_update(v1x, c.dt, x);
     o.y = pos_update(v1y, c.dt, y);
     o.vx = v1x; o.vy = v1y; o.ax = ax; o.ay = ay;
@@ -183,6 +192,33 @@ __device__ __forceinline__ bool free_step_fast(float x, float y, float vx, float
     return div_range_ok(nmin, nmax, c);
 }
 
+// ONE AXIS of the free-flight step (ball_sim.py:192-202 acts on x and y separately: the potential and the
+// friction clip are per component): (pos, vel) of one coordinate -> the candidate (pos', vel'), `att` = that
+// coordinate of the attractor.  Exactly the operations of free_step_acc() / free_step() on one component, so
+// two lanes that integrate the two axes of a ball produce the same bits as one lane doing both: the serial
+// chain per step is then 24 instructions instead of 49 (rollout_fwd_pipe_kernel's producer warp).
+__device__ __forceinline__ void axis_step_acc(float& pos, float& vel, float att, const Consts& c, float& nmin, float& nmax) {
+    const float pp = -(2.0f * (pos - att));
+    const float nf = (((-clip_nan(vel, -1.0f, 1.0f)) * c.m) * 9.8f) * c.f;
+    const float fr = div_markstein(nf, c.r, c.rcp_r);
+    const float na = DOPER_FORCE_SUM(c.ks, pp, fr);
+    const float a = div_markstein(na, c.m, c.rcp_m);
+    const float v1 = vel_update(a, c.dt, vel);
+    pos = pos_update(v1, c.dt, pos);
+    vel = v1;
+    nmax = fmaxf(fmaxf(nmax, fabsf(nf)), fabsf(na));
+    nmin = fminf(fminf(nmin, fabsf(nf)), fabsf(na));
+}
+
+__device__ __forceinline__ void axis_step(float& pos, float& vel, float att, const Consts& c) {
+    const float pp = -(2.0f * (pos - att));
+    const float fr = fric(vel, c);
+    const float a = div_invariant(DOPER_FORCE_SUM(c.ks, pp, fr), c.m, c.rcp_m, c);
+    const float v1 = vel_update(a, c.dt, vel);
+    pos = pos_update(v1, c.dt, pos);
+    vel = v1;
+}
+
 // ball_sim.py:97-132 : time-of-impact sub-step, reflection, remaining sub-step
 // (out of line: rare, and keeps the hot step loop small; everything by value = in registers)
 __device__ __forceinline__ State resolve_inline(float x, float y, float vx, float vy, const State& s1, const float4& seg,
@@ -200,26 +236,26 @@ __device__ __forceinline__ State resolve_inline(float x, float y, float vx, floa
     float c1x, c1y, t1;
     proj(s1.x, s1.y, seg, c1x, c1y, t1);
     float ox = c1x - x, oy = c1y - y;  // OLD coordinate (ball_sim.py:100)
-    float od = sqrtf(ox * ox + oy * oy);
+    float od = sqrtf(dot2(ox, ox, oy, oy));
     float nx = ox / od, ny = oy / od;
-    float toi = fabsf(od - c.r) / fabsf(nx * s1.vx + ny * s1.vy);
+    float toi = fabsf(od - c.r) / fabsf(dot2(nx, s1.vx, ny, s1.vy));
     toi = clip_nan(toi, 0.0f, c.dt);
-    float vsx = vx + s1.ax * toi, vsy = vy + s1.ay * toi;
+    float vsx = vel_update(s1.ax, toi, vx), vsy = vel_update(s1.ay, toi, vy);
     float xsx = pos_update(vsx, toi, x), xsy = pos_update(vsy, toi, y);
     float c2x, c2y, t2;
     proj(xsx, xsy, seg, c2x, c2y, t2);
     float o2x = c2x - xsx, o2y = c2y - xsy;
-    float o2d = sqrtf(o2x * o2x + o2y * o2y);
+    float o2d = sqrtf(dot2(o2x, o2x, o2y, o2y));
     float n2x = o2x / o2d, n2y = o2y / o2d;
-    float k = n2x * vsx + n2y * vsy;
+    float k = dot2(n2x, vsx, n2y, vsy);
     float vnx = n2x * k, vny = n2y * k;
     float vpx = vsx - vnx, vpy = vsy - vny;
-    float vax = vpx - c.e * vnx, vay = vpy - c.e * vny;
+    float vax = DOPER_REFLECT(vpx, c.e, vnx), vay = DOPER_REFLECT(vpy, c.e, vny);
     float pbx = -(2.0f * (xsx - c.ax)), pby = -(2.0f * (xsy - c.ay));  // no attractor_strength (:124)
     float fbx = fric(vax, c), fby = fric(vay, c);
     float abx = div_invariant(pbx + fbx, c.m, c.rcp_m, c), aby = div_invariant(pby + fby, c.m, c.rcp_m, c);
     float tau = c.dt - toi;
-    float vbx = vax + abx * tau, vby = vay + aby * tau;
+    float vbx = vel_update(abx, tau, vax), vby = vel_update(aby, tau, vay);
     o.x = pos_update(vbx, tau, xsx);
     o.y = pos_update(vby, tau, xsy);
     o.vx = vbx; o.vy = vby; o.ax = abx; o.ay = aby;
@@ -276,28 +312,28 @@ __device__ __forceinline__ HitFwd hit_forward(float x, float y, float vx, float 
     float c1x, c1y;
     proj(s1.x, s1.y, seg, c1x, c1y, f.t1);
     float ox = c1x - x, oy = c1y - y;
-    f.od = sqrtf(ox * ox + oy * oy);
+    f.od = sqrtf(dot2(ox, ox, oy, oy));
     f.nx = ox / f.od; f.ny = oy / f.od;
-    f.s = f.nx * s1.vx + f.ny * s1.vy;
+    f.s = dot2(f.nx, s1.vx, f.ny, s1.vy);
     float num = fabsf(f.od - c.r);
     f.den = fabsf(f.s);
     f.toi_raw = num / f.den;
     f.toi = clip_nan(f.toi_raw, 0.0f, c.dt);
-    f.vsx = vx + s1.ax * f.toi; f.vsy = vy + s1.ay * f.toi;
+    f.vsx = vel_update(s1.ax, f.toi, vx); f.vsy = vel_update(s1.ay, f.toi, vy);
     float xsx = pos_update(f.vsx, f.toi, x), xsy = pos_update(f.vsy, f.toi, y);
     float c2x, c2y;
     proj(xsx, xsy, seg, c2x, c2y, f.t2);
     float o2x = c2x - xsx, o2y = c2y - xsy;
-    f.o2d = sqrtf(o2x * o2x + o2y * o2y);
+    f.o2d = sqrtf(dot2(o2x, o2x, o2y, o2y));
     f.n2x = o2x / f.o2d; f.n2y = o2y / f.o2d;
-    f.k = f.n2x * f.vsx + f.n2y * f.vsy;
+    f.k = dot2(f.n2x, f.vsx, f.n2y, f.vsy);
     float vnx = f.n2x * f.k, vny = f.n2y * f.k;
-    f.vax = (f.vsx - vnx) - c.e * vnx; f.vay = (f.vsy - vny) - c.e * vny;
+    f.vax = DOPER_REFLECT(f.vsx - vnx, c.e, vnx); f.vay = DOPER_REFLECT(f.vsy - vny, c.e, vny);
     float pbx = -(2.0f * (xsx - c.ax)), pby = -(2.0f * (xsy - c.ay));
     f.abx = div_invariant(pbx + fric(f.vax, c), c.m, c.rcp_m, c);
     f.aby = div_invariant(pby + fric(f.vay, c), c.m, c.rcp_m, c);
     f.tau = c.dt - f.toi;
-    f.vbx = f.vax + f.abx * f.tau; f.vby = f.vay + f.aby * f.tau;
+    f.vbx = vel_update(f.abx, f.tau, f.vax); f.vby = vel_update(f.aby, f.tau, f.vay);
     return f;
 }
 

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kQueryThreads) points_inside_kernel(int64_t N,
             float4 s = raw[base + j];
             float svx = s.z - s.x, svy = s.w - s.y;      // :21
             float nx = svy, ny = -svx;                   // :22
-            float nrm = sqrtf(nx * nx + ny * ny);        // :23
+            float nrm = sqrtf(dot2(nx, nx, ny, ny));      // :23
             tile[j] = make_float4(s.x, s.y, nx / nrm, ny / nrm);
         }
         __syncthreads();
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kQueryThreads) points_inside_kernel(int64_t N,
             for (int e = 0; e < 3; ++e) {
                 float4 q = tile[t + e];
                 float pvx = px - q.x, pvy = py - q.y;    // :52
-                float d = pvx * q.z + pvy * q.w;         // :53
+                float d = dot2(pvx, q.z, pvy, q.w);          // :53
                 all = all && (d < 0.0f);                 // sign(d) < 0 ; NaN -> false
             }
             any = any || all;

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128) scene_prepare_kernel(int64_t n_scenes, in
         if (i < S) {
             float4 s = in[i];
             float svx = s.z - s.x, svy = s.w - s.y;  // jax_geometry.py:132
-            float len2 = svx * svx + svy * svy;      // :133
+            float len2 = dot2(svx, svx, svy, svy);    // :133
             q[i] = make_float4(s.x, s.y, svx, svy);
             rl[i] = 1.0f / len2;
             e1[i] = make_float2(s.z, s.w);

@@ -140,14 +140,14 @@ constexpr float kFilterKappaPerM2 = 4.0f * 129.0f * 1.02f *   // 4 (1 + 1/eps), 
 // Reference distance of ONE candidate. The division is skipped exactly when the clip decides
 // alone: dot <= 0 -> t = 0 and dot >= L -> t = 1 (L > 0 finite on this path; RN is monotone).
 __device__ __forceinline__ float cand_dist(float px, float py, const float4& q) {
-    const float L = q.z * q.z + q.w * q.w;
+    const float L = dot2(q.z, q.z, q.w, q.w);
     const float pvx = px - q.x, pvy = py - q.y;
-    const float dot = pvx * q.z + pvy * q.w;
+    const float dot = dot2(pvx, q.z, pvy, q.w);
     float t = 0.0f;
     if (dot > 0.0f) t = (dot >= L) ? 1.0f : dot / L;
-    const float cx = q.x + t * q.z, cy = q.y + t * q.w;
+    const float cx = DOPER_LERP(q.x, t, q.z), cy = DOPER_LERP(q.y, t, q.w);
     const float dx = px - cx, dy = py - cy;
-    return sqrtf(dx * dx + dy * dy);
+    return sqrtf(dot2(dx, dx, dy, dy));
 }
 
 // One lane's share of the filtered sweep: branch-free estimate loop that records candidates as

@@ -41,7 +41,8 @@ class RolloutOptions:
                  sequential_backward: bool = False, smem_forward: bool = False, time_parallel: bool = True,
                  broad_phase: bool = None, exact_index_log: bool = False,
                  broad_phase_time_parallel: bool = False, hit_records: bool = True, hit_capacity: int = 0,
-                 baked_broad_phase: bool = True, baked_lanes: int = 0):
+                 baked_broad_phase: bool = True, baked_lanes: int = 0,
+                 pipelined: bool | None = None, pipe_window: int = 0):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
@@ -63,11 +64,14 @@ class RolloutOptions:
         # False keeps the kernels with per-ball candidate lists
         self.baked_broad_phase = bool(baked_broad_phase)
         self.baked_lanes = int(baked_lanes)  # 0 = chosen from the batch size; else lanes (speculated steps) per ball
+        self.pipelined = pipelined  # None = library default; False: forbid rollout_fwd_pipe_kernel
+        self.pipe_window = int(pipe_window)  # 4, 8 or 16: pin rollout_fwd_pipe_kernel with that window
 
     def key(self) -> tuple:
         return (self.ckpt_every, self.lanes_per_ball, self.force_exact_sweep, self.sequential_backward, self.smem_forward,
                 self.time_parallel, self.broad_phase, self.exact_index_log, self.broad_phase_time_parallel,
-                self.hit_records, self.hit_capacity, self.baked_broad_phase, self.baked_lanes)
+                self.hit_records, self.hit_capacity, self.baked_broad_phase, self.baked_lanes, self.pipelined,
+                self.pipe_window)
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -115,6 +119,11 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
     if opts.baked_lanes:
         d.lanes_per_ball = opts.baked_lanes
         d.flags |= 1 << 21
+    if opts.pipelined is False:
+        d.flags |= 1 << 22
+    if opts.pipe_window:
+        d.lanes_per_ball = opts.pipe_window
+        d.flags |= 1 << 23
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d

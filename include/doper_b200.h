@@ -81,6 +81,10 @@ enum {
 #define DOPER_ABI_VERSION 2
 
 int doper_abi_version(void);
+
+/* The floating-point contraction mask the kernels were compiled with (include/doper_fp_policy.h): which
+ * mul+add pairs of the reference's arithmetic are single-rounding FMAs.  Default 1 (the coordinate update). */
+int doper_fp_policy(void);
 const char* doper_error_string(int code);
 
 /* ---- scene ---------------------------------------------------------------------------- */
@@ -167,6 +171,10 @@ typedef struct {
                                       lanes (speculated steps) per ball instead of the batch-size rule;
                                bit 20: keep the per-ball candidate-list kernels for a shared scene
                                       (default there: the baked per-cell lists of doper_scene_prepare);
+                               bit 22: forbid the pipelined forward kernel (producer / consumer warp pairs over
+                                      the baked lists: the default of shared scenes up to 16,384 balls);
+                               bit 23: with lanes_per_ball = 4, 8 or 16: the pipelined kernel with that window
+                                      length (speculated steps per producer / consumer hand-over);
                                bit 19: no collision records (the backward replays every collided
                                       step from its checkpoint: slower, same results);
                                bit 17: hit log holds the exact closest index at EVERY step (the

@@ -24,20 +24,23 @@
 #include <stdlib.h>
 #include <string.h>
 
-/* get_new_state's coordinate update x + v'*dt (ball_sim.py:76) is the one expression the
- * reference's recorded output (notebook cell 7) shows was contracted to a single-rounding FMA by
- * the authors' XLA:CPU; see oracle/ball_sim_np.py CONTRACT_POSITION_UPDATE. fmaf() is exact. */
-#ifndef ORACLE_NO_CONTRACT
-#define POS_UPDATE(v, dt, x) fmaf((v), (dt), (x))
-#else
-#define POS_UPDATE(v, dt, x) ((x) + (v) * (dt))
-#endif
+/* Which mul+add pairs of the forward arithmetic are single-rounding FMAs is decided in ONE header shared with
+ * the product kernels (include/doper_fp_policy.h; default: only get_new_state's coordinate update,
+ * ball_sim.py:76, which the reference's recorded output pins as contracted).  Build with
+ * -DDOPER_FP_POLICY=<mask> for another policy (oracle/cref.py build(policy=...)). fmaf() is exact. */
+#include "../include/doper_fp_policy.h"
 
 #define R float
 #define N(name) name##_f
 #define SQRT sqrtf
 #define FABS fabsf
 #define LIT(x) x##f
+#define POS_UPDATE(v, dt, x) DOPER_POS_UPDATE(v, dt, x)
+#define VEL_UPDATE(a, dt, v) DOPER_VEL_UPDATE(a, dt, v)
+#define LERP(s0, t, sv) DOPER_LERP(s0, t, sv)
+#define DOT2(a0, b0, a1, b1) DOPER_DOT2(a0, b0, a1, b1)
+#define FORCE_SUM(ks, p, f) DOPER_FORCE_SUM(ks, p, f)
+#define REFLECT(vp, e, vn) DOPER_REFLECT(vp, e, vn)
 #include "ball_sim_step.inc"
 #undef R
 #undef N
@@ -45,13 +48,24 @@
 #undef FABS
 #undef LIT
 #undef POS_UPDATE
+#undef VEL_UPDATE
+#undef LERP
+#undef DOT2
+#undef FORCE_SUM
+#undef REFLECT
 
+/* binary64 instantiation (gradient truth): the real-arithmetic formulas, no policy */
 #define R double
 #define N(name) name##_d
 #define SQRT sqrt
 #define FABS fabs
 #define LIT(x) x
 #define POS_UPDATE(v, dt, x) ((x) + (v) * (dt))
+#define VEL_UPDATE(a, dt, v) ((v) + (a) * (dt))
+#define LERP(s0, t, sv) ((s0) + (t) * (sv))
+#define DOT2(a0, b0, a1, b1) ((a0) * (b0) + (a1) * (b1))
+#define FORCE_SUM(ks, p, f) ((ks) * (p) + (f))
+#define REFLECT(vp, e, vn) ((vp) - (e) * (vn))
 #include "ball_sim_step.inc"
 #undef R
 #undef N
@@ -59,6 +73,11 @@
 #undef FABS
 #undef LIT
 #undef POS_UPDATE
+#undef VEL_UPDATE
+#undef LERP
+#undef DOT2
+#undef FORCE_SUM
+#undef REFLECT
 
 /* the fp32 instantiation under its historical names */
 typedef consts_t_f consts_t;
@@ -75,7 +94,7 @@ static inline float seg_dist(float px, float py, const float *s) {
     float cx, cy, t;
     proj(px, py, s, &cx, &cy, &t);
     float dx = px - cx, dy = py - cy;
-    return sqrtf(dx * dx + dy * dy);
+    return sqrtf(DOPER_DOT2(dx, dx, dy, dy));
 }
 
 /* jax_geometry.py:172-174; first minimal index, NaN counts as minimal */
@@ -119,6 +138,8 @@ static consts_t mk(const float *k) {
 
 /* ---- exported ---------------------------------------------------------- */
 
+int oracle_fp_policy(void) { return DOPER_FP_POLICY; }
+
 void oracle_closest_segment(int64_t N, int S, const float *pts, const float *segs,
                             int32_t *idx, float *dist) {
 #pragma omp parallel for schedule(static)
@@ -138,10 +159,10 @@ void oracle_points_inside(int64_t N, int n_tri, const float *pts, const float *s
                 const float *s = segs + 4 * (size_t)(3 * t + e);
                 float svx = s[2] - s[0], svy = s[3] - s[1];
                 float nx = svy, ny = -svx;
-                float nrm = sqrtf(nx * nx + ny * ny);
+                float nrm = sqrtf(DOPER_DOT2(nx, nx, ny, ny));
                 float nhx = nx / nrm, nhy = ny / nrm;
                 float pvx = px - s[0], pvy = py - s[1];
-                float d = pvx * nhx + pvy * nhy;
+                float d = DOPER_DOT2(pvx, nhx, pvy, nhy);
                 all &= (d < 0.0f); /* sign(d) < 0 ; NaN -> false */
             }
             any |= all;

@@ -28,13 +28,23 @@ _FLAGS = {
 }
 
 
-def build(flavour: str = "portable", force: bool = False) -> Path:
+_POLICY_H = _HERE.parent / "include" / "doper_fp_policy.h"
+
+# bits of include/doper_fp_policy.h (which mul+add pairs are single-rounding FMAs)
+FP_POS, FP_VEL, FP_LERP, FP_DOT, FP_DOT_REV, FP_FORCE = 1, 2, 4, 8, 16, 32
+FP_DEFAULT = FP_POS
+
+
+def build(flavour: str = "portable", force: bool = False, policy: int | None = None) -> Path:
+    """``policy``: contraction mask (None = the header's default, shared with the product kernels)."""
     _OUT.mkdir(exist_ok=True)
-    so = _OUT / f"liboracle_{flavour}.so"
-    if so.exists() and not force and so.stat().st_mtime >= max(_SRC.stat().st_mtime, _INC.stat().st_mtime):
+    so = _OUT / (f"liboracle_{flavour}.so" if policy is None else f"liboracle_{flavour}_p{int(policy)}.so")
+    newest = max(_SRC.stat().st_mtime, _INC.stat().st_mtime, _POLICY_H.stat().st_mtime)
+    if so.exists() and not force and so.stat().st_mtime >= newest:
         return so
     cmd = ["gcc", "-std=c11", "-shared", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math",
-           *_FLAGS[flavour], str(_SRC), "-o", str(so), "-lm"]
+           *_FLAGS[flavour], *([] if policy is None else [f"-DDOPER_FP_POLICY={int(policy)}"]),
+           str(_SRC), "-o", str(so), "-lm"]
     subprocess.run(cmd, check=True)
     return so
 
@@ -51,9 +61,11 @@ def _fp(a):
 class CRef:
     """Thin numpy wrapper. All arrays are float32 C-contiguous."""
 
-    def __init__(self, flavour: str = "portable"):
-        self.lib = ctypes.CDLL(str(build(flavour)))
+    def __init__(self, flavour: str = "portable", policy: int | None = None):
+        self.lib = ctypes.CDLL(str(build(flavour, policy=policy)))
         L = self.lib
+        L.oracle_fp_policy.restype = ctypes.c_int
+        self.policy = int(L.oracle_fp_policy())
         L.oracle_closest_segment.argtypes = [ctypes.c_int64, ctypes.c_int, _f, _f, _i, _f]
         L.oracle_points_inside.argtypes = [ctypes.c_int64, ctypes.c_int, _f, _f, _u8]
         L.oracle_rollout_fwd.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_int,

@@ -16,7 +16,12 @@ from .ball_sim_np import acceleration, euler, Consts
 f32 = np.float32
 
 
-def run_notebook_sim(physics: dict):
+FP_POS, FP_VEL, FP_FORCE = 1, 2, 32  # bits of include/doper_fp_policy.h that this prototype exercises
+
+
+def run_notebook_sim(physics: dict, policy: int | None = None):
+    """``policy``: None = the oracle's default helpers (ball_sim_np.euler); else a contraction mask, evaluated
+    here explicitly so that tests can show which masks reproduce the recorded output."""
     r = physics["radius"]
     volume = 4 * np.pi * (r ** 3) / 3  # cell 5: python-double arithmetic
     mass = volume * physics["ro"]
@@ -33,6 +38,15 @@ def run_notebook_sim(physics: dict):
         traj.append(x.copy())
         pot = -(scale * (f32(2.0) * (x - A)))  # -grad(20*sum((x-A)**2))
         fr = ((((-np.sign(v)) * c.mass) * c.g) * c.radius) * c.friction / c.radius  # cell 2
-        a = acceleration(pot, fr, c)  # same helper as the rollout oracle
-        x, v = euler(x, v, a, dt)  # same helper as the rollout oracle
+        if policy is None:
+            a = acceleration(pot, fr, c)  # same helper as the rollout oracle
+            x, v = euler(x, v, a, dt)  # same helper as the rollout oracle
+            continue
+        from .ball_sim_np import fma_f32
+        y = f32(2.0) * (x - A)
+        num = fma_f32(np.full_like(y, -scale), y, fr) if policy & FP_FORCE else pot + fr  # -(scale*y) + fr
+        a = num / c.mass
+        v1 = fma_f32(a, dt, v) if policy & FP_VEL else v + a * dt
+        x = fma_f32(v1, dt, x) if policy & FP_POS else x + v1 * dt
+        v = v1
     return x, v, np.stack(traj)

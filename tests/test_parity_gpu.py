@@ -656,12 +656,12 @@ def test_baked_forward_bitexact_every_lane_count(sim, cref, n_balls, n_steps, la
     ball_sim, geo = sim
     w = syn.make_workload("c2", n_balls=n_balls)
     scene = geo.JaxScene(w["segments"])
-    assert _plan(ball_sim, n_balls, scene, n_steps, w) == f"rollout_fwd_baked_kernel<{lanes}>"
+    assert _plan(ball_sim, n_balls, scene, n_steps, w, _opts(ball_sim, pipelined=False)) == f"rollout_fwd_baked_kernel<{lanes}>"
     c = onp.make_constants(w["constants"])
     ref = cref.rollout_fwd(n_steps, np.float32((n_steps / 1000) / n_steps), c, w["attractor"], w["segments"], w["x0"], w["v0"],
                            want_traj=True)
     got = ball_sim.rollout_history(n_steps / 1000, n_steps, scene, w["x0"], w["v0"], w["attractor"], w["constants"],
-                                   _opts(ball_sim, ckpt_every=16), want_trajectory=True)
+                                   _opts(ball_sim, ckpt_every=16, pipelined=False), want_trajectory=True)
     assert np.array_equal(got["hit"], ref["hit"]), "hit flags"
     assert np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]]), "collision segment indices"
     assert got["records_seen"] == int(ref["hit"].sum())
@@ -683,6 +683,106 @@ def test_baked_forward_bitexact_every_lane_count(sim, cref, n_balls, n_steps, la
         assert_bitexact(got["record_states"][ks, :2], start_x, "record states")
 
 
+# ------------------------------------------------------------------------------------------------
+# pipelined forward (producer / consumer warp pairs over the baked lists): default plan up to 16,384 balls
+# ------------------------------------------------------------------------------------------------
+def _start_states(ref, w):
+    tt, bb = np.nonzero(ref["hit"])
+    sx = np.where(tt[:, None] > 0, ref["traj_x"][np.maximum(tt - 1, 0), bb], w["x0"][bb])
+    sv = np.where(tt[:, None] > 0, ref["traj_v"][np.maximum(tt - 1, 0), bb], w["v0"][bb])
+    return tt, bb, sx, sv
+
+
+@pytest.mark.parametrize("window", [0, 4, 8, 16])  # 0 = the default plan
+@pytest.mark.parametrize("n_balls,n_steps,K", [(1, 1, 0), (1, 64, 16), (15, 7, 4), (16, 300, 16), (333, 301, 16), (3000, 150, 7),
+                                                (4096, 500, 32)])
+def test_pipelined_forward_bitexact(sim, cref, n_balls, n_steps, K, window):
+    """rollout_fwd_pipe_kernel<U>: hit flags, collision segment indices, collision records (state at the start of
+    each collided step), checkpoints, clip bits of the log and final states bit-exact against the oracle, for
+    every window length, ragged batches, rollouts shorter than a window and lengths that are not multiples of it."""
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=n_balls)
+    scene = geo.JaxScene(w["segments"])
+    opts = _opts(ball_sim, ckpt_every=K, pipe_window=window)
+    assert _plan(ball_sim, n_balls, scene, n_steps, w, opts) == f"rollout_fwd_pipe_kernel<{window or 8}>"
+    c = onp.make_constants(w["constants"])
+    ref = cref.rollout_fwd(n_steps, np.float32((n_steps / 1000) / n_steps), c, w["attractor"], w["segments"], w["x0"], w["v0"],
+                           want_traj=True)
+    got = ball_sim.rollout_history(n_steps / 1000, n_steps, scene, w["x0"], w["v0"], w["attractor"], w["constants"], opts)
+    assert np.array_equal(got["hit"], ref["hit"]), "hit flags"
+    assert np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]]), "collision segment indices"
+    assert got["records_seen"] == int(ref["hit"].sum())
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    assert_bitexact(got["v_T"], ref["v_T"], "v_T")
+    # clip bits of every log word = |v| < 1 at the START of the step
+    v_start = np.concatenate([w["v0"][None], ref["traj_v"][:-1]], axis=0)
+    inside = (v_start > -1.0) & (v_start < 1.0)
+    assert np.array_equal((got["hitlog"] >> 29) & 1, inside[..., 0].astype(np.int32)), "clip bit x"
+    assert np.array_equal((got["hitlog"] >> 30) & 1, inside[..., 1].astype(np.int32)), "clip bit y"
+    Kc = K or 32
+    x_start = np.concatenate([w["x0"][None], ref["traj_x"][:-1]], axis=0)
+    for k in range(got["checkpoints"].shape[0]):
+        assert_bitexact(got["checkpoints"][k, :, :2], x_start[k * Kc], f"ckpt {k} x")
+        assert_bitexact(got["checkpoints"][k, :, 2:], v_start[k * Kc], f"ckpt {k} v")
+    if ref["hit"].any():
+        tt, bb, sx, sv = _start_states(ref, w)
+        order = {(int(r[5]), int(r[4])): k for k, r in enumerate(got["records"])}
+        ks = np.array([order[(int(t), int(b))] for t, b in zip(tt, bb)])
+        assert_bitexact(got["record_states"][ks, :2], sx, "record positions")
+        assert_bitexact(got["record_states"][ks, 2:], sv, "record velocities")
+
+
+@pytest.mark.parametrize("window", [4, 8, 16])
+def test_pipelined_bouncy_regime_and_gradients(sim, cref, window):
+    """Collisions every few steps (restart after restart, sliding contact): forward bit-exact, the sequential
+    backward on the pipelined kernel's workspace bit-exact against the oracle's adjoint, the default backward
+    within the calibrated bound."""
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=700)
+    consts = dict(w["constants"]); consts["attractor_strength"] = 2000.0
+    n = 400
+    c = onp.make_constants(consts)
+    dt = np.float32((n / 1000) / n)
+    ref = cref.value_and_grad(n, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+    assert ref["hit"].sum() > 3000 and ref["hit"].sum(0).max() > 100
+    opts = _opts(ball_sim, pipe_window=window)
+    got = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], consts, opts)
+    assert np.array_equal(got["hit"], ref["hit"]) and np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]])
+    assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+    assert_bitexact(got["v_T"], ref["v_T"], "v_T")
+    (_, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"],
+                                                        consts, _opts(ball_sim, sequential_backward=True, pipe_window=window))
+    assert_bitexact(vT, ref["v_T"], "v_T")
+    assert_bitexact(gv, ref["grad_v0"], "gradient (sequential backward)")
+
+
+def test_pipelined_outside_grid_nonfinite_and_slow_division_path(sim, cref):
+    """Balls outside the baked grid, non-finite states, and balls at rest / on the attractor (numerators of the
+    fast division are exactly zero: the producer redoes the window with IEEE divisions)."""
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=64)
+    x0, v0 = w["x0"].copy(), w["v0"].copy()
+    x0[:8] += np.float32(40.0)
+    x0[8:12] = np.float32(-3.0e4)
+    x0[12] = np.float32(1.0e20)
+    v0[13] = np.float32(np.inf)
+    x0[14, 0] = np.float32(np.nan)
+    v0[16:24] = (np.array([[-3.0, 2.0]], np.float32) - x0[16:24]) / np.float32(0.25)
+    v0[24:28] = 0.0                                   # at rest: friction numerator exactly 0
+    x0[28] = np.asarray(w["attractor"], np.float32)   # on the attractor: potential numerator exactly 0
+    v0[28] = (0.0, -0.0)
+    n = 300
+    c = onp.make_constants(w["constants"])
+    ref = cref.rollout_fwd(n, np.float32((n / 1000) / n), c, w["attractor"], w["segments"], x0, v0)
+    for window in (4, 8, 16):
+        got = ball_sim.rollout_history(n / 1000, n, w["segments"], x0, v0, w["attractor"], w["constants"],
+                                       _opts(ball_sim, pipe_window=window))
+        assert np.array_equal(got["hit"], ref["hit"])
+        assert np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]])
+        assert_bitexact(got["x_T"], ref["x_T"], "x_T")
+        assert_bitexact(got["v_T"], ref["v_T"], "v_T")
+
+
 @pytest.mark.parametrize("n_balls", [200, 3000])
 def test_baked_bouncy_regime_and_gradients(sim, cref, n_balls):
     """A strong attractor presses balls against obstacles (collisions every few steps, sliding contact)."""
@@ -694,11 +794,11 @@ def test_baked_bouncy_regime_and_gradients(sim, cref, n_balls):
     dt = np.float32((n / 1000) / n)
     ref = cref.value_and_grad(n, dt, c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
     assert ref["hit"].sum() > 3000 and ref["hit"].sum(0).max() > 100
-    got = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], consts)
+    got = ball_sim.rollout_history(n / 1000, n, w["segments"], w["x0"], w["v0"], w["attractor"], consts, _opts(ball_sim, pipelined=False))
     assert np.array_equal(got["hit"], ref["hit"]) and np.array_equal(got["idx"][ref["hit"]], ref["idx"][ref["hit"]])
     assert_bitexact(got["x_T"], ref["x_T"], "x_T")
     (_, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"],
-                                                        consts, _opts(ball_sim, sequential_backward=True))
+                                                        consts, _opts(ball_sim, sequential_backward=True, pipelined=False))
     assert_bitexact(vT, ref["v_T"], "v_T")
     assert_bitexact(gv, ref["grad_v0"], "gradient (sequential backward)")
 

@@ -48,6 +48,9 @@ def time_fwd(opts, reps=10):
 
 
 res["default"] = time_fwd(ball_sim.RolloutOptions())
+for u in (4, 8, 16):
+    if B <= 300_000:
+        res[f"pipe_{u}"] = time_fwd(ball_sim.RolloutOptions(pipe_window=u))
 for g in (1, 2, 4, 8, 16):
     if B * g <= 4_500_000:
         res[f"baked_{g}"] = time_fwd(ball_sim.RolloutOptions(baked_lanes=g))
