@@ -197,6 +197,71 @@ def parity_block(ball_sim, lib, check, ptr, st, desc, sws, bufs, w, scene, opts,
 
 
 # ------------------------------------------------------------------------------------------------
+# the sharded BASELINE workloads (configs[2] and configs[4]) next to the headline line
+# ------------------------------------------------------------------------------------------------
+def measure_sharded(name, world, rank, device, exchange, steps, strong):
+    """Device-timed fwd + loss + bwd (+ the per-step exchange when world > 1) of one rank's contiguous slice of a
+    GLOBALLY seeded batch (results independent of the GPU count): c5 = 1,048,576 balls / 8 = 131,072 per GPU
+    (weak: every GPU runs a full 131,072-ball share), c3 = 65,536 environments with their own maps (strong: the
+    fixed total is split over the ranks).  Returns the per-rank timing; the caller takes the max over ranks."""
+    import ctypes
+
+    import torch
+
+    from doper_b200 import synthetic as syn
+    from doper_b200._abi import check, lib
+    from doper_b200._device import ptr
+    from doper_b200.distributed import ball_shard
+    from doper_b200.sim import ball_sim
+    from doper_b200.sim.jax_geometry import JaxScene
+
+    full = syn.WORKLOADS[name][0]
+    if name == "c5":
+        per_gpu = full // 8
+        total = per_gpu * world
+    else:
+        per_gpu = full // world if strong else full
+        total = per_gpu * world
+    lo, hi = ball_shard(total, rank, world)
+    w = syn.make_workload(name, n_balls=total, lo=lo, hi=hi)
+    B, n_steps = hi - lo, w["n_steps"]
+    scene = JaxScene(w["segments"])
+    opts = ball_sim.RolloutOptions()
+    desc = ball_sim._make_desc(B, scene, w["sim_time"], n_steps, w["attractor"], w["constants"], opts)
+    _, sws = scene.prepared(device, float(desc.consts[0]))
+    x0, v0 = torch.tensor(w["x0"], device=device), torch.tensor(w["v0"], device=device)
+    bufs = ball_sim._Buffers.get(device, desc)
+    o = bufs.out
+    xT, vT = o[4:4 + 2 * B], o[4 + 2 * B:4 + 4 * B]
+    gv, gx, lpb = o[4 + 4 * B:4 + 6 * B], o[4 + 6 * B:4 + 8 * B], o[4 + 8 * B:4 + 9 * B]
+    loss_sum = torch.zeros(1, dtype=torch.float32, device=device)
+    tgt = ball_sim._target2(w["target"])
+    dref = ctypes.byref(desc)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def step():
+        st = torch.cuda.current_stream().cuda_stream
+        check(lib.doper_rollout_fwd(st, dref, ptr(sws), ptr(x0), ptr(v0), ptr(xT), ptr(vT), 0, 0, 0, ptr(bufs.ws)), "fwd")
+        check(lib.doper_l1_loss(st, B, ptr(xT), tgt, ptr(lpb), ptr(loss_sum), ptr(bufs.scratch)), "loss")
+        check(lib.doper_rollout_bwd(st, dref, ptr(sws), ptr(bufs.ws), ptr(bufs.bwd_scratch), ptr(bufs.scratch), 0, ptr(gx), ptr(gv)), "bwd")
+        if world > 1:
+            exchange()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(3)
+        a.record(); step(); b.record()
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    return {"ms": ms, "B": B, "n_steps": n_steps, "S": int(w["segments"].shape[-3]), "per_env": bool(w["per_env"]),
+            "fwd_kernel": lib.doper_rollout_plan_name(dref, 0).decode(), "bwd_kernel": lib.doper_rollout_plan_name(dref, 1).decode(),
+            "finite": bool(torch.isfinite(gv).all().item())}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def ours(args):
@@ -429,6 +494,27 @@ def ours(args):
         peer.check()
         exch_check = {"vectors": 20, "max_rel_diff_vs_nccl": worst, "bit_identical_across_ranks": bool(bits_equal),
                       "what": "doper_allreduce_oneshot vs torch.distributed.all_reduce (NCCL) on the same random vectors"}
+    # ---- the sharded BASELINE workloads on the same ranks (configs[4] weak, configs[2] strong) -------
+    sharded = None
+    if args.sharded or (world > 1 and not args.no_sharded and name == "c2" and not args.balls and not args.sim_steps):
+        sharded = {}
+        for wl, strong in (("c5", False), ("c3", True)):
+            barrier()
+            r = measure_sharded(wl, world, rank, device, exchange, steps=5, strong=strong)
+            t = torch.tensor([r["ms"]], dtype=torch.float64, device=device)
+            ok = torch.tensor([1.0 if r["finite"] else 0.0], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            tot_b = r["B"] * world
+            sharded[wl] = {
+                "workload": workload_label(wl, r["B"], r["S"], r["n_steps"], r["per_env"]) + f" per GPU, {tot_b} in total",
+                "scaling": "strong (65,536 environments split over the ranks)" if strong else "weak (131,072 balls per GPU = 1,048,576 / 8)",
+                "n_gpus": world, "steps": 5, "warmup": 3, "ms_per_step": round(float(t.item()), 4),
+                "value": round(tot_b * r["n_steps"] / (float(t.item()) * 1e-3), 1), "unit": UNIT,
+                "forward_kernel": r["fwd_kernel"], "backward_kernel": r["bwd_kernel"], "gradients_finite": bool(ok.item() > 0.5),
+                "timing": "CUDA events around fwd + loss + bwd" + (" + exchange" if world > 1 else "") + ", L2 flushed between steps, max over ranks",
+            }
     barrier()
     # ---- roofline of the dominant kernel -----------------------------------------------------
     roof = None
@@ -554,6 +640,8 @@ def ours(args):
             line["parity"] = parity
         if exch_check:
             line["exchange_self_check"] = exch_check
+        if sharded:
+            line["sharded_workloads"] = sharded
         print(json.dumps(line), flush=True)
     if world > 1:
         if peer is not None:
@@ -616,6 +704,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the timed steps eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) parity block")
+    ap.add_argument("--sharded", action="store_true",
+                    help="also time one rank's slice of the sharded BASELINE workloads (c5 weak, c3 strong); default when N > 1")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded workloads block")
     args = ap.parse_args()
     if args.impl == "reference":
         reference(args)

@@ -53,12 +53,12 @@ def build(force: bool = False, verbose: bool = False, policy: int | None = None,
     stamp = STAMP if policy is None else OUT_DIR / f"build_p{int(policy)}.stamp"
     dig = _digest(extra)
     if lib.exists() and stamp.exists() and stamp.read_text() == dig and not force:
-        return lib
+        return lib if wait else (lambda: lib)
     cmd = ["nvcc", *NVCC_FLAGS, *extra, "-o", str(lib), str(CSRC / "kernels.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
-    if not wait:  # caller overlaps several builds: returns (process, finish)
+    if not wait:  # caller overlaps several builds: returns a function that waits for this one
         proc = subprocess.Popen(cmd)
 
         def finish():
@@ -72,5 +72,20 @@ def build(force: bool = False, verbose: bool = False, policy: int | None = None,
     return lib
 
 
+# the non-default contraction mask that is built next to the product library, to show (tests/test_fp_policy_gpu.py)
+# that switching the policy is a flag on both sides: POS | LERP | DOT | FORCE
+ALT_POLICY = 1 | 4 | 8 | 32
+
+
+def build_all(force: bool = False):
+    """The product library and the alternative-policy build, compiled concurrently."""
+    alt = build(force=force, policy=ALT_POLICY, wait=False)
+    lib = build(force=force)
+    return lib, alt()
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--all" in sys.argv:
+        print(build_all(force="--force" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -35,20 +35,30 @@
 
 namespace doper {
 
-constexpr int kPipeGroups = 2;  // (1 producer + CW consumer warps) groups per block: they share the staged scene
-constexpr int kPipeBalls = 16;  // balls per group
+// Debug build only (-DDOPER_PIPE_TIMERS, tools/pipe_timers.py): clock64() totals per phase of lane 0 of every warp,
+// added into the buffer passed as traj_a (the launcher then ignores the trajectory pointers).
+#ifdef DOPER_PIPE_TIMERS
+#define PIPE_T0() long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_last = clock64()
+#define PIPE_MARK(ph) { const long long pt_now = clock64(); pt_acc[ph] += pt_now - pt_last; pt_last = pt_now; }
+#define PIPE_FLUSH(base) if (lane == 0 && p.traj_a) { unsigned long long* pt_d = reinterpret_cast<unsigned long long*>(p.traj_a); \
+    for (int pt_i = 0; pt_i < 8; ++pt_i) atomicAdd(pt_d + (base) + pt_i, (unsigned long long)pt_acc[pt_i]); }
+#else
+#define PIPE_T0()
+#define PIPE_MARK(ph)
+#define PIPE_FLUSH(base)
+#endif
+
+constexpr int kPipeBalls = 16;  // balls per group (= per producer warp)
 
 template <int U>
 struct PipeShared {  // one per group
     float4 slot[2][U + 1][kPipeBalls];  // [window parity][0: window start, j: after the window's step j - 1][ball] = (x, vx, y, vy)
     int t_start[2][kPipeBalls];         // first step of the window
     int epoch_w[2][kPipeBalls];         // restart epoch the window was integrated in
-    float4 mail_state[2][kPipeBalls];   // restart state (x, vx, y, vy) posted by the consumer while it read window parity p
+    float4 mail_state[2][kPipeBalls];   // restart state (x, vx, y, vy) posted by a consumer while it read window parity p
     int mail_t[2][kPipeBalls];
     int mail_epoch[2][kPipeBalls];
-    int first_hit[4][kPipeBalls];       // per consumer warp: the ball's first collided step among that warp's steps (U: none)
-    int done_at;                        // the consumers' last window + 1
-    int pad[3];
+    int fin_at[16];                     // per consumer warp: the barrier index from which on its balls are all final (0: not yet)
 };
 
 __device__ __forceinline__ void named_barrier(int id, int threads) {
@@ -56,35 +66,33 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// U: window length (steps integrated between two hand-overs); CW: consumer warps per producer warp.
-// A consumer lane checks SPL = U / (2 CW) consecutive steps of one ball.
-template <int U, int CW>
-__global__ void __launch_bounds__(32 * (1 + CW) * kPipeGroups) rollout_fwd_pipe_kernel(const FwdParams p) {
+// U: window length = steps the producer integrates between two hand-overs.  Warps per group: 1 producer + U / 2
+// consumers; a consumer warp owns 32 / U balls and gives every (ball, step of the window) its own lane, so that the
+// consumers' latency per window does not grow with U while the producer's does: U = 16 balances the two.
+template <int U>
+__global__ void __launch_bounds__(32 * (1 + U / 2)) rollout_fwd_pipe_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    static_assert(U % (2 * CW) == 0 && CW >= 1 && CW <= 4, "every consumer lane gets a whole number of steps");
-    constexpr int SPL = U / (2 * CW);        // steps per consumer lane
-    constexpr int GW = 1 + CW;               // warps per group
-    constexpr int GT = 32 * GW;              // threads per group
+    static_assert(U == 8 || U == 16 || U == 32, "window length");
+    constexpr int CW = U / 2;          // consumer warps
+    constexpr int GT = 32 * (1 + CW);  // threads per group = per block
+    constexpr unsigned kSeg = U == 32 ? 0xffffffffu : ((1u << U) - 1u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int group = warp / GW, role = warp % GW;  // role 0: producer; 1..CW: consumer role - 1
+    const bool producer = warp == 0;
     const SceneLayout L = scene_layout(1, p.S);
     const uint32_t scene_bytes = (uint32_t)L.S_pad * 20;
     const uint32_t bbytes = (uint32_t)(bake_bytes(L.S_pad) - sizeof(BakeHeader));
     unsigned char* sbake = smem + scene_bytes;  // 16-byte aligned: S_pad is a multiple of 32
     uint64_t* bar = reinterpret_cast<uint64_t*>(sbake + bbytes);
-    PipeShared<U>& sh = reinterpret_cast<PipeShared<U>*>(sbake + bbytes + 16)[group];
+    PipeShared<U>& sh = *reinterpret_cast<PipeShared<U>*>(sbake + bbytes + 16);
 
-    const int64_t first = ((int64_t)blockIdx.x * kPipeGroups + group) * kPipeBalls;
-    const int b = lane >> 1;  // ball of this lane within the group (both roles)
-    const int64_t ball = first + b;
-    const bool active = ball < p.B;
+    const int64_t first = (int64_t)blockIdx.x * kPipeBalls;
     const int n = p.n_steps;
     const Consts c = p.c;
 
     if (tid == 0) mbar_init(bar, 1);
-    if (role == 1 && lane < kPipeBalls) {
-        sh.mail_epoch[0][lane] = 0; sh.mail_epoch[1][lane] = 0;
-        if (lane == 0) sh.done_at = -1;
+    if (tid < kPipeBalls) {
+        sh.mail_epoch[0][tid] = 0; sh.mail_epoch[1][tid] = 0;
+        sh.fin_at[tid] = 0;
     }
     __syncthreads();
     if (tid == 0) {  // scene + baked lists -> shared memory (1-D TMA bulk copies); only the consumers wait for them
@@ -97,12 +105,20 @@ __global__ void __launch_bounds__(32 * (1 + CW) * kPipeGroups) rollout_fwd_pipe_
         for (uint32_t o = 0; o < rb; o += kTmaChunk) tma_load_1d(smem + qb + o, gr + o, min(kTmaChunk, rb - o), bar);
         for (uint32_t o = 0; o < bbytes; o += kTmaChunk) tma_load_1d(sbake + o, gb + o, min(kTmaChunk, bbytes - o), bar);
     }
-    if (first >= p.B) return;  // a group without balls (last block): all its warps leave together
-    const int bar_all = 1 + 2 * group, bar_cons = 2 + 2 * group;
 
-    if (role == 0) {
+    // every warp leaves after the first barrier B_j at which all consumer warps had declared their balls final
+    auto group_done = [&](int j) {
+        bool all = true;
+#pragma unroll
+        for (int w = 0; w < CW; ++w) { const int f = sh.fin_at[w]; all = all && f != 0 && f <= j; }
+        return all;
+    };
+
+    if (producer) {
         // ---------------------------------------------------------------------------------- producer
-        const int axis = lane & 1;
+        const int b = lane >> 1, axis = lane & 1;
+        const int64_t ball = first + b;
+        const bool active = ball < p.B;
         const float att = axis ? c.ay : c.ax;
         float pos = 0.0f, vel = 0.0f;
         if (active) {
@@ -110,10 +126,11 @@ __global__ void __launch_bounds__(32 * (1 + CW) * kPipeGroups) rollout_fwd_pipe_
             pos = axis ? xx.y : xx.x; vel = axis ? vv.y : vv.x;
         }
         int t = active ? 0 : n, epoch = 0;
+        PIPE_T0();
         for (int k = 0;; ++k) {
             const int buf = k & 1;
             const int me = sh.mail_epoch[buf][b];
-            if (me > epoch) {  // the consumers resolved a collision of this ball two windows ago: restart after it
+            if (me > epoch) {  // a consumer resolved a collision of this ball two windows ago: restart after it
                 const float4 s = sh.mail_state[buf][b];
                 pos = axis ? s.z : s.x; vel = axis ? s.w : s.y;
                 t = sh.mail_t[buf][b];
@@ -124,6 +141,7 @@ __global__ void __launch_bounds__(32 * (1 + CW) * kPipeGroups) rollout_fwd_pipe_
             constexpr int kSlotStride = kPipeBalls * 2;  // float2 per slot
             const float p0 = pos, v0 = vel;
             out[0] = make_float2(pos, vel);
+            PIPE_MARK(0);
             if (t < n) {
                 float nmin = __int_as_float(0x7f800000), nmax = 0.0f;
 #pragma unroll
@@ -141,14 +159,26 @@ __global__ void __launch_bounds__(32 * (1 + CW) * kPipeGroups) rollout_fwd_pipe_
                 }
                 t = min(t + U, n);
             }
-            named_barrier(bar_all, GT);  // B_k: window k is complete, the consumers have finished window k - 1
-            if (sh.done_at == k) break;
+            PIPE_MARK(1);
+            named_barrier(1, GT);  // B_k: window k is complete, the consumers have finished window k - 1
+            const bool done = group_done(k);
+            PIPE_MARK(2);
+#ifdef DOPER_PIPE_TIMERS
+            pt_acc[7] += 1;
+#endif
+            if (done) break;
         }
+        PIPE_FLUSH(0);
         return;
     }
 
     // -------------------------------------------------------------------------------------- consumers
-    const int cw = role - 1;
+    const int cw = warp - 1;
+    constexpr int BPW = 32 / U;                  // balls per consumer warp
+    const int bl = lane / U, j = lane % U;       // my ball within the warp, my step within the window
+    const int b = cw * BPW + bl;                 // my ball within the group
+    const int64_t ball = first + b;
+    const bool active = ball < p.B;
     SceneView sc;
     BakeView bk;
     {
@@ -165,83 +195,114 @@ __global__ void __launch_bounds__(32 * (1 + CW) * kPipeGroups) rollout_fwd_pipe_
         bk.ok = bh.enabled && !sc.weird && c.r <= bh.r_max;
     }
     mbar_wait(bar, 0);
-    const int j0 = (cw * 2 + (lane & 1)) * SPL;  // my first step within the window
     const int K = p.K;
     const int kshift = (K > 0 && (K & (K - 1)) == 0) ? (31 - __clz(K)) : -1;
     int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
-    int committed = active ? 0 : n;  // steps of this ball that are final (the same value in every lane of the ball)
+    int committed = active ? 0 : n;  // steps of my ball that are final (the same value in every lane of the ball)
     int epoch = 0;
     bool finished = false;
+    PIPE_T0();
     for (int k = 0;; ++k) {
-        named_barrier(bar_all, GT);  // B_k
-        if (finished) break;
+        named_barrier(1, GT);  // B_k
+        const bool done = group_done(k);
+        PIPE_MARK(0);
+        if (done) break;
         const int buf = k & 1;
+#if defined(DOPER_PIPE_ABLATE) && DOPER_PIPE_ABLATE == 0
+        if (k >= (n + U - 1) / U) { finished = true; if (lane == 0) sh.fin_at[cw] = k + 1; }  // timing experiment: barriers only
+        continue;
+#endif
         const int ts0 = sh.t_start[buf][b];
         const bool fresh = committed < n && sh.epoch_w[buf][b] == epoch;  // else: integrated from a superseded state
         const int nv = fresh ? min(U, n - ts0) : 0;                       // steps of the window that exist
-        float4 st[SPL + 1];  // st[i]: state at the start of my step i (= after the step before), (x, vx, y, vy)
-#pragma unroll
-        for (int i = 0; i <= SPL; ++i) st[i] = sh.slot[buf][j0 + i][b];
-        // (1) my candidates against the baked lists, in step order; my first collision
-        int myf = U, myidx = 0, mine = 0;
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-            if (j0 + i < nv && myf == U) {
-                int idx;
-                if (baked_hit(sc, bk, st[i + 1].x, st[i + 1].z, c.r, idx)) { myf = j0 + i; myidx = idx; mine = i; }
-            }
-        }
-        // (2) the ball's first collision in the window: over the two lanes of the ball in this warp, then over the warps
-        const int wf = min(myf, __shfl_xor_sync(0xffffffffu, myf, 1));
-        int f = wf;
-        if (CW > 1) {
-            if ((lane & 1) == 0) sh.first_hit[cw][b] = wf;
-            named_barrier(bar_cons, 32 * CW);
-#pragma unroll
-            for (int w = 0; w < CW; ++w) f = min(f, sh.first_hit[w][b]);
-        }
+        const float4 s = sh.slot[buf][j][b], cand = sh.slot[buf][j + 1][b];  // start state and candidate of my step
+        // (1) my candidate against the baked lists
+        int idx = 0, k0 = 0, k1 = 0;
+        const int kind = j < nv ? baked_cell(bk, cand.x, cand.z, k0, k1) : 0;
+        PIPE_MARK(1);
+        bool myhit = false;
+#if defined(DOPER_PIPE_ABLATE) && DOPER_PIPE_ABLATE == 1
+        if (kind == 77) myhit = true;  // timing experiment: no narrow phase
+#else
+        if (kind != 0) myhit = baked_list_hit(sc, bk, cand.x, cand.z, c.r, kind, k0, k1, idx);
+#endif
+#ifdef DOPER_PIPE_TIMERS
+        __syncwarp();
+        { const long long pt_now = clock64(); const long long d = pt_now - pt_last; pt_acc[4] += d; pt_last = pt_now;
+          if (__any_sync(0xffffffffu, kind != 0)) pt_acc[5] += 1;
+          if (d > 1000) pt_acc[6] += 1; }
+#endif
+        // (2) the ball's first collision in the window
+        const unsigned hm = (__ballot_sync(0xffffffffu, myhit) >> (bl * U)) & kSeg;
+        const int f = hm ? (__ffs(hm) - 1) : U;
         const bool hit = f < nv;
         const int n_commit = hit ? f + 1 : nv;
-        const bool owner = hit && myf == f;  // the lane that checked step f resolves and logs it
         State r;
         r.x = r.y = r.vx = r.vy = r.ax = r.ay = 0.0f;
-        int payload = 0;
-        if (owner) {
-            float4 s = st[0];
-#pragma unroll
-            for (int i = 1; i < SPL; ++i)
-                if (mine == i) s = st[i];
+        int payload = 0, extra = 0;
+        if (hit && j == f) {  // my step: resolve it, post the state after it
             State s1;
             free_step(s.x, s.z, s.y, s.w, c, s1);  // the candidate again, with its acceleration (resolve needs it)
-            r = resolve(s.x, s.z, s.y, s.w, s1, sc.q[myidx], c);
-            payload = record_collision(p.sink, ball, ts0 + f, s.x, s.z, s.y, s.w, myidx);
-            sh.mail_state[buf][b] = make_float4(r.x, r.vx, r.y, r.vy);
-            sh.mail_t[buf][b] = ts0 + f + 1;
+            payload = record_collision(p.sink, ball, ts0 + f, s.x, s.z, s.y, s.w, idx);  // first: the atomic's round trip overlaps the resolve
+            r = resolve(s.x, s.z, s.y, s.w, s1, sc.q[idx], c);
+            // Contact mode: while the very next step collides again (resting / sliding contact, a bounce in a corner),
+            // this lane steps the ball itself — a restart through the producer costs ~1.5 windows per collision.  At
+            // most U steps per window, so that the other balls of the group keep moving.
+            State cur = r;
+            int tn = ts0 + f + 1;
+            while (extra < U && tn < n) {
+                State c1;
+                free_step(cur.x, cur.y, cur.vx, cur.vy, c, c1);
+                int i2;
+                if (!baked_hit(sc, bk, c1.x, c1.y, c.r, i2)) break;  // free flight again: the producer takes over from `cur`
+                const int pl = record_collision(p.sink, ball, tn, cur.x, cur.y, cur.vx, cur.vy, i2);
+                const State r2 = resolve(cur.x, cur.y, cur.vx, cur.vy, c1, sc.q[i2], c);
+                if (hl) hl[(int64_t)tn * p.hl_st] = pack_log(pl, true, clip_bits(cur.vx, cur.vy));
+                if (p.ckpt) {
+                    const bool at = kshift >= 0 ? (tn & (K - 1)) == 0 : (tn % K) == 0;
+                    if (at) p.ckpt[(size_t)(kshift >= 0 ? tn >> kshift : tn / K) * p.B + ball] = make_float4(cur.x, cur.y, cur.vx, cur.vy);
+                }
+                cur = r2;
+                ++tn; ++extra;
+            }
+            if (extra > 0 && tn == n) { p.xT[ball] = make_float2(cur.x, cur.y); p.vT[ball] = make_float2(cur.vx, cur.vy); }
+            sh.mail_state[buf][b] = make_float4(cur.x, cur.vx, cur.y, cur.vy);
+            sh.mail_t[buf][b] = tn;
             sh.mail_epoch[buf][b] = epoch + 1;
         }
-        // (3) commit my steps before the collision, and the collided one
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-            const int j = j0 + i;
-            if (j < n_commit) {
-                const int ts = ts0 + j;
-                const bool h = hit && j == f;
-                if (hl) hl[(int64_t)ts * p.hl_st] = pack_log(h ? payload : 0, h, clip_bits(st[i].y, st[i].w));
-                if (p.ckpt) {
-                    const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
-                    if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(st[i].x, st[i].z, st[i].y, st[i].w);
-                }
-                if (ts + 1 == n) {  // the rollout's last step: final state
-                    if (h) { p.xT[ball] = make_float2(r.x, r.y); p.vT[ball] = make_float2(r.vx, r.vy); }
-                    else { p.xT[ball] = make_float2(st[i + 1].x, st[i + 1].z); p.vT[ball] = make_float2(st[i + 1].y, st[i + 1].w); }
-                }
+        extra = __shfl_sync(0xffffffffu, extra, bl * U + (hit ? f : 0));  // steps the contact loop committed for my ball
+        if (!hit) extra = 0;
+        PIPE_MARK(2);
+        // (3) commit my step if it lies before the collision or is the collided one
+#if defined(DOPER_PIPE_ABLATE) && DOPER_PIPE_ABLATE <= 2
+        if (j < n_commit && ts0 + j + 1 == n) {  // timing experiment: no log / checkpoint stores
+#else
+        if (j < n_commit) {
+#endif
+            const int ts = ts0 + j;
+            const bool h = hit && j == f;
+            if (hl) hl[(int64_t)ts * p.hl_st] = pack_log(h ? payload : 0, h, clip_bits(s.y, s.w));
+            if (p.ckpt) {
+                const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
+                if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(s.x, s.z, s.y, s.w);
+            }
+            if (ts + 1 == n) {  // the rollout's last step: final state
+                if (h) { p.xT[ball] = make_float2(r.x, r.y); p.vT[ball] = make_float2(r.vx, r.vy); }
+                else { p.xT[ball] = make_float2(cand.x, cand.z); p.vT[ball] = make_float2(cand.y, cand.w); }
             }
         }
-        if (fresh) committed = ts0 + n_commit;
+        if (fresh) committed = ts0 + n_commit + extra;
         if (hit) ++epoch;
-        finished = __all_sync(0xffffffffu, committed >= n);
-        if (finished && cw == 0 && lane == 0) sh.done_at = k + 1;
+        if (!finished) {
+            finished = __all_sync(0xffffffffu, committed >= n);
+            if (finished && lane == 0) sh.fin_at[cw] = k + 1;
+        }
+        PIPE_MARK(3);
+#ifdef DOPER_PIPE_TIMERS
+        pt_acc[7] += 1;
+#endif
     }
+    PIPE_FLUSH(8);
 }
 
 }  // namespace doper

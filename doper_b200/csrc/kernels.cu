@@ -163,19 +163,19 @@ bool baked_staged(const doper_rollout_desc* d) {
 
 // Pipelined kernel (fwd_pipe.cuh: producer / consumer warp pairs over the baked lists): the default of shared
 // scenes that fit shared memory up to kPipeMaxBalls balls (beyond, one thread per ball fills the machine and
-// executes fewer instructions per ball-step).  flags bit 22 forbids it; bit 23 with lanes_per_ball = 4, 8 or 16
+// executes fewer instructions per ball-step).  flags bit 22 forbids it; bit 23 with lanes_per_ball = 8, 16 or 32
 // pins it with that window length.
-constexpr int64_t kPipeMaxBalls = 16384;
+constexpr int64_t kPipeMaxBalls = 6144;
 bool pipe_pinned(const doper_rollout_desc* d) {
     return !d->per_env && (d->flags & (1 << 23)) && !(d->flags & kBakedOffBits) &&
-           (d->lanes_per_ball == 4 || d->lanes_per_ball == 8 || d->lanes_per_ball == 16);
+           (d->lanes_per_ball == 8 || d->lanes_per_ball == 16 || d->lanes_per_ball == 32);
 }
 bool use_pipe(const doper_rollout_desc* d) {
     if (d->per_env || d->n_steps < 1 || !baked_staged(d)) return false;
     if (pipe_pinned(d)) return true;
     return d->lanes_per_ball == 0 && !(d->flags & (kBakedOffBits | (1 << 21) | (1 << 22) | (1 << 23))) && d->B <= kPipeMaxBalls;
 }
-int pipe_window(const doper_rollout_desc* d) { return pipe_pinned(d) ? d->lanes_per_ball : 8; }
+int pipe_window(const doper_rollout_desc* d) { return pipe_pinned(d) ? d->lanes_per_ball : 16; }
 
 bool use_baked(const doper_rollout_desc* d) {
     if (use_pipe(d)) return true;  // same lists; the lane = step kernel serves the calls the pipelined one does not (trajectory output)
@@ -368,16 +368,15 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
     return staged ? go(rollout_fwd_baked_kernel<G, true, THREADS>) : go(rollout_fwd_baked_kernel<G, false, THREADS>);
 }
 
-template <int U, int CW>
+template <int U>
 int launch_fwd_pipe(cudaStream_t st, const FwdParams& p) {
     const int S_pad = scene_layout(1, p.S).S_pad;
-    const size_t smem = (size_t)S_pad * 20 + (bake_bytes(S_pad) - sizeof(BakeHeader)) + 16 + kPipeGroups * sizeof(PipeShared<U>);
+    const size_t smem = (size_t)S_pad * 20 + (bake_bytes(S_pad) - sizeof(BakeHeader)) + 16 + sizeof(PipeShared<U>);
     if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(rollout_fwd_pipe_kernel<U, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        cudaFuncSetAttribute(rollout_fwd_pipe_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DOPER_ERR_SMEM_LIMIT;
-    const int bpb = kPipeGroups * kPipeBalls;
-    const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
-    rollout_fwd_pipe_kernel<U, CW><<<grid, 32 * (1 + CW) * kPipeGroups, smem, st>>>(p);
+    const unsigned grid = (unsigned)((p.B + kPipeBalls - 1) / kPipeBalls);
+    rollout_fwd_pipe_kernel<U><<<grid, 32 * (1 + U / 2), smem, st>>>(p);
     return launch_status();
 }
 
@@ -551,7 +550,7 @@ const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backwar
     if (backward) return (d->flags & 2) ? "rollout_bwd_kernel" : "rollout_bwd_jacobian_kernel+rollout_bwd_fold_kernel";
     if (use_pipe(d)) {
         const int u = pipe_window(d);
-        return u == 4 ? "rollout_fwd_pipe_kernel<4>" : (u == 16 ? "rollout_fwd_pipe_kernel<16>" : "rollout_fwd_pipe_kernel<8>");
+        return u == 8 ? "rollout_fwd_pipe_kernel<8>" : (u == 32 ? "rollout_fwd_pipe_kernel<32>" : "rollout_fwd_pipe_kernel<16>");
     }
     if (use_baked(d)) {
         static const char* const baked[] = {"rollout_fwd_baked_kernel<1>", "rollout_fwd_baked_kernel<2>", "rollout_fwd_baked_kernel<4>",
@@ -625,11 +624,15 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         p.sink.cap = (int)w.cap;
         if (cudaMemsetAsync(base, 0, 256, st) != cudaSuccess) return DOPER_ERR_LAUNCH;  // record counter
     }
+#ifdef DOPER_PIPE_TIMERS
+    if (use_pipe(d)) {
+#else
     if (use_pipe(d) && !traj_x && !traj_v && !traj_a) {
+#endif
         switch (pipe_window(d)) {
-            case 4: return launch_fwd_pipe<4, 2>(st, p);
-            case 16: return launch_fwd_pipe<16, 4>(st, p);
-            default: return launch_fwd_pipe<8, 4>(st, p);
+            case 8: return launch_fwd_pipe<8>(st, p);
+            case 32: return launch_fwd_pipe<32>(st, p);
+            default: return launch_fwd_pipe<16>(st, p);
         }
     }
     if (use_baked(d)) {

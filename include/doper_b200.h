@@ -172,8 +172,8 @@ typedef struct {
                                bit 20: keep the per-ball candidate-list kernels for a shared scene
                                       (default there: the baked per-cell lists of doper_scene_prepare);
                                bit 22: forbid the pipelined forward kernel (producer / consumer warp pairs over
-                                      the baked lists: the default of shared scenes up to 16,384 balls);
-                               bit 23: with lanes_per_ball = 4, 8 or 16: the pipelined kernel with that window
+                                      the baked lists: the default of shared scenes up to 6,144 balls);
+                               bit 23: with lanes_per_ball = 8, 16 or 32: the pipelined kernel with that window
                                       length (speculated steps per producer / consumer hand-over);
                                bit 19: no collision records (the backward replays every collided
                                       step from its checkpoint: slower, same results);

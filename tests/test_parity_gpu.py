@@ -693,7 +693,7 @@ def _start_states(ref, w):
     return tt, bb, sx, sv
 
 
-@pytest.mark.parametrize("window", [0, 4, 8, 16])  # 0 = the default plan
+@pytest.mark.parametrize("window", [0, 8, 16, 32])  # 0 = the default plan
 @pytest.mark.parametrize("n_balls,n_steps,K", [(1, 1, 0), (1, 64, 16), (15, 7, 4), (16, 300, 16), (333, 301, 16), (3000, 150, 7),
                                                 (4096, 500, 32)])
 def test_pipelined_forward_bitexact(sim, cref, n_balls, n_steps, K, window):
@@ -704,7 +704,7 @@ def test_pipelined_forward_bitexact(sim, cref, n_balls, n_steps, K, window):
     w = syn.make_workload("c2", n_balls=n_balls)
     scene = geo.JaxScene(w["segments"])
     opts = _opts(ball_sim, ckpt_every=K, pipe_window=window)
-    assert _plan(ball_sim, n_balls, scene, n_steps, w, opts) == f"rollout_fwd_pipe_kernel<{window or 8}>"
+    assert _plan(ball_sim, n_balls, scene, n_steps, w, opts) == f"rollout_fwd_pipe_kernel<{window or 16}>"
     c = onp.make_constants(w["constants"])
     ref = cref.rollout_fwd(n_steps, np.float32((n_steps / 1000) / n_steps), c, w["attractor"], w["segments"], w["x0"], w["v0"],
                            want_traj=True)
@@ -732,7 +732,7 @@ def test_pipelined_forward_bitexact(sim, cref, n_balls, n_steps, K, window):
         assert_bitexact(got["record_states"][ks, 2:], sv, "record velocities")
 
 
-@pytest.mark.parametrize("window", [4, 8, 16])
+@pytest.mark.parametrize("window", [8, 16, 32])
 def test_pipelined_bouncy_regime_and_gradients(sim, cref, window):
     """Collisions every few steps (restart after restart, sliding contact): forward bit-exact, the sequential
     backward on the pipelined kernel's workspace bit-exact against the oracle's adjoint, the default backward
@@ -774,7 +774,7 @@ def test_pipelined_outside_grid_nonfinite_and_slow_division_path(sim, cref):
     n = 300
     c = onp.make_constants(w["constants"])
     ref = cref.rollout_fwd(n, np.float32((n / 1000) / n), c, w["attractor"], w["segments"], x0, v0)
-    for window in (4, 8, 16):
+    for window in (8, 16, 32):
         got = ball_sim.rollout_history(n / 1000, n, w["segments"], x0, v0, w["attractor"], w["constants"],
                                        _opts(ball_sim, pipe_window=window))
         assert np.array_equal(got["hit"], ref["hit"])

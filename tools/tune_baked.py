@@ -48,7 +48,7 @@ def time_fwd(opts, reps=10):
 
 
 res["default"] = time_fwd(ball_sim.RolloutOptions())
-for u in (4, 8, 16):
+for u in (8, 16, 32):
     if B <= 300_000:
         res[f"pipe_{u}"] = time_fwd(ball_sim.RolloutOptions(pipe_window=u))
 for g in (1, 2, 4, 8, 16):
