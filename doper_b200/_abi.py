@@ -15,7 +15,7 @@ import os
 # DOPER_B200_LIB points the binding at another build of the same library (kernel A/B tuning)
 LIB_PATH = Path(os.environ.get("DOPER_B200_LIB") or (Path(__file__).resolve().parent / "_lib" / "libdoper_b200.so"))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "doper_abi_version", "doper_fp_policy", "doper_error_string", "doper_scene_workspace_bytes", "doper_scene_prepare",
@@ -24,6 +24,8 @@ EXPORTS = (
     "doper_rollout_fwd", "doper_rollout_bwd", "doper_l1_loss", "doper_value_and_grad",
     "doper_fp32_probe",
     "doper_ray_segment_points", "doper_range_sensor", "doper_agent_observations",
+    "doper_closest_segment_env", "doper_points_inside_env", "doper_range_sensor_env", "doper_range_sensor_f64",
+    "doper_agent_observations_env",
     "doper_peer_buffer_bytes", "doper_peer_alloc", "doper_peer_open", "doper_peer_close", "doper_peer_free",
     "doper_allreduce_oneshot",
 )
@@ -76,6 +78,8 @@ def _load() -> ctypes.CDLL:
     lib.doper_scene_prepare.argtypes = [vp, c_int64, c_int32, fp, c_float, vp]
     lib.doper_closest_segment.argtypes = [vp, c_int64, c_int32, fp, fp, vp, vp, fp, fp]
     lib.doper_points_inside.argtypes = [vp, c_int64, c_int32, fp, fp, vp]
+    lib.doper_closest_segment_env.argtypes = lib.doper_closest_segment.argtypes
+    lib.doper_points_inside_env.argtypes = lib.doper_points_inside.argtypes
     lib.doper_rollout_ckpt_every.restype = c_int32
     lib.doper_rollout_ckpt_every.argtypes = [POINTER(RolloutDesc)]
     lib.doper_rollout_log_ball_major.restype = c_int32
@@ -96,6 +100,9 @@ def _load() -> ctypes.CDLL:
     lib.doper_range_sensor.argtypes = [vp, c_int64, c_int32, c_int32, fp, fp, vp, c_float, fp, fp, vp]
     lib.doper_agent_observations.argtypes = [vp, c_int64, c_int32, c_int32, fp, fp, fp, vp, c_float,
                                              POINTER(ctypes.c_double), fp]
+    lib.doper_range_sensor_env.argtypes = lib.doper_range_sensor.argtypes
+    lib.doper_agent_observations_env.argtypes = lib.doper_agent_observations.argtypes
+    lib.doper_range_sensor_f64.argtypes = [vp, c_int64, c_int32, c_int32, c_int32, vp, fp, vp, c_float, vp, fp, vp]
     lib.doper_peer_buffer_bytes.restype = c_size_t
     lib.doper_peer_buffer_bytes.argtypes = [c_int32]
     lib.doper_peer_alloc.argtypes = [c_int32, POINTER(c_void_p), ctypes.c_char_p]

@@ -63,7 +63,10 @@ class SimpleRangeSensor(Sensor):
         return_intersection_points: Optional[bool] = False,
     ) -> Union[onp.ndarray, Tuple[onp.ndarray, onp.ndarray]]:
         """observations.py:29-79 for one position: ranges ``[R]`` or ``(ranges, points [R,2])``."""
-        position = onp.asarray(position, dtype=onp.float32).reshape(1, 2)
+        # observations.py:50 `onp.array(position)`: a float32 array stays float32, anything else (python floats,
+        # float64 arrays: e.g. the sampler's proposals) is float64 and the ranges come out in float64 (:67)
+        position = onp.array(position)
+        position = (position if position.dtype == onp.float32 else position.astype(onp.float64)).reshape(1, 2)
         out = self._batch(position, heading_direction, scene, return_intersection_points)
         if return_intersection_points:
             return out[0][0], out[1][0]

@@ -36,8 +36,6 @@ class RangeSensingAgent:
         ``jax_scene`` attribute (doper/scenes/*), or a scene itself."""
         device = require_cuda()
         scene = _as_scene(getattr(scene_handler, "jax_scene", scene_handler))
-        if scene.per_env:
-            raise ValueError("RangeSensingAgent: per-environment scenes are not supported here")
         _, ws = scene.prepared(device)
         on_device = is_device_tensor(coordinate_init)
         pos = as_f32_device(coordinate_init, device).reshape(-1, 2)
@@ -47,7 +45,10 @@ class RangeSensingAgent:
         N, R, S = int(pos.shape[0]), int(self._dirs.shape[0]), scene.n_segments
         tgt = onp.array(self.config["sim"]["coordinate_target"], dtype=onp.float64).reshape(2)
         obs = torch.empty((N, 7 + R), dtype=torch.float32, device=device)
-        check(lib.doper_agent_observations(stream_ptr(), N, R, S, ptr(pos), ptr(vel), ptr(self._dirs), ptr(ws),
+        if scene.per_env and N != scene.n_scenes:
+            raise ValueError(f"per-environment scenes: {N} agents for {scene.n_scenes} scenes")
+        fn = lib.doper_agent_observations_env if scene.per_env else lib.doper_agent_observations  # ball i looks at scene i
+        check(fn(stream_ptr(), N, R, S, ptr(pos), ptr(vel), ptr(self._dirs), ptr(ws),
                                            float(self.config["sim"]["agent_params"]["distance_range"]),
                                            (ctypes.c_double * 2)(tgt[0], tgt[1]), ptr(obs)),
               "doper_agent_observations")

@@ -381,39 +381,61 @@ int launch_fwd_pipe(cudaStream_t st, const FwdParams& p) {
 }
 
 template <int G>
-int launch_closest(cudaStream_t st, int64_t N, int S, const float* pts, const float* segs, const void* ws,
-                   int32_t* idx, float* dist, float* seg_out, size_t smem) {
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(closest_segment_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem) != cudaSuccess)
-        return DOPER_ERR_SMEM_LIMIT;
+int launch_closest(cudaStream_t st, int64_t N, int S, int per_env, const float* pts, const float* segs, const void* ws,
+                   int32_t* idx, float* dist, float* seg_out) {
+    const size_t smem = (size_t)scene_layout(1, S).S_pad * 20 + 16;
+    const bool staged = !per_env && (int)smem <= max_optin_smem();  // else the scene(s) are read in place
     const int ppb = kQueryThreads / G;
     const unsigned grid = (unsigned)((N + ppb - 1) / ppb);
-    closest_segment_kernel<G><<<grid, kQueryThreads, smem, st>>>(
-        N, S, reinterpret_cast<const float2*>(pts), reinterpret_cast<const float4*>(segs),
-        reinterpret_cast<const unsigned char*>(ws), idx, dist, reinterpret_cast<float4*>(seg_out));
+    if (staged) {
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(closest_segment_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return DOPER_ERR_SMEM_LIMIT;
+        closest_segment_kernel<G, true><<<grid, kQueryThreads, smem, st>>>(
+            N, S, 0, reinterpret_cast<const float2*>(pts), reinterpret_cast<const float4*>(segs),
+            reinterpret_cast<const unsigned char*>(ws), idx, dist, reinterpret_cast<float4*>(seg_out));
+    } else {
+        closest_segment_kernel<G, false><<<grid, kQueryThreads, 0, st>>>(
+            N, S, per_env, reinterpret_cast<const float2*>(pts), reinterpret_cast<const float4*>(segs),
+            reinterpret_cast<const unsigned char*>(ws), idx, dist, reinterpret_cast<float4*>(seg_out));
+    }
     return launch_status();
+}
+
+int closest_dispatch(cudaStream_t st, int64_t N, int S, int per_env, const float* points, const float* segments,
+                     const void* scene_ws, int32_t* idx, float* dist, float* seg_out) {
+    int G = 1;
+    while (G < 32 && N * G < 148 * 256) G *= 2;
+    switch (G) {
+        case 1: return launch_closest<1>(st, N, S, per_env, points, segments, scene_ws, idx, dist, seg_out);
+        case 2: return launch_closest<2>(st, N, S, per_env, points, segments, scene_ws, idx, dist, seg_out);
+        case 4: return launch_closest<4>(st, N, S, per_env, points, segments, scene_ws, idx, dist, seg_out);
+        case 8: return launch_closest<8>(st, N, S, per_env, points, segments, scene_ws, idx, dist, seg_out);
+        case 16: return launch_closest<16>(st, N, S, per_env, points, segments, scene_ws, idx, dist, seg_out);
+        default: return launch_closest<32>(st, N, S, per_env, points, segments, scene_ws, idx, dist, seg_out);
+    }
 }
 
 }  // namespace
 
 namespace {
-template <bool OBS>
-int launch_range_sensor(cudaStream_t st, int64_t N, int R, int S, const float* pos, const float* vel,
+template <bool OBS, bool POS64>
+int launch_range_sensor(cudaStream_t st, int64_t N, int R, int S, int per_env, const void* pos, const float* vel,
                         const float* ray_dirs, const void* scene_ws, float distance_range, double tx, double ty,
-                        float* ranges, float* points, int32_t* idx, float* obs) {
+                        void* ranges, float* points, int32_t* idx, float* obs) {
     const size_t smem = (size_t)scene_layout(1, S).S_pad * 20 + 16;
-    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(range_sensor_kernel<OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
-        return DOPER_ERR_SMEM_LIMIT;
+    const bool staged = !per_env && (int)smem <= max_optin_smem();  // else the scene(s) are read in place
     const int64_t n = N * (int64_t)R;
-    range_sensor_kernel<OBS><<<(unsigned)((n + kSensorThreads - 1) / kSensorThreads), kSensorThreads, smem, st>>>(
-        N, R, S, reinterpret_cast<const float2*>(pos), reinterpret_cast<const float2*>(vel),
-        reinterpret_cast<const float2*>(ray_dirs), reinterpret_cast<const unsigned char*>(scene_ws), distance_range,
-        tx, ty, ranges, reinterpret_cast<float2*>(points), idx, obs);
-    return launch_status();
+    const unsigned grid = (unsigned)((n + kSensorThreads - 1) / kSensorThreads);
+    auto go = [&](auto kernel, size_t sm) {
+        if (sm > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+            return (int)DOPER_ERR_SMEM_LIMIT;
+        kernel<<<grid, kSensorThreads, sm, st>>>(N, R, S, per_env, pos, reinterpret_cast<const float2*>(vel),
+                                                 reinterpret_cast<const float2*>(ray_dirs), reinterpret_cast<const unsigned char*>(scene_ws),
+                                                 distance_range, tx, ty, ranges, reinterpret_cast<float2*>(points), idx, obs);
+        return launch_status();
+    };
+    return staged ? go(range_sensor_kernel<OBS, true, POS64>, smem) : go(range_sensor_kernel<OBS, false, POS64>, 0);
 }
 }  // namespace
 
@@ -465,20 +487,19 @@ int doper_closest_segment(doper_stream_t stream, int64_t N, int32_t S, const flo
     if (!aligned(points, 8) || !aligned(segments, 16) || !aligned(scene_ws, 256) ||
         (seg_out && !aligned(seg_out, 16)))
         return DOPER_ERR_MISALIGNED;
-    const SceneLayout L = scene_layout(1, S);
-    const size_t smem = (size_t)L.S_pad * 20 + 16;
-    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
-    int G = 1;
-    while (G < 32 && N * G < 148 * 256) G *= 2;
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (G) {
-        case 1: return launch_closest<1>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
-        case 2: return launch_closest<2>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
-        case 4: return launch_closest<4>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
-        case 8: return launch_closest<8>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
-        case 16: return launch_closest<16>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
-        default: return launch_closest<32>(st, N, S, points, segments, scene_ws, idx, dist, seg_out, smem);
-    }
+    return closest_dispatch((cudaStream_t)stream, N, S, 0, points, segments, scene_ws, idx, dist, seg_out);
+}
+
+int doper_closest_segment_env(doper_stream_t stream, int64_t N, int32_t S, const float* points,
+                              const float* segments, const void* scene_ws, int32_t* idx, float* dist,
+                              float* seg_out) {
+    if (N < 0 || S <= 0 || N > 0x7fffffff) return DOPER_ERR_BAD_SHAPE;
+    if (N == 0) return DOPER_OK;
+    if (!points || !segments || !scene_ws || !idx || !dist) return DOPER_ERR_NULL_PTR;
+    if (!aligned(points, 8) || !aligned(segments, 16) || !aligned(scene_ws, 256) ||
+        (seg_out && !aligned(seg_out, 16)))
+        return DOPER_ERR_MISALIGNED;
+    return closest_dispatch((cudaStream_t)stream, N, S, 1, points, segments, scene_ws, idx, dist, seg_out);
 }
 
 int doper_points_inside(doper_stream_t stream, int64_t N, int32_t S, const float* points,
@@ -490,6 +511,19 @@ int doper_points_inside(doper_stream_t stream, int64_t N, int32_t S, const float
     if (!aligned(points, 8) || !aligned(segments, 16)) return DOPER_ERR_MISALIGNED;
     const unsigned grid = (unsigned)((N + kQueryThreads - 1) / kQueryThreads);
     points_inside_kernel<<<grid, kQueryThreads, 0, (cudaStream_t)stream>>>(
+        N, S, reinterpret_cast<const float2*>(points), reinterpret_cast<const float4*>(segments), flag);
+    return launch_status();
+}
+
+int doper_points_inside_env(doper_stream_t stream, int64_t N, int32_t S, const float* points,
+                            const float* segments, uint8_t* flag) {
+    if (N < 0 || S <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (S % 3 != 0) return DOPER_ERR_UNSUPPORTED;
+    if (N == 0) return DOPER_OK;
+    if (!points || !segments || !flag) return DOPER_ERR_NULL_PTR;
+    if (!aligned(points, 8) || !aligned(segments, 16)) return DOPER_ERR_MISALIGNED;
+    const unsigned grid = (unsigned)((N + kQueryThreads - 1) / kQueryThreads);
+    points_inside_env_kernel<<<grid, kQueryThreads, 0, (cudaStream_t)stream>>>(
         N, S, reinterpret_cast<const float2*>(points), reinterpret_cast<const float4*>(segments), flag);
     return launch_status();
 }
@@ -509,30 +543,68 @@ int doper_ray_segment_points(doper_stream_t stream, int64_t R, int32_t S, const 
     return launch_status();
 }
 
+namespace {
+int sensor_args_ok(int64_t N, int R, int S, const void* positions, const void* ray_directions, const void* scene_ws, size_t pos_align) {
+    if (N < 0 || R <= 0 || S <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (N > 0 && (!positions || !ray_directions || !scene_ws)) return DOPER_ERR_NULL_PTR;
+    if (!aligned(positions, pos_align) || !aligned(ray_directions, 8) || !aligned(scene_ws, 256)) return DOPER_ERR_MISALIGNED;
+    return DOPER_OK;
+}
+}  // namespace
+
 int doper_range_sensor(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
                        const float* ray_directions, const void* scene_ws, float distance_range, float* ranges,
                        float* points, int32_t* idx) {
-    if (N < 0 || R <= 0 || S <= 0) return DOPER_ERR_BAD_SHAPE;
-    if (N == 0) return DOPER_OK;
-    if (!positions || !ray_directions || !scene_ws || !ranges) return DOPER_ERR_NULL_PTR;
-    if (!aligned(positions, 8) || !aligned(ray_directions, 8) || !aligned(scene_ws, 256) ||
-        (points && !aligned(points, 8)))
-        return DOPER_ERR_MISALIGNED;
-    return launch_range_sensor<false>((cudaStream_t)stream, N, R, S, positions, nullptr, ray_directions, scene_ws,
-                                      distance_range, 0.0, 0.0, ranges, points, idx, nullptr);
+    const int rc = sensor_args_ok(N, R, S, positions, ray_directions, scene_ws, 8);
+    if (rc || N == 0) return rc;
+    if (!ranges) return DOPER_ERR_NULL_PTR;
+    if (points && !aligned(points, 8)) return DOPER_ERR_MISALIGNED;
+    return launch_range_sensor<false, false>((cudaStream_t)stream, N, R, S, 0, positions, nullptr, ray_directions, scene_ws,
+                                             distance_range, 0.0, 0.0, ranges, points, idx, nullptr);
+}
+
+int doper_range_sensor_env(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
+                           const float* ray_directions, const void* scene_ws, float distance_range, float* ranges,
+                           float* points, int32_t* idx) {
+    const int rc = sensor_args_ok(N, R, S, positions, ray_directions, scene_ws, 8);
+    if (rc || N == 0) return rc;
+    if (!ranges) return DOPER_ERR_NULL_PTR;
+    if (points && !aligned(points, 8)) return DOPER_ERR_MISALIGNED;
+    return launch_range_sensor<false, false>((cudaStream_t)stream, N, R, S, 1, positions, nullptr, ray_directions, scene_ws,
+                                             distance_range, 0.0, 0.0, ranges, points, idx, nullptr);
+}
+
+int doper_range_sensor_f64(doper_stream_t stream, int64_t N, int32_t R, int32_t S, int32_t per_env, const double* positions,
+                           const float* ray_directions, const void* scene_ws, float distance_range, double* ranges,
+                           float* points, int32_t* idx) {
+    const int rc = sensor_args_ok(N, R, S, positions, ray_directions, scene_ws, 16);
+    if (rc || N == 0) return rc;
+    if (!ranges) return DOPER_ERR_NULL_PTR;
+    if (points && !aligned(points, 8)) return DOPER_ERR_MISALIGNED;
+    return launch_range_sensor<false, true>((cudaStream_t)stream, N, R, S, per_env ? 1 : 0, positions, nullptr, ray_directions,
+                                            scene_ws, distance_range, 0.0, 0.0, ranges, points, idx, nullptr);
 }
 
 int doper_agent_observations(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
                              const float* velocities, const float* ray_directions, const void* scene_ws,
                              float distance_range, const double target[2], float* observations) {
-    if (N < 0 || R <= 0 || S <= 0) return DOPER_ERR_BAD_SHAPE;
-    if (N == 0) return DOPER_OK;
-    if (!positions || !velocities || !ray_directions || !scene_ws || !target || !observations)
-        return DOPER_ERR_NULL_PTR;
-    if (!aligned(positions, 8) || !aligned(velocities, 8) || !aligned(ray_directions, 8) || !aligned(scene_ws, 256))
-        return DOPER_ERR_MISALIGNED;
-    return launch_range_sensor<true>((cudaStream_t)stream, N, R, S, positions, velocities, ray_directions, scene_ws,
-                                     distance_range, target[0], target[1], nullptr, nullptr, nullptr, observations);
+    const int rc = sensor_args_ok(N, R, S, positions, ray_directions, scene_ws, 8);
+    if (rc || N == 0) return rc;
+    if (!velocities || !target || !observations) return DOPER_ERR_NULL_PTR;
+    if (!aligned(velocities, 8)) return DOPER_ERR_MISALIGNED;
+    return launch_range_sensor<true, false>((cudaStream_t)stream, N, R, S, 0, positions, velocities, ray_directions, scene_ws,
+                                            distance_range, target[0], target[1], nullptr, nullptr, nullptr, observations);
+}
+
+int doper_agent_observations_env(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
+                                 const float* velocities, const float* ray_directions, const void* scene_ws,
+                                 float distance_range, const double target[2], float* observations) {
+    const int rc = sensor_args_ok(N, R, S, positions, ray_directions, scene_ws, 8);
+    if (rc || N == 0) return rc;
+    if (!velocities || !target || !observations) return DOPER_ERR_NULL_PTR;
+    if (!aligned(velocities, 8)) return DOPER_ERR_MISALIGNED;
+    return launch_range_sensor<true, false>((cudaStream_t)stream, N, R, S, 1, positions, velocities, ray_directions, scene_ws,
+                                            distance_range, target[0], target[1], nullptr, nullptr, nullptr, observations);
 }
 
 int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d) {

@@ -44,34 +44,45 @@ __global__ void __launch_bounds__(kLossThreads) l1_loss_kernel(int64_t B, const 
 // ------------------------------------------------------------------------------------------
 constexpr int kQueryThreads = 128;
 
-template <int G>
+// STAGED: the (shared) scene is copied into shared memory by TMA; else it is read in place (a scene that does not
+// fit shared memory, or per-environment scenes: point i belongs to scene i, `per_env` = 1, N scenes in scene_ws).
+template <int G, bool STAGED>
 __global__ void __launch_bounds__(kQueryThreads) closest_segment_kernel(
-    int64_t N, int S, const float2* __restrict__ pts, const float4* __restrict__ raw,
+    int64_t N, int S, int per_env, const float2* __restrict__ pts, const float4* __restrict__ raw,
     const unsigned char* __restrict__ scene_ws, int32_t* __restrict__ idx_out,
     float* __restrict__ dist_out, float4* __restrict__ seg_out) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SceneLayout L = scene_layout(1, S);
-    float4* sq = reinterpret_cast<float4*>(smem);
-    float* srl = reinterpret_cast<float*>(smem + (size_t)L.S_pad * sizeof(float4));
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)L.S_pad * 20);
+    const SceneLayout L = scene_layout(per_env ? N : 1, S);
     const int tid = threadIdx.x, lane = tid % G;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (tid == 0) stage_scenes(sq, srl, scene_ws, L, 0, 1, bar);
-    const SceneHeader hdr = *reinterpret_cast<const SceneHeader*>(scene_ws + L.hdr_off);
-    SceneView sc;
-    sc.q = sq; sc.rl = srl; sc.S = S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)L.S_pad * 20);
+    if (STAGED) {
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) stage_scenes(reinterpret_cast<float4*>(smem), reinterpret_cast<float*>(smem + (size_t)L.S_pad * sizeof(float4)),
+                                   scene_ws, L, 0, 1, bar);
+    }
     int64_t i = (int64_t)blockIdx.x * (kQueryThreads / G) + tid / G;
     const bool active = i < N;
     if (!active) i = N - 1;
+    const int64_t env = per_env ? i : 0;
+    const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(scene_ws + L.hdr_off)[env];
+    SceneView sc;
+    if (STAGED) {
+        sc.q = reinterpret_cast<const float4*>(smem);
+        sc.rl = reinterpret_cast<const float*>(smem + (size_t)L.S_pad * sizeof(float4));
+    } else {
+        sc.q = reinterpret_cast<const float4*>(scene_ws + L.q_off) + env * L.S_pad;
+        sc.rl = reinterpret_cast<const float*>(scene_ws + L.rl_off) + env * L.S_pad;
+    }
+    sc.S = S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird;
     const float2 p = pts[i];
-    mbar_wait(bar, 0);
+    if (STAGED) mbar_wait(bar, 0);
     int idx; float dist;
     sweep_any<G>(sc, p.x, p.y, lane, -1, idx, dist);
     if (active && lane == 0) {
         idx_out[i] = idx;
         dist_out[i] = dist;
-        if (seg_out) seg_out[i] = raw[idx];
+        if (seg_out) seg_out[i] = raw[env * S + idx];
     }
 }
 
@@ -141,5 +152,31 @@ __global__ void fp32_probe_kernel(int iters, int use_fma, float* out) {
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// Per-environment scenes: point i against the triangles of scene i (raw [N][S][4]); same arithmetic, the unit
+// normals computed per use (no sharing between points).
+__global__ void __launch_bounds__(kQueryThreads) points_inside_env_kernel(int64_t N, int S, const float2* __restrict__ pts,
+                                                                         const float4* __restrict__ raw, uint8_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * kQueryThreads + threadIdx.x;
+    if (i >= N) return;
+    const float2 p = pts[i];
+    const float4* seg = raw + i * (int64_t)S;
+    bool any = false;
+    for (int t = 0; t + 2 < S; t += 3) {
+        bool all = true;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const float4 g = __ldg(seg + t + e);
+            const float svx = g.z - g.x, svy = g.w - g.y;  // :21
+            const float nx = svy, ny = -svx;               // :22
+            const float nrm = sqrtf(dot2(nx, nx, ny, ny)); // :23
+            const float pvx = p.x - g.x, pvy = p.y - g.y;  // :52
+            const float d = dot2(pvx, nx / nrm, pvy, ny / nrm);  // :53
+            all = all && (d < 0.0f);
+        }
+        any = any || all;
+    }
+    flag[i] = any ? 1 : 0;
+}
 
 }  // namespace doper

@@ -67,52 +67,85 @@ __global__ void __launch_bounds__(256) ray_points_kernel(int64_t R, int S, const
 // OBS: also / instead write RangeSensingAgent's observation rows [N][7 + R].
 constexpr int kSensorThreads = 128;
 
-template <bool OBS>
+// STAGED / per_env as in closest_segment_kernel (position i looks at scene i).
+// POS64: the positions are float64 (the reference's numpy code keeps a float64 position as it is,
+// observations.py:50; jax rounds the ray origins to float32 for the intersections, :62-65; the ranges
+// `norm(points - position)` are then float64, :67): intersections from the rounded origin, ranges in binary64
+// against the float64 position, float64 outputs.
+template <bool OBS, bool STAGED, bool POS64>
 __global__ void __launch_bounds__(kSensorThreads) range_sensor_kernel(
-    int64_t N, int R, int S, const float2* __restrict__ pos, const float2* __restrict__ vel,
+    int64_t N, int R, int S, int per_env, const void* __restrict__ pos_v, const float2* __restrict__ vel,
     const float2* __restrict__ ray_dirs, const unsigned char* __restrict__ scene_ws, float distance_range,
-    double tx, double ty, float* __restrict__ ranges, float2* __restrict__ points, int32_t* __restrict__ idx_out,
+    double tx, double ty, void* __restrict__ ranges_v, float2* __restrict__ points, int32_t* __restrict__ idx_out,
     float* __restrict__ obs) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SceneLayout L = scene_layout(1, S);
-    float4* sq = reinterpret_cast<float4*>(smem);
-    float* srl = reinterpret_cast<float*>(smem + (size_t)L.S_pad * sizeof(float4));
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)L.S_pad * 20);
+    const SceneLayout L = scene_layout(per_env ? N : 1, S);
     const int tid = threadIdx.x;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (tid == 0) stage_scenes(sq, srl, scene_ws, L, 0, 1, bar);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)L.S_pad * 20);
+    if (STAGED) {
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) stage_scenes(reinterpret_cast<float4*>(smem), reinterpret_cast<float*>(smem + (size_t)L.S_pad * sizeof(float4)),
+                                   scene_ws, L, 0, 1, bar);
+    }
     const int64_t e = (int64_t)blockIdx.x * kSensorThreads + tid;
     const bool active = e < N * (int64_t)R;
     const int64_t i = active ? e / R : 0;
     const int r = active ? (int)(e - i * R) : 0;
-    const float2 o = pos[i];
+    double ox64 = 0.0, oy64 = 0.0;
+    float2 o;
+    if (POS64) {
+        const double2 o64 = reinterpret_cast<const double2*>(pos_v)[i];
+        ox64 = o64.x; oy64 = o64.y;
+        o = make_float2((float)o64.x, (float)o64.y);
+    } else {
+        o = reinterpret_cast<const float2*>(pos_v)[i];
+    }
     const float2 dd = ray_dirs[r];
     float ux, uy;
     normalise(dd.x, dd.y, ux, uy);
-    mbar_wait(bar, 0);
+    const float4* sq = STAGED ? reinterpret_cast<const float4*>(smem)
+                              : reinterpret_cast<const float4*>(scene_ws + L.q_off) + (per_env ? i : 0) * L.S_pad;
+    if (STAGED) mbar_wait(bar, 0);
     unsigned long long key = kNoKey;
+    double best64 = __longlong_as_double(0x7ff0000000000000ll);  // POS64: (range, first index) minimum in binary64
+    int best_i = 0;
     float bx = __int_as_float(0x7f800000), by = bx;
     for (int j = 0; j < S; ++j) {
         const float4 q = sq[j];
         const RayHit h = ray_segment(o.x, o.y, ux, uy, q.x, q.y, q.z, q.w);
         if (h.hit) {
-            const float ex = h.px - o.x, ey = h.py - o.y;
-            const float rng = sqrtf(ex * ex + ey * ey);  // observations.py:66
-            const unsigned long long k = make_key(rng, j);
-            if (k < key) { key = k; bx = h.px; by = h.py; }
+            if (POS64) {
+                const double ex = (double)h.px - ox64, ey = (double)h.py - oy64;
+                const double rng = sqrt(ex * ex + ey * ey);  // observations.py:67 in float64
+                if (rng < best64) { best64 = rng; best_i = j; bx = h.px; by = h.py; }
+            } else {
+                const float ex = h.px - o.x, ey = h.py - o.y;
+                const float rng = sqrtf(ex * ex + ey * ey);  // observations.py:67
+                const unsigned long long k = make_key(rng, j);
+                if (k < key) { key = k; bx = h.px; by = h.py; }
+            }
         }
     }
     if (!active) return;
-    // all rays missed: every range is +inf, argmin = 0 (observations.py:69)
+    // all rays missed: every range is +inf, argmin = 0 (observations.py:70)
     int idx = 0;
     float rng = __int_as_float(0x7f800000);
-    if (key != kNoKey) unpack_key(key, idx, rng);
-    if (rng > distance_range) {  // observations.py:72-73 / :76 (NaN stays NaN)
-        bx = __int_as_float(0x7f800000); by = bx;
-        rng = distance_range;
+    double rng64 = best64;
+    if (POS64) {
+        idx = best_i;
+        if (rng64 > (double)distance_range) { bx = __int_as_float(0x7f800000); by = bx; rng64 = (double)distance_range; }
+    } else {
+        if (key != kNoKey) unpack_key(key, idx, rng);
+        if (rng > distance_range) {  // observations.py:73-74 / :77 (NaN stays NaN)
+            bx = __int_as_float(0x7f800000); by = bx;
+            rng = distance_range;
+        }
     }
-    if (ranges) ranges[e] = rng;
+    if (ranges_v) {
+        if (POS64) reinterpret_cast<double*>(ranges_v)[e] = rng64;
+        else reinterpret_cast<float*>(ranges_v)[e] = rng;
+    }
     if (points) points[e] = make_float2(bx, by);
     if (idx_out) idx_out[e] = idx;
     if (OBS) {

@@ -129,16 +129,20 @@ def _closest(points, segments):
     device = require_cuda()
     on_device = is_device_tensor(points)
     scene = _as_scene(segments)
-    if scene.per_env:
-        raise ValueError("find_closest_segment_*: per-environment scenes are not supported here")
     raw, ws = scene.prepared(device)
     pts = as_f32_device(points, device).reshape(-1, 2)
     N, S = int(pts.shape[0]), scene.n_segments
     idx = torch.empty(N, dtype=torch.int32, device=device)
     dist = torch.empty(N, dtype=torch.float32, device=device)
     seg = torch.empty((N, 2, 2), dtype=torch.float32, device=device)
-    check(lib.doper_closest_segment(stream_ptr(), N, S, ptr(pts), ptr(raw), ptr(ws), ptr(idx), ptr(dist),
-                                    ptr(seg)), "doper_closest_segment")
+    if scene.per_env:  # point i against scene i ([E,S,2,2] scenes: one environment per ball, ball_sim.py:332 vmapped over maps)
+        if N != scene.n_scenes:
+            raise ValueError(f"per-environment scenes: {N} points for {scene.n_scenes} scenes")
+        check(lib.doper_closest_segment_env(stream_ptr(), N, S, ptr(pts), ptr(raw), ptr(ws), ptr(idx), ptr(dist),
+                                            ptr(seg)), "doper_closest_segment_env")
+    else:
+        check(lib.doper_closest_segment(stream_ptr(), N, S, ptr(pts), ptr(raw), ptr(ws), ptr(idx), ptr(dist),
+                                        ptr(seg)), "doper_closest_segment")
     if on_device:
         return seg, dist, idx
     return seg.cpu().numpy(), dist.cpu().numpy(), idx.cpu().numpy()
@@ -166,13 +170,16 @@ def if_points_inside_any_polygon(points, scene: JaxScene):
     device = require_cuda()
     on_device = is_device_tensor(points)
     scene = _as_scene(scene)
-    if scene.per_env:
-        raise ValueError("if_points_inside_any_polygon: per-environment scenes are not supported here")
     raw, _ = scene.prepared(device)
     pts = as_f32_device(points, device).reshape(-1, 2)
     N, S = int(pts.shape[0]), scene.n_segments
     flag = torch.empty(N, dtype=torch.uint8, device=device)
-    check(lib.doper_points_inside(stream_ptr(), N, S, ptr(pts), ptr(raw), ptr(flag)), "doper_points_inside")
+    if scene.per_env:
+        if N != scene.n_scenes:
+            raise ValueError(f"per-environment scenes: {N} points for {scene.n_scenes} scenes")
+        check(lib.doper_points_inside_env(stream_ptr(), N, S, ptr(pts), ptr(raw), ptr(flag)), "doper_points_inside_env")
+    else:
+        check(lib.doper_points_inside(stream_ptr(), N, S, ptr(pts), ptr(raw), ptr(flag)), "doper_points_inside")
     out = flag.to(torch.bool)
     return out if on_device else out.cpu().numpy()
 
@@ -216,17 +223,29 @@ def range_sensor(positions, ray_directions, scene, distance_range: float, want_p
     device = require_cuda()
     on_device = is_device_tensor(positions)
     scene = _as_scene(scene)
-    if scene.per_env:
-        raise ValueError("range_sensor: per-environment scenes are not supported here")
     _, ws = scene.prepared(device)
-    pos = as_f32_device(positions, device).reshape(-1, 2)
+    # float64 positions keep their precision in the ranges, like the reference's numpy code (observations.py:50,67)
+    f64 = (isinstance(positions, torch.Tensor) and positions.dtype == torch.float64) or \
+        (not isinstance(positions, torch.Tensor) and np.asarray(positions).dtype == np.float64)
+    if f64:
+        pos = torch.as_tensor(np.asarray(positions) if not isinstance(positions, torch.Tensor) else positions,
+                              dtype=torch.float64, device=device).reshape(-1, 2).contiguous()
+    else:
+        pos = as_f32_device(positions, device).reshape(-1, 2)
     dirs = as_f32_device(ray_directions, device).reshape(-1, 2)
     N, R, S = int(pos.shape[0]), int(dirs.shape[0]), scene.n_segments
-    ranges = torch.empty((N, R), dtype=torch.float32, device=device)
+    if scene.per_env and N != scene.n_scenes:
+        raise ValueError(f"per-environment scenes: {N} positions for {scene.n_scenes} scenes")
+    ranges = torch.empty((N, R), dtype=torch.float64 if f64 else torch.float32, device=device)
     points = torch.empty((N, R, 2), dtype=torch.float32, device=device) if want_points else None
     idx = torch.empty((N, R), dtype=torch.int32, device=device) if want_points else None
-    check(lib.doper_range_sensor(stream_ptr(), N, R, S, ptr(pos), ptr(dirs), ptr(ws), float(distance_range),
-                                 ptr(ranges), ptr(points), ptr(idx)), "doper_range_sensor")
+    if f64:
+        check(lib.doper_range_sensor_f64(stream_ptr(), N, R, S, 1 if scene.per_env else 0, ptr(pos), ptr(dirs), ptr(ws),
+                                         float(distance_range), ptr(ranges), ptr(points), ptr(idx)), "doper_range_sensor_f64")
+    else:
+        fn = lib.doper_range_sensor_env if scene.per_env else lib.doper_range_sensor
+        check(fn(stream_ptr(), N, R, S, ptr(pos), ptr(dirs), ptr(ws), float(distance_range),
+                 ptr(ranges), ptr(points), ptr(idx)), "doper_range_sensor")
     if not want_points:
         return ranges if on_device else ranges.cpu().numpy()
     if on_device:

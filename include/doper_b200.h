@@ -72,13 +72,14 @@ enum {
     DOPER_ERR_BAD_SHAPE = 1,   /* negative / zero / inconsistent sizes */
     DOPER_ERR_NULL_PTR = 2,    /* a required pointer is NULL */
     DOPER_ERR_MISALIGNED = 3,  /* pointer not aligned as documented */
-    DOPER_ERR_SMEM_LIMIT = 4,  /* scene does not fit the kernel's shared-memory plan */
+    DOPER_ERR_SMEM_LIMIT = 4,  /* scene does not fit the kernel's shared-memory plan (pinned full-sweep rollout kernels
+                                  only: the default rollout plans, the queries and the sensor read a large scene in place) */
     DOPER_ERR_LAUNCH = 5,      /* cudaPeekAtLastError() != success after launch */
     DOPER_ERR_WORKSPACE = 6,   /* workspace too small */
     DOPER_ERR_UNSUPPORTED = 7  /* e.g. S >= 2^31, triangle count mismatch */
 };
 
-#define DOPER_ABI_VERSION 2
+#define DOPER_ABI_VERSION 3
 
 int doper_abi_version(void);
 
@@ -118,6 +119,14 @@ int doper_closest_segment(doper_stream_t stream, int64_t N, int32_t S, const flo
 int doper_points_inside(doper_stream_t stream, int64_t N, int32_t S, const float* points,
                         const float* segments, uint8_t* flag);
 
+/* Per-environment forms: point i is tested against scene i (segments [N][S][2][2], scene_ws prepared with
+ * n_scenes = N); the scenes are read in place.  Same results as N calls with one point each. */
+int doper_closest_segment_env(doper_stream_t stream, int64_t N, int32_t S, const float* points,
+                              const float* segments, const void* scene_ws, int32_t* idx, float* dist,
+                              float* seg_out);
+int doper_points_inside_env(doper_stream_t stream, int64_t N, int32_t S, const float* points,
+                            const float* segments, uint8_t* flag);
+
 /* ---- range sensor (observation path) ------------------------------- */
 
 /* batch_line_ray_intersection_point (doper/sim/jax_geometry.py:237-261):
@@ -135,6 +144,19 @@ int doper_range_sensor(doper_stream_t stream, int64_t N, int32_t R, int32_t S, c
                        const float* ray_directions, const void* scene_ws, float distance_range, float* ranges,
                        float* points, int32_t* idx);
 
+/* Per-environment form: position i looks at scene i (scene_ws prepared with n_scenes = N). */
+int doper_range_sensor_env(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
+                           const float* ray_directions, const void* scene_ws, float distance_range, float* ranges,
+                           float* points, int32_t* idx);
+
+/* float64 positions (doper/agents/observations.py:50,67: numpy keeps a float64 position as it is, so the
+ * reference's ranges `norm(points - position)` are float64, while JAX rounds the ray origins to float32 for
+ * the intersections, jax_geometry.py:237-261): intersections from the rounded origins, ranges and the
+ * (range, first index) minimum in binary64, float64 ranges out.  per_env = 0 / 1 as above. */
+int doper_range_sensor_f64(doper_stream_t stream, int64_t N, int32_t R, int32_t S, int32_t per_env,
+                           const double* positions, const float* ray_directions, const void* scene_ws,
+                           float distance_range, double* ranges, float* points, int32_t* idx);
+
 /* RangeSensingAgent.get_observations (doper/agents/range_sensor_agent.py:17-41), fused:
  * observations[i] = [ |x_i - target|, (x_i - target) / |x_i - target| (2), x_i (2), v_i (2),
  * ranges[i][0..R) / distance_range ], float32 [N][7 + R]; the first three entries are evaluated in
@@ -142,6 +164,9 @@ int doper_range_sensor(doper_stream_t stream, int64_t N, int32_t R, int32_t S, c
 int doper_agent_observations(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
                              const float* velocities, const float* ray_directions, const void* scene_ws,
                              float distance_range, const double target[2], float* observations);
+int doper_agent_observations_env(doper_stream_t stream, int64_t N, int32_t R, int32_t S, const float* positions,
+                                 const float* velocities, const float* ray_directions, const void* scene_ws,
+                                 float distance_range, const double target[2], float* observations);
 
 /* ---- rollout -------------------------------------------------------------------------- */
 
