@@ -26,6 +26,7 @@ EXPORTS = (
     "doper_ray_segment_points", "doper_range_sensor", "doper_agent_observations",
     "doper_closest_segment_env", "doper_points_inside_env", "doper_range_sensor_env", "doper_range_sensor_f64",
     "doper_agent_observations_env",
+    "doper_controller_scratch_bytes", "doper_controller_fwd", "doper_controller_bwd", "doper_adam_clip_step",
     "doper_peer_buffer_bytes", "doper_peer_alloc", "doper_peer_open", "doper_peer_close", "doper_peer_free",
     "doper_allreduce_oneshot",
 )
@@ -102,6 +103,12 @@ def _load() -> ctypes.CDLL:
                                              POINTER(ctypes.c_double), fp]
     lib.doper_range_sensor_env.argtypes = lib.doper_range_sensor.argtypes
     lib.doper_agent_observations_env.argtypes = lib.doper_agent_observations.argtypes
+    i4 = POINTER(c_int32)
+    lib.doper_controller_scratch_bytes.restype = c_size_t
+    lib.doper_controller_scratch_bytes.argtypes = [i4, c_int64]
+    lib.doper_controller_fwd.argtypes = [vp, i4, c_int64, fp, fp, fp, c_float, fp, fp]
+    lib.doper_controller_bwd.argtypes = [vp, i4, c_int64, fp, fp, fp, c_float, vp, fp]
+    lib.doper_adam_clip_step.argtypes = [vp, c_int32, fp, fp, fp, fp, fp, c_float, c_float, c_float, c_float, c_float, fp]
     lib.doper_range_sensor_f64.argtypes = [vp, c_int64, c_int32, c_int32, c_int32, vp, fp, vp, c_float, vp, fp, vp]
     lib.doper_peer_buffer_bytes.restype = c_size_t
     lib.doper_peer_buffer_bytes.argtypes = [c_int32]
@@ -111,7 +118,7 @@ def _load() -> ctypes.CDLL:
     lib.doper_peer_free.argtypes = [c_void_p]
     lib.doper_allreduce_oneshot.argtypes = [vp, c_int32, c_int32, POINTER(c_void_p), c_int32, fp, fp, vp, ctypes.c_double]
     for name in EXPORTS:
-        if name not in ("doper_peer_buffer_bytes", "doper_error_string", "doper_scene_workspace_bytes",
+        if name not in ("doper_controller_scratch_bytes", "doper_peer_buffer_bytes", "doper_error_string", "doper_scene_workspace_bytes",
                         "doper_rollout_workspace_bytes", "doper_rollout_bwd_scratch_bytes", "doper_abi_version", "doper_rollout_ckpt_every",
                         "doper_rollout_log_ball_major", "doper_rollout_plan_name"):
             getattr(lib, name).restype = ctypes.c_int

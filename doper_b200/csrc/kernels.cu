@@ -16,6 +16,7 @@
 //   queries.cuh    l1_loss_kernel, closest_segment_kernel, points_inside_kernel, fp32_probe_kernel
 //   sensor.cuh     range-sensor ray casting
 //   peer.cuh       one-shot all-reduce of the policy gradient over NVLink peer memory
+//   controller.cuh the trainer's glue: controller MLP forward / backward, gradient clip + Adam (three kernels)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -35,6 +36,7 @@
 
 #include "sensor.cuh"
 #include "peer.cuh"
+#include "controller.cuh"
 
 // ==========================================================================================
 // C ABI
@@ -891,6 +893,71 @@ int doper_allreduce_oneshot(doper_stream_t stream, int32_t rank, int32_t world, 
     const double secs = timeout_seconds > 0.0 ? (timeout_seconds < 3600.0 ? timeout_seconds : 3600.0) : 60.0;
     allreduce_oneshot_kernel<<<blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(P, rank, world, n, in, out, status,
                                                                                (long long)(secs * 2.0e9));
+    return launch_status();
+}
+
+namespace {
+int ctl_dims(const int32_t dims[4], CtlDims* d) {
+    if (!dims) return DOPER_ERR_NULL_PTR;
+    d->d_in = dims[0]; d->h1 = dims[1]; d->h2 = dims[2]; d->d_out = dims[3];
+    if (d->d_in < 1 || d->d_in > kCtlMaxIn || d->h1 < 1 || d->h1 > kCtlMaxHidden || d->h2 < 1 || d->h2 > kCtlMaxHidden ||
+        d->d_out < 2 || d->d_out > kCtlMaxOut)
+        return DOPER_ERR_UNSUPPORTED;
+    return DOPER_OK;
+}
+}  // namespace
+
+size_t doper_controller_scratch_bytes(const int32_t dims[4], int64_t B) {
+    CtlDims d;
+    if (ctl_dims(dims, &d) != DOPER_OK || B <= 0) return 0;
+    return (size_t)((B + kCtlBalls - 1) / kCtlBalls) * d.n_params() * sizeof(float);
+}
+
+int doper_controller_fwd(doper_stream_t stream, const int32_t dims[4], int64_t B, const float* params, const float* observations,
+                         const float* velocity_init, float mass, float* impulse, float* v0) {
+    CtlDims d;
+    int rc = ctl_dims(dims, &d);
+    if (rc) return rc;
+    if (B <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (!params || !observations || (v0 && !velocity_init) || (!v0 && !impulse)) return DOPER_ERR_NULL_PTR;
+    if ((v0 && (!aligned(v0, 8) || !aligned(velocity_init, 8))) || !aligned(params, 4) || !aligned(observations, 4)) return DOPER_ERR_MISALIGNED;
+    const size_t smem = CtlSmem::floats(d) * sizeof(float);
+    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(controller_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DOPER_ERR_SMEM_LIMIT;
+    const unsigned grid = (unsigned)((B + kCtlBalls - 1) / kCtlBalls);
+    controller_fwd_kernel<<<grid, kCtlThreads, smem, (cudaStream_t)stream>>>(d, B, params, observations,
+                                                                            reinterpret_cast<const float2*>(velocity_init), mass, impulse,
+                                                                            reinterpret_cast<float2*>(v0));
+    return launch_status();
+}
+
+int doper_controller_bwd(doper_stream_t stream, const int32_t dims[4], int64_t B, const float* params, const float* observations,
+                         const float* v0_bar, float mass, void* scratch, float* grad) {
+    CtlDims d;
+    int rc = ctl_dims(dims, &d);
+    if (rc) return rc;
+    if (B <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (!params || !observations || !v0_bar || !scratch || !grad) return DOPER_ERR_NULL_PTR;
+    if (!aligned(v0_bar, 8) || !aligned(scratch, 16)) return DOPER_ERR_MISALIGNED;
+    const size_t smem = (CtlSmem::floats(d) + (size_t)kCtlBalls * (d.h2 + d.h1 + d.d_out)) * sizeof(float);
+    if ((int)smem > max_optin_smem()) return DOPER_ERR_SMEM_LIMIT;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(controller_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DOPER_ERR_SMEM_LIMIT;
+    const unsigned grid = (unsigned)((B + kCtlBalls - 1) / kCtlBalls);
+    cudaStream_t st = (cudaStream_t)stream;
+    controller_bwd_kernel<<<grid, kCtlThreads, smem, st>>>(d, B, params, observations, reinterpret_cast<const float2*>(v0_bar), mass,
+                                                           reinterpret_cast<float*>(scratch));
+    if (launch_status() != DOPER_OK) return DOPER_ERR_LAUNCH;
+    controller_grad_reduce_kernel<<<(d.n_params() + 255) / 256, 256, 0, st>>>(d.n_params(), (int)grid, reinterpret_cast<const float*>(scratch), grad);
+    return launch_status();
+}
+
+int doper_adam_clip_step(doper_stream_t stream, int32_t n, float* params, float* grad, float* exp_avg, float* exp_avg_sq, float* step,
+                         float max_norm, float lr, float beta1, float beta2, float eps, float* total_norm) {
+    if (n <= 0) return DOPER_ERR_BAD_SHAPE;
+    if (!params || !grad || !exp_avg || !exp_avg_sq || !step) return DOPER_ERR_NULL_PTR;
+    adam_clip_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, params, grad, exp_avg, exp_avg_sq, step, max_norm, lr, beta1, beta2, eps, total_norm);
     return launch_status();
 }
 

@@ -41,6 +41,8 @@ class SingleScene:
                           else self.jax_scene.segments)
         eps = self.config["constants"]["radius"] / 2
         limit = self.config["constants"]["radius"] + eps
+        if self.jax_scene.per_env:
+            return self._get_init_state_per_env(batch_size, seg, limit, device, generator)
         lo = torch.tensor([seg[:, :, 0].min(), seg[:, :, 1].min()], dtype=torch.float32, device=device)
         hi = torch.tensor([seg[:, :, 0].max(), seg[:, :, 1].max()], dtype=torch.float32, device=device)
 
@@ -62,3 +64,27 @@ class SingleScene:
             remaining = remaining[torch.logical_not(acceptable)]
             proposal = draw(len(remaining), lo, hi)
         return out
+
+    def _get_init_state_per_env(self, batch_size, seg, limit, device, generator):
+        """One environment per ball ([E,S,2,2] scenes, BASELINE configs[2]): ball i is sampled in the box of ITS map
+        and tested against ITS triangles and segments (per-environment kernels: point i <-> scene i).  Same
+        acceptance rule and sampling boxes as single_scene.py:39-61, applied per environment; every iteration
+        re-tests the whole batch (accepted balls keep their position), so point i always meets scene i."""
+        E = self.jax_scene.n_scenes
+        if batch_size != E:
+            raise ValueError(f"per-environment scenes: batch_size {batch_size} != {E} environments")
+        lo = torch.tensor(seg.reshape(E, -1, 2).min(axis=1), dtype=torch.float32, device=device)
+        hi = torch.tensor(seg.reshape(E, -1, 2).max(axis=1), dtype=torch.float32, device=device)
+
+        def draw(a, b):
+            return a + (b - a) * torch.rand((E, 2), dtype=torch.float32, device=device, generator=generator)
+
+        out = draw(lo - 1, hi + 1)
+        while True:
+            is_inner = if_points_inside_any_polygon(out, self.jax_scene)
+            _, distance = find_closest_segment_to_points_batch(out, self.jax_scene)
+            acceptable = torch.logical_not(torch.logical_or(is_inner, distance <= limit))
+            if bool(acceptable.all()):
+                return out
+            logger.debug("Resampling starting position")
+            out = torch.where(acceptable[:, None], out, draw(lo, hi))

@@ -283,6 +283,28 @@ int doper_peer_free(void* buffer);
 int doper_allreduce_oneshot(doper_stream_t stream, int32_t rank, int32_t world, void* const* buffers, int32_t n,
                             const float* in, float* out, int32_t* status, double timeout_seconds);
 
+/* ---- trainer glue around the rollout ------------------------------------ */
+
+/* The reference's controller (doper/networks/controllers.py:12-18): Linear(d_in, h1) - ReLU - Linear(h1, h2) - ReLU -
+ * Linear(h2, d_out), dims = {d_in, h1, h2, d_out} (shipped: 25, 50, 100, 2), parameters as ONE flat float vector in
+ * torch order W1 [h1][d_in], b1, W2 [h2][h1], b2, W3 [d_out][h2], b3.
+ *   doper_controller_fwd   impulse [B][d_out] = controller(observations [B][d_in]) (nullable), and
+ *                          v0 [B][2] = velocity_init + impulse[:, :2] / mass (nullable)      ball_trainer.py:57-64
+ *   doper_controller_bwd   grad [n_params] += d(sum_b v0_bar[b] . v0[b]) / d params = impulse.backward(dL/dv0)
+ *                          (ball_trainer.py:70-71); deterministic (block partials in `scratch`,
+ *                          doper_controller_scratch_bytes, added in block order); `grad` can be the buffer that
+ *                          doper_allreduce_oneshot exchanges
+ *   doper_adam_clip_step   torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam.step() (no weight decay / amsgrad)
+ *                          on the flat vectors, then grad <- 0; `step` is a device float counter (starts at 0);
+ *                          total_norm (nullable) receives the gradient norm before clipping   ball_trainer.py:74-76 */
+size_t doper_controller_scratch_bytes(const int32_t dims[4], int64_t B);
+int doper_controller_fwd(doper_stream_t stream, const int32_t dims[4], int64_t B, const float* params, const float* observations,
+                         const float* velocity_init, float mass, float* impulse, float* v0);
+int doper_controller_bwd(doper_stream_t stream, const int32_t dims[4], int64_t B, const float* params, const float* observations,
+                         const float* v0_bar, float mass, void* scratch, float* grad);
+int doper_adam_clip_step(doper_stream_t stream, int32_t n, float* params, float* grad, float* exp_avg, float* exp_avg_sq, float* step,
+                         float max_norm, float lr, float beta1, float beta2, float eps, float* total_norm);
+
 /* ---- measurement helper --------------------------------------------------------------- */
 
 /* Register-only dependent FADD/FMUL chains (no FMA): every thread executes `iters` x 16

@@ -55,8 +55,16 @@ def main():
         e = timeit(eager, 20)
         run = tr.graphed_iteration(agent, handler)
         g = timeit(lambda: run(x0, v0), 50)
+        # the fused action loop (controller / clip / Adam as kernels of this library), eager and as one graph
+        tr2 = BallAttractorTrainer(copy.deepcopy(cfg))
+        fl = tr2.fused_loop(5)
+        fe = timeit(lambda: fl.run(agent, handler, x0, v0), 20)
+        run2 = tr2.graphed_iteration(agent, handler, fused=True)
+        fg = timeit(lambda: run2(x0, v0), 50)
         out["rows"].append({"batch": B, "eager_ms": round(e, 4), "graph_ms": round(g, 4),
-                            "ball_steps_per_s_graph": round(B * 300 * 8 / (g * 1e-3), 1)})
+                            "fused_eager_ms": round(fe, 4), "fused_graph_ms": round(fg, 4),
+                            "ball_steps_per_s_graph": round(B * 300 * 8 / (g * 1e-3), 1),
+                            "ball_steps_per_s_fused_graph": round(B * 300 * 8 / (fg * 1e-3), 1)})
     print(json.dumps(out))
     Path("gpurun_out").mkdir(exist_ok=True)
     Path("gpurun_out/trainer_bench.json").write_text(json.dumps(out))
