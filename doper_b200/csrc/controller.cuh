@@ -66,29 +66,39 @@ __device__ __forceinline__ void ctl_load_params(const CtlSmem& s, const CtlDims&
     for (int e = tid; e < d.d_out; e += kCtlThreads) s.b3[e] = params[d.ob3() + e];
 }
 
+// out[o] = post(init(o) + sum_k A(o, k) * Bm(o, k)) for o in [0, total): four outputs per thread in flight (four
+// independent accumulator chains: the per-output dot products are short dependent FMA chains, and a block is
+// latency bound)
+template <typename Init, typename A, typename Bm, typename Post>
+__device__ __forceinline__ void ctl_dots(int total, int K, Init init, A a, Bm bm, Post post) {
+    for (int o0 = threadIdx.x; o0 < total; o0 += 4 * kCtlThreads) {
+        int o[4];
+        float acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { o[u] = min(o0 + u * kCtlThreads, total - 1); acc[u] = init(o[u]); }
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = __fmaf_rn(a(o[u], k), bm(o[u], k), acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (o0 + u * kCtlThreads < total) post(o[u], acc[u]);
+    }
+}
+
 // activations of the block's balls: a1 = relu(W1 x + b1), a2 = relu(W2 a1 + b2), y = W3 a2 + b3
 __device__ __forceinline__ void ctl_forward(const CtlSmem& s, const CtlDims& d, int nb) {
-    const int tid = threadIdx.x;
-    for (int o = tid; o < nb * d.h1; o += kCtlThreads) {
-        const int b = o / d.h1, n = o - b * d.h1;
-        float acc = s.b1[n];
-        for (int k = 0; k < d.d_in; ++k) acc = __fmaf_rn(s.W1t[k * d.h1 + n], s.x[b * d.d_in + k], acc);
-        s.a1[o] = fmaxf(acc, 0.0f);
-    }
+    ctl_dots(nb * d.h1, d.d_in, [&](int o) { return s.b1[o % d.h1]; },
+             [&](int o, int k) { return s.W1t[k * d.h1 + o % d.h1]; }, [&](int o, int k) { return s.x[(o / d.h1) * d.d_in + k]; },
+             [&](int o, float v) { s.a1[o] = fmaxf(v, 0.0f); });
     __syncthreads();
-    for (int o = tid; o < nb * d.h2; o += kCtlThreads) {
-        const int b = o / d.h2, n = o - b * d.h2;
-        float acc = s.b2[n];
-        for (int k = 0; k < d.h1; ++k) acc = __fmaf_rn(s.W2t[k * d.h2 + n], s.a1[b * d.h1 + k], acc);
-        s.a2[o] = fmaxf(acc, 0.0f);
-    }
+    ctl_dots(nb * d.h2, d.h1, [&](int o) { return s.b2[o % d.h2]; },
+             [&](int o, int k) { return s.W2t[k * d.h2 + o % d.h2]; }, [&](int o, int k) { return s.a1[(o / d.h2) * d.h1 + k]; },
+             [&](int o, float v) { s.a2[o] = fmaxf(v, 0.0f); });
     __syncthreads();
-    for (int o = tid; o < nb * d.d_out; o += kCtlThreads) {
-        const int b = o / d.d_out, n = o - b * d.d_out;
-        float acc = s.b3[n];
-        for (int k = 0; k < d.h2; ++k) acc = __fmaf_rn(s.W3t[k * d.d_out + n], s.a2[b * d.h2 + k], acc);
-        s.y[o] = acc;
-    }
+    ctl_dots(nb * d.d_out, d.h2, [&](int o) { return s.b3[o % d.d_out]; },
+             [&](int o, int k) { return s.W3t[k * d.d_out + o % d.d_out]; }, [&](int o, int k) { return s.a2[(o / d.d_out) * d.h2 + k]; },
+             [&](int o, float v) { s.y[o] = v; });
     __syncthreads();
 }
 
@@ -138,41 +148,26 @@ __global__ void __launch_bounds__(kCtlThreads) controller_bwd_kernel(CtlDims d, 
     __syncthreads();
     ctl_forward(s, d, nb);
     // dz2 = (W3^T dy) * [a2 > 0]
-    for (int o = tid; o < nb * d.h2; o += kCtlThreads) {
-        const int b = o / d.h2, k = o - b * d.h2;
-        float acc = 0.0f;
-        for (int n = 0; n < d.d_out; ++n) acc = __fmaf_rn(s.W3t[k * d.d_out + n], dy[b * d.d_out + n], acc);
-        dz2[o] = s.a2[o] > 0.0f ? acc : 0.0f;
-    }
+    ctl_dots(nb * d.h2, d.d_out, [&](int) { return 0.0f; },
+             [&](int o, int n) { return s.W3t[(o % d.h2) * d.d_out + n]; }, [&](int o, int n) { return dy[(o / d.h2) * d.d_out + n]; },
+             [&](int o, float v) { dz2[o] = s.a2[o] > 0.0f ? v : 0.0f; });
     __syncthreads();
     // dz1 = (W2^T dz2) * [a1 > 0]
-    for (int o = tid; o < nb * d.h1; o += kCtlThreads) {
-        const int b = o / d.h1, k = o - b * d.h1;
-        float acc = 0.0f;
-        for (int n = 0; n < d.h2; ++n) acc = __fmaf_rn(s.W2t[k * d.h2 + n], dz2[b * d.h2 + n], acc);
-        dz1[o] = s.a1[o] > 0.0f ? acc : 0.0f;
-    }
+    ctl_dots(nb * d.h1, d.h2, [&](int) { return 0.0f; },
+             [&](int o, int n) { return s.W2t[(o % d.h1) * d.h2 + n]; }, [&](int o, int n) { return dz2[(o / d.h1) * d.h2 + n]; },
+             [&](int o, float v) { dz1[o] = s.a1[o] > 0.0f ? v : 0.0f; });
     __syncthreads();
     float* out = partial + (size_t)blockIdx.x * d.n_params();
     // weight gradients: entry (n, k) = sum over the block's balls of delta[b][n] * input[b][k]
-    for (int e = tid; e < d.h1 * d.d_in; e += kCtlThreads) {
-        const int n = e / d.d_in, k = e - n * d.d_in;
-        float acc = 0.0f;
-        for (int b = 0; b < nb; ++b) acc = __fmaf_rn(dz1[b * d.h1 + n], s.x[b * d.d_in + k], acc);
-        out[d.oW1() + e] = acc;
-    }
-    for (int e = tid; e < d.h2 * d.h1; e += kCtlThreads) {
-        const int n = e / d.h1, k = e - n * d.h1;
-        float acc = 0.0f;
-        for (int b = 0; b < nb; ++b) acc = __fmaf_rn(dz2[b * d.h2 + n], s.a1[b * d.h1 + k], acc);
-        out[d.oW2() + e] = acc;
-    }
-    for (int e = tid; e < d.d_out * d.h2; e += kCtlThreads) {
-        const int n = e / d.h2, k = e - n * d.h2;
-        float acc = 0.0f;
-        for (int b = 0; b < nb; ++b) acc = __fmaf_rn(dy[b * d.d_out + n], s.a2[b * d.h2 + k], acc);
-        out[d.oW3() + e] = acc;
-    }
+    ctl_dots(d.h1 * d.d_in, nb, [&](int) { return 0.0f; },
+             [&](int e, int b) { return dz1[b * d.h1 + e / d.d_in]; }, [&](int e, int b) { return s.x[b * d.d_in + e % d.d_in]; },
+             [&](int e, float v) { out[d.oW1() + e] = v; });
+    ctl_dots(d.h2 * d.h1, nb, [&](int) { return 0.0f; },
+             [&](int e, int b) { return dz2[b * d.h2 + e / d.h1]; }, [&](int e, int b) { return s.a1[b * d.h1 + e % d.h1]; },
+             [&](int e, float v) { out[d.oW2() + e] = v; });
+    ctl_dots(d.d_out * d.h2, nb, [&](int) { return 0.0f; },
+             [&](int e, int b) { return dy[b * d.d_out + e / d.h2]; }, [&](int e, int b) { return s.a2[b * d.h2 + e % d.h2]; },
+             [&](int e, float v) { out[d.oW3() + e] = v; });
     for (int n = tid; n < d.h1; n += kCtlThreads) { float acc = 0.0f; for (int b = 0; b < nb; ++b) acc += dz1[b * d.h1 + n]; out[d.ob1() + n] = acc; }
     for (int n = tid; n < d.h2; n += kCtlThreads) { float acc = 0.0f; for (int b = 0; b < nb; ++b) acc += dz2[b * d.h2 + n]; out[d.ob2() + n] = acc; }
     for (int n = tid; n < d.d_out; n += kCtlThreads) { float acc = 0.0f; for (int b = 0; b < nb; ++b) acc += dy[b * d.d_out + n]; out[d.ob3() + n] = acc; }
@@ -184,7 +179,13 @@ __global__ void __launch_bounds__(256) controller_grad_reduce_kernel(int n_param
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e >= n_params) return;
     float acc = 0.0f;
-    for (int b = 0; b < n_blocks; ++b) acc += partial[(size_t)b * n_params + e];
+    int b = 0;
+    for (; b + 4 <= n_blocks; b += 4) {  // four loads in flight; the additions stay in block order
+        const float p0 = partial[(size_t)b * n_params + e], p1 = partial[(size_t)(b + 1) * n_params + e];
+        const float p2 = partial[(size_t)(b + 2) * n_params + e], p3 = partial[(size_t)(b + 3) * n_params + e];
+        acc = (((acc + p0) + p1) + p2) + p3;
+    }
+    for (; b < n_blocks; ++b) acc += partial[(size_t)b * n_params + e];
     grad[e] += acc;
 }
 

@@ -250,21 +250,28 @@ __global__ void __launch_bounds__(32 * (1 + U / 2)) rollout_fwd_pipe_kernel(cons
             // most U steps per window, so that the other balls of the group keep moving.
             State cur = r;
             int tn = ts0 + f + 1;
+            // the log word of a contact step needs the slot that record_collision's atomic returns (~1 us round trip
+            // to L2): it is written one iteration later, so that the next step's arithmetic hides the latency
+            int pend_t = -1, pend_pl = 0;
+            uint32_t pend_clip = 0u;
             while (extra < U && tn < n) {
                 State c1;
                 free_step(cur.x, cur.y, cur.vx, cur.vy, c, c1);
                 int i2;
                 if (!baked_hit(sc, bk, c1.x, c1.y, c.r, i2)) break;  // free flight again: the producer takes over from `cur`
                 const int pl = record_collision(p.sink, ball, tn, cur.x, cur.y, cur.vx, cur.vy, i2);
-                const State r2 = resolve(cur.x, cur.y, cur.vx, cur.vy, c1, sc.q[i2], c);
-                if (hl) hl[(int64_t)tn * p.hl_st] = pack_log(pl, true, clip_bits(cur.vx, cur.vy));
                 if (p.ckpt) {
                     const bool at = kshift >= 0 ? (tn & (K - 1)) == 0 : (tn % K) == 0;
                     if (at) p.ckpt[(size_t)(kshift >= 0 ? tn >> kshift : tn / K) * p.B + ball] = make_float4(cur.x, cur.y, cur.vx, cur.vy);
                 }
+                const uint32_t clip = clip_bits(cur.vx, cur.vy);
+                const State r2 = resolve(cur.x, cur.y, cur.vx, cur.vy, c1, sc.q[i2], c);
+                if (hl && pend_t >= 0) hl[(int64_t)pend_t * p.hl_st] = pack_log(pend_pl, true, pend_clip);
+                pend_t = tn; pend_pl = pl; pend_clip = clip;
                 cur = r2;
                 ++tn; ++extra;
             }
+            if (hl && pend_t >= 0) hl[(int64_t)pend_t * p.hl_st] = pack_log(pend_pl, true, pend_clip);
             if (extra > 0 && tn == n) { p.xT[ball] = make_float2(cur.x, cur.y); p.vT[ball] = make_float2(cur.vx, cur.vy); }
             sh.mail_state[buf][b] = make_float4(cur.x, cur.vx, cur.y, cur.vy);
             sh.mail_t[buf][b] = tn;

@@ -44,9 +44,11 @@ def main():
         cfg["train"]["batch_size"] = B
         handler = SingleScene(cfg, jax_scene=JaxScene(syn.make_map(1002, 67)))
         agent = RangeSensingAgent(cfg)
+        torch.manual_seed(0)  # same controller, same draw in every run: the iteration time depends on the trajectories
         tr = BallAttractorTrainer(cfg)
-        x0 = handler.get_init_state(B)
-        v0 = -1 + 3 * torch.rand((B, 2), device="cuda")
+        gen = torch.Generator(device="cuda"); gen.manual_seed(1)
+        x0 = handler.get_init_state(B, generator=gen)
+        v0 = -1 + 3 * torch.rand((B, 2), device="cuda", generator=gen)
 
         def eager():
             tr.optimizer.zero_grad(set_to_none=True)
@@ -56,6 +58,7 @@ def main():
         run = tr.graphed_iteration(agent, handler)
         g = timeit(lambda: run(x0, v0), 50)
         # the fused action loop (controller / clip / Adam as kernels of this library), eager and as one graph
+        torch.manual_seed(0)
         tr2 = BallAttractorTrainer(copy.deepcopy(cfg))
         fl = tr2.fused_loop(5)
         fe = timeit(lambda: fl.run(agent, handler, x0, v0), 20)
