@@ -475,7 +475,7 @@ def ours(args):
     # ---- parity of the timed plan on the timed workload (untimed) -----------------------------
     parity = None
     if rank == 0 and not args.no_parity:
-        one_step()  # eager, so that gv / the workspace are those of this exact workload
+        fwd(); loss_bwd()  # eager and WITHOUT the exchange (a collective: rank 0 alone must not enter it)
         torch.cuda.synchronize()
         parity = parity_block(ball_sim, lib, check, ptr, cur(), desc, sws, bufs, w, scene, opts, gv, B, n_steps)
     # ---- N > 1: the peer-memory exchange against NCCL on the same vectors (every run) ---------

@@ -104,6 +104,18 @@ def timeit(fn, reps=30):
     return float(t)
 
 
+# (d) the fused action loop (controller / clip / Adam as library kernels), one graph per rank, the flat gradient
+# buffer exchanged in place by the peer kernel: parameters close to (a), identical bits on every rank
+fusedt = trainer("nvlink")
+runf = fusedt.graphed_iteration(agent, handler, fused=True)
+losses_d = [float(runf(x0, v0)) for x0, v0 in draws]
+fused_close = all(torch.allclose(a, b, rtol=1e-3, atol=2e-5) for a, b in zip(eager.controller.parameters(), fusedt.controller.parameters()))
+fused_close = fused_close and all(abs(a - b) <= 1e-3 * abs(a) for a, b in zip(losses_a, losses_d))
+fbits = True
+q = fusedt.fused_loop().pflat.detach().clone()
+dist.broadcast(q, 0)
+fbits = bool(torch.equal(q, fusedt.fused_loop().pflat))
+
 x0, v0 = draws[0]
 
 
@@ -113,15 +125,19 @@ def eager_it():
 
 
 t_eager, t_graph = timeit(eager_it), timeit(lambda: run(x0, v0))
+t_fused = timeit(lambda: runf(x0, v0))
 status = int(graphed._reducer.peer.status.item())
-flags = torch.tensor([int(same_as_eager), int(bits)], device=dev)
+flags = torch.tensor([int(same_as_eager), int(bits), int(fused_close), int(fbits)], device=dev)
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
     line = {"world": world, "balls_per_rank": B, "graph_equals_eager_nccl": bool(flags[0]), "same_bits_on_every_rank": bool(flags[1]),
             "first_iteration_grad_vs_single_gpu_big_batch_rel_err": grad_err, "loss_rel_err": loss_err, "peer_status": status,
-            "eager_nccl_ms": round(t_eager, 4), "graph_peer_ms": round(t_graph, 4)}
+            "fused_graph_close_to_eager_nccl": bool(flags[2]), "fused_same_bits_on_every_rank": bool(flags[3]),
+            "eager_nccl_ms": round(t_eager, 4), "graph_peer_ms": round(t_graph, 4), "fused_graph_peer_ms": round(t_fused, 4)}
     print(json.dumps(line), flush=True)
     Path("gpurun_out").mkdir(exist_ok=True)
     Path(f"gpurun_out/trainer_multi_gpu_n{world}.json").write_text(json.dumps(line))
 graphed._reducer.peer.close()
+if fusedt.fused_loop()._peer:
+    fusedt.fused_loop()._peer.close()
 dist.destroy_process_group()
