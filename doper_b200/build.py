@@ -46,6 +46,13 @@ def lib_path(policy: int | None = None) -> Path:
     return LIB if policy is None else OUT_DIR / f"libdoper_b200_p{int(policy)}.so"
 
 
+def is_current(policy: int | None = None) -> bool:
+    """The library of this policy exists and was built from the sources as they are now."""
+    extra = [] if policy is None else [f"-DDOPER_FP_POLICY={int(policy)}"]
+    stamp = STAMP if policy is None else OUT_DIR / f"build_p{int(policy)}.stamp"
+    return lib_path(policy).exists() and stamp.exists() and stamp.read_text() == _digest(extra)
+
+
 def build(force: bool = False, verbose: bool = False, policy: int | None = None, wait: bool = True):
     OUT_DIR.mkdir(exist_ok=True)
     extra = [] if policy is None else [f"-DDOPER_FP_POLICY={int(policy)}"]

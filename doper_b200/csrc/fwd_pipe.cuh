@@ -52,7 +52,8 @@ constexpr int kPipeBalls = 16;  // balls per group (= per producer warp)
 
 template <int U>
 struct PipeShared {  // one per group
-    float4 slot[2][U + 1][kPipeBalls];  // [window parity][0: window start, j: after the window's step j - 1][ball] = (x, vx, y, vy)
+    float4 slot[2][kPipeBalls][U + 1];  // [window parity][ball][0: window start, j: after the window's step j - 1] = (x, vx, y, vy);
+                                        // ball-major: the consumers' lanes (ball, step) read consecutive 16-byte words
     int t_start[2][kPipeBalls];         // first step of the window
     int epoch_w[2][kPipeBalls];         // restart epoch the window was integrated in
     float4 mail_state[2][kPipeBalls];   // restart state (x, vx, y, vy) posted by a consumer while it read window parity p
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(32 * (1 + U / 2)) rollout_fwd_pipe_kernel(cons
                 epoch = me;
             }
             if (axis == 0) { sh.t_start[buf][b] = t; sh.epoch_w[buf][b] = epoch; }
-            float2* out = reinterpret_cast<float2*>(&sh.slot[buf][0][b]) + axis;
-            constexpr int kSlotStride = kPipeBalls * 2;  // float2 per slot
+            float2* out = reinterpret_cast<float2*>(&sh.slot[buf][b][0]) + axis;
+            constexpr int kSlotStride = 2;  // float2 per slot
             const float p0 = pos, v0 = vel;
             out[0] = make_float2(pos, vel);
             PIPE_MARK(0);
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2)) rollout_fwd_pipe_kernel(cons
         const int ts0 = sh.t_start[buf][b];
         const bool fresh = committed < n && sh.epoch_w[buf][b] == epoch;  // else: integrated from a superseded state
         const int nv = fresh ? min(U, n - ts0) : 0;                       // steps of the window that exist
-        const float4 s = sh.slot[buf][j][b], cand = sh.slot[buf][j + 1][b];  // start state and candidate of my step
+        const float4 s = sh.slot[buf][b][j], cand = sh.slot[buf][b][j + 1];  // start state and candidate of my step
         // (1) my candidate against the baked lists
         int idx = 0, k0 = 0, k1 = 0;
         const int kind = j < nv ? baked_cell(bk, cand.x, cand.z, k0, k1) : 0;

@@ -46,8 +46,8 @@ print(json.dumps(out))
 def test_alternative_policy_build_matches_the_oracle_built_with_the_same_mask():
     from doper_b200 import build as b
     lib = b.lib_path(b.ALT_POLICY)
-    if not lib.exists():
-        pytest.skip(f"{lib.name} not built (python -m doper_b200.build --all)")
+    if not b.is_current(b.ALT_POLICY):
+        pytest.skip(f"{lib.name} is missing or older than the sources (python -m doper_b200.build --all, or __graft_entry__.build())")
     env = dict(os.environ, DOPER_B200_LIB=str(lib))
     r = subprocess.run([sys.executable, "-c", CHILD % {"root": str(ROOT)}], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
