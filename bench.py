@@ -161,7 +161,12 @@ def parity_block(ball_sim, lib, check, ptr, st, desc, sws, bufs, w, scene, opts,
     d2.flags = int(desc.flags) | 2
     gx2 = torch.empty(2 * B, dtype=torch.float32, device=gv_default.device)
     gv2 = torch.empty(2 * B, dtype=torch.float32, device=gv_default.device)
-    check(lib.doper_rollout_bwd(st, ctypes.byref(d2), ptr(sws), ptr(bufs.ws), 0, ptr(bufs.scratch), 0, ptr(gx2), ptr(gv2)),
+    # the seeds sign(x_T - target) of the backward (the fused launch computes them in place and leaves none behind)
+    xT_t = bufs.out[4:4 + 2 * B]
+    seeds = torch.empty(2 * B, dtype=torch.float32, device=gv_default.device)
+    tmp = torch.empty(1, dtype=torch.float32, device=gv_default.device)
+    check(lib.doper_l1_loss(st, B, ptr(xT_t), ball_sim._target2(w["target"]), 0, ptr(tmp), ptr(seeds)), "loss (seeds)")
+    check(lib.doper_rollout_bwd(st, ctypes.byref(d2), ptr(sws), ptr(bufs.ws), 0, ptr(seeds), 0, ptr(gx2), ptr(gv2)),
           "bwd (sequential)")
     torch.cuda.synchronize()
     a = gv_default.double().view(B, 2).cpu().numpy()
@@ -382,8 +387,17 @@ def ours(args):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    def value_and_grad():
+        # the C-ABI entry of the path (= the reference's vmapped_grad_and_value): ONE launch when the pipelined plan
+        # applies (forward + loss + backward fused per block), else forward, loss and backward launches
+        check(lib.doper_value_and_grad(cur(), dref, ptr(sws), ptr(x0), ptr(v0), tgt, ptr(bufs.ws), ptr(bufs.bwd_scratch),
+                                       ptr(bufs.scratch), ptr(loss_sum), ptr(lpb), ptr(xT), ptr(vT), ptr(gv), ptr(gx)), "value_and_grad")
+
     def one_step():
-        fwd(); loss_bwd()
+        if args.separate_launches:
+            fwd(); loss_bwd()
+        else:
+            value_and_grad()
         if world > 1:
             exchange()
 
@@ -424,11 +438,7 @@ def ours(args):
         if step_graph is not None:
             step_graph.replay()
         else:
-            fwd()
-            ev[k][1].record()
-            loss_bwd()
-            if world > 1:
-                exchange()
+            one_step()
         ev[k][2].record()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
@@ -444,7 +454,12 @@ def ours(args):
         torch.cuda.synchronize()
         fwd_ms = np.array([a.elapsed_time(b) for a, b in fev])
     else:
-        fwd_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+        fev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(min(K, 20))]
+        for a, b in fev:
+            flush.fill_(1)
+            a.record(); fwd(); b.record()
+        torch.cuda.synchronize()
+        fwd_ms = np.array([a.elapsed_time(b) for a, b in fev])
     tot = torch.tensor([step_ms.sum()], dtype=torch.float64, device=device)
     tot_min = tot.clone()
     if world > 1:
@@ -475,7 +490,11 @@ def ours(args):
     # ---- parity of the timed plan on the timed workload (untimed) -----------------------------
     parity = None
     if rank == 0 and not args.no_parity:
-        fwd(); loss_bwd()  # eager and WITHOUT the exchange (a collective: rank 0 alone must not enter it)
+        # eager, the timed entry point, WITHOUT the exchange (a collective: rank 0 alone must not enter it)
+        if args.separate_launches:
+            fwd(); loss_bwd()
+        else:
+            value_and_grad()
         torch.cuda.synchronize()
         parity = parity_block(ball_sim, lib, check, ptr, cur(), desc, sws, bufs, w, scene, opts, gv, B, n_steps)
     # ---- N > 1: the peer-memory exchange against NCCL on the same vectors (every run) ---------
@@ -551,7 +570,7 @@ def ours(args):
             peaks = json.loads(mp.read_text())
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         fwd_kernel = lib.doper_rollout_plan_name(dref, 0).decode()
-        bwd_kernel = lib.doper_rollout_plan_name(dref, 1).decode()
+        bwd_kernel = lib.doper_rollout_plan_name(dref, 1 if args.separate_launches else 2).decode()
         prof = {}
         if tp.exists():
             try:
@@ -614,7 +633,7 @@ def ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_block(name, B, S, n_steps, bool(w["per_env"]), args),
             "plan": {"forward_kernel": lib.doper_rollout_plan_name(dref, 0).decode(),
-                     "backward_kernel": lib.doper_rollout_plan_name(dref, 1).decode(),
+                     "backward_kernel": lib.doper_rollout_plan_name(dref, 1 if args.separate_launches else 2).decode(),
                      "ckpt_every": int(lib.doper_rollout_ckpt_every(dref)),
                      "sweep": "exact" if args.exact else ("filtered+exact, every pair" if args.full_sweep else
                                                         "broad phase (baked per-cell lists / per-ball lists) + exact"),
@@ -630,7 +649,8 @@ def ours(args):
                     "d2h_bytes_per_step": (4 + 6 * B) * 4, "ms_per_step": round(float(e2e_ms.item()), 5),
                     "api": "doper_b200.sim.ball_sim.vmapped_grad_and_value(host numpy arrays)"},
             # kernels of this repository per step: forward, loss, backward (1 or 2), exchange (N > 1, peer kernel)
-            "gpu_launches": (3 + lib.doper_rollout_plan_name(dref, 1).decode().count("+") + (1 if peer is not None else 0)) * K,
+            "gpu_launches": ((1 if (not args.separate_launches and "fused" in lib.doper_rollout_plan_name(dref, 2).decode())
+                              else 3 + lib.doper_rollout_plan_name(dref, 1).decode().count("+")) + (1 if peer is not None else 0)) * K,
             "wall_ms_timed_region": round(wall_ms, 3),
             "roofline": roof,
         }
@@ -704,6 +724,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the timed steps eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) parity block")
+    ap.add_argument("--separate-launches", action="store_true",
+                    help="time doper_rollout_fwd + doper_l1_loss + doper_rollout_bwd instead of doper_value_and_grad")
     ap.add_argument("--sharded", action="store_true",
                     help="also time one rank's slice of the sharded BASELINE workloads (c5 weak, c3 strong); default when N > 1")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded workloads block")

@@ -282,6 +282,79 @@ __global__ void __launch_bounds__(128) rollout_bwd_jacobian_kernel(const BwdPara
 // memory (warp 0, one lane per ball).  With lane = ball the loads of a step-major hit log ([n_steps][B], the
 // lane-split forward kernels) are coalesced; a ball-major log ([B][n_steps], lane = step forward kernels) is
 // read in per-lane runs that the L1 keeps.
+// g[k] <- (product of the transposed step Jacobians of steps t1-1 .. t0) e_k for the four basis cotangents: column k
+// of the chunk's transposed Jacobian.  Free-flight steps from the two clip bits of the log word alone; collided steps
+// from the Jacobian pass's matrix (p.jac), or computed in place when no pass ran / no record exists.
+__device__ __forceinline__ void chunk_product(const BwdParams& p, const ConstsD& cd, const int64_t ball, const int t0, const int t1,
+                                              double (&g)[4][4]) {
+    const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
+    bool coupled = false;
+    for (int tb = t1; tb > t0;) {
+        const int ta = max(t0, tb - kBwdPrefetch);
+        unsigned m_hit = 0u, m_cx = 0u, m_cy = 0u;
+#pragma unroll
+        for (int j = 0; j < kBwdPrefetch; ++j) {
+            const uint32_t w = (ta + j < tb) ? (uint32_t)hl[(size_t)(ta + j) * p.hl_st] : 0u;
+            m_hit |= (w >> 31) << j;
+            m_cx |= ((w >> 29) & 1u) << j;
+            m_cy |= ((w >> 30) & 1u) << j;
+        }
+        for (int t = tb - 1; t >= ta; --t) {
+            const int j = t - ta;
+            if (!((m_hit >> j) & 1u)) {
+                const double avx = ((m_cx >> j) & 1u) ? cd.a_v : 0.0, avy = ((m_cy >> j) & 1u) ? cd.a_v : 0.0;
+                if (!coupled) {
+#pragma unroll
+                    for (int k = 0; k < 4; k += 2) {  // columns 0, 2 live on (x, vx); columns 1, 3 on (y, vy)
+                        const double tx = fma(g[k][0], cd.dt, g[k][2]);
+                        g[k][0] = fma(cd.a_p, tx, g[k][0]);
+                        g[k][2] = fma(tx, avx, tx);
+                        const double ty = fma(g[k + 1][1], cd.dt, g[k + 1][3]);
+                        g[k + 1][1] = fma(cd.a_p, ty, g[k + 1][1]);
+                        g[k + 1][3] = fma(ty, avy, ty);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double tx = fma(g[k][0], cd.dt, g[k][2]);
+                        g[k][0] = fma(cd.a_p, tx, g[k][0]);
+                        g[k][2] = fma(tx, avx, tx);
+                        const double ty = fma(g[k][1], cd.dt, g[k][3]);
+                        g[k][1] = fma(cd.a_p, ty, g[k][1]);
+                        g[k][3] = fma(ty, avy, ty);
+                    }
+                }
+                continue;
+            }
+            const uint32_t h = (uint32_t)hl[(size_t)t * p.hl_st];
+            double Jl[16];
+            const double* J;
+            if (h & kLogNoRecord) {  // no record: replay the state from the checkpoint, Jacobian in place (slow path)
+                const float4* q = scene_q(p, ball);
+                const float4 st = replay_state(p, ball, t, q);
+                hit_jacobian_d(st, __ldg(q + (h & kLogSeg)), __ldg(scene_s1(p, ball) + (h & kLogSeg)), cd, Jl);
+                J = Jl;
+            } else if (p.jac != nullptr) {
+                J = p.jac + (size_t)(h & kLogSeg) * 16;
+            } else {  // no Jacobian pass ran (the fused forward + backward launch): from the record, in place
+                const float4* r = reinterpret_cast<const float4*>(p.rec + (h & kLogSeg));
+                const int seg = reinterpret_cast<const int4*>(r)[1].z;
+                hit_jacobian_d(r[0], __ldg(scene_q(p, ball) + seg), __ldg(scene_s1(p, ball) + seg), cd, Jl);
+                J = Jl;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double a0 = g[k][0], a1 = g[k][1], a2 = g[k][2], a3 = g[k][3];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    g[k][r] = fma(J[4 * r + 0], a0, fma(J[4 * r + 1], a1, fma(J[4 * r + 2], a2, J[4 * r + 3] * a3)));
+            }
+            coupled = true;
+        }
+        tb = ta;
+    }
+}
+
 constexpr int kFoldMaxChunks = 16;  // 512 threads per block: 128 registers per thread (the 4x4 binary64 product needs ~90)
 
 __global__ void __launch_bounds__(32 * kFoldMaxChunks) rollout_bwd_fold_kernel(const BwdParams p, const int n_chunks,
@@ -298,69 +371,7 @@ __global__ void __launch_bounds__(32 * kFoldMaxChunks) rollout_bwd_fold_kernel(c
 #pragma unroll
         for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0 : 0.0;
     const int t0 = chunk * chunk_len, t1 = min(p.n_steps, t0 + chunk_len);
-    if (active && t0 < t1) {
-        const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
-        bool coupled = false;
-        for (int tb = t1; tb > t0;) {
-            const int ta = max(t0, tb - kBwdPrefetch);
-            unsigned m_hit = 0u, m_cx = 0u, m_cy = 0u;
-#pragma unroll
-            for (int j = 0; j < kBwdPrefetch; ++j) {
-                const uint32_t w = (ta + j < tb) ? (uint32_t)hl[(size_t)(ta + j) * p.hl_st] : 0u;
-                m_hit |= (w >> 31) << j;
-                m_cx |= ((w >> 29) & 1u) << j;
-                m_cy |= ((w >> 30) & 1u) << j;
-            }
-            for (int t = tb - 1; t >= ta; --t) {
-                const int j = t - ta;
-                if (!((m_hit >> j) & 1u)) {
-                    const double avx = ((m_cx >> j) & 1u) ? cd.a_v : 0.0, avy = ((m_cy >> j) & 1u) ? cd.a_v : 0.0;
-                    if (!coupled) {
-#pragma unroll
-                        for (int k = 0; k < 4; k += 2) {  // columns 0, 2 live on (x, vx); columns 1, 3 on (y, vy)
-                            const double tx = fma(g[k][0], cd.dt, g[k][2]);
-                            g[k][0] = fma(cd.a_p, tx, g[k][0]);
-                            g[k][2] = fma(tx, avx, tx);
-                            const double ty = fma(g[k + 1][1], cd.dt, g[k + 1][3]);
-                            g[k + 1][1] = fma(cd.a_p, ty, g[k + 1][1]);
-                            g[k + 1][3] = fma(ty, avy, ty);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const double tx = fma(g[k][0], cd.dt, g[k][2]);
-                            g[k][0] = fma(cd.a_p, tx, g[k][0]);
-                            g[k][2] = fma(tx, avx, tx);
-                            const double ty = fma(g[k][1], cd.dt, g[k][3]);
-                            g[k][1] = fma(cd.a_p, ty, g[k][1]);
-                            g[k][3] = fma(ty, avy, ty);
-                        }
-                    }
-                    continue;
-                }
-                const uint32_t h = (uint32_t)hl[(size_t)t * p.hl_st];
-                double Jl[16];
-                const double* J;
-                if (h & kLogNoRecord) {  // no record: replay the state from the checkpoint, Jacobian in place (slow path)
-                    const float4* q = scene_q(p, ball);
-                    const float4 st = replay_state(p, ball, t, q);
-                    hit_jacobian_d(st, __ldg(q + (h & kLogSeg)), __ldg(scene_s1(p, ball) + (h & kLogSeg)), cd, Jl);
-                    J = Jl;
-                } else {
-                    J = p.jac + (size_t)(h & kLogSeg) * 16;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const double a0 = g[k][0], a1 = g[k][1], a2 = g[k][2], a3 = g[k][3];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        g[k][r] = fma(J[4 * r + 0], a0, fma(J[4 * r + 1], a1, fma(J[4 * r + 2], a2, J[4 * r + 3] * a3)));
-                }
-                coupled = true;
-            }
-            tb = ta;
-        }
-    }
+    if (active && t0 < t1) chunk_product(p, cd, ball, t0, t1, g);
     // fold: v <- P_c v for c = n_chunks - 1 .. 0, P_c column k = g[k] of thread (ball, c)
 #pragma unroll
     for (int k = 0; k < 4; ++k)

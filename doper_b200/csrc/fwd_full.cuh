@@ -27,6 +27,14 @@ struct FwdParams {
     HitSink sink;     // collision records (state at the START of each collided step + segment index), appended
     int32_t* hitlog;  // element (t, ball) at t * hl_st + ball * hl_sb
     int64_t hl_st, hl_sb;
+    // fused forward + loss + backward launch (rollout_fwd_pipe_kernel<U, true> only; null otherwise)
+    float tgt_x, tgt_y;       // loss target
+    float* loss_sum;          // sum_b |x_T - target|_1 (written by the last block to finish)
+    float* loss_pb;           // per-ball loss terms (always written: the total is summed from them)
+    float2* g_v0;             // dL/dv0
+    float2* g_x0;             // dL/dx0 (nullable)
+    unsigned int* done_blocks;  // zeroed counter in the workspace header
+    double* jac;                // the backward's scratch: one 4x4 Jacobian per collision record (nullable)
 };
 
 template <int G>

@@ -31,6 +31,7 @@
 // the steps of the BASELINE batches.  Every value comes out of the same device functions as in every other
 // forward kernel: results are bit-identical (tests/test_parity_gpu.py runs the same cases over this kernel).
 #pragma once
+#include "bwd.cuh"
 #include "fwd_baked.cuh"
 
 namespace doper {
@@ -70,8 +71,17 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 // U: window length = steps the producer integrates between two hand-overs.  Warps per group: 1 producer + U / 2
 // consumers; a consumer warp owns 32 / U balls and gives every (ball, step of the window) its own lane, so that the
 // consumers' latency per window does not grow with U while the producer's does: U = 16 balances the two.
-template <int U>
-__global__ void __launch_bounds__(32 * (1 + U / 2)) rollout_fwd_pipe_kernel(const FwdParams p) {
+// FUSED: when the block's 16 balls have reached step n it also evaluates their loss terms and pulls the loss gradient
+// back through the hit log it has just written (binary64 chunk products + fold, bwd.cuh; collision Jacobians from the
+// block's own records, in place), so that forward + L1 loss + backward are ONE launch: the backward of a block
+// overlaps the forward of the blocks that are still running, and a small batch (the reference's 16 balls) costs one
+// launch instead of four.  The last block to finish adds the per-ball loss terms in l1_loss_kernel's order.
+// (The fused variant's binary64 tail takes 168 registers per thread: one block per SM.  It is therefore used for
+// batches of at most 148 blocks only — kFusedMaxBalls — where a second block per SM would not be used anyway; for
+// BASELINE configs[1] (256 blocks) the separate backward launches are faster: measured 0.151 ms per step against
+// 0.164 fused with the registers capped for two blocks per SM, 0.177 uncapped.)
+template <int U, bool FUSED>
+__global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1) rollout_fwd_pipe_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     static_assert(U == 8 || U == 16 || U == 32, "window length");
     constexpr int CW = U / 2;          // consumer warps
@@ -170,9 +180,8 @@ __global__ void __launch_bounds__(32 * (1 + U / 2)) rollout_fwd_pipe_kernel(cons
             if (done) break;
         }
         PIPE_FLUSH(0);
-        return;
-    }
-
+        if (!FUSED) return;
+    } else {
     // -------------------------------------------------------------------------------------- consumers
     const int cw = warp - 1;
     constexpr int BPW = 32 / U;                  // balls per consumer warp
@@ -311,6 +320,111 @@ __global__ void __launch_bounds__(32 * (1 + U / 2)) rollout_fwd_pipe_kernel(cons
 #endif
     }
     PIPE_FLUSH(8);
+    }  // consumers
+    if (!FUSED) return;
+
+    // ---------------------------------------------------------------------------- fused loss + backward of this block
+    named_barrier(1, GT);  // every warp left its loop after the same barrier; the block's log, records and x_T are written
+    constexpr int NC = 16;  // chunks per ball: thread (ball = tid & 15, chunk = tid >> 4), 256 of the block's threads
+    double* fold = reinterpret_cast<double*>(smem);  // [NC][16 entries][16 balls]: over the staged scene (no longer needed)
+    BwdParams bp;
+    bp.B = p.B; bp.S = p.S; bp.per_env = 0; bp.n_steps = n; bp.K = p.K; bp.c = c; bp.scene_ws = p.scene_ws;
+    bp.ckpt = p.ckpt; bp.rec = p.sink.rec; bp.rec_count = p.sink.count; bp.rec_cap = p.sink.cap; bp.jac = nullptr;
+    bp.hitlog = p.hitlog; bp.hl_st = p.hl_st; bp.hl_sb = p.hl_sb;
+    bp.xT_bar = nullptr; bp.vT_bar = nullptr; bp.x0_bar = nullptr; bp.v0_bar = nullptr;
+    const ConstsD cd = make_consts_d(c);
+    const int chunk_len = (n + NC - 1) / NC;
+    // (a) the block's collision Jacobians, one thread per collided step (a binary64 Jacobian is a ~5 us dependent
+    //     chain: in line, a chunk with several collisions would serialise them): the threads list the records their
+    //     chunks refer to, then every listed record gets its own thread; matrices go to the backward's scratch
+    __shared__ int jl_count;
+    int* jlist = reinterpret_cast<int*>(&sh);  // the window buffers are free now
+    constexpr int kJlCap = (int)(sizeof(sh.slot) / sizeof(int));
+    const int bb = tid & 15, chunk = tid >> 4;
+    const int64_t fb = first + bb;
+    const int t0 = chunk * chunk_len, t1 = min(n, t0 + chunk_len);
+    const bool mine = tid < 16 * NC && fb < p.B && t0 < t1;
+    if (tid == 0) jl_count = 0;
+    named_barrier(1, GT);
+    if (p.jac != nullptr && mine) {
+        const int32_t* hlb = p.hitlog + (size_t)fb * p.hl_sb;
+        for (int t = t0; t < t1; ++t) {
+            const uint32_t wv = (uint32_t)hlb[(size_t)t * p.hl_st];
+            if ((wv & kLogHit) && !(wv & kLogNoRecord)) {
+                const int k = atomicAdd(&jl_count, 1);
+                if (k < kJlCap) jlist[k] = (int)(wv & kLogSeg);
+            }
+        }
+    }
+    named_barrier(1, GT);
+    const int n_jac = jl_count;
+    if (p.jac != nullptr && n_jac <= kJlCap) {
+        for (int i = tid; i < n_jac; i += GT) {
+            const int slot = jlist[i];
+            const float4* rr = reinterpret_cast<const float4*>(p.sink.rec + slot);
+            const int4 m = reinterpret_cast<const int4*>(rr)[1];
+            const int64_t rb = ((int64_t)m.w << 32) | (uint32_t)m.x;
+            double J[16];
+            hit_jacobian_d(rr[0], __ldg(scene_q(bp, rb) + m.z), __ldg(scene_s1(bp, rb) + m.z), cd, J);
+            double2* out = reinterpret_cast<double2*>(p.jac + (size_t)slot * 16);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[k] = make_double2(J[2 * k], J[2 * k + 1]);
+        }
+        bp.jac = p.jac;
+    }
+    named_barrier(1, GT);
+    // (b) chunk products
+    if (tid < 16 * NC) {
+        double g[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0 : 0.0;
+        if (mine) chunk_product(bp, cd, fb, t0, t1, g);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) fold[((size_t)chunk * 16 + (k * 4 + r)) * 16 + bb] = g[k][r];
+    }
+    named_barrier(1, GT);
+    if (tid < 16 && first + tid < p.B) {
+        const int64_t fb = first + tid;
+        const float2 xT = p.xT[fb];
+        const float ex = xT.x - p.tgt_x, ey = xT.y - p.tgt_y;
+        p.loss_pb[fb] = fabsf(ex) + fabsf(ey);                      // ball_sim.py:286
+        double v[4] = {(double)sgnf(ex), (double)sgnf(ey), 0.0, 0.0};  // seed: d|e| / de
+        for (int cc = NC - 1; cc >= 0; --cc) {
+            const double* P = fold + (size_t)cc * 16 * 16 + tid;
+            double o[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                o[r] = fma(v[0], P[(0 * 4 + r) * 16], fma(v[1], P[(1 * 4 + r) * 16], fma(v[2], P[(2 * 4 + r) * 16], v[3] * P[(3 * 4 + r) * 16])));
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = o[r];
+        }
+        p.g_v0[fb] = make_float2((float)v[2], (float)v[3]);
+        if (p.g_x0) p.g_x0[fb] = make_float2((float)v[0], (float)v[1]);
+    }
+    // the loss total: the last block to get here adds the per-ball terms in l1_loss_kernel's order (same bits)
+    __shared__ int last_s;
+    __threadfence();
+    named_barrier(1, GT);
+    if (tid == 0) last_s = atomicAdd(p.done_blocks, 1u) == gridDim.x - 1 ? 1 : 0;
+    named_barrier(1, GT);
+    if (!last_s) return;
+    __threadfence();
+    float* part = reinterpret_cast<float*>(smem);
+    if (tid < 256) {
+        float acc = 0.0f;
+        for (int64_t q = tid; q < p.B; q += 256) acc += __ldcg(p.loss_pb + q);
+        part[tid] = acc;
+    }
+    named_barrier(1, GT);
+    for (int sft = 128; sft > 0; sft >>= 1) {
+        if (tid < sft) part[tid] += part[tid + sft];
+        named_barrier(1, GT);
+    }
+    if (tid == 0) *p.loss_sum = part[0];  // ball_sim.py:324
 }
 
 }  // namespace doper

@@ -30,8 +30,8 @@
 #include "fwd_full.cuh"
 #include "fwd_broad.cuh"
 #include "fwd_baked.cuh"
-#include "fwd_pipe.cuh"
 #include "bwd.cuh"
+#include "fwd_pipe.cuh"
 #include "queries.cuh"
 
 #include "sensor.cuh"
@@ -177,6 +177,15 @@ bool use_pipe(const doper_rollout_desc* d) {
     if (pipe_pinned(d)) return true;
     return d->lanes_per_ball == 0 && !(d->flags & (kBakedOffBits | (1 << 21) | (1 << 22) | (1 << 23))) && d->B <= kPipeMaxBalls;
 }
+// One launch for forward + L1 loss + backward (rollout_fwd_pipe_kernel<U, true>): the pipelined plan, the default
+// (binary64) backward, collision records enabled, and a staged scene large enough to hold the fold's matrices.
+constexpr int64_t kFusedMaxBalls = 1024;  // 64 blocks: the fused variant runs one block per SM (fwd_pipe.cuh)
+bool fused_ok(const doper_rollout_desc* d) {
+    if (!use_pipe(d) || (d->flags & 2) || record_capacity(d) <= 0 || d->n_steps < 1 || d->B > kFusedMaxBalls) return false;
+    const int S_pad = scene_layout(1, d->S).S_pad;
+    return (size_t)S_pad * 20 + (bake_bytes(S_pad) - sizeof(BakeHeader)) >= 16 * 16 * 16 * sizeof(double);
+}
+
 int pipe_window(const doper_rollout_desc* d) { return pipe_pinned(d) ? d->lanes_per_ball : 16; }
 
 bool use_baked(const doper_rollout_desc* d) {
@@ -370,16 +379,25 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
     return staged ? go(rollout_fwd_baked_kernel<G, true, THREADS>) : go(rollout_fwd_baked_kernel<G, false, THREADS>);
 }
 
-template <int U>
+template <int U, bool FUSED>
 int launch_fwd_pipe(cudaStream_t st, const FwdParams& p) {
     const int S_pad = scene_layout(1, p.S).S_pad;
     const size_t smem = (size_t)S_pad * 20 + (bake_bytes(S_pad) - sizeof(BakeHeader)) + 16 + sizeof(PipeShared<U>);
     if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(rollout_fwd_pipe_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        cudaFuncSetAttribute(rollout_fwd_pipe_kernel<U, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DOPER_ERR_SMEM_LIMIT;
     const unsigned grid = (unsigned)((p.B + kPipeBalls - 1) / kPipeBalls);
-    rollout_fwd_pipe_kernel<U><<<grid, 32 * (1 + U / 2), smem, st>>>(p);
+    rollout_fwd_pipe_kernel<U, FUSED><<<grid, 32 * (1 + U / 2), smem, st>>>(p);
     return launch_status();
+}
+
+template <bool FUSED>
+int dispatch_fwd_pipe(cudaStream_t st, const FwdParams& p, int window) {
+    switch (window) {
+        case 8: return launch_fwd_pipe<8, FUSED>(st, p);
+        case 32: return launch_fwd_pipe<32, FUSED>(st, p);
+        default: return launch_fwd_pipe<16, FUSED>(st, p);
+    }
 }
 
 template <int G>
@@ -621,6 +639,9 @@ int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
 
 const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward) {
     if (validate_desc(d) != DOPER_OK) return "invalid";
+    if (backward == 2)  // what doper_value_and_grad launches for the backward
+        return (fused_ok(d) && !(d->flags & (1 << 24))) ? "fused into the forward launch (rollout_fwd_pipe_kernel<U, true>)"
+                                                        : ((d->flags & 2) ? "rollout_bwd_kernel" : "rollout_bwd_jacobian_kernel+rollout_bwd_fold_kernel");
     if (backward) return (d->flags & 2) ? "rollout_bwd_kernel" : "rollout_bwd_jacobian_kernel+rollout_bwd_fold_kernel";
     if (use_pipe(d)) {
         const int u = pipe_window(d);
@@ -655,9 +676,31 @@ size_t doper_rollout_workspace_bytes(const doper_rollout_desc* d) {
     return w.total;
 }
 
+}  // extern "C"
+
+namespace {
+struct FusedArgs { const float* target; float* loss_sum; float* loss_pb; float* v0_bar; float* x0_bar; void* bwd_scratch; };
+
+int rollout_fwd_impl(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                     const float* x0, const float* v0, float* xT, float* vT, float* traj_x,
+                     float* traj_v, float* traj_a, void* ws, const FusedArgs* fa);
+}  // namespace
+
+extern "C" {
+
 int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
                       const float* x0, const float* v0, float* xT, float* vT, float* traj_x,
                       float* traj_v, float* traj_a, void* ws) {
+    return rollout_fwd_impl(stream, d, scene_ws, x0, v0, xT, vT, traj_x, traj_v, traj_a, ws, nullptr);
+}
+
+}  // extern "C"
+
+namespace {
+int rollout_fwd_impl(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                     const float* x0, const float* v0, float* xT, float* vT, float* traj_x,
+                     float* traj_v, float* traj_a, void* ws, const FusedArgs* fa) {
+    const bool fused = fa != nullptr;
     int rc = validate_desc(d);
     if (rc) return rc;
     if (!scene_ws || !x0 || !v0 || !xT || !vT) return DOPER_ERR_NULL_PTR;
@@ -687,6 +730,15 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     p.traj_x = reinterpret_cast<float2*>(traj_x); p.traj_v = reinterpret_cast<float2*>(traj_v);
     p.traj_a = reinterpret_cast<float2*>(traj_a);
     p.ckpt = nullptr; p.hitlog = nullptr; p.sink.rec = nullptr; p.sink.count = nullptr; p.sink.cap = 0;
+    p.tgt_x = p.tgt_y = 0.0f; p.loss_sum = nullptr; p.loss_pb = nullptr; p.g_v0 = nullptr; p.g_x0 = nullptr; p.done_blocks = nullptr; p.jac = nullptr;
+    if (fused) {
+        if (!ws || !fa->target || !fa->loss_sum || !fa->loss_pb || !fa->v0_bar) return DOPER_ERR_NULL_PTR;
+        p.tgt_x = fa->target[0]; p.tgt_y = fa->target[1];
+        p.loss_sum = fa->loss_sum; p.loss_pb = fa->loss_pb;
+        p.g_v0 = reinterpret_cast<float2*>(fa->v0_bar); p.g_x0 = reinterpret_cast<float2*>(fa->x0_bar);
+        p.done_blocks = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(ws) + 16);  // header, zeroed below
+        p.jac = reinterpret_cast<double*>(fa->bwd_scratch);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (ws) {
         const WsLayout w = ws_layout(d);
@@ -703,11 +755,7 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
 #else
     if (use_pipe(d) && !traj_x && !traj_v && !traj_a) {
 #endif
-        switch (pipe_window(d)) {
-            case 8: return launch_fwd_pipe<8>(st, p);
-            case 32: return launch_fwd_pipe<32>(st, p);
-            default: return launch_fwd_pipe<16>(st, p);
-        }
+        return fused ? dispatch_fwd_pipe<true>(st, p, pipe_window(d)) : dispatch_fwd_pipe<false>(st, p, pipe_window(d));
     }
     if (use_baked(d)) {
         switch (baked_lanes(d)) {
@@ -764,6 +812,9 @@ int doper_rollout_fwd(doper_stream_t stream, const doper_rollout_desc* d, const 
         default: return launch_fwd<32>(st, p, smem);
     }
 }
+}  // namespace
+
+extern "C" {
 
 size_t doper_rollout_bwd_scratch_bytes(const doper_rollout_desc* d) {
     if (validate_desc(d) != DOPER_OK) return 0;
@@ -843,6 +894,16 @@ int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, con
                          float* scratch, float* loss_sum, float* loss_per_ball, float* xT,
                          float* vT, float* v0_bar, float* x0_bar) {
     if (!ws || !scratch || !target) return DOPER_ERR_NULL_PTR;
+    if (validate_desc(d) == DOPER_OK && fused_ok(d) && !(d->flags & (1 << 24))) {
+        // ONE launch: every block of the pipelined forward also evaluates the loss terms of its balls and pulls the
+        // gradient back through the log it has just written (flags bit 24 keeps the separate launches).  The
+        // per-ball loss terms are needed for the total: they go to loss_per_ball, or to `scratch` when that is NULL.
+        FusedArgs fa;
+        fa.target = target; fa.loss_sum = loss_sum; fa.loss_pb = loss_per_ball ? loss_per_ball : scratch;
+        fa.v0_bar = v0_bar; fa.x0_bar = x0_bar; fa.bwd_scratch = bwd_scratch;
+        if (!loss_sum || !v0_bar) return DOPER_ERR_NULL_PTR;
+        return rollout_fwd_impl(stream, d, scene_ws, x0, v0, xT, vT, nullptr, nullptr, nullptr, ws, &fa);
+    }
     int rc = doper_rollout_fwd(stream, d, scene_ws, x0, v0, xT, vT, nullptr, nullptr, nullptr, ws);
     if (rc) return rc;
     rc = doper_l1_loss(stream, d->B, xT, target, loss_per_ball, loss_sum, scratch);

@@ -43,7 +43,8 @@ class RolloutOptions:
                  broad_phase: bool = None, exact_index_log: bool = False,
                  broad_phase_time_parallel: bool = False, hit_records: bool = True, hit_capacity: int = 0,
                  baked_broad_phase: bool = True, baked_lanes: int = 0,
-                 pipelined: bool | None = None, pipe_window: int = 0):
+                 pipelined: bool | None = None, pipe_window: int = 0,
+                 fused_value_and_grad: bool = True):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
@@ -66,13 +67,14 @@ class RolloutOptions:
         self.baked_broad_phase = bool(baked_broad_phase)
         self.baked_lanes = int(baked_lanes)  # 0 = chosen from the batch size; else lanes (speculated steps) per ball
         self.pipelined = pipelined  # None = library default; False: forbid rollout_fwd_pipe_kernel
-        self.pipe_window = int(pipe_window)  # 4, 8 or 16: pin rollout_fwd_pipe_kernel with that window
+        self.pipe_window = int(pipe_window)  # 8, 16 or 32: pin rollout_fwd_pipe_kernel with that window
+        self.fused_value_and_grad = bool(fused_value_and_grad)  # False: doper_value_and_grad as separate launches
 
     def key(self) -> tuple:
         return (self.ckpt_every, self.lanes_per_ball, self.force_exact_sweep, self.sequential_backward, self.smem_forward,
                 self.time_parallel, self.broad_phase, self.exact_index_log, self.broad_phase_time_parallel,
                 self.hit_records, self.hit_capacity, self.baked_broad_phase, self.baked_lanes, self.pipelined,
-                self.pipe_window)
+                self.pipe_window, self.fused_value_and_grad)
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -125,6 +127,8 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
     if opts.pipe_window:
         d.lanes_per_ball = opts.pipe_window
         d.flags |= 1 << 23
+    if not opts.fused_value_and_grad:
+        d.flags |= 1 << 24
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d

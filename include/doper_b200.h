@@ -198,6 +198,9 @@ typedef struct {
                                       (default there: the baked per-cell lists of doper_scene_prepare);
                                bit 22: forbid the pipelined forward kernel (producer / consumer warp pairs over
                                       the baked lists: the default of shared scenes up to 6,144 balls);
+                               bit 24: doper_value_and_grad keeps forward, loss and backward as separate launches
+                                      (default up to 1,024 balls on the pipelined forward: ONE launch, each block
+                                      pulls the gradient of its own balls back as soon as they have finished);
                                bit 23: with lanes_per_ball = 8, 16 or 32: the pipelined kernel with that window
                                       length (speculated steps per producer / consumer hand-over);
                                bit 19: no collision records (the backward replays every collided
@@ -221,8 +224,9 @@ int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d);
  * workspace need this; doper_rollout_bwd derives it from the same descriptor. */
 int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d);
 
-/* Name of the kernel the library will launch for this rollout (backward = 0: forward, 1: backward);
- * a static string, for benchmark / profile reports. */
+/* Name of the kernel the library will launch for this rollout (backward = 0: doper_rollout_fwd, 1: doper_rollout_bwd,
+ * 2: the backward inside doper_value_and_grad, which may be fused into the forward launch); a static string, for
+ * benchmark / profile reports. */
 const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward);
 
 /* Bytes of the forward's workspace (header + checkpoints + hit log + collision records). */
@@ -248,8 +252,11 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
 int doper_l1_loss(doper_stream_t stream, int64_t B, const float* xT, const float target[2],
                   float* loss_per_ball, float* loss_sum, float* xT_bar);
 
-/* vmapped_grad_and_value in one call: fwd -> loss -> bwd on `stream`.
- * scratch: device float[2*B] (holds xT_bar).  x0_bar nullable. */
+/* vmapped_grad_and_value in one call: fwd -> loss -> bwd on `stream` — as ONE kernel launch for small batches on the
+ * pipelined forward plan (shared scene in shared memory, <= 1,024 balls, default backward, collision records on; flags
+ * bit 24 forces the separate launches), else a forward, a loss and one or two backward launches.  Same results either way
+ * (the loss total is summed in the same order).  scratch: device float[2*B] (holds xT_bar / per-ball loss terms).
+ * x0_bar and loss_per_ball nullable. */
 int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
                          const float* x0, const float* v0, const float target[2], void* ws, void* bwd_scratch,
                          float* scratch, float* loss_sum, float* loss_per_ball, float* xT,

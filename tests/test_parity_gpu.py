@@ -898,3 +898,56 @@ def test_baked_lists_hold_every_touchable_segment(sim, radius, scale):
             n_checked += 1
     assert n_checked > 100
     assert (np.diff(cs[: nx * ny + 1].astype(np.int64)) >= 0).all() and cs[nx * ny] == n_items
+
+
+# ------------------------------------------------------------------------------------------------
+# forward + loss + backward as ONE launch (rollout_fwd_pipe_kernel<U, true>, the default of doper_value_and_grad)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_balls,n_steps", [(1, 1), (16, 300), (17, 5), (333, 301), (1024, 500), (1000, 64)])
+def test_fused_value_and_grad_matches_the_separate_launches_and_truth(sim, cref, n_balls, n_steps):
+    """One launch == forward, loss and backward launches: final states and per-ball results bit for bit, the loss total
+    bit for bit (same summation order), gradients equal to the separate binary64 backward to 1e-6 of the ball's gradient
+    norm (the chunk boundaries of the binary64 product may differ) and within 1e-6 of the float64 truth."""
+    import ctypes
+    from doper_b200._abi import lib
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=n_balls)
+    scene = geo.JaxScene(w["segments"])
+    args = (n_steps / 1000, n_steps, scene, w["x0"], w["v0"], w["target"], w["attractor"], w["constants"])
+    d = ball_sim._make_desc(n_balls, scene, n_steps / 1000, n_steps, w["attractor"], w["constants"], ball_sim.RolloutOptions())
+    assert "fused" in lib.doper_rollout_plan_name(ctypes.byref(d), 2).decode()
+    (l1, (x1, v1)), g1 = ball_sim.vmapped_grad_and_value(*args)
+    (l2, (x2, v2)), g2 = ball_sim.vmapped_grad_and_value(*args, _opts(ball_sim, fused_value_and_grad=False))
+    assert_bitexact(x1, x2, "x_T"); assert_bitexact(v1, v2, "v_T")
+    assert np.float32(l1).view(np.uint32) == np.float32(l2).view(np.uint32), (l1, l2)
+    c = onp.make_constants(w["constants"])
+    truth, _ = cref.grad_truth64(n_steps, np.float32((n_steps / 1000) / n_steps), c, w["attractor"], w["target"], w["segments"],
+                                 w["x0"], w["v0"])
+    nrm = np.maximum(np.linalg.norm(truth, axis=1), 1e-30)
+    assert (np.abs(g1.astype(np.float64) - g2.astype(np.float64)).max(axis=1) / nrm).max() <= 1e-6
+    assert (np.abs(g1 - truth).max(axis=1) / nrm).max() <= 1e-6
+    # device inputs, dL/dx0 and the per-ball loss terms come out of the fused launch too
+    r, _ = ball_sim._value_and_grad_raw(n_steps / 1000, n_steps, scene, torch.tensor(w["x0"], device="cuda"),
+                                        torch.tensor(w["v0"], device="cuda"), w["target"], w["attractor"], w["constants"],
+                                        ball_sim.RolloutOptions(), True)
+    ref = cref.value_and_grad(n_steps, np.float32((n_steps / 1000) / n_steps), c, w["attractor"], w["target"], w["segments"],
+                              w["x0"], w["v0"])
+    assert_bitexact(r["loss_per_ball"].cpu().numpy(), ref["loss_per_ball"], "per-ball loss")
+    assert np.isfinite(r["grad_x0"].cpu().numpy()).all()
+
+
+def test_fused_value_and_grad_bouncy_regime_and_full_record_area(sim, cref):
+    """Collisions every few steps (contact mode, many collision Jacobians per block) and a record area too small for
+    them (the fused backward then replays those steps from the checkpoints): still the float64 truth to 1e-6."""
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=500)
+    consts = dict(w["constants"]); consts["attractor_strength"] = 2000.0
+    n = 400
+    c = onp.make_constants(consts)
+    truth, _ = cref.grad_truth64(n, np.float32((n / 1000) / n), c, w["attractor"], w["target"], w["segments"], w["x0"], w["v0"])
+    nrm = np.maximum(np.linalg.norm(truth, axis=1), 1e-30)
+    for cap in (0, 700):
+        (_, _), g = ball_sim.vmapped_grad_and_value(n / 1000, n, w["segments"], w["x0"], w["v0"], w["target"], w["attractor"], consts,
+                                                    _opts(ball_sim, hit_capacity=cap))
+        fin = np.isfinite(truth).all(1)
+        assert (np.abs(g[fin] - truth[fin]).max(axis=1) / nrm[fin]).max() <= 1e-6, cap
