@@ -1,6 +1,4 @@
-"""[historical: produced profiles/r2_pipe_ablation.txt; the DOPER_PIPE_ABLATE hooks it needs were removed from
-fwd_pipe.cuh with the experiments — git show 4627623..c9e15bc has them]
-Latency budget of rollout_fwd_pipe_kernel's consumers by ablation (debug builds, results are WRONG by
+"""Latency budget of rollout_fwd_pipe_kernel's consumers by ablation (debug builds, results are WRONG by
 construction — only the kernel time is read): 0 = consumers only meet the barriers, 1 = + loads and cell
 look-ups, 2 = + narrow phase and collisions, 3 = everything (= the product kernel).
     python tools/pipe_ablate.py build      # here
