@@ -105,9 +105,14 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
     constexpr int BPB = THREADS / G;  // balls per block
     constexpr unsigned kLow = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
     const int tid = threadIdx.x, lane = tid % G, gbase = (tid & 31) - lane;
-    const SceneLayout L = scene_layout(1, p.S);
-    const SceneHeader hdr = *reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off);
-    const BakeHeader bh = *reinterpret_cast<const BakeHeader*>(p.scene_ws + L.bake_off);
+    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
+    int64_t ball = (int64_t)blockIdx.x * BPB + tid / G;
+    const bool active = ball < p.B;
+    if (!active) ball = p.B - 1;  // absent ball: reads the last ball's inputs, never advances, writes nothing
+    const int64_t env = p.per_env ? ball : 0;  // per-environment scenes: ball b lives in scene b (baked per scene, read in place)
+    const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off)[env];
+    const unsigned char* gbake = p.scene_ws + L.bake_off + (size_t)env * L.bake_stride;
+    const BakeHeader bh = *reinterpret_cast<const BakeHeader*>(gbake);
 
     SceneView sc;
     BakeView bk;
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
             mbar_expect_tx(bar, qb + rb + bbytes);
             const unsigned char* gq = p.scene_ws + L.q_off;
             const unsigned char* gr = p.scene_ws + L.rl_off;
-            const unsigned char* gb = p.scene_ws + L.bake_off + sizeof(BakeHeader);
+            const unsigned char* gb = gbake + sizeof(BakeHeader);
             for (uint32_t o = 0; o < qb; o += kTmaChunk) tma_load_1d(reinterpret_cast<unsigned char*>(sq) + o, gq + o, min(kTmaChunk, qb - o), bar);
             for (uint32_t o = 0; o < rb; o += kTmaChunk) tma_load_1d(reinterpret_cast<unsigned char*>(srl) + o, gr + o, min(kTmaChunk, rb - o), bar);
             for (uint32_t o = 0; o < bbytes; o += kTmaChunk) tma_load_1d(sbake + o, gb + o, min(kTmaChunk, bbytes - o), bar);
@@ -135,9 +140,9 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
         sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
         mbar_wait(bar, 0);
     } else {
-        sc.q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off);
-        sc.rl = reinterpret_cast<const float*>(p.scene_ws + L.rl_off);
-        bk.cell_start = reinterpret_cast<const uint32_t*>(p.scene_ws + L.bake_off + sizeof(BakeHeader));
+        sc.q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) + env * L.S_pad;
+        sc.rl = reinterpret_cast<const float*>(p.scene_ws + L.rl_off) + env * L.S_pad;
+        bk.cell_start = reinterpret_cast<const uint32_t*>(gbake + sizeof(BakeHeader));
         bk.items = reinterpret_cast<const unsigned short*>(bk.cell_start + (kBakeMaxCells + 16));
         sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
     }
@@ -147,9 +152,6 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
     bk.rho2chk = (kCullRhoCheck * bh.rho) * (kCullRhoCheck * bh.rho);
     bk.ok = bh.enabled && !sc.weird && c.r <= bh.r_max;
 
-    int64_t ball = (int64_t)blockIdx.x * BPB + tid / G;
-    const bool active = ball < p.B;
-    if (!active) ball = p.B - 1;  // absent ball: reads the last ball's inputs, never advances, writes nothing
     const float2 xx = p.x0[ball], vv = p.v0[ball];
     float x = xx.x, y = xx.y, vx = vv.x, vy = vv.y;  // state at step t (uniform within the group)
     const int n = p.n_steps, K = p.K;

@@ -159,6 +159,7 @@ bool use_cull(const doper_rollout_desc* d) {
 constexpr int kBakedOffBits = 1 | kLegacyPlanBits | (1 << 15) | (1 << 16) | (1 << 17) | (1 << 18) | (1 << 20);
 
 bool baked_staged(const doper_rollout_desc* d) {
+    if (d->per_env) return false;  // every ball has its own scene and baked lists: read in place
     const int S_pad = scene_layout(1, d->S).S_pad;
     return (size_t)S_pad * 20 + bake_bytes(S_pad) + 64 <= 96 * 1024;
 }
@@ -190,13 +191,19 @@ int pipe_window(const doper_rollout_desc* d) { return pipe_pinned(d) ? d->lanes_
 
 bool use_baked(const doper_rollout_desc* d) {
     if (use_pipe(d)) return true;  // same lists; the lane = step kernel serves the calls the pipelined one does not (trajectory output)
-    if (!d->per_env && (d->flags & (1 << 21)) && d->lanes_per_ball >= 1 && d->lanes_per_ball <= 16) return true;  // pinned G
-    return !d->per_env && d->lanes_per_ball == 0 && !(d->flags & kBakedOffBits);
+    if ((d->flags & (1 << 21)) && d->lanes_per_ball >= 1 && d->lanes_per_ball <= 16) return true;  // pinned G
+    return d->lanes_per_ball == 0 && !(d->flags & kBakedOffBits);  // shared scenes and, read in place, per-environment scenes
 }
 
 // lanes (= speculated time steps) per ball of the baked kernel: small batches need them to fill the SMs
 int baked_lanes(const doper_rollout_desc* d) {
     if ((d->flags & (1 << 21)) && !pipe_pinned(d)) return d->lanes_per_ball;
+    if (d->per_env) {  // scenes and lists read in place (L2 latency): more speculated steps per ball pay longer
+        if (d->B <= 2048) return 16;   // measured (tools/tune_baked.py c3): 8,192 envs 0.33 ms with 8 lanes, 0.41 with 4;
+        if (d->B <= 16384) return 8;   // 65,536 envs 2.54 ms with 2 lanes, 2.72 with 1
+        if (d->B <= 131072) return 2;
+        return 1;
+    }
     if (d->B <= 1024) return 16;
     if (d->B <= 4096) return 8;
     if (d->B <= 16384) return 4;
@@ -492,9 +499,9 @@ int doper_scene_prepare(doper_stream_t stream, int64_t n_scenes, int32_t S, cons
     scene_prepare_kernel<<<(unsigned)n_scenes, 128, 0, (cudaStream_t)stream>>>(
         n_scenes, S, reinterpret_cast<const float4*>(segments), reinterpret_cast<unsigned char*>(scene_ws));
     if (launch_status() != DOPER_OK) return DOPER_ERR_LAUNCH;
-    if (n_scenes == 1)  // shared scene: bake the per-cell candidate lists (max_radius <= 0 or NaN: marked absent)
-        scene_bake_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(S, max_radius > 0.0f ? max_radius : 0.0f,
-                                                               reinterpret_cast<unsigned char*>(scene_ws));
+    // bake the per-cell candidate lists of every scene (max_radius <= 0 or NaN: marked absent)
+    scene_bake_kernel<<<(unsigned)n_scenes, 256, 0, (cudaStream_t)stream>>>(n_scenes, S, max_radius > 0.0f ? max_radius : 0.0f,
+                                                                           reinterpret_cast<unsigned char*>(scene_ws));
     return launch_status();
 }
 

@@ -18,7 +18,8 @@ struct SceneHeader {  // 16 B per scene
 };
 
 struct SceneLayout {
-    size_t hdr_off, q_off, rl_off, s1_off, grid_off, bake_off, total;  // grid_off / bake_off = 0: none (per-environment scenes)
+    size_t hdr_off, q_off, rl_off, s1_off, grid_off, bake_off, total;  // grid_off = 0: none (per-environment scenes)
+    size_t bake_stride;  // bytes between the baked areas of consecutive scenes
     int bake_cap;  // item capacity of the baked cell lists
     int S_pad;
 };
@@ -69,13 +70,11 @@ __host__ __device__ inline SceneLayout scene_layout(int64_t n_scenes, int S) {
         L.total += sizeof(GridHeader) + (size_t)(kGridMaxCells + 1) * sizeof(int) + (size_t)4 * L.S_pad * sizeof(int);
         L.total = (L.total + 255) / 256 * 256;
     }
-    L.bake_off = 0; L.bake_cap = 0;
-    if (n_scenes == 1) {  // [BakeHeader 64 B | cell_start u32 (kBakeMaxCells + 16) | items u16 (bake_cap)]
-        L.bake_off = L.total;
-        L.bake_cap = kBakeItemsPerSeg * L.S_pad;
-        L.total += bake_bytes(L.S_pad);
-        L.total = (L.total + 255) / 256 * 256;
-    }
+    // per scene: [BakeHeader 64 B | cell_start u32 (kBakeMaxCells + 16) | items u16 (bake_cap)]
+    L.bake_off = L.total;
+    L.bake_cap = kBakeItemsPerSeg * L.S_pad;
+    L.bake_stride = (bake_bytes(L.S_pad) + 255) / 256 * 256;
+    L.total += (size_t)n_scenes * L.bake_stride;
     return L;
 }
 
@@ -222,19 +221,21 @@ __global__ void __launch_bounds__(128) scene_prepare_kernel(int64_t n_scenes, in
     }
 }
 
-// One block.  Segment-driven: each segment visits the cells whose centre can be within `reach` of it
+// One block per scene.  Segment-driven: each segment visits the cells whose centre can be within `reach` of it
 // (its bounding box grown by reach, plus one cell of slack) and applies the list test of sweep.cuh
 // (estimate at the cell centre <= reach, on squares with upward slack); counting sort into CSR; the items
 // of a cell are then sorted ascending so that the layout is deterministic.  If the lists overflow the
 // item capacity the cell size grows by 1.5x and the pass repeats (a single cell always fits).
-__global__ void __launch_bounds__(256) scene_bake_kernel(int S, float r_max, unsigned char* __restrict__ ws) {
-    const SceneLayout L = scene_layout(1, S);
-    const SceneHeader sh = *reinterpret_cast<const SceneHeader*>(ws + L.hdr_off);
-    const float4* q = reinterpret_cast<const float4*>(ws + L.q_off);
-    const float* rl = reinterpret_cast<const float*>(ws + L.rl_off);
-    const float2* e1 = reinterpret_cast<const float2*>(ws + L.s1_off);
-    BakeHeader* bh = reinterpret_cast<BakeHeader*>(ws + L.bake_off);
-    uint32_t* cell_start = reinterpret_cast<uint32_t*>(ws + L.bake_off + sizeof(BakeHeader));
+__global__ void __launch_bounds__(256) scene_bake_kernel(int64_t n_scenes, int S, float r_max, unsigned char* __restrict__ ws) {
+    const SceneLayout L = scene_layout(n_scenes, S);
+    const int64_t scn = blockIdx.x;  // one block per scene
+    const SceneHeader sh = reinterpret_cast<const SceneHeader*>(ws + L.hdr_off)[scn];
+    const float4* q = reinterpret_cast<const float4*>(ws + L.q_off) + scn * L.S_pad;
+    const float* rl = reinterpret_cast<const float*>(ws + L.rl_off) + scn * L.S_pad;
+    const float2* e1 = reinterpret_cast<const float2*>(ws + L.s1_off) + scn * L.S_pad;
+    unsigned char* bake = ws + L.bake_off + (size_t)scn * L.bake_stride;
+    BakeHeader* bh = reinterpret_cast<BakeHeader*>(bake);
+    uint32_t* cell_start = reinterpret_cast<uint32_t*>(bake + sizeof(BakeHeader));
     unsigned short* items = reinterpret_cast<unsigned short*>(cell_start + (kBakeMaxCells + 16));
     __shared__ float s_red[4][256];
     __shared__ int s_cnt[kBakeMaxCells];

@@ -77,7 +77,7 @@ class JaxScene:
         device = device or require_cuda()
         key = (device.type, device.index)
         hit = self._dev.get(key)
-        if hit is not None and (radius is None or self.per_env or (hit[2] is not None and radius <= hit[2])):
+        if hit is not None and (radius is None or (hit[2] is not None and radius <= hit[2])):
             return hit[0], hit[1]
         if hit is None:
             raw = as_f32_device(self.segments, device)
