@@ -160,6 +160,45 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
     int t = active ? 0 : n;
     int T = G;  // speculation length of the next round (1 after a collision at the round's first step)
 
+    if constexpr (G == 1) {
+        // One thread per ball (large batches: the kernel is issue bound there, profiles/r2_ncu_fwd_baked1_c5_before_streamlined_loop.txt): the
+        // same step with nothing warp-wide and nothing recomputed — running log pointer instead of a 64-bit multiply,
+        // a checkpoint counter instead of shift / mask tests, one test for the three trajectory pointers.
+        const bool want_traj = p.traj_x != nullptr || p.traj_v != nullptr || p.traj_a != nullptr;
+        int32_t* hlp = hl;
+        const int64_t hl_step = p.hl_st;
+        int next_ck = p.ckpt ? 0 : n + 1, ck_i = 0;
+        for (; t < n; ++t) {
+            State my;
+            if (!free_step_fast(x, y, vx, vy, c, my)) free_step(x, y, vx, vy, c, my);  // a numerator left the fast division's range
+            int idx = 0;
+            const bool hit = baked_hit(sc, bk, my.x, my.y, c.r, idx);
+            State out = my;
+            int payload = 0;
+            if (hit) {
+                payload = record_collision(p.sink, ball, t, x, y, vx, vy, idx);
+                out = resolve(x, y, vx, vy, my, sc.q[idx], c);
+            }
+            if (hlp) { *hlp = pack_log(payload, hit, clip_bits(vx, vy)); hlp += hl_step; }
+            if (t == next_ck) {
+                p.ckpt[(size_t)ck_i * p.B + ball] = make_float4(x, y, vx, vy);
+                ++ck_i; next_ck += K;
+            }
+            if (want_traj) {
+                const size_t o = (size_t)t * p.B + ball;
+                if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
+                if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
+                if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+            }
+            x = out.x; y = out.y; vx = out.vx; vy = out.vy;
+        }
+        if (active) {
+            p.xT[ball] = make_float2(x, y);
+            p.vT[ball] = make_float2(vx, vy);
+        }
+        return;
+    } else {  // G > 1
+
     while (__any_sync(0xffffffffu, t < n)) {
         // ---- (1) free flight: lane k keeps step t + k ---------------------------------------------------
         const int Tq = t < n ? min(T, n - t) : 0;
@@ -247,6 +286,7 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
         p.xT[ball] = make_float2(x, y);
         p.vT[ball] = make_float2(vx, vy);
     }
+    }  // G > 1
 }
 
 }  // namespace doper

@@ -200,8 +200,7 @@ int baked_lanes(const doper_rollout_desc* d) {
     if ((d->flags & (1 << 21)) && !pipe_pinned(d)) return d->lanes_per_ball;
     if (d->per_env) {  // scenes and lists read in place (L2 latency): more speculated steps per ball pay longer
         if (d->B <= 2048) return 16;   // measured (tools/tune_baked.py c3): 8,192 envs 0.33 ms with 8 lanes, 0.41 with 4;
-        if (d->B <= 16384) return 8;   // 65,536 envs 2.54 ms with 2 lanes, 2.72 with 1
-        if (d->B <= 131072) return 2;
+        if (d->B <= 16384) return 8;   // 65,536 envs 2.50 ms with one thread per ball, 2.70 with 2 lanes
         return 1;
     }
     if (d->B <= 1024) return 16;
