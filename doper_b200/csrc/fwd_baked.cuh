@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
         }
         return;
     } else {  // G > 1
+    const bool want_traj_g = p.traj_x != nullptr || p.traj_v != nullptr || p.traj_a != nullptr;
 
     while (__any_sync(0xffffffffu, t < n)) {
         // ---- (1) free flight: lane k keeps step t + k ---------------------------------------------------
@@ -271,10 +272,12 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
                 const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
                 if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
             }
-            const size_t o = (size_t)ts * p.B + ball;
-            if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
-            if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
-            if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+            if (want_traj_g) {
+                const size_t o = (size_t)ts * p.B + ball;
+                if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
+                if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
+                if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+            }
         }
         if (Tq > 0) { x = nx; y = ny; vx = nvx; vy = nvy; }
         t += n_commit;
