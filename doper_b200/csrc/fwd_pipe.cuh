@@ -8,28 +8,29 @@
 // for both axes in one thread, executed by a warp that has the scheduler almost to itself) plus ~1,500 cycles of
 // cell look-ups, votes, shuffles and log stores that sit between two rounds of the same ball.
 //
-// Here a ball is served by a producer warp and CW consumer warps of a block that never wait for each other inside
-// a window of U steps:
+// Here a block serves 16 balls with one PRODUCER warp and U / 2 CONSUMER warps that never wait for each other inside
+// a window of U steps (U = 16 by default: 9 warps per block):
 //
-//   PRODUCER warp   lane = (ball, axis): 16 balls per warp, the x and the y coordinate of a ball integrated by two
-//                   lanes (the free-flight step acts on each axis separately: physics.cuh axis_step_acc — the
-//                   same operations, hence the same bits).  Nothing but the chain: 24 dependent instructions
-//                   per step, candidate states stored to shared memory as they appear.  It runs AHEAD: window
-//                   k + 1 is integrated from the last candidate of window k, on the assumption that window k
-//                   holds no collision.
-//   CONSUMER warps  lane = (ball, step(s) of the window), 16 U candidates spread over 32 CW lanes: check the
-//                   candidates of window k against the baked cell lists
-//                   (fwd_baked.cuh: same look-up, same narrow phase, same results) while the producer is busy
-//                   with window k + 1, finds the ball's first collision, writes the hit log / checkpoints /
-//                   collision records of the steps before it, resolves the collision (physics.cuh resolve) and
-//                   posts the state after it; the producer restarts that ball two windows later and the
-//                   consumer drops the window that was integrated from the wrong state (epoch tag).
+//   PRODUCER warp   lane = (ball, axis): the x and the y coordinate of a ball integrated by two lanes (the free-flight
+//                   step acts on each axis separately: physics.cuh axis_step_acc — the same operations, hence the
+//                   same bits).  Nothing but the chain: 21 dependent instructions per step (measured 96 cycles),
+//                   candidate states stored to shared memory as they appear.  It runs AHEAD: window k + 1 is
+//                   integrated from the last candidate of window k, on the assumption that window k holds no collision.
+//   CONSUMER warps  lane = (ball, step of the window): 32 / U balls per warp, every candidate of a window has its own
+//                   lane.  While the producer is busy with window k + 1 they check the candidates of window k against
+//                   the baked cell lists (fwd_baked.cuh: same look-up, same narrow phase, same results), find the
+//                   ball's first collision by a ballot, write the hit log / checkpoints / collision record of the
+//                   steps up to it, resolve the collision (physics.cuh resolve; while the very next step collides
+//                   again the resolving lane steps the ball itself: contact mode) and post the state after it to a
+//                   mailbox; the producer restarts that ball two windows later and the consumers drop the window that
+//                   was integrated from the superseded state (epoch tag).
 //
-// One named barrier per pair and window orders the shared-memory traffic (two candidate buffers, two restart
-// mailboxes, all indexed by window parity, so that nothing is read in the interval in which it is written).
-// A collision costs its ball the rest of its window and the next one (~1.5 U steps); collisions are ~0.15 % of
-// the steps of the BASELINE batches.  Every value comes out of the same device functions as in every other
-// forward kernel: results are bit-identical (tests/test_parity_gpu.py runs the same cases over this kernel).
+// One named barrier per window (all warps of the block) orders the shared-memory traffic: two candidate buffers
+// ([ball][step], so that the consumers' lanes read consecutive 16-byte words) and two restart mailboxes, all indexed
+// by window parity, so that nothing is read in the interval in which it is written.  A collision costs its ball the
+// rest of its window and the next one (~1.5 U steps); collisions are ~0.15 % of the steps of the BASELINE batches.
+// Every value comes out of the same device functions as in every other forward kernel: results are bit-identical
+// (tests/test_parity_gpu.py::test_pipelined_*).  Measurements, the ablation and the variants that lost: DESIGN.md §10.
 #pragma once
 #include "bwd.cuh"
 #include "fwd_baked.cuh"
@@ -182,144 +183,144 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
         PIPE_FLUSH(0);
         if (!FUSED) return;
     } else {
-    // -------------------------------------------------------------------------------------- consumers
-    const int cw = warp - 1;
-    constexpr int BPW = 32 / U;                  // balls per consumer warp
-    const int bl = lane / U, j = lane % U;       // my ball within the warp, my step within the window
-    const int b = cw * BPW + bl;                 // my ball within the group
-    const int64_t ball = first + b;
-    const bool active = ball < p.B;
-    SceneView sc;
-    BakeView bk;
-    {
-        const SceneHeader hdr = *reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off);
-        const BakeHeader bh = *reinterpret_cast<const BakeHeader*>(p.scene_ws + L.bake_off);
-        sc.q = reinterpret_cast<const float4*>(smem);
-        sc.rl = reinterpret_cast<const float*>(smem + (size_t)L.S_pad * sizeof(float4));
-        sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
-        bk.cell_start = reinterpret_cast<const uint32_t*>(sbake);
-        bk.items = reinterpret_cast<const unsigned short*>(sbake + (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t));
-        bk.x0 = bh.x0; bk.y0 = bh.y0; bk.h = bh.h; bk.inv_h = bh.inv_h; bk.fnx = bh.fnx; bk.fny = bh.fny; bk.nx = bh.nx;
-        bk.far2 = bh.far2; bk.M = bh.M;
-        bk.rho2chk = (kCullRhoCheck * bh.rho) * (kCullRhoCheck * bh.rho);
-        bk.ok = bh.enabled && !sc.weird && c.r <= bh.r_max;
-    }
-    mbar_wait(bar, 0);
-    const int K = p.K;
-    const int kshift = (K > 0 && (K & (K - 1)) == 0) ? (31 - __clz(K)) : -1;
-    int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
-    int committed = active ? 0 : n;  // steps of my ball that are final (the same value in every lane of the ball)
-    int epoch = 0;
-    bool finished = false;
-    PIPE_T0();
-    for (int k = 0;; ++k) {
-        named_barrier(1, GT);  // B_k
-        const bool done = group_done(k);
-        PIPE_MARK(0);
-        if (done) break;
-        const int buf = k & 1;
+        // -------------------------------------------------------------------------------------- consumers
+        const int cw = warp - 1;
+        constexpr int BPW = 32 / U;                  // balls per consumer warp
+        const int bl = lane / U, j = lane % U;       // my ball within the warp, my step within the window
+        const int b = cw * BPW + bl;                 // my ball within the group
+        const int64_t ball = first + b;
+        const bool active = ball < p.B;
+        SceneView sc;
+        BakeView bk;
+        {
+            const SceneHeader hdr = *reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off);
+            const BakeHeader bh = *reinterpret_cast<const BakeHeader*>(p.scene_ws + L.bake_off);
+            sc.q = reinterpret_cast<const float4*>(smem);
+            sc.rl = reinterpret_cast<const float*>(smem + (size_t)L.S_pad * sizeof(float4));
+            sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
+            bk.cell_start = reinterpret_cast<const uint32_t*>(sbake);
+            bk.items = reinterpret_cast<const unsigned short*>(sbake + (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t));
+            bk.x0 = bh.x0; bk.y0 = bh.y0; bk.h = bh.h; bk.inv_h = bh.inv_h; bk.fnx = bh.fnx; bk.fny = bh.fny; bk.nx = bh.nx;
+            bk.far2 = bh.far2; bk.M = bh.M;
+            bk.rho2chk = (kCullRhoCheck * bh.rho) * (kCullRhoCheck * bh.rho);
+            bk.ok = bh.enabled && !sc.weird && c.r <= bh.r_max;
+        }
+        mbar_wait(bar, 0);
+        const int K = p.K;
+        const int kshift = (K > 0 && (K & (K - 1)) == 0) ? (31 - __clz(K)) : -1;
+        int32_t* hl = p.hitlog ? p.hitlog + ball * p.hl_sb : nullptr;
+        int committed = active ? 0 : n;  // steps of my ball that are final (the same value in every lane of the ball)
+        int epoch = 0;
+        bool finished = false;
+        PIPE_T0();
+        for (int k = 0;; ++k) {
+            named_barrier(1, GT);  // B_k
+            const bool done = group_done(k);
+            PIPE_MARK(0);
+            if (done) break;
+            const int buf = k & 1;
 #if defined(DOPER_PIPE_ABLATE) && DOPER_PIPE_ABLATE == 0
-        if (k >= (n + U - 1) / U) { finished = true; if (lane == 0) sh.fin_at[cw] = k + 1; }  // timing experiment: barriers only
-        continue;
+            if (k >= (n + U - 1) / U) { finished = true; if (lane == 0) sh.fin_at[cw] = k + 1; }  // timing experiment: barriers only
+            continue;
 #endif
-        const int ts0 = sh.t_start[buf][b];
-        const bool fresh = committed < n && sh.epoch_w[buf][b] == epoch;  // else: integrated from a superseded state
-        const int nv = fresh ? min(U, n - ts0) : 0;                       // steps of the window that exist
-        const float4 s = sh.slot[buf][b][j], cand = sh.slot[buf][b][j + 1];  // start state and candidate of my step
-        // (1) my candidate against the baked lists
-        int idx = 0, k0 = 0, k1 = 0;
-        const int kind = j < nv ? baked_cell(bk, cand.x, cand.z, k0, k1) : 0;
-        PIPE_MARK(1);
-        bool myhit = false;
+            const int ts0 = sh.t_start[buf][b];
+            const bool fresh = committed < n && sh.epoch_w[buf][b] == epoch;  // else: integrated from a superseded state
+            const int nv = fresh ? min(U, n - ts0) : 0;                       // steps of the window that exist
+            const float4 s = sh.slot[buf][b][j], cand = sh.slot[buf][b][j + 1];  // start state and candidate of my step
+            // (1) my candidate against the baked lists
+            int idx = 0, k0 = 0, k1 = 0;
+            const int kind = j < nv ? baked_cell(bk, cand.x, cand.z, k0, k1) : 0;
+            PIPE_MARK(1);
+            bool myhit = false;
 #if defined(DOPER_PIPE_ABLATE) && DOPER_PIPE_ABLATE == 1
-        if (kind == 77) myhit = true;  // timing experiment: no narrow phase
+            if (kind == 77) myhit = true;  // timing experiment: no narrow phase
 #else
-        if (kind != 0) myhit = baked_list_hit(sc, bk, cand.x, cand.z, c.r, kind, k0, k1, idx);
+            if (kind != 0) myhit = baked_list_hit(sc, bk, cand.x, cand.z, c.r, kind, k0, k1, idx);
 #endif
 #ifdef DOPER_PIPE_TIMERS
-        __syncwarp();
-        { const long long pt_now = clock64(); const long long d = pt_now - pt_last; pt_acc[4] += d; pt_last = pt_now;
-          if (__any_sync(0xffffffffu, kind != 0)) pt_acc[5] += 1;
-          if (d > 1000) pt_acc[6] += 1; }
+            __syncwarp();
+            { const long long pt_now = clock64(); const long long d = pt_now - pt_last; pt_acc[4] += d; pt_last = pt_now;
+              if (__any_sync(0xffffffffu, kind != 0)) pt_acc[5] += 1;
+              if (d > 1000) pt_acc[6] += 1; }
 #endif
-        // (2) the ball's first collision in the window
-        const unsigned hm = (__ballot_sync(0xffffffffu, myhit) >> (bl * U)) & kSeg;
-        const int f = hm ? (__ffs(hm) - 1) : U;
-        const bool hit = f < nv;
-        const int n_commit = hit ? f + 1 : nv;
-        State r;
-        r.x = r.y = r.vx = r.vy = r.ax = r.ay = 0.0f;
-        int payload = 0, extra = 0;
-        if (hit && j == f) {  // my step: resolve it, post the state after it
-            State s1;
-            free_step(s.x, s.z, s.y, s.w, c, s1);  // the candidate again, with its acceleration (resolve needs it)
-            payload = record_collision(p.sink, ball, ts0 + f, s.x, s.z, s.y, s.w, idx);  // first: the atomic's round trip overlaps the resolve
-            r = resolve(s.x, s.z, s.y, s.w, s1, sc.q[idx], c);
-            // Contact mode: while the very next step collides again (resting / sliding contact, a bounce in a corner),
-            // this lane steps the ball itself — a restart through the producer costs ~1.5 windows per collision.  At
-            // most U steps per window, so that the other balls of the group keep moving.
-            State cur = r;
-            int tn = ts0 + f + 1;
-            // the log word of a contact step needs the slot that record_collision's atomic returns (~1 us round trip
-            // to L2): it is written one iteration later, so that the next step's arithmetic hides the latency
-            int pend_t = -1, pend_pl = 0;
-            uint32_t pend_clip = 0u;
-            while (extra < U && tn < n) {
-                State c1;
-                free_step(cur.x, cur.y, cur.vx, cur.vy, c, c1);
-                int i2;
-                if (!baked_hit(sc, bk, c1.x, c1.y, c.r, i2)) break;  // free flight again: the producer takes over from `cur`
-                const int pl = record_collision(p.sink, ball, tn, cur.x, cur.y, cur.vx, cur.vy, i2);
-                if (p.ckpt) {
-                    const bool at = kshift >= 0 ? (tn & (K - 1)) == 0 : (tn % K) == 0;
-                    if (at) p.ckpt[(size_t)(kshift >= 0 ? tn >> kshift : tn / K) * p.B + ball] = make_float4(cur.x, cur.y, cur.vx, cur.vy);
+            // (2) the ball's first collision in the window
+            const unsigned hm = (__ballot_sync(0xffffffffu, myhit) >> (bl * U)) & kSeg;
+            const int f = hm ? (__ffs(hm) - 1) : U;
+            const bool hit = f < nv;
+            const int n_commit = hit ? f + 1 : nv;
+            State r;
+            r.x = r.y = r.vx = r.vy = r.ax = r.ay = 0.0f;
+            int payload = 0, extra = 0;
+            if (hit && j == f) {  // my step: resolve it, post the state after it
+                State s1;
+                free_step(s.x, s.z, s.y, s.w, c, s1);  // the candidate again, with its acceleration (resolve needs it)
+                payload = record_collision(p.sink, ball, ts0 + f, s.x, s.z, s.y, s.w, idx);  // first: the atomic's round trip overlaps the resolve
+                r = resolve(s.x, s.z, s.y, s.w, s1, sc.q[idx], c);
+                // Contact mode: while the very next step collides again (resting / sliding contact, a bounce in a corner),
+                // this lane steps the ball itself — a restart through the producer costs ~1.5 windows per collision.  At
+                // most U steps per window, so that the other balls of the group keep moving.
+                State cur = r;
+                int tn = ts0 + f + 1;
+                // the log word of a contact step needs the slot that record_collision's atomic returns (~1 us round trip
+                // to L2): it is written one iteration later, so that the next step's arithmetic hides the latency
+                int pend_t = -1, pend_pl = 0;
+                uint32_t pend_clip = 0u;
+                while (extra < U && tn < n) {
+                    State c1;
+                    free_step(cur.x, cur.y, cur.vx, cur.vy, c, c1);
+                    int i2;
+                    if (!baked_hit(sc, bk, c1.x, c1.y, c.r, i2)) break;  // free flight again: the producer takes over from `cur`
+                    const int pl = record_collision(p.sink, ball, tn, cur.x, cur.y, cur.vx, cur.vy, i2);
+                    if (p.ckpt) {
+                        const bool at = kshift >= 0 ? (tn & (K - 1)) == 0 : (tn % K) == 0;
+                        if (at) p.ckpt[(size_t)(kshift >= 0 ? tn >> kshift : tn / K) * p.B + ball] = make_float4(cur.x, cur.y, cur.vx, cur.vy);
+                    }
+                    const uint32_t clip = clip_bits(cur.vx, cur.vy);
+                    const State r2 = resolve(cur.x, cur.y, cur.vx, cur.vy, c1, sc.q[i2], c);
+                    if (hl && pend_t >= 0) hl[(int64_t)pend_t * p.hl_st] = pack_log(pend_pl, true, pend_clip);
+                    pend_t = tn; pend_pl = pl; pend_clip = clip;
+                    cur = r2;
+                    ++tn; ++extra;
                 }
-                const uint32_t clip = clip_bits(cur.vx, cur.vy);
-                const State r2 = resolve(cur.x, cur.y, cur.vx, cur.vy, c1, sc.q[i2], c);
                 if (hl && pend_t >= 0) hl[(int64_t)pend_t * p.hl_st] = pack_log(pend_pl, true, pend_clip);
-                pend_t = tn; pend_pl = pl; pend_clip = clip;
-                cur = r2;
-                ++tn; ++extra;
+                if (extra > 0 && tn == n) { p.xT[ball] = make_float2(cur.x, cur.y); p.vT[ball] = make_float2(cur.vx, cur.vy); }
+                sh.mail_state[buf][b] = make_float4(cur.x, cur.vx, cur.y, cur.vy);
+                sh.mail_t[buf][b] = tn;
+                sh.mail_epoch[buf][b] = epoch + 1;
             }
-            if (hl && pend_t >= 0) hl[(int64_t)pend_t * p.hl_st] = pack_log(pend_pl, true, pend_clip);
-            if (extra > 0 && tn == n) { p.xT[ball] = make_float2(cur.x, cur.y); p.vT[ball] = make_float2(cur.vx, cur.vy); }
-            sh.mail_state[buf][b] = make_float4(cur.x, cur.vx, cur.y, cur.vy);
-            sh.mail_t[buf][b] = tn;
-            sh.mail_epoch[buf][b] = epoch + 1;
-        }
-        extra = __shfl_sync(0xffffffffu, extra, bl * U + (hit ? f : 0));  // steps the contact loop committed for my ball
-        if (!hit) extra = 0;
-        PIPE_MARK(2);
-        // (3) commit my step if it lies before the collision or is the collided one
+            extra = __shfl_sync(0xffffffffu, extra, bl * U + (hit ? f : 0));  // steps the contact loop committed for my ball
+            if (!hit) extra = 0;
+            PIPE_MARK(2);
+            // (3) commit my step if it lies before the collision or is the collided one
 #if defined(DOPER_PIPE_ABLATE) && DOPER_PIPE_ABLATE <= 2
-        if (j < n_commit && ts0 + j + 1 == n) {  // timing experiment: no log / checkpoint stores
+            if (j < n_commit && ts0 + j + 1 == n) {  // timing experiment: no log / checkpoint stores
 #else
-        if (j < n_commit) {
+            if (j < n_commit) {
 #endif
-            const int ts = ts0 + j;
-            const bool h = hit && j == f;
-            if (hl) hl[(int64_t)ts * p.hl_st] = pack_log(h ? payload : 0, h, clip_bits(s.y, s.w));
-            if (p.ckpt) {
-                const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
-                if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(s.x, s.z, s.y, s.w);
+                const int ts = ts0 + j;
+                const bool h = hit && j == f;
+                if (hl) hl[(int64_t)ts * p.hl_st] = pack_log(h ? payload : 0, h, clip_bits(s.y, s.w));
+                if (p.ckpt) {
+                    const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
+                    if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(s.x, s.z, s.y, s.w);
+                }
+                if (ts + 1 == n) {  // the rollout's last step: final state
+                    if (h) { p.xT[ball] = make_float2(r.x, r.y); p.vT[ball] = make_float2(r.vx, r.vy); }
+                    else { p.xT[ball] = make_float2(cand.x, cand.z); p.vT[ball] = make_float2(cand.y, cand.w); }
+                }
             }
-            if (ts + 1 == n) {  // the rollout's last step: final state
-                if (h) { p.xT[ball] = make_float2(r.x, r.y); p.vT[ball] = make_float2(r.vx, r.vy); }
-                else { p.xT[ball] = make_float2(cand.x, cand.z); p.vT[ball] = make_float2(cand.y, cand.w); }
+            if (fresh) committed = ts0 + n_commit + extra;
+            if (hit) ++epoch;
+            if (!finished) {
+                finished = __all_sync(0xffffffffu, committed >= n);
+                if (finished && lane == 0) sh.fin_at[cw] = k + 1;
             }
-        }
-        if (fresh) committed = ts0 + n_commit + extra;
-        if (hit) ++epoch;
-        if (!finished) {
-            finished = __all_sync(0xffffffffu, committed >= n);
-            if (finished && lane == 0) sh.fin_at[cw] = k + 1;
-        }
-        PIPE_MARK(3);
+            PIPE_MARK(3);
 #ifdef DOPER_PIPE_TIMERS
-        pt_acc[7] += 1;
+            pt_acc[7] += 1;
 #endif
-    }
-    PIPE_FLUSH(8);
+        }
+        PIPE_FLUSH(8);
     }  // consumers
     if (!FUSED) return;
 
