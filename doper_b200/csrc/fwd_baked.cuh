@@ -27,12 +27,31 @@ namespace doper {
 
 struct BakeView {
     const uint32_t* cell_start;
+    const unsigned long long* fine;  // one bit per sub-cell: its disc's hit list is not empty (scene.cuh)
     const unsigned short* items;
+    float fsub;   // sub-cells per cell edge (1, 2, 4 or 8)
+    int fshift;
     float x0, y0, h, inv_h, fnx, fny, far2;
     float rho2chk;  // (0.98 rho)^2: a cell's list is valid for every point this close to the cell centre
     float M;        // bound on |coordinate| of the scene and of every point within rho of a cell centre
     int nx, ok;
 };
+
+// the arrays behind a BakeHeader (in shared memory when staged, else in place)
+__device__ __forceinline__ void bake_view_arrays(BakeView& bk, const unsigned char* arrays) {
+    bk.cell_start = reinterpret_cast<const uint32_t*>(arrays);
+    bk.fine = reinterpret_cast<const unsigned long long*>(arrays + kBakeFineOff);
+    bk.items = reinterpret_cast<const unsigned short*>(arrays + kBakeItemsOff);
+}
+
+__device__ __forceinline__ void bake_view_header(BakeView& bk, const BakeHeader& bh, int weird, float r) {
+    bk.x0 = bh.x0; bk.y0 = bh.y0; bk.h = bh.h; bk.inv_h = bh.inv_h; bk.fnx = bh.fnx; bk.fny = bh.fny; bk.nx = bh.nx;
+    bk.far2 = bh.far2; bk.M = bh.M;
+    bk.rho2chk = (kCullRhoCheck * bh.rho) * (kCullRhoCheck * bh.rho);
+    bk.ok = bh.enabled && !weird && r <= bh.r_max;
+    bk.fshift = bh.fine_shift;
+    bk.fsub = (float)(1 << bh.fine_shift);
+}
 
 // (hit, idx) of ONE point against the baked lists; reference semantics: hit = (min_j d_ref_j <= r), idx = its
 // first index (valid only when hit).  One pass over the cell's list: an entry whose estimate^2 exceeds far2
@@ -50,7 +69,11 @@ __device__ __forceinline__ int baked_cell(const BakeView& bk, float px, float py
     // r_max + h - (rounding of the look-up), and at least |p| / 2 once |p| > 2 M; d_ref >= D - 38 u max(M, |p|) > r.
     const float fx = (px - bk.x0) * bk.inv_h, fy = (py - bk.y0) * bk.inv_h;
     if (!(fx >= 0.0f && fx < bk.fnx && fy >= 0.0f && fy < bk.fny)) return 0;
-    const int cell = (int)fy * bk.nx + (int)fx;
+    // sub-cell first (fx * fsub is exact): a clear bit = no segment within r_max of any point of the sub-cell
+    const int jx = (int)(fx * bk.fsub), jy = (int)(fy * bk.fsub), sm = (1 << bk.fshift) - 1;
+    const int cell = (jy >> bk.fshift) * bk.nx + (jx >> bk.fshift);
+    const int bit = ((jy & sm) << bk.fshift) | (jx & sm);
+    if (!((bk.fine[cell] >> bit) & 1ull)) return 0;
     k0 = (int)bk.cell_start[cell];
     k1 = (int)bk.cell_start[cell + 1];
     return k1 > k0 ? 1 : 0;
@@ -99,10 +122,13 @@ __device__ __forceinline__ bool baked_hit(const SceneView& sc, const BakeView& b
     return baked_list_hit(sc, bk, px, py, r, kind, k0, k1, idx);
 }
 
-template <int G, bool STAGED, int THREADS>
-__global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdParams p) {
+// MAXT bounds the block size (register budget); the launcher picks blockDim.x = 32 w with w = the warps ONE SM gets
+// when the batch is spread evenly over the SMs (kernels.cu balanced_block): the kernel is a latency chain per warp,
+// so its duration is set by the SM with the most resident warps, and a second partial wave doubles it.
+template <int G, bool STAGED, int MAXT>
+__global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int BPB = THREADS / G;  // balls per block
+    const int BPB = (int)blockDim.x / G;  // balls per block
     constexpr unsigned kLow = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
     const int tid = threadIdx.x, lane = tid % G, gbase = (tid & 31) - lane;
     const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
@@ -135,22 +161,17 @@ __global__ void __launch_bounds__(THREADS) rollout_fwd_baked_kernel(const FwdPar
             for (uint32_t o = 0; o < bbytes; o += kTmaChunk) tma_load_1d(sbake + o, gb + o, min(kTmaChunk, bbytes - o), bar);
         }
         sc.q = sq; sc.rl = srl;
-        bk.cell_start = reinterpret_cast<const uint32_t*>(sbake);
-        bk.items = reinterpret_cast<const unsigned short*>(sbake + (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t));
+        bake_view_arrays(bk, sbake);
         sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
         mbar_wait(bar, 0);
     } else {
         sc.q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) + env * L.S_pad;
         sc.rl = reinterpret_cast<const float*>(p.scene_ws + L.rl_off) + env * L.S_pad;
-        bk.cell_start = reinterpret_cast<const uint32_t*>(gbake + sizeof(BakeHeader));
-        bk.items = reinterpret_cast<const unsigned short*>(bk.cell_start + (kBakeMaxCells + 16));
+        bake_view_arrays(bk, gbake + sizeof(BakeHeader));
         sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
     }
     const Consts c = p.c;
-    bk.x0 = bh.x0; bk.y0 = bh.y0; bk.h = bh.h; bk.inv_h = bh.inv_h; bk.fnx = bh.fnx; bk.fny = bh.fny; bk.nx = bh.nx;
-    bk.far2 = bh.far2; bk.M = bh.M;
-    bk.rho2chk = (kCullRhoCheck * bh.rho) * (kCullRhoCheck * bh.rho);
-    bk.ok = bh.enabled && !sc.weird && c.r <= bh.r_max;
+    bake_view_header(bk, bh, sc.weird, c.r);
 
     const float2 xx = p.x0[ball], vv = p.v0[ball];
     float x = xx.x, y = xx.y, vx = vv.x, vy = vv.y;  // state at step t (uniform within the group)

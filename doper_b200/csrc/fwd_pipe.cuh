@@ -198,12 +198,8 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
             sc.q = reinterpret_cast<const float4*>(smem);
             sc.rl = reinterpret_cast<const float*>(smem + (size_t)L.S_pad * sizeof(float4));
             sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
-            bk.cell_start = reinterpret_cast<const uint32_t*>(sbake);
-            bk.items = reinterpret_cast<const unsigned short*>(sbake + (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t));
-            bk.x0 = bh.x0; bk.y0 = bh.y0; bk.h = bh.h; bk.inv_h = bh.inv_h; bk.fnx = bh.fnx; bk.fny = bh.fny; bk.nx = bh.nx;
-            bk.far2 = bh.far2; bk.M = bh.M;
-            bk.rho2chk = (kCullRhoCheck * bh.rho) * (kCullRhoCheck * bh.rho);
-            bk.ok = bh.enabled && !sc.weird && c.r <= bh.r_max;
+            bake_view_arrays(bk, sbake);
+            bake_view_header(bk, bh, sc.weird, c.r);
         }
         mbar_wait(bar, 0);
         const int K = p.K;
@@ -345,7 +341,8 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
     const int64_t fb = first + bb;
     const int t0 = chunk * chunk_len, t1 = min(n, t0 + chunk_len);
     const bool mine = tid < 16 * NC && fb < p.B && t0 < t1;
-    if (tid == 0) jl_count = 0;
+    __shared__ double t16[8];
+    if (tid == 0) { jl_count = 0; free_pow_table(cd, t16); }
     named_barrier(1, GT);
     if (p.jac != nullptr && mine) {
         const int32_t* hlb = p.hitlog + (size_t)fb * p.hl_sb;
@@ -381,7 +378,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
         for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0 : 0.0;
-        if (mine) chunk_product(bp, cd, fb, t0, t1, g);
+        if (mine) chunk_product(bp, cd, fb, t0, t1, g, t16);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll

@@ -19,6 +19,7 @@
 //   controller.cuh the trainer's glue: controller MLP forward / backward, gradient clip + Adam (three kernels)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -161,7 +162,7 @@ constexpr int kBakedOffBits = 1 | kLegacyPlanBits | (1 << 15) | (1 << 16) | (1 <
 bool baked_staged(const doper_rollout_desc* d) {
     if (d->per_env) return false;  // every ball has its own scene and baked lists: read in place
     const int S_pad = scene_layout(1, d->S).S_pad;
-    return (size_t)S_pad * 20 + bake_bytes(S_pad) + 64 <= 96 * 1024;
+    return (size_t)S_pad * 20 + bake_bytes(S_pad) + 64 <= 128 * 1024;  // 32 KB of it are the sub-cell masks
 }
 
 // Pipelined kernel (fwd_pipe.cuh: producer / consumer warp pairs over the baked lists): the default of shared
@@ -368,21 +369,50 @@ int launch_fwd_tpc(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
     return run(std::integral_constant<int, 128>{});
 }
 
+// Block size of the one-wave kernels whose warps are independent latency chains (baked forward, G <= 4): the kernel
+// lasts as long as the SM with the most resident warps, so the batch's warps are dealt out evenly — w = ceil(warps /
+// (SMs x waves)) warps per block, one block per SM and wave — instead of fixed 128-thread blocks (131,072 balls = 1,024
+// blocks against 6 resident per SM by shared memory: a second wave of 136 blocks; 65,536 threads = 512 blocks: 4 on
+// some SMs, 3 on others).  `fits(threads)` = resident blocks per SM at that size.  DOPER_BAKED_THREADS pins the size
+// (tuning: tools/tune_block.py).
+template <class Fits>
+int balanced_block(int64_t threads_total, int max_threads, Fits fits) {
+    const char* const env = getenv("DOPER_BAKED_THREADS");
+    const int pinned = env ? atoi(env) : 0;
+    if (pinned >= 32 && pinned <= max_threads && pinned % 32 == 0) return pinned;
+    const int64_t warps = (threads_total + 31) / 32, sms = sm_count();
+    int cap = max_threads / 32;  // warps one SM holds in ONE block of this kernel
+    while (cap > 1 && fits(32 * cap) < 1) --cap;
+    int resident = cap * fits(32 * cap);  // warps one SM holds in blocks of the largest size
+    if (resident > 64) resident = 64;
+    const int64_t waves = (warps + sms * resident - 1) / (sms * resident);
+    const int per_sm = (int)((warps + sms * waves - 1) / (sms * waves));  // warps per SM and wave, dealt evenly
+    const int blocks = (per_sm + cap - 1) / cap;                           // ... in this many equal blocks
+    const int w = (per_sm + blocks - 1) / blocks;
+    return 32 * (w < 1 ? 1 : w);
+}
+
 template <int G>
 int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
-    constexpr int THREADS = G >= 8 ? 64 : 128;
+    constexpr int MAXT = 256;
+    constexpr int MAXT_STAGED = G == 1 ? 1024 : MAXT;  // one thread per ball, staged scene: 64 registers, up to 32 warps in one block
     const int S_pad = scene_layout(1, p.S).S_pad;
     const size_t smem = staged ? (size_t)S_pad * 20 + (bake_bytes(S_pad) - sizeof(BakeHeader)) + 16 : 0;
-    const int bpb = THREADS / G;
-    const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
     auto go = [&](auto kernel) {
         if (smem > 48 * 1024 &&
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return (int)DOPER_ERR_SMEM_LIMIT;
-        kernel<<<grid, THREADS, smem, st>>>(p);
+        const int max_threads = staged ? MAXT_STAGED : MAXT;
+        const int threads = balanced_block(p.B * G, max_threads, [&](int t) {
+            int nb = 0;
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, t, smem) == cudaSuccess ? nb : 0;
+        });
+        const int bpb = threads / G;
+        const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
+        kernel<<<grid, threads, smem, st>>>(p);
         return launch_status();
     };
-    return staged ? go(rollout_fwd_baked_kernel<G, true, THREADS>) : go(rollout_fwd_baked_kernel<G, false, THREADS>);
+    return staged ? go(rollout_fwd_baked_kernel<G, true, MAXT_STAGED>) : go(rollout_fwd_baked_kernel<G, false, MAXT>);
 }
 
 template <int U, bool FUSED>

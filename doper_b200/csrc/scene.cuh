@@ -35,6 +35,16 @@ struct SceneLayout {
 // once per (scene, r_max) by scene_bake_kernel; read by rollout_fwd_baked_kernel.
 constexpr int kBakeMaxCells = 4096;
 constexpr int kBakeItemsPerSeg = 32;
+// Second level (round 2): every cell is cut into 2^s x 2^s sub-cells (s = fine_shift <= 3) and keeps ONE BIT per
+// sub-cell — "the hit list of this sub-cell's circumscribed disc is empty / is not".  A cell of the seeded maps is
+// ~5 ball radii wide, so 14 % of the points a rollout visits fall in a cell with a list and practically every warp
+// step walks one (some lane of 32 does); at an eighth of the cell size 1.8 % of the points do, and the list of the
+// (coarse) cell is only read for those.  Same proof as for the cells themselves with rho_f = sub-cell half diagonal
+// / 0.98: a clear bit proves "no collision" for every point that falls in the sub-cell.
+constexpr int kBakeFineShiftMax = 3;
+// byte offsets of the arrays behind the BakeHeader
+constexpr size_t kBakeFineOff = (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t);
+constexpr size_t kBakeItemsOff = kBakeFineOff + (size_t)kBakeMaxCells * sizeof(unsigned long long);
 
 struct BakeHeader {  // 64 B
     float x0, y0, h, inv_h;   // cell (ix, iy) = [x0 + ix h, x0 + (ix + 1) h) x ...
@@ -44,11 +54,12 @@ struct BakeHeader {  // 64 B
     float far2;    // cull_far2(r_max, M): estimates^2 above it prove "no collision"
     float rho;     // radius of the disc a cell list was built for
     float fnx, fny;  // (float)nx, (float)ny
-    int pad[2];
+    int fine_shift;  // sub-cells per cell edge = 1 << fine_shift (0: no second level, every mask is all ones)
+    int pad;
 };
 
 __host__ __device__ inline size_t bake_bytes(int S_pad) {
-    size_t b = sizeof(BakeHeader) + (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t) + (size_t)kBakeItemsPerSeg * S_pad * sizeof(unsigned short);
+    size_t b = sizeof(BakeHeader) + kBakeItemsOff + (size_t)kBakeItemsPerSeg * S_pad * sizeof(unsigned short);
     return (b + 15) / 16 * 16;
 }
 
@@ -70,7 +81,7 @@ __host__ __device__ inline SceneLayout scene_layout(int64_t n_scenes, int S) {
         L.total += sizeof(GridHeader) + (size_t)(kGridMaxCells + 1) * sizeof(int) + (size_t)4 * L.S_pad * sizeof(int);
         L.total = (L.total + 255) / 256 * 256;
     }
-    // per scene: [BakeHeader 64 B | cell_start u32 (kBakeMaxCells + 16) | items u16 (bake_cap)]
+    // per scene: [BakeHeader 64 B | cell_start u32 (kBakeMaxCells + 16) | sub-cell masks u64 (kBakeMaxCells) | items u16 (bake_cap)]
     L.bake_off = L.total;
     L.bake_cap = kBakeItemsPerSeg * L.S_pad;
     L.bake_stride = (bake_bytes(L.S_pad) + 255) / 256 * 256;
@@ -236,7 +247,8 @@ __global__ void __launch_bounds__(256) scene_bake_kernel(int64_t n_scenes, int S
     unsigned char* bake = ws + L.bake_off + (size_t)scn * L.bake_stride;
     BakeHeader* bh = reinterpret_cast<BakeHeader*>(bake);
     uint32_t* cell_start = reinterpret_cast<uint32_t*>(bake + sizeof(BakeHeader));
-    unsigned short* items = reinterpret_cast<unsigned short*>(cell_start + (kBakeMaxCells + 16));
+    unsigned long long* fine = reinterpret_cast<unsigned long long*>(bake + sizeof(BakeHeader) + kBakeFineOff);
+    unsigned short* items = reinterpret_cast<unsigned short*>(bake + sizeof(BakeHeader) + kBakeItemsOff);
     __shared__ float s_red[4][256];
     __shared__ int s_cnt[kBakeMaxCells];
     __shared__ int s_tot;
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(256) scene_bake_kernel(int64_t n_scenes, int S
             for (int k = 0; k < 4; ++k) s_red[k][0] = fminf(s_red[k][0], s_red[k][i]);
         BakeHeader b;
         b.enabled = 0; b.nx = b.ny = 1; b.n_items = 0; b.r_max = r_max; b.x0 = b.y0 = 0.f; b.h = b.inv_h = 1.f;
-        b.M = sh.scale; b.far2 = 0.f; b.rho = 0.f; b.fnx = b.fny = 1.f; b.pad[0] = b.pad[1] = 0;
+        b.M = sh.scale; b.far2 = 0.f; b.rho = 0.f; b.fnx = b.fny = 1.f; b.fine_shift = 0; b.pad = 0;
         const float W = -s_red[2][0] - s_red[0][0], H = -s_red[3][0] - s_red[1][0];
         const bool ok = !sh.weird && r_max > 0.0f && r_max <= 1.0e15f && W >= 0.0f && H >= 0.0f && W <= 1.0e15f && H <= 1.0e15f &&
                         S <= 65535;
@@ -358,7 +370,41 @@ __global__ void __launch_bounds__(256) scene_bake_kernel(int64_t n_scenes, int S
                     items[m + 1] = v;
                 }
             }
-            if (tid == 0) { BakeHeader out = s_b; out.n_items = s_tot; *bh = out; }
+            // second level: one bit per sub-cell.  Sub-cells no finer than 2^-10 of the coordinate scale (as for the
+            // cells: the look-up's rounding stays far inside the 2 % slack of rho_f).  A segment on the hit list of a
+            // sub-cell's disc is on the list of its cell: centre to centre is at most hd - hd_f (half diagonals), so
+            // its estimate at the cell centre is below r_max + rho_f + (hd - hd_f) + safe M + 2 err, and
+            // rho - rho_f - (hd - hd_f) = 0.0204 (hd - hd_f) >= 1e-5 M is far above the estimate's error (err ~
+            // 40 ulp of M).  Only the cell's own list is therefore tested, sub-cell by sub-cell.
+            int fs = kBakeFineShiftMax;
+            while (fs > 0 && b.h / (float)(1 << fs) < fmaxf(sh.scale, r_max) * 0.0009765625f) --fs;
+            const int nsub = 1 << fs;
+            const float hf = b.h / (float)nsub;  // exact: a power of two
+            const float rho_f = (hf * 0.70710678f) * (1.0f / kCullRhoCheck) * 1.0001f;
+            const float reach_f = __fmaf_rn(kCullSafePerM, b.M, rho_f + r_max) * kCullUp;
+            const float T_f = (reach_f * reach_f) * kCullUp;
+            for (int c = tid; c < kBakeMaxCells; c += blockDim.x) {
+                unsigned long long mask = 0ull;
+                if (fs == 0) {
+                    mask = ~0ull;
+                } else if (c < ncell) {
+                    const int k0 = (int)cell_start[c], k1 = (int)cell_start[c + 1];
+                    const int cx = c % b.nx, cy = c / b.nx;
+                    for (int k = k0; k < k1; ++k) {
+                        const int i = items[k];
+                        const float4 a = q[i];
+                        const float r1 = rl[i];
+                        for (int sy = 0; sy < nsub; ++sy)
+                            for (int sx = 0; sx < nsub; ++sx) {
+                                const float ccx = __fmaf_rn((float)(cx * nsub + sx) + 0.5f, hf, b.x0);
+                                const float ccy = __fmaf_rn((float)(cy * nsub + sy) + 0.5f, hf, b.y0);
+                                if (approx_d2(ccx, ccy, a, r1) <= T_f) mask |= 1ull << ((sy << fs) | sx);
+                            }
+                    }
+                }
+                fine[c] = mask;
+            }
+            if (tid == 0) { BakeHeader out = s_b; out.n_items = s_tot; out.fine_shift = fs; *bh = out; }
             return;
         }
     }
