@@ -165,8 +165,10 @@ __device__ __forceinline__ double sgn_d(double a) { return a > 0.0 ? 1.0 : (a < 
 // step that collided with the segment s0 = (q.x, q.y) -> s1, starting from the fp32 state st.  The formulas of
 // oracle/ball_sim_step.inc:step_vjp in binary64, the segment direction included
 // (s1 - s0 in binary64, like oracle_grad_truth64); column k = the pull-back of e_k.
+// Columns [col0, col1) only: the four columns are independent given the step's forward internals, so four
+// threads can share one collided step (each recomputes the internals and pulls ONE basis cotangent back).
 __device__ __noinline__ void hit_jacobian_d(const float4 st, const float4 q, const float2 s1, const ConstsD c,
-                                            double* __restrict__ Jt) {
+                                            double* __restrict__ Jt, const int col0 = 0, const int col1 = 4) {
     const double x = st.x, y = st.y, vx = st.z, vy = st.w;
     const double s0x = q.x, s0y = q.y, svx = (double)s1.x - (double)q.x, svy = (double)s1.y - (double)q.y;
     const double L = svx * svx + svy * svy;
@@ -201,8 +203,12 @@ __device__ __noinline__ void hit_jacobian_d(const float4 st, const float4 q, con
     const double dfx = (vx > -1.0 && vx < 1.0) ? c.dk : 0.0, dfy = (vy > -1.0 && vy < 1.0) ? c.dk : 0.0;
     const bool in1 = t1 > 0.0 && t1 < 1.0, in2 = t2 > 0.0 && t2 < 1.0, raw_in = toi_raw > 0.0 && toi_raw < c.dt;
     const double sg_od = sgn_d(od - c.r), sg_s = sgn_d(s);
+    // the pull-back divides by m, o2d, L, den and od a dozen times per column: five reciprocals, taken once (a binary64
+    // division is a ~100-cycle dependent sequence and the columns are a serial chain; the products differ from the
+    // quotients by an ulp of binary64, nine orders of magnitude below the fp32 result's rounding)
+    const double rm = 1.0 / c.m, ro2d = 1.0 / o2d, rL = 1.0 / L, rden = 1.0 / den, rod = 1.0 / od;
 #pragma unroll 1
-    for (int col = 0; col < 4; ++col) {
+    for (int col = col0; col < col1; ++col) {
         const double gx = col == 0 ? 1.0 : 0.0, gy = col == 1 ? 1.0 : 0.0;
         const double gvx = col == 2 ? 1.0 : 0.0, gvy = col == 3 ? 1.0 : 0.0;
         double bx = 0.0, by = 0.0, bvx = 0.0, bvy = 0.0, bax = 0.0, bay = 0.0;
@@ -211,8 +217,8 @@ __device__ __noinline__ void hit_jacobian_d(const float4 st, const float4 q, con
         const double gtau = (gx * vbx + gy * vby) + (gvbx * abx + gvby * aby);
         double gvax = gvbx, gvay = gvby;
         const double gabx = gvbx * tau, gaby = gvby * tau;
-        gxsx += -2.0 * (gabx / c.m); gxsy += -2.0 * (gaby / c.m);
-        gvax += (gabx / c.m) * dfax; gvay += (gaby / c.m) * dfay;
+        gxsx += -2.0 * (gabx * rm); gxsy += -2.0 * (gaby * rm);
+        gvax += (gabx * rm) * dfax; gvay += (gaby * rm) * dfay;
         double gtoi = -gtau;
         double gvsx = gvax, gvsy = gvay;
         const double gvnx = -(1.0 + c.e) * gvax, gvny = -(1.0 + c.e) * gvay;
@@ -220,8 +226,8 @@ __device__ __noinline__ void hit_jacobian_d(const float4 st, const float4 q, con
         const double gn2x = gvnx * k + gk * vsx, gn2y = gvny * k + gk * vsy;
         gvsx += gk * n2x; gvsy += gk * n2y;
         const double nd = n2x * gn2x + n2y * gn2y;
-        const double go2x = (gn2x - n2x * nd) / o2d, go2y = (gn2y - n2y * nd) / o2d;
-        const double j2 = in2 ? (go2x * svx + go2y * svy) / L : 0.0;
+        const double go2x = (gn2x - n2x * nd) * ro2d, go2y = (gn2y - n2y * nd) * ro2d;
+        const double j2 = in2 ? (go2x * svx + go2y * svy) * rL : 0.0;
         gxsx += j2 * svx - go2x; gxsy += j2 * svy - go2y;
         bx += gxsx; by += gxsy;
         gvsx += gxsx * toi; gvsy += gxsy * toi;
@@ -230,43 +236,44 @@ __device__ __noinline__ void hit_jacobian_d(const float4 st, const float4 q, con
         bax += gvsx * toi; bay += gvsy * toi;
         gtoi += gvsx * a1x + gvsy * a1y;
         const double graw = raw_in ? gtoi : 0.0;
-        const double gnum = graw / den;
-        const double gden = -(graw * toi_raw) / den;
+        const double gnum = graw * rden;
+        const double gden = -(graw * toi_raw) * rden;
         const double god = gnum * sg_od;
         const double gs = gden * sg_s;
         const double gnx = gs * v1x, gny = gs * v1y;
         const double b1vx = gs * nx, b1vy = gs * ny;
         const double nd1 = nx * gnx + ny * gny;
-        const double gox = (gnx - nx * nd1) / od + god * nx, goy = (gny - ny * nd1) / od + god * ny;
+        const double gox = (gnx - nx * nd1) * rod + god * nx, goy = (gny - ny * nd1) * rod + god * ny;
         bx -= gox; by -= goy;
-        const double j1 = in1 ? (gox * svx + goy * svy) / L : 0.0;
+        const double j1 = in1 ? (gox * svx + goy * svy) * rL : 0.0;
         const double b1x = j1 * svx, b1y = j1 * svy;
         // common tail: x1 = x + v1 dt ; v1 = v + a dt ; a = (ks pot + fric(v)) / m
         const double tvx = b1vx + b1x * c.dt, tvy = b1vy + b1y * c.dt;
         bx += b1x; by += b1y;
         bvx += tvx; bvy += tvy;
         bax += tvx * c.dt; bay += tvy * c.dt;
-        const double amx = bax / c.m, amy = bay / c.m;
+        const double amx = bax * rm, amy = bay * rm;
         bx += -2.0 * (c.ks * amx); by += -2.0 * (c.ks * amy);
         bvx += amx * dfx; bvy += amy * dfy;
         Jt[0 * 4 + col] = bx; Jt[1 * 4 + col] = by; Jt[2 * 4 + col] = bvx; Jt[3 * 4 + col] = bvy;
     }
 }
 
-// pass 1: one thread per collision record (grid-stride)
+// pass 1: four threads per collision record, one column of the transposed Jacobian each (grid-stride)
 __global__ void __launch_bounds__(128) rollout_bwd_jacobian_kernel(const BwdParams p) {
     const int n = min(*p.rec_count, p.rec_cap);
     const ConstsD cd = make_consts_d(p.c);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < 4 * (int64_t)n; w += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(w >> 2), col = (int)(w & 3);
         const float4* r = reinterpret_cast<const float4*>(p.rec + i);
         const float4 st = r[0];
         const int4 m = reinterpret_cast<const int4*>(r)[1];
         const int64_t ball = ((int64_t)m.w << 32) | (uint32_t)m.x;
         double J[16];
-        hit_jacobian_d(st, __ldg(scene_q(p, ball) + m.z), __ldg(scene_s1(p, ball) + m.z), cd, J);
-        double2* out = reinterpret_cast<double2*>(p.jac + (size_t)i * 16);
+        hit_jacobian_d(st, __ldg(scene_q(p, ball) + m.z), __ldg(scene_s1(p, ball) + m.z), cd, J, col, col + 1);
+        double* out = p.jac + (size_t)i * 16 + col;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) out[k] = make_double2(J[2 * k], J[2 * k + 1]);
+        for (int k = 0; k < 4; ++k) out[4 * k] = J[4 * k + col];
     }
 }
 

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
     const bool producer = warp == 0;
     const SceneLayout L = scene_layout(1, p.S);
     const uint32_t scene_bytes = (uint32_t)L.S_pad * 20;
-    const uint32_t bbytes = (uint32_t)(bake_bytes(L.S_pad) - sizeof(BakeHeader));
+    const uint32_t bbytes = (uint32_t)bake_lists_bytes(L.S_pad);  // cell lists only: the sub-cell masks do not pay here (measured)
     unsigned char* sbake = smem + scene_bytes;  // 16-byte aligned: S_pad is a multiple of 32
     uint64_t* bar = reinterpret_cast<uint64_t*>(sbake + bbytes);
     PipeShared<U>& sh = *reinterpret_cast<PipeShared<U>*>(sbake + bbytes + 16);
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
             sc.q = reinterpret_cast<const float4*>(smem);
             sc.rl = reinterpret_cast<const float*>(smem + (size_t)L.S_pad * sizeof(float4));
             sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
-            bake_view_arrays(bk, sbake);
+            bake_view_arrays(bk, sbake, L.S_pad, false);
             bake_view_header(bk, bh, sc.weird, c.r);
         }
         mbar_wait(bar, 0);
@@ -250,8 +250,9 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
             if (hit && j == f) {  // my step: resolve it, post the state after it
                 State s1;
                 free_step(s.x, s.z, s.y, s.w, c, s1);  // the candidate again, with its acceleration (resolve needs it)
-                payload = record_collision(p.sink, ball, ts0 + f, s.x, s.z, s.y, s.w, idx);  // first: the atomic's round trip overlaps the resolve
+                const int slot = record_reserve(p.sink);  // first: the atomic's round trip overlaps the resolve
                 r = resolve(s.x, s.z, s.y, s.w, s1, sc.q[idx], c);
+                payload = record_commit(p.sink, slot, ball, ts0 + f, s.x, s.z, s.y, s.w, idx);
                 // Contact mode: while the very next step collides again (resting / sliding contact, a bounce in a corner),
                 // this lane steps the ball itself — a restart through the producer costs ~1.5 windows per collision.  At
                 // most U steps per window, so that the other balls of the group keep moving.
@@ -266,13 +267,14 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
                     free_step(cur.x, cur.y, cur.vx, cur.vy, c, c1);
                     int i2;
                     if (!baked_hit(sc, bk, c1.x, c1.y, c.r, i2)) break;  // free flight again: the producer takes over from `cur`
-                    const int pl = record_collision(p.sink, ball, tn, cur.x, cur.y, cur.vx, cur.vy, i2);
+                    const int slot2 = record_reserve(p.sink);
                     if (p.ckpt) {
                         const bool at = kshift >= 0 ? (tn & (K - 1)) == 0 : (tn % K) == 0;
                         if (at) p.ckpt[(size_t)(kshift >= 0 ? tn >> kshift : tn / K) * p.B + ball] = make_float4(cur.x, cur.y, cur.vx, cur.vy);
                     }
                     const uint32_t clip = clip_bits(cur.vx, cur.vy);
                     const State r2 = resolve(cur.x, cur.y, cur.vx, cur.vy, c1, sc.q[i2], c);
+                    const int pl = record_commit(p.sink, slot2, ball, tn, cur.x, cur.y, cur.vx, cur.vy, i2);
                     if (hl && pend_t >= 0) hl[(int64_t)pend_t * p.hl_st] = pack_log(pend_pl, true, pend_clip);
                     pend_t = tn; pend_pl = pl; pend_clip = clip;
                     cur = r2;
@@ -357,16 +359,16 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
     named_barrier(1, GT);
     const int n_jac = jl_count;
     if (p.jac != nullptr && n_jac <= kJlCap) {
-        for (int i = tid; i < n_jac; i += GT) {
-            const int slot = jlist[i];
+        for (int w = tid; w < 4 * n_jac; w += GT) {  // four threads per record: one column each
+            const int slot = jlist[w >> 2], col = w & 3;
             const float4* rr = reinterpret_cast<const float4*>(p.sink.rec + slot);
             const int4 m = reinterpret_cast<const int4*>(rr)[1];
             const int64_t rb = ((int64_t)m.w << 32) | (uint32_t)m.x;
             double J[16];
-            hit_jacobian_d(rr[0], __ldg(scene_q(bp, rb) + m.z), __ldg(scene_s1(bp, rb) + m.z), cd, J);
-            double2* out = reinterpret_cast<double2*>(p.jac + (size_t)slot * 16);
+            hit_jacobian_d(rr[0], __ldg(scene_q(bp, rb) + m.z), __ldg(scene_s1(bp, rb) + m.z), cd, J, col, col + 1);
+            double* out = p.jac + (size_t)slot * 16 + col;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) out[k] = make_double2(J[2 * k], J[2 * k + 1]);
+            for (int k = 0; k < 4; ++k) out[4 * k] = J[4 * k + col];
         }
         bp.jac = p.jac;
     }

@@ -185,7 +185,7 @@ constexpr int64_t kFusedMaxBalls = 1024;  // 64 blocks: the fused variant runs o
 bool fused_ok(const doper_rollout_desc* d) {
     if (!use_pipe(d) || (d->flags & 2) || record_capacity(d) <= 0 || d->n_steps < 1 || d->B > kFusedMaxBalls) return false;
     const int S_pad = scene_layout(1, d->S).S_pad;
-    return (size_t)S_pad * 20 + (bake_bytes(S_pad) - sizeof(BakeHeader)) >= 16 * 16 * 16 * sizeof(double);
+    return (size_t)S_pad * 20 + bake_lists_bytes(S_pad) >= 16 * 16 * 16 * sizeof(double);
 }
 
 int pipe_window(const doper_rollout_desc* d) { return pipe_pinned(d) ? d->lanes_per_ball : 16; }
@@ -418,7 +418,7 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
 template <int U, bool FUSED>
 int launch_fwd_pipe(cudaStream_t st, const FwdParams& p) {
     const int S_pad = scene_layout(1, p.S).S_pad;
-    const size_t smem = (size_t)S_pad * 20 + (bake_bytes(S_pad) - sizeof(BakeHeader)) + 16 + sizeof(PipeShared<U>);
+    const size_t smem = (size_t)S_pad * 20 + bake_lists_bytes(S_pad) + 16 + sizeof(PipeShared<U>);
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(rollout_fwd_pipe_kernel<U, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DOPER_ERR_SMEM_LIMIT;

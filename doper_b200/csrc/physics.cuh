@@ -115,18 +115,28 @@ struct HitSink {
     int cap;
 };
 
-__device__ __forceinline__ int record_collision(const HitSink& s, int64_t ball, int t, float x, float y, float vx,
-                                                float vy, int idx) {
-    if (s.rec != nullptr && s.cap > 0) {
-        const int slot = atomicAdd(s.count, 1);
-        if (slot < s.cap) {
-            float4* dst = reinterpret_cast<float4*>(s.rec + slot);
-            dst[0] = make_float4(x, y, vx, vy);
-            reinterpret_cast<int4*>(dst)[1] = make_int4((int)(ball & 0xffffffffll), t, idx, (int)(ball >> 32));
-            return slot;
-        }
+// Split in two so that the atomic's round trip to L2 (~0.5 - 1 us, and the branch on its result) does not sit on
+// the serial chain of a collided step: record_reserve() BEFORE the collision is resolved (the slot is not consumed
+// yet), record_commit() after it.  A ball in sliding contact collides on every step; its chain sets the duration of
+// the whole forward kernel (profiles/r2_ncu_fwd_baked1_c5.txt: the SMs are active 49 % of the kernel on average).
+__device__ __forceinline__ int record_reserve(const HitSink& s) {
+    return (s.rec != nullptr && s.cap > 0) ? atomicAdd(s.count, 1) : 0x7fffffff;
+}
+
+__device__ __forceinline__ int record_commit(const HitSink& s, int slot, int64_t ball, int t, float x, float y, float vx,
+                                             float vy, int idx) {
+    if (slot < s.cap) {  // (no record area: slot = INT_MAX)
+        float4* dst = reinterpret_cast<float4*>(s.rec + slot);
+        dst[0] = make_float4(x, y, vx, vy);
+        reinterpret_cast<int4*>(dst)[1] = make_int4((int)(ball & 0xffffffffll), t, idx, (int)(ball >> 32));
+        return slot;
     }
     return (int)((uint32_t)idx | kLogNoRecord);
+}
+
+__device__ __forceinline__ int record_collision(const HitSink& s, int64_t ball, int t, float x, float y, float vx,
+                                                float vy, int idx) {
+    return record_commit(s, record_reserve(s), ball, t, x, y, vx, vy, idx);
 }
 
 __device__ __forceinline__ uint32_t clip_bits(float vx, float vy) {

@@ -42,9 +42,13 @@ constexpr int kBakeItemsPerSeg = 32;
 // (coarse) cell is only read for those.  Same proof as for the cells themselves with rho_f = sub-cell half diagonal
 // / 0.98: a clear bit proves "no collision" for every point that falls in the sub-cell.
 constexpr int kBakeFineShiftMax = 3;
-// byte offsets of the arrays behind the BakeHeader
-constexpr size_t kBakeFineOff = (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t);
-constexpr size_t kBakeItemsOff = kBakeFineOff + (size_t)kBakeMaxCells * sizeof(unsigned long long);
+// byte offsets of the arrays behind the BakeHeader: [cell_start | items | sub-cell masks]; the masks come last so that
+// a kernel that does not use them (the pipelined forward) stages bake_lists_bytes() only
+constexpr size_t kBakeItemsOff = (size_t)(kBakeMaxCells + 16) * sizeof(uint32_t);
+__host__ __device__ inline size_t bake_lists_bytes(int S_pad) {  // cell_start + items (S_pad is a multiple of 32: 16-byte aligned)
+    return kBakeItemsOff + (size_t)kBakeItemsPerSeg * S_pad * sizeof(unsigned short);
+}
+__host__ __device__ inline size_t bake_fine_off(int S_pad) { return bake_lists_bytes(S_pad); }
 
 struct BakeHeader {  // 64 B
     float x0, y0, h, inv_h;   // cell (ix, iy) = [x0 + ix h, x0 + (ix + 1) h) x ...
@@ -59,7 +63,7 @@ struct BakeHeader {  // 64 B
 };
 
 __host__ __device__ inline size_t bake_bytes(int S_pad) {
-    size_t b = sizeof(BakeHeader) + kBakeItemsOff + (size_t)kBakeItemsPerSeg * S_pad * sizeof(unsigned short);
+    size_t b = sizeof(BakeHeader) + bake_fine_off(S_pad) + (size_t)kBakeMaxCells * sizeof(unsigned long long);
     return (b + 15) / 16 * 16;
 }
 
@@ -81,7 +85,7 @@ __host__ __device__ inline SceneLayout scene_layout(int64_t n_scenes, int S) {
         L.total += sizeof(GridHeader) + (size_t)(kGridMaxCells + 1) * sizeof(int) + (size_t)4 * L.S_pad * sizeof(int);
         L.total = (L.total + 255) / 256 * 256;
     }
-    // per scene: [BakeHeader 64 B | cell_start u32 (kBakeMaxCells + 16) | sub-cell masks u64 (kBakeMaxCells) | items u16 (bake_cap)]
+    // per scene: [BakeHeader 64 B | cell_start u32 (kBakeMaxCells + 16) | items u16 (bake_cap) | sub-cell masks u64 (kBakeMaxCells)]
     L.bake_off = L.total;
     L.bake_cap = kBakeItemsPerSeg * L.S_pad;
     L.bake_stride = (bake_bytes(L.S_pad) + 255) / 256 * 256;
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(256) scene_bake_kernel(int64_t n_scenes, int S
     unsigned char* bake = ws + L.bake_off + (size_t)scn * L.bake_stride;
     BakeHeader* bh = reinterpret_cast<BakeHeader*>(bake);
     uint32_t* cell_start = reinterpret_cast<uint32_t*>(bake + sizeof(BakeHeader));
-    unsigned long long* fine = reinterpret_cast<unsigned long long*>(bake + sizeof(BakeHeader) + kBakeFineOff);
+    unsigned long long* fine = reinterpret_cast<unsigned long long*>(bake + sizeof(BakeHeader) + bake_fine_off(L.S_pad));
     unsigned short* items = reinterpret_cast<unsigned short*>(bake + sizeof(BakeHeader) + kBakeItemsOff);
     __shared__ float s_red[4][256];
     __shared__ int s_cnt[kBakeMaxCells];

@@ -864,7 +864,9 @@ def test_baked_lists_hold_every_touchable_segment(sim, radius, scale):
     S = segs.shape[0]
     total = lib.doper_scene_workspace_bytes(1, S)
     S_pad = (S + 31) // 32 * 32
-    bake_bytes = (64 + (4096 + 16) * 4 + 32 * S_pad * 2 + 15) // 16 * 16
+    items_off = 64 + (4096 + 16) * 4
+    fine_off = items_off + 32 * S_pad * 2    # sub-cell masks (one u64 per cell) behind the items
+    bake_bytes = (fine_off + 4096 * 8 + 15) // 16 * 16
     bake_off = total - (bake_bytes + 255) // 256 * 256
     raw = ws.cpu().numpy()
     hdr = raw[bake_off:bake_off + 64]
@@ -873,7 +875,10 @@ def test_baked_lists_hold_every_touchable_segment(sim, radius, scale):
     assert enabled == 1 and nx * ny <= 4096 and n_items <= 32 * S_pad
     assert abs(hdr[32:36].view(np.float32)[0] - np.float32(r)) == 0
     cs = raw[bake_off + 64: bake_off + 64 + (4096 + 16) * 4].view(np.uint32)
-    items = raw[bake_off + 64 + (4096 + 16) * 4: bake_off + 64 + (4096 + 16) * 4 + 2 * n_items].view(np.uint16)
+    items = raw[bake_off + items_off: bake_off + items_off + 2 * n_items].view(np.uint16)
+    fine = raw[bake_off + fine_off: bake_off + fine_off + 4096 * 8].view(np.uint64)
+    fshift = int(hdr[56:60].view(np.int32)[0])
+    assert 0 <= fshift <= 3
     rng = np.random.default_rng(5)
     lo = segs.reshape(-1, 2).min(0).astype(np.float64) - 3 * r - 3 * h
     hi = segs.reshape(-1, 2).max(0).astype(np.float64) + 3 * r + 3 * h
@@ -888,6 +893,12 @@ def test_baked_lists_hold_every_touchable_segment(sim, radius, scale):
     assert inside.mean() > 0.5
     assert (D[~inside].min(axis=1) > r * 1.0001).all(), "a point outside the grid is within r_max of a segment"
     cell = (fy[inside].astype(np.int32) * nx + fx[inside].astype(np.int32))
+    # the sub-cell bit of the point, as baked_cell computes it
+    nsub = np.float32(1 << fshift)
+    jx, jy = (fx[inside] * nsub).astype(np.int32), (fy[inside] * nsub).astype(np.int32)
+    assert ((jy >> fshift) * nx + (jx >> fshift) == cell).all()
+    bit = ((jy & ((1 << fshift) - 1)) << fshift) | (jx & ((1 << fshift) - 1))
+    passes = ((fine[cell] >> bit.astype(np.uint64)) & np.uint64(1)).astype(bool)
     Din = D[inside]
     n_checked = 0
     for k in range(len(cell)):
@@ -895,8 +906,12 @@ def test_baked_lists_hold_every_touchable_segment(sim, radius, scale):
         if len(near):
             lst = items[cs[cell[k]]:cs[cell[k] + 1]]
             assert np.isin(near, lst).all(), (k, near, lst)
+            assert passes[k], (k, near, "sub-cell bit clear although a segment is within r_max")
             n_checked += 1
     assert n_checked > 100
+    if fshift > 0:  # the second level must actually filter: points in a listed cell whose sub-cell is clear
+        listed = cs[cell + 1] > cs[cell]
+        assert (~passes[listed]).mean() > 0.2, (~passes[listed]).mean()
     assert (np.diff(cs[: nx * ny + 1].astype(np.int64)) >= 0).all() and cs[nx * ny] == n_items
 
 
