@@ -651,7 +651,9 @@ def ours(args):
                     "api": "doper_b200.sim.ball_sim.vmapped_grad_and_value(host numpy arrays)"},
             # kernels of this repository per step: forward, loss, backward (1 or 2), exchange (N > 1, peer kernel)
             "gpu_launches": ((1 if (not args.separate_launches and "fused" in lib.doper_rollout_plan_name(dref, 2).decode())
-                              else 3 + lib.doper_rollout_plan_name(dref, 1).decode().count("+")) + (1 if peer is not None else 0)) * K,
+                              else 3 + lib.doper_rollout_plan_name(dref, 1).decode().count("+")
+                              + (1 if lib.doper_rollout_plan_name(dref, 3).decode() else 0))  # + the hand-over drain kernel
+                             + (1 if peer is not None else 0)) * K,
             "wall_ms_timed_region": round(wall_ms, 3),
             "roofline": roof,
         }

@@ -125,18 +125,182 @@ __device__ __forceinline__ bool baked_hit(const SceneView& sc, const BakeView& b
     return baked_list_hit(sc, bk, px, py, r, kind, k0, k1, idx);
 }
 
+// Scene and baked views of one environment read in place (per-environment scenes: `env` = the ball; else 0).
+__device__ __forceinline__ void baked_bind_in_place(const FwdParams& p, const SceneLayout& L, int64_t env, SceneView& sc, BakeView& bk) {
+    const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off)[env];
+    const unsigned char* gbake = p.scene_ws + L.bake_off + (size_t)env * L.bake_stride;
+    const BakeHeader bh = *reinterpret_cast<const BakeHeader*>(gbake);
+    sc.q = reinterpret_cast<const float4*>(p.scene_ws + L.q_off) + env * L.S_pad;
+    sc.rl = reinterpret_cast<const float*>(p.scene_ws + L.rl_off) + env * L.S_pad;
+    sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
+    bake_view_arrays(bk, gbake + sizeof(BakeHeader), L.S_pad);
+    bake_view_header(bk, bh, sc.weird, p.c.r);
+}
+
+// Hand-over of a ball in sliding / resting contact (DeferQueue, physics.cuh).  A ball that has collided on
+// kDeferStreak consecutive steps and has at least kDeferMinSteps to go is pushed to the queue with the state at the
+// start of its next step; its lane stops.
+constexpr int kDeferStreak = 8, kDeferMinSteps = 64;
+
+__device__ __forceinline__ void defer_push(const DeferQueue& dq, int64_t ball, int t, float x, float y, float vx, float vy) {
+    const unsigned slot = atomicAdd(dq.alloc, 1u);  // < cap = B: a ball is pushed at most once
+    float4* e = reinterpret_cast<float4*>(dq.entry + slot);
+    e[0] = make_float4(x, y, vx, vy);
+    reinterpret_cast<int4*>(e)[1] = make_int4((int)(ball & 0xffffffffll), t, 0, (int)(ball >> 32));
+    __threadfence();
+    *reinterpret_cast<volatile unsigned int*>(dq.flag + slot) = 1u;
+}
+
+// One ball, one thread, steps t .. n - 1 from the state (x, y, vx, vy) at the start of step t: free flight, cell
+// look-up, narrow phase, collision, log / checkpoint / record / trajectory — the loop of the one-thread-per-ball
+// kernel, of its tail workers and of the drain kernel (same device functions as every forward kernel: same bits).
+// (Measured and dropped for the tail workers, tools/contact_chain_probe.py: a four-entries-per-trip branch-free narrow
+// phase and the collision resolved in line — the ball alone 3.11 -> 3.12 ms, C5 forward 4.25 -> 4.43, C3 1.85 -> 2.04.)
+__device__ __forceinline__ void baked_run_ball(const FwdParams& p, const SceneView& sc, const BakeView& bk, const Consts& c,
+                                               const int64_t ball, int t, float x, float y, float vx, float vy, const bool may_defer) {
+    const int n = p.n_steps, K = p.K;
+    const bool want_traj = p.traj_x != nullptr || p.traj_v != nullptr || p.traj_a != nullptr;
+    const int64_t hl_step = p.hl_st;
+    int32_t* hlp = p.hitlog ? p.hitlog + ball * p.hl_sb + (int64_t)t * hl_step : nullptr;  // running log pointer
+    int ck_i = p.ckpt ? (t + K - 1) / K : 0;
+    int next_ck = p.ckpt ? ck_i * K : n + 1;  // checkpoint counter instead of shift / mask tests
+    int streak = 0;
+    for (; t < n; ++t) {
+        State my;
+        if (!free_step_fast(x, y, vx, vy, c, my)) free_step(x, y, vx, vy, c, my);  // a numerator left the fast division's range
+        int idx = 0;
+        const bool hit = baked_hit(sc, bk, my.x, my.y, c.r, idx);
+        State out = my;
+        int payload = 0;
+        int slot = 0;
+        if (hit) {
+            // The record slot is an atomic's round trip to L2 (~1,000 cycles: a third of a collided step's serial
+            // chain when the warp waits for it, profiles/r2_ncu_contact_chain.txt).  Reserved here, consumed after
+            // everything else of the step.  (Inlining the resolve here was measured slower: 3.14 -> 3.31 ms for
+            // the ball in sliding contact alone.)
+            slot = record_reserve(p.sink);
+            out = resolve(x, y, vx, vy, my, sc.q[idx], c);
+        }
+        if (t == next_ck) {
+            p.ckpt[(size_t)ck_i * p.B + ball] = make_float4(x, y, vx, vy);
+            ++ck_i; next_ck += K;
+        }
+        if (hit) payload = record_commit(p.sink, slot, ball, t, x, y, vx, vy, idx);
+        if (hlp) { *hlp = pack_log(payload, hit, clip_bits(vx, vy)); hlp += hl_step; }
+        if (want_traj) {
+            const size_t o = (size_t)t * p.B + ball;
+            if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
+            if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
+            if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+        }
+        x = out.x; y = out.y; vx = out.vx; vy = out.vy;
+        if (may_defer) {
+            streak = hit ? streak + 1 : 0;
+            if (streak >= kDeferStreak && n - (t + 1) >= kDeferMinSteps) {
+                defer_push(p.defer, ball, t + 1, x, y, vx, vy);
+                return;
+            }
+        }
+    }
+    p.xT[ball] = make_float2(x, y);
+    p.vT[ball] = make_float2(vx, vy);
+}
+
+// The same ball, run by a WHOLE WARP (tail workers, drain kernel): every lane carries the same state through the same
+// free flight, look-up and resolve (uniform control flow, no divergence), and the narrow phase — half of a collided
+// step's serial chain when one thread walks a corner's list entry by entry — gives every list entry its own lane and
+// takes the (distance, index) minimum by shuffles: the same keys, the same minimum, the same bits.  Lane 0 owns the
+// stores.  The record of a collided step is committed one step LATE (its slot is an atomic's round trip to L2, and a
+// warp that consumes the slot in the same step waits it out): the atomic is issued at the end of step t and consumed
+// behind the free flight and narrow phase of step t + 1.
+__device__ __forceinline__ void baked_run_ball_warp(const FwdParams& p, const SceneView& sc, const BakeView& bk, const Consts& c,
+                                                    const int64_t ball, int t, float x, float y, float vx, float vy) {
+    const int n = p.n_steps, K = p.K, lane = threadIdx.x & 31;
+    const bool want_traj = p.traj_x != nullptr || p.traj_v != nullptr || p.traj_a != nullptr;
+    const int64_t hl_step = p.hl_st;
+    int32_t* hlp = p.hitlog ? p.hitlog + ball * p.hl_sb + (int64_t)t * hl_step : nullptr;
+    int ck_i = p.ckpt ? (t + K - 1) / K : 0;
+    int next_ck = p.ckpt ? ck_i * K : n + 1;
+    // lane 0: the collided step whose record is still to be committed
+    bool pend = false;
+    int pend_slot = 0, pend_t = 0, pend_idx = 0;
+    float pend_x = 0.f, pend_y = 0.f, pend_vx = 0.f, pend_vy = 0.f;
+    int32_t* pend_hl = nullptr;
+    for (; t < n; ++t) {
+        State my;
+        if (!free_step_fast(x, y, vx, vy, c, my)) free_step(x, y, vx, vy, c, my);
+        int idx = 0, k0, k1;
+        bool hit = false;
+        const int kind = baked_cell(bk, my.x, my.y, k0, k1);
+        if (kind == 1) {
+            unsigned long long key = kNoKey;
+            for (int k = k0 + lane; k < k1; k += 32) {
+                const int i = bk.items[k];
+                const float4 q = sc.q[i];
+                if (!(approx_d2(my.x, my.y, q, sc.rl[i]) > bk.far2)) {
+                    const unsigned long long kk = make_key(cand_dist(my.x, my.y, q), i);
+                    key = kk < key ? kk : key;
+                }
+            }
+            __syncwarp();
+            key = group_min<32>(key);
+            if (key != kNoKey) {
+                float dist;
+                unpack_key(key, idx, dist);
+                hit = dist <= c.r;  // NaN -> false (ball_sim.py:164)
+            }
+        } else if (kind == 2) {
+            hit = baked_list_hit(sc, bk, my.x, my.y, c.r, kind, k0, k1, idx);
+        }
+        State out = my;
+        if (hit) out = resolve(x, y, vx, vy, my, sc.q[idx], c);
+        if (lane == 0) {
+            if (pend) {  // the previous collided step: its slot has arrived by now
+                const int payload = record_commit(p.sink, pend_slot, ball, pend_t, pend_x, pend_y, pend_vx, pend_vy, pend_idx);
+                if (pend_hl) *pend_hl = pack_log(payload, true, clip_bits(pend_vx, pend_vy));
+                pend = false;
+            }
+            if (hit) {
+                pend_slot = record_reserve(p.sink);
+                pend = true; pend_t = t; pend_idx = idx; pend_x = x; pend_y = y; pend_vx = vx; pend_vy = vy; pend_hl = hlp;
+            } else if (hlp) {
+                *hlp = pack_log(0, false, clip_bits(vx, vy));
+            }
+            if (t == next_ck) p.ckpt[(size_t)ck_i * p.B + ball] = make_float4(x, y, vx, vy);
+            if (want_traj) {
+                const size_t o = (size_t)t * p.B + ball;
+                if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
+                if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
+                if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+            }
+        }
+        if (t == next_ck) { ++ck_i; next_ck += K; }
+        if (hlp) hlp += hl_step;
+        x = out.x; y = out.y; vx = out.vx; vy = out.vy;
+    }
+    if (lane == 0) {
+        if (pend) {
+            const int payload = record_commit(p.sink, pend_slot, ball, pend_t, pend_x, pend_y, pend_vx, pend_vy, pend_idx);
+            if (pend_hl) *pend_hl = pack_log(payload, true, clip_bits(pend_vx, pend_vy));
+        }
+        p.xT[ball] = make_float2(x, y);
+        p.vT[ball] = make_float2(vx, vy);
+    }
+}
+
 // MAXT bounds the block size (register budget); the launcher picks blockDim.x = 32 w with w = the warps ONE SM gets
 // when the batch is spread evenly over the SMs (kernels.cu balanced_block): the kernel is a latency chain per warp,
 // so its duration is set by the SM with the most resident warps, and a second partial wave doubles it.
 template <int G, bool STAGED, int MAXT>
 __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int BPB = (int)blockDim.x / G;  // balls per block
+    const int tail_threads = (G == 1 && p.defer.entry) ? 32 * p.defer.tail_warps : 0;  // the block's last warps: tail workers
+    const int BPB = ((int)blockDim.x - tail_threads) / G;  // balls per block
     constexpr unsigned kLow = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
     const int tid = threadIdx.x, lane = tid % G, gbase = (tid & 31) - lane;
     const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
     int64_t ball = (int64_t)blockIdx.x * BPB + tid / G;
-    const bool active = ball < p.B;
+    const bool active = ball < p.B && tid < (int)blockDim.x - tail_threads;
     if (!active) ball = p.B - 1;  // absent ball: reads the last ball's inputs, never advances, writes nothing
     const int64_t env = p.per_env ? ball : 0;  // per-environment scenes: ball b lives in scene b (baked per scene, read in place)
     const SceneHeader hdr = reinterpret_cast<const SceneHeader*>(p.scene_ws + L.hdr_off)[env];
@@ -145,13 +309,14 @@ __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams
 
     SceneView sc;
     BakeView bk;
+    __shared__ int s_normal_left;  // warps of this block that still run their own balls (tail workers poll while > 0)
     if (STAGED) {
         float4* sq = reinterpret_cast<float4*>(smem);
         float* srl = reinterpret_cast<float*>(smem + (size_t)L.S_pad * sizeof(float4));
         unsigned char* sbake = smem + (size_t)L.S_pad * 20;  // 16-byte aligned: S_pad is a multiple of 32
         const uint32_t bbytes = (uint32_t)(bake_bytes(L.S_pad) - sizeof(BakeHeader));
         uint64_t* bar = reinterpret_cast<uint64_t*>(sbake + bbytes);
-        if (tid == 0) mbar_init(bar, 1);
+        if (tid == 0) { mbar_init(bar, 1); s_normal_left = ((int)blockDim.x - tail_threads) / 32; }
         __syncthreads();
         if (tid == 0) {
             const uint32_t qb = (uint32_t)L.S_pad * sizeof(float4), rb = (uint32_t)L.S_pad * sizeof(float);
@@ -172,6 +337,10 @@ __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams
         sc.rl = reinterpret_cast<const float*>(p.scene_ws + L.rl_off) + env * L.S_pad;
         bake_view_arrays(bk, gbake + sizeof(BakeHeader), L.S_pad);
         sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
+        if (G == 1) {
+            if (tid == 0) s_normal_left = ((int)blockDim.x - tail_threads) / 32;
+            __syncthreads();
+        }
     }
     const Consts c = p.c;
     bake_view_header(bk, bh, sc.weird, c.r);
@@ -185,41 +354,56 @@ __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams
     int T = G;  // speculation length of the next round (1 after a collision at the round's first step)
 
     if constexpr (G == 1) {
-        // One thread per ball (large batches: the kernel is issue bound there, profiles/r2_ncu_fwd_baked1_c5_before_streamlined_loop.txt): the
-        // same step with nothing warp-wide and nothing recomputed — running log pointer instead of a 64-bit multiply,
-        // a checkpoint counter instead of shift / mask tests, one test for the three trajectory pointers.
-        const bool want_traj = p.traj_x != nullptr || p.traj_v != nullptr || p.traj_a != nullptr;
-        int32_t* hlp = hl;
-        const int64_t hl_step = p.hl_st;
-        int next_ck = p.ckpt ? 0 : n + 1, ck_i = 0;
-        for (; t < n; ++t) {
-            State my;
-            if (!free_step_fast(x, y, vx, vy, c, my)) free_step(x, y, vx, vy, c, my);  // a numerator left the fast division's range
-            int idx = 0;
-            const bool hit = baked_hit(sc, bk, my.x, my.y, c.r, idx);
-            State out = my;
-            int payload = 0;
-            if (hit) {
-                const int slot = record_reserve(p.sink);  // the atomic's round trip overlaps the resolve
-                out = resolve(x, y, vx, vy, my, sc.q[idx], c);
-                payload = record_commit(p.sink, slot, ball, t, x, y, vx, vy, idx);
+        // One thread per ball (large batches): the step loop with nothing warp-wide and nothing recomputed
+        // (baked_run_ball).  A ball in sliding contact collides on every step: a ~2 us serial chain per step (its own
+        // ~600 dependent instructions plus the divergent work of the 31 other lanes) that used to set the duration
+        // of the whole kernel — BASELINE configs[4]: one ball of 131,072 collides on 1,972 of 2,000 steps, and the
+        // SMs were busy 49 % of the kernel (profiles/r2_ncu_fwd_baked1_c5.txt).  Such a ball is handed to a
+        // TAIL WORKER: the block's last warps serve the queue from the start, every other warp joins them when its
+        // own balls are done, and a worker runs ONE ball in lane 0.  Workers never wait for other blocks (they leave
+        // when their own block's balls are done and the queue is empty), so nothing here can deadlock on residency;
+        // what is still queued when the kernel ends is finished by rollout_fwd_drain_kernel.
+        const DeferQueue dq = p.defer;
+        bool own = tid < (int)blockDim.x - tail_threads;  // first pass of a normal warp: its own balls
+        const bool live = active;
+        for (;;) {
+            if (!own) {
+                int claimed = -1;
+                if ((tid & 31) == 0) {
+                    for (;;) {
+                        const unsigned alloc = *reinterpret_cast<volatile unsigned int*>(dq.alloc);
+                        const unsigned head = *reinterpret_cast<volatile unsigned int*>(dq.head);
+                        if (head < alloc) {
+                            if (atomicCAS(dq.head, head, head + 1u) == head) { claimed = (int)head; break; }
+                            continue;
+                        }
+                        if (*reinterpret_cast<volatile int*>(&s_normal_left) <= 0) break;
+                        __nanosleep(200);
+                    }
+                }
+                claimed = __shfl_sync(0xffffffffu, claimed, 0);
+                if (claimed < 0) break;
+                if ((tid & 31) == 0) {
+                    while (*reinterpret_cast<volatile unsigned int*>(dq.flag + claimed) == 0u) __nanosleep(40);
+                    __threadfence();
+                }
+                __syncwarp();
+                const float4 st = __ldcg(reinterpret_cast<const float4*>(dq.entry + claimed));  // L2: written by another SM
+                const int4 m = __ldcg(reinterpret_cast<const int4*>(dq.entry + claimed) + 1);
+                const int64_t eball = ((int64_t)m.w << 32) | (uint32_t)m.x;
+                if (!STAGED && p.per_env) baked_bind_in_place(p, L, eball, sc, bk);
+                // Scene read in place (L2 / L1): the whole warp on the ball, its list entries fetched side by side
+                // (C3 forward 1.96 -> 1.64 ms).  Scene in shared memory: lane 0 alone is as fast (the shuffle
+                // minimum costs what the parallel entries save: C5 forward 4.38 vs 4.50 ms).
+                if (!STAGED) baked_run_ball_warp(p, sc, bk, c, eball, m.y, st.x, st.y, st.z, st.w);
+                else if ((tid & 31) == 0) baked_run_ball(p, sc, bk, c, eball, m.y, st.x, st.y, st.z, st.w, false);
+            } else if (live) {
+                baked_run_ball(p, sc, bk, c, ball, 0, x, y, vx, vy, dq.entry != nullptr);
             }
-            if (hlp) { *hlp = pack_log(payload, hit, clip_bits(vx, vy)); hlp += hl_step; }
-            if (t == next_ck) {
-                p.ckpt[(size_t)ck_i * p.B + ball] = make_float4(x, y, vx, vy);
-                ++ck_i; next_ck += K;
-            }
-            if (want_traj) {
-                const size_t o = (size_t)t * p.B + ball;
-                if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
-                if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
-                if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
-            }
-            x = out.x; y = out.y; vx = out.vx; vy = out.vy;
-        }
-        if (active) {
-            p.xT[ball] = make_float2(x, y);
-            p.vT[ball] = make_float2(vx, vy);
+            if (dq.entry == nullptr) break;  // no queue: a thread only has its own ball
+            __syncwarp();
+            if (own && (tid & 31) == 0) atomicSub(&s_normal_left, 1);
+            own = false;
         }
         return;
     } else {  // G > 1
@@ -317,6 +501,24 @@ __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams
         p.vT[ball] = make_float2(vx, vy);
     }
     }  // G > 1
+}
+
+// What the tail workers left in the hand-over queue (balls pushed when every worker was busy or had gone): one warp
+// per entry (baked_run_ball_warp), scene and lists read in place.  Launched behind every rollout_fwd_baked_kernel<1>
+// that has a queue; with an empty queue it reads two counters and exits.
+__global__ void __launch_bounds__(128) rollout_fwd_drain_kernel(const FwdParams p) {
+    const unsigned alloc = *p.defer.alloc, head = *p.defer.head;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const SceneLayout L = scene_layout(p.per_env ? p.B : 1, p.S);
+    for (unsigned e = head + warp; e < alloc; e += n_warps) {
+        const float4 st = *reinterpret_cast<const float4*>(p.defer.entry + e);
+        const int4 m = reinterpret_cast<const int4*>(p.defer.entry + e)[1];
+        const int64_t eball = ((int64_t)m.w << 32) | (uint32_t)m.x;
+        SceneView sc;
+        BakeView bk;
+        baked_bind_in_place(p, L, p.per_env ? eball : 0, sc, bk);
+        baked_run_ball_warp(p, sc, bk, p.c, eball, m.y, st.x, st.y, st.z, st.w);
+    }
 }
 
 }  // namespace doper

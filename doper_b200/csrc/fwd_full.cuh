@@ -34,6 +34,8 @@ struct FwdParams {
     float2* g_v0;             // dL/dv0
     float2* g_x0;             // dL/dx0 (nullable)
     unsigned int* done_blocks;  // zeroed counter in the workspace header
+    // hand-over of balls in sliding / resting contact to tail-worker warps (rollout_fwd_baked_kernel<1>; null: off)
+    DeferQueue defer;
     double* jac;                // the backward's scratch: one 4x4 Jacobian per collision record (nullable)
 };
 

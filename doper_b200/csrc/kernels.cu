@@ -98,20 +98,23 @@ int64_t record_capacity(const doper_rollout_desc* d) {
     return cap;
 }
 
-// Forward workspace: [header 256 B: int record count | checkpoints n_ckpt x B x 16 B | hit log n x B x 4 B |
-// collision records cap x 32 B].  Backward scratch (separate, caller-owned, written by doper_rollout_bwd):
+// Forward workspace: [header 256 B: int record count, hand-over counters | hand-over flags B x 4 B | checkpoints
+// n_ckpt x B x 16 B | hit log n x B x 4 B | collision records cap x 32 B | hand-over entries B x 32 B].  Backward scratch (separate, caller-owned, written by doper_rollout_bwd):
 // [cap x 16 doubles].
-struct WsLayout { size_t ckpt_off, log_off, rec_off, total; int64_t cap; };
+struct WsLayout { size_t flag_off, ckpt_off, log_off, rec_off, defer_off, total; int64_t cap; };
 
 WsLayout ws_layout(const doper_rollout_desc* d) {
     const int K = resolve_K(d);
     const size_t n_ckpt = (size_t)(d->n_steps + K - 1) / K;
     WsLayout w;
     w.cap = record_capacity(d);
-    w.ckpt_off = 256;
+    // [256: hand-over flags u32 x B, zeroed with the header by the plans that use them (use_defer)] ... [hand-over entries 32 B x B]
+    w.flag_off = 256;
+    w.ckpt_off = (w.flag_off + (size_t)d->B * sizeof(unsigned int) + 255) / 256 * 256;
     w.log_off = (w.ckpt_off + n_ckpt * (size_t)d->B * sizeof(float4) + 255) / 256 * 256;
     w.rec_off = (w.log_off + (size_t)d->n_steps * (size_t)d->B * sizeof(int32_t) + 255) / 256 * 256;
-    w.total = (w.rec_off + (size_t)w.cap * sizeof(HitRecord) + 255) / 256 * 256 + 256;
+    w.defer_off = (w.rec_off + (size_t)w.cap * sizeof(HitRecord) + 255) / 256 * 256;
+    w.total = (w.defer_off + (size_t)d->B * sizeof(DeferEntry) + 255) / 256 * 256 + 256;
     return w;
 }
 
@@ -209,6 +212,12 @@ int baked_lanes(const doper_rollout_desc* d) {
     if (d->B <= 16384) return 4;
     if (d->B <= 49152) return 2;
     return 1;
+}
+
+// Hand-over of balls in sliding contact to tail-worker warps: the one-thread-per-ball baked kernel (its duration is
+// otherwise the serial chain of the one ball that collides on every step).  flags bit 25 switches it off.
+bool use_defer(const doper_rollout_desc* d) {
+    return use_baked(d) && !use_pipe(d) && baked_lanes(d) == 1 && !(d->flags & (1 << 25));
 }
 
 bool use_tpc(const doper_rollout_desc* d) {
@@ -403,14 +412,23 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return (int)DOPER_ERR_SMEM_LIMIT;
         const int max_threads = staged ? MAXT_STAGED : MAXT;
-        const int threads = balanced_block(p.B * G, max_threads, [&](int t) {
+        // tail-worker warps (hand-over of balls in sliding contact, G = 1 only): the block's last warps
+        FwdParams q = p;
+        const int tail = (G == 1 && p.defer.entry) ? (max_threads >= 1024 ? 4 : 1) : 0;
+        q.defer.tail_warps = tail;
+        const int threads = balanced_block(p.B * G, max_threads - 32 * tail, [&](int t) {
             int nb = 0;
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, t, smem) == cudaSuccess ? nb : 0;
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, t + 32 * tail, smem) == cudaSuccess ? nb : 0;
         });
         const int bpb = threads / G;
         const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
-        kernel<<<grid, threads, smem, st>>>(p);
-        return launch_status();
+        kernel<<<grid, threads + 32 * tail, smem, st>>>(q);
+        if (launch_status() != DOPER_OK) return (int)DOPER_ERR_LAUNCH;
+        if (tail > 0) {  // whatever the workers left in the queue (usually nothing)
+            rollout_fwd_drain_kernel<<<(unsigned)sm_count(), 128, 0, st>>>(q);
+            return launch_status();
+        }
+        return (int)DOPER_OK;
     };
     return staged ? go(rollout_fwd_baked_kernel<G, true, MAXT_STAGED>) : go(rollout_fwd_baked_kernel<G, false, MAXT>);
 }
@@ -675,6 +693,8 @@ int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d) {
 
 const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward) {
     if (validate_desc(d) != DOPER_OK) return "invalid";
+    if (backward == 3)  // a second forward launch behind the main kernel ("" = none)
+        return use_defer(d) ? "rollout_fwd_drain_kernel" : "";
     if (backward == 2)  // what doper_value_and_grad launches for the backward
         return (fused_ok(d) && !(d->flags & (1 << 24))) ? "fused into the forward launch (rollout_fwd_pipe_kernel<U, true>)"
                                                         : ((d->flags & 2) ? "rollout_bwd_kernel" : "rollout_bwd_jacobian_kernel+rollout_bwd_fold_kernel");
@@ -767,6 +787,7 @@ int rollout_fwd_impl(doper_stream_t stream, const doper_rollout_desc* d, const v
     p.traj_a = reinterpret_cast<float2*>(traj_a);
     p.ckpt = nullptr; p.hitlog = nullptr; p.sink.rec = nullptr; p.sink.count = nullptr; p.sink.cap = 0;
     p.tgt_x = p.tgt_y = 0.0f; p.loss_sum = nullptr; p.loss_pb = nullptr; p.g_v0 = nullptr; p.g_x0 = nullptr; p.done_blocks = nullptr; p.jac = nullptr;
+    p.defer.entry = nullptr; p.defer.flag = nullptr; p.defer.alloc = p.defer.head = nullptr; p.defer.cap = 0;
     if (fused) {
         if (!ws || !fa->target || !fa->loss_sum || !fa->loss_pb || !fa->v0_bar) return DOPER_ERR_NULL_PTR;
         p.tgt_x = fa->target[0]; p.tgt_y = fa->target[1];
@@ -784,7 +805,17 @@ int rollout_fwd_impl(doper_stream_t stream, const doper_rollout_desc* d, const v
         p.sink.rec = reinterpret_cast<HitRecord*>(base + w.rec_off);
         p.sink.count = reinterpret_cast<int*>(base);
         p.sink.cap = (int)w.cap;
-        if (cudaMemsetAsync(base, 0, 256, st) != cudaSuccess) return DOPER_ERR_LAUNCH;  // record counter
+        size_t zero = 256;  // record counter, block counter, hand-over counters
+        p.defer.entry = nullptr; p.defer.flag = nullptr; p.defer.alloc = p.defer.head = nullptr; p.defer.cap = 0;
+        if (use_defer(d) && !(traj_x || traj_v || traj_a)) {
+            p.defer.entry = reinterpret_cast<DeferEntry*>(base + w.defer_off);
+            p.defer.flag = reinterpret_cast<unsigned int*>(base + w.flag_off);
+            p.defer.alloc = reinterpret_cast<unsigned int*>(base + 32);
+            p.defer.head = reinterpret_cast<unsigned int*>(base + 36);
+            p.defer.cap = (int)(d->B < 0x7fffffff ? d->B : 0x7fffffff);
+            zero = w.ckpt_off;  // + the flags
+        }
+        if (cudaMemsetAsync(base, 0, zero, st) != cudaSuccess) return DOPER_ERR_LAUNCH;
     }
 #ifdef DOPER_PIPE_TIMERS
     if (use_pipe(d)) {

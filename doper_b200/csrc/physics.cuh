@@ -120,7 +120,14 @@ struct HitSink {
 // yet), record_commit() after it.  A ball in sliding contact collides on every step; its chain sets the duration of
 // the whole forward kernel (profiles/r2_ncu_fwd_baked1_c5.txt: the SMs are active 49 % of the kernel on average).
 __device__ __forceinline__ int record_reserve(const HitSink& s) {
-    return (s.rec != nullptr && s.cap > 0) ? atomicAdd(s.count, 1) : 0x7fffffff;
+    // atomicInc, not atomicAdd(count, 1): for a uniform increment the compiler (ptxas, even from inline PTX)
+    // aggregates the atomic over the warp — leader election, one ATOMG, SHFL of its result to the other lanes — and
+    // that shuffle consumes the result on the spot: the warp then waits out the whole round trip here.  Colliding
+    // lanes per warp step are 0 or 1 anyway.  (Bound 2^31 - 1, never reached: with the all-ones bound ptxas turns the
+    // INC back into an aggregated ADD.)
+    int slot = 0x7fffffff;
+    if (s.rec != nullptr && s.cap > 0) slot = (int)atomicInc(reinterpret_cast<unsigned int*>(s.count), 0x7fffffffu);
+    return slot;
 }
 
 __device__ __forceinline__ int record_commit(const HitSink& s, int slot, int64_t ball, int t, float x, float y, float vx,
@@ -138,6 +145,22 @@ __device__ __forceinline__ int record_collision(const HitSink& s, int64_t ball, 
                                                 float vy, int idx) {
     return record_commit(s, record_reserve(s), ball, t, x, y, vx, vy, idx);
 }
+
+// Hand-over queue of rollout_fwd_baked_kernel<1> (fwd_baked.cuh): a ball whose lane collides step after step is
+// taken out of its warp (whose 31 other lanes it would stall for the rest of the rollout, and whose divergent work
+// lengthens its own serial chain) and finished by a tail-worker warp that runs this one ball alone.
+struct DeferEntry {   // 32 B
+    float x, y, vx, vy;            // state at the START of step t
+    int32_t ball_lo, t, pad, ball_hi;
+};
+struct DeferQueue {
+    DeferEntry* entry;     // [cap]; null = no hand-over
+    unsigned int* flag;    // [cap] zeroed per launch; 1 = the entry is complete
+    unsigned int* alloc;   // entries allocated (zeroed counter in the workspace header)
+    unsigned int* head;    // entries claimed
+    int cap;
+    int tail_warps;        // warps per block that only serve the queue (the block's last warps)
+};
 
 __device__ __forceinline__ uint32_t clip_bits(float vx, float vy) {
     return ((vx > -1.0f && vx < 1.0f) ? kLogClipX : 0u) | ((vy > -1.0f && vy < 1.0f) ? kLogClipY : 0u);

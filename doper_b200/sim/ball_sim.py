@@ -44,7 +44,7 @@ class RolloutOptions:
                  broad_phase_time_parallel: bool = False, hit_records: bool = True, hit_capacity: int = 0,
                  baked_broad_phase: bool = True, baked_lanes: int = 0,
                  pipelined: bool | None = None, pipe_window: int = 0,
-                 fused_value_and_grad: bool = True):
+                 fused_value_and_grad: bool = True, contact_handover: bool = True):
         self.ckpt_every = int(ckpt_every)
         self.lanes_per_ball = int(lanes_per_ball)
         self.force_exact_sweep = bool(force_exact_sweep)  # every pair through the reference arithmetic
@@ -69,12 +69,14 @@ class RolloutOptions:
         self.pipelined = pipelined  # None = library default; False: forbid rollout_fwd_pipe_kernel
         self.pipe_window = int(pipe_window)  # 8, 16 or 32: pin rollout_fwd_pipe_kernel with that window
         self.fused_value_and_grad = bool(fused_value_and_grad)  # False: doper_value_and_grad as separate launches
+        # one-thread-per-ball forward: balls in sliding contact are handed to tail-worker warps (False: stay in their warp)
+        self.contact_handover = bool(contact_handover)
 
     def key(self) -> tuple:
         return (self.ckpt_every, self.lanes_per_ball, self.force_exact_sweep, self.sequential_backward, self.smem_forward,
                 self.time_parallel, self.broad_phase, self.exact_index_log, self.broad_phase_time_parallel,
                 self.hit_records, self.hit_capacity, self.baked_broad_phase, self.baked_lanes, self.pipelined,
-                self.pipe_window, self.fused_value_and_grad)
+                self.pipe_window, self.fused_value_and_grad, self.contact_handover)
 
 
 _DEFAULT_OPTIONS = RolloutOptions()
@@ -129,6 +131,8 @@ def _make_desc(B: int, scene: JaxScene, sim_time, n_steps: int, attractor, const
         d.flags |= 1 << 23
     if not opts.fused_value_and_grad:
         d.flags |= 1 << 24
+    if not opts.contact_handover:
+        d.flags |= 1 << 25
     if scene.per_env and scene.n_scenes != d.B:
         raise ValueError(f"per-environment scene count {scene.n_scenes} != batch {d.B}")
     return d
@@ -488,19 +492,22 @@ def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, at
     tp = [ptr(traj[i]) for i in range(3)] if want_trajectory else [0, 0, 0]
     check(lib.doper_rollout_fwd(stream_ptr(), ctypes.byref(desc), ptr(sws), ptr(x0), ptr(v0), ptr(out[0]),
                                 ptr(out[1]), tp[0], tp[1], tp[2], ptr(ws)), "doper_rollout_fwd")
-    # workspace layout (include/doper_b200.h): [256 B header | checkpoints | hit log | collision records]
+    # workspace layout (include/doper_b200.h): [256 B header | hand-over flags 4 B x B | checkpoints | hit log |
+    # collision records | hand-over entries 32 B x B | 256 B]
     r256 = lambda v: (v + 255) // 256 * 256
     ck_bytes = n_ckpt * B * 16
-    log_off = r256(256 + ck_bytes)
+    ck_off = r256(256 + 4 * B)
+    log_off = r256(ck_off + ck_bytes)
     rec_off = r256(log_off + n * B * 4)
-    ckpt = ws[256:256 + ck_bytes].view(torch.float32).view(n_ckpt, B, 4).cpu().numpy()
+    defer_off = ws.numel() - 256 - r256(32 * B)
+    ckpt = ws[ck_off:ck_off + ck_bytes].view(torch.float32).view(n_ckpt, B, 4).cpu().numpy()
     hl = ws[log_off:log_off + n * B * 4].view(torch.int32)
     if lib.doper_rollout_log_ball_major(ctypes.byref(desc)):
         hl = hl.view(B, n).t().contiguous().cpu().numpy()
     else:
         hl = hl.view(n, B).cpu().numpy()
     n_rec_seen = int(ws[:4].view(torch.int32).item())
-    cap = (ws.numel() - 256 - rec_off) // 32
+    cap = (defer_off - rec_off) // 32
     n_rec = min(n_rec_seen, cap)
     rec = ws[rec_off:rec_off + n_rec * 32].view(torch.int32).view(n_rec, 8).cpu().numpy()
     hit = hl < 0
@@ -518,7 +525,8 @@ def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, at
     if want_trajectory:
         th = traj.cpu().numpy()
         t = BallState(th[0], th[1], th[2])
-    return {"x_T": out[0].cpu().numpy(), "v_T": out[1].cpu().numpy(), "idx": idx, "hit": hit,
+    handed_over = int(ws[32:36].view(torch.int32).item())  # balls finished by tail workers (contact hand-over)
+    return {"x_T": out[0].cpu().numpy(), "v_T": out[1].cpu().numpy(), "idx": idx, "hit": hit, "handed_over": handed_over,
             "hitlog": hl, "checkpoints": ckpt, "trajectory": t, "records": rec, "records_seen": n_rec_seen,
             "record_capacity": cap,
             "record_states": rec[:, :4].copy().view(np.float32) if n_rec else np.zeros((0, 4), np.float32)}

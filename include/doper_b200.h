@@ -43,8 +43,10 @@
  *             START of the collided step, then int32 (ball low word, step, segment index, ball high
  *             word).  The record count is the int32 at offset 0 of the workspace.
  *   checkpoints [ceil(n_steps/ckpt_every)][B][4] = (x,y,vx,vy) at the START of step k*ckpt_every
- *   workspace (doper_rollout_workspace_bytes): [256 B header | checkpoints | hit log | records], each
- *             part 256-B aligned; written by doper_rollout_fwd only.
+ *   workspace (doper_rollout_workspace_bytes): [256 B header | hand-over flags u32[B] | checkpoints | hit log |
+ *             records | hand-over entries 32 B x B | 256 B], each part 256-B aligned; written by
+ *             doper_rollout_fwd only.  Header: int32 record count at offset 0, finished-block counter at 16,
+ *             hand-over queue counters at 32 (entries pushed) and 36 (entries claimed by tail workers).
  *   backward scratch (doper_rollout_bwd_scratch_bytes): one 4x4 binary64 Jacobian per record
  *             capacity; written by doper_rollout_bwd (so that the forward's workspace stays
  *             read-only for the backward: XLA input buffers are immutable, and two backward calls
@@ -201,6 +203,10 @@ typedef struct {
                                bit 24: doper_value_and_grad keeps forward, loss and backward as separate launches
                                       (default up to 1,024 balls on the pipelined forward: ONE launch, each block
                                       pulls the gradient of its own balls back as soon as they have finished);
+                               bit 25: one-thread-per-ball forward (large batches): keep a ball in sliding contact
+                                      in its warp (default: after 8 collided steps in a row it is handed to a
+                                      tail-worker warp that runs it alone — its serial chain otherwise sets the
+                                      duration of the whole launch);
                                bit 23: with lanes_per_ball = 8, 16 or 32: the pipelined kernel with that window
                                       length (speculated steps per producer / consumer hand-over);
                                bit 19: no collision records (the backward replays every collided
@@ -225,8 +231,9 @@ int32_t doper_rollout_ckpt_every(const doper_rollout_desc* d);
 int32_t doper_rollout_log_ball_major(const doper_rollout_desc* d);
 
 /* Name of the kernel the library will launch for this rollout (backward = 0: doper_rollout_fwd, 1: doper_rollout_bwd,
- * 2: the backward inside doper_value_and_grad, which may be fused into the forward launch); a static string, for
- * benchmark / profile reports. */
+ * 2: the backward inside doper_value_and_grad, which may be fused into the forward launch; 3: the second kernel
+ * doper_rollout_fwd launches behind the main one — the hand-over drain of the one-thread-per-ball plan — or "");
+ * a static string, for benchmark / profile reports. */
 const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backward);
 
 /* Bytes of the forward's workspace (header + checkpoints + hit log + collision records). */

@@ -803,6 +803,43 @@ def test_baked_bouncy_regime_and_gradients(sim, cref, n_balls):
     assert_bitexact(gv, ref["grad_v0"], "gradient (sequential backward)")
 
 
+@pytest.mark.parametrize("per_env", [False, True])
+@pytest.mark.parametrize("n_balls", [333, 4096])
+def test_contact_handover_is_bitexact(sim, cref, n_balls, per_env):
+    """One thread per ball: a ball that collides step after step is handed to a tail-worker warp (or to the drain
+    kernel).  Same hit flags, collision indices, final states and (sequential-backward) gradients as the oracle and
+    as the same kernel with the hand-over switched off; and the hand-over must actually happen here."""
+    ball_sim, geo = sim
+    w = syn.make_workload("c2", n_balls=n_balls)
+    consts = dict(w["constants"]); consts["attractor_strength"] = 2000.0
+    n = 400
+    c = onp.make_constants(consts)
+    dt = np.float32((n / 1000) / n)
+    segs = w["segments"]
+    ref = cref.value_and_grad(n, dt, c, w["attractor"], w["target"], segs, w["x0"], w["v0"])
+    scene = np.broadcast_to(segs, (n_balls,) + segs.shape).copy() if per_env else segs
+    on = _opts(ball_sim, pipelined=False, baked_lanes=1)
+    off = _opts(ball_sim, pipelined=False, baked_lanes=1, contact_handover=False)
+    got = ball_sim.rollout_history(n / 1000, n, scene, w["x0"], w["v0"], w["attractor"], consts, on)
+    base = ball_sim.rollout_history(n / 1000, n, scene, w["x0"], w["v0"], w["attractor"], consts, off)
+    assert got["handed_over"] > 0 and base["handed_over"] == 0
+    for h in (got, base):
+        assert np.array_equal(h["hit"], ref["hit"]) and np.array_equal(h["idx"][ref["hit"]], ref["idx"][ref["hit"]])
+        assert_bitexact(h["x_T"], ref["x_T"], "x_T")
+        assert_bitexact(h["v_T"], ref["v_T"], "v_T")
+    assert np.array_equal(got["checkpoints"].view(np.uint32), base["checkpoints"].view(np.uint32))
+    for o in (on, off):
+        o.sequential_backward = True
+        (_, (xT, vT)), gv = ball_sim.vmapped_grad_and_value(n / 1000, n, scene, w["x0"], w["v0"], w["target"], w["attractor"], consts, o)
+        assert_bitexact(vT, ref["v_T"], "v_T")
+        assert_bitexact(gv, ref["grad_v0"], "gradient (sequential backward)")
+    on.sequential_backward = False
+    (_, _), gd = ball_sim.vmapped_grad_and_value(n / 1000, n, scene, w["x0"], w["v0"], w["target"], w["attractor"], consts, on)
+    off.sequential_backward = False
+    (_, _), gd0 = ball_sim.vmapped_grad_and_value(n / 1000, n, scene, w["x0"], w["v0"], w["target"], w["attractor"], consts, off)
+    assert_bitexact(gd, gd0, "default (binary64) backward with / without the hand-over")
+
+
 def test_baked_far_points_outside_grid_and_nonfinite(sim, cref):
     """Balls that start (and fly) outside the baked grid, far outside it (|p| > 2 M: exact path), and
     non-finite states: same results as the oracle."""
