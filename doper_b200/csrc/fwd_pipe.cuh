@@ -208,12 +208,23 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
         int committed = active ? 0 : n;  // steps of my ball that are final (the same value in every lane of the ball)
         int epoch = 0;
         bool finished = false;
+        // the collided step of this thread whose record is still to be written (see below)
+        bool pr_on = false;
+        int pr_slot = 0, pr_t = 0, pr_idx = 0;
+        float pr_x = 0.0f, pr_y = 0.0f, pr_vx = 0.0f, pr_vy = 0.0f;
+        auto flush_record = [&]() {
+            if (!pr_on) return;
+            const int pl = record_commit(p.sink, pr_slot, ball, pr_t, pr_x, pr_y, pr_vx, pr_vy, pr_idx);
+            if (hl) hl[(int64_t)pr_t * p.hl_st] = pack_log(pl, true, clip_bits(pr_vx, pr_vy));
+            pr_on = false;
+        };
         PIPE_T0();
         for (int k = 0;; ++k) {
             named_barrier(1, GT);  // B_k
             const bool done = group_done(k);
             PIPE_MARK(0);
             if (done) break;
+            flush_record();  // a collision of the previous window
             const int buf = k & 1;
 #if defined(DOPER_PIPE_ABLATE) && DOPER_PIPE_ABLATE == 0
             if (k >= (n + U - 1) / U) { finished = true; if (lane == 0) sh.fin_at[cw] = k + 1; }  // timing experiment: barriers only
@@ -246,41 +257,39 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
             const int n_commit = hit ? f + 1 : nv;
             State r;
             r.x = r.y = r.vx = r.vy = r.ax = r.ay = 0.0f;
-            int payload = 0, extra = 0;
+            int extra = 0;
             if (hit && j == f) {  // my step: resolve it, post the state after it
                 State s1;
                 free_step(s.x, s.z, s.y, s.w, c, s1);  // the candidate again, with its acceleration (resolve needs it)
-                const int slot = record_reserve(p.sink);  // first: the atomic's round trip overlaps the resolve
                 r = resolve(s.x, s.z, s.y, s.w, s1, sc.q[idx], c);
-                payload = record_commit(p.sink, slot, ball, ts0 + f, s.x, s.z, s.y, s.w, idx);
+                // The record's slot is an atomic's round trip to L2, and whoever consumes it waits the trip out (a call
+                // in between does too: scoreboards do not survive one).  So the record of a collided step stays PENDING
+                // in this thread's registers — slot reserved, nothing consumed — until the thread's next collision or
+                // the next window, and record + log word are written then (flush_record).
+                flush_record();
+                pr_slot = record_reserve(p.sink);
+                pr_on = true; pr_t = ts0 + f; pr_idx = idx; pr_x = s.x; pr_y = s.z; pr_vx = s.y; pr_vy = s.w;
                 // Contact mode: while the very next step collides again (resting / sliding contact, a bounce in a corner),
                 // this lane steps the ball itself — a restart through the producer costs ~1.5 windows per collision.  At
                 // most U steps per window, so that the other balls of the group keep moving.
                 State cur = r;
                 int tn = ts0 + f + 1;
-                // the log word of a contact step needs the slot that record_collision's atomic returns (~1 us round trip
-                // to L2): it is written one iteration later, so that the next step's arithmetic hides the latency
-                int pend_t = -1, pend_pl = 0;
-                uint32_t pend_clip = 0u;
                 while (extra < U && tn < n) {
                     State c1;
                     free_step(cur.x, cur.y, cur.vx, cur.vy, c, c1);
                     int i2;
                     if (!baked_hit(sc, bk, c1.x, c1.y, c.r, i2)) break;  // free flight again: the producer takes over from `cur`
-                    const int slot2 = record_reserve(p.sink);
                     if (p.ckpt) {
                         const bool at = kshift >= 0 ? (tn & (K - 1)) == 0 : (tn % K) == 0;
                         if (at) p.ckpt[(size_t)(kshift >= 0 ? tn >> kshift : tn / K) * p.B + ball] = make_float4(cur.x, cur.y, cur.vx, cur.vy);
                     }
-                    const uint32_t clip = clip_bits(cur.vx, cur.vy);
                     const State r2 = resolve(cur.x, cur.y, cur.vx, cur.vy, c1, sc.q[i2], c);
-                    const int pl = record_commit(p.sink, slot2, ball, tn, cur.x, cur.y, cur.vx, cur.vy, i2);
-                    if (hl && pend_t >= 0) hl[(int64_t)pend_t * p.hl_st] = pack_log(pend_pl, true, pend_clip);
-                    pend_t = tn; pend_pl = pl; pend_clip = clip;
+                    flush_record();  // the previous collided step: its slot arrived during this step's arithmetic
+                    pr_slot = record_reserve(p.sink);
+                    pr_on = true; pr_t = tn; pr_idx = i2; pr_x = cur.x; pr_y = cur.y; pr_vx = cur.vx; pr_vy = cur.vy;
                     cur = r2;
                     ++tn; ++extra;
                 }
-                if (hl && pend_t >= 0) hl[(int64_t)pend_t * p.hl_st] = pack_log(pend_pl, true, pend_clip);
                 if (extra > 0 && tn == n) { p.xT[ball] = make_float2(cur.x, cur.y); p.vT[ball] = make_float2(cur.vx, cur.vy); }
                 sh.mail_state[buf][b] = make_float4(cur.x, cur.vx, cur.y, cur.vy);
                 sh.mail_t[buf][b] = tn;
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
 #endif
                 const int ts = ts0 + j;
                 const bool h = hit && j == f;
-                if (hl) hl[(int64_t)ts * p.hl_st] = pack_log(h ? payload : 0, h, clip_bits(s.y, s.w));
+                if (hl && !h) hl[(int64_t)ts * p.hl_st] = pack_log(0, false, clip_bits(s.y, s.w));  // (a collided step: flush_record)
                 if (p.ckpt) {
                     const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
                     if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(s.x, s.z, s.y, s.w);
@@ -318,6 +327,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
             pt_acc[7] += 1;
 #endif
         }
+        flush_record();
         PIPE_FLUSH(8);
     }  // consumers
     if (!FUSED) return;
