@@ -36,6 +36,7 @@ struct FwdParams {
     unsigned int* done_blocks;  // zeroed counter in the workspace header
     // hand-over of balls in sliding / resting contact to tail-worker warps (rollout_fwd_baked_kernel<1>; null: off)
     DeferQueue defer;
+    int pipe_balls;  // rollout_fwd_pipe_kernel: ball slots of a block that are used (16, or fewer: see launch_fwd_pipe)
     double* jac;                // the backward's scratch: one 4x4 Jacobian per collision record (nullable)
 };
 

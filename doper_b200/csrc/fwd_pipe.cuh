@@ -81,11 +81,15 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 // batches of at most 148 blocks only — kFusedMaxBalls — where a second block per SM would not be used anyway; for
 // BASELINE configs[1] (256 blocks) the separate backward launches are faster: measured 0.151 ms per step against
 // 0.164 fused with the registers capped for two blocks per SM, 0.177 uncapped.)
-template <int U, bool FUSED>
-__global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1) rollout_fwd_pipe_kernel(const FwdParams p) {
+// PB: ball slots per block (16: a full producer warp; 8: half of it, for U = 16 — a collision stalls the window barrier
+// of PB - 1 other balls, and the launch ends with the block that collected the most collisions).
+template <int U, bool FUSED, int PB = kPipeBalls>
+__global__ void __launch_bounds__(32 * (1 + PB * U / 32), (U <= 16 && !FUSED) ? (PB == 8 ? 4 : 2) : 1)
+    rollout_fwd_pipe_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     static_assert(U == 8 || U == 16 || U == 32, "window length");
-    constexpr int CW = U / 2;          // consumer warps
+    static_assert(PB == kPipeBalls || (PB == 8 && U == 16 && !FUSED), "ball slots per block");
+    constexpr int CW = PB * U / 32;    // consumer warps
     constexpr int GT = 32 * (1 + CW);  // threads per group = per block
     constexpr unsigned kSeg = U == 32 ? 0xffffffffu : ((1u << U) - 1u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
     uint64_t* bar = reinterpret_cast<uint64_t*>(sbake + bbytes);
     PipeShared<U>& sh = *reinterpret_cast<PipeShared<U>*>(sbake + bbytes + 16);
 
-    const int64_t first = (int64_t)blockIdx.x * kPipeBalls;
+    const int64_t first = (int64_t)blockIdx.x * p.pipe_balls;  // (slots >= pipe_balls stay empty)
     const int n = p.n_steps;
     const Consts c = p.c;
 
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
         // ---------------------------------------------------------------------------------- producer
         const int b = lane >> 1, axis = lane & 1;
         const int64_t ball = first + b;
-        const bool active = ball < p.B;
+        const bool active = b < p.pipe_balls && ball < p.B;
         const float att = axis ? c.ay : c.ax;
         float pos = 0.0f, vel = 0.0f;
         if (active) {
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
         const int bl = lane / U, j = lane % U;       // my ball within the warp, my step within the window
         const int b = cw * BPW + bl;                 // my ball within the group
         const int64_t ball = first + b;
-        const bool active = ball < p.B;
+        const bool active = b < p.pipe_balls && ball < p.B;
         SceneView sc;
         BakeView bk;
         {
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
     const int bb = tid & 15, chunk = tid >> 4;
     const int64_t fb = first + bb;
     const int t0 = chunk * chunk_len, t1 = min(n, t0 + chunk_len);
-    const bool mine = tid < 16 * NC && fb < p.B && t0 < t1;
+    const bool mine = tid < 16 * NC && bb < p.pipe_balls && fb < p.B && t0 < t1;
     __shared__ double t16[8];
     if (tid == 0) { jl_count = 0; free_pow_table(cd, t16); }
     named_barrier(1, GT);
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(32 * (1 + U / 2), (U <= 16 && !FUSED) ? 2 : 1)
             for (int r = 0; r < 4; ++r) fold[((size_t)chunk * 16 + (k * 4 + r)) * 16 + bb] = g[k][r];
     }
     named_barrier(1, GT);
-    if (tid < 16 && first + tid < p.B) {
+    if (tid < p.pipe_balls && first + tid < p.B) {
         const int64_t fb = first + tid;
         const float2 xT = p.xT[fb];
         const float ex = xT.x - p.tgt_x, ey = xT.y - p.tgt_y;

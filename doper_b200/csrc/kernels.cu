@@ -433,16 +433,42 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
     return staged ? go(rollout_fwd_baked_kernel<G, true, MAXT_STAGED>) : go(rollout_fwd_baked_kernel<G, false, MAXT>);
 }
 
-template <int U, bool FUSED>
-int launch_fwd_pipe(cudaStream_t st, const FwdParams& p) {
+template <int U, bool FUSED, int PB>
+int launch_fwd_pipe_pb(cudaStream_t st, const FwdParams& p, int used_slots) {
     const int S_pad = scene_layout(1, p.S).S_pad;
     const size_t smem = (size_t)S_pad * 20 + bake_lists_bytes(S_pad) + 16 + sizeof(PipeShared<U>);
     if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(rollout_fwd_pipe_kernel<U, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        cudaFuncSetAttribute(rollout_fwd_pipe_kernel<U, FUSED, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DOPER_ERR_SMEM_LIMIT;
-    const unsigned grid = (unsigned)((p.B + kPipeBalls - 1) / kPipeBalls);
-    rollout_fwd_pipe_kernel<U, FUSED><<<grid, 32 * (1 + U / 2), smem, st>>>(p);
+    FwdParams q = p;
+    q.pipe_balls = used_slots < 1 ? 1 : (used_slots > PB ? PB : used_slots);
+    const unsigned grid = (unsigned)((p.B + q.pipe_balls - 1) / q.pipe_balls);
+    rollout_fwd_pipe_kernel<U, FUSED, PB><<<grid, 32 * (1 + PB * U / 32), smem, st>>>(q);
     return launch_status();
+}
+
+// Ball slots per block.  A collision holds up the window barrier of its block, so a block should carry as few balls as
+// the machine allows: (a) small batches leave block slots of the GPU empty — they use only ceil(B / slots) of a
+// block's 16 ball slots (16 balls: 0.039 -> 0.033 ms forward with 2 per block; 1,024 balls 0.090 -> 0.080 with 4);
+// (b) DOPER_PIPE_PB / DOPER_PIPE_BALLS pin the block shape / the used slots (tools/tune_env.py).
+template <int U, bool FUSED>
+int launch_fwd_pipe(cudaStream_t st, const FwdParams& p) {
+    // (c) the default window with separate backward launches: blocks of 8 ball slots (5 warps, four resident per SM)
+    //     while the batch fits one wave of them — BASELINE configs[1]: forward 0.1126 -> 0.1065 ms
+    int pb = kPipeBalls;
+    if (U == 16 && !FUSED && p.B <= (int64_t)8 * 4 * sm_count()) pb = 8;
+    if (const char* e = getenv("DOPER_PIPE_PB")) pb = atoi(e) == 8 ? 8 : kPipeBalls;
+    if (!(U == 16 && !FUSED)) pb = kPipeBalls;
+    const int resident = (FUSED || U > 16) ? 1 : (pb == 8 ? 4 : 2);  // blocks per SM (launch bounds of the kernel)
+    const int64_t slots = (int64_t)sm_count() * resident;
+    int used = (int)((p.B + slots - 1) / slots);
+    if (used < 2) used = 2;
+    if (used > pb) used = pb;
+    if (const char* e = getenv("DOPER_PIPE_BALLS")) { const int v = atoi(e); if (v >= 1 && v <= pb) used = v; }
+    if constexpr (U == 16 && !FUSED) {
+        if (pb == 8) return launch_fwd_pipe_pb<U, FUSED, 8>(st, p, used);
+    }
+    return launch_fwd_pipe_pb<U, FUSED, kPipeBalls>(st, p, used);
 }
 
 template <bool FUSED>
@@ -787,7 +813,8 @@ int rollout_fwd_impl(doper_stream_t stream, const doper_rollout_desc* d, const v
     p.traj_a = reinterpret_cast<float2*>(traj_a);
     p.ckpt = nullptr; p.hitlog = nullptr; p.sink.rec = nullptr; p.sink.count = nullptr; p.sink.cap = 0;
     p.tgt_x = p.tgt_y = 0.0f; p.loss_sum = nullptr; p.loss_pb = nullptr; p.g_v0 = nullptr; p.g_x0 = nullptr; p.done_blocks = nullptr; p.jac = nullptr;
-    p.defer.entry = nullptr; p.defer.flag = nullptr; p.defer.alloc = p.defer.head = nullptr; p.defer.cap = 0;
+    p.defer.entry = nullptr; p.defer.flag = nullptr; p.defer.alloc = p.defer.head = nullptr; p.defer.cap = 0; p.defer.tail_warps = 0;
+    p.pipe_balls = kPipeBalls;
     if (fused) {
         if (!ws || !fa->target || !fa->loss_sum || !fa->loss_pb || !fa->v0_bar) return DOPER_ERR_NULL_PTR;
         p.tgt_x = fa->target[0]; p.tgt_y = fa->target[1];
