@@ -110,6 +110,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.mask, self.stop_flag, self.max_mhz, self.err = index, [], 0, False, None, None
+        self.ready, self.window, self.handle, self.nv = threading.Event(), None, None, None
 
     def run(self):
         try:
@@ -117,19 +118,36 @@ class ClockSampler(threading.Thread):
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.handle, self.nv = h, nv
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(
-                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(
-                    nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.sample()
+                self.ready.set()
                 time.sleep(0.002)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
+            self.ready.set()
+
+    def sample(self):
+        """One (time, SM MHz, throttle reasons) sample; also called from the main thread while the timed steps are
+        still running on the GPU, so that a timed region of a few milliseconds is never left without one."""
+        nv, h = self.nv, self.handle
+        if nv is None:
+            return
+        mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(
+            nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        self.samples.append((time.perf_counter(), mhz, mask))
 
     def summary(self):
-        reasons = [n for b, n in self.REASONS.items() if self.mask & b and n != "gpu_idle"]
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples),
+        """Median SM clock and the union of throttle reasons over the samples taken inside the timed region
+        (`window` = its perf_counter bounds; samples before it are idle clocks and do not count)."""
+        inside = [x for x in self.samples if self.window is None or self.window[0] <= x[0] <= self.window[1]]
+        mask = 0
+        for x in inside:
+            mask |= x[2]
+        reasons = [n for b, n in self.REASONS.items() if mask & b and n != "gpu_idle"]
+        return {"sm_mhz": float(np.median([x[1] for x in inside])) if inside else None,
+                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(inside),
                 **({"error": self.err} if self.err else {})}
 
 
@@ -426,7 +444,7 @@ def ours(args):
 
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
-    time.sleep(0.01)
+    sampler.ready.wait(5.0)  # NVML is initialised and sampling before the timed region starts
     K = args.steps
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     pending = None
@@ -440,8 +458,13 @@ def ours(args):
         else:
             one_step()
         ev[k][2].record()
+    try:
+        sampler.sample()  # the steps just enqueued are still running: a sample under load whatever the region's length
+    except Exception:  # pragma: no cover
+        pass
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    sampler.window = (t_wall, time.perf_counter())
     sampler.stop_flag = True
     sampler.join(timeout=2)
     step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])

@@ -31,7 +31,7 @@ for row in rows[2:]:
     short = name.split("::")[-1]
     short = short.replace(" ", "")
     import re
-    short = re.sub(r"pipe_kernel<(\d+),0>", r"pipe_kernel<\1>", short)  # the name doper_rollout_plan_name reports
+    short = re.sub(r"pipe_kernel<(\d+),0(?:,\d+)?>", r"pipe_kernel<\1>", short)  # the name doper_rollout_plan_name reports
     if short in seen:
         continue
     seen.add(short)
