@@ -269,6 +269,9 @@ __global__ void __launch_bounds__(128) rollout_bwd_jacobian_kernel(const BwdPara
         const float4 st = r[0];
         const int4 m = reinterpret_cast<const int4*>(r)[1];
         const int64_t ball = ((int64_t)m.w << 32) | (uint32_t)m.x;
+        // a slot no collision was written to (the unused tail of a tail worker's slab: stale bytes) — nothing refers
+        // to its matrix, but its indices must not reach the scene
+        if ((unsigned)m.z >= (unsigned)p.S || ball < 0 || ball >= p.B) continue;
         double J[16];
         hit_jacobian_d(st, __ldg(scene_q(p, ball) + m.z), __ldg(scene_s1(p, ball) + m.z), cd, J, col, col + 1);
         double* out = p.jac + (size_t)i * 16 + col;

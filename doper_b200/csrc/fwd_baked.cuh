@@ -165,6 +165,8 @@ __device__ __forceinline__ void baked_run_ball(const FwdParams& p, const SceneVi
     int ck_i = p.ckpt ? (t + K - 1) / K : 0;
     int next_ck = p.ckpt ? ck_i * K : n + 1;  // checkpoint counter instead of shift / mask tests
     int streak = 0;
+    const bool worker = !may_defer && p.defer.entry != nullptr;  // a handed-over ball: record slots by the slab
+    RecordSlab slab;
     for (; t < n; ++t) {
         State my;
         if (!free_step_fast(x, y, vx, vy, c, my)) free_step(x, y, vx, vy, c, my);  // a numerator left the fast division's range
@@ -178,7 +180,7 @@ __device__ __forceinline__ void baked_run_ball(const FwdParams& p, const SceneVi
             // chain when the warp waits for it, profiles/r2_ncu_contact_chain.txt).  Reserved here, consumed after
             // everything else of the step.  (Inlining the resolve here was measured slower: 3.14 -> 3.31 ms for
             // the ball in sliding contact alone.)
-            slot = record_reserve(p.sink);
+            slot = worker ? record_reserve_slab(p.sink, slab) : record_reserve(p.sink);
             out = resolve(x, y, vx, vy, my, sc.q[idx], c);
         }
         if (t == next_ck) {
@@ -210,9 +212,7 @@ __device__ __forceinline__ void baked_run_ball(const FwdParams& p, const SceneVi
 // free flight, look-up and resolve (uniform control flow, no divergence), and the narrow phase — half of a collided
 // step's serial chain when one thread walks a corner's list entry by entry — gives every list entry its own lane and
 // takes the (distance, index) minimum by shuffles: the same keys, the same minimum, the same bits.  Lane 0 owns the
-// stores.  The record of a collided step is committed one step LATE (its slot is an atomic's round trip to L2, and a
-// warp that consumes the slot in the same step waits it out): the atomic is issued at the end of step t and consumed
-// behind the free flight and narrow phase of step t + 1.
+// stores; record slots come by the slab (physics.cuh record_reserve_slab): no atomic on the chain.
 __device__ __forceinline__ void baked_run_ball_warp(const FwdParams& p, const SceneView& sc, const BakeView& bk, const Consts& c,
                                                     const int64_t ball, int t, float x, float y, float vx, float vy) {
     const int n = p.n_steps, K = p.K, lane = threadIdx.x & 31;
@@ -221,11 +221,7 @@ __device__ __forceinline__ void baked_run_ball_warp(const FwdParams& p, const Sc
     int32_t* hlp = p.hitlog ? p.hitlog + ball * p.hl_sb + (int64_t)t * hl_step : nullptr;
     int ck_i = p.ckpt ? (t + K - 1) / K : 0;
     int next_ck = p.ckpt ? ck_i * K : n + 1;
-    // lane 0: the collided step whose record is still to be committed
-    bool pend = false;
-    int pend_slot = 0, pend_t = 0, pend_idx = 0;
-    float pend_x = 0.f, pend_y = 0.f, pend_vx = 0.f, pend_vy = 0.f;
-    int32_t* pend_hl = nullptr;
+    RecordSlab slab;  // lane 0: record slots by the slab (one atomic per kRecordSlab collisions)
     for (; t < n; ++t) {
         State my;
         if (!free_step_fast(x, y, vx, vy, c, my)) free_step(x, y, vx, vy, c, my);
@@ -255,17 +251,9 @@ __device__ __forceinline__ void baked_run_ball_warp(const FwdParams& p, const Sc
         State out = my;
         if (hit) out = resolve(x, y, vx, vy, my, sc.q[idx], c);
         if (lane == 0) {
-            if (pend) {  // the previous collided step: its slot has arrived by now
-                const int payload = record_commit(p.sink, pend_slot, ball, pend_t, pend_x, pend_y, pend_vx, pend_vy, pend_idx);
-                if (pend_hl) *pend_hl = pack_log(payload, true, clip_bits(pend_vx, pend_vy));
-                pend = false;
-            }
-            if (hit) {
-                pend_slot = record_reserve(p.sink);
-                pend = true; pend_t = t; pend_idx = idx; pend_x = x; pend_y = y; pend_vx = vx; pend_vy = vy; pend_hl = hlp;
-            } else if (hlp) {
-                *hlp = pack_log(0, false, clip_bits(vx, vy));
-            }
+            int payload = 0;
+            if (hit) payload = record_commit(p.sink, record_reserve_slab(p.sink, slab), ball, t, x, y, vx, vy, idx);
+            if (hlp) *hlp = pack_log(payload, hit, clip_bits(vx, vy));
             if (t == next_ck) p.ckpt[(size_t)ck_i * p.B + ball] = make_float4(x, y, vx, vy);
             if (want_traj) {
                 const size_t o = (size_t)t * p.B + ball;
@@ -279,10 +267,6 @@ __device__ __forceinline__ void baked_run_ball_warp(const FwdParams& p, const Sc
         x = out.x; y = out.y; vx = out.vx; vy = out.vy;
     }
     if (lane == 0) {
-        if (pend) {
-            const int payload = record_commit(p.sink, pend_slot, ball, pend_t, pend_x, pend_y, pend_vx, pend_vy, pend_idx);
-            if (pend_hl) *pend_hl = pack_log(payload, true, clip_bits(pend_vx, pend_vy));
-        }
         p.xT[ball] = make_float2(x, y);
         p.vT[ball] = make_float2(vx, vy);
     }

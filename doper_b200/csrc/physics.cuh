@@ -130,6 +130,18 @@ __device__ __forceinline__ int record_reserve(const HitSink& s) {
     return slot;
 }
 
+// A thread that runs ONE ball in sliding contact (tail workers) reserves record slots a SLAB at a time: one atomic per
+// kRecordSlab collisions instead of one per collided step, whose round trip would sit on the ball's serial chain.  What
+// is left of the last slab when the ball ends stays unused: the record area may hold slots no log word refers to
+// (stale bytes; the Jacobian pass validates a record's indices before it touches the scene).
+constexpr int kRecordSlab = 128;
+struct RecordSlab { int next = 0, end = 0; };
+__device__ __forceinline__ int record_reserve_slab(const HitSink& s, RecordSlab& sl) {
+    if (s.rec == nullptr || s.cap <= 0) return 0x7fffffff;
+    if (sl.next == sl.end) { sl.next = atomicAdd(s.count, kRecordSlab); sl.end = sl.next + kRecordSlab; }
+    return sl.next++;
+}
+
 __device__ __forceinline__ int record_commit(const HitSink& s, int slot, int64_t ball, int t, float x, float y, float vx,
                                              float vy, int idx) {
     if (slot < s.cap) {  // (no record area: slot = INT_MAX)

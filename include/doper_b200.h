@@ -41,7 +41,8 @@
  *             [n_steps][B] or [B][n_steps] (see doper_rollout_log_ball_major)
  *   collision records  32 B each, appended by the forward in arrival order: float (x,y,vx,vy) at the
  *             START of the collided step, then int32 (ball low word, step, segment index, ball high
- *             word).  The record count is the int32 at offset 0 of the workspace.
+ *             word).  The int32 at offset 0 of the workspace counts the slots handed out; a slot that no log
+ *             word refers to (the unused rest of a slab a tail worker reserved) holds stale bytes.
  *   checkpoints [ceil(n_steps/ckpt_every)][B][4] = (x,y,vx,vy) at the START of step k*ckpt_every
  *   workspace (doper_rollout_workspace_bytes): [256 B header | hand-over flags u32[B] | checkpoints | hit log |
  *             records | hand-over entries 32 B x B | 256 B], each part 256-B aligned; written by
