@@ -8,8 +8,8 @@
 // for both axes in one thread, executed by a warp that has the scheduler almost to itself) plus ~1,500 cycles of
 // cell look-ups, votes, shuffles and log stores that sit between two rounds of the same ball.
 //
-// Here a block serves 16 balls with one PRODUCER warp and U / 2 CONSUMER warps that never wait for each other inside
-// a window of U steps (U = 16 by default: 9 warps per block):
+// Here a block serves PB ball slots (16, or 8: half a producer warp) with one PRODUCER warp and PB U / 32 CONSUMER warps
+// that never wait for each other inside a window of U steps (U = 16, PB = 8 by default: 5 warps per block):
 //
 //   PRODUCER warp   lane = (ball, axis): the x and the y coordinate of a ball integrated by two lanes (the free-flight
 //                   step acts on each axis separately: physics.cuh axis_step_acc — the same operations, hence the
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(32 * (1 + PB * U / 32), (U <= 16 && !FUSED) ? 
     rollout_fwd_pipe_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     static_assert(U == 8 || U == 16 || U == 32, "window length");
-    static_assert(PB == kPipeBalls || (PB == 8 && U == 16 && !FUSED), "ball slots per block");
+    static_assert(PB == kPipeBalls || (PB == 8 && U <= 16 && !FUSED), "ball slots per block");
     constexpr int CW = PB * U / 32;    // consumer warps
     constexpr int GT = 32 * (1 + CW);  // threads per group = per block
     constexpr unsigned kSeg = U == 32 ? 0xffffffffu : ((1u << U) - 1u);

@@ -184,7 +184,7 @@ bool use_pipe(const doper_rollout_desc* d) {
 }
 // One launch for forward + L1 loss + backward (rollout_fwd_pipe_kernel<U, true>): the pipelined plan, the default
 // (binary64) backward, collision records enabled, and a staged scene large enough to hold the fold's matrices.
-constexpr int64_t kFusedMaxBalls = 1024;  // 64 blocks: the fused variant runs one block per SM (fwd_pipe.cuh)
+constexpr int64_t kFusedMaxBalls = 1024;  // the fused variant runs one block per SM (fwd_pipe.cuh): at most 148 blocks of ceil(B / 148) balls
 bool fused_ok(const doper_rollout_desc* d) {
     if (!use_pipe(d) || (d->flags & 2) || record_capacity(d) <= 0 || d->n_steps < 1 || d->B > kFusedMaxBalls) return false;
     const int S_pad = scene_layout(1, d->S).S_pad;
@@ -456,16 +456,16 @@ int launch_fwd_pipe(cudaStream_t st, const FwdParams& p) {
     // (c) the default window with separate backward launches: blocks of 8 ball slots (5 warps, four resident per SM)
     //     while the batch fits one wave of them — BASELINE configs[1]: forward 0.1126 -> 0.1065 ms
     int pb = kPipeBalls;
-    if (U == 16 && !FUSED && p.B <= (int64_t)8 * 4 * sm_count()) pb = 8;
+    if (U <= 16 && !FUSED && p.B <= (int64_t)8 * 4 * sm_count()) pb = 8;
     if (const char* e = getenv("DOPER_PIPE_PB")) pb = atoi(e) == 8 ? 8 : kPipeBalls;
-    if (!(U == 16 && !FUSED)) pb = kPipeBalls;
+    if (!(U <= 16 && !FUSED)) pb = kPipeBalls;
     const int resident = (FUSED || U > 16) ? 1 : (pb == 8 ? 4 : 2);  // blocks per SM (launch bounds of the kernel)
     const int64_t slots = (int64_t)sm_count() * resident;
     int used = (int)((p.B + slots - 1) / slots);
     if (used < 2) used = 2;
     if (used > pb) used = pb;
     if (const char* e = getenv("DOPER_PIPE_BALLS")) { const int v = atoi(e); if (v >= 1 && v <= pb) used = v; }
-    if constexpr (U == 16 && !FUSED) {
+    if constexpr (U <= 16 && !FUSED) {
         if (pb == 8) return launch_fwd_pipe_pb<U, FUSED, 8>(st, p, used);
     }
     return launch_fwd_pipe_pb<U, FUSED, kPipeBalls>(st, p, used);

@@ -1,5 +1,5 @@
 """Forward time of a workload's default plan under several values of a launcher tuning variable (read per launch):
-python tools/tune_env.py DOPER_PIPE_BALLS 16,12,8,4 [workload] [balls]      (also DOPER_BAKED_THREADS)
+python tools/tune_env.py DOPER_PIPE_BALLS 16,12,8,4 [workload] [balls] [window]      (also DOPER_BAKED_THREADS)
 Checks that x_T / v_T do not depend on the value."""
 import ctypes
 import json
@@ -19,6 +19,7 @@ from doper_b200.sim.jax_geometry import JaxScene
 env, values = sys.argv[1], sys.argv[2].split(",")
 name = sys.argv[3] if len(sys.argv) > 3 else "c2"
 balls = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+window = int(sys.argv[5]) if len(sys.argv) > 5 else 0  # pin the pipelined kernel's window length (8, 16, 32)
 dev = torch.device("cuda")
 w = syn.make_workload(name, n_balls=balls) if balls else syn.make_workload(name)
 B, n = w["x0"].shape[0], w["n_steps"]
@@ -26,7 +27,7 @@ scene = JaxScene(w["segments"])
 x0, v0 = torch.tensor(w["x0"], device=dev), torch.tensor(w["v0"], device=dev)
 st = torch.cuda.current_stream().cuda_stream
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-desc = ball_sim._make_desc(B, scene, w["sim_time"], n, w["attractor"], w["constants"], ball_sim.RolloutOptions())
+desc = ball_sim._make_desc(B, scene, w["sim_time"], n, w["attractor"], w["constants"], ball_sim.RolloutOptions(pipe_window=window) if window else ball_sim.RolloutOptions())
 _, sws = scene.prepared(dev, float(desc.consts[0]))
 bufs = ball_sim._Buffers.get(dev, desc)
 out = torch.empty((2, B, 2), device=dev)
