@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams
                             continue;
                         }
                         if (*reinterpret_cast<volatile int*>(&s_normal_left) <= 0) break;
-                        __nanosleep(200);
+                        __nanosleep(1000);  // ~600 polling warps on one L2 line: a pick-up a microsecond late costs nothing
                     }
                 }
                 claimed = __shfl_sync(0xffffffffu, claimed, 0);

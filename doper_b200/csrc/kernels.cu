@@ -837,8 +837,10 @@ int rollout_fwd_impl(doper_stream_t stream, const doper_rollout_desc* d, const v
         if (use_defer(d) && !(traj_x || traj_v || traj_a)) {
             p.defer.entry = reinterpret_cast<DeferEntry*>(base + w.defer_off);
             p.defer.flag = reinterpret_cast<unsigned int*>(base + w.flag_off);
-            p.defer.alloc = reinterpret_cast<unsigned int*>(base + 32);
-            p.defer.head = reinterpret_cast<unsigned int*>(base + 36);
+            // (their own 128-B line: the tail workers poll these two words, the record counter at offset 0 is hit by
+            // every collision's atomic)
+            p.defer.alloc = reinterpret_cast<unsigned int*>(base + 128);
+            p.defer.head = reinterpret_cast<unsigned int*>(base + 132);
             p.defer.cap = (int)(d->B < 0x7fffffff ? d->B : 0x7fffffff);
             zero = w.ckpt_off;  // + the flags
         }

@@ -525,7 +525,7 @@ def rollout_history(sim_time, n_steps, scene, coordinate_init, velocity_init, at
     if want_trajectory:
         th = traj.cpu().numpy()
         t = BallState(th[0], th[1], th[2])
-    handed_over = int(ws[32:36].view(torch.int32).item())  # balls finished by tail workers (contact hand-over)
+    handed_over = int(ws[128:132].view(torch.int32).item())  # balls finished by tail workers (contact hand-over)
     return {"x_T": out[0].cpu().numpy(), "v_T": out[1].cpu().numpy(), "idx": idx, "hit": hit, "handed_over": handed_over,
             "hitlog": hl, "checkpoints": ckpt, "trajectory": t, "records": rec, "records_seen": n_rec_seen,
             "record_capacity": cap,

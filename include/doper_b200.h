@@ -47,7 +47,7 @@
  *   workspace (doper_rollout_workspace_bytes): [256 B header | hand-over flags u32[B] | checkpoints | hit log |
  *             records | hand-over entries 32 B x B | 256 B], each part 256-B aligned; written by
  *             doper_rollout_fwd only.  Header: int32 record count at offset 0, finished-block counter at 16,
- *             hand-over queue counters at 32 (entries pushed) and 36 (entries claimed by tail workers).
+ *             hand-over queue counters at 128 (entries pushed) and 132 (entries claimed by tail workers).
  *   backward scratch (doper_rollout_bwd_scratch_bytes): one 4x4 binary64 Jacobian per record
  *             capacity; written by doper_rollout_bwd (so that the forward's workspace stays
  *             read-only for the backward: XLA input buffers are immutable, and two backward calls

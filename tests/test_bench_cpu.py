@@ -36,3 +36,21 @@ def test_product_arm_fails_loudly_without_cuda():
     out = _run("--steps", "1", "--warmup", "1", "--no-cpu")
     assert out.returncode != 0
     assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]  # no number from a fallback
+
+
+def test_clock_sampler_counts_only_samples_inside_the_timed_region():
+    """bench.py's `clocks`: the median SM clock and the throttle reasons come from the samples taken inside the timed
+    region (idle clocks before it do not count), and a region without samples reports None, never an idle clock."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.max_mhz = 1965
+    s.samples = [(0.5, 600, 0x1), (1.1, 1965, 0x0), (1.2, 1950, 0x4), (1.3, 1965, 0x0), (2.5, 700, 0x8)]
+    s.window = (1.0, 2.0)
+    out = s.summary()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"] and out["sm_max_mhz"] == 1965
+    s.window = (3.0, 4.0)
+    assert s.summary()["sm_mhz"] is None and s.summary()["samples"] == 0
