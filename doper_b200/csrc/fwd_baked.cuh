@@ -198,7 +198,7 @@ __device__ __forceinline__ void baked_run_ball(const FwdParams& p, const SceneVi
         x = out.x; y = out.y; vx = out.vx; vy = out.vy;
         if (may_defer) {
             streak = hit ? streak + 1 : 0;
-            if (streak >= kDeferStreak && n - (t + 1) >= kDeferMinSteps) {
+            if (streak >= p.defer.streak && n - (t + 1) >= kDeferMinSteps) {
                 defer_push(p.defer, ball, t + 1, x, y, vx, vy);
                 return;
             }

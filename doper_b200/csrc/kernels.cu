@@ -416,6 +416,8 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
         FwdParams q = p;
         const int tail = (G == 1 && p.defer.entry) ? (max_threads >= 1024 ? 4 : 1) : 0;
         q.defer.tail_warps = tail;
+        q.defer.streak = kDeferStreak;
+        if (const char* e = getenv("DOPER_DEFER_STREAK")) { const int v = atoi(e); if (v >= 1) q.defer.streak = v; }  // tuning
         const int threads = balanced_block(p.B * G, max_threads - 32 * tail, [&](int t) {
             int nb = 0;
             return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, t + 32 * tail, smem) == cudaSuccess ? nb : 0;
@@ -813,7 +815,7 @@ int rollout_fwd_impl(doper_stream_t stream, const doper_rollout_desc* d, const v
     p.traj_a = reinterpret_cast<float2*>(traj_a);
     p.ckpt = nullptr; p.hitlog = nullptr; p.sink.rec = nullptr; p.sink.count = nullptr; p.sink.cap = 0;
     p.tgt_x = p.tgt_y = 0.0f; p.loss_sum = nullptr; p.loss_pb = nullptr; p.g_v0 = nullptr; p.g_x0 = nullptr; p.done_blocks = nullptr; p.jac = nullptr;
-    p.defer.entry = nullptr; p.defer.flag = nullptr; p.defer.alloc = p.defer.head = nullptr; p.defer.cap = 0; p.defer.tail_warps = 0;
+    p.defer.entry = nullptr; p.defer.flag = nullptr; p.defer.alloc = p.defer.head = nullptr; p.defer.cap = 0; p.defer.tail_warps = 0; p.defer.streak = kDeferStreak;
     p.pipe_balls = kPipeBalls;
     if (fused) {
         if (!ws || !fa->target || !fa->loss_sum || !fa->loss_pb || !fa->v0_bar) return DOPER_ERR_NULL_PTR;

@@ -172,6 +172,7 @@ struct DeferQueue {
     unsigned int* head;    // entries claimed
     int cap;
     int tail_warps;        // warps per block that only serve the queue (the block's last warps)
+    int streak;            // consecutive collided steps after which a ball is handed over
 };
 
 __device__ __forceinline__ uint32_t clip_bits(float vx, float vy) {
