@@ -278,7 +278,7 @@ __device__ __forceinline__ void baked_run_ball_warp(const FwdParams& p, const Sc
 template <int G, bool STAGED, int MAXT>
 __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tail_threads = (G == 1 && p.defer.entry) ? 32 * p.defer.tail_warps : 0;  // the block's last warps: tail workers
+    const int tail_threads = p.defer.entry ? 32 * p.defer.tail_warps : 0;  // the block's last warps: tail workers
     const int BPB = ((int)blockDim.x - tail_threads) / G;  // balls per block
     constexpr unsigned kLow = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
     const int tid = threadIdx.x, lane = tid % G, gbase = (tid & 31) - lane;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams
         sc.rl = reinterpret_cast<const float*>(p.scene_ws + L.rl_off) + env * L.S_pad;
         bake_view_arrays(bk, gbake + sizeof(BakeHeader), L.S_pad);
         sc.S = p.S; sc.S_pad = L.S_pad; sc.scale = hdr.scale; sc.weird = hdr.weird | p.force_exact;
-        if (G == 1) {
+        if (p.defer.entry) {
             if (tid == 0) s_normal_left = ((int)blockDim.x - tail_threads) / 32;
             __syncthreads();
         }
@@ -337,61 +337,55 @@ __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams
     int t = active ? 0 : n;
     int T = G;  // speculation length of the next round (1 after a collision at the round's first step)
 
-    if constexpr (G == 1) {
-        // One thread per ball (large batches): the step loop with nothing warp-wide and nothing recomputed
-        // (baked_run_ball).  A ball in sliding contact collides on every step: a ~2 us serial chain per step (its own
-        // ~600 dependent instructions plus the divergent work of the 31 other lanes) that used to set the duration
-        // of the whole kernel — BASELINE configs[4]: one ball of 131,072 collides on 1,972 of 2,000 steps, and the
-        // SMs were busy 49 % of the kernel (profiles/r2_ncu_fwd_baked1_c5.txt).  Such a ball is handed to a
-        // TAIL WORKER: the block's last warps serve the queue from the start, every other warp joins them when its
-        // own balls are done, and a worker runs ONE ball in lane 0.  Workers never wait for other blocks (they leave
-        // when their own block's balls are done and the queue is empty), so nothing here can deadlock on residency;
-        // what is still queued when the kernel ends is finished by rollout_fwd_drain_kernel.
-        const DeferQueue dq = p.defer;
-        bool own = tid < (int)blockDim.x - tail_threads;  // first pass of a normal warp: its own balls
-        const bool live = active;
-        for (;;) {
-            if (!own) {
-                int claimed = -1;
-                if ((tid & 31) == 0) {
-                    for (;;) {
-                        const unsigned alloc = *reinterpret_cast<volatile unsigned int*>(dq.alloc);
-                        const unsigned head = *reinterpret_cast<volatile unsigned int*>(dq.head);
-                        if (head < alloc) {
-                            if (atomicCAS(dq.head, head, head + 1u) == head) { claimed = (int)head; break; }
-                            continue;
-                        }
-                        if (*reinterpret_cast<volatile int*>(&s_normal_left) <= 0) break;
-                        __nanosleep(1000);  // ~600 polling warps on one L2 line: a pick-up a microsecond late costs nothing
+    // Own balls first, then the hand-over queue.  G = 1 is one thread per ball (large batches): the step loop with
+    // nothing warp-wide and nothing recomputed (baked_run_ball); G > 1: the lane = step rounds below.
+    // A ball in sliding contact collides on every step: a ~2 us serial chain per step (its own ~600 dependent
+    // instructions plus the divergent work of the warp's other balls) that used to set the duration of the whole
+    // kernel — BASELINE configs[4]: one ball of 131,072 collides on 1,972 of 2,000 steps, and the SMs were busy 49 % of
+    // the kernel (profiles/r2_ncu_fwd_baked1_c5.txt).  Such a ball is handed to a TAIL WORKER (after p.defer.streak
+    // collided steps — G > 1: rounds whose first step collided — in a row): the block's last warps serve the queue from
+    // the start, every other warp joins them when its own balls are done, and a worker runs ONE ball.  Workers never
+    // wait for other blocks (they leave when their own block's balls are done and the queue is empty), so nothing here
+    // can deadlock on residency; what is still queued when the kernel ends is finished by rollout_fwd_drain_kernel.
+    const DeferQueue dq = p.defer;
+    bool own = tid < (int)blockDim.x - tail_threads;  // first pass of a normal warp: its own balls
+    for (;;) {
+        if (!own) {
+            int claimed = -1;
+            if ((tid & 31) == 0) {
+                for (;;) {
+                    const unsigned alloc = *reinterpret_cast<volatile unsigned int*>(dq.alloc);
+                    const unsigned head = *reinterpret_cast<volatile unsigned int*>(dq.head);
+                    if (head < alloc) {
+                        if (atomicCAS(dq.head, head, head + 1u) == head) { claimed = (int)head; break; }
+                        continue;
                     }
+                    if (*reinterpret_cast<volatile int*>(&s_normal_left) <= 0) break;
+                    __nanosleep(1000);  // ~600 polling warps on one L2 line: a pick-up a microsecond late costs nothing
                 }
-                claimed = __shfl_sync(0xffffffffu, claimed, 0);
-                if (claimed < 0) break;
-                if ((tid & 31) == 0) {
-                    while (*reinterpret_cast<volatile unsigned int*>(dq.flag + claimed) == 0u) __nanosleep(40);
-                    __threadfence();
-                }
-                __syncwarp();
-                const float4 st = __ldcg(reinterpret_cast<const float4*>(dq.entry + claimed));  // L2: written by another SM
-                const int4 m = __ldcg(reinterpret_cast<const int4*>(dq.entry + claimed) + 1);
-                const int64_t eball = ((int64_t)m.w << 32) | (uint32_t)m.x;
-                if (!STAGED && p.per_env) baked_bind_in_place(p, L, eball, sc, bk);
-                // Scene read in place (L2 / L1): the whole warp on the ball, its list entries fetched side by side
-                // (C3 forward 1.96 -> 1.64 ms).  Scene in shared memory: lane 0 alone is as fast (the shuffle
-                // minimum costs what the parallel entries save: C5 forward 4.38 vs 4.50 ms).
-                if (!STAGED) baked_run_ball_warp(p, sc, bk, c, eball, m.y, st.x, st.y, st.z, st.w);
-                else if ((tid & 31) == 0) baked_run_ball(p, sc, bk, c, eball, m.y, st.x, st.y, st.z, st.w, false);
-            } else if (live) {
-                baked_run_ball(p, sc, bk, c, ball, 0, x, y, vx, vy, dq.entry != nullptr);
             }
-            if (dq.entry == nullptr) break;  // no queue: a thread only has its own ball
+            claimed = __shfl_sync(0xffffffffu, claimed, 0);
+            if (claimed < 0) break;
+            if ((tid & 31) == 0) {
+                while (*reinterpret_cast<volatile unsigned int*>(dq.flag + claimed) == 0u) __nanosleep(40);
+                __threadfence();
+            }
             __syncwarp();
-            if (own && (tid & 31) == 0) atomicSub(&s_normal_left, 1);
-            own = false;
-        }
-        return;
-    } else {  // G > 1
+            const float4 st = __ldcg(reinterpret_cast<const float4*>(dq.entry + claimed));  // L2: written by another SM
+            const int4 m = __ldcg(reinterpret_cast<const int4*>(dq.entry + claimed) + 1);
+            const int64_t eball = ((int64_t)m.w << 32) | (uint32_t)m.x;
+            if (!STAGED && p.per_env) baked_bind_in_place(p, L, eball, sc, bk);
+            // Scene read in place (L2 / L1): the whole warp on the ball, its list entries fetched side by side
+            // (C3 forward 1.96 -> 1.64 ms).  Scene in shared memory: lane 0 alone is as fast (the shuffle
+            // minimum costs what the parallel entries save: C5 forward 4.38 vs 4.50 ms).
+            if (!STAGED) baked_run_ball_warp(p, sc, bk, c, eball, m.y, st.x, st.y, st.z, st.w);
+            else if ((tid & 31) == 0) baked_run_ball(p, sc, bk, c, eball, m.y, st.x, st.y, st.z, st.w, false);
+        } else if constexpr (G == 1) {
+            if (active) baked_run_ball(p, sc, bk, c, ball, 0, x, y, vx, vy, dq.entry != nullptr);
+        } else {
     const bool want_traj_g = p.traj_x != nullptr || p.traj_v != nullptr || p.traj_a != nullptr;
+    int streak_g = 0;       // rounds in a row whose FIRST step collided (contact: one step per round)
+    bool deferred = false;  // the ball was handed over: a tail worker writes its final state
 
     while (__any_sync(0xffffffffu, t < n)) {
         // ---- (1) free flight: lane k keeps step t + k ---------------------------------------------------
@@ -476,15 +470,28 @@ __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams
         }
         if (Tq > 0) { x = nx; y = ny; vx = nvx; vy = nvy; }
         t += n_commit;
+        if (dq.entry != nullptr && Tq > 0) {  // contact hand-over, as in the one-thread-per-ball loop
+            streak_g = (ev_hit && f == 0) ? streak_g + 1 : 0;
+            if (streak_g >= dq.streak && n - t >= kDeferMinSteps) {
+                if (active && lane == 0) defer_push(dq, ball, t, x, y, vx, vy);
+                deferred = true;
+                t = n;
+            }
+        }
         // colliding step after step (resting / sliding contact): speculation is wasted, one step per round
         // until the ball leaves the wall
         if (G > 1) T = (ev_hit && f == 0) ? 1 : min(2 * T, G);
     }
-    if (active && lane == 0) {
+    if (active && lane == 0 && !deferred) {
         p.xT[ball] = make_float2(x, y);
         p.vT[ball] = make_float2(vx, vy);
     }
-    }  // G > 1
+        }
+        if (dq.entry == nullptr) break;  // no queue: a thread only has its own ball
+        __syncwarp();
+        if (own && (tid & 31) == 0) atomicSub(&s_normal_left, 1);
+        own = false;
+    }
 }
 
 // What the tail workers left in the hand-over queue (balls pushed when every worker was busy or had gone): one warp

@@ -214,10 +214,11 @@ int baked_lanes(const doper_rollout_desc* d) {
     return 1;
 }
 
-// Hand-over of balls in sliding contact to tail-worker warps: the one-thread-per-ball baked kernel (its duration is
-// otherwise the serial chain of the one ball that collides on every step).  flags bit 25 switches it off.
+// Hand-over of balls in sliding contact to tail-worker warps: the baked kernels (not the pipelined one); a launch
+// otherwise lasts as long as the slowest warp's share of the chain of a ball that collides on every step.  flags
+// bit 25 switches it off.
 bool use_defer(const doper_rollout_desc* d) {
-    return use_baked(d) && !use_pipe(d) && baked_lanes(d) == 1 && !(d->flags & (1 << 25));
+    return use_baked(d) && !use_pipe(d) && !(d->flags & (1 << 25));
 }
 
 bool use_tpc(const doper_rollout_desc* d) {
@@ -414,7 +415,7 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
         const int max_threads = staged ? MAXT_STAGED : MAXT;
         // tail-worker warps (hand-over of balls in sliding contact, G = 1 only): the block's last warps
         FwdParams q = p;
-        const int tail = (G == 1 && p.defer.entry) ? (max_threads >= 1024 ? 4 : 1) : 0;
+        const int tail = p.defer.entry ? (max_threads >= 1024 ? 4 : 1) : 0;
         q.defer.tail_warps = tail;
         q.defer.streak = kDeferStreak;
         if (const char* e = getenv("DOPER_DEFER_STREAK")) { const int v = atoi(e); if (v >= 1) q.defer.streak = v; }  // tuning
@@ -426,7 +427,7 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
         const unsigned grid = (unsigned)((p.B + bpb - 1) / bpb);
         kernel<<<grid, threads + 32 * tail, smem, st>>>(q);
         if (launch_status() != DOPER_OK) return (int)DOPER_ERR_LAUNCH;
-        if (tail > 0) {  // whatever the workers left in the queue (usually nothing)
+        if (tail > 0) {  // (= a hand-over queue exists) whatever the workers left in it: usually nothing
             rollout_fwd_drain_kernel<<<(unsigned)sm_count(), 128, 0, st>>>(q);
             return launch_status();
         }

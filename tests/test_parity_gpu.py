@@ -804,11 +804,12 @@ def test_baked_bouncy_regime_and_gradients(sim, cref, n_balls):
 
 
 @pytest.mark.parametrize("per_env", [False, True])
-@pytest.mark.parametrize("n_balls", [333, 4096])
-def test_contact_handover_is_bitexact(sim, cref, n_balls, per_env):
-    """One thread per ball: a ball that collides step after step is handed to a tail-worker warp (or to the drain
-    kernel).  Same hit flags, collision indices, final states and (sequential-backward) gradients as the oracle and
-    as the same kernel with the hand-over switched off; and the hand-over must actually happen here."""
+@pytest.mark.parametrize("n_balls,lanes", [(333, 1), (4096, 1), (333, 4), (1000, 8), (333, 16)])
+def test_contact_handover_is_bitexact(sim, cref, n_balls, per_env, lanes):
+    """Baked kernels (one thread per ball and lane = step): a ball that collides step after step is handed to a
+    tail-worker warp (or to the drain kernel).  Same hit flags, collision indices, final states and
+    (sequential-backward) gradients as the oracle and as the same kernel with the hand-over switched off; and the
+    hand-over must actually happen here."""
     ball_sim, geo = sim
     w = syn.make_workload("c2", n_balls=n_balls)
     consts = dict(w["constants"]); consts["attractor_strength"] = 2000.0
@@ -818,8 +819,8 @@ def test_contact_handover_is_bitexact(sim, cref, n_balls, per_env):
     segs = w["segments"]
     ref = cref.value_and_grad(n, dt, c, w["attractor"], w["target"], segs, w["x0"], w["v0"])
     scene = np.broadcast_to(segs, (n_balls,) + segs.shape).copy() if per_env else segs
-    on = _opts(ball_sim, pipelined=False, baked_lanes=1)
-    off = _opts(ball_sim, pipelined=False, baked_lanes=1, contact_handover=False)
+    on = _opts(ball_sim, pipelined=False, baked_lanes=lanes)
+    off = _opts(ball_sim, pipelined=False, baked_lanes=lanes, contact_handover=False)
     got = ball_sim.rollout_history(n / 1000, n, scene, w["x0"], w["v0"], w["attractor"], consts, on)
     base = ball_sim.rollout_history(n / 1000, n, scene, w["x0"], w["v0"], w["attractor"], consts, off)
     assert got["handed_over"] > 0 and base["handed_over"] == 0
