@@ -204,10 +204,10 @@ typedef struct {
                                bit 24: doper_value_and_grad keeps forward, loss and backward as separate launches
                                       (default up to 1,024 balls on the pipelined forward: ONE launch, each block
                                       pulls the gradient of its own balls back as soon as they have finished);
-                               bit 25: one-thread-per-ball forward (large batches): keep a ball in sliding contact
+                               bit 25: baked forward kernels (not the pipelined one): keep a ball in sliding contact
                                       in its warp (default: after 8 collided steps in a row it is handed to a
-                                      tail-worker warp that runs it alone — its serial chain otherwise sets the
-                                      duration of the whole launch);
+                                      tail-worker warp that runs it alone — its serial chain, lengthened by its
+                                      warp mates' divergent work, otherwise sets the duration of the whole launch);
                                bit 23: with lanes_per_ball = 8, 16 or 32: the pipelined kernel with that window
                                       length (speculated steps per producer / consumer hand-over);
                                bit 19: no collision records (the backward replays every collided
