@@ -383,109 +383,109 @@ __global__ void __launch_bounds__(MAXT) rollout_fwd_baked_kernel(const FwdParams
         } else if constexpr (G == 1) {
             if (active) baked_run_ball(p, sc, bk, c, ball, 0, x, y, vx, vy, dq.entry != nullptr);
         } else {
-    const bool want_traj_g = p.traj_x != nullptr || p.traj_v != nullptr || p.traj_a != nullptr;
-    int streak_g = 0;       // rounds in a row whose FIRST step collided (contact: one step per round)
-    bool deferred = false;  // the ball was handed over: a tail worker writes its final state
+            const bool want_traj_g = p.traj_x != nullptr || p.traj_v != nullptr || p.traj_a != nullptr;
+            int streak_g = 0;       // rounds in a row whose FIRST step collided (contact: one step per round)
+            bool deferred = false;  // the ball was handed over: a tail worker writes its final state
 
-    while (__any_sync(0xffffffffu, t < n)) {
-        // ---- (1) free flight: lane k keeps step t + k ---------------------------------------------------
-        const int Tq = t < n ? min(T, n - t) : 0;
-        State my; my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
-        const int last = min(lane, Tq - 1);
-        {
-            float nmin = __int_as_float(0x7f800000), nmax = 0.0f;
-            for (int k = 0; k <= last; ++k) free_step_acc(my.x, my.y, my.vx, my.vy, c, my, nmin, nmax);
-            const bool ok = div_range_ok(nmin, nmax, c);
-            if (__any_sync(0xffffffffu, !ok)) {  // a numerator left the range of the fast division: redo exactly
-                my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
-                for (int k = 0; k <= last; ++k) free_step(my.x, my.y, my.vx, my.vy, c, my);
-            }
-        }
-        // state at the START of my step = the end state of the lane before me
-        float sx = x, sy = y, svx = vx, svy = vy;
-        if (G > 1) {
-            const float ux = __shfl_up_sync(0xffffffffu, my.x, 1, G), uy = __shfl_up_sync(0xffffffffu, my.y, 1, G);
-            const float uvx = __shfl_up_sync(0xffffffffu, my.vx, 1, G), uvy = __shfl_up_sync(0xffffffffu, my.vy, 1, G);
-            if (lane != 0) { sx = ux; sy = uy; svx = uvx; svy = uvy; }
-        }
-        // ---- (2) my step against the baked list of my point's cell -------------------------------------
-        const bool valid = lane < Tq;
-        int idx = 0;
-        bool hit = false;
-        hit = valid && baked_hit(sc, bk, my.x, my.y, c.r, idx);
-        // ---- (3) first collision of the group, commit ---------------------------------------------------
-        int f = Tq, slot_g = 0x7fffffff;
-        bool ev_hit = false;
-        State out = my;
-        float nx = my.x, ny = my.y, nvx = my.vx, nvy = my.vy;  // G == 1: the state after my only step
-        if (G > 1) {
-            const unsigned evb = (__ballot_sync(0xffffffffu, hit) >> gbase) & kLow;
-            f = evb ? (__ffs(evb) - 1) : Tq;  // lanes < f: free flight, final
-            ev_hit = f < Tq;
-            const int src = f > 0 ? f - 1 : 0;
-            nx = __shfl_sync(0xffffffffu, my.x, src, G); ny = __shfl_sync(0xffffffffu, my.y, src, G);
-            nvx = __shfl_sync(0xffffffffu, my.vx, src, G); nvy = __shfl_sync(0xffffffffu, my.vy, src, G);
-            if (f == 0) { nx = x; ny = y; nvx = vx; nvy = vy; }
-            if (ev_hit && lane == f) slot_g = record_reserve(p.sink);  // the atomic's round trip overlaps the resolve
-            if (__any_sync(0xffffffffu, ev_hit)) {  // resolve the collision of step t + f (all lanes of the group, redundantly)
-                const int s = ev_hit ? f : 0;
-                const float bx = __shfl_sync(0xffffffffu, sx, s, G), by = __shfl_sync(0xffffffffu, sy, s, G);
-                const float bvx = __shfl_sync(0xffffffffu, svx, s, G), bvy = __shfl_sync(0xffffffffu, svy, s, G);
-                State b1;
-                b1.x = __shfl_sync(0xffffffffu, my.x, s, G); b1.y = __shfl_sync(0xffffffffu, my.y, s, G);
-                b1.vx = __shfl_sync(0xffffffffu, my.vx, s, G); b1.vy = __shfl_sync(0xffffffffu, my.vy, s, G);
-                b1.ax = __shfl_sync(0xffffffffu, my.ax, s, G); b1.ay = __shfl_sync(0xffffffffu, my.ay, s, G);
-                const int hidx = __shfl_sync(0xffffffffu, idx, s, G);
-                if (ev_hit) {
-                    const State r = resolve(bx, by, bvx, bvy, b1, sc.q[hidx], c);
-                    if (lane == f) out = r;
-                    nx = r.x; ny = r.y; nvx = r.vx; nvy = r.vy;
+            while (__any_sync(0xffffffffu, t < n)) {
+                // ---- (1) free flight: lane k keeps step t + k ---------------------------------------------------
+                const int Tq = t < n ? min(T, n - t) : 0;
+                State my; my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
+                const int last = min(lane, Tq - 1);
+                {
+                    float nmin = __int_as_float(0x7f800000), nmax = 0.0f;
+                    for (int k = 0; k <= last; ++k) free_step_acc(my.x, my.y, my.vx, my.vy, c, my, nmin, nmax);
+                    const bool ok = div_range_ok(nmin, nmax, c);
+                    if (__any_sync(0xffffffffu, !ok)) {  // a numerator left the range of the fast division: redo exactly
+                        my.x = x; my.y = y; my.vx = vx; my.vy = vy; my.ax = 0.f; my.ay = 0.f;
+                        for (int k = 0; k <= last; ++k) free_step(my.x, my.y, my.vx, my.vy, c, my);
+                    }
                 }
+                // state at the START of my step = the end state of the lane before me
+                float sx = x, sy = y, svx = vx, svy = vy;
+                if (G > 1) {
+                    const float ux = __shfl_up_sync(0xffffffffu, my.x, 1, G), uy = __shfl_up_sync(0xffffffffu, my.y, 1, G);
+                    const float uvx = __shfl_up_sync(0xffffffffu, my.vx, 1, G), uvy = __shfl_up_sync(0xffffffffu, my.vy, 1, G);
+                    if (lane != 0) { sx = ux; sy = uy; svx = uvx; svy = uvy; }
+                }
+                // ---- (2) my step against the baked list of my point's cell -------------------------------------
+                const bool valid = lane < Tq;
+                int idx = 0;
+                bool hit = false;
+                hit = valid && baked_hit(sc, bk, my.x, my.y, c.r, idx);
+                // ---- (3) first collision of the group, commit ---------------------------------------------------
+                int f = Tq, slot_g = 0x7fffffff;
+                bool ev_hit = false;
+                State out = my;
+                float nx = my.x, ny = my.y, nvx = my.vx, nvy = my.vy;  // G == 1: the state after my only step
+                if (G > 1) {
+                    const unsigned evb = (__ballot_sync(0xffffffffu, hit) >> gbase) & kLow;
+                    f = evb ? (__ffs(evb) - 1) : Tq;  // lanes < f: free flight, final
+                    ev_hit = f < Tq;
+                    const int src = f > 0 ? f - 1 : 0;
+                    nx = __shfl_sync(0xffffffffu, my.x, src, G); ny = __shfl_sync(0xffffffffu, my.y, src, G);
+                    nvx = __shfl_sync(0xffffffffu, my.vx, src, G); nvy = __shfl_sync(0xffffffffu, my.vy, src, G);
+                    if (f == 0) { nx = x; ny = y; nvx = vx; nvy = vy; }
+                    if (ev_hit && lane == f) slot_g = record_reserve(p.sink);  // the atomic's round trip overlaps the resolve
+                    if (__any_sync(0xffffffffu, ev_hit)) {  // resolve the collision of step t + f (all lanes of the group, redundantly)
+                        const int s = ev_hit ? f : 0;
+                        const float bx = __shfl_sync(0xffffffffu, sx, s, G), by = __shfl_sync(0xffffffffu, sy, s, G);
+                        const float bvx = __shfl_sync(0xffffffffu, svx, s, G), bvy = __shfl_sync(0xffffffffu, svy, s, G);
+                        State b1;
+                        b1.x = __shfl_sync(0xffffffffu, my.x, s, G); b1.y = __shfl_sync(0xffffffffu, my.y, s, G);
+                        b1.vx = __shfl_sync(0xffffffffu, my.vx, s, G); b1.vy = __shfl_sync(0xffffffffu, my.vy, s, G);
+                        b1.ax = __shfl_sync(0xffffffffu, my.ax, s, G); b1.ay = __shfl_sync(0xffffffffu, my.ay, s, G);
+                        const int hidx = __shfl_sync(0xffffffffu, idx, s, G);
+                        if (ev_hit) {
+                            const State r = resolve(bx, by, bvx, bvy, b1, sc.q[hidx], c);
+                            if (lane == f) out = r;
+                            nx = r.x; ny = r.y; nvx = r.vx; nvy = r.vy;
+                        }
+                    }
+                } else {
+                    ev_hit = hit;
+                    f = hit ? 0 : Tq;
+                    if (hit) {
+                        out = resolve(x, y, vx, vy, my, sc.q[idx], c);
+                        nx = out.x; ny = out.y; nvx = out.vx; nvy = out.vy;
+                    }
+                }
+                const int n_commit = f + (ev_hit ? 1 : 0);
+                if (active && lane < n_commit) {
+                    const int ts = t + lane;
+                    const bool h = ev_hit && lane == f;
+                    if (G == 1 && h) slot_g = record_reserve(p.sink);
+                    const int payload = h ? record_commit(p.sink, slot_g, ball, ts, sx, sy, svx, svy, idx) : 0;
+                    if (hl) hl[(int64_t)ts * p.hl_st] = pack_log(payload, h, clip_bits(svx, svy));
+                    if (p.ckpt) {  // K is usually a power of two: shift and mask instead of two integer divisions
+                        const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
+                        if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
+                    }
+                    if (want_traj_g) {
+                        const size_t o = (size_t)ts * p.B + ball;
+                        if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
+                        if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
+                        if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
+                    }
+                }
+                if (Tq > 0) { x = nx; y = ny; vx = nvx; vy = nvy; }
+                t += n_commit;
+                if (dq.entry != nullptr && Tq > 0) {  // contact hand-over, as in the one-thread-per-ball loop
+                    streak_g = (ev_hit && f == 0) ? streak_g + 1 : 0;
+                    if (streak_g >= dq.streak && n - t >= kDeferMinSteps) {
+                        if (active && lane == 0) defer_push(dq, ball, t, x, y, vx, vy);
+                        deferred = true;
+                        t = n;
+                    }
+                }
+                // colliding step after step (resting / sliding contact): speculation is wasted, one step per round
+                // until the ball leaves the wall
+                if (G > 1) T = (ev_hit && f == 0) ? 1 : min(2 * T, G);
             }
-        } else {
-            ev_hit = hit;
-            f = hit ? 0 : Tq;
-            if (hit) {
-                out = resolve(x, y, vx, vy, my, sc.q[idx], c);
-                nx = out.x; ny = out.y; nvx = out.vx; nvy = out.vy;
+            if (active && lane == 0 && !deferred) {
+                p.xT[ball] = make_float2(x, y);
+                p.vT[ball] = make_float2(vx, vy);
             }
-        }
-        const int n_commit = f + (ev_hit ? 1 : 0);
-        if (active && lane < n_commit) {
-            const int ts = t + lane;
-            const bool h = ev_hit && lane == f;
-            if (G == 1 && h) slot_g = record_reserve(p.sink);
-            const int payload = h ? record_commit(p.sink, slot_g, ball, ts, sx, sy, svx, svy, idx) : 0;
-            if (hl) hl[(int64_t)ts * p.hl_st] = pack_log(payload, h, clip_bits(svx, svy));
-            if (p.ckpt) {  // K is usually a power of two: shift and mask instead of two integer divisions
-                const bool at = kshift >= 0 ? (ts & (K - 1)) == 0 : (ts % K) == 0;
-                if (at) p.ckpt[(size_t)(kshift >= 0 ? ts >> kshift : ts / K) * p.B + ball] = make_float4(sx, sy, svx, svy);
-            }
-            if (want_traj_g) {
-                const size_t o = (size_t)ts * p.B + ball;
-                if (p.traj_x) p.traj_x[o] = make_float2(out.x, out.y);
-                if (p.traj_v) p.traj_v[o] = make_float2(out.vx, out.vy);
-                if (p.traj_a) p.traj_a[o] = make_float2(out.ax, out.ay);
-            }
-        }
-        if (Tq > 0) { x = nx; y = ny; vx = nvx; vy = nvy; }
-        t += n_commit;
-        if (dq.entry != nullptr && Tq > 0) {  // contact hand-over, as in the one-thread-per-ball loop
-            streak_g = (ev_hit && f == 0) ? streak_g + 1 : 0;
-            if (streak_g >= dq.streak && n - t >= kDeferMinSteps) {
-                if (active && lane == 0) defer_push(dq, ball, t, x, y, vx, vy);
-                deferred = true;
-                t = n;
-            }
-        }
-        // colliding step after step (resting / sliding contact): speculation is wasted, one step per round
-        // until the ball leaves the wall
-        if (G > 1) T = (ev_hit && f == 0) ? 1 : min(2 * T, G);
-    }
-    if (active && lane == 0 && !deferred) {
-        p.xT[ball] = make_float2(x, y);
-        p.vT[ball] = make_float2(vx, vy);
-    }
         }
         if (dq.entry == nullptr) break;  // no queue: a thread only has its own ball
         __syncwarp();
