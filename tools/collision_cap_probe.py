@@ -16,16 +16,12 @@ from doper_b200._abi import lib
 from doper_b200._device import ptr
 from doper_b200.sim import ball_sim
 from doper_b200.sim.jax_geometry import JaxScene
-from oracle import ball_sim_np as onp  # (a probe tool, not the product path)
-from oracle.cref import CRef
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 balls = int(sys.argv[2]) if len(sys.argv) > 2 else None
 w = syn.make_workload(name, n_balls=balls)
 B, n = w["x0"].shape[0], w["n_steps"]
-c = onp.make_constants(w["constants"])
-ref = CRef("portable").rollout_fwd(n, np.float32(w["sim_time"] / n), c, w["attractor"], w["segments"], w["x0"], w["v0"])
-hits = ref["hit"].sum(0)
+hits = ball_sim.rollout_history(w["sim_time"], n, w["segments"], w["x0"], w["v0"], w["attractor"], w["constants"])["hit"].sum(0)
 quiet = int(np.nonzero(hits == 0)[0][0])
 dev = torch.device("cuda")
 scene = JaxScene(w["segments"])
