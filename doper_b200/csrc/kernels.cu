@@ -379,7 +379,7 @@ int launch_fwd_tpc(cudaStream_t st, const FwdParams& p, size_t scene_smem) {
     return run(std::integral_constant<int, 128>{});
 }
 
-// Block size of the one-wave kernels whose warps are independent latency chains (baked forward, G <= 4): the kernel
+// Block size of the one-wave kernels whose warps are independent latency chains (the baked forward kernels): the kernel
 // lasts as long as the SM with the most resident warps, so the batch's warps are dealt out evenly — w = ceil(warps /
 // (SMs x waves)) warps per block, one block per SM and wave — instead of fixed 128-thread blocks (131,072 balls = 1,024
 // blocks against 6 resident per SM by shared memory: a second wave of 136 blocks; 65,536 threads = 512 blocks: 4 on
@@ -413,7 +413,7 @@ int launch_fwd_baked(cudaStream_t st, const FwdParams& p, bool staged) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return (int)DOPER_ERR_SMEM_LIMIT;
         const int max_threads = staged ? MAXT_STAGED : MAXT;
-        // tail-worker warps (hand-over of balls in sliding contact, G = 1 only): the block's last warps
+        // tail-worker warps (hand-over of balls in sliding contact, fwd_baked.cuh): the block's last warps
         FwdParams q = p;
         const int tail = p.defer.entry ? (max_threads >= 1024 ? 4 : 1) : 0;
         q.defer.tail_warps = tail;
