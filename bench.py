@@ -151,6 +151,21 @@ class ClockSampler(threading.Thread):
                 **({"error": self.err} if self.err else {})}
 
 
+def launches_per_step(lib, dref, separate):
+    """Kernels of this repository per timed step: doper_value_and_grad launches the forward (+ the hand-over drain
+    kernel of the baked plans), then either nothing more (fused), or loss + Jacobian pass as ONE kernel and the fold
+    (default backward), or loss and the sequential backward; --separate-launches: forward, loss, backward kernels."""
+    fwd = 1 + (1 if lib.doper_rollout_plan_name(dref, 3).decode() else 0)
+    if separate:
+        return fwd + 1 + len(lib.doper_rollout_plan_name(dref, 1).decode().split("+"))
+    name = lib.doper_rollout_plan_name(dref, 2).decode()
+    if "fused" in name:
+        return 1
+    if "loss_jacobian_kernel" in name:
+        return fwd + len(name.split("+"))
+    return fwd + 1 + len(name.split("+"))
+
+
 def physical_gpu_index(local_index):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -673,10 +688,7 @@ def ours(args):
                     "d2h_bytes_per_step": (4 + 6 * B) * 4, "ms_per_step": round(float(e2e_ms.item()), 5),
                     "api": "doper_b200.sim.ball_sim.vmapped_grad_and_value(host numpy arrays)"},
             # kernels of this repository per step: forward, loss, backward (1 or 2), exchange (N > 1, peer kernel)
-            "gpu_launches": ((1 if (not args.separate_launches and "fused" in lib.doper_rollout_plan_name(dref, 2).decode())
-                              else 3 + lib.doper_rollout_plan_name(dref, 1).decode().count("+")
-                              + (1 if lib.doper_rollout_plan_name(dref, 3).decode() else 0))  # + the hand-over drain kernel
-                             + (1 if peer is not None else 0)) * K,
+            "gpu_launches": (launches_per_step(lib, dref, args.separate_launches) + (1 if peer is not None else 0)) * K,
             "wall_ms_timed_region": round(wall_ms, 3),
             "roofline": roof,
         }

@@ -259,11 +259,11 @@ __device__ __noinline__ void hit_jacobian_d(const float4 st, const float4 q, con
     }
 }
 
-// pass 1: four threads per collision record, one column of the transposed Jacobian each (grid-stride)
-__global__ void __launch_bounds__(128) rollout_bwd_jacobian_kernel(const BwdParams p) {
+// pass 1: four threads per collision record, one column of the transposed Jacobian each; thread `first` of `total`
+__device__ __forceinline__ void bwd_jacobian_part(const BwdParams& p, const int64_t first, const int64_t total) {
     const int n = min(*p.rec_count, p.rec_cap);
     const ConstsD cd = make_consts_d(p.c);
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < 4 * (int64_t)n; w += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t w = first; w < 4 * (int64_t)n; w += total) {
         const int i = (int)(w >> 2), col = (int)(w & 3);
         const float4* r = reinterpret_cast<const float4*>(p.rec + i);
         const float4 st = r[0];
@@ -278,6 +278,10 @@ __global__ void __launch_bounds__(128) rollout_bwd_jacobian_kernel(const BwdPara
 #pragma unroll
         for (int k = 0; k < 4; ++k) out[4 * k] = J[4 * k + col];
     }
+}
+
+__global__ void __launch_bounds__(128) rollout_bwd_jacobian_kernel(const BwdParams p) {
+    bwd_jacobian_part(p, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -39,6 +39,24 @@
 #include "peer.cuh"
 #include "controller.cuh"
 
+namespace doper {
+// doper_value_and_grad, separate-launch plan: the L1 loss (blocks [0, loss_blocks): l1_loss_kernel's blocks) and pass 1
+// of the binary64 backward (the other blocks: rollout_bwd_jacobian_kernel's threads) are independent of each other —
+// both only read what the forward wrote — so they share ONE launch: a launch gap and the shorter of the two kernels
+// come off BASELINE configs[1]'s critical path.  Same device functions, same bits.
+__global__ void __launch_bounds__(kLossThreads) loss_jacobian_kernel(const int loss_blocks, int64_t B, const float2* __restrict__ xT,
+                                                                    float tx, float ty, float* __restrict__ loss_pb,
+                                                                    float* __restrict__ loss_sum, float2* __restrict__ xT_bar,
+                                                                    const BwdParams p) {
+    if ((int)blockIdx.x < loss_blocks) {
+        l1_loss_block(blockIdx.x, B, xT, tx, ty, loss_pb, loss_sum, xT_bar);
+    } else {
+        bwd_jacobian_part(p, (int64_t)(blockIdx.x - loss_blocks) * blockDim.x + threadIdx.x,
+                          (int64_t)(gridDim.x - loss_blocks) * blockDim.x);
+    }
+}
+}  // namespace doper
+
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
@@ -726,7 +744,7 @@ const char* doper_rollout_plan_name(const doper_rollout_desc* d, int32_t backwar
         return use_defer(d) ? "rollout_fwd_drain_kernel" : "";
     if (backward == 2)  // what doper_value_and_grad launches for the backward
         return (fused_ok(d) && !(d->flags & (1 << 24))) ? "fused into the forward launch (rollout_fwd_pipe_kernel<U, true>)"
-                                                        : ((d->flags & 2) ? "rollout_bwd_kernel" : "rollout_bwd_jacobian_kernel+rollout_bwd_fold_kernel");
+                                                        : ((d->flags & 2) ? "rollout_bwd_kernel" : "loss_jacobian_kernel+rollout_bwd_fold_kernel");
     if (backward) return (d->flags & 2) ? "rollout_bwd_kernel" : "rollout_bwd_jacobian_kernel+rollout_bwd_fold_kernel";
     if (use_pipe(d)) {
         const int u = pipe_window(d);
@@ -920,9 +938,30 @@ size_t doper_rollout_bwd_scratch_bytes(const doper_rollout_desc* d) {
     return (size_t)record_capacity(d) * 16 * sizeof(double) + 256;
 }
 
+}  // extern "C"
+
+namespace {
+// loss: when non-null (doper_value_and_grad), the L1 loss rides in the launch of the backward's pass 1
+struct LossArgs { const float* xT; const float* target; float* loss_per_ball; float* loss_sum; float* xT_bar_out; };
+int rollout_bwd_impl(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                     const void* ws, void* bwd_scratch, const float* xT_bar, const float* vT_bar,
+                     float* x0_bar, float* v0_bar, const LossArgs* loss);
+}  // namespace
+
+extern "C" {
+
 int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
                       const void* ws, void* bwd_scratch, const float* xT_bar, const float* vT_bar,
                       float* x0_bar, float* v0_bar) {
+    return rollout_bwd_impl(stream, d, scene_ws, ws, bwd_scratch, xT_bar, vT_bar, x0_bar, v0_bar, nullptr);
+}
+
+}  // extern "C"
+
+namespace {
+int rollout_bwd_impl(doper_stream_t stream, const doper_rollout_desc* d, const void* scene_ws,
+                     const void* ws, void* bwd_scratch, const float* xT_bar, const float* vT_bar,
+                     float* x0_bar, float* v0_bar, const LossArgs* loss) {
     int rc = validate_desc(d);
     if (rc) return rc;
     if (!scene_ws || !ws || !xT_bar || !v0_bar) return DOPER_ERR_NULL_PTR;
@@ -953,12 +992,25 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     p.v0_bar = reinterpret_cast<float2*>(v0_bar);
     cudaStream_t st = (cudaStream_t)stream;
     if (sequential) {  // fp32 in the oracle's operation order (bit-exact), one thread per ball
+        if (loss != nullptr) {
+            rc = doper_l1_loss(stream, d->B, loss->xT, loss->target, loss->loss_per_ball, loss->loss_sum, loss->xT_bar_out);
+            if (rc) return rc;
+        }
         const unsigned grid = (unsigned)((d->B + kBwdThreads - 1) / kBwdThreads);
         rollout_bwd_kernel<<<grid, kBwdThreads, 0, st>>>(p);
         return launch_status();
     }
     // binary64 plan: Jacobians of the collided steps, then chunk products + fold
-    if (w.cap > 0) {
+    if (loss != nullptr) {  // ... with the L1 loss in the same launch (loss_jacobian_kernel)
+        const int loss_blocks = 1 + (int)((d->B + kLossThreads - 1) / kLossThreads);
+        int64_t jac_blocks = w.cap > 0 ? (4 * w.cap + kLossThreads - 1) / kLossThreads : 0;
+        const int64_t max_blocks = (int64_t)sm_count() * 4;
+        if (jac_blocks > max_blocks) jac_blocks = max_blocks;
+        loss_jacobian_kernel<<<(unsigned)(loss_blocks + jac_blocks), kLossThreads, 0, st>>>(
+            loss_blocks, d->B, reinterpret_cast<const float2*>(loss->xT), loss->target[0], loss->target[1], loss->loss_per_ball,
+            loss->loss_sum, reinterpret_cast<float2*>(loss->xT_bar_out), p);
+        if (launch_status() != DOPER_OK) return DOPER_ERR_LAUNCH;
+    } else if (w.cap > 0) {
         int64_t blocks = (w.cap + 127) / 128;
         const int64_t max_blocks = (int64_t)sm_count() * 8;
         if (blocks > max_blocks) blocks = max_blocks;
@@ -975,6 +1027,9 @@ int doper_rollout_bwd(doper_stream_t stream, const doper_rollout_desc* d, const 
     rollout_bwd_fold_kernel<<<grid, 32 * n_chunks, smem, st>>>(p, n_chunks, chunk_len);
     return launch_status();
 }
+}  // namespace
+
+extern "C" {
 
 int doper_l1_loss(doper_stream_t stream, int64_t B, const float* xT, const float target[2],
                   float* loss_per_ball, float* loss_sum, float* xT_bar) {
@@ -1005,9 +1060,10 @@ int doper_value_and_grad(doper_stream_t stream, const doper_rollout_desc* d, con
     }
     int rc = doper_rollout_fwd(stream, d, scene_ws, x0, v0, xT, vT, nullptr, nullptr, nullptr, ws);
     if (rc) return rc;
-    rc = doper_l1_loss(stream, d->B, xT, target, loss_per_ball, loss_sum, scratch);
-    if (rc) return rc;
-    return doper_rollout_bwd(stream, d, scene_ws, ws, bwd_scratch, scratch, nullptr, x0_bar, v0_bar);
+    // the loss (per-ball terms, total, seeds sign(x_T - target) -> scratch) shares the launch of the backward's pass 1
+    if (!xT || !loss_sum || !aligned(xT, 8) || !aligned(scratch, 8)) return !xT || !loss_sum ? DOPER_ERR_NULL_PTR : DOPER_ERR_MISALIGNED;
+    const LossArgs la{xT, target, loss_per_ball, loss_sum, scratch};
+    return rollout_bwd_impl(stream, d, scene_ws, ws, bwd_scratch, scratch, nullptr, x0_bar, v0_bar, &la);
 }
 
 size_t doper_peer_buffer_bytes(int32_t n) { return n > 0 ? peer_buffer_bytes(n) : 0; }

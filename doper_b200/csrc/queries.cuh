@@ -10,12 +10,11 @@ namespace doper {
 constexpr int kLossThreads = 256;
 
 // block 0: deterministic total (fixed strided partials + fixed tree); blocks >= 1: per-ball outputs
-__global__ void __launch_bounds__(kLossThreads) l1_loss_kernel(int64_t B, const float2* __restrict__ xT,
-                                                              float tx, float ty,
-                                                              float* __restrict__ loss_pb,
-                                                              float* __restrict__ loss_sum,
-                                                              float2* __restrict__ xT_bar) {
-    if (blockIdx.x == 0) {
+// (a device function of `block`: loss_jacobian_kernel, bwd.cuh, runs the same blocks next to the backward's pass 1)
+__device__ __forceinline__ void l1_loss_block(const unsigned block, int64_t B, const float2* __restrict__ xT, float tx, float ty,
+                                              float* __restrict__ loss_pb, float* __restrict__ loss_sum,
+                                              float2* __restrict__ xT_bar) {
+    if (block == 0) {
         __shared__ float part[kLossThreads];
         float acc = 0.0f;
         for (int64_t b = threadIdx.x; b < B; b += kLossThreads) {
@@ -31,12 +30,20 @@ __global__ void __launch_bounds__(kLossThreads) l1_loss_kernel(int64_t B, const 
         if (threadIdx.x == 0) *loss_sum = part[0];  // ball_sim.py:324
         return;
     }
-    const int64_t b = (int64_t)(blockIdx.x - 1) * kLossThreads + threadIdx.x;
+    const int64_t b = (int64_t)(block - 1) * kLossThreads + threadIdx.x;
     if (b >= B) return;
     float2 p = xT[b];
     float ex = p.x - tx, ey = p.y - ty;
     if (loss_pb) loss_pb[b] = fabsf(ex) + fabsf(ey);
     if (xT_bar) xT_bar[b] = make_float2(sgnf(ex), sgnf(ey));  // d|e|/de, 0 at e == 0 (and NaN -> 0)
+}
+
+__global__ void __launch_bounds__(kLossThreads) l1_loss_kernel(int64_t B, const float2* __restrict__ xT,
+                                                              float tx, float ty,
+                                                              float* __restrict__ loss_pb,
+                                                              float* __restrict__ loss_sum,
+                                                              float2* __restrict__ xT_bar) {
+    l1_loss_block(blockIdx.x, B, xT, tx, ty, loss_pb, loss_sum, xT_bar);
 }
 
 // ------------------------------------------------------------------------------------------
