@@ -17,7 +17,7 @@ for r in rows:
     a[0] += 1
     a[1] += v
 tot = sum(a[1] for a in agg.values())
-step = {k: a for k, a in agg.items() if any(t in k for t in ("rollout_", "l1_loss", "allreduce_oneshot"))}
+step = {k: a for k, a in agg.items() if any(t in k for t in ("rollout_", "l1_loss", "loss_jacobian", "allreduce_oneshot"))}
 stot = sum(a[1] for a in step.values())
 print(f"# ncu launch list — `{sys.argv[2]}`, gpu__time_duration.sum (ns), --clock-control none")
 print("# per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes\n")
