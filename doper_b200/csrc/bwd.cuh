@@ -301,22 +301,28 @@ __global__ void __launch_bounds__(128) rollout_bwd_jacobian_kernel(const BwdPara
 // from the Jacobian pass's matrix (p.jac), or computed in place when no pass ran / no record exists.
 //
 // Runs of free flight.  The transposed Jacobian of a free-flight step acts on the (position, velocity) cotangent pair
-// of each axis as one of two constant 2x2 matrices (clip bit clear / set), and the clip bit of a ball changes a few
-// times per rollout.  A prefetch group of kBwdPrefetch steps without collision whose clip bits are uniform per axis —
-// almost every group — is therefore ONE product with the precomputed kBwdPrefetch-th power of that matrix (t16:
-// free_pow_table, in shared memory) instead of kBwdPrefetch x 12 DFMA: the kernel is then bound by the log reads
-// alone.  (Binary64 throughout; the power differs from the step-by-step product by a few 1e-16 relative.)
-__device__ __forceinline__ void free_pow_table(const ConstsD& cd, double* t16) {  // [clip bit][R00 R01 R10 R11]
+// of each axis as one of two constant 2x2 matrices (clip bit of that axis clear / set) — the two axes never mix in
+// free flight, whether or not an earlier collision has coupled the columns — and a ball's clip bits change a few
+// times per rollout.  Between two collided steps a prefetch group is therefore, per axis, a few RUNS of equal clip
+// bits, and a run of L steps is the L-th power of one matrix: the powers 1, 2, 4, 8, 16 of both matrices sit in
+// shared memory (free_pow_table) and a run applies the ones in L's binary expansion (the powers of one matrix
+// commute) — one product per axis for the typical group of 16 steps instead of 16 x 12 DFMA, a handful when a clip
+// bit flips inside the group.  Only collided steps are multiplied one by one.  (Binary64 throughout; a power differs
+// from the step-by-step product by a few 1e-16 relative.)
+constexpr int kPowLevels = 5;  // powers 2^0 .. 2^4 (kBwdPrefetch <= 32 steps per group: run lengths below 32)
+constexpr int kPowTableDoubles = 2 * kPowLevels * 4;
+__device__ __forceinline__ void free_pow_table(const ConstsD& cd, double* tp) {  // [clip bit][level][R00 R01 R10 R11]
     for (int b = 0; b < 2; ++b) {
         const double av = b ? cd.a_v : 0.0;
         // one step on a pair (a, b): tx = a dt + b; a' = a + a_p tx; b' = tx + av tx
         double r00 = fma(cd.a_p, cd.dt, 1.0), r01 = cd.a_p, r10 = (1.0 + av) * cd.dt, r11 = 1.0 + av;
-        for (int sq = 1; sq < kBwdPrefetch; sq *= 2) {
+        for (int lv = 0; lv < kPowLevels; ++lv) {
+            double* o = tp + (b * kPowLevels + lv) * 4;
+            o[0] = r00; o[1] = r01; o[2] = r10; o[3] = r11;
             const double n00 = fma(r00, r00, r01 * r10), n01 = fma(r00, r01, r01 * r11);
             const double n10 = fma(r10, r00, r11 * r10), n11 = fma(r10, r01, r11 * r11);
             r00 = n00; r01 = n01; r10 = n10; r11 = n11;
         }
-        t16[4 * b + 0] = r00; t16[4 * b + 1] = r01; t16[4 * b + 2] = r10; t16[4 * b + 3] = r11;
     }
 }
 
@@ -325,10 +331,38 @@ __device__ __forceinline__ void pair_pow(double& a, double& b, const double r00,
     a = na; b = nb;
 }
 
+// Steps lo .. hi (bit positions of `mask`, no collided step among them) of ONE axis, newest first: pos / vel index the
+// cotangent pair of that axis in a column (0 / 2 for x, 1 / 3 for y); uncoupled columns off the axis stay zero and
+// are skipped.
+template <int POS, int VEL>
+__device__ __forceinline__ void axis_runs(double (&g)[4][4], const bool coupled, const unsigned mask, const int lo, const int hi,
+                                          const double* __restrict__ tp) {
+    for (int q = hi; q >= lo;) {
+        const unsigned bit = (mask >> q) & 1u;
+        const unsigned same = (bit ? mask : ~mask) << (31 - q);  // bit 31 = step q; ones = steps with the same clip bit
+        int run = __clz(~same);                                   // leading ones (32 if all)
+        run = min(run, q - lo + 1);
+        const double* tb = tp + bit * (kPowLevels * 4);
+#pragma unroll
+        for (int lv = 0; lv < kPowLevels; ++lv) {
+            if ((run >> lv) & 1) {
+                const double r00 = tb[lv * 4 + 0], r01 = tb[lv * 4 + 1], r10 = tb[lv * 4 + 2], r11 = tb[lv * 4 + 3];
+                if (coupled) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pair_pow(g[k][POS], g[k][VEL], r00, r01, r10, r11);
+                } else {  // columns POS and VEL live on this axis
+                    pair_pow(g[POS][POS], g[POS][VEL], r00, r01, r10, r11);
+                    pair_pow(g[VEL][POS], g[VEL][VEL], r00, r01, r10, r11);
+                }
+            }
+        }
+        q -= run;
+    }
+}
+
 __device__ __forceinline__ void chunk_product(const BwdParams& p, const ConstsD& cd, const int64_t ball, const int t0, const int t1,
-                                              double (&g)[4][4], const double* __restrict__ t16) {
-    static_assert((kBwdPrefetch & (kBwdPrefetch - 1)) == 0 && kBwdPrefetch <= 32, "free_pow_table squares up to kBwdPrefetch");
-    constexpr unsigned kFull = kBwdPrefetch == 32 ? 0xffffffffu : ((1u << kBwdPrefetch) - 1u);
+                                              double (&g)[4][4], const double* __restrict__ tp) {
+    static_assert(kBwdPrefetch < (1 << kPowLevels), "run lengths must fit the power table");
     const int32_t* hl = p.hitlog + (size_t)ball * p.hl_sb;
     bool coupled = false;
     for (int tb = t1; tb > t0;) {
@@ -341,52 +375,17 @@ __device__ __forceinline__ void chunk_product(const BwdParams& p, const ConstsD&
             m_cx |= ((w >> 29) & 1u) << j;
             m_cy |= ((w >> 30) & 1u) << j;
         }
-        if (tb - ta == kBwdPrefetch && m_hit == 0u && (m_cx == 0u || m_cx == kFull) && (m_cy == 0u || m_cy == kFull)) {
-            const double* rx = t16 + (m_cx ? 4 : 0);
-            const double* ry = t16 + (m_cy ? 4 : 0);
-            const double x00 = rx[0], x01 = rx[1], x10 = rx[2], x11 = rx[3];
-            const double y00 = ry[0], y01 = ry[1], y10 = ry[2], y11 = ry[3];
-            if (!coupled) {
-                pair_pow(g[0][0], g[0][2], x00, x01, x10, x11); pair_pow(g[2][0], g[2][2], x00, x01, x10, x11);
-                pair_pow(g[1][1], g[1][3], y00, y01, y10, y11); pair_pow(g[3][1], g[3][3], y00, y01, y10, y11);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    pair_pow(g[k][0], g[k][2], x00, x01, x10, x11);
-                    pair_pow(g[k][1], g[k][3], y00, y01, y10, y11);
-                }
-            }
-            tb = ta;
-            continue;
-        }
-        for (int t = tb - 1; t >= ta; --t) {
-            const int j = t - ta;
-            if (!((m_hit >> j) & 1u)) {
-                const double avx = ((m_cx >> j) & 1u) ? cd.a_v : 0.0, avy = ((m_cy >> j) & 1u) ? cd.a_v : 0.0;
-                if (!coupled) {
-#pragma unroll
-                    for (int k = 0; k < 4; k += 2) {  // columns 0, 2 live on (x, vx); columns 1, 3 on (y, vy)
-                        const double tx = fma(g[k][0], cd.dt, g[k][2]);
-                        g[k][0] = fma(cd.a_p, tx, g[k][0]);
-                        g[k][2] = fma(tx, avx, tx);
-                        const double ty = fma(g[k + 1][1], cd.dt, g[k + 1][3]);
-                        g[k + 1][1] = fma(cd.a_p, ty, g[k + 1][1]);
-                        g[k + 1][3] = fma(ty, avy, ty);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const double tx = fma(g[k][0], cd.dt, g[k][2]);
-                        g[k][0] = fma(cd.a_p, tx, g[k][0]);
-                        g[k][2] = fma(tx, avx, tx);
-                        const double ty = fma(g[k][1], cd.dt, g[k][3]);
-                        g[k][1] = fma(cd.a_p, ty, g[k][1]);
-                        g[k][3] = fma(ty, avy, ty);
-                    }
-                }
+        for (int j = tb - ta - 1; j >= 0;) {
+            if (!((m_hit >> j) & 1u)) {  // free flight down to the next collided step (or the group's first step)
+                const unsigned below = m_hit & ((1u << j) - 1u);
+                const int lo = below ? 32 - __clz(below) : 0;
+                axis_runs<0, 2>(g, coupled, m_cx, lo, j, tp);
+                axis_runs<1, 3>(g, coupled, m_cy, lo, j, tp);
+                j = lo - 1;
                 continue;
             }
-            const uint32_t h = (uint32_t)hl[(size_t)t * p.hl_st];
+            const int t = ta + j;
+            const uint32_t h = (uint32_t)hl[(size_t)t * p.hl_st];  // collided step: the payload is needed (rare reload)
             double Jl[16];
             const double* J;
             if (h & kLogNoRecord) {  // no record: replay the state from the checkpoint, Jacobian in place (slow path)
@@ -410,6 +409,7 @@ __device__ __forceinline__ void chunk_product(const BwdParams& p, const ConstsD&
                     g[k][r] = fma(J[4 * r + 0], a0, fma(J[4 * r + 1], a1, fma(J[4 * r + 2], a2, J[4 * r + 3] * a3)));
             }
             coupled = true;
+            --j;
         }
         tb = ta;
     }
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(32 * kFoldMaxChunks) rollout_bwd_fold_kernel(c
 #pragma unroll
         for (int r = 0; r < 4; ++r) g[k][r] = (k == r) ? 1.0 : 0.0;
     const int t0 = chunk * chunk_len, t1 = min(p.n_steps, t0 + chunk_len);
-    __shared__ double t16[8];
+    __shared__ double t16[kPowTableDoubles];
     if (threadIdx.x == 0) free_pow_table(cd, t16);
     __syncthreads();
     if (active && t0 < t1) chunk_product(p, cd, ball, t0, t1, g, t16);

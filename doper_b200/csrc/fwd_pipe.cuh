@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(32 * (1 + PB * U / 32), (U <= 16 && !FUSED) ? 
     const int64_t fb = first + bb;
     const int t0 = chunk * chunk_len, t1 = min(n, t0 + chunk_len);
     const bool mine = tid < 16 * NC && bb < p.pipe_balls && fb < p.B && t0 < t1;
-    __shared__ double t16[8];
+    __shared__ double t16[kPowTableDoubles];
     if (tid == 0) { jl_count = 0; free_pow_table(cd, t16); }
     named_barrier(1, GT);
     if (p.jac != nullptr && mine) {
